@@ -1,0 +1,185 @@
+/* icc_b200.h — C-ABI of the B200-native continuous-time IMU-camera calibration solver.
+ *
+ * Drop-in boundary for the ONE hot path of urbste/OpenImuCameraCalibrator: everything below
+ * OpenICC::core::ImuCameraCalibrator (include/OpenCameraCalibrator/core/imu_camera_calibrator.h:29-118)
+ * and SplineTrajectoryEstimator<6> (core/spline_trajectory_estimator.h:31-218), i.e. what the reference
+ * delegates to Ceres autodiff + sparse Cholesky + Theia camera projections.  The reference has no FFI layer;
+ * each entry point cites the C++ member it replaces.  Plain pointers and sizes only, no torch / C++ types.
+ * All arithmetic is FP64; all device work is hand-written sm_100a CUDA; there is NO CPU fallback:
+ * every compute entry point fails with ICC_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Threading: one host thread per handle; one handle per GPU; handles are independent.
+ * Ownership: caller owns every input array (copied during the call) and every output buffer.
+ */
+#ifndef ICC_B200_H_
+#define ICC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct icc_handle icc_handle;
+
+typedef enum {
+  ICC_OK = 0,
+  ICC_ERR_INVALID_ARGUMENT = 1,
+  ICC_ERR_NO_DEVICE = 2,       /* CUDA device / driver unusable: the product path never falls back to the CPU */
+  ICC_ERR_CUDA = 3,
+  ICC_ERR_STATE = 4,           /* call order violated (e.g. optimize before batch_init_spline) */
+  ICC_ERR_UNSUPPORTED = 5,     /* flag combination outside the hot CLI's reach (POINTS, IMU_INTRINSICS) */
+  ICC_ERR_NUMERIC = 6          /* factorisation broke down / non-finite cost */
+} icc_status;
+
+/* theia::CameraIntrinsicsModelType numeric values (pyTheiaSfM@69c3d37); JSON `intrinsic_type` strings are the
+ * upper-case names (src/io/read_camera_calibration.cc:59-116).  Intrinsic vectors use Theia's index order:
+ *   PINHOLE                   [f, ar, skew, cx, cy, k1, k2]
+ *   PINHOLE_RADIAL_TANGENTIAL [f, ar, skew, cx, cy, k1, k2, k3, t1, t2]
+ *   FISHEYE                   [f, ar, skew, cx, cy, k1, k2, k3, k4]
+ *   FOV                       [f, ar, cx, cy, omega]          (extension: the reference never dispatches FOV)
+ *   DIVISION_UNDISTORTION     [f, ar, cx, cy, k]
+ *   DOUBLE_SPHERE             [f, ar, skew, cx, cy, xi, alpha]
+ *   EXTENDED_UNIFIED          [f, ar, skew, cx, cy, alpha, beta] */
+typedef enum {
+  ICC_CAM_PINHOLE = 0,
+  ICC_CAM_PINHOLE_RADIAL_TANGENTIAL = 1,
+  ICC_CAM_FISHEYE = 2,
+  ICC_CAM_FOV = 3,
+  ICC_CAM_DIVISION_UNDISTORTION = 4,
+  ICC_CAM_DOUBLE_SPHERE = 5,
+  ICC_CAM_EXTENDED_UNIFIED = 6
+} icc_camera_model;
+
+/* OpenICC::core::SplineOptimFlags (core/spline_trajectory_estimator.h:17-27), same numeric values. */
+enum {
+  ICC_FLAG_POINTS = 1 << 0,
+  ICC_FLAG_T_I_C = 1 << 1,
+  ICC_FLAG_IMU_BIASES = 1 << 2,
+  ICC_FLAG_IMU_INTRINSICS = 1 << 3,
+  ICC_FLAG_GRAVITY_DIR = 1 << 4,
+  ICC_FLAG_CAM_LINE_DELAY = 1 << 5,
+  ICC_FLAG_SPLINE = 1 << 6,
+  ICC_FLAG_ACC_BIAS = 1 << 7,
+  ICC_FLAG_GYR_BIAS = 1 << 8
+};
+
+/* Arguments of ImuCameraCalibrator::BatchInitSpline (src/core/imu_camera_calibrator.cc:21-124). */
+typedef struct {
+  double T_i_c_init[7];        /* Sophus SE3 storage: quaternion x,y,z,w then translation (impl.h:519,579) */
+  double dt_so3_s, dt_r3_s;    /* SplineWeightingData::dt_so3 / dt_r3 (seconds) */
+  double std_so3, std_r3;      /* weights are 1/std (imu_camera_calibrator.cc:111,117) */
+  double time_offset_imu_to_cam_s;
+  double init_line_delay_s;    /* 0 => global shutter path (vision zero-weighted) */
+  double acc_intrinsics[6];    /* [misYZ, misZY, misZX, sX, sY, sZ]                         (impl.h:1236-1239) */
+  double gyr_intrinsics[9];    /* [misYZ, misZY, misZX, misXZ, misXY, misYX, sX, sY, sZ]    (impl.h:1241-1245) */
+  double acc_bias[3], gyr_bias[3];
+  int32_t dispatch_fov;        /* 0 = reference behaviour (FOV fails -> 1e10 residuals); 1 = enable FOV extension */
+  int32_t reserved;
+} icc_init_params;
+
+/* Solver knobs: ceres::Solver::Options as set in SplineTrajectoryEstimator::Optimize (impl.h:254-266)
+ * plus the Ceres 2.1 defaults that shape the Levenberg-Marquardt path. */
+typedef struct {
+  double function_tolerance;        /* 1e-4  (impl.h:262) */
+  double parameter_tolerance;       /* 1e-7  (impl.h:263) */
+  double gradient_tolerance;        /* 1e-10 (Ceres default) */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;   /* 1e16 */
+  double min_trust_region_radius;   /* 1e-32 */
+  double min_relative_decrease;     /* 1e-3 */
+  double min_lm_diagonal;           /* 1e-6 */
+  double max_lm_diagonal;           /* 1e32 */
+  int32_t jacobi_scaling;           /* 1 */
+  int32_t max_consecutive_invalid_steps; /* 5 */
+} icc_solver_options;
+
+typedef struct {
+  int32_t iterations;               /* LM iterations executed (successful + unsuccessful) */
+  int32_t successful_steps;
+  int32_t termination;              /* 0 = max iterations, 1 = function tol, 2 = parameter tol, 3 = gradient tol, 4 = failure */
+  int32_t num_residuals;            /* scalar residuals per evaluation */
+  int32_t num_tangent;              /* active tangent parameters */
+  int32_t jacobian_evaluations;
+  int32_t cost_evaluations;
+  int32_t gpu_launches;             /* CUDA kernels launched inside this optimize call */
+  double initial_cost, final_cost;
+  double mean_reproj_error;         /* GetMeanReprojectionError (impl.h:993-1072) — return value of Optimize */
+  double seconds_total;             /* host wall clock of the optimize call */
+  double seconds_jacobian;          /* device time in residual+Jacobian+normal-equation kernels (CUDA events) */
+  double seconds_linear_solve;      /* device time in the banded/bordered Cholesky + step kernels */
+} icc_summary;
+
+/* Optional cross-rank reduction hook for residual sharding: called on the host with the DEVICE pointer
+ * of the packed FP64 normal-equation buffer {band, border coupling, border block, gradient, cost}; must sum it in place
+ * across ranks (e.g. torch.distributed / ncclAllReduce on the handle's stream) before returning. */
+typedef void (*icc_allreduce_fn)(void* device_ptr, int64_t n_doubles, void* cuda_stream, void* user);
+
+/* ---- lifetime --------------------------------------------------------------------------------------------- */
+icc_status icc_create(icc_handle** out, int device_ordinal);
+void icc_destroy(icc_handle* h);
+const char* icc_last_error(const icc_handle* h);          /* never NULL */
+const char* icc_version(void);
+void icc_default_solver_options(icc_solver_options* o);
+icc_status icc_set_solver_options(icc_handle* h, const icc_solver_options* o);
+
+/* ---- problem data (what main() hands to ImuCameraCalibrator, continuous_time_imu_to_camera_calibration.cc:104-199) */
+/* theia::Camera intrinsics read at ceres_calib_split_residuals.h:333-336 */
+icc_status icc_set_camera(icc_handle* h, int model, const double* intrinsics, int n_intrinsics, int image_width, int image_height);
+/* theia::Track::Point() homogeneous board points, id = index (app :111-119) */
+icc_status icc_set_board_points(icc_handle* h, int n_points, const double* xyzw);
+/* Views of the calibration dataset (app :131-161): timestamp [s], observed corners (CSR over frames), and the per-view
+ * pose prior used by BatchInitSO3R3VisPoses: q_wc (x,y,z,w) = R_cw^T and camera position p_wc (impl.h:290-300). */
+icc_status icc_set_frames(icc_handle* h, int n_frames, const double* timestamps_s, const int32_t* corner_offsets /* n_frames+1 */,
+                          const int32_t* point_ids, const double* uv, const double* q_wc_xyzw, const double* p_wc);
+/* CameraTelemetryData accelerometer/gyroscope streams (src/io/read_telemetry.cc:49-56) */
+icc_status icc_set_imu(icc_handle* h, int n_samples, const double* timestamps_s, const double* accel_xyz, const double* gyro_xyz);
+
+/* ---- ImuCameraCalibrator API -------------------------------------------------------------------------------- */
+/* BatchInitSpline (imu_camera_calibrator.cc:21-124): spline time range, knot counts, knot initialisation, bias
+ * splines, measurement wiring (CalcTimes impl.h:763-788), gravity initialisation; uploads everything to HBM. */
+icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* p);
+/* SetKnownGravityDir (imu_camera_calibrator.cc:126-128) */
+icc_status icc_set_known_gravity_dir(icc_handle* h, const double g[3]);
+/* Residual sharding: keep only frames/IMU samples in shard `rank` of `world` (time-sliced, equal residual counts);
+ * knots stay replicated.  Must be called before icc_batch_init_spline.  world = 1 restores the full problem. */
+icc_status icc_set_shard(icc_handle* h, int rank, int world);
+icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user);
+/* Optimize (imu_camera_calibrator.cc:163-168 -> impl.h:254-276): LM over the blocks selected by `flags`. */
+icc_status icc_optimize(icc_handle* h, int max_iterations, int flags, icc_summary* summary);
+
+/* ---- getters (imu_camera_calibrator.h:48-77; impl.h:898-1072,1180-1234) -------------------------------------- */
+icc_status icc_get_T_i_c(const icc_handle* h, double T_i_c[7]);
+icc_status icc_get_gravity(const icc_handle* h, double g[3]);
+icc_status icc_get_line_delay(const icc_handle* h, double* line_delay_s);
+icc_status icc_get_num_knots(const icc_handle* h, int* n_so3, int* n_r3, int* n_acc_bias, int* n_gyr_bias);
+icc_status icc_get_knots(const icc_handle* h, double* so3_xyzw, double* r3_xyz, double* acc_bias_xyz, double* gyr_bias_xyz); /* any may be NULL */
+icc_status icc_set_knots(icc_handle* h, const double* so3_xyzw, const double* r3_xyz, const double* acc_bias_xyz, const double* gyr_bias_xyz);
+icc_status icc_set_T_i_c(icc_handle* h, const double T_i_c[7]);
+icc_status icc_set_line_delay(icc_handle* h, double line_delay_s);
+icc_status icc_get_mean_reprojection_error(icc_handle* h, double* err);
+/* number of IMU samples kept by BatchInitSpline and their (offset-corrected) timestamps / raw readings (app :265-327) */
+icc_status icc_get_num_imu_used(const icc_handle* h, int* n);
+icc_status icc_get_imu_used(const icc_handle* h, double* t_s, double* accel_xyz, double* gyro_xyz);
+/* GetAngularVelocity / GetAcceleration / GetGyroBias / GetAcclBias / GetPose evaluated on the GPU for n timestamps [ns];
+ * valid[i] = 0 where CalcTimes rejects the timestamp (outputs left untouched there). Any output may be NULL. */
+icc_status icc_eval_trajectory(icc_handle* h, int n, const int64_t* t_ns, double* gyro_xyz, double* accel_xyz,
+                               double* gyro_bias_xyz, double* accel_bias_xyz, double* pose_q_xyzw, double* pose_p, int32_t* valid);
+
+/* ---- test / measurement surface ----------------------------------------------------------------------------- */
+icc_status icc_num_residuals(const icc_handle* h, int* n_vision, int* n_accel, int* n_gyro);   /* scalar residual counts */
+icc_status icc_num_tangent(const icc_handle* h, int flags, int* n);
+/* One evaluation at the current state.  Canonical tangent order: so3 knots (3 each), r3 knots (3 each), T_i_c (6: upsilon,
+ * omega), gravity (3), line delay (1), acc-bias knots (3 each), gyr-bias knots (3 each) — only blocks active under `flags`.
+ * residuals: [vision 2/corner in frame order | accel 3/sample | gyro 3/sample].  hessian_dense: n x n row-major J^T J
+ * (small problems only).  Any output may be NULL. */
+icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residuals, double* gradient, double* hessian_dense);
+/* Run exactly `n` LM iterations (no convergence test) from the current state; used by bench.py as the timed "step". */
+icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summary);
+/* Run `n` bare residual+Jacobian+normal-equation evaluations (the residual-eval kernels only); device ms per evaluation. */
+icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICC_B200_H_ */

@@ -1,0 +1,259 @@
+"""ctypes binding of the C-ABI declared in include/icc_b200.h.
+
+`CApi(lib, prefix)` binds every entry point of a loaded shared library; the product binds `libicc_b200.so` with prefix
+`icc_`.  (tests/ bind the CPU oracle, which deliberately exports the same shapes under `icco_`, through the same class —
+the product package itself never loads or references the oracle.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+FLAG_POINTS, FLAG_T_I_C, FLAG_IMU_BIASES, FLAG_IMU_INTRINSICS = 1, 2, 4, 8
+FLAG_GRAVITY_DIR, FLAG_CAM_LINE_DELAY, FLAG_SPLINE, FLAG_ACC_BIAS, FLAG_GYR_BIAS = 16, 32, 64, 128, 256
+
+STATUS_NAMES = {0: "ICC_OK", 1: "ICC_ERR_INVALID_ARGUMENT", 2: "ICC_ERR_NO_DEVICE", 3: "ICC_ERR_CUDA", 4: "ICC_ERR_STATE",
+                5: "ICC_ERR_UNSUPPORTED", 6: "ICC_ERR_NUMERIC"}
+TERMINATION = {0: "max_iterations", 1: "function_tolerance", 2: "parameter_tolerance", 3: "gradient_tolerance", 4: "failure"}
+
+
+class InitParams(C.Structure):
+    _fields_ = [("T_i_c_init", C.c_double * 7), ("dt_so3_s", C.c_double), ("dt_r3_s", C.c_double), ("std_so3", C.c_double),
+                ("std_r3", C.c_double), ("time_offset_imu_to_cam_s", C.c_double), ("init_line_delay_s", C.c_double),
+                ("acc_intrinsics", C.c_double * 6), ("gyr_intrinsics", C.c_double * 9), ("acc_bias", C.c_double * 3),
+                ("gyr_bias", C.c_double * 3), ("dispatch_fov", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [("function_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32), ("max_consecutive_invalid_steps", C.c_int32)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("termination", C.c_int32), ("num_residuals", C.c_int32),
+                ("num_tangent", C.c_int32), ("jacobian_evaluations", C.c_int32), ("cost_evaluations", C.c_int32),
+                ("gpu_launches", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("mean_reproj_error", C.c_double), ("seconds_total", C.c_double), ("seconds_jacobian", C.c_double),
+                ("seconds_linear_solve", C.c_double)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["termination_name"] = TERMINATION.get(self.termination, "?")
+        return d
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
+class IccError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class CApi:
+    """Thin object wrapper around one solver handle of a loaded library."""
+
+    def __init__(self, lib: C.CDLL, prefix: str, create_arg: int = 0):
+        self.lib, self.prefix = lib, prefix
+        self._keepalive = []
+        h = C.c_void_p()
+        f = self._fn("create"); f.restype = C.c_int; f.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        st = f(C.byref(h), create_arg)
+        self.h = h
+        if st != 0:
+            msg = self.last_error() if h.value else ""
+            self.h = None
+            raise IccError(f"{prefix}create failed: {STATUS_NAMES.get(st, st)} {msg}")
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def last_error(self) -> str:
+        f = self._fn("last_error"); f.restype = C.c_char_p; f.argtypes = [C.c_void_p]
+        return (f(self.h) or b"").decode()
+
+    def _call(self, name, argtypes, *args):
+        f = self._fn(name); f.restype = C.c_int; f.argtypes = [C.c_void_p] + list(argtypes)
+        st = f(self.h, *args)
+        if st != 0:
+            raise IccError(f"{self.prefix}{name}: {STATUS_NAMES.get(st, st)}: {self.last_error()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            f = self._fn("destroy"); f.restype = None; f.argtypes = [C.c_void_p]
+            f(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- problem data --------------------------------------------------------------------------------------
+    def set_solver_options(self, **kw):
+        o = default_solver_options()
+        for k, v in kw.items():
+            setattr(o, k, v)
+        self._call("set_solver_options", [C.POINTER(SolverOptions)], C.byref(o))
+
+    def set_camera(self, model, intrinsics, width, height):
+        k = _f64(intrinsics)
+        self._call("set_camera", [C.c_int, c_double_p, C.c_int, C.c_int, C.c_int], int(model), _dp(k), k.size, int(width), int(height))
+
+    def set_board_points(self, xyzw):
+        p = _f64(xyzw).reshape(-1, 4)
+        self._call("set_board_points", [C.c_int, c_double_p], p.shape[0], _dp(p))
+
+    def set_frames(self, t_s, corner_offsets, point_ids, uv, q_wc, p_wc):
+        t = _f64(t_s); off = np.ascontiguousarray(corner_offsets, dtype=np.int32); ids = np.ascontiguousarray(point_ids, dtype=np.int32)
+        uv = _f64(uv); q = _f64(q_wc); p = _f64(p_wc)
+        assert off.size == t.size + 1 and ids.size == off[-1] and uv.size == 2 * ids.size and q.size == 4 * t.size and p.size == 3 * t.size
+        self._call("set_frames", [C.c_int, c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_double_p], t.size, _dp(t),
+                   off.ctypes.data_as(c_int32_p), ids.ctypes.data_as(c_int32_p), _dp(uv), _dp(q), _dp(p))
+
+    def set_imu(self, t_s, accel, gyro):
+        t = _f64(t_s); a = _f64(accel); g = _f64(gyro)
+        assert a.size == 3 * t.size and g.size == 3 * t.size
+        self._call("set_imu", [C.c_int, c_double_p, c_double_p, c_double_p], t.size, _dp(t), _dp(a), _dp(g))
+
+    def set_shard(self, rank, world):
+        self._call("set_shard", [C.c_int, C.c_int], int(rank), int(world))
+
+    def set_allreduce(self, pyfunc):
+        cb = ALLREDUCE_FN(pyfunc) if pyfunc is not None else C.cast(None, ALLREDUCE_FN)
+        self._keepalive.append(cb)
+        self._call("set_allreduce", [ALLREDUCE_FN, C.c_void_p], cb, None)
+
+    def batch_init_spline(self, T_i_c_init, dt_so3_s, dt_r3_s, std_so3, std_r3, time_offset_imu_to_cam_s, init_line_delay_s,
+                          acc_intrinsics=(0, 0, 0, 1, 1, 1), gyr_intrinsics=(0, 0, 0, 0, 0, 0, 1, 1, 1), acc_bias=(0, 0, 0),
+                          gyr_bias=(0, 0, 0), dispatch_fov=False):
+        p = InitParams()
+        p.T_i_c_init[:] = list(map(float, T_i_c_init)); p.dt_so3_s = dt_so3_s; p.dt_r3_s = dt_r3_s; p.std_so3 = std_so3; p.std_r3 = std_r3
+        p.time_offset_imu_to_cam_s = time_offset_imu_to_cam_s; p.init_line_delay_s = init_line_delay_s
+        p.acc_intrinsics[:] = list(map(float, acc_intrinsics)); p.gyr_intrinsics[:] = list(map(float, gyr_intrinsics))
+        p.acc_bias[:] = list(map(float, acc_bias)); p.gyr_bias[:] = list(map(float, gyr_bias)); p.dispatch_fov = int(bool(dispatch_fov))
+        self._call("batch_init_spline", [C.POINTER(InitParams)], C.byref(p))
+
+    def set_known_gravity_dir(self, g):
+        g = _f64(g)
+        self._call("set_known_gravity_dir", [c_double_p], _dp(g))
+
+    # ---- solve ---------------------------------------------------------------------------------------------
+    def optimize(self, max_iterations, flags) -> Summary:
+        s = Summary()
+        self._call("optimize", [C.c_int, C.c_int, C.POINTER(Summary)], int(max_iterations), int(flags), C.byref(s))
+        return s
+
+    def lm_iterations(self, n, flags) -> Summary:
+        s = Summary()
+        self._call("lm_iterations", [C.c_int, C.c_int, C.POINTER(Summary)], int(n), int(flags), C.byref(s))
+        return s
+
+    def time_evaluations(self, n, flags, with_jacobian=True) -> float:
+        ms = C.c_double()
+        self._call("time_evaluations", [C.c_int, C.c_int, C.c_int, c_double_p], int(n), int(flags), int(with_jacobian), C.byref(ms))
+        return ms.value
+
+    # ---- getters -------------------------------------------------------------------------------------------
+    def get_T_i_c(self):
+        T = np.zeros(7); self._call("get_T_i_c", [c_double_p], _dp(T)); return T
+
+    def set_T_i_c(self, T):
+        T = _f64(T); self._call("set_T_i_c", [c_double_p], _dp(T))
+
+    def get_gravity(self):
+        g = np.zeros(3); self._call("get_gravity", [c_double_p], _dp(g)); return g
+
+    def get_line_delay(self):
+        v = C.c_double(); self._call("get_line_delay", [c_double_p], C.byref(v)); return v.value
+
+    def set_line_delay(self, v):
+        self._call("set_line_delay", [C.c_double], float(v))
+
+    def num_knots(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._call("get_num_knots", [C.POINTER(C.c_int)] * 4, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
+
+    def get_knots(self):
+        a, b, c, d = self.num_knots()
+        so3, r3, ba, bg = np.zeros((a, 4)), np.zeros((b, 3)), np.zeros((c, 3)), np.zeros((d, 3))
+        self._call("get_knots", [c_double_p] * 4, _dp(so3), _dp(r3), _dp(ba), _dp(bg))
+        return so3, r3, ba, bg
+
+    def set_knots(self, so3=None, r3=None, ba=None, bg=None):
+        arrs = [None if x is None else _f64(x) for x in (so3, r3, ba, bg)]
+        self._call("set_knots", [c_double_p] * 4, *[_dp(x) for x in arrs])
+
+    def mean_reprojection_error(self):
+        v = C.c_double(); self._call("get_mean_reprojection_error", [c_double_p], C.byref(v)); return v.value
+
+    def imu_used(self):
+        n = C.c_int(); self._call("get_num_imu_used", [C.POINTER(C.c_int)], C.byref(n))
+        t, a, g = np.zeros(n.value), np.zeros((n.value, 3)), np.zeros((n.value, 3))
+        self._call("get_imu_used", [c_double_p] * 3, _dp(t), _dp(a), _dp(g))
+        return t, a, g
+
+    def eval_trajectory(self, t_ns):
+        t = np.ascontiguousarray(t_ns, dtype=np.int64); n = t.size
+        out = dict(gyro=np.zeros((n, 3)), accel=np.zeros((n, 3)), gyro_bias=np.zeros((n, 3)), accel_bias=np.zeros((n, 3)),
+                   pose_q=np.zeros((n, 4)), pose_p=np.zeros((n, 3)), valid=np.zeros(n, dtype=np.int32))
+        self._call("eval_trajectory", [C.c_int, c_int64_p] + [c_double_p] * 6 + [c_int32_p], n, t.ctypes.data_as(c_int64_p), _dp(out["gyro"]),
+                   _dp(out["accel"]), _dp(out["gyro_bias"]), _dp(out["accel_bias"]), _dp(out["pose_q"]), _dp(out["pose_p"]),
+                   out["valid"].ctypes.data_as(c_int32_p))
+        return out
+
+    # ---- test / measurement surface --------------------------------------------------------------------------
+    def num_residuals(self):
+        v, a, g = C.c_int(), C.c_int(), C.c_int()
+        self._call("num_residuals", [C.POINTER(C.c_int)] * 3, C.byref(v), C.byref(a), C.byref(g))
+        return v.value, a.value, g.value
+
+    def num_tangent(self, flags):
+        n = C.c_int(); self._call("num_tangent", [C.c_int, C.POINTER(C.c_int)], int(flags), C.byref(n)); return n.value
+
+    def evaluate(self, flags, residuals=True, gradient=True, hessian=False):
+        nres = sum(self.num_residuals()); n = self.num_tangent(flags)
+        cost = C.c_double()
+        r = np.zeros(nres) if residuals else None
+        g = np.zeros(n) if gradient else None
+        H = np.zeros((n, n)) if hessian else None
+        self._call("evaluate", [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p], int(flags), C.byref(cost), _dp(r), _dp(g), _dp(H))
+        return cost.value, r, g, H
+
+
+def default_solver_options() -> SolverOptions:
+    """ceres::Solver::Options of SplineTrajectoryEstimator::Optimize (impl.h:254-266) + Ceres 2.1 defaults."""
+    return SolverOptions(1e-4, 1e-7, 1e-10, 1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 1, 5)
+
+
+def load_dataset(api: CApi, ds: dict, known_gravity=True, dispatch_fov=None, shard=None):
+    """Feed a synthetic dataset (synthetic.make_dataset) through the boundary in the order the hot CLI does."""
+    W, H = ds["image_size"]
+    api.set_camera(ds["model"], ds["intrinsics"], W, H)
+    api.set_board_points(ds["board_xyzw"])
+    api.set_frames(ds["frame_t"], ds["corner_offsets"], ds["point_ids"], ds["uv"], ds["q_wc"], ds["p_wc"])
+    api.set_imu(ds["imu_t"], ds["accel"], ds["gyro"])
+    if shard is not None:
+        api.set_shard(*shard)
+    if dispatch_fov is None:
+        dispatch_fov = ds["model"] == 3
+    api.batch_init_spline(ds["T_i_c_init"], ds["dt_so3_s"], ds["dt_r3_s"], ds["std_so3"], ds["std_r3"], ds["time_offset_imu_to_cam_s"],
+                          ds["init_line_delay_s"], acc_bias=ds["acc_bias"], gyr_bias=ds["gyr_bias"], dispatch_fov=dispatch_fov)
+    if known_gravity:
+        api.set_known_gravity_dir(ds["gravity"])

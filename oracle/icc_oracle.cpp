@@ -1,0 +1,955 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.hpp header).  PARITY UNPINNED by reference tests (none exist).
+//
+// CPU restatement of the reference's continuous-time IMU-camera calibration hot path, exported with the same C-ABI
+// shape as include/icc_b200.h but with the `icco_` prefix:
+//   * problem assembly      ~ src/core/imu_camera_calibrator.cc:21-161
+//                             include/OpenCameraCalibrator/core/spline_trajectory_estimator.impl.h:37-90,278-339,341-613,763-788
+//   * spline initialisation ~ src/utils/utils.cc:194-261 (FindClosestTimestamp / slerp / lerp, quirks kept)
+//   * residual functors     ~ include/OpenCameraCalibrator/basalt_spline/ceres_calib_split_residuals.h:52-93,133-169,319-402
+//   * Jacobians             ~ ceres::DynamicAutoDiffCostFunction (stride-4 forward-mode passes over the ACTIVE ambient
+//                             parameters) times LieLocalParameterization::ComputeJacobian
+//                             (basalt_spline/ceres_local_param.h:96-108; Sophus so3.hpp:191-220, se3.hpp:135-200)
+//   * fixed / free blocks   ~ SplineTrajectoryEstimator::SetFixedParams (impl.h:92-252)
+//   * Levenberg-Marquardt   ~ ceres::Solve with the options of impl.h:254-266 and Ceres-2.1 defaults (external source;
+//                             restated from its documentation: TrustRegionMinimizer + LevenbergMarquardtStrategy,
+//                             Jacobi scaling, SPARSE_NORMAL_CHOLESKY replaced by an exact banded+bordered Cholesky).
+//                             NOT restated: use_inner_iterations (coordinate-descent refinement; same optimum, different
+//                             path) and the projected line search for bound constraints (plain projection is used).
+//   * result getters        ~ impl.h:898-1072,1180-1234
+// Doubles as the timed CPU baseline (std::thread over residual blocks, like Ceres' num_threads = hardware_concurrency()).
+#include "oracle_math.hpp"
+#include "../include/icc_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace icco;
+
+namespace {
+
+constexpr int SPLINE_N = 6;   // core/imu_camera_calibrator.h:27
+constexpr int BIAS_N = 3;     // basalt_spline/ceres_calib_split_residuals.h:21
+constexpr double S_TO_NS = 1e9, NS_TO_S = 1e-9;
+
+enum BlockType { BLK_RS_VISION = 0, BLK_ACCEL = 1, BLK_GYRO = 2 };
+enum LocalParam { LP_NONE = 0, LP_SO3 = 1, LP_SE3 = 2 };
+
+struct ParamRef { const double* ptr; int size; int lp; int tan_off; };  // tan_off < 0 => constant block
+
+struct Block {
+  int type;
+  int n_res;
+  int res_off;                  // offset into the global residual vector
+  int frame;                    // vision: frame index; imu: sample index
+  double u_so3, u_r3, u_bias;
+  std::vector<ParamRef> params;
+};
+
+struct Frame { double t_s; int c0, c1; int64_t s_so3, s_r3; double u_so3, u_r3; bool ok; };
+struct ImuUsed { double t_s; double acc[3], gyr[3]; };
+
+struct Oracle {
+  std::string err;
+  icc_solver_options opt;
+  int n_threads = 0;
+  // camera + board
+  int model = -1, n_intr = 0, width = 0, height = 0; double intr[10] = {0};
+  std::vector<double> points;
+  // frames
+  std::vector<double> frame_t; std::vector<int> corner_off, point_ids; std::vector<double> uv, q_wc, p_wc;
+  // imu
+  std::vector<double> imu_t, imu_acc, imu_gyr;
+  // shard
+  int shard_rank = 0, shard_world = 1;
+  // initialised problem
+  bool initialised = false;
+  icc_init_params ip;
+  bool dispatch_fov = false;
+  int64_t dt_so3_ns = 0, dt_r3_ns = 0, start_ns = 0, end_ns = 0, dt_ba_ns = 0, dt_bg_ns = 0;
+  double inv_so3_dt = 0, inv_r3_dt = 0, inv_ba_dt = 0, inv_bg_dt = 0;
+  double t0_s = 0, tend_s = 0;
+  std::vector<double> so3, r3, ba, bg;   // knots
+  double T_ic[7], grav[3], line_delay = 0, acc_intr[6], gyr_intr[9];
+  double max_ba = 1.0, max_bg = 0.1;
+  std::vector<Frame> frames;
+  std::vector<ImuUsed> imu_used;
+  std::vector<Block> blocks;
+  int n_res_vis = 0, n_res_acc = 0, n_res_gyr = 0;
+  // active set / ordering (rebuilt per flags)
+  int cur_flags = -1;
+  int n_tan = 0;
+  int off_so3 = -1, off_r3 = -1, off_tic = -1, off_g = -1, off_ld = -1, off_ba = -1, off_bg = -1;  // canonical offsets
+  // solver ordering: canonical tangent index -> solver index
+  std::vector<int> perm;      // canonical -> solver
+  int n_knot_dims = 0, n_border = 0, kd = 0;
+  int jac_evals = 0, cost_evals = 0;
+};
+
+int nknots(const std::vector<double>& v, int dim) { return int(v.size()) / dim; }
+
+// impl.h:763-788
+bool calc_times(int64_t sensor_ns, int64_t start_ns, int64_t dt_ns, size_t nr_knots, int N, double& u, int64_t& s) {
+  const int64_t st_ns = sensor_ns - start_ns;
+  if (st_ns < 0) { u = 0.0; return false; }
+  s = st_ns / dt_ns;
+  if (s < 0) return false;
+  if (size_t(s + N) > nr_knots) return false;
+  u = double(st_ns % dt_ns) / double(dt_ns);
+  return true;
+}
+
+// utils.cc:194-212
+size_t find_closest(double t, const std::vector<double>& ts, double& dist_out) {
+  double dist = 1.7976931348623157e308; size_t idx = 0;
+  for (size_t i = 0; i < ts.size(); ++i) {
+    double nd = std::fabs(t - ts[i]);
+    if (nd < dist) { dist_out = nd; idx = i; dist = nd; if (dist_out == 0.0) break; }
+  }
+  return idx;
+}
+// Eigen::QuaternionBase::slerp
+void slerp(const double a[4], const double b[4], double t, double out[4]) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+  double ad = std::fabs(d), s0, s1;
+  if (ad >= one) { s0 = 1.0 - t; s1 = t; }
+  else { double th = std::acos(ad), st = std::sin(th); s0 = std::sin((1.0 - t) * th) / st; s1 = std::sin(t * th) / st; }
+  if (d < 0) s1 = -s1;
+  for (int i = 0; i < 4; ++i) out[i] = s0 * a[i] + s1 * b[i];
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Residual functors, templated on the scalar like the reference.
+// -------------------------------------------------------------------------------------------------------------
+template <class T>
+void rs_reprojection(const Oracle& o, const Block& b, const T* const* P, T* res) {   // residuals.h:319-402
+  const int N2 = 2 * SPLINE_N;
+  SE3T<T> T_i_c{{P[N2][0], P[N2][1], P[N2][2], P[N2][3]}, {P[N2][4], P[N2][5], P[N2][6]}};
+  const T line_delay = P[N2 + 1][0];
+  T intr[10];
+  for (int i = 0; i < o.n_intr; ++i) intr[i] = T(o.intr[i]);
+  const Frame& f = o.frames[b.frame];
+  for (int c = f.c0; c < f.c1; ++c) {
+    const int i = c - f.c0;
+    const double ox = o.uv[2 * c], oy = o.uv[2 * c + 1];
+    const T y_coord = T(oy) * line_delay;
+    const T t_so3_row = T(b.u_so3) + y_coord;
+    const T t_r3_row = T(b.u_r3) + y_coord;
+    Q4<T> R_w_i;
+    evaluate_lie_so3<SPLINE_N, T>(P, t_so3_row, T(o.inv_so3_dt), &R_w_i, nullptr);
+    V3<T> t_w_i = evaluate_r3<SPLINE_N, 0, T>(P + SPLINE_N, t_r3_row, T(o.inv_r3_dt));
+    SE3T<T> T_w_c = se3_mul(SE3T<T>{R_w_i, t_w_i}, T_i_c);
+    SE3T<T> T_c_w = se3_inv(T_w_c);
+    M3<T> R = so3_matrix(T_c_w.q);
+    const T* X = P[N2 + 2 + i];
+    // (T_c_w.matrix() * X_h).hnormalized()
+    T h[3];
+    h[0] = R.m[0][0] * X[0] + R.m[0][1] * X[1] + R.m[0][2] * X[2] + T_c_w.t.x * X[3];
+    h[1] = R.m[1][0] * X[0] + R.m[1][1] * X[1] + R.m[1][2] * X[2] + T_c_w.t.y * X[3];
+    h[2] = R.m[2][0] * X[0] + R.m[2][1] * X[1] + R.m[2][2] * X[2] + T_c_w.t.z * X[3];
+    T p3[3] = {h[0] / X[3], h[1] / X[3], h[2] / X[3]};
+    T px[2];
+    const bool ok = project<T>(o.model, intr, p3, px, o.dispatch_fov);
+    if (!ok) { res[2 * i] = T(1e10); res[2 * i + 1] = T(1e10); }
+    else { res[2 * i] = px[0] - T(ox); res[2 * i + 1] = px[1] - T(oy); }   // covariance = I (app :157)
+  }
+}
+
+template <class T>
+void accel_residual(const Oracle& o, const Block& b, const T* const* P, T* res) {   // residuals.h:52-93
+  const ImuUsed& m = o.imu_used[b.frame];
+  Q4<T> R_w_i;
+  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3), T(o.inv_so3_dt), &R_w_i, nullptr);
+  V3<T> accel_w = evaluate_r3<SPLINE_N, 2, T>(P + SPLINE_N, T(b.u_r3), T(o.inv_r3_dt));
+  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + 2 * SPLINE_N, T(b.u_bias), T(o.inv_ba_dt));
+  const T* g = P[2 * SPLINE_N + BIAS_N];
+  const T* ai = P[2 * SPLINE_N + BIAS_N + 1];
+  V3<T> raw{T(m.acc[0]), T(m.acc[1]), T(m.acc[2])};
+  V3<T> cal = triad_unbias_normalize<T>(ai[0], ai[1], ai[2], T(0.0), T(0.0), T(0.0), ai[3], ai[4], ai[5], bias, raw);
+  V3<T> aw{accel_w.x + g[0], accel_w.y + g[1], accel_w.z + g[2]};
+  V3<T> pred = so3_act(so3_inv(R_w_i), aw);
+  const T w(1.0 / o.ip.std_r3);
+  res[0] = w * (pred.x - cal.x); res[1] = w * (pred.y - cal.y); res[2] = w * (pred.z - cal.z);
+}
+
+template <class T>
+void gyro_residual(const Oracle& o, const Block& b, const T* const* P, T* res) {   // residuals.h:133-169
+  const ImuUsed& m = o.imu_used[b.frame];
+  V3<T> rot_vel;
+  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3), T(o.inv_so3_dt), nullptr, &rot_vel);
+  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + SPLINE_N, T(b.u_bias), T(o.inv_bg_dt));
+  const T* gi = P[SPLINE_N + BIAS_N];
+  V3<T> raw{T(m.gyr[0]), T(m.gyr[1]), T(m.gyr[2])};
+  V3<T> cal = triad_unbias_normalize<T>(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gi[7], gi[8], bias, raw);
+  const T w(1.0 / o.ip.std_so3);
+  res[0] = w * (rot_vel.x - cal.x); res[1] = w * (rot_vel.y - cal.y); res[2] = w * (rot_vel.z - cal.z);
+}
+
+template <class T>
+void eval_block_T(const Oracle& o, const Block& b, const T* const* P, T* res) {
+  switch (b.type) {
+    case BLK_RS_VISION: rs_reprojection<T>(o, b, P, res); break;
+    case BLK_ACCEL: accel_residual<T>(o, b, P, res); break;
+    case BLK_GYRO: gyro_residual<T>(o, b, P, res); break;
+  }
+}
+
+// so3.hpp:191-220 / se3.hpp:135-200 : d(this * exp(x))/dx at 0, rows = ambient coeffs, cols = tangent
+void lp_jacobian_so3(const double* q, double J[4][3]) {
+  const double c0 = 0.5 * q[3], c1 = 0.5 * q[2], c2 = -c1, c3 = 0.5 * q[1], c4 = 0.5 * q[0], c5 = -c4, c6 = -c3;
+  J[0][0] = c0; J[0][1] = c2; J[0][2] = c3;
+  J[1][0] = c1; J[1][1] = c0; J[1][2] = c5;
+  J[2][0] = c6; J[2][1] = c4; J[2][2] = c0;
+  J[3][0] = c5; J[3][1] = c6; J[3][2] = c2;
+}
+void lp_jacobian_se3(const double* T7, double J[7][6]) {
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 6; ++j) J[i][j] = 0;
+  double Jq[4][3]; lp_jacobian_so3(T7, Jq);
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) J[i][3 + j] = Jq[i][j];
+  Q4<double> q{T7[0], T7[1], T7[2], T7[3]};
+  M3<double> R = so3_matrix(q);   // identical to the c7..c21 polynomial for unit quaternions
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[4 + i][j] = R.m[i][j];
+}
+
+struct Scratch {
+  std::vector<Jet<4>> jets; std::vector<const Jet<4>*> jptr; std::vector<Jet<4>> jres;
+  std::vector<const double*> dptr; std::vector<double> res; std::vector<double> Jamb, Jtan; std::vector<int> cols;
+};
+
+// Evaluate one block: residuals always; tangent Jacobian (row-major n_res x n_cols with global canonical column ids) if wanted.
+void eval_block(const Oracle& o, const Block& b, Scratch& s, bool want_jac, int& n_cols_out) {
+  const int np = int(b.params.size());
+  s.dptr.resize(np);
+  for (int i = 0; i < np; ++i) s.dptr[i] = b.params[i].ptr;
+  s.res.assign(b.n_res, 0.0);
+  n_cols_out = 0;
+  if (!want_jac) { eval_block_T<double>(o, b, s.dptr.data(), s.res.data()); return; }
+  // ambient layout over active params
+  int A = 0, total = 0;
+  for (const auto& p : b.params) { total += p.size; if (p.tan_off >= 0) A += p.size; }
+  s.jets.resize(total); s.jptr.resize(np); s.jres.resize(b.n_res);
+  s.Jamb.assign(size_t(b.n_res) * std::max(A, 1), 0.0);
+  const int passes = (A + 3) / 4;
+  bool have_res = false;
+  for (int pass = 0; pass < std::max(passes, 1); ++pass) {
+    int off = 0, a = 0;
+    for (int i = 0; i < np; ++i) {
+      const auto& p = b.params[i];
+      s.jptr[i] = &s.jets[off];
+      for (int k = 0; k < p.size; ++k) {
+        Jet<4>& j = s.jets[off + k];
+        j.a = p.ptr[k]; j.v[0] = j.v[1] = j.v[2] = j.v[3] = 0;
+        if (p.tan_off >= 0) { const int lane = a - 4 * pass; if (lane >= 0 && lane < 4) j.v[lane] = 1.0; ++a; }
+      }
+      off += p.size;
+    }
+    eval_block_T<Jet<4>>(o, b, s.jptr.data(), s.jres.data());
+    if (!have_res) { for (int r = 0; r < b.n_res; ++r) s.res[r] = s.jres[r].a; have_res = true; }
+    for (int r = 0; r < b.n_res; ++r) for (int l = 0; l < 4; ++l) { const int col = 4 * pass + l; if (col < A) s.Jamb[size_t(r) * A + col] = s.jres[r].v[l]; }
+  }
+  // ambient -> tangent through the local parameterisations
+  int ncols = 0;
+  for (const auto& p : b.params) if (p.tan_off >= 0) ncols += (p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.size);
+  s.Jtan.assign(size_t(b.n_res) * std::max(ncols, 1), 0.0); s.cols.resize(ncols);
+  int a = 0, c = 0;
+  for (const auto& p : b.params) {
+    if (p.tan_off < 0) continue;
+    if (p.lp == LP_SO3) {
+      double L[4][3]; lp_jacobian_so3(p.ptr, L);
+      for (int r = 0; r < b.n_res; ++r) for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 4; ++k) v += s.Jamb[size_t(r) * A + a + k] * L[k][j]; s.Jtan[size_t(r) * ncols + c + j] = v; }
+      for (int j = 0; j < 3; ++j) s.cols[c + j] = p.tan_off + j;
+      a += 4; c += 3;
+    } else if (p.lp == LP_SE3) {
+      double L[7][6]; lp_jacobian_se3(p.ptr, L);
+      for (int r = 0; r < b.n_res; ++r) for (int j = 0; j < 6; ++j) { double v = 0; for (int k = 0; k < 7; ++k) v += s.Jamb[size_t(r) * A + a + k] * L[k][j]; s.Jtan[size_t(r) * ncols + c + j] = v; }
+      for (int j = 0; j < 6; ++j) s.cols[c + j] = p.tan_off + j;
+      a += 7; c += 6;
+    } else {
+      for (int r = 0; r < b.n_res; ++r) for (int j = 0; j < p.size; ++j) s.Jtan[size_t(r) * ncols + c + j] = s.Jamb[size_t(r) * A + a + j];
+      for (int j = 0; j < p.size; ++j) s.cols[c + j] = p.tan_off + j;
+      a += p.size; c += p.size;
+    }
+  }
+  n_cols_out = ncols;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Active set (SetFixedParams, impl.h:92-252) and solver ordering.
+// -------------------------------------------------------------------------------------------------------------
+bool configure(Oracle& o, int flags) {
+  if (flags & (ICC_FLAG_POINTS)) { o.err = "POINTS flag is not supported (never set by the hot CLI)"; return false; }
+  const int nso3 = nknots(o.so3, 4), nr3 = nknots(o.r3, 3), nba = nknots(o.ba, 3), nbg = nknots(o.bg, 3);
+  const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
+  // line delay block: only touched by SetFixedParams when != 0; a zero line delay means the GS path (no such block)
+  const bool ld = (flags & ICC_FLAG_CAM_LINE_DELAY) && o.line_delay != 0.0;
+  const bool abias = flags & (ICC_FLAG_ACC_BIAS | ICC_FLAG_IMU_BIASES), gbias = flags & (ICC_FLAG_GYR_BIAS | ICC_FLAG_IMU_BIASES);
+  const bool imu_intr = flags & ICC_FLAG_IMU_INTRINSICS;
+  int n = 0;
+  o.off_so3 = spline ? n : -1; if (spline) n += 3 * nso3;
+  o.off_r3 = spline ? n : -1; if (spline) n += 3 * nr3;
+  o.off_tic = tic ? n : -1; if (tic) n += 6;
+  o.off_g = grav ? n : -1; if (grav) n += 3;
+  o.off_ld = ld ? n : -1; if (ld) n += 1;
+  o.off_ba = abias ? n : -1; if (abias) n += 3 * nba;
+  o.off_bg = gbias ? n : -1; if (gbias) n += 3 * nbg;
+  const int off_ai = imu_intr ? n : -1; if (imu_intr) n += 6;
+  const int off_gi = imu_intr ? n : -1; if (imu_intr) n += 9;
+  o.n_tan = n; o.cur_flags = flags;
+  // wire tangent offsets into the blocks
+  for (auto& b : o.blocks) {
+    int k = 0;
+    auto so3k = [&](int64_t s) { for (int i = 0; i < SPLINE_N; ++i) b.params[k++].tan_off = spline ? o.off_so3 + 3 * int(s + i) : -1; };
+    auto r3k = [&](int64_t s) { for (int i = 0; i < SPLINE_N; ++i) b.params[k++].tan_off = spline ? o.off_r3 + 3 * int(s + i) : -1; };
+    if (b.type == BLK_RS_VISION) {
+      const Frame& f = o.frames[b.frame];
+      so3k(f.s_so3); r3k(f.s_r3);
+      b.params[k++].tan_off = o.off_tic;
+      b.params[k++].tan_off = o.off_ld;
+      for (; k < int(b.params.size()); ++k) b.params[k].tan_off = -1;
+    } else if (b.type == BLK_ACCEL) {
+      const int64_t s_so3 = (b.params[0].ptr - o.so3.data()) / 4, s_r3 = (b.params[SPLINE_N].ptr - o.r3.data()) / 3;
+      const int64_t s_b = (b.params[2 * SPLINE_N].ptr - o.ba.data()) / 3;
+      so3k(s_so3); r3k(s_r3);
+      for (int i = 0; i < BIAS_N; ++i) b.params[k++].tan_off = abias ? o.off_ba + 3 * int(s_b + i) : -1;
+      b.params[k++].tan_off = o.off_g;
+      b.params[k++].tan_off = off_ai;
+    } else {
+      const int64_t s_so3 = (b.params[0].ptr - o.so3.data()) / 4, s_b = (b.params[SPLINE_N].ptr - o.bg.data()) / 3;
+      so3k(s_so3);
+      for (int i = 0; i < BIAS_N; ++i) b.params[k++].tan_off = gbias ? o.off_bg + 3 * int(s_b + i) : -1;
+      b.params[k++].tan_off = off_gi;
+    }
+  }
+  // solver ordering: spline knots sorted by knot time (so3 before r3 on ties) form the banded part, rest = border
+  o.perm.assign(n, -1);
+  int pos = 0;
+  if (spline) {
+    int i = 0, j = 0;
+    while (i < nso3 || j < nr3) {
+      const bool take_so3 = j >= nr3 || (i < nso3 && int64_t(i) * o.dt_so3_ns <= int64_t(j) * o.dt_r3_ns);
+      const int base = take_so3 ? o.off_so3 + 3 * i++ : o.off_r3 + 3 * j++;
+      for (int d = 0; d < 3; ++d) o.perm[base + d] = pos++;
+    }
+  }
+  o.n_knot_dims = pos;
+  for (int c = 0; c < n; ++c) if (o.perm[c] < 0) o.perm[c] = pos++;
+  o.n_border = n - o.n_knot_dims;
+  // half bandwidth from the residual blocks
+  int kd = 0;
+  if (spline) for (const auto& b : o.blocks) {
+    int lo = 1 << 30, hi = -1;
+    for (const auto& p : b.params) if (p.tan_off >= 0 && o.perm[p.tan_off] < o.n_knot_dims) { lo = std::min(lo, o.perm[p.tan_off]); hi = std::max(hi, o.perm[p.tan_off] + 2); }
+    if (hi >= 0) kd = std::max(kd, hi - lo);
+  }
+  o.kd = kd;
+  return true;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Normal equations in banded + bordered ("arrowhead") storage, solver ordering.
+// -------------------------------------------------------------------------------------------------------------
+struct Normal {
+  int nk = 0, nb = 0, kd = 0;
+  std::vector<double> band;   // nk x (kd+1): band[j*(kd+1) + (i-j)], i >= j
+  std::vector<double> E;      // nb x nk : E[b*nk + j]
+  std::vector<double> C;      // nb x nb (full symmetric)
+  std::vector<double> g;      // nk + nb
+  double cost = 0;
+  void init(int nk_, int nb_, int kd_) { nk = nk_; nb = nb_; kd = kd_; band.assign(size_t(nk) * (kd + 1), 0.0); E.assign(size_t(nb) * nk, 0.0); C.assign(size_t(nb) * nb, 0.0); g.assign(nk + nb, 0.0); cost = 0; }
+  inline void add(int i, int j, double v) {   // solver indices, any order; adds to the symmetric entry once
+    if (i < j) std::swap(i, j);
+    if (i < nk) band[size_t(j) * (kd + 1) + (i - j)] += v;
+    else if (j < nk) E[size_t(i - nk) * nk + j] += v;
+    else { C[size_t(i - nk) * nb + (j - nk)] += v; if (i != j) C[size_t(j - nk) * nb + (i - nk)] += v; }
+  }
+  void operator+=(const Normal& o) {
+    for (size_t i = 0; i < band.size(); ++i) band[i] += o.band[i];
+    for (size_t i = 0; i < E.size(); ++i) E[i] += o.E[i];
+    for (size_t i = 0; i < C.size(); ++i) C[i] += o.C[i];
+    for (size_t i = 0; i < g.size(); ++i) g[i] += o.g[i];
+    cost += o.cost;
+  }
+  double get(int i, int j) const {
+    if (i < j) std::swap(i, j);
+    if (i < nk) return (i - j <= kd) ? band[size_t(j) * (kd + 1) + (i - j)] : 0.0;
+    if (j < nk) return E[size_t(i - nk) * nk + j];
+    return C[size_t(i - nk) * nb + (j - nk)];
+  }
+};
+
+int thread_count(const Oracle& o) { int n = o.n_threads > 0 ? o.n_threads : int(std::thread::hardware_concurrency()); return std::max(1, n); }
+
+// Full evaluation.  residuals (optional, global order), normal equations (optional), dense J (optional, tests only).
+void evaluate(Oracle& o, double* cost_out, double* residuals, Normal* ne, std::vector<double>* Jdense, int n_res_total) {
+  const int T = std::min<int>(thread_count(o), std::max<size_t>(1, o.blocks.size()));
+  std::vector<Normal> parts(ne ? T : 0);
+  std::vector<double> costs(T, 0.0);
+  if (ne) for (auto& p : parts) p.init(o.n_knot_dims, o.n_border, o.kd);
+  if (Jdense) Jdense->assign(size_t(n_res_total) * o.n_tan, 0.0);
+  auto work = [&](int tid) {
+    Scratch s;
+    const size_t nb = o.blocks.size();
+    // interleaved chunks for load balance (vision blocks are much heavier than IMU blocks)
+    for (size_t bi = tid; bi < nb; bi += T) {
+      const Block& b = o.blocks[bi];
+      int ncols = 0;
+      eval_block(o, b, s, ne != nullptr || Jdense != nullptr, ncols);
+      double c = 0;
+      for (int r = 0; r < b.n_res; ++r) c += s.res[r] * s.res[r];
+      costs[tid] += 0.5 * c;
+      if (residuals) for (int r = 0; r < b.n_res; ++r) residuals[b.res_off + r] = s.res[r];
+      if (Jdense) for (int r = 0; r < b.n_res; ++r) for (int k = 0; k < ncols; ++k) (*Jdense)[size_t(b.res_off + r) * o.n_tan + s.cols[k]] = s.Jtan[size_t(r) * ncols + k];
+      if (ne && ncols > 0) {
+        Normal& P = parts[tid];
+        std::vector<int>& cols = s.cols;
+        for (int k = 0; k < ncols; ++k) {
+          const int sk = o.perm[cols[k]];
+          double gk = 0;
+          for (int r = 0; r < b.n_res; ++r) gk += s.Jtan[size_t(r) * ncols + k] * s.res[r];
+          P.g[sk] += gk;
+          for (int l = k; l < ncols; ++l) {
+            double h = 0;
+            for (int r = 0; r < b.n_res; ++r) h += s.Jtan[size_t(r) * ncols + k] * s.Jtan[size_t(r) * ncols + l];
+            if (h != 0.0) P.add(sk, o.perm[cols[l]], h);
+          }
+        }
+      }
+    }
+  };
+  if (T == 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& t : th) t.join(); }
+  double cost = 0; for (double c : costs) cost += c;
+  if (ne) { *ne = std::move(parts[0]); for (int t = 1; t < T; ++t) *ne += parts[t]; ne->cost = cost; }
+  if (cost_out) *cost_out = cost;
+}
+
+// In-place Cholesky of (H + diag(D2)) in arrowhead storage followed by solve of (H + D2) x = rhs.  Returns false on breakdown.
+bool arrowhead_solve(Normal A, const std::vector<double>& D2, const std::vector<double>& rhs, std::vector<double>& x) {
+  const int nk = A.nk, nb = A.nb, kd = A.kd, n = nk + nb, ld = kd + 1;
+  for (int j = 0; j < nk; ++j) A.band[size_t(j) * ld] += D2[j];
+  for (int b = 0; b < nb; ++b) A.C[size_t(b) * nb + b] += D2[nk + b];
+  // factor the banded part column by column, carrying the border rows along
+  for (int j = 0; j < nk; ++j) {
+    double* col = &A.band[size_t(j) * ld];
+    if (!(col[0] > 0.0)) return false;
+    const double d = std::sqrt(col[0]), inv = 1.0 / d;
+    col[0] = d;
+    const int m = std::min(kd, nk - 1 - j);
+    for (int i = 1; i <= m; ++i) col[i] *= inv;
+    for (int b = 0; b < nb; ++b) A.E[size_t(b) * nk + j] *= inv;
+    for (int k = 1; k <= m; ++k) {         // trailing band update
+      const double lk = col[k]; if (lk == 0.0) continue;
+      double* ck = &A.band[size_t(j + k) * ld];
+      for (int i = k; i <= m; ++i) ck[i - k] -= col[i] * lk;
+      for (int b = 0; b < nb; ++b) A.E[size_t(b) * nk + j + k] -= A.E[size_t(b) * nk + j] * lk;
+    }
+    for (int b = 0; b < nb; ++b) { const double eb = A.E[size_t(b) * nk + j]; if (eb == 0.0) continue; for (int c = 0; c <= b; ++c) A.C[size_t(b) * nb + c] -= eb * A.E[size_t(c) * nk + j]; }
+  }
+  // dense Cholesky of the Schur complement (lower triangle of C)
+  for (int j = 0; j < nb; ++j) {
+    double d = A.C[size_t(j) * nb + j];
+    for (int k = 0; k < j; ++k) d -= A.C[size_t(j) * nb + k] * A.C[size_t(j) * nb + k];
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d); A.C[size_t(j) * nb + j] = d;
+    for (int i = j + 1; i < nb; ++i) {
+      double v = A.C[size_t(i) * nb + j];
+      for (int k = 0; k < j; ++k) v -= A.C[size_t(i) * nb + k] * A.C[size_t(j) * nb + k];
+      A.C[size_t(i) * nb + j] = v / d;
+    }
+  }
+  // forward substitution  L y = rhs
+  x = rhs;
+  for (int j = 0; j < nk; ++j) {
+    const double* col = &A.band[size_t(j) * ld];
+    x[j] /= col[0];
+    const int m = std::min(kd, nk - 1 - j);
+    for (int i = 1; i <= m; ++i) x[j + i] -= col[i] * x[j];
+    for (int b = 0; b < nb; ++b) x[nk + b] -= A.E[size_t(b) * nk + j] * x[j];
+  }
+  for (int j = 0; j < nb; ++j) { double v = x[nk + j]; for (int k = 0; k < j; ++k) v -= A.C[size_t(j) * nb + k] * x[nk + k]; x[nk + j] = v / A.C[size_t(j) * nb + j]; }
+  // back substitution  L^T x = y
+  for (int j = nb - 1; j >= 0; --j) { double v = x[nk + j]; for (int k = j + 1; k < nb; ++k) v -= A.C[size_t(k) * nb + j] * x[nk + k]; x[nk + j] = v / A.C[size_t(j) * nb + j]; }
+  for (int j = nk - 1; j >= 0; --j) {
+    const double* col = &A.band[size_t(j) * ld];
+    double v = x[j];
+    const int m = std::min(kd, nk - 1 - j);
+    for (int i = 1; i <= m; ++i) v -= col[i] * x[j + i];
+    for (int b = 0; b < nb; ++b) v -= A.E[size_t(b) * nk + j] * x[nk + b];
+    x[j] = v / col[0];
+  }
+  (void)n;
+  return true;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// State vector plumbing: Plus(), norms, snapshots.
+// -------------------------------------------------------------------------------------------------------------
+struct State { std::vector<double> so3, r3, ba, bg; double T_ic[7], grav[3], ld, acc_intr[6], gyr_intr[9]; };
+void save_state(const Oracle& o, State& s) { s.so3 = o.so3; s.r3 = o.r3; s.ba = o.ba; s.bg = o.bg; memcpy(s.T_ic, o.T_ic, sizeof s.T_ic); memcpy(s.grav, o.grav, sizeof s.grav); s.ld = o.line_delay; memcpy(s.acc_intr, o.acc_intr, sizeof s.acc_intr); memcpy(s.gyr_intr, o.gyr_intr, sizeof s.gyr_intr); }
+void load_state(Oracle& o, const State& s) {
+  // copy element-wise: residual blocks hold raw pointers into these vectors
+  std::copy(s.so3.begin(), s.so3.end(), o.so3.begin()); std::copy(s.r3.begin(), s.r3.end(), o.r3.begin());
+  std::copy(s.ba.begin(), s.ba.end(), o.ba.begin()); std::copy(s.bg.begin(), s.bg.end(), o.bg.begin());
+  memcpy(o.T_ic, s.T_ic, sizeof s.T_ic); memcpy(o.grav, s.grav, sizeof s.grav); o.line_delay = s.ld; memcpy(o.acc_intr, s.acc_intr, sizeof s.acc_intr); memcpy(o.gyr_intr, s.gyr_intr, sizeof s.gyr_intr);
+}
+
+// x <- Plus(x, delta) with delta in CANONICAL tangent order.  Returns squared ambient step norm and squared ambient x norm (before).
+void apply_plus(Oracle& o, const std::vector<double>& d, double& step_sq, double& x_sq) {
+  step_sq = 0; x_sq = 0;
+  auto acc = [&](double oldv, double newv) { step_sq += (newv - oldv) * (newv - oldv); x_sq += oldv * oldv; };
+  const int flags = o.cur_flags;
+  if (o.off_so3 >= 0) {
+    const int n = nknots(o.so3, 4);
+    for (int i = 0; i < n; ++i) {
+      double* q = &o.so3[4 * i];
+      V3<double> w{d[o.off_so3 + 3 * i], d[o.off_so3 + 3 * i + 1], d[o.off_so3 + 3 * i + 2]};
+      Q4<double> r = so3_mul(Q4<double>{q[0], q[1], q[2], q[3]}, so3_exp(w));   // LieLocalParameterization::Plus (ceres_local_param.h:84-92)
+      acc(q[0], r.x); acc(q[1], r.y); acc(q[2], r.z); acc(q[3], r.w);
+      q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
+    }
+    const int m = nknots(o.r3, 3);
+    for (int i = 0; i < 3 * m; ++i) { const double nv = o.r3[i] + d[o.off_r3 + i]; acc(o.r3[i], nv); o.r3[i] = nv; }
+  }
+  if (o.off_tic >= 0) {
+    SE3T<double> T{{o.T_ic[0], o.T_ic[1], o.T_ic[2], o.T_ic[3]}, {o.T_ic[4], o.T_ic[5], o.T_ic[6]}};
+    SE3T<double> r = se3_mul(T, se3_exp(&d[o.off_tic]));
+    const double nv[7] = {r.q.x, r.q.y, r.q.z, r.q.w, r.t.x, r.t.y, r.t.z};
+    for (int i = 0; i < 7; ++i) { acc(o.T_ic[i], nv[i]); o.T_ic[i] = nv[i]; }
+  }
+  if (o.off_g >= 0) for (int i = 0; i < 3; ++i) { const double nv = o.grav[i] + d[o.off_g + i]; acc(o.grav[i], nv); o.grav[i] = nv; }
+  if (o.off_ld >= 0) { const double nv = o.line_delay + d[o.off_ld]; acc(o.line_delay, nv); o.line_delay = nv; }
+  auto clampv = [](double v, double r) { return std::min(std::max(v, -r), r); };
+  if (o.off_ba >= 0) for (size_t i = 0; i < o.ba.size(); ++i) { const double nv = clampv(o.ba[i] + d[o.off_ba + i], o.max_ba); acc(o.ba[i], nv); o.ba[i] = nv; }
+  if (o.off_bg >= 0) for (size_t i = 0; i < o.bg.size(); ++i) { const double nv = clampv(o.bg[i] + d[o.off_bg + i], o.max_bg); acc(o.bg[i], nv); o.bg[i] = nv; }
+  if (flags & ICC_FLAG_IMU_INTRINSICS) {
+    int off = o.n_tan - 15;
+    for (int i = 0; i < 6; ++i) { const double nv = o.acc_intr[i] + d[off + i]; acc(o.acc_intr[i], nv); o.acc_intr[i] = nv; }
+    for (int i = 0; i < 9; ++i) { const double nv = o.gyr_intr[i] + d[off + 6 + i]; acc(o.gyr_intr[i], nv); o.gyr_intr[i] = nv; }
+  }
+}
+
+int total_residuals(const Oracle& o) { return o.n_res_vis + o.n_res_acc + o.n_res_gyr; }
+
+// impl.h:993-1072
+double mean_reproj_error(Oracle& o) {
+  double sum = 0; int num = 0;
+  Scratch s;
+  for (const auto& b : o.blocks) {
+    if (b.type != BLK_RS_VISION) continue;
+    int nc; eval_block(o, b, s, false, nc);
+    for (int i = 0; i < b.n_res / 2; ++i) {
+      const double rx = s.res[2 * i], ry = s.res[2 * i + 1];
+      if (rx != 0.0 && ry != 0.0) { sum += std::sqrt(rx * rx + ry * ry); ++num; }
+    }
+  }
+  return sum / num;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt, Ceres TrustRegionMinimizer semantics.
+// -------------------------------------------------------------------------------------------------------------
+struct LMResult { icc_summary sum; };
+
+void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_summary& S) {
+  using clk = std::chrono::steady_clock;
+  const auto t_start = clk::now();
+  memset(&S, 0, sizeof S);
+  const int n = o.n_tan, nres = total_residuals(o);
+  S.num_residuals = nres; S.num_tangent = n;
+  double t_jac = 0, t_lin = 0;
+  Normal ne;
+  double x_cost = 0;
+  auto eval_jac = [&]() { auto t0 = clk::now(); evaluate(o, &x_cost, nullptr, &ne, nullptr, nres); t_jac += std::chrono::duration<double>(clk::now() - t0).count(); ++S.jacobian_evaluations; };
+  eval_jac();
+  S.initial_cost = x_cost;
+  std::vector<double> scale(n, 1.0);   // solver order
+  auto diagH = [&](int i) { return i < ne.nk ? ne.band[size_t(i) * (ne.kd + 1)] : ne.C[size_t(i - ne.nk) * ne.nb + (i - ne.nk)]; };
+  if (o.opt.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(diagH(i)));
+  double radius = o.opt.initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  std::vector<double> diag(n, 0.0), D2(n), rhs(n), y(n), delta_canon(n);
+  int invalid = 0;
+  S.termination = 0;
+  auto grad_max = [&]() { double m = 0; for (double v : ne.g) m = std::max(m, std::fabs(v)); return m; };
+  if (check_convergence && grad_max() <= o.opt.gradient_tolerance) { S.termination = 3; max_iters = 0; }
+  Normal sc;
+  for (int it = 0; it < max_iters; ++it) {
+    ++S.iterations;
+    // scaled system  Hs = S H S, gs = S g
+    sc = ne;
+    for (int j = 0; j < ne.nk; ++j) { const int m = std::min(ne.kd, ne.nk - 1 - j); for (int i = 0; i <= m; ++i) sc.band[size_t(j) * (ne.kd + 1) + i] *= scale[j] * scale[j + i]; }
+    for (int b = 0; b < ne.nb; ++b) for (int j = 0; j < ne.nk; ++j) sc.E[size_t(b) * ne.nk + j] *= scale[ne.nk + b] * scale[j];
+    for (int b = 0; b < ne.nb; ++b) for (int c = 0; c < ne.nb; ++c) sc.C[size_t(b) * ne.nb + c] *= scale[ne.nk + b] * scale[ne.nk + c];
+    for (int i = 0; i < n; ++i) rhs[i] = -scale[i] * ne.g[i];
+    if (!reuse_diagonal) for (int i = 0; i < n; ++i) { const double dv = i < sc.nk ? sc.band[size_t(i) * (sc.kd + 1)] : sc.C[size_t(i - sc.nk) * sc.nb + (i - sc.nk)]; diag[i] = std::min(std::max(dv, o.opt.min_lm_diagonal), o.opt.max_lm_diagonal); }
+    for (int i = 0; i < n; ++i) D2[i] = diag[i] / radius;
+    auto t0 = clk::now();
+    const bool ok = arrowhead_solve(sc, D2, rhs, y);
+    t_lin += std::chrono::duration<double>(clk::now() - t0).count();
+    // model_cost_change = -y^T gs - 0.5 y^T Hs y
+    double model_change = 0;
+    if (ok) {
+      double yg = 0, yHy = 0;
+      for (int i = 0; i < n; ++i) yg += y[i] * (-rhs[i]);
+      for (int j = 0; j < sc.nk; ++j) { const int m = std::min(sc.kd, sc.nk - 1 - j); yHy += sc.band[size_t(j) * (sc.kd + 1)] * y[j] * y[j]; for (int i = 1; i <= m; ++i) yHy += 2.0 * sc.band[size_t(j) * (sc.kd + 1) + i] * y[j] * y[j + i]; }
+      for (int b = 0; b < sc.nb; ++b) { for (int j = 0; j < sc.nk; ++j) yHy += 2.0 * sc.E[size_t(b) * sc.nk + j] * y[sc.nk + b] * y[j]; for (int c = 0; c < sc.nb; ++c) yHy += sc.C[size_t(b) * sc.nb + c] * y[sc.nk + b] * y[sc.nk + c]; }
+      model_change = -yg - 0.5 * yHy;
+    }
+    if (!ok || !(model_change > 0.0)) {
+      if (++invalid >= o.opt.max_consecutive_invalid_steps) { S.termination = 4; break; }
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      continue;
+    }
+    invalid = 0;
+    for (int c = 0; c < n; ++c) delta_canon[c] = y[o.perm[c]] * scale[o.perm[c]];
+    State snap; save_state(o, snap);
+    double step_sq, x_sq; apply_plus(o, delta_canon, step_sq, x_sq);
+    double cand_cost; evaluate(o, &cand_cost, nullptr, nullptr, nullptr, nres); ++S.cost_evaluations;
+    const double step_norm = std::sqrt(step_sq), x_norm = std::sqrt(x_sq);
+    if (check_convergence && step_norm <= o.opt.parameter_tolerance * (x_norm + o.opt.parameter_tolerance)) { load_state(o, snap); S.termination = 2; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (check_convergence && std::fabs(cost_change) <= o.opt.function_tolerance * x_cost) { load_state(o, snap); S.termination = 1; break; }
+    const double rel_dec = cost_change / model_change;
+    if (rel_dec > o.opt.min_relative_decrease) {
+      ++S.successful_steps;
+      eval_jac();
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel_dec - 1.0, 3)); radius = std::min(o.opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0; reuse_diagonal = false;
+      if (check_convergence && grad_max() <= o.opt.gradient_tolerance) { S.termination = 3; break; }
+    } else {
+      load_state(o, snap);
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      if (radius < o.opt.min_trust_region_radius) { S.termination = 4; break; }
+    }
+  }
+  S.final_cost = x_cost;
+  S.seconds_jacobian = t_jac; S.seconds_linear_solve = t_lin;
+  S.seconds_total = std::chrono::duration<double>(clk::now() - t_start).count();
+}
+
+Oracle* O(void* h) { return reinterpret_cast<Oracle*>(h); }
+const Oracle* O(const void* h) { return reinterpret_cast<const Oracle*>(h); }
+
+}  // namespace
+
+// =================================================================================================================
+// C-ABI (icco_*), mirrors include/icc_b200.h
+// =================================================================================================================
+extern "C" {
+
+icc_status icco_create(void** out, int n_threads) {
+  Oracle* o = new Oracle();
+  o->n_threads = n_threads;
+  o->opt.function_tolerance = 1e-4; o->opt.parameter_tolerance = 1e-7; o->opt.gradient_tolerance = 1e-10;
+  o->opt.initial_trust_region_radius = 1e4; o->opt.max_trust_region_radius = 1e16; o->opt.min_trust_region_radius = 1e-32;
+  o->opt.min_relative_decrease = 1e-3; o->opt.min_lm_diagonal = 1e-6; o->opt.max_lm_diagonal = 1e32; o->opt.jacobi_scaling = 1;
+  o->opt.max_consecutive_invalid_steps = 5;
+  *out = o; return ICC_OK;
+}
+void icco_destroy(void* h) { delete O(h); }
+const char* icco_last_error(const void* h) { return O(h)->err.c_str(); }
+icc_status icco_set_solver_options(void* h, const icc_solver_options* p) { O(h)->opt = *p; return ICC_OK; }
+int icco_num_threads(const void* h) { return thread_count(*O(h)); }
+
+icc_status icco_set_camera(void* h, int model, const double* intr, int n, int w, int hgt) {
+  Oracle& o = *O(h);
+  if (camera_num_params(model) < 0 || n != camera_num_params(model)) { o.err = "bad camera model / intrinsic count"; return ICC_ERR_INVALID_ARGUMENT; }
+  o.model = model; o.n_intr = n; o.width = w; o.height = hgt; for (int i = 0; i < n; ++i) o.intr[i] = intr[i];
+  return ICC_OK;
+}
+icc_status icco_set_board_points(void* h, int n, const double* xyzw) { O(h)->points.assign(xyzw, xyzw + 4 * size_t(n)); return ICC_OK; }
+icc_status icco_set_frames(void* h, int nf, const double* t, const int32_t* off, const int32_t* ids, const double* uv, const double* q, const double* p) {
+  Oracle& o = *O(h);
+  o.frame_t.assign(t, t + nf); o.corner_off.assign(off, off + nf + 1);
+  const int nc = off[nf];
+  o.point_ids.assign(ids, ids + nc); o.uv.assign(uv, uv + 2 * size_t(nc)); o.q_wc.assign(q, q + 4 * size_t(nf)); o.p_wc.assign(p, p + 3 * size_t(nf));
+  return ICC_OK;
+}
+icc_status icco_set_imu(void* h, int n, const double* t, const double* a, const double* g) {
+  Oracle& o = *O(h); o.imu_t.assign(t, t + n); o.imu_acc.assign(a, a + 3 * size_t(n)); o.imu_gyr.assign(g, g + 3 * size_t(n)); return ICC_OK;
+}
+icc_status icco_set_shard(void* h, int rank, int world) { Oracle& o = *O(h); if (world < 1 || rank < 0 || rank >= world) { o.err = "bad shard"; return ICC_ERR_INVALID_ARGUMENT; } o.shard_rank = rank; o.shard_world = world; return ICC_OK; }
+
+icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
+  Oracle& o = *O(h);
+  if (o.model < 0 || o.frame_t.empty() || o.points.empty()) { o.err = "camera, board points and frames must be set first"; return ICC_ERR_STATE; }
+  o.ip = *ipp; o.dispatch_fov = ipp->dispatch_fov != 0;
+  const int nf = int(o.frame_t.size());
+  memcpy(o.T_ic, ipp->T_i_c_init, sizeof o.T_ic);
+  { Q4<double> q = qnormalized(Q4<double>{o.T_ic[0], o.T_ic[1], o.T_ic[2], o.T_ic[3]}); o.T_ic[0] = q.x; o.T_ic[1] = q.y; o.T_ic[2] = q.z; o.T_ic[3] = q.w; }
+  memcpy(o.acc_intr, ipp->acc_intrinsics, sizeof o.acc_intr); memcpy(o.gyr_intr, ipp->gyr_intrinsics, sizeof o.gyr_intr);
+  o.line_delay = ipp->init_line_delay_s;
+  // imu_camera_calibrator.cc:37-63
+  std::vector<double> cam_ts(o.frame_t); std::sort(cam_ts.begin(), cam_ts.end());
+  o.t0_s = cam_ts.front(); o.tend_s = cam_ts.back();
+  o.start_ns = int64_t(o.t0_s * S_TO_NS);
+  o.end_ns = int64_t(o.tend_s * S_TO_NS + 0.01 * S_TO_NS + ipp->init_line_delay_s);
+  o.dt_so3_ns = int64_t(ipp->dt_so3_s * S_TO_NS); o.dt_r3_ns = int64_t(ipp->dt_r3_s * S_TO_NS);
+  if (o.dt_so3_ns <= 0 || o.dt_r3_ns <= 0) { o.err = "knot spacing must be positive"; return ICC_ERR_INVALID_ARGUMENT; }
+  const int64_t duration = o.end_ns - o.start_ns;
+  const int nso3 = int(duration / o.dt_so3_ns) + SPLINE_N, nr3 = int(duration / o.dt_r3_ns) + SPLINE_N;   // impl.h:46-48
+  o.inv_so3_dt = S_TO_NS / double(o.dt_so3_ns); o.inv_r3_dt = S_TO_NS / double(o.dt_r3_ns);
+  // BatchInitSO3R3VisPoses (impl.h:278-339): time-sorted map of T_w_i = T_w_c * T_i_c^-1
+  std::map<double, int> by_time; for (int i = 0; i < nf; ++i) by_time[o.frame_t[i]] = i;
+  std::vector<double> t_vis; std::vector<double> q_vis, p_vis;
+  SE3T<double> Tic{{o.T_ic[0], o.T_ic[1], o.T_ic[2], o.T_ic[3]}, {o.T_ic[4], o.T_ic[5], o.T_ic[6]}};
+  SE3T<double> Tci = se3_inv(Tic);
+  for (auto& kv : by_time) {
+    const int i = kv.second;
+    SE3T<double> Twc{qnormalized(Q4<double>{o.q_wc[4 * i], o.q_wc[4 * i + 1], o.q_wc[4 * i + 2], o.q_wc[4 * i + 3]}), {o.p_wc[3 * i], o.p_wc[3 * i + 1], o.p_wc[3 * i + 2]}};
+    SE3T<double> Twi = se3_mul(Twc, Tci);
+    t_vis.push_back(kv.first);
+    q_vis.insert(q_vis.end(), {Twi.q.x, Twi.q.y, Twi.q.z, Twi.q.w}); p_vis.insert(p_vis.end(), {Twi.t.x, Twi.t.y, Twi.t.z});
+  }
+  const int nv = int(t_vis.size());
+  o.so3.assign(4 * size_t(nso3), 0.0); o.r3.assign(3 * size_t(nr3), 0.0);
+  for (int i = 0; i < nso3; ++i) {       // utils.cc:221-241 (knot times are zero-based: quirk q7)
+    const double t = double(i) * double(o.dt_so3_ns) * NS_TO_S;
+    double dist = 0; const size_t k = find_closest(t, t_vis, dist);
+    double q[4];
+    if (k < size_t(nv) - 1) { const double frac = dist / (t_vis[k + 1] - t_vis[k]); slerp(&q_vis[4 * k], &q_vis[4 * (k + 1)], frac, q); }
+    else memcpy(q, &q_vis[4 * k], sizeof q);
+    Q4<double> qn = qnormalized(Q4<double>{q[0], q[1], q[2], q[3]});
+    o.so3[4 * i] = qn.x; o.so3[4 * i + 1] = qn.y; o.so3[4 * i + 2] = qn.z; o.so3[4 * i + 3] = qn.w;
+  }
+  for (int i = 0; i < nr3; ++i) {        // utils.cc:243-261; the `nearest < t_new.size()` test is the reference's (quirk);
+    const double t = double(i) * double(o.dt_r3_ns) * NS_TO_S;   // reading one past the end (UB there) falls back to the nearest value here
+    double dist = 0; const size_t k = find_closest(t, t_vis, dist);
+    if (k < size_t(nr3) && k + 1 < size_t(nv)) {
+      const double frac = dist / (t_vis[k + 1] - t_vis[k]);
+      for (int d = 0; d < 3; ++d) o.r3[3 * i + d] = (1.0 - frac) * p_vis[3 * k + d] + frac * p_vis[3 * (k + 1) + d];
+    } else for (int d = 0; d < 3; ++d) o.r3[3 * i + d] = p_vis[3 * k + d];
+  }
+  // InitBiasSplines(…, 10e9, 10e9, 1.0, 0.1)  (imu_camera_calibrator.cc:80-85, impl.h:53-90)
+  o.dt_ba_ns = o.dt_bg_ns = int64_t(10 * 1e9); o.max_ba = 1.0; o.max_bg = 1e-1;
+  o.inv_ba_dt = 1.0 / double(o.dt_ba_ns); o.inv_bg_dt = 1.0 / double(o.dt_bg_ns);
+  const int nba = int(duration / o.dt_ba_ns) + BIAS_N, nbg = int(duration / o.dt_bg_ns) + BIAS_N;
+  o.ba.resize(3 * size_t(nba)); o.bg.resize(3 * size_t(nbg));
+  for (int i = 0; i < nba; ++i) for (int d = 0; d < 3; ++d) o.ba[3 * i + d] = ipp->acc_bias[d];
+  for (int i = 0; i < nbg; ++i) for (int d = 0; d < 3; ++d) o.bg[3 * i + d] = ipp->gyr_bias[d];
+
+  // ---- measurement wiring ---------------------------------------------------------------------------------
+  // Shards (icc_set_shard): time-sorted residual units are cut into `world` slices of equal scalar-residual count.
+  o.frames.clear(); o.blocks.clear(); o.imu_used.clear();
+  o.n_res_vis = o.n_res_acc = o.n_res_gyr = 0;
+  struct Unit { double t; int kind; int idx; int nres; };
+  std::vector<Unit> units;
+  const bool rolling = ipp->init_line_delay_s != 0.0;
+  std::vector<Frame> all_frames(nf);
+  for (int i = 0; i < nf; ++i) {
+    Frame& f = all_frames[i]; f.t_s = o.frame_t[i]; f.c0 = o.corner_off[i]; f.c1 = o.corner_off[i + 1];
+    const int64_t t_ns = int64_t(f.t_s * S_TO_NS);     // impl.h:541
+    f.ok = calc_times(t_ns, o.start_ns, o.dt_r3_ns, nr3, SPLINE_N, f.u_r3, f.s_r3) && calc_times(t_ns, o.start_ns, o.dt_so3_ns, nso3, SPLINE_N, f.u_so3, f.s_so3);
+    if (f.ok) units.push_back({f.t_s, 0, i, 2 * (f.c1 - f.c0)});
+  }
+  std::vector<ImuUsed> all_imu; std::map<double, int> imu_by_t;
+  for (size_t i = 0; i < o.imu_t.size(); ++i) {           // imu_camera_calibrator.cc:102-120
+    const double t = o.imu_t[i] + ipp->time_offset_imu_to_cam_s;
+    if (t < o.t0_s || t >= o.tend_s) continue;
+    ImuUsed m; m.t_s = t; for (int d = 0; d < 3; ++d) { m.acc[d] = o.imu_acc[3 * i + d]; m.gyr[d] = o.imu_gyr[3 * i + d]; }
+    imu_by_t[t] = int(all_imu.size()); all_imu.push_back(m);
+    units.push_back({t, 1, int(all_imu.size()) - 1, 6});
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.t < b.t; });
+  long total = 0; for (auto& u : units) total += u.nres;
+  long lo = total * o.shard_rank / o.shard_world, hi = total * (o.shard_rank + 1) / o.shard_world, run = 0;
+  int res_vis = 0;
+  std::vector<int> imu_sel;
+  std::vector<int> frame_sel;
+  for (auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; if (u.kind == 0) frame_sel.push_back(u.idx); else imu_sel.push_back(u.idx); }
+  std::sort(frame_sel.begin(), frame_sel.end());
+  // vision blocks (RS path; the GS path is Huber(0) => zero weight, quirk q3, so no block is created)
+  for (int fi : frame_sel) {
+    const Frame& f = all_frames[fi];
+    o.frames.push_back(f);
+    if (!rolling) continue;
+    Block b; b.type = BLK_RS_VISION; b.frame = int(o.frames.size()) - 1; b.n_res = 2 * (f.c1 - f.c0); b.res_off = res_vis; res_vis += b.n_res;
+    b.u_so3 = f.u_so3; b.u_r3 = f.u_r3; b.u_bias = 0;
+    for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.so3[4 * (f.s_so3 + i)], 4, LP_SO3, -1});
+    for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.r3[3 * (f.s_r3 + i)], 3, LP_NONE, -1});
+    b.params.push_back({o.T_ic, 7, LP_SE3, -1});
+    b.params.push_back({&o.line_delay, 1, LP_NONE, -1});
+    for (int c = f.c0; c < f.c1; ++c) b.params.push_back({&o.points[4 * size_t(o.point_ids[c])], 4, LP_NONE, -1});
+    o.blocks.push_back(std::move(b));
+  }
+  o.n_res_vis = res_vis;
+  // IMU blocks: accelerometer residuals first, then gyroscope residuals, both in time order
+  std::vector<Block> acc_blocks, gyr_blocks;
+  for (int mi : imu_sel) {
+    const ImuUsed& m = all_imu[mi];
+    o.imu_used.push_back(m);
+    const int ui = int(o.imu_used.size()) - 1;
+    const int64_t t_ns = int64_t(m.t_s * S_TO_NS);
+    double u_r3, u_so3, u_b; int64_t s_r3, s_so3, s_b;
+    if (calc_times(t_ns, o.start_ns, o.dt_r3_ns, nr3, SPLINE_N, u_r3, s_r3) && calc_times(t_ns, o.start_ns, o.dt_so3_ns, nso3, SPLINE_N, u_so3, s_so3) &&
+        calc_times(t_ns, o.start_ns, o.dt_ba_ns, nba, BIAS_N, u_b, s_b)) {
+      Block b; b.type = BLK_ACCEL; b.frame = ui; b.n_res = 3; b.u_so3 = u_so3; b.u_r3 = u_r3; b.u_bias = u_b;
+      for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.so3[4 * (s_so3 + i)], 4, LP_SO3, -1});
+      for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.r3[3 * (s_r3 + i)], 3, LP_NONE, -1});
+      for (int i = 0; i < BIAS_N; ++i) b.params.push_back({&o.ba[3 * (s_b + i)], 3, LP_NONE, -1});
+      b.params.push_back({o.grav, 3, LP_NONE, -1});
+      b.params.push_back({o.acc_intr, 6, LP_NONE, -1});
+      acc_blocks.push_back(std::move(b));
+    }
+    if (calc_times(t_ns, o.start_ns, o.dt_so3_ns, nso3, SPLINE_N, u_so3, s_so3) && calc_times(t_ns, o.start_ns, o.dt_bg_ns, nbg, BIAS_N, u_b, s_b)) {
+      Block b; b.type = BLK_GYRO; b.frame = ui; b.n_res = 3; b.u_so3 = u_so3; b.u_r3 = 0; b.u_bias = u_b;
+      for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.so3[4 * (s_so3 + i)], 4, LP_SO3, -1});
+      for (int i = 0; i < BIAS_N; ++i) b.params.push_back({&o.bg[3 * (s_b + i)], 3, LP_NONE, -1});
+      b.params.push_back({o.gyr_intr, 9, LP_NONE, -1});
+      gyr_blocks.push_back(std::move(b));
+    }
+  }
+  int off = res_vis;
+  for (auto& b : acc_blocks) { b.res_off = off; off += 3; o.blocks.push_back(std::move(b)); }
+  o.n_res_acc = 3 * int(acc_blocks.size());
+  for (auto& b : gyr_blocks) { b.res_off = off; off += 3; o.blocks.push_back(std::move(b)); }
+  o.n_res_gyr = 3 * int(gyr_blocks.size());
+
+  // InitializeGravity (imu_camera_calibrator.cc:130-161), incl. the integer-second truncation of the accelerometer time
+  bool ginit = false; double g0[3] = {0, 0, 9.81};
+  for (size_t j = 0; j < cam_ts.size() && !ginit; ++j) {
+    const int vi = by_time[cam_ts[j]];
+    SE3T<double> Twc{qnormalized(Q4<double>{o.q_wc[4 * vi], o.q_wc[4 * vi + 1], o.q_wc[4 * vi + 2], o.q_wc[4 * vi + 3]}), {o.p_wc[3 * vi], o.p_wc[3 * vi + 1], o.p_wc[3 * vi + 2]}};
+    SE3T<double> Tai = se3_mul(Twc, Tci);
+    for (size_t i = 0; i < o.imu_t.size(); ++i) {
+      const int64_t accl_t = int64_t(o.imu_t[i]);
+      if (std::fabs(double(accl_t) - cam_ts[j]) < 1. / 30.) {
+        V3<double> g = so3_act(Tai.q, V3<double>{o.imu_acc[3 * i], o.imu_acc[3 * i + 1], o.imu_acc[3 * i + 2]});
+        g0[0] = g.x; g0[1] = g.y; g0[2] = g.z; ginit = true; break;
+      }
+    }
+  }
+  memcpy(o.grav, g0, sizeof g0);
+  o.initialised = true; o.cur_flags = -1;
+  return ICC_OK;
+}
+
+icc_status icco_set_known_gravity_dir(void* h, const double g[3]) { memcpy(O(h)->grav, g, 3 * sizeof(double)); return ICC_OK; }
+
+icc_status icco_optimize(void* h, int max_iters, int flags, icc_summary* S) {
+  Oracle& o = *O(h);
+  if (!o.initialised) { o.err = "batch_init_spline first"; return ICC_ERR_STATE; }
+  if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
+  icc_summary s; lm_solve(o, max_iters, flags, true, s);
+  s.mean_reproj_error = o.n_res_vis ? mean_reproj_error(o) : 0.0;
+  if (S) *S = s;
+  return ICC_OK;
+}
+icc_status icco_lm_iterations(void* h, int n, int flags, icc_summary* S) {
+  Oracle& o = *O(h);
+  if (!o.initialised) { o.err = "batch_init_spline first"; return ICC_ERR_STATE; }
+  if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
+  icc_summary s; lm_solve(o, n, flags, false, s);
+  if (S) *S = s;
+  return ICC_OK;
+}
+
+icc_status icco_get_T_i_c(const void* h, double T[7]) { memcpy(T, O(h)->T_ic, 7 * sizeof(double)); return ICC_OK; }
+icc_status icco_get_gravity(const void* h, double g[3]) { memcpy(g, O(h)->grav, 3 * sizeof(double)); return ICC_OK; }
+icc_status icco_get_line_delay(const void* h, double* ld) { *ld = O(h)->line_delay; return ICC_OK; }
+icc_status icco_get_num_knots(const void* h, int* a, int* b, int* c, int* d) { const Oracle& o = *O(h); if (a) *a = nknots(o.so3, 4); if (b) *b = nknots(o.r3, 3); if (c) *c = nknots(o.ba, 3); if (d) *d = nknots(o.bg, 3); return ICC_OK; }
+icc_status icco_get_knots(const void* h, double* so3, double* r3, double* ba, double* bg) {
+  const Oracle& o = *O(h);
+  if (so3) std::copy(o.so3.begin(), o.so3.end(), so3); if (r3) std::copy(o.r3.begin(), o.r3.end(), r3);
+  if (ba) std::copy(o.ba.begin(), o.ba.end(), ba); if (bg) std::copy(o.bg.begin(), o.bg.end(), bg);
+  return ICC_OK;
+}
+icc_status icco_set_knots(void* h, const double* so3, const double* r3, const double* ba, const double* bg) {
+  Oracle& o = *O(h);
+  if (so3) std::copy(so3, so3 + o.so3.size(), o.so3.begin()); if (r3) std::copy(r3, r3 + o.r3.size(), o.r3.begin());
+  if (ba) std::copy(ba, ba + o.ba.size(), o.ba.begin()); if (bg) std::copy(bg, bg + o.bg.size(), o.bg.begin());
+  return ICC_OK;
+}
+icc_status icco_set_T_i_c(void* h, const double T[7]) { memcpy(O(h)->T_ic, T, 7 * sizeof(double)); return ICC_OK; }
+icc_status icco_set_line_delay(void* h, double ld) { O(h)->line_delay = ld; return ICC_OK; }
+icc_status icco_get_mean_reprojection_error(void* h, double* e) { Oracle& o = *O(h); if (!o.initialised) return ICC_ERR_STATE; *e = mean_reproj_error(o); return ICC_OK; }
+icc_status icco_get_num_imu_used(const void* h, int* n) { *n = int(O(h)->imu_used.size()); return ICC_OK; }
+icc_status icco_get_imu_used(const void* h, double* t, double* a, double* g) {
+  const Oracle& o = *O(h);
+  for (size_t i = 0; i < o.imu_used.size(); ++i) { if (t) t[i] = o.imu_used[i].t_s; for (int d = 0; d < 3; ++d) { if (a) a[3 * i + d] = o.imu_used[i].acc[d]; if (g) g[3 * i + d] = o.imu_used[i].gyr[d]; } }
+  return ICC_OK;
+}
+
+// impl.h:898-991,1180-1234
+icc_status icco_eval_trajectory(void* h, int n, const int64_t* t_ns, double* gyro, double* accel, double* bg, double* ba, double* pose_q, double* pose_p, int32_t* valid) {
+  Oracle& o = *O(h);
+  if (!o.initialised) return ICC_ERR_STATE;
+  const int nso3 = nknots(o.so3, 4), nr3 = nknots(o.r3, 3), nba = nknots(o.ba, 3), nbg = nknots(o.bg, 3);
+  for (int i = 0; i < n; ++i) {
+    double u_so3, u_r3, u_b; int64_t s_so3, s_r3, s_b;
+    const bool ok_so3 = calc_times(t_ns[i], o.start_ns, o.dt_so3_ns, nso3, SPLINE_N, u_so3, s_so3);
+    const bool ok_r3 = calc_times(t_ns[i], o.start_ns, o.dt_r3_ns, nr3, SPLINE_N, u_r3, s_r3);
+    if (valid) valid[i] = ok_so3 && ok_r3;
+    const double* ks[SPLINE_N]; const double* kr[SPLINE_N];
+    if (ok_so3) for (int k = 0; k < SPLINE_N; ++k) ks[k] = &o.so3[4 * (s_so3 + k)];
+    if (ok_r3) for (int k = 0; k < SPLINE_N; ++k) kr[k] = &o.r3[3 * (s_r3 + k)];
+    Q4<double> R{0, 0, 0, 1}; V3<double> w{0, 0, 0};
+    if (ok_so3) evaluate_lie_so3<SPLINE_N, double>(ks, u_so3, o.inv_so3_dt, &R, &w);
+    if (gyro && ok_so3) { gyro[3 * i] = w.x; gyro[3 * i + 1] = w.y; gyro[3 * i + 2] = w.z; }
+    if (accel && ok_so3 && ok_r3) {
+      V3<double> aw = evaluate_r3<SPLINE_N, 2, double>(kr, u_r3, o.inv_r3_dt);
+      V3<double> a = so3_act(so3_inv(R), V3<double>{aw.x + o.grav[0], aw.y + o.grav[1], aw.z + o.grav[2]});
+      accel[3 * i] = a.x; accel[3 * i + 1] = a.y; accel[3 * i + 2] = a.z;
+    }
+    if (pose_q && ok_so3 && ok_r3) { pose_q[4 * i] = R.x; pose_q[4 * i + 1] = R.y; pose_q[4 * i + 2] = R.z; pose_q[4 * i + 3] = R.w; }
+    if (pose_p && ok_so3 && ok_r3) { V3<double> p = evaluate_r3<SPLINE_N, 0, double>(kr, u_r3, o.inv_r3_dt); pose_p[3 * i] = p.x; pose_p[3 * i + 1] = p.y; pose_p[3 * i + 2] = p.z; }
+    if (bg) { double v[3] = {0, 0, 0}; if (calc_times(t_ns[i], o.start_ns, o.dt_bg_ns, nbg, BIAS_N, u_b, s_b)) { const double* kb[BIAS_N]; for (int k = 0; k < BIAS_N; ++k) kb[k] = &o.bg[3 * (s_b + k)]; V3<double> b = evaluate_r3<BIAS_N, 0, double>(kb, u_b, o.inv_bg_dt); v[0] = b.x; v[1] = b.y; v[2] = b.z; } for (int d = 0; d < 3; ++d) bg[3 * i + d] = v[d]; }
+    if (ba) { double v[3] = {0, 0, 0}; if (calc_times(t_ns[i], o.start_ns, o.dt_ba_ns, nba, BIAS_N, u_b, s_b)) { const double* kb[BIAS_N]; for (int k = 0; k < BIAS_N; ++k) kb[k] = &o.ba[3 * (s_b + k)]; V3<double> b = evaluate_r3<BIAS_N, 0, double>(kb, u_b, o.inv_ba_dt); v[0] = b.x; v[1] = b.y; v[2] = b.z; } for (int d = 0; d < 3; ++d) ba[3 * i + d] = v[d]; }
+  }
+  return ICC_OK;
+}
+
+icc_status icco_num_residuals(const void* h, int* v, int* a, int* g) { const Oracle& o = *O(h); if (v) *v = o.n_res_vis; if (a) *a = o.n_res_acc; if (g) *g = o.n_res_gyr; return ICC_OK; }
+icc_status icco_num_tangent(void* h, int flags, int* n) { Oracle& o = *O(h); if (!o.initialised) return ICC_ERR_STATE; if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED; *n = o.n_tan; return ICC_OK; }
+
+icc_status icco_evaluate(void* h, int flags, double* cost, double* residuals, double* gradient, double* hessian_dense) {
+  Oracle& o = *O(h);
+  if (!o.initialised) { o.err = "batch_init_spline first"; return ICC_ERR_STATE; }
+  if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
+  const int nres = total_residuals(o), n = o.n_tan;
+  if (!gradient && !hessian_dense) { evaluate(o, cost, residuals, nullptr, nullptr, nres); return ICC_OK; }
+  Normal ne; double c;
+  evaluate(o, &c, residuals, &ne, nullptr, nres);
+  if (cost) *cost = c;
+  if (gradient) for (int i = 0; i < n; ++i) gradient[i] = ne.g[o.perm[i]];
+  if (hessian_dense) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) hessian_dense[size_t(i) * n + j] = ne.get(o.perm[i], o.perm[j]);
+  return ICC_OK;
+}
+// Dense Jacobian (n_res x n_tan, row-major, canonical column order) — tests only.
+icc_status icco_jacobian_dense(void* h, int flags, double* J) {
+  Oracle& o = *O(h);
+  if (!o.initialised) return ICC_ERR_STATE;
+  if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
+  std::vector<double> Jd; double c;
+  evaluate(o, &c, nullptr, nullptr, &Jd, total_residuals(o));
+  std::copy(Jd.begin(), Jd.end(), J);
+  return ICC_OK;
+}
+// Time `n` Jacobian (or cost-only) evaluations; seconds per evaluation on this host.
+icc_status icco_time_evaluations(void* h, int n, int flags, int with_jacobian, double* ms_per_eval) {
+  Oracle& o = *O(h);
+  if (!o.initialised) return ICC_ERR_STATE;
+  if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
+  const int nres = total_residuals(o);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n; ++i) { Normal ne; double c; evaluate(o, &c, nullptr, with_jacobian ? &ne : nullptr, nullptr, nres); }
+  *ms_per_eval = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / std::max(n, 1);
+  return ICC_OK;
+}
+// Known-answer access to the blending matrices.
+void icco_blending_matrix(int N, int cumulative, double* out) {
+  if (N == 6) { const auto& B = blend<6>(); for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i * 6 + j] = cumulative ? B.Mc[i][j] : B.M[i][j]; }
+  if (N == 3) { const auto& B = blend<3>(); for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out[i * 3 + j] = cumulative ? B.Mc[i][j] : B.M[i][j]; }
+}
+void icco_base_coefficients(int N, double* out) {
+  if (N == 6) { const auto& B = blend<6>(); for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i * 6 + j] = B.base[i][j]; }
+}
+// Camera projection (double) for generator cross-checks.
+int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }
+
+}  // extern "C"

@@ -1,0 +1,765 @@
+// C-ABI + host logic of the B200 calibration solver (see include/icc_b200.h for the boundary contract).
+//
+// Host side mirrors, in its own structure, what the reference does on one thread before/around ceres::Solve:
+//   ImuCameraCalibrator::BatchInitSpline / InitializeGravity / Optimize   src/core/imu_camera_calibrator.cc:21-168
+//   SplineTrajectoryEstimator::SetTimes / InitBiasSplines / BatchInitSO3R3VisPoses / Add*Measurement / CalcTimes /
+//   SetFixedParams / Optimize / getters       include/OpenCameraCalibrator/core/spline_trajectory_estimator.impl.h
+//   InterpolateQuaternions / InterpolateVector3d                           src/utils/utils.cc:194-261
+// Everything numerical per LM iteration runs on the GPU (icc_eval.cu, icc_solver.cu); the host only sequences launches
+// and applies the trust-region accept/reject logic to a few scalars read back per iteration.  There is no CPU fallback.
+#include "../../include/icc_b200.h"
+#include "icc_camera.cuh"
+#include "icc_kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace icc;
+
+namespace {
+
+constexpr double S_TO_NS = 1e9, NS_TO_S = 1e-9;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) { release(); n = count; if (!count) return cudaSuccess; return cudaMalloc(&p, count * sizeof(T)); }
+  cudaError_t upload(const std::vector<T>& v) { cudaError_t e = alloc(v.size()); if (e != cudaSuccess || v.empty()) return e; return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice); }
+};
+
+struct StateBufs {
+  DevBuf<double4> so3, r3, ba, bg; DevBuf<double> glob;
+  DeviceState view() const { DeviceState s; s.so3 = so3.p; s.r3 = r3.p; s.ba = ba.p; s.bg = bg.p; s.glob = glob.p; return s; }
+};
+
+struct FrameHost { double t_s; int c0, c1; int s_so3, s_r3; double u_so3, u_r3; };
+
+}  // namespace
+
+struct icc_handle {
+  std::string err = "";
+  int device = -1;
+  icc_solver_options opt;
+  // ---- raw inputs -------------------------------------------------------------------------------------------
+  int model = -1, n_intr = 0, width = 0, height = 0; double intr[10] = {0};
+  std::vector<double> points;
+  std::vector<double> frame_t; std::vector<int> corner_off, point_ids; std::vector<double> uv, q_wc, p_wc;
+  std::vector<double> imu_t, imu_acc, imu_gyr;
+  int shard_rank = 0, shard_world = 1;
+  icc_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
+  // ---- assembled problem (host) -----------------------------------------------------------------------------
+  bool initialised = false;
+  icc_init_params ip;
+  int64_t dt_so3_ns = 0, dt_r3_ns = 0, dt_ba_ns = 0, dt_bg_ns = 0, start_ns = 0, end_ns = 0;
+  double t0_s = 0, tend_s = 0, max_ba = 1.0, max_bg = 0.1;
+  std::vector<double> so3, r3, ba, bg;       // host mirror of the state (4/3/3/3 doubles per knot)
+  double glob[G_COUNT] = {0};
+  std::vector<FrameHost> frames;             // frames in the problem (this shard)
+  std::vector<double> used_uv; std::vector<int> used_pid;
+  std::vector<double> imu_used_t, imu_used_acc, imu_used_gyr; std::vector<int64_t> imu_used_st;
+  std::vector<ImuCell> cells;
+  int dropped_frames = 0, dropped_imu = 0;
+  // ---- device ---------------------------------------------------------------------------------------------------
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  StateBufs st[2]; int cur = 0;
+  DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
+  DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
+  DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
+  DevBuf<double> d_ne, d_scale, d_ws, d_delta, d_scal, d_res;
+  DeviceProblem P;
+  bool state_dirty_host = false;   // device state newer than host mirror
+  // ---- active set ------------------------------------------------------------------------------------------------
+  int cur_flags = -1;
+  std::vector<int> so3_col, r3_col, ba_col, bg_col;   // solver index of first dim or -1
+  int col_tic = -1, col_g = -1, col_ld = -1;
+  int n_tan = 0;
+  std::vector<int> perm;           // canonical tangent index -> solver index
+  int launches_at_start = 0;
+};
+
+namespace {
+
+icc_status fail(icc_handle* h, icc_status s, const std::string& m) { if (h) h->err = m; return s; }
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, ICC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+#define NEED_DEVICE() do { if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device bound to this handle (host-only handle): compute entry points are unavailable"); } while (0)
+
+Q4 qn(const double* q) { return qnormalized(q4(q[0], q[1], q[2], q[3])); }
+
+// CalcTimes (impl.h:763-788)
+bool calc_times(int64_t sensor_ns, int64_t start_ns, int64_t dt_ns, size_t nr_knots, int N, double& u, int64_t& s) {
+  const int64_t st = sensor_ns - start_ns;
+  if (st < 0) { u = 0.0; return false; }
+  s = st / dt_ns;
+  if (s < 0) return false;
+  if (size_t(s + N) > nr_knots) return false;
+  u = double(st % dt_ns) / double(dt_ns);
+  return true;
+}
+
+size_t nearest_index(double t, const std::vector<double>& ts, double& dist_out) {   // utils.cc:194-212
+  double best = 1.7976931348623157e308; size_t idx = 0;
+  for (size_t i = 0; i < ts.size(); ++i) { const double d = std::fabs(t - ts[i]); if (d < best) { best = d; dist_out = d; idx = i; if (d == 0.0) break; } }
+  return idx;
+}
+
+void quat_slerp(const double* a, const double* b, double t, double* o) {   // Eigen::Quaternion::slerp semantics (utils.cc:234)
+  const double thresh = 1.0 - 2.220446049250313e-16;
+  const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3], ad = std::fabs(d);
+  double s0, s1;
+  if (ad >= thresh) { s0 = 1.0 - t; s1 = t; }
+  else { const double th = std::acos(ad), sth = std::sin(th); s0 = std::sin((1.0 - t) * th) / sth; s1 = std::sin(t * th) / sth; }
+  if (d < 0) s1 = -s1;
+  for (int i = 0; i < 4; ++i) o[i] = s0 * a[i] + s1 * b[i];
+}
+
+struct Pose { Q4 q; V3 t; };
+Pose pose_mul(const Pose& a, const Pose& b) { return {qnormalized(qmul(a.q, b.q)), a.t + qrot(a.q, b.t)}; }
+Pose pose_inv(const Pose& a) { const Q4 qi = qnormalized(qconj(a.q)); return {qi, qrot(qi, -a.t)}; }
+
+std::vector<double4> pad4(const std::vector<double>& v, int dim) {
+  const size_t n = v.size() / dim; std::vector<double4> o(n);
+  for (size_t i = 0; i < n; ++i) o[i] = make_double4(v[dim * i], v[dim * i + 1], v[dim * i + 2], dim == 4 ? v[dim * i + 3] : 0.0);
+  return o;
+}
+
+icc_status upload_state(icc_handle* h, int which) {
+  StateBufs& s = h->st[which];
+  CU(s.so3.upload(pad4(h->so3, 4))); CU(s.r3.upload(pad4(h->r3, 3))); CU(s.ba.upload(pad4(h->ba, 3))); CU(s.bg.upload(pad4(h->bg, 3)));
+  std::vector<double> g(h->glob, h->glob + G_COUNT);
+  CU(s.glob.upload(g));
+  return ICC_OK;
+}
+
+icc_status sync_state_to_host(icc_handle* h) {
+  if (!h->state_dirty_host || h->device < 0) return ICC_OK;
+  const StateBufs& s = h->st[h->cur];
+  auto pull = [&](const DevBuf<double4>& d, std::vector<double>& v, int dim) -> cudaError_t {
+    std::vector<double4> tmp(d.n);
+    if (d.n) { cudaError_t e = cudaMemcpy(tmp.data(), d.p, d.n * sizeof(double4), cudaMemcpyDeviceToHost); if (e != cudaSuccess) return e; }
+    for (size_t i = 0; i < d.n; ++i) { v[dim * i] = tmp[i].x; v[dim * i + 1] = tmp[i].y; v[dim * i + 2] = tmp[i].z; if (dim == 4) v[dim * i + 3] = tmp[i].w; }
+    return cudaSuccess;
+  };
+  CU(cudaStreamSynchronize(h->stream));
+  CU(pull(s.so3, h->so3, 4)); CU(pull(s.r3, h->r3, 3)); CU(pull(s.ba, h->ba, 3)); CU(pull(s.bg, h->bg, 3));
+  CU(cudaMemcpy(h->glob, s.glob.p, G_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+  h->state_dirty_host = false;
+  return ICC_OK;
+}
+
+icc_status push_state_to_device(icc_handle* h) {
+  if (h->device < 0 || !h->initialised) return ICC_OK;
+  icc_status s = upload_state(h, h->cur);
+  h->state_dirty_host = false;
+  return s;
+}
+
+// Active set (SetFixedParams, impl.h:92-252) -> column maps in SOLVER order: spline knots sorted by knot time (SO3 before
+// R3 on ties) form the banded part; T_i_c, gravity, line delay and bias knots form the border.
+icc_status configure(icc_handle* h, int flags) {
+  if (flags & ICC_FLAG_POINTS) return fail(h, ICC_ERR_UNSUPPORTED, "POINTS is never set by the hot CLI and is not supported");
+  if (flags & ICC_FLAG_IMU_INTRINSICS) return fail(h, ICC_ERR_UNSUPPORTED, "IMU_INTRINSICS is never set by the hot CLI and is not supported");
+  if (h->cur_flags == flags) return ICC_OK;
+  const int nso3 = (int)h->so3.size() / 4, nr3 = (int)h->r3.size() / 3, nba = (int)h->ba.size() / 3, nbg = (int)h->bg.size() / 3;
+  const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
+  const bool ld = (flags & ICC_FLAG_CAM_LINE_DELAY) && h->ip.init_line_delay_s != 0.0;
+  const bool ab = flags & (ICC_FLAG_ACC_BIAS | ICC_FLAG_IMU_BIASES), gb = flags & (ICC_FLAG_GYR_BIAS | ICC_FLAG_IMU_BIASES);
+  // canonical offsets
+  int n = 0;
+  const int c_so3 = spline ? n : -1; if (spline) n += 3 * nso3;
+  const int c_r3 = spline ? n : -1; if (spline) n += 3 * nr3;
+  const int c_tic = tic ? n : -1; if (tic) n += 6;
+  const int c_g = grav ? n : -1; if (grav) n += 3;
+  const int c_ld = ld ? n : -1; if (ld) n += 1;
+  const int c_ba = ab ? n : -1; if (ab) n += 3 * nba;
+  const int c_bg = gb ? n : -1; if (gb) n += 3 * nbg;
+  h->n_tan = n;
+  h->so3_col.assign(nso3, -1); h->r3_col.assign(nr3, -1); h->ba_col.assign(nba, -1); h->bg_col.assign(nbg, -1);
+  int pos = 0;
+  if (spline) {
+    int i = 0, j = 0;
+    while (i < nso3 || j < nr3) {
+      const bool take_so3 = j >= nr3 || (i < nso3 && int64_t(i) * h->dt_so3_ns <= int64_t(j) * h->dt_r3_ns);
+      if (take_so3) h->so3_col[i++] = pos; else h->r3_col[j++] = pos;
+      pos += 3;
+    }
+  }
+  const int nk = pos;
+  h->col_tic = tic ? pos : -1; if (tic) pos += 6;
+  h->col_g = grav ? pos : -1; if (grav) pos += 3;
+  h->col_ld = ld ? pos : -1; if (ld) pos += 1;
+  if (ab) for (int k = 0; k < nba; ++k) { h->ba_col[k] = pos; pos += 3; }
+  if (gb) for (int k = 0; k < nbg; ++k) { h->bg_col[k] = pos; pos += 3; }
+  const int nb = pos - nk;
+  h->perm.assign(n, -1);
+  if (spline) { for (int k = 0; k < nso3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_so3 + 3 * k + d] = h->so3_col[k] + d; for (int k = 0; k < nr3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_r3 + 3 * k + d] = h->r3_col[k] + d; }
+  if (tic) for (int d = 0; d < 6; ++d) h->perm[c_tic + d] = h->col_tic + d;
+  if (grav) for (int d = 0; d < 3; ++d) h->perm[c_g + d] = h->col_g + d;
+  if (ld) h->perm[c_ld] = h->col_ld;
+  if (ab) for (int k = 0; k < nba; ++k) for (int d = 0; d < 3; ++d) h->perm[c_ba + 3 * k + d] = h->ba_col[k] + d;
+  if (gb) for (int k = 0; k < nbg; ++k) for (int d = 0; d < 3; ++d) h->perm[c_bg + 3 * k + d] = h->bg_col[k] + d;
+  // half bandwidth: widest knot window touched by one residual block
+  int kd = 0;
+  if (spline) {
+    auto span = [&](int s_so3, int s_r3, bool use_r3) {
+      int lo = h->so3_col[s_so3], hi = h->so3_col[s_so3 + SPLINE_N - 1] + 2;
+      if (use_r3) { lo = std::min(lo, h->r3_col[s_r3]); hi = std::max(hi, h->r3_col[s_r3 + SPLINE_N - 1] + 2); }
+      kd = std::max(kd, hi - lo);
+    };
+    if (h->ip.init_line_delay_s != 0.0) for (const auto& f : h->frames) span(f.s_so3, f.s_r3, true);
+    for (const auto& c : h->cells) span(c.s_so3, c.s_r3, true);
+    if (h->shard_world > 1) {   // every rank must agree on the layout: use the global worst case of the time-sorted order
+      for (int s = 0; s + SPLINE_N <= nso3; ++s) { const int64_t t = int64_t(s) * h->dt_so3_ns; const int sr = (int)std::min<int64_t>(t / h->dt_r3_ns, nr3 - SPLINE_N); span(s, sr, true); }
+      for (int s = 0; s + SPLINE_N <= nr3; ++s) { const int64_t t = int64_t(s) * h->dt_r3_ns; const int ss = (int)std::min<int64_t>(t / h->dt_so3_ns, nso3 - SPLINE_N); span(ss, s, true); }
+    }
+  }
+  if (kd > 255) return fail(h, ICC_ERR_UNSUPPORTED, "knot-spacing ratio produces a half bandwidth > 255");
+  h->cur_flags = flags;
+  DeviceProblem& P = h->P;
+  P.nk = nk; P.nb = nb; P.kd = kd; P.ldb = kd + 1;
+  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.bias_active = (ab || gb) ? 1 : 0;
+  P.ne_off_E = (int64_t)nk * P.ldb; P.ne_off_C = P.ne_off_E + (int64_t)nk * nb; P.ne_off_g = P.ne_off_C + (int64_t)nb * nb;
+  P.ne_off_cost = P.ne_off_g + nk + nb; P.ne_size = (P.ne_off_cost + 1 + 3) / 4 * 4;
+  if (h->device >= 0) {
+    CU(h->d_so3_col.upload(h->so3_col)); CU(h->d_r3_col.upload(h->r3_col)); CU(h->d_ba_col.upload(h->ba_col)); CU(h->d_bg_col.upload(h->bg_col));
+    P.so3_col = h->d_so3_col.p; P.r3_col = h->d_r3_col.p; P.ba_col = h->d_ba_col.p; P.bg_col = h->d_bg_col.p;
+    CU(h->d_ne.alloc((size_t)P.ne_size)); P.ne = h->d_ne.p;
+    CU(h->d_scale.alloc((size_t)std::max(1, nk + nb))); CU(h->d_delta.alloc((size_t)std::max(1, nk + nb)));
+    CU(h->d_ws.alloc(solve_workspace_doubles(P)));
+  }
+  return ICC_OK;
+}
+
+// One Jacobian evaluation on the current state: zero the packed normal equations, run the kernels, cross-rank reduce.
+icc_status eval_jacobian(icc_handle* h, const DeviceState& S, double* residuals_dev) {
+  CU(cudaMemsetAsync(h->P.ne, 0, (size_t)h->P.ne_size * sizeof(double), h->stream));
+  if (launch_eval(h->P, S, true, nullptr, residuals_dev, nullptr, h->stream)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
+  if (h->allreduce && h->shard_world > 1) { h->allreduce(h->P.ne, h->P.ne_size, (void*)h->stream, h->allreduce_user); }
+  return ICC_OK;
+}
+icc_status eval_cost(icc_handle* h, const DeviceState& S, double* cost_dev, double* residuals_dev, double* reproj_dev) {
+  if (launch_eval(h->P, S, false, cost_dev, residuals_dev, reproj_dev, h->stream)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
+  if (h->allreduce && h->shard_world > 1 && cost_dev) { h->allreduce(cost_dev, 1, (void*)h->stream, h->allreduce_user); }
+  return ICC_OK;
+}
+
+icc_status mean_reproj(icc_handle* h, double* out) {
+  // GetMeanReprojectionError (impl.h:993-1072): RS functor on every view, values only
+  if (h->P.n_vwork == 0) { *out = 0.0; return ICC_OK; }
+  CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
+  DeviceProblem P = h->P; P.n_iwork = 0; P.rolling = 1;
+  if (launch_eval(P, h->st[h->cur].view(), false, h->d_scal.p + SC_CAND_COST, nullptr, h->d_scal.p + SC_REPROJ_SUM, h->stream)) return fail(h, ICC_ERR_CUDA, "eval launch failed");
+  if (h->allreduce && h->shard_world > 1) h->allreduce(h->d_scal.p + SC_REPROJ_SUM, 2, (void*)h->stream, h->allreduce_user);
+  double sc[SC_COUNT];
+  CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *out = sc[SC_REPROJ_SUM] / sc[SC_REPROJ_CNT];
+  return ICC_OK;
+}
+
+// Levenberg-Marquardt with Ceres TrustRegionMinimizer semantics (options: impl.h:254-266 + Ceres 2.1 defaults).
+icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergence, icc_summary* out) {
+  using clk = std::chrono::steady_clock;
+  const auto t_start = clk::now();
+  icc_status rc = configure(h, flags);
+  if (rc != ICC_OK) return rc;
+  icc_summary S; memset(&S, 0, sizeof S);
+  const DeviceProblem& P = h->P;
+  const int n = P.nk + P.nb;
+  S.num_residuals = P.n_res_vis + P.n_res_acc + P.n_res_gyr; S.num_tangent = n;
+  const int launches0 = kernel_launch_count();
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); ev.push_back(e); return (int)ev.size() - 1; };
+  std::vector<std::pair<int, int>> jac_spans, lin_spans;
+  double sc[SC_COUNT];
+  double x_cost = 0.0;
+  auto jac = [&]() -> icc_status {
+    const int a = mark();
+    icc_status r = eval_jacobian(h, h->st[h->cur].view(), nullptr);
+    if (r != ICC_OK) return r;
+    const int b = mark(); jac_spans.push_back({a, b});
+    ++S.jacobian_evaluations;
+    return ICC_OK;
+  };
+  auto read_cost_and_grad = [&](bool compute_scale) -> icc_status {
+    CU(cudaMemsetAsync(h->d_scal.p + SC_GRAD_MAX, 0, sizeof(double), h->stream));
+    launch_compute_scale(P, compute_scale ? h->d_scale.p : nullptr, h->opt.jacobi_scaling, h->d_scal.p, h->stream);
+    double c;
+    CU(cudaMemcpyAsync(&c, P.ne + P.ne_off_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    x_cost = c;
+    return ICC_OK;
+  };
+  if (n == 0) { if (out) *out = S; return ICC_OK; }
+  rc = jac(); if (rc != ICC_OK) return rc;
+  rc = read_cost_and_grad(true); if (rc != ICC_OK) return rc;
+  S.initial_cost = x_cost;
+  if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost");
+  double radius = h->opt.initial_trust_region_radius, decrease_factor = 2.0;
+  int invalid = 0;
+  S.termination = 0;
+  if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; max_iters = 0; }
+  for (int it = 0; it < max_iters; ++it) {
+    ++S.iterations;
+    CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
+    SolveParams sp; sp.radius = radius; sp.min_diag = h->opt.min_lm_diagonal; sp.max_diag = h->opt.max_lm_diagonal; sp.jacobi_scaling = h->opt.jacobi_scaling;
+    const int a = mark();
+    launch_solve(P, h->d_scale.p, sp, h->d_ws.p, h->d_delta.p, h->d_scal.p, h->stream);
+    const int b = mark(); lin_spans.push_back({a, b});
+    const int cand = 1 - h->cur;
+    launch_update(P, h->st[h->cur].view(), h->st[cand].view(), h->d_delta.p, h->max_ba, h->max_bg, h->d_scal.p, h->stream);
+    rc = eval_cost(h, h->st[cand].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); if (rc != ICC_OK) return rc;
+    ++S.cost_evaluations;
+    CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const double model_change = sc[SC_MODEL_CHANGE];
+    if (sc[SC_OK] == 0.0 || !(model_change > 0.0)) {          // invalid step (HandleInvalidStep)
+      if (++invalid >= h->opt.max_consecutive_invalid_steps) { S.termination = 4; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      continue;
+    }
+    invalid = 0;
+    const double step_norm = std::sqrt(sc[SC_STEP_SQ]), x_norm = std::sqrt(sc[SC_X_SQ]);
+    double cand_cost = sc[SC_CAND_COST];
+    if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+    if (check_convergence && step_norm <= h->opt.parameter_tolerance * (x_norm + h->opt.parameter_tolerance)) { S.termination = 2; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (check_convergence && std::fabs(cost_change) <= h->opt.function_tolerance * x_cost) { S.termination = 1; break; }
+    const double rel = cost_change / model_change;
+    if (rel > h->opt.min_relative_decrease) {               // HandleSuccessfulStep
+      ++S.successful_steps;
+      h->cur = cand; h->state_dirty_host = true;
+      rc = jac(); if (rc != ICC_OK) return rc;
+      rc = read_cost_and_grad(false); if (rc != ICC_OK) return rc;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(h->opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; break; }
+    } else {                                                  // StepRejected
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      if (radius < h->opt.min_trust_region_radius) { S.termination = 4; break; }
+    }
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  S.final_cost = x_cost;
+  auto span_s = [&](const std::vector<std::pair<int, int>>& v) { double tot = 0; for (auto& p : v) { float ms = 0; cudaEventElapsedTime(&ms, ev[p.first], ev[p.second]); tot += ms; } return tot * 1e-3; };
+  S.seconds_jacobian = span_s(jac_spans); S.seconds_linear_solve = span_s(lin_spans);
+  for (auto e : ev) cudaEventDestroy(e);
+  S.gpu_launches = kernel_launch_count() - launches0;
+  S.seconds_total = std::chrono::duration<double>(clk::now() - t_start).count();
+  if (out) *out = S;
+  return ICC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* icc_version(void) { return "icc_b200 0.1 (sm_100a, fp64)"; }
+
+void icc_default_solver_options(icc_solver_options* o) {
+  o->function_tolerance = 1e-4; o->parameter_tolerance = 1e-7; o->gradient_tolerance = 1e-10;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
+}
+
+// device_ordinal >= 0 binds a GPU (required for every compute entry point).  device_ordinal == -1 creates a host-only
+// handle whose sole use is inspecting the problem ASSEMBLY (knot initialisation, counts) without a GPU; it cannot compute.
+icc_status icc_create(icc_handle** out, int device_ordinal) {
+  if (!out) return ICC_ERR_INVALID_ARGUMENT;
+  icc_handle* h = new icc_handle();
+  icc_default_solver_options(&h->opt);
+  memset(&h->P, 0, sizeof h->P);
+  *out = h;
+  if (device_ordinal < 0) { h->device = -1; return ICC_OK; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device_ordinal >= count) {
+    h->err = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range") + "); this library has no CPU fallback";
+    return ICC_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) { h->err = "cudaSetDevice failed"; return ICC_ERR_NO_DEVICE; }
+  h->device = device_ordinal;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; h->device = -1; return ICC_ERR_CUDA; }
+  if (h->d_scal.alloc(SC_COUNT) != cudaSuccess) { h->err = "cudaMalloc failed"; return ICC_ERR_CUDA; }
+  return ICC_OK;
+}
+void icc_destroy(icc_handle* h) { if (!h) return; if (h->device >= 0) { cudaSetDevice(h->device); if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); } } delete h; }
+const char* icc_last_error(const icc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+icc_status icc_set_solver_options(icc_handle* h, const icc_solver_options* o) { if (!h || !o) return ICC_ERR_INVALID_ARGUMENT; h->opt = *o; return ICC_OK; }
+
+icc_status icc_set_camera(icc_handle* h, int model, const double* intr, int n, int w, int hgt) {
+  if (!h || !intr) return ICC_ERR_INVALID_ARGUMENT;
+  if (camera_num_params(model) < 0 || n != camera_num_params(model)) return fail(h, ICC_ERR_INVALID_ARGUMENT, "unknown camera model or wrong intrinsic count");
+  h->model = model; h->n_intr = n; h->width = w; h->height = hgt; for (int i = 0; i < n; ++i) h->intr[i] = intr[i];
+  return ICC_OK;
+}
+icc_status icc_set_board_points(icc_handle* h, int n, const double* xyzw) { if (!h || n <= 0 || !xyzw) return ICC_ERR_INVALID_ARGUMENT; h->points.assign(xyzw, xyzw + 4 * (size_t)n); return ICC_OK; }
+icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t* off, const int32_t* ids, const double* uv, const double* q, const double* p) {
+  if (!h || nf <= 0 || !t || !off || !ids || !uv || !q || !p) return ICC_ERR_INVALID_ARGUMENT;
+  const int nc = off[nf];
+  for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
+  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->point_ids.assign(ids, ids + nc); h->uv.assign(uv, uv + 2 * (size_t)nc);
+  h->q_wc.assign(q, q + 4 * (size_t)nf); h->p_wc.assign(p, p + 3 * (size_t)nf);
+  return ICC_OK;
+}
+icc_status icc_set_imu(icc_handle* h, int n, const double* t, const double* a, const double* g) {
+  if (!h || n < 0 || (n > 0 && (!t || !a || !g))) return ICC_ERR_INVALID_ARGUMENT;
+  h->imu_t.assign(t, t + n); h->imu_acc.assign(a, a + 3 * (size_t)n); h->imu_gyr.assign(g, g + 3 * (size_t)n);
+  return ICC_OK;
+}
+icc_status icc_set_shard(icc_handle* h, int rank, int world) { if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, ICC_ERR_INVALID_ARGUMENT, "bad shard"); h->shard_rank = rank; h->shard_world = world; return ICC_OK; }
+icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user) { if (!h) return ICC_ERR_INVALID_ARGUMENT; h->allreduce = fn; h->allreduce_user = user; return ICC_OK; }
+
+icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
+  if (!h || !ipp) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->model < 0 || h->frame_t.empty() || h->points.empty()) return fail(h, ICC_ERR_STATE, "camera, board points and frames must be set before batch_init_spline");
+  for (int id : h->point_ids) if (id < 0 || (size_t)id >= h->points.size() / 4) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner references an unknown board point");
+  h->ip = *ipp;
+  const int nf = (int)h->frame_t.size();
+  // T_i_c, IMU intrinsics, line delay (imu_camera_calibrator.cc:30-47)
+  { const Q4 q = qn(ipp->T_i_c_init); h->glob[G_TIC + 0] = q.x; h->glob[G_TIC + 1] = q.y; h->glob[G_TIC + 2] = q.z; h->glob[G_TIC + 3] = q.w; for (int i = 4; i < 7; ++i) h->glob[G_TIC + i] = ipp->T_i_c_init[i]; }
+  for (int i = 0; i < 6; ++i) h->glob[G_ACC_INTR + i] = ipp->acc_intrinsics[i];
+  for (int i = 0; i < 9; ++i) h->glob[G_GYR_INTR + i] = ipp->gyr_intrinsics[i];
+  h->glob[G_LD] = ipp->init_line_delay_s;
+  // spline time range and knot counts (imu_camera_calibrator.cc:49-72, impl.h:37-51)
+  std::vector<double> cam_ts(h->frame_t); std::sort(cam_ts.begin(), cam_ts.end());
+  h->t0_s = cam_ts.front(); h->tend_s = cam_ts.back();
+  h->start_ns = (int64_t)(h->t0_s * S_TO_NS);
+  h->end_ns = (int64_t)(h->tend_s * S_TO_NS + 0.01 * S_TO_NS + ipp->init_line_delay_s);
+  h->dt_so3_ns = (int64_t)(ipp->dt_so3_s * S_TO_NS); h->dt_r3_ns = (int64_t)(ipp->dt_r3_s * S_TO_NS);
+  if (h->dt_so3_ns <= 0 || h->dt_r3_ns <= 0) return fail(h, ICC_ERR_INVALID_ARGUMENT, "knot spacing must be positive");
+  const int64_t duration = h->end_ns - h->start_ns;
+  const int nso3 = (int)(duration / h->dt_so3_ns) + SPLINE_N, nr3 = (int)(duration / h->dt_r3_ns) + SPLINE_N;
+  // knot initialisation from the per-view pose priors (impl.h:278-339)
+  const Pose Tic{q4(h->glob[0], h->glob[1], h->glob[2], h->glob[3]), v3(h->glob[4], h->glob[5], h->glob[6])};
+  const Pose Tci = pose_inv(Tic);
+  std::map<double, int> by_time; for (int i = 0; i < nf; ++i) by_time[h->frame_t[i]] = i;
+  std::vector<double> t_vis, q_vis, p_vis;
+  for (const auto& kv : by_time) {
+    const int i = kv.second;
+    const Pose Twc{qn(&h->q_wc[4 * i]), v3(h->p_wc[3 * i], h->p_wc[3 * i + 1], h->p_wc[3 * i + 2])};
+    const Pose Twi = pose_mul(Twc, Tci);
+    t_vis.push_back(kv.first);
+    q_vis.push_back(Twi.q.x); q_vis.push_back(Twi.q.y); q_vis.push_back(Twi.q.z); q_vis.push_back(Twi.q.w);
+    p_vis.push_back(Twi.t.x); p_vis.push_back(Twi.t.y); p_vis.push_back(Twi.t.z);
+  }
+  const size_t nv = t_vis.size();
+  h->so3.assign(4 * (size_t)nso3, 0.0); h->r3.assign(3 * (size_t)nr3, 0.0);
+  for (int i = 0; i < nso3; ++i) {   // InterpolateQuaternions (utils.cc:221-241); knot times are zero based
+    const double t = double(i) * double(h->dt_so3_ns) * NS_TO_S;
+    double dist = 0; const size_t k = nearest_index(t, t_vis, dist);
+    double q[4];
+    if (k < nv - 1) quat_slerp(&q_vis[4 * k], &q_vis[4 * (k + 1)], dist / (t_vis[k + 1] - t_vis[k]), q); else memcpy(q, &q_vis[4 * k], sizeof q);
+    const Q4 r = qn(q);
+    h->so3[4 * i] = r.x; h->so3[4 * i + 1] = r.y; h->so3[4 * i + 2] = r.z; h->so3[4 * i + 3] = r.w;
+  }
+  for (int i = 0; i < nr3; ++i) {    // InterpolateVector3d (utils.cc:243-261) incl. its `nearest < t_new.size()` test; the reference's
+    const double t = double(i) * double(h->dt_r3_ns) * NS_TO_S;   // out-of-range read past the last view falls back to the nearest value
+    double dist = 0; const size_t k = nearest_index(t, t_vis, dist);
+    if (k < (size_t)nr3 && k + 1 < nv) { const double f = dist / (t_vis[k + 1] - t_vis[k]); for (int d = 0; d < 3; ++d) h->r3[3 * i + d] = (1.0 - f) * p_vis[3 * k + d] + f * p_vis[3 * (k + 1) + d]; }
+    else for (int d = 0; d < 3; ++d) h->r3[3 * i + d] = p_vis[3 * k + d];
+  }
+  // bias splines: InitBiasSplines(bias, bias, 10 s, 10 s, 1.0, 0.1) (imu_camera_calibrator.cc:80-85, impl.h:53-90)
+  h->dt_ba_ns = h->dt_bg_ns = (int64_t)(10 * 1e9); h->max_ba = 1.0; h->max_bg = 1e-1;
+  const int nba = (int)(duration / h->dt_ba_ns) + BIAS_N, nbg = (int)(duration / h->dt_bg_ns) + BIAS_N;
+  h->ba.resize(3 * (size_t)nba); h->bg.resize(3 * (size_t)nbg);
+  for (int i = 0; i < nba; ++i) for (int d = 0; d < 3; ++d) h->ba[3 * i + d] = ipp->acc_bias[d];
+  for (int i = 0; i < nbg; ++i) for (int d = 0; d < 3; ++d) h->bg[3 * i + d] = ipp->gyr_bias[d];
+
+  // ---- measurement wiring (imu_camera_calibrator.cc:87-120; Add*Measurement impl.h:341-613) ----------------------
+  struct Unit { double t; int kind, idx, nres; };
+  std::vector<Unit> units;
+  std::vector<FrameHost> all_frames(nf);
+  h->dropped_frames = h->dropped_imu = 0;
+  for (int i = 0; i < nf; ++i) {
+    FrameHost& f = all_frames[i]; f.t_s = h->frame_t[i]; f.c0 = h->corner_off[i]; f.c1 = h->corner_off[i + 1];
+    const int64_t t_ns = (int64_t)(f.t_s * S_TO_NS);
+    int64_t s1 = 0, s2 = 0;
+    const bool ok = calc_times(t_ns, h->start_ns, h->dt_r3_ns, nr3, SPLINE_N, f.u_r3, s1) && calc_times(t_ns, h->start_ns, h->dt_so3_ns, nso3, SPLINE_N, f.u_so3, s2);
+    f.s_r3 = (int)s1; f.s_so3 = (int)s2;
+    if (ok) units.push_back({f.t_s, 0, i, 2 * (f.c1 - f.c0)}); else ++h->dropped_frames;
+  }
+  struct ImuHost { double t_s; int64_t st; int s_so3, s_r3, s_ba, s_bg; int src; };
+  std::vector<ImuHost> all_imu;
+  for (size_t i = 0; i < h->imu_t.size(); ++i) {
+    const double t = h->imu_t[i] + ipp->time_offset_imu_to_cam_s;
+    if (t < h->t0_s || t >= h->tend_s) continue;
+    const int64_t t_ns = (int64_t)(t * S_TO_NS);
+    double u; int64_t a, b, c, d;
+    const bool ok = calc_times(t_ns, h->start_ns, h->dt_r3_ns, nr3, SPLINE_N, u, a) && calc_times(t_ns, h->start_ns, h->dt_so3_ns, nso3, SPLINE_N, u, b) &&
+                    calc_times(t_ns, h->start_ns, h->dt_ba_ns, nba, BIAS_N, u, c) && calc_times(t_ns, h->start_ns, h->dt_bg_ns, nbg, BIAS_N, u, d);
+    if (!ok) { ++h->dropped_imu; continue; }
+    all_imu.push_back({t, t_ns - h->start_ns, (int)b, (int)a, (int)c, (int)d, (int)i});
+    units.push_back({t, 1, (int)all_imu.size() - 1, 6});
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.t < y.t; });
+  long total = 0; for (const auto& u : units) total += u.nres;
+  const long lo = total * h->shard_rank / h->shard_world, hi = total * (h->shard_rank + 1) / h->shard_world;
+  long run = 0;
+  std::vector<int> frame_sel, imu_sel;
+  for (const auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; (u.kind == 0 ? frame_sel : imu_sel).push_back(u.idx); }
+  std::sort(frame_sel.begin(), frame_sel.end());
+  h->frames.clear(); h->used_uv.clear(); h->used_pid.clear();
+  for (int fi : frame_sel) {
+    FrameHost f = all_frames[fi];
+    const int c0 = (int)h->used_pid.size();
+    for (int c = f.c0; c < f.c1; ++c) { h->used_pid.push_back(h->point_ids[c]); h->used_uv.push_back(h->uv[2 * c]); h->used_uv.push_back(h->uv[2 * c + 1]); }
+    f.c0 = c0; f.c1 = (int)h->used_pid.size();
+    h->frames.push_back(f);
+  }
+  h->imu_used_t.clear(); h->imu_used_acc.clear(); h->imu_used_gyr.clear(); h->imu_used_st.clear(); h->cells.clear();
+  for (int mi : imu_sel) {
+    const ImuHost& m = all_imu[mi];
+    const int idx = (int)h->imu_used_t.size();
+    h->imu_used_t.push_back(m.t_s); h->imu_used_st.push_back(m.st);
+    for (int d = 0; d < 3; ++d) { h->imu_used_acc.push_back(h->imu_acc[3 * m.src + d]); h->imu_used_gyr.push_back(h->imu_gyr[3 * m.src + d]); }
+    if (h->cells.empty() || h->cells.back().s_so3 != m.s_so3 || h->cells.back().s_r3 != m.s_r3 || h->cells.back().s_ba != m.s_ba || h->cells.back().s_bg != m.s_bg)
+      h->cells.push_back({m.s_so3, m.s_r3, m.s_ba, m.s_bg, idx, idx});
+    h->cells.back().i_end = idx + 1;
+  }
+  // gravity initialisation (imu_camera_calibrator.cc:130-161) incl. the integer-second truncation of the accelerometer time
+  bool ginit = false; double g0[3] = {0.0, 0.0, 9.81};   // GRAVITY_MAGN (spline_trajectory_estimator.h:29) when never initialised
+  for (size_t j = 0; j < cam_ts.size() && !ginit; ++j) {
+    const int vi = by_time[cam_ts[j]];
+    const Pose Twc{qn(&h->q_wc[4 * vi]), v3(h->p_wc[3 * vi], h->p_wc[3 * vi + 1], h->p_wc[3 * vi + 2])};
+    const Pose Tai = pose_mul(Twc, Tci);
+    for (size_t i = 0; i < h->imu_t.size(); ++i) {
+      const int64_t accl_t = (int64_t)h->imu_t[i];
+      if (std::fabs(double(accl_t) - cam_ts[j]) < 1. / 30.) { const V3 g = qrot(Tai.q, v3(h->imu_acc[3 * i], h->imu_acc[3 * i + 1], h->imu_acc[3 * i + 2])); g0[0] = g.x; g0[1] = g.y; g0[2] = g.z; ginit = true; break; }
+    }
+  }
+  for (int d = 0; d < 3; ++d) h->glob[G_GRAV + d] = g0[d];
+
+  // ---- device upload ----------------------------------------------------------------------------------------------
+  DeviceProblem& P = h->P;
+  memset(&P, 0, sizeof P);
+  P.model = h->model; P.dispatch_fov = ipp->dispatch_fov; for (int i = 0; i < 10; ++i) P.intr[i] = h->intr[i];
+  P.n_frames = (int)h->frames.size(); P.n_corners = (int)h->used_pid.size(); P.rolling = ipp->init_line_delay_s != 0.0 ? 1 : 0;
+  P.n_imu = (int)h->imu_used_t.size(); P.n_cells = (int)h->cells.size();
+  P.dt_so3_ns = h->dt_so3_ns; P.dt_r3_ns = h->dt_r3_ns; P.dt_ba_ns = h->dt_ba_ns; P.dt_bg_ns = h->dt_bg_ns;
+  P.inv_so3_dt = S_TO_NS / double(h->dt_so3_ns); P.inv_r3_dt = S_TO_NS / double(h->dt_r3_ns);
+  P.w_acc = 1.0 / ipp->std_r3; P.w_gyr = 1.0 / ipp->std_so3;
+  P.n_so3 = nso3; P.n_r3 = nr3; P.n_ba = nba; P.n_bg = nbg;
+  P.n_res_vis = P.rolling ? 2 * P.n_corners : 0; P.n_res_acc = 3 * P.n_imu; P.n_res_gyr = 3 * P.n_imu;
+  h->cur_flags = -1; h->initialised = true; h->cur = 0; h->state_dirty_host = false;
+  if (h->device < 0) return ICC_OK;
+  CU(cudaSetDevice(h->device));
+  {
+    std::vector<double4> board(h->points.size() / 4);
+    for (size_t i = 0; i < board.size(); ++i) board[i] = make_double4(h->points[4 * i], h->points[4 * i + 1], h->points[4 * i + 2], h->points[4 * i + 3]);
+    CU(h->d_board.upload(board)); P.board = h->d_board.p;
+    std::vector<int> off, s1, s2; std::vector<double> u1, u2;
+    for (const auto& f : h->frames) { off.push_back(f.c0); s1.push_back(f.s_so3); s2.push_back(f.s_r3); u1.push_back(f.u_so3); u2.push_back(f.u_r3); }
+    off.push_back(P.n_corners);
+    CU(h->d_f_off.upload(off)); CU(h->d_f_s_so3.upload(s1)); CU(h->d_f_s_r3.upload(s2)); CU(h->d_f_u_so3.upload(u1)); CU(h->d_f_u_r3.upload(u2));
+    P.f_off = h->d_f_off.p; P.f_s_so3 = h->d_f_s_so3.p; P.f_s_r3 = h->d_f_s_r3.p; P.f_u_so3 = h->d_f_u_so3.p; P.f_u_r3 = h->d_f_u_r3.p;
+    std::vector<double2> uv2(P.n_corners); for (int c = 0; c < P.n_corners; ++c) uv2[c] = make_double2(h->used_uv[2 * c], h->used_uv[2 * c + 1]);
+    CU(h->d_uv.upload(uv2)); CU(h->d_pid.upload(h->used_pid)); P.uv = h->d_uv.p; P.pid = h->d_pid.p;
+    // work lists: one warp per item; items sized so that the grid fills the GPU but every item amortises its tile flush
+    const int target_items = h->sm_count * 8;
+    auto round32 = [](long v) { return (int)((v + 31) / 32 * 32); };
+    const int per_v = std::max(32, round32(P.n_corners / std::max(1, target_items)));
+    std::vector<VisionWork> vw;
+    for (int fi = 0; fi < P.n_frames; ++fi) for (int c = h->frames[fi].c0; c < h->frames[fi].c1; c += per_v) vw.push_back({fi, c, std::min(c + per_v, h->frames[fi].c1), 0});
+    CU(h->d_vwork.upload(vw)); P.vwork = h->d_vwork.p; P.n_vwork = (int)vw.size();
+    const int per_i = std::max(32, round32(P.n_imu / std::max(1, target_items)));
+    std::vector<ImuCell> iw;
+    for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
+    CU(h->d_iwork.upload(iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
+    CU(h->d_cells.upload(h->cells)); P.cells = h->d_cells.p;
+    CU(h->d_imu_t.upload(h->imu_used_st)); CU(h->d_imu_acc.upload(h->imu_used_acc)); CU(h->d_imu_gyr.upload(h->imu_used_gyr));
+    P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
+  }
+  icc_status s = upload_state(h, 0); if (s != ICC_OK) return s;
+  s = upload_state(h, 1); if (s != ICC_OK) return s;
+  return ICC_OK;
+}
+
+icc_status icc_set_known_gravity_dir(icc_handle* h, const double g[3]) {
+  if (!h || !g) return ICC_ERR_INVALID_ARGUMENT;
+  icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s;
+  for (int d = 0; d < 3; ++d) h->glob[G_GRAV + d] = g[d];
+  return push_state_to_device(h);
+}
+
+icc_status icc_optimize(icc_handle* h, int max_iterations, int flags, icc_summary* summary) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  icc_summary S;
+  icc_status s = run_lm(h, max_iterations, flags, true, &S); if (s != ICC_OK) return s;
+  const int l0 = kernel_launch_count();
+  s = mean_reproj(h, &S.mean_reproj_error); if (s != ICC_OK) return s;
+  S.gpu_launches += kernel_launch_count() - l0;
+  if (summary) *summary = S;
+  return ICC_OK;
+}
+icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summary) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  return run_lm(h, n, flags, false, summary);
+}
+
+icc_status icc_get_T_i_c(const icc_handle* hc, double T[7]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !T) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(T, h->glob + G_TIC, 7 * sizeof(double)); return ICC_OK; }
+icc_status icc_get_gravity(const icc_handle* hc, double g[3]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !g) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(g, h->glob + G_GRAV, 3 * sizeof(double)); return ICC_OK; }
+icc_status icc_get_line_delay(const icc_handle* hc, double* ld) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !ld) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; *ld = h->glob[G_LD]; return ICC_OK; }
+icc_status icc_get_num_knots(const icc_handle* h, int* a, int* b, int* c, int* d) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  if (a) *a = (int)h->so3.size() / 4; if (b) *b = (int)h->r3.size() / 3; if (c) *c = (int)h->ba.size() / 3; if (d) *d = (int)h->bg.size() / 3;
+  return ICC_OK;
+}
+icc_status icc_get_knots(const icc_handle* hc, double* so3, double* r3, double* ba, double* bg) {
+  icc_handle* h = const_cast<icc_handle*>(hc); if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s;
+  if (so3) std::copy(h->so3.begin(), h->so3.end(), so3);
+  if (r3) std::copy(h->r3.begin(), h->r3.end(), r3);
+  if (ba) std::copy(h->ba.begin(), h->ba.end(), ba);
+  if (bg) std::copy(h->bg.begin(), h->bg.end(), bg);
+  return ICC_OK;
+}
+icc_status icc_set_knots(icc_handle* h, const double* so3, const double* r3, const double* ba, const double* bg) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s;
+  if (so3) std::copy(so3, so3 + h->so3.size(), h->so3.begin());
+  if (r3) std::copy(r3, r3 + h->r3.size(), h->r3.begin());
+  if (ba) std::copy(ba, ba + h->ba.size(), h->ba.begin());
+  if (bg) std::copy(bg, bg + h->bg.size(), h->bg.begin());
+  return push_state_to_device(h);
+}
+icc_status icc_set_T_i_c(icc_handle* h, const double T[7]) { if (!h || !T) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(h->glob + G_TIC, T, 7 * sizeof(double)); return push_state_to_device(h); }
+icc_status icc_set_line_delay(icc_handle* h, double ld) { if (!h) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; h->glob[G_LD] = ld; return push_state_to_device(h); }
+icc_status icc_get_mean_reprojection_error(icc_handle* h, double* e) {
+  if (!h || !e) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  return mean_reproj(h, e);
+}
+icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->imu_used_t.size(); return ICC_OK; }
+icc_status icc_get_imu_used(const icc_handle* h, double* t, double* a, double* g) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  if (t) std::copy(h->imu_used_t.begin(), h->imu_used_t.end(), t);
+  if (a) std::copy(h->imu_used_acc.begin(), h->imu_used_acc.end(), a);
+  if (g) std::copy(h->imu_used_gyr.begin(), h->imu_used_gyr.end(), g);
+  return ICC_OK;
+}
+
+icc_status icc_eval_trajectory(icc_handle* h, int n, const int64_t* t_ns, double* gyro, double* accel, double* gb, double* ab, double* pq, double* pp, int32_t* valid) {
+  if (!h || n < 0 || (n > 0 && !t_ns)) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  if (n == 0) return ICC_OK;
+  CU(cudaSetDevice(h->device));
+  DevBuf<int64_t> d_t; DevBuf<double> d_out; DevBuf<int> d_valid;
+  std::vector<int64_t> tv(t_ns, t_ns + n);
+  CU(d_t.upload(tv)); CU(d_out.alloc((size_t)n * 19)); CU(d_valid.alloc(n));
+  CU(cudaMemsetAsync(d_out.p, 0, (size_t)n * 19 * sizeof(double), h->stream));
+  double* o = d_out.p;
+  launch_eval_trajectory(h->P, h->st[h->cur].view(), n, d_t.p, h->start_ns, o, o + 3 * n, o + 6 * n, o + 9 * n, o + 12 * n, o + 16 * n, d_valid.p, h->stream);
+  std::vector<double> ho((size_t)n * 19); std::vector<int> hv(n);
+  CU(cudaMemcpyAsync(ho.data(), d_out.p, ho.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hv.data(), d_valid.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) {
+    const bool v = hv[i] != 0;
+    if (valid) valid[i] = hv[i];
+    // like the reference getters, outputs are only written where CalcTimes accepts the timestamp (gyro needs SO3 only,
+    // but the hot CLI queries inside the spline range where both hold)
+    if (gyro && v) for (int d = 0; d < 3; ++d) gyro[3 * i + d] = ho[3 * i + d];
+    if (accel && v) for (int d = 0; d < 3; ++d) accel[3 * i + d] = ho[3 * n + 3 * i + d];
+    if (gb) for (int d = 0; d < 3; ++d) gb[3 * i + d] = ho[6 * n + 3 * i + d];
+    if (ab) for (int d = 0; d < 3; ++d) ab[3 * i + d] = ho[9 * n + 3 * i + d];
+    if (pq && v) for (int d = 0; d < 4; ++d) pq[4 * i + d] = ho[12 * n + 4 * i + d];
+    if (pp && v) for (int d = 0; d < 3; ++d) pp[3 * i + d] = ho[16 * n + 3 * i + d];
+  }
+  return ICC_OK;
+}
+
+icc_status icc_num_residuals(const icc_handle* h, int* v, int* a, int* g) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  if (v) *v = h->P.n_res_vis; if (a) *a = h->P.n_res_acc; if (g) *g = h->P.n_res_gyr;
+  return ICC_OK;
+}
+icc_status icc_num_tangent(const icc_handle* hc, int flags, int* n) {
+  icc_handle* h = const_cast<icc_handle*>(hc);
+  if (!h || !n) return ICC_ERR_INVALID_ARGUMENT;
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  icc_status s = configure(h, flags); if (s != ICC_OK) return s;
+  *n = h->n_tan; return ICC_OK;
+}
+
+icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residuals, double* gradient, double* hessian) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  icc_status s = configure(h, flags); if (s != ICC_OK) return s;
+  const DeviceProblem& P = h->P;
+  const int nres = P.n_res_vis + P.n_res_acc + P.n_res_gyr, n = h->n_tan;
+  double* res_dev = nullptr;
+  if (residuals) { CU(h->d_res.alloc((size_t)std::max(1, nres))); CU(cudaMemsetAsync(h->d_res.p, 0, (size_t)nres * sizeof(double), h->stream)); res_dev = h->d_res.p; }
+  if (!gradient && !hessian) {
+    CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
+    s = eval_cost(h, h->st[h->cur].view(), h->d_scal.p + SC_CAND_COST, res_dev, nullptr); if (s != ICC_OK) return s;
+    double c; CU(cudaMemcpyAsync(&c, h->d_scal.p + SC_CAND_COST, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (residuals) CU(cudaMemcpyAsync(residuals, res_dev, (size_t)nres * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (cost) *cost = c;
+    return ICC_OK;
+  }
+  s = eval_jacobian(h, h->st[h->cur].view(), res_dev); if (s != ICC_OK) return s;
+  std::vector<double> ne((size_t)P.ne_size);
+  CU(cudaMemcpyAsync(ne.data(), P.ne, ne.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (residuals) CU(cudaMemcpyAsync(residuals, res_dev, (size_t)nres * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cost) *cost = ne[P.ne_off_cost];
+  if (gradient) for (int i = 0; i < n; ++i) gradient[i] = ne[P.ne_off_g + h->perm[i]];
+  if (hessian) {
+    auto get = [&](int a, int b) -> double {
+      const int lo = std::min(a, b), hi = std::max(a, b);
+      if (hi < P.nk) return hi - lo <= P.kd ? ne[(size_t)lo * P.ldb + (hi - lo)] : 0.0;
+      if (lo < P.nk) return ne[P.ne_off_E + (size_t)lo * P.nb + (hi - P.nk)];
+      return ne[P.ne_off_C + (size_t)(hi - P.nk) * P.nb + (lo - P.nk)];
+    };
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) hessian[(size_t)i * n + j] = get(h->perm[i], h->perm[j]);
+  }
+  return ICC_OK;
+}
+
+icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval) {
+  if (!h || !ms_per_eval || n <= 0) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  icc_status s = configure(h, flags); if (s != ICC_OK) return s;
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
+  CU(cudaEventRecord(e0, h->stream));
+  for (int i = 0; i < n; ++i) {
+    if (with_jacobian) { s = eval_jacobian(h, h->st[h->cur].view(), nullptr); }
+    else { s = eval_cost(h, h->st[h->cur].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); }
+    if (s != ICC_OK) return s;
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_eval = ms / n;
+  return ICC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+// Residual + analytic Jacobian evaluation kernels (sm_100a), fused with the J^T J / J^T r reduction.
+//
+// Replaces, for every board-corner observation and every accelerometer / gyroscope sample in parallel, what the
+// reference evaluates per residual block through ceres::DynamicAutoDiffCostFunction on CPU threads:
+//   RSReprojectionCostFunctorSplit<6>::operator()   include/OpenCameraCalibrator/basalt_spline/ceres_calib_split_residuals.h:319-402
+//   AccelerationCostFunctorSplit<6>::operator()     ...ceres_calib_split_residuals.h:52-93
+//   GyroCostFunctorSplit<6,SO3,false>::operator()   ...ceres_calib_split_residuals.h:133-169
+//   CeresSplineHelper<T,6>::evaluate_lie / evaluate ...ceres_spline_helper.h:101-220
+// plus Ceres' J^T J assembly.  Jacobians are closed-form w.r.t. right-multiplicative increments of the six active
+// SO(3) knots, the six R^3 knots, T_i_c (upsilon, omega), the line delay, gravity and the bias-spline knots, which is
+// exactly autodiff x LieLocalParameterization of the reference.
+//
+// Mapping to the machine: one WARP owns one work item (a camera frame / an IMU knot-interval cell), so the 6+6 knot
+// window and the per-window quantities (log increments d_i, Jr^-1(d_i)) are staged ONCE in shared memory (16-byte
+// vector loads of the padded knots); every lane evaluates one observation; each residual row [J | r] is written to a
+// per-warp shared tile stored column-major (conflict-free) and the symmetric product [J|r]^T [J|r] is accumulated
+// with FP64 tensor-core MMAs (mma.sync m8n8k4 f64: "tensor cores only where it is genuinely a contraction") into
+// register fragments that persist across the whole work item; one atomic RED per tile entry then lands in the packed
+// banded+bordered normal-equation buffer in HBM/L2.
+#include "icc_camera.cuh"
+#include "icc_kernels.h"
+
+#include <atomic>
+
+namespace icc {
+
+static std::atomic<int> g_launches{0};
+int kernel_launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr int LDJ = 36;   // rows per tile column (32 + 4 pad: stride = 4 mod 16 => conflict-free DMMA fragment loads)
+
+struct WarpCtx {
+  Q4 q[6];
+  V3 d[5];
+  M3 jri[5];
+  V3 p[6];
+  V3 ba[3], bg[3];
+  int gidx[64];
+  int gidx2[32];
+};
+
+ICC_D void mma_f64(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// acc += Jt^T Jt over rows [0, 4*nsteps) of the column-major tile; NB 8-column blocks; upper block triangle only.
+template <int NB>
+ICC_D void syrk_dmma(const double* __restrict__ Jt, int nsteps, double (&acc)[NB * (NB + 1) / 2][2]) {
+  const int lane = threadIdx.x & 31;
+  const double* base = Jt + (lane >> 2) * LDJ + (lane & 3);
+  for (int s = 0; s < nsteps; ++s) {
+    double f[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) f[b] = base[(8 * b) * LDJ + 4 * s];
+    int idx = 0;
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < NB; ++bj) { mma_f64(acc[idx], f[bi], f[bj]); ++idx; }
+  }
+}
+
+ICC_D void ne_add(const DeviceProblem& P, int gi, int gj, double v) {
+  const int lo = min(gi, gj), hi = max(gi, gj);
+  double* dst;
+  if (hi < P.nk) dst = P.ne + (int64_t)lo * P.ldb + (hi - lo);
+  else if (lo < P.nk) dst = P.ne + P.ne_off_E + (int64_t)lo * P.nb + (hi - P.nk);
+  else dst = P.ne + P.ne_off_C + (int64_t)(hi - P.nk) * P.nb + (lo - P.nk);
+  atomicAdd(dst, v);
+}
+
+// Scatter the register fragments of one work item.  Local column `rescol` is the residual column:
+// (I, rescol) -> gradient, (rescol, rescol) -> 2 * cost.
+template <int NB>
+ICC_D void flush_tile(const DeviceProblem& P, const int* gidx, int ncols, int rescol, double (&acc)[NB * (NB + 1) / 2][2]) {
+  const int lane = threadIdx.x & 31;
+  int idx = 0;
+#pragma unroll
+  for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+    for (int bj = bi; bj < NB; ++bj) {
+      const int I = 8 * bi + (lane >> 2);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int J = 8 * bj + 2 * (lane & 3) + e;
+        const double v = acc[idx][e];
+        if (I < ncols && J < ncols && I <= J && v != 0.0) {
+          if (J == rescol) {
+            if (I == rescol) atomicAdd(P.ne + P.ne_off_cost, 0.5 * v);
+            else { const int gi = gidx[I]; if (gi >= 0) atomicAdd(P.ne + P.ne_off_g + gi, v); }
+          } else {
+            const int gi = gidx[I], gj = gidx[J];
+            if (gi >= 0 && gj >= 0) ne_add(P, gi, gj, v);
+          }
+        }
+      }
+      ++idx;
+    }
+}
+
+ICC_D double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Stage the SO(3) window (6 knots -> 5 log increments and their Jr^-1) for one work item.
+template <bool JAC>
+ICC_D void stage_so3_window(WarpCtx* wc, const DeviceState& S, int s_so3, int lane) {
+  if (lane < 6) { const double4 k = S.so3[s_so3 + lane]; wc->q[lane] = q4(k.x, k.y, k.z, k.w); }
+  __syncwarp();
+  if (lane < 5) {
+    const V3 d = so3_log(qmul(qconj(wc->q[lane]), wc->q[lane + 1]));
+    wc->d[lane] = d;
+    if (JAC) wc->jri[lane] = so3_jr_inv(d);
+  }
+}
+
+// Per-observation spline rotation chain shared by all residual types.
+struct Chain {
+  Q4 A[5];          // exp(lambda_i d_i), i = 1..5
+  double ja[5], jb[5];
+  double lam[5], dlam[5];
+  Q4 q;             // R_w_i
+};
+ICC_D void build_chain(const WarpCtx* wc, double u, Chain& ch) {
+  cum_coeffs6(u, ch.lam, ch.dlam);
+  Q4 q = wc->q[0];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const ExpOut e = so3_exp_jr(ch.lam[i] * wc->d[i]);
+    ch.A[i] = e.q; ch.ja[i] = e.a; ch.jb[i] = e.b;
+    q = qmul(q, e.q);
+  }
+  ch.q = q;
+}
+
+// Given the row covector m_theta = d r / d theta (right increment of R_w_i), write d r / d eps_j for the six SO(3) knots
+// into tile columns [0, 18) of row `lane`, and return sum_i dlam_i <w_i, d_i>  (= d r / d u through the rotation).
+ICC_D double so3_knot_row(const WarpCtx* wc, const Chain& ch, V3 m_theta, double* __restrict__ Jt, int lane, double scale) {
+  V3 w = m_theta;                  // w_5
+  V3 z_next = v3(0, 0, 0);         // Jr^-1_{j+1} z_{j+1} handled below
+  double du = 0.0;
+#pragma unroll
+  for (int i = 4; i >= 0; --i) {   // knot pair (i, i+1): increment index i+1 in the text, array index i
+    const V3 di = wc->d[i];
+    du += ch.dlam[i] * dot(w, di);
+    const V3 z = ch.lam[i] * row_times_jr(w, ch.lam[i] * di, ch.ja[i], ch.jb[i]);
+    // knot i+1 receives  z Jr^-1(d_i)  (row-vector times matrix) minus the contribution found in the previous iteration
+    const V3 up = mulT(wc->jri[i], z) - z_next;
+    Jt[(3 * (i + 1) + 0) * LDJ + lane] = scale * up.x;
+    Jt[(3 * (i + 1) + 1) * LDJ + lane] = scale * up.y;
+    Jt[(3 * (i + 1) + 2) * LDJ + lane] = scale * up.z;
+    z_next = mul(wc->jri[i], z);   // z Jl^-1(d_i) = Jr^-1(d_i) z, subtracted from knot i
+    w = qrot(ch.A[i], w);          // w_{i}  (P_i^T applied)
+  }
+  const V3 k0 = w - z_next;
+  Jt[0 * LDJ + lane] = scale * k0.x; Jt[1 * LDJ + lane] = scale * k0.y; Jt[2 * LDJ + lane] = scale * k0.z;
+  return du;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vision: rolling-shutter reprojection residuals.  Tile columns: [so3 0..17 | r3 18..35 | T_i_c 36..41 | ld 42 | r 43].
+// ---------------------------------------------------------------------------------------------------------------
+template <bool JAC>
+__global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, DeviceState S, double* cost_out, double* res_out, double* reproj_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpCtx* wc = reinterpret_cast<WarpCtx*>(smem_raw) + warp;
+  double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (48 * LDJ);
+  constexpr int NB = 6, NCOL = 44, RES = 43;
+
+  const Q4 q_ic = q4(S.glob[G_TIC + 0], S.glob[G_TIC + 1], S.glob[G_TIC + 2], S.glob[G_TIC + 3]);
+  const V3 t_ic = v3(S.glob[G_TIC + 4], S.glob[G_TIC + 5], S.glob[G_TIC + 6]);
+  const double ld = S.glob[G_LD];
+  if (JAC) { for (int i = lane; i < 48 * LDJ; i += 32) Jt[i] = 0.0; }
+
+  double cost_acc = 0.0, rp_sum = 0.0, rp_cnt = 0.0;
+  for (int item = blockIdx.x * WARPS + warp; item < P.n_vwork; item += gridDim.x * WARPS) {
+    const VisionWork wk = P.vwork[item];
+    const int s_so3 = P.f_s_so3[wk.frame], s_r3 = P.f_s_r3[wk.frame];
+    const double u_so3 = P.f_u_so3[wk.frame], u_r3 = P.f_u_r3[wk.frame];
+    __syncwarp();
+    if (lane < 6) { const double4 k = S.r3[s_r3 + lane]; wc->p[lane] = v3(k.x, k.y, k.z); }
+    stage_so3_window<JAC>(wc, S, s_so3, lane);
+    if (JAC) {
+      for (int c = lane; c < 48; c += 32) {
+        int g = -1;
+        if (c < 18) { const int b = P.so3_col[s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
+        else if (c < 36) { const int b = P.r3_col[s_r3 + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
+        else if (c < 42) g = P.col_tic < 0 ? -1 : P.col_tic + (c - 36);
+        else if (c == 42) g = P.col_ld;
+        wc->gidx[c] = g;
+      }
+    }
+    __syncwarp();
+    double acc[NB * (NB + 1) / 2][2];
+    if (JAC) {
+#pragma unroll
+      for (int i = 0; i < NB * (NB + 1) / 2; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    }
+    for (int base = wk.c_begin; base < wk.c_end; base += 32) {
+      const int c = base + lane;
+      const bool act = c < wk.c_end;
+      const int nact = min(32, wk.c_end - base);
+      double r0 = 0.0, r1 = 0.0, y = 0.0;
+      bool ok = false;
+      Chain ch; Proj pr; V3 qi = v3(0, 0, 0), pc = v3(0, 0, 0), tdot = v3(0, 0, 0);
+      double cc[6];
+      if (act) {
+        const double2 ob = P.uv[c];
+        y = ob.y;
+        const double us = u_so3 + y * ld, ur = u_r3 + y * ld;   // residuals.h:344-346 (row time added to normalised u)
+        build_chain(wc, us, ch);
+        double dc[6];
+        coeffs6(ur, cc, JAC ? dc : nullptr, nullptr);
+        V3 t = v3(0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { t = fma3(cc[j], wc->p[j], t); if (JAC) tdot = fma3(dc[j], wc->p[j], tdot); }
+        const double4 X = P.board[P.pid[c]];
+        const double iw = 1.0 / X.w;
+        qi = qrot_inv(ch.q, v3(X.x * iw, X.y * iw, X.z * iw) - t);   // point in the IMU frame
+        pc = qrot_inv(q_ic, qi - t_ic);                                // point in the camera frame
+        pr = project(P.model, P.intr, pc, P.dispatch_fov != 0);
+        ok = pr.ok;
+        if (ok) { r0 = pr.u - ob.x; r1 = pr.v - ob.y; } else { r0 = 1e10; r1 = 1e10; }   // residuals.h:391-398, cov = I
+        if (res_out) { res_out[2 * c] = r0; res_out[2 * c + 1] = r1; }
+        if (!JAC) {
+          cost_acc += 0.5 * (r0 * r0 + r1 * r1);
+          if (reproj_out && r0 != 0.0 && r1 != 0.0) { rp_sum += sqrt(r0 * r0 + r1 * r1); rp_cnt += 1.0; }   // impl.h:1058-1064
+        }
+      }
+      if (JAC) {
+#pragma unroll 1
+        for (int row = 0; row < 2; ++row) {
+          if (act && ok) {
+            const V3 Dp = v3(pr.J[3 * row], pr.J[3 * row + 1], pr.J[3 * row + 2]);
+            const V3 m_q = qrot(q_ic, Dp);        // Dp R_ic^T as a covector
+            const V3 m_th = cross(m_q, qi);       // m_q [qi]x
+            const V3 m_t = qrot(ch.q, m_q);       // m_q R_wi^T
+            const double du = so3_knot_row(wc, ch, m_th, Jt, lane, 1.0);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              Jt[(18 + 3 * j + 0) * LDJ + lane] = -cc[j] * m_t.x;
+              Jt[(18 + 3 * j + 1) * LDJ + lane] = -cc[j] * m_t.y;
+              Jt[(18 + 3 * j + 2) * LDJ + lane] = -cc[j] * m_t.z;
+            }
+            const V3 om = cross(Dp, pc);
+            Jt[36 * LDJ + lane] = -Dp.x; Jt[37 * LDJ + lane] = -Dp.y; Jt[38 * LDJ + lane] = -Dp.z;
+            Jt[39 * LDJ + lane] = om.x; Jt[40 * LDJ + lane] = om.y; Jt[41 * LDJ + lane] = om.z;
+            Jt[42 * LDJ + lane] = y * (du - dot(m_t, tdot));
+            Jt[RES * LDJ + lane] = row == 0 ? r0 : r1;
+          } else {
+            for (int k = 0; k < RES; ++k) Jt[k * LDJ + lane] = 0.0;
+            Jt[RES * LDJ + lane] = act ? (row == 0 ? r0 : r1) : 0.0;
+          }
+          __syncwarp();
+          syrk_dmma<NB>(Jt, (nact + 3) >> 2, acc);
+          __syncwarp();
+        }
+      }
+    }
+    if (JAC) flush_tile<NB>(P, wc->gidx, NCOL, RES, acc);
+  }
+  if (!JAC) {
+    cost_acc = warp_sum(cost_acc);
+    if (lane == 0 && cost_out) atomicAdd(cost_out, cost_acc);
+    if (reproj_out) { rp_sum = warp_sum(rp_sum); rp_cnt = warp_sum(rp_cnt); if (lane == 0) { atomicAdd(reproj_out, rp_sum); atomicAdd(reproj_out + 1, rp_cnt); } }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IMU: accelerometer + gyroscope residuals of one knot-interval cell per warp.
+//   accel tile columns: [so3 0..17 | r3 18..35 | g 36..38 | (ba 39..47) | r]     NB = 5 (no bias) / 7 (bias)
+//   gyro  tile columns: [so3 0..17 | (bg 18..26) | r]                            NB = 3 (no bias) / 4 (bias)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool JAC, bool BIAS>
+__global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, DeviceState S, double* cost_out, double* res_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NBA = BIAS ? 7 : 5, NBG = BIAS ? 4 : 3;
+  constexpr int RESA = BIAS ? 48 : 39, NCOLA = RESA + 1, RESG = BIAS ? 27 : 18, NCOLG = RESG + 1;
+  constexpr int TILE_COLS = 8 * NBA;
+  WarpCtx* wc = reinterpret_cast<WarpCtx*>(smem_raw) + warp;
+  double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (TILE_COLS * LDJ);
+  if (JAC) { for (int i = lane; i < TILE_COLS * LDJ; i += 32) Jt[i] = 0.0; }
+
+  const double* ai = S.glob + G_ACC_INTR;
+  const double* gi = S.glob + G_GYR_INTR;
+  // misalignment * scale matrices (utils/types.h:226-246)
+  const double Ma[9] = {ai[3], -ai[0] * ai[4], ai[1] * ai[5], 0.0, ai[4], -ai[2] * ai[5], 0.0, 0.0, ai[5]};
+  const double Mg[9] = {gi[6], -gi[0] * gi[7], gi[1] * gi[8], gi[3] * gi[6], gi[7], -gi[2] * gi[8], -gi[4] * gi[6], gi[5] * gi[7], gi[8]};
+  const V3 grav = v3(S.glob[G_GRAV], S.glob[G_GRAV + 1], S.glob[G_GRAV + 2]);
+  const double idt2 = P.inv_r3_dt * P.inv_r3_dt;
+
+  double cost_acc = 0.0;
+  for (int item = blockIdx.x * WARPS + warp; item < P.n_iwork; item += gridDim.x * WARPS) {
+    const ImuCell cell = P.iwork[item];
+    __syncwarp();
+    if (lane < 6) { const double4 k = S.r3[cell.s_r3 + lane]; wc->p[lane] = v3(k.x, k.y, k.z); }
+    if (lane < 3) { const double4 a = S.ba[cell.s_ba + lane]; wc->ba[lane] = v3(a.x, a.y, a.z); const double4 g = S.bg[cell.s_bg + lane]; wc->bg[lane] = v3(g.x, g.y, g.z); }
+    stage_so3_window<JAC>(wc, S, cell.s_so3, lane);
+    if (JAC) {
+      for (int c = lane; c < 64; c += 32) {
+        int g = -1;
+        if (c < 18) { const int b = P.so3_col[cell.s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
+        else if (c < 36) { const int b = P.r3_col[cell.s_r3 + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
+        else if (c < 39) g = P.col_g < 0 ? -1 : P.col_g + (c - 36);
+        else if (BIAS && c < 48) { const int b = P.ba_col[cell.s_ba + (c - 39) / 3]; g = b < 0 ? -1 : b + (c - 39) % 3; }
+        wc->gidx[c] = g;
+      }
+      {
+        const int c = lane;
+        int g = -1;
+        if (c < 18) { const int b = P.so3_col[cell.s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
+        else if (BIAS && c < 27) { const int b = P.bg_col[cell.s_bg + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
+        wc->gidx2[c] = g;
+      }
+    }
+    __syncwarp();
+    double accA[NBA * (NBA + 1) / 2][2], accG[NBG * (NBG + 1) / 2][2];
+    if (JAC) {
+#pragma unroll
+      for (int i = 0; i < NBA * (NBA + 1) / 2; ++i) { accA[i][0] = 0.0; accA[i][1] = 0.0; }
+#pragma unroll
+      for (int i = 0; i < NBG * (NBG + 1) / 2; ++i) { accG[i][0] = 0.0; accG[i][1] = 0.0; }
+    }
+    for (int base = cell.i_begin; base < cell.i_end; base += 32) {
+      const int i = base + lane;
+      const bool act = i < cell.i_end;
+      const int nact = min(32, cell.i_end - base);
+      const int nsteps = (nact + 3) >> 2;
+      Chain ch;
+      double ra[3] = {0, 0, 0}, rg[3] = {0, 0, 0};
+      double ddc[6], cba[3], cbg[3];
+      V3 h = v3(0, 0, 0);
+      if (act) {
+        const int64_t st = P.imu_t_ns[i];
+        // CalcTimes (impl.h:763-788): u = (st % dt) / dt with the segment index known from the cell
+        const double u_so3 = double(st - (int64_t)cell.s_so3 * P.dt_so3_ns) / double(P.dt_so3_ns);
+        const double u_r3 = double(st - (int64_t)cell.s_r3 * P.dt_r3_ns) / double(P.dt_r3_ns);
+        const double u_ba = double(st - (int64_t)cell.s_ba * P.dt_ba_ns) / double(P.dt_ba_ns);
+        const double u_bg = double(st - (int64_t)cell.s_bg * P.dt_bg_ns) / double(P.dt_bg_ns);
+        build_chain(wc, u_so3, ch);
+        double cdum[6];
+        coeffs6(u_r3, cdum, nullptr, ddc);
+        coeffs3(u_ba, cba); coeffs3(u_bg, cbg);
+        // accelerometer residual (residuals.h:52-93)
+        V3 aw = v3(0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) aw = fma3(ddc[j] * idt2, wc->p[j], aw);
+        h = qrot_inv(ch.q, aw + grav);
+        V3 bacc = v3(0, 0, 0), bgyr = v3(0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { bacc = fma3(cba[k], wc->ba[k], bacc); bgyr = fma3(cbg[k], wc->bg[k], bgyr); }
+        const V3 a_raw = v3(P.imu_acc[3 * i], P.imu_acc[3 * i + 1], P.imu_acc[3 * i + 2]) - bacc;
+        const V3 g_raw = v3(P.imu_gyr[3 * i], P.imu_gyr[3 * i + 1], P.imu_gyr[3 * i + 2]) - bgyr;
+        ra[0] = P.w_acc * (h.x - (Ma[0] * a_raw.x + Ma[1] * a_raw.y + Ma[2] * a_raw.z));
+        ra[1] = P.w_acc * (h.y - (Ma[3] * a_raw.x + Ma[4] * a_raw.y + Ma[5] * a_raw.z));
+        ra[2] = P.w_acc * (h.z - (Ma[6] * a_raw.x + Ma[7] * a_raw.y + Ma[8] * a_raw.z));
+        // gyroscope residual (residuals.h:133-169): body velocity recursion (spline_helper.h:159-164)
+        V3 om = v3(0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) om = qrot_inv(ch.A[k], om) + (ch.dlam[k] * P.inv_so3_dt) * wc->d[k];
+        rg[0] = P.w_gyr * (om.x - (Mg[0] * g_raw.x + Mg[1] * g_raw.y + Mg[2] * g_raw.z));
+        rg[1] = P.w_gyr * (om.y - (Mg[3] * g_raw.x + Mg[4] * g_raw.y + Mg[5] * g_raw.z));
+        rg[2] = P.w_gyr * (om.z - (Mg[6] * g_raw.x + Mg[7] * g_raw.y + Mg[8] * g_raw.z));
+        if (res_out) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { res_out[P.n_res_vis + 3 * i + k] = ra[k]; res_out[P.n_res_vis + P.n_res_acc + 3 * i + k] = rg[k]; }
+        }
+        if (!JAC) cost_acc += 0.5 * (ra[0] * ra[0] + ra[1] * ra[1] + ra[2] * ra[2] + rg[0] * rg[0] + rg[1] * rg[1] + rg[2] * rg[2]);
+      }
+      if (JAC) {
+        // ---- accelerometer rows -----------------------------------------------------------------------------
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+          if (act) {
+            const V3 ek = v3(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0);
+            const V3 m_th = cross(ek, h);              // e_k^T [h]x
+            const V3 m_t = qrot(ch.q, ek);             // e_k^T R_wi^T
+            so3_knot_row(wc, ch, m_th, Jt, lane, P.w_acc);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const double s = P.w_acc * ddc[j] * idt2;
+              Jt[(18 + 3 * j + 0) * LDJ + lane] = s * m_t.x; Jt[(18 + 3 * j + 1) * LDJ + lane] = s * m_t.y; Jt[(18 + 3 * j + 2) * LDJ + lane] = s * m_t.z;
+            }
+            Jt[36 * LDJ + lane] = P.w_acc * m_t.x; Jt[37 * LDJ + lane] = P.w_acc * m_t.y; Jt[38 * LDJ + lane] = P.w_acc * m_t.z;
+            if (BIAS) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double s = P.w_acc * cba[j];
+                Jt[(39 + 3 * j + 0) * LDJ + lane] = s * Ma[3 * k + 0]; Jt[(39 + 3 * j + 1) * LDJ + lane] = s * Ma[3 * k + 1]; Jt[(39 + 3 * j + 2) * LDJ + lane] = s * Ma[3 * k + 2];
+              }
+            }
+            Jt[RESA * LDJ + lane] = ra[k];
+          } else {
+            for (int c = 0; c < NCOLA; ++c) Jt[c * LDJ + lane] = 0.0;
+          }
+          __syncwarp();
+          syrk_dmma<NBA>(Jt, nsteps, accA);
+          __syncwarp();
+        }
+        // ---- gyroscope rows ------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+          if (act) {
+            // d omega_k / d eps_j = y_j Jr^-1_j - Jr^-1_{j+1} y_{j+1},  y_i = lam_i ((w_i x s_i) Jr(phi_i)) + lam'_i w_i
+            // s_i = A_i^T omega_{i-1} needs the forward recursion; recompute it backwards-compatible: store s_i first.
+            V3 s[5];
+            {
+              V3 om = v3(0, 0, 0);
+#pragma unroll
+              for (int i2 = 0; i2 < 5; ++i2) { s[i2] = qrot_inv(ch.A[i2], om); om = s[i2] + (ch.dlam[i2] * P.inv_so3_dt) * wc->d[i2]; }
+            }
+            V3 w = v3(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0);
+            V3 z_next = v3(0, 0, 0);
+#pragma unroll
+            for (int i2 = 4; i2 >= 0; --i2) {
+              const V3 yv = ch.lam[i2] * row_times_jr(cross(w, s[i2]), ch.lam[i2] * wc->d[i2], ch.ja[i2], ch.jb[i2]) + (ch.dlam[i2] * P.inv_so3_dt) * w;
+              const V3 up = mulT(wc->jri[i2], yv) - z_next;
+              Jt[(3 * (i2 + 1) + 0) * LDJ + lane] = P.w_gyr * up.x; Jt[(3 * (i2 + 1) + 1) * LDJ + lane] = P.w_gyr * up.y; Jt[(3 * (i2 + 1) + 2) * LDJ + lane] = P.w_gyr * up.z;
+              z_next = mul(wc->jri[i2], yv);
+              w = qrot(ch.A[i2], w);
+            }
+            Jt[0 * LDJ + lane] = -P.w_gyr * z_next.x; Jt[1 * LDJ + lane] = -P.w_gyr * z_next.y; Jt[2 * LDJ + lane] = -P.w_gyr * z_next.z;
+            if (BIAS) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double sc = P.w_gyr * cbg[j];
+                Jt[(18 + 3 * j + 0) * LDJ + lane] = sc * Mg[3 * k + 0]; Jt[(18 + 3 * j + 1) * LDJ + lane] = sc * Mg[3 * k + 1]; Jt[(18 + 3 * j + 2) * LDJ + lane] = sc * Mg[3 * k + 2];
+              }
+            }
+            Jt[RESG * LDJ + lane] = rg[k];
+            for (int c = NCOLG; c < 8 * NBG; ++c) Jt[c * LDJ + lane] = 0.0;
+          } else {
+            for (int c = 0; c < 8 * NBG; ++c) Jt[c * LDJ + lane] = 0.0;
+          }
+          __syncwarp();
+          syrk_dmma<NBG>(Jt, nsteps, accG);
+          __syncwarp();
+        }
+        // the accelerometer layout is wider than the gyroscope one: clear what the gyro rows overwrote beyond their own
+        // columns is unnecessary (accel rewrites all its columns), but the accel PAD columns must stay zero: they are never written.
+      }
+    }
+    if (JAC) {
+      flush_tile<NBA>(P, wc->gidx, NCOLA, RESA, accA);
+      flush_tile<NBG>(P, wc->gidx2, NCOLG, RESG, accG);
+    }
+  }
+  if (!JAC) {
+    cost_acc = warp_sum(cost_acc);
+    if (lane == 0 && cost_out) atomicAdd(cost_out, cost_acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Trajectory getters (impl.h:898-991,1180-1234), one thread per timestamp.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ bool calc_times_dev(int64_t t_ns, int64_t start_ns, int64_t dt_ns, int nr_knots, int N, double& u, int& s) {
+  const int64_t st = t_ns - start_ns;
+  if (st < 0) return false;
+  const int64_t sl = st / dt_ns;
+  if (sl + N > (int64_t)nr_knots) return false;
+  s = (int)sl; u = double(st % dt_ns) / double(dt_ns);
+  return true;
+}
+
+__global__ void trajectory_kernel(DeviceProblem P, DeviceState S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel, double* bg,
+                                  double* ba, double* pose_q, double* pose_p, int* valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u_so3 = 0, u_r3 = 0, u_b = 0; int s_so3 = 0, s_r3 = 0, s_b = 0;
+  const bool ok_so3 = calc_times_dev(t_ns[i], start_ns, P.dt_so3_ns, P.n_so3, SPLINE_N, u_so3, s_so3);
+  const bool ok_r3 = calc_times_dev(t_ns[i], start_ns, P.dt_r3_ns, P.n_r3, SPLINE_N, u_r3, s_r3);
+  if (valid) valid[i] = ok_so3 && ok_r3;
+  Q4 R = q4(0, 0, 0, 1); V3 om = v3(0, 0, 0);
+  if (ok_so3) {
+    double lam[5], dlam[5];
+    cum_coeffs6(u_so3, lam, dlam);
+    double4 k0 = S.so3[s_so3];
+    Q4 prev = q4(k0.x, k0.y, k0.z, k0.w);
+    R = prev;
+    for (int k = 0; k < 5; ++k) {
+      const double4 kn = S.so3[s_so3 + k + 1];
+      const Q4 next = q4(kn.x, kn.y, kn.z, kn.w);
+      const V3 d = so3_log(qmul(qconj(prev), next));
+      const Q4 A = so3_exp(lam[k] * d);
+      R = qmul(R, A);
+      om = qrot_inv(A, om) + (dlam[k] * P.inv_so3_dt) * d;
+      prev = next;
+    }
+  }
+  if (gyro && ok_so3) { gyro[3 * i] = om.x; gyro[3 * i + 1] = om.y; gyro[3 * i + 2] = om.z; }
+  if (ok_so3 && ok_r3) {
+    double c[6], ddc[6];
+    coeffs6(u_r3, c, nullptr, ddc);
+    V3 p = v3(0, 0, 0), a = v3(0, 0, 0);
+    for (int k = 0; k < 6; ++k) { const double4 kk = S.r3[s_r3 + k]; const V3 kv = v3(kk.x, kk.y, kk.z); p = fma3(c[k], kv, p); a = fma3(ddc[k] * P.inv_r3_dt * P.inv_r3_dt, kv, a); }
+    if (accel) { const V3 h = qrot_inv(R, a + v3(S.glob[G_GRAV], S.glob[G_GRAV + 1], S.glob[G_GRAV + 2])); accel[3 * i] = h.x; accel[3 * i + 1] = h.y; accel[3 * i + 2] = h.z; }
+    if (pose_q) { pose_q[4 * i] = R.x; pose_q[4 * i + 1] = R.y; pose_q[4 * i + 2] = R.z; pose_q[4 * i + 3] = R.w; }
+    if (pose_p) { pose_p[3 * i] = p.x; pose_p[3 * i + 1] = p.y; pose_p[3 * i + 2] = p.z; }
+  }
+  if (bg) {
+    V3 b = v3(0, 0, 0);
+    if (calc_times_dev(t_ns[i], start_ns, P.dt_bg_ns, P.n_bg, BIAS_N, u_b, s_b)) { double c[3]; coeffs3(u_b, c); for (int k = 0; k < 3; ++k) { const double4 kk = S.bg[s_b + k]; b = fma3(c[k], v3(kk.x, kk.y, kk.z), b); } }
+    bg[3 * i] = b.x; bg[3 * i + 1] = b.y; bg[3 * i + 2] = b.z;
+  }
+  if (ba) {
+    V3 b = v3(0, 0, 0);
+    if (calc_times_dev(t_ns[i], start_ns, P.dt_ba_ns, P.n_ba, BIAS_N, u_b, s_b)) { double c[3]; coeffs3(u_b, c); for (int k = 0; k < 3; ++k) { const double4 kk = S.ba[s_b + k]; b = fma3(c[k], v3(kk.x, kk.y, kk.z), b); } }
+    ba[3 * i] = b.x; ba[3 * i + 1] = b.y; ba[3 * i + 2] = b.z;
+  }
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : 1; }
+
+int grid_for(int n_items, int sm_count) { const int ctas = (n_items + WARPS - 1) / WARPS; return ctas < 1 ? 1 : (ctas > sm_count * 8 ? sm_count * 8 : ctas); }
+
+}  // namespace
+
+int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st) {
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+  const size_t sm_vis = WARPS * sizeof(WarpCtx) + WARPS * 48 * LDJ * sizeof(double);
+  const size_t sm_imu_nb = WARPS * sizeof(WarpCtx) + WARPS * 40 * LDJ * sizeof(double);
+  const size_t sm_imu_b = WARPS * sizeof(WarpCtx) + WARPS * 56 * LDJ * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    int e = 0;
+    e |= set_smem(vision_kernel<true>, sm_vis); e |= set_smem(vision_kernel<false>, sm_vis);
+    e |= set_smem(imu_kernel<true, false>, sm_imu_nb); e |= set_smem(imu_kernel<false, false>, sm_imu_nb);
+    e |= set_smem(imu_kernel<true, true>, sm_imu_b); e |= set_smem(imu_kernel<false, true>, sm_imu_b);
+    if (e) return 1;
+    attr_done = true;
+  }
+  if (P.n_vwork > 0 && P.rolling) {
+    const int grid = grid_for(P.n_vwork, sm_count);
+    if (with_jacobian) vision_kernel<true><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    else vision_kernel<false><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    count_launch();
+  }
+  if (P.n_iwork > 0) {
+    const int grid = grid_for(P.n_iwork, sm_count);
+    if (P.bias_active) {
+      if (with_jacobian) imu_kernel<true, true><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, true><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+    } else {
+      if (with_jacobian) imu_kernel<true, false><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, false><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
+    }
+    count_launch();
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,
+                            double* bg, double* ba, double* pose_q, double* pose_p, int* valid, cudaStream_t st) {
+  if (n <= 0) return;
+  trajectory_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, S, n, t_ns, start_ns, gyro, accel, bg, ba, pose_q, pose_p, valid);
+  count_launch();
+}
+
+}  // namespace icc

@@ -1,0 +1,86 @@
+// Shared host/device structs and kernel launch prototypes (internal to libicc_b200.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace icc {
+
+constexpr int SPLINE_N = 6;   // core/imu_camera_calibrator.h:27
+constexpr int BIAS_N = 3;     // basalt_spline/ceres_calib_split_residuals.h:21
+
+// Offsets inside the 26-double "globals" block of a state.
+enum { G_TIC = 0, G_GRAV = 7, G_LD = 10, G_ACC_INTR = 11, G_GYR_INTR = 17, G_COUNT = 26 };
+
+// One LM state in HBM.  Knots are padded to 32 B (x,y,z,w / x,y,z,0) for 16-byte vector loads.
+struct DeviceState {
+  double4* so3;
+  double4* r3;
+  double4* ba;
+  double4* bg;
+  double* glob;   // G_COUNT doubles
+};
+
+struct VisionWork { int frame, c_begin, c_end, pad; };
+struct ImuCell { int s_so3, s_r3, s_ba, s_bg; int i_begin, i_end; };
+
+struct DeviceProblem {
+  // camera
+  int model, dispatch_fov;
+  double intr[10];
+  const double4* board;
+  // vision: frames in CSR form
+  int n_frames, n_corners, rolling;
+  const int* f_off;          // n_frames + 1
+  const int* f_s_so3; const int* f_s_r3;
+  const double* f_u_so3; const double* f_u_r3;
+  const double2* uv;
+  const int* pid;
+  int n_vwork; const VisionWork* vwork;
+  // imu: samples sorted by time, grouped into cells sharing all knot windows
+  int n_imu;
+  const int64_t* imu_t_ns;   // relative to spline start (st_ns)
+  const double* imu_acc;     // 3 per sample
+  const double* imu_gyr;
+  int n_cells; const ImuCell* cells;
+  int n_iwork; const ImuCell* iwork;   // cells possibly split into sub-ranges
+  int64_t dt_so3_ns, dt_r3_ns, dt_ba_ns, dt_bg_ns;
+  double inv_so3_dt, inv_r3_dt;
+  double w_acc, w_gyr;
+  int n_so3, n_r3, n_ba, n_bg;
+  // active-set column maps (solver ordering); -1 = constant block
+  const int* so3_col; const int* r3_col; const int* ba_col; const int* bg_col;
+  int col_tic, col_g, col_ld;
+  int bias_active;           // any bias block active -> wide IMU tiles
+  // normal equations: [band nk x ldb][E nk x nb][C nb x nb (lower)][g nk+nb][cost][pad]
+  int nk, nb, kd, ldb;
+  double* ne;
+  int64_t ne_off_E, ne_off_C, ne_off_g, ne_off_cost, ne_size;
+  // residual layout
+  int n_res_vis, n_res_acc, n_res_gyr;
+};
+
+struct SolveParams {
+  double radius, min_diag, max_diag;
+  int jacobi_scaling;
+};
+
+// scal[] layout written by the solver / update kernels and read back by the host each LM iteration
+enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK = 4, SC_GRAD_MAX = 5, SC_REPROJ_SUM = 6, SC_REPROJ_CNT = 7, SC_COUNT = 8 };
+
+// ---- launches (all asynchronous on `st`) ----------------------------------------------------------------------
+// residuals + analytic Jacobians + J^T J / J^T r tiles reduced into P.ne (must be zeroed first), or cost only into *cost
+int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st);
+// scale[i] = 1/(1+sqrt(H_ii)) (Jacobi scaling, computed once per optimize) ; gradient inf-norm
+void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, double* scal, cudaStream_t st);
+// banded + bordered Cholesky solve of (S H S + D) y = -S g ; delta = S y (solver order) ; model cost change
+void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st);
+size_t solve_workspace_doubles(const DeviceProblem& P);
+// candidate = Plus(current, delta) ; step / x squared norms
+void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st);
+// trajectory getters
+void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,
+                            double* bg, double* ba, double* pose_q, double* pose_p, int* valid, cudaStream_t st);
+// dense dump of the packed normal equations into canonical order (tests)
+int kernel_launch_count();
+
+}  // namespace icc

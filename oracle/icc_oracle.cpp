@@ -855,14 +855,18 @@ icc_status icco_get_line_delay(const void* h, double* ld) { *ld = O(h)->line_del
 icc_status icco_get_num_knots(const void* h, int* a, int* b, int* c, int* d) { const Oracle& o = *O(h); if (a) *a = nknots(o.so3, 4); if (b) *b = nknots(o.r3, 3); if (c) *c = nknots(o.ba, 3); if (d) *d = nknots(o.bg, 3); return ICC_OK; }
 icc_status icco_get_knots(const void* h, double* so3, double* r3, double* ba, double* bg) {
   const Oracle& o = *O(h);
-  if (so3) std::copy(o.so3.begin(), o.so3.end(), so3); if (r3) std::copy(o.r3.begin(), o.r3.end(), r3);
-  if (ba) std::copy(o.ba.begin(), o.ba.end(), ba); if (bg) std::copy(o.bg.begin(), o.bg.end(), bg);
+  if (so3) std::copy(o.so3.begin(), o.so3.end(), so3);
+  if (r3) std::copy(o.r3.begin(), o.r3.end(), r3);
+  if (ba) std::copy(o.ba.begin(), o.ba.end(), ba);
+  if (bg) std::copy(o.bg.begin(), o.bg.end(), bg);
   return ICC_OK;
 }
 icc_status icco_set_knots(void* h, const double* so3, const double* r3, const double* ba, const double* bg) {
   Oracle& o = *O(h);
-  if (so3) std::copy(so3, so3 + o.so3.size(), o.so3.begin()); if (r3) std::copy(r3, r3 + o.r3.size(), o.r3.begin());
-  if (ba) std::copy(ba, ba + o.ba.size(), o.ba.begin()); if (bg) std::copy(bg, bg + o.bg.size(), o.bg.begin());
+  if (so3) std::copy(so3, so3 + o.so3.size(), o.so3.begin());
+  if (r3) std::copy(r3, r3 + o.r3.size(), o.r3.begin());
+  if (ba) std::copy(ba, ba + o.ba.size(), o.ba.begin());
+  if (bg) std::copy(bg, bg + o.bg.size(), o.bg.begin());
   return ICC_OK;
 }
 icc_status icco_set_T_i_c(void* h, const double T[7]) { memcpy(O(h)->T_ic, T, 7 * sizeof(double)); return ICC_OK; }

@@ -178,6 +178,8 @@ icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residual
 icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summary);
 /* Run `n` bare residual+Jacobian+normal-equation evaluations (the residual-eval kernels only); device ms per evaluation. */
 icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval);
+/* The handle's cudaStream_t (so that callers can bracket calls with their own CUDA events on the launching stream). */
+void* icc_get_stream(icc_handle* h);
 
 #ifdef __cplusplus
 }

@@ -218,6 +218,10 @@ class CApi:
                    out["valid"].ctypes.data_as(c_int32_p))
         return out
 
+    def get_stream(self) -> int:
+        f = self._fn("get_stream"); f.restype = C.c_void_p; f.argtypes = [C.c_void_p]
+        return int(f(self.h) or 0)
+
     # ---- test / measurement surface --------------------------------------------------------------------------
     def num_residuals(self):
         v, a, g = C.c_int(), C.c_int(), C.c_int()

@@ -299,15 +299,20 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     return ICC_OK;
   };
   if (n == 0) { if (out) *out = S; return ICC_OK; }
-  rc = jac(); if (rc != ICC_OK) return rc;
-  rc = read_cost_and_grad(true); if (rc != ICC_OK) return rc;
-  S.initial_cost = x_cost;
-  if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost");
   double radius = h->opt.initial_trust_region_radius, decrease_factor = 2.0;
   int invalid = 0;
+  bool ne_valid = false, first = true;
   S.termination = 0;
-  if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; max_iters = 0; }
   for (int it = 0; it < max_iters; ++it) {
+    // The Jacobian / normal equations are (re)built lazily at the top of the iteration that needs them, so that n
+    // iterations cost n linear solves + n cost evaluations + one Jacobian evaluation per accepted step (and the first).
+    if (!ne_valid) {
+      rc = jac(); if (rc != ICC_OK) return rc;
+      rc = read_cost_and_grad(first); if (rc != ICC_OK) return rc;
+      ne_valid = true;
+      if (first) { S.initial_cost = x_cost; first = false; if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost"); }
+      if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; break; }
+    }
     ++S.iterations;
     CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
     SolveParams sp; sp.radius = radius; sp.min_diag = h->opt.min_lm_diagonal; sp.max_diag = h->opt.max_lm_diagonal; sp.jacobi_scaling = h->opt.jacobi_scaling;
@@ -337,17 +342,16 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     if (rel > h->opt.min_relative_decrease) {               // HandleSuccessfulStep
       ++S.successful_steps;
       h->cur = cand; h->state_dirty_host = true;
-      rc = jac(); if (rc != ICC_OK) return rc;
-      rc = read_cost_and_grad(false); if (rc != ICC_OK) return rc;
+      x_cost = cand_cost; ne_valid = false;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(h->opt.max_trust_region_radius, radius);
       decrease_factor = 2.0;
-      if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; break; }
     } else {                                                  // StepRejected
       radius /= decrease_factor; decrease_factor *= 2.0;
       if (radius < h->opt.min_trust_region_radius) { S.termination = 4; break; }
     }
   }
+  if (first) { rc = jac(); if (rc != ICC_OK) return rc; rc = read_cost_and_grad(true); if (rc != ICC_OK) return rc; S.initial_cost = x_cost; }
   CU(cudaStreamSynchronize(h->stream));
   S.final_cost = x_cost;
   auto span_s = [&](const std::vector<std::pair<int, int>>& v) { double tot = 0; for (auto& p : v) { float ms = 0; cudaEventElapsedTime(&ms, ev[p.first], ev[p.second]); tot += ms; } return tot * 1e-3; };
@@ -750,7 +754,11 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
   CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
   CU(cudaEventRecord(e0, h->stream));
   for (int i = 0; i < n; ++i) {
-    if (with_jacobian) { s = eval_jacobian(h, h->st[h->cur].view(), nullptr); }
+    if (with_jacobian == 1) { s = eval_jacobian(h, h->st[h->cur].view(), nullptr); }
+    else if (with_jacobian == 2 || with_jacobian == 3) {   // one kernel family only (2 = vision, 3 = imu), Jacobian mode, no memset
+      DeviceProblem Q = h->P; if (with_jacobian == 2) Q.n_iwork = 0; else Q.n_vwork = 0;
+      s = launch_eval(Q, h->st[h->cur].view(), true, nullptr, nullptr, nullptr, h->stream) ? fail(h, ICC_ERR_CUDA, "eval launch failed") : ICC_OK;
+    }
     else { s = eval_cost(h, h->st[h->cur].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); }
     if (s != ICC_OK) return s;
   }
@@ -761,5 +769,7 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
   *ms_per_eval = ms / n;
   return ICC_OK;
 }
+
+void* icc_get_stream(icc_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 }  // extern "C"

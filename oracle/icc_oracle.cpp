@@ -79,6 +79,7 @@ struct Oracle {
   std::vector<Frame> frames;
   std::vector<ImuUsed> imu_used;
   std::vector<Block> blocks;
+  std::vector<Block> vis_blocks;   // RS vision blocks of every view, always built (GetMeanReprojectionError uses them even on the GS path)
   int n_res_vis = 0, n_res_acc = 0, n_res_gyr = 0;
   // active set / ordering (rebuilt per flags)
   int cur_flags = -1;
@@ -539,8 +540,7 @@ int total_residuals(const Oracle& o) { return o.n_res_vis + o.n_res_acc + o.n_re
 double mean_reproj_error(Oracle& o) {
   double sum = 0; int num = 0;
   Scratch s;
-  for (const auto& b : o.blocks) {
-    if (b.type != BLK_RS_VISION) continue;
+  for (const auto& b : o.vis_blocks) {
     int nc; eval_block(o, b, s, false, nc);
     for (int i = 0; i < b.n_res / 2; ++i) {
       const double rx = s.res[2 * i], ry = s.res[2 * i + 1];
@@ -565,20 +565,26 @@ void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_s
   Normal ne;
   double x_cost = 0;
   auto eval_jac = [&]() { auto t0 = clk::now(); evaluate(o, &x_cost, nullptr, &ne, nullptr, nres); t_jac += std::chrono::duration<double>(clk::now() - t0).count(); ++S.jacobian_evaluations; };
-  eval_jac();
-  S.initial_cost = x_cost;
-  std::vector<double> scale(n, 1.0);   // solver order
+  std::vector<double> scale;   // solver order
   auto diagH = [&](int i) { return i < ne.nk ? ne.band[size_t(i) * (ne.kd + 1)] : ne.C[size_t(i - ne.nk) * ne.nb + (i - ne.nk)]; };
-  if (o.opt.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(diagH(i)));
   double radius = o.opt.initial_trust_region_radius, decrease_factor = 2.0;
-  bool reuse_diagonal = false;
+  bool reuse_diagonal = false, ne_valid = false, first = true;
   std::vector<double> diag(n, 0.0), D2(n), rhs(n), y(n), delta_canon(n);
   int invalid = 0;
   S.termination = 0;
   auto grad_max = [&]() { double m = 0; for (double v : ne.g) m = std::max(m, std::fabs(v)); return m; };
-  if (check_convergence && grad_max() <= o.opt.gradient_tolerance) { S.termination = 3; max_iters = 0; }
   Normal sc;
   for (int it = 0; it < max_iters; ++it) {
+    // Jacobian rebuilt lazily at the top of the iteration that needs it (same schedule as the CUDA driver)
+    if (!ne_valid) {
+      eval_jac(); ne_valid = true;
+      if (first) {
+        first = false; S.initial_cost = x_cost;
+        scale.assign(n, 1.0);
+        if (o.opt.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(diagH(i)));
+      }
+      if (check_convergence && grad_max() <= o.opt.gradient_tolerance) { S.termination = 3; break; }
+    }
     ++S.iterations;
     // scaled system  Hs = S H S, gs = S g
     sc = ne;
@@ -617,16 +623,16 @@ void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_s
     const double rel_dec = cost_change / model_change;
     if (rel_dec > o.opt.min_relative_decrease) {
       ++S.successful_steps;
-      eval_jac();
+      x_cost = cand_cost; ne_valid = false;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel_dec - 1.0, 3)); radius = std::min(o.opt.max_trust_region_radius, radius);
       decrease_factor = 2.0; reuse_diagonal = false;
-      if (check_convergence && grad_max() <= o.opt.gradient_tolerance) { S.termination = 3; break; }
     } else {
       load_state(o, snap);
       radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
       if (radius < o.opt.min_trust_region_radius) { S.termination = 4; break; }
     }
   }
+  if (first) { eval_jac(); S.initial_cost = x_cost; }
   S.final_cost = x_cost;
   S.seconds_jacobian = t_jac; S.seconds_linear_solve = t_lin;
   S.seconds_total = std::chrono::duration<double>(clk::now() - t_start).count();
@@ -735,7 +741,7 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
 
   // ---- measurement wiring ---------------------------------------------------------------------------------
   // Shards (icc_set_shard): time-sorted residual units are cut into `world` slices of equal scalar-residual count.
-  o.frames.clear(); o.blocks.clear(); o.imu_used.clear();
+  o.frames.clear(); o.blocks.clear(); o.vis_blocks.clear(); o.imu_used.clear();
   o.n_res_vis = o.n_res_acc = o.n_res_gyr = 0;
   struct Unit { double t; int kind; int idx; int nres; };
   std::vector<Unit> units;
@@ -767,7 +773,6 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
   for (int fi : frame_sel) {
     const Frame& f = all_frames[fi];
     o.frames.push_back(f);
-    if (!rolling) continue;
     Block b; b.type = BLK_RS_VISION; b.frame = int(o.frames.size()) - 1; b.n_res = 2 * (f.c1 - f.c0); b.res_off = res_vis; res_vis += b.n_res;
     b.u_so3 = f.u_so3; b.u_r3 = f.u_r3; b.u_bias = 0;
     for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.so3[4 * (f.s_so3 + i)], 4, LP_SO3, -1});
@@ -775,8 +780,10 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
     b.params.push_back({o.T_ic, 7, LP_SE3, -1});
     b.params.push_back({&o.line_delay, 1, LP_NONE, -1});
     for (int c = f.c0; c < f.c1; ++c) b.params.push_back({&o.points[4 * size_t(o.point_ids[c])], 4, LP_NONE, -1});
-    o.blocks.push_back(std::move(b));
+    o.vis_blocks.push_back(b);
+    if (rolling) o.blocks.push_back(std::move(b));
   }
+  if (!rolling) res_vis = 0;
   o.n_res_vis = res_vis;
   // IMU blocks: accelerometer residuals first, then gyroscope residuals, both in time order
   std::vector<Block> acc_blocks, gyr_blocks;
@@ -836,7 +843,7 @@ icc_status icco_optimize(void* h, int max_iters, int flags, icc_summary* S) {
   if (!o.initialised) { o.err = "batch_init_spline first"; return ICC_ERR_STATE; }
   if (!configure(o, flags)) return ICC_ERR_UNSUPPORTED;
   icc_summary s; lm_solve(o, max_iters, flags, true, s);
-  s.mean_reproj_error = o.n_res_vis ? mean_reproj_error(o) : 0.0;
+  s.mean_reproj_error = o.vis_blocks.empty() ? 0.0 : mean_reproj_error(o);
   if (S) *S = s;
   return ICC_OK;
 }

@@ -1,0 +1,99 @@
+"""The C-ABI library loads, exports every symbol include/icc_b200.h declares, refuses to compute without a GPU, and its
+host-side problem assembly (BatchInitSpline) agrees with the oracle's restatement of the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from openimucameracalibrator_b200 import _capi as capi
+from openimucameracalibrator_b200 import calibrator
+from openimucameracalibrator_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "icc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(icc_[a-z0-9_]+)\s*\(", text)) - {"icc_allreduce_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = calibrator.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/icc_b200.h but not exported"
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device path is exercised on the CPU box")
+    with pytest.raises(capi.IccError, match="ICC_ERR_NO_DEVICE"):
+        capi.CApi(calibrator.load_library(), "icc_", 0)
+    # a host-only handle can assemble but must refuse every compute entry point
+    h = capi.CApi(calibrator.load_library(), "icc_", -1)
+    capi.load_dataset(h, syn.make_dataset(syn.tiny_config()))
+    for call in (lambda: h.optimize(1, 66), lambda: h.evaluate(66), lambda: h.lm_iterations(1, 66), lambda: h.mean_reprojection_error(),
+                 lambda: h.eval_trajectory([0]), lambda: h.time_evaluations(1, 66)):
+        with pytest.raises(capi.IccError, match="ICC_ERR_NO_DEVICE"):
+            call()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(calibrator, "_LIB", None)
+    monkeypatch.setattr(calibrator, "library_path", lambda: str(tmp_path / "libicc_b200.so"))
+    with pytest.raises(capi.IccError, match="no CPU fallback"):
+        calibrator.load_library()
+
+
+def test_product_package_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "openimucameracalibrator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "libicc_oracle" not in text and "icc_oracle" not in text and "oracle_api" not in text and "icco_" not in text.replace("`icco_`", ""), f
+
+
+@pytest.mark.parametrize("cfg", [syn.tiny_config(), syn.tiny_config(dt_so3_s=0.04, dt_r3_s=0.07), syn.CONFIGS[1]], ids=["tiny", "tiny_uneven_dt", "cfg1"])
+def test_host_assembly_matches_oracle(oracle_factory, cfg):
+    """Knot counts, knot initialisation (slerp/lerp quirks), kept IMU samples, residual counts, gravity init."""
+    ds = syn.make_dataset(cfg)
+    o = oracle_factory(); capi.load_dataset(o, ds, known_gravity=False)
+    h = capi.CApi(calibrator.load_library(), "icc_", -1); capi.load_dataset(h, ds, known_gravity=False)
+    assert o.num_knots() == h.num_knots()
+    assert o.num_residuals() == h.num_residuals()
+    for a, b in zip(o.get_knots(), h.get_knots()):
+        assert np.array_equal(a, b) or np.allclose(a, b, rtol=0, atol=1e-15)
+    for a, b in zip(o.imu_used(), h.imu_used()):
+        assert np.array_equal(a, b)
+    assert np.allclose(o.get_gravity(), h.get_gravity(), rtol=0, atol=1e-14)
+    assert np.allclose(o.get_T_i_c(), h.get_T_i_c(), rtol=0, atol=1e-15)
+    for flags in (66, 66 | 16 | 32 | 4, 32):
+        assert o.num_tangent(flags) == h.num_tangent(flags)
+
+
+def test_shards_partition_the_residuals(oracle_factory):
+    ds = syn.make_dataset(syn.tiny_config())
+    full = capi.CApi(calibrator.load_library(), "icc_", -1); capi.load_dataset(full, ds)
+    tot = np.zeros(3, dtype=int)
+    for r in range(3):
+        h = capi.CApi(calibrator.load_library(), "icc_", -1); capi.load_dataset(h, ds, shard=(r, 3))
+        o = oracle_factory(); capi.load_dataset(o, ds, shard=(r, 3))
+        assert h.num_residuals() == o.num_residuals()
+        tot += np.array(h.num_residuals())
+    assert tuple(tot) == full.num_residuals()
+
+
+def test_invalid_arguments_are_reported():
+    h = capi.CApi(calibrator.load_library(), "icc_", -1)
+    with pytest.raises(capi.IccError, match="INVALID_ARGUMENT"):
+        h.set_camera(4, [1.0, 2.0], 10, 10)           # wrong intrinsic count
+    with pytest.raises(capi.IccError, match="STATE"):
+        h.batch_init_spline(np.array([0, 0, 0, 1, 0, 0, 0.0]), 0.05, 0.05, 1, 1, 0, 1e-5)
+    with pytest.raises(capi.IccError, match="INVALID_ARGUMENT"):
+        h.set_shard(3, 2)

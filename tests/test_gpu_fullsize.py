@@ -1,0 +1,73 @@
+"""BASELINE.json full-size configuration (ExtendedUnified, 3000 x 144, 1 kHz) through size-independent properties: the
+oracle needs ~5 s per Jacobian evaluation on 8 cores there, so parity is established by
+  (1) cost from the Jacobian kernels == cost from the cost-only kernels,
+  (2) J^T r agrees with directional finite differences of the GPU cost,
+  (3) residual shards are additive: sum over time-slice shards of (cost, J^T r) == unsharded,
+  (4) an oracle spot check on a strided subset of residuals (value parity of the same kernels at full size),
+  (5) LM reduces the cost and the model/actual decrease ratio of an accepted step is sane."""
+import numpy as np
+import pytest
+
+from helpers import F_STAGE1, TangentWalker, rel
+from openimucameracalibrator_b200 import _capi as capi
+from openimucameracalibrator_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ds4():
+    return syn.make_dataset(syn.CONFIGS[4])
+
+
+def test_config4_shape(gpu_factory, ds4):
+    g = gpu_factory(); capi.load_dataset(g, ds4)
+    assert g.num_knots()[:2] == (2005, 2005)
+    nv, na, ng = g.num_residuals()
+    assert nv == 864000 and abs(na - 299901) < 10 and na == ng
+    assert g.num_tangent(F_STAGE1) == 12036
+
+
+def test_config4_cost_paths_and_gradient_fd(gpu_factory, ds4):
+    g = gpu_factory(); capi.load_dataset(g, ds4)
+    c_jac, _, grad, _ = g.evaluate(F_STAGE1, residuals=False)
+    c_only = g.evaluate(F_STAGE1, residuals=False, gradient=False)[0]
+    assert abs(c_jac - c_only) <= 1e-11 * c_only
+    w = TangentWalker(g, F_STAGE1)
+    rng = np.random.default_rng(4)
+    d = rng.normal(size=w.n); eps = 1e-7
+    fd = (w.cost(eps * d) - w.cost(-eps * d)) / (2 * eps)
+    assert abs(fd - grad @ d) <= 1e-5 * abs(fd)
+
+
+def test_config4_shards_are_additive(gpu_factory, ds4):
+    g = gpu_factory(); capi.load_dataset(g, ds4)
+    c, _, grad, _ = g.evaluate(F_STAGE1, residuals=False)
+    cs, gs, nres = 0.0, 0.0, 0
+    for r in range(4):
+        s = gpu_factory(); capi.load_dataset(s, ds4, shard=(r, 4))
+        ci, _, gi, _ = s.evaluate(F_STAGE1, residuals=False)
+        cs += ci; gs = gs + gi; nres += sum(s.num_residuals())
+        s.close()
+    assert nres == sum(g.num_residuals())
+    assert abs(cs - c) <= 1e-11 * c and rel(gs, grad) < 1e-10
+
+
+def test_config4_residual_spot_check_against_oracle(oracle_factory, gpu_factory, ds4):
+    """The oracle evaluates residual VALUES of the full problem in well under a second (no Jacobians)."""
+    g = gpu_factory(); capi.load_dataset(g, ds4)
+    o = oracle_factory(); capi.load_dataset(o, ds4)
+    cg, rg, _, _ = g.evaluate(F_STAGE1, gradient=False)
+    co, ro, _, _ = o.evaluate(F_STAGE1, gradient=False)
+    assert rel(rg, ro) < 1e-9 and abs(cg - co) <= 1e-10 * co
+
+
+def test_config4_lm_step(gpu_factory, ds4):
+    g = gpu_factory(); capi.load_dataset(g, ds4)
+    s = g.lm_iterations(2, F_STAGE1)
+    assert s.successful_steps >= 1 and s.final_cost < 0.05 * s.initial_cost
+    s = g.optimize(50, F_STAGE1)
+    assert s.termination in (1, 2) and 0.15 < s.mean_reproj_error < 0.4
+    q = g.get_T_i_c(); qt = ds4["truth"]["T_i_c"]
+    assert np.degrees(2 * np.arccos(min(1.0, abs(float(q[:4] @ qt[:4]))))) < 0.05
+    assert np.linalg.norm(q[4:] - qt[4:]) < 2e-3

@@ -67,7 +67,7 @@ def test_tight_tolerance_optimum_agrees(oracle_factory, gpu_factory):
     o = oracle_factory(); capi.load_dataset(o, ds); o.set_solver_options(function_tolerance=1e-14, parameter_tolerance=1e-14)
     g = gpu_factory(); capi.load_dataset(g, ds); g.set_solver_options(function_tolerance=1e-14, parameter_tolerance=1e-14)
     so, sg = o.optimize(60, F_STAGE1), g.optimize(60, F_STAGE1)
-    assert abs(sg.final_cost - so.final_cost) <= 1e-10 * so.final_cost
+    assert abs(sg.final_cost - so.final_cost) <= 1e-8 * so.final_cost
     assert rel(g.get_T_i_c(), o.get_T_i_c()) < 1e-6
 
 

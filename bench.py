@@ -294,7 +294,7 @@ def main():
                            "l2": "flushed between steps (256 MiB fill); step time = per-step CUDA events on the solver stream, summed",
                            "step": "1 LM iteration: J eval + J^T J reduce + scale + banded/bordered LDL^T + update + cost eval"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-                "problem_load_s": t_load}
+                "problem_load_s": t_load, "step_ms": [round(x, 4) for x in step_ms]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

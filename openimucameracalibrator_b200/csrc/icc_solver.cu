@@ -61,50 +61,177 @@ __device__ __forceinline__ double lm_d2(const DeviceProblem& P, const double* sc
   return fmin(fmax(d * s * s, sp.min_diag), sp.max_diag) / sp.radius;
 }
 
-// Update descriptors of one column elimination: value = col[srcA] * col[srcB] / pivot is subtracted from
-//   window column (j + dc) at offset dst            (dc != 0xFFFF)   — band x band and border x band entries
-//   the dense local-border block at offset dst       (dc == 0xFFFF)   — border x border entries
-__device__ void build_descriptors(ushort4* desc, int kd, int ldb, int nbl) {
+constexpr int KB = 8;             // panel width of the blocked LDL^T
+
+// Blocked right-looking LDL^T inside a circular shared-memory window.
+//
+// Window column layout (CL doubles): [band part, ldbp = kd + KB entries, offsets > kd are zero padding][local border rows, nbl].
+// Per panel of KB columns:
+//   (1) KB sequential column steps that only update the OTHER PANEL columns (<= (KB-1)(kd+1+nbl) entries, 1 sync each);
+//   (2) one rank-KB update of the whole trailing window + the dense local-border block (T entries, KB terms each, 1 sync).
+// Thanks to the zero padding no term needs a bounds test: an out-of-band operand reads 0.
+// Trailing descriptors (ushort4): x = A0 | (sA << 15), y = B0 | (sB << 15), z = destination column offset from the panel
+// start (0xFFFF: dense border block), w = destination offset.  Term jj reads col_jj[A0 - jj*sA] * col_jj[B0 - jj*sB] / D_jj.
+__device__ void build_trailing_descriptors(ushort4* desc, int kd, int ldbp, int nbl) {
   const int np = kd * (kd + 1) / 2, nbb = nbl * kd, ncc = nbl * (nbl + 1) / 2;
   for (int idx = threadIdx.x; idx < np + nbb + ncc; idx += blockDim.x) {
     ushort4 d;
-    if (idx < np) { const int r0 = tri_row(idx), c0 = idx - r0 * (r0 + 1) / 2; const int r = r0 + 1, c = c0 + 1; d = make_ushort4(r, c, c, r - c); }
-    else if (idx < np + nbb) { const int k = idx - np, b = k / kd, c = k % kd + 1; d = make_ushort4(ldb + b, c, c, ldb + b); }
-    else { const int k = idx - np - nbb, b = tri_row(k), c = k - b * (b + 1) / 2; d = make_ushort4(ldb + b, ldb + c, 0xFFFF, b * nbl + c); }
+    if (idx < np) {            // band x band: destination column Coff = KB + D, rows Roff = Coff .. KB-1+kd
+      const int q = tri_row(idx), k = idx - q * (q + 1) / 2;      // q = kd-1-D (rows available - 1), k = row index within column
+      const int D = kd - 1 - q, Coff = KB + D, Roff = Coff + k;
+      d = make_ushort4(Roff | 0x8000, Coff | 0x8000, Coff, Roff - Coff);
+    } else if (idx < np + nbb) {
+      const int k = idx - np, b = k / kd, Coff = KB + k % kd;
+      d = make_ushort4(ldbp + b, Coff | 0x8000, Coff, ldbp + b);
+    } else {
+      const int k = idx - np - nbb, b1 = tri_row(k), b2 = k - b1 * (b1 + 1) / 2;
+      d = make_ushort4(ldbp + b1, ldbp + b2, 0xFFFF, b1 * nbl + b2);
+    }
     desc[idx] = d;
   }
 }
+// Panel descriptors (ushort2): x = distance dc to the target panel column (1..KB-1), y = source offset in the pivot column
+// (band offset dc..kd, or ldbp + b for a border row).  Sorted by dc so that pivot column jj uses the first pcount[KB-1-jj].
+__device__ void build_panel_descriptors(ushort2* pdesc, int* pcount, int kd, int ldbp, int nbl) {
+  const int per0 = kd + 1 + nbl;   // entries for dc = 0 (unused); dc has per0 - dc entries
+  if (threadIdx.x == 0) { int acc = 0; pcount[0] = 0; for (int dc = 1; dc < KB; ++dc) { acc += per0 - dc; pcount[dc] = acc; } }
+  __syncthreads();
+  const int total = pcount[KB - 1];
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int dc = 1; while (idx >= pcount[dc]) ++dc;
+    const int k = idx - pcount[dc - 1];
+    const int nband = kd - dc + 1;
+    pdesc[idx] = k < nband ? make_ushort2(dc, dc + k) : make_ushort2(dc, ldbp + (k - nband));
+  }
+}
 
-// LDL^T elimination of columns [j_begin, j_end) of a banded matrix with dense "local border" rows, through a circular
-// shared-memory window of WS column slots (each CL = ldb + nbl doubles).  load(col, e) returns the (scaled, damped)
-// original entry e of column col (0 outside the matrix); store(col, e, v) receives every finished column (unscaled
-// LDL^T storage: entry 0 = pivot D_j, others = L_ij D_j).  On return the window still holds the updated columns
-// [j_end, j_end + kd].  Returns false on a non-positive pivot.
+struct FactorSmem { double* W; double* Cl; ushort4* desc; ushort2* pdesc; int* pcount; double* inv; int T; };
+
+// LDL^T elimination of columns [j_begin, j_end).  load(col, e) returns the (scaled, damped) original entry e of column col
+// (0 outside the matrix AND for the padding offsets kd < e < ldbp); store(col, e, v) receives every finished column
+// (unscaled storage: entry 0 = pivot D_j, others = L_ij D_j).  On return the window holds the updated columns >= j_end.
 template <class Load, class Store>
-__device__ bool factor_range(double* W, double* Cl, const ushort4* desc, int T, int j_begin, int j_end, int kd, int CL, int WS, Load load, Store store) {
-  const int tid = threadIdx.x, nt = blockDim.x, PB = WS - kd - 1, mask = WS - 1;
+__device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int kd, int ldbp, int CL, int WS, Load load, Store store) {
+  const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1;
+  const int PB = ((WS - kd) / KB) * KB;
+  double* W = fs.W;
   for (int j0 = j_begin; j0 < j_end; j0 += PB) {
-    const int first = j0 == j_begin ? j_begin : j0 + kd + 1, last = j0 + PB + kd + 1;
+    const int first = j0 == j_begin ? j_begin : j0 + kd, last = j0 + PB + kd;
     for (int idx = tid; idx < (last - first) * CL; idx += nt) { const int col = first + idx / CL, e = idx % CL; W[(size_t)(col & mask) * CL + e] = load(col, e); }
     __syncthreads();
-    const int jend = min(j0 + PB, j_end);
-    for (int j = j0; j < jend; ++j) {
-      const double* cj = W + (size_t)(j & mask) * CL;
-      const double piv = cj[0];
-      if (!(piv > 0.0) || !isfinite(piv)) return false;       // uniform: every thread reads the same pivot
-      const double inv = 1.0 / piv;
-      for (int idx = tid; idx < T; idx += nt) {
-        const ushort4 d = desc[idx];
-        const double v = cj[d.x] * cj[d.y] * inv;
-        double* dst = d.z == 0xFFFF ? Cl + d.w : W + (size_t)((j + d.z) & mask) * CL + d.w;
-        *dst -= v;
+    const int gend = min(j0 + PB, j_end);
+    for (int jp = j0; jp < gend; jp += KB) {
+      const int kb = min(KB, gend - jp);
+      // (1) panel factorisation
+      for (int jj = 0; jj < kb; ++jj) {
+        const int j = jp + jj;
+        double* cj = W + (size_t)(j & mask) * CL;
+        const double piv = cj[0];
+        if (!(piv > 0.0) || !isfinite(piv)) return false;     // uniform: every thread reads the same pivot
+        const double inv = 1.0 / piv;
+        if (tid == 0) fs.inv[jj] = inv;
+        const int cnt = fs.pcount[KB - 1 - jj];
+        for (int idx = tid; idx < cnt; idx += nt) {
+          const ushort2 d = fs.pdesc[idx];
+          const int dst = d.y < ldbp ? d.y - d.x : d.y;
+          W[(size_t)((j + d.x) & mask) * CL + dst] -= cj[d.y] * cj[d.x] * inv;
+        }
+        __syncthreads();
+      }
+      if (tid < KB - kb) fs.inv[kb + tid] = 0.0;               // short last panel: missing columns contribute nothing
+      __syncthreads();
+      // (2) rank-kb trailing update
+      const double* pb[KB]; double iv[KB];
+#pragma unroll
+      for (int jj = 0; jj < KB; ++jj) { pb[jj] = W + (size_t)((jp + jj) & mask) * CL; iv[jj] = fs.inv[jj]; }
+      for (int idx = tid; idx < fs.T; idx += nt) {
+        const ushort4 d = fs.desc[idx];
+        const int A0 = d.x & 0x7FFF, sA = d.x >> 15, B0 = d.y & 0x7FFF, sB = d.y >> 15;
+        double acc = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < KB; ++jj) acc = fma(pb[jj][A0 - jj * sA] * iv[jj], pb[jj][B0 - jj * sB], acc);
+        double* dst = d.z == 0xFFFF ? fs.Cl + d.w : W + (size_t)((jp + d.z) & mask) * CL + d.w;
+        *dst -= acc;
       }
       __syncthreads();
     }
-    for (int idx = tid; idx < (jend - j0) * CL; idx += nt) { const int col = j0 + idx / CL, e = idx % CL; store(col, e, W[(size_t)(col & mask) * CL + e]); }
+    for (int idx = tid; idx < (gend - j0) * CL; idx += nt) { const int col = j0 + idx / CL, e = idx % CL; store(col, e, W[(size_t)(col & mask) * CL + e]); }
     __syncthreads();
   }
   return true;
+}
+
+// Descending back-substitution of the band part, driven by ONE warp whose registers hold the sliding window of pending
+// right-hand sides (32*NR >= kd + 1 slots); x_j is broadcast with a shuffle, so the per-column dependency chain is
+// select -> SHFL -> DMUL -> DFMA instead of shared-memory round trips.  tw[col - base] holds t on entry and x on exit.
+// Columns >= unknown_end are known values (x = t, no pivot) that only scatter into the unknown ones.
+template <int NR>
+__device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, win = 32 * NR;
+  double t[NR]; int r[NR];
+  if (tid < 32) {
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      int rr = ((top - 1 - lane - 32 * k) % win + win) % win;   // distance from column top-1 to this slot's column
+      r[k] = rr; const int col = top - 1 - rr;
+      t[k] = col >= base ? tw[col - base] : 0.0;
+    }
+  }
+  for (int hi = top; hi > base; hi -= PB) {
+    const int lo_own = max(base, hi - PB), lo = max(base, lo_own - kd);
+    for (int idx = tid; idx < (hi - lo) * ldb; idx += nt) { const int col = lo + idx / ldb; Bw[idx] = col < unknown_end ? Lb_g[(int64_t)lo * ldb + idx] : 0.0; }
+    __syncthreads();
+    if (tid < 32) {
+      for (int j = hi - 1; j >= lo_own; --j) {
+        const int reg = (j % win) >> 5;
+        double l[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) { const int c = j - r[k]; l[k] = (r[k] >= 1 && r[k] <= kd && c >= base && c < unknown_end) ? Bw[(size_t)(c - lo) * ldb + r[k]] : 0.0; }
+        const double ipiv = j < unknown_end ? 1.0 / Bw[(size_t)(j - lo) * ldb] : 1.0;
+        double v = t[0];
+#pragma unroll
+        for (int k = 1; k < NR; ++k) if (k == reg) v = t[k];
+        const double xj = __shfl_sync(0xffffffffu, v, j & 31) * ipiv;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) t[k] = fma(-l[k], xj, t[k]);
+        if (lane == (j & 31)) {
+          tw[j - base] = xj;
+          const int cnew = j - win;
+          const double tn = cnew >= base ? tw[cnew - base] : 0.0;
+#pragma unroll
+          for (int k = 0; k < NR; ++k) if (k == reg) t[k] = tn;
+        }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) r[k] = r[k] == 0 ? win - 1 : r[k] - 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+__device__ void backsub_dispatch(const double* Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB) {
+  if (kd < 64) backsub_warp<2>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+  else if (kd < 96) backsub_warp<3>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+  else if (kd < 128) backsub_warp<4>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+  else backsub_warp<8>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+}
+
+// shared-memory carve-up shared by kernels A and B
+__device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, int ldbp, double** extra, int extra_doubles) {
+  FactorSmem fs;
+  fs.W = sm;
+  fs.Cl = fs.W + (size_t)WS * CL;
+  double* p = fs.Cl + nbl * nbl;
+  *extra = p; p += extra_doubles;
+  fs.inv = p; p += KB;
+  fs.T = kd * (kd + 1) / 2 + nbl * kd + nbl * (nbl + 1) / 2;
+  fs.desc = reinterpret_cast<ushort4*>(p);
+  fs.pdesc = reinterpret_cast<ushort2*>(fs.desc + fs.T);
+  fs.pcount = reinterpret_cast<int*>(fs.pdesc + (KB - 1) * (kd + 1 + nbl));
+  return fs;
+}
+__host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int kd, int extra_doubles) {
+  const size_t T = (size_t)kd * (kd + 1) / 2 + (size_t)nbl * kd + (size_t)nbl * (nbl + 1) / 2;
+  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + KB) * sizeof(double) + T * sizeof(ushort4) + (size_t)(KB - 1) * (kd + 1 + nbl) * sizeof(ushort2) + (KB + 2) * sizeof(int) + 64;
 }
 
 // ---- kernel A: eliminate the interior knots of every time chunk ---------------------------------------------------
@@ -113,27 +240,27 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl, nbp = nb + 1;
   const int a = pl.a[c], b = pl.b[c];
   const bool has_left = c > 0, has_right = c < pl.P - 1;
-  const int CL = ldb + nbl, WS = pl.WS_A;
-  double* W = sm;
-  double* Cl = W + (size_t)WS * CL;
-  ushort4* desc = reinterpret_cast<ushort4*>(Cl + nbl * nbl);
-  const int T = kd * (kd + 1) / 2 + nbl * kd + nbl * (nbl + 1) / 2;
+  const int ldbp = kd + KB, CL = ldbp + nbl, WS = pl.WS_A;
+  double* extra;
+  const FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
+  double* W = fs.W; double* Cl = fs.Cl;
   const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
-  build_descriptors(desc, kd, ldb, nbl);
+  build_trailing_descriptors(fs.desc, kd, ldbp, nbl);
+  build_panel_descriptors(fs.pdesc, fs.pcount, kd, ldbp, nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
   __syncthreads();
   const int right_end = has_right ? b + w : b;
   auto load = [&](int col, int e) -> double {
     if (col >= right_end) return 0.0;
-    if (e < ldb) {
+    if (e < ldbp) {
       const int i = col + e;
-      if (i >= nk || i >= right_end) return 0.0;                // rows beyond the right separator belong to the next chunk
+      if (e > kd || i >= nk || i >= right_end) return 0.0;      // padding / rows beyond the right separator (next chunk's)
       double v = band[(int64_t)col * ldb + e] * scale[col] * scale[i];
       if (e == 0) v += lm_d2(P, scale, sp, col);
       return v;
     }
-    const int lb = e - ldb;
+    const int lb = e - ldbp;
     if (lb < w) {                                               // coupling to the left separator (stored transposed in H)
       if (!has_left || col >= b) return 0.0;
       const int s = a - w + lb, off = col - s;
@@ -142,24 +269,20 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
     if (lb < w + nb) return E[(int64_t)col * nb + (lb - w)] * scale[col] * scale[nk + lb - w];
     return -g[col] * scale[col];
   };
-  auto store = [&](int col, int e, double v) { if (e < ldb) ws.Lb[(int64_t)col * ldb + e] = v; else ws.El[(int64_t)col * nbl + (e - ldb)] = v; };
-  const bool ok = factor_range(W, Cl, desc, T, a, b, kd, CL, WS, load, store);
+  auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) ws.Lb[(int64_t)col * ldb + e] = v; } else ws.El[(int64_t)col * nbl + (e - ldbp)] = v; };
+  const bool ok = factor_range(fs, a, b, kd, ldbp, CL, WS, load, store);
   if (!ok) { if (threadIdx.x == 0) scal[SC_OK] = -1.0; return; }
   // ---- scatter the Schur complement of this chunk into the reduced system ------------------------------------------
   const int mask = WS - 1;
-  if (b == a) {   // empty interior (cannot happen with a valid plan) — still need the separator columns in the window
-    for (int idx = threadIdx.x; idx < (right_end - b) * CL; idx += blockDim.x) { const int col = b + idx / CL, e = idx % CL; W[(size_t)(col & mask) * CL + e] = load(col, e); }
-    __syncthreads();
-  }
   const int sl0 = (c - 1) * w, sr0 = c * w;                     // reduced indices of the left / right separator
   if (has_right) {
     for (int idx = threadIdx.x; idx < w * CL; idx += blockDim.x) {
       const int t = idx / CL, e = idx % CL, col = b + t;
       const double v = W[(size_t)(col & mask) * CL + e];
       if (v == 0.0) continue;
-      if (e < ldb) { if (t + e < w) atomicAdd(ws.bandr + (int64_t)(sr0 + t) * pl.ldbr + e, v); }
+      if (e < ldbp) { if (t + e < w) atomicAdd(ws.bandr + (int64_t)(sr0 + t) * pl.ldbr + e, v); }
       else {
-        const int lb = e - ldb;
+        const int lb = e - ldbp;
         if (lb < w) { if (has_left) atomicAdd(ws.bandr + (int64_t)(sl0 + lb) * pl.ldbr + (sr0 + t - sl0 - lb), v); }
         else atomicAdd(ws.Er + (int64_t)(sr0 + t) * nbp + (lb - w), v);
       }
@@ -179,16 +302,14 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
 __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
   extern __shared__ __align__(16) double sm[];
   const int nk = P.nk, nb = P.nb, nbp = nb + 1, nkr = pl.nkr, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w;
-  const int CL = ldbr + nbp, WS = pl.WS_B, tid = threadIdx.x, nt = blockDim.x;
-  double* W = sm;
-  double* Cs = W + (size_t)WS * CL;                 // nbp x nbp lower, row nb = rhs
-  double* xb = Cs + nbp * nbp;                      // nbp
-  ushort4* desc = reinterpret_cast<ushort4*>(xb + nbp + 1);
-  const int T = kdr * (kdr + 1) / 2 + nbp * kdr + nbp * (nbp + 1) / 2;
+  const int ldbp = kdr + KB, CL = ldbp + nbp, WS = pl.WS_B, tid = threadIdx.x, nt = blockDim.x;
+  double* xb;
+  const FactorSmem fs = carve_smem(sm, WS, CL, nbp, kdr, ldbp, &xb, nbp + 1);
+  double* W = fs.W; double* Cs = fs.Cl;           // nbp x nbp lower, row nb = rhs
   const double* C = P.ne + P.ne_off_C; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // a chunk hit a bad pivot
-  if (nkr > 0) build_descriptors(desc, kdr, ldbr, nbp);
+  if (nkr > 0) { build_trailing_descriptors(fs.desc, kdr, ldbp, nbp); build_panel_descriptors(fs.pdesc, fs.pcount, kdr, ldbp, nbp); }
   for (int idx = tid; idx < nbp * nbp; idx += nt) {
     const int b = idx / nbp, c = idx % nbp;
     double v = 0.0;
@@ -204,11 +325,11 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   if (nkr > 0) {
     auto load = [&](int col, int e) -> double {
       if (col >= nkr) return 0.0;
-      if (e < ldbr) return col + e < nkr ? ws.bandr[(int64_t)col * ldbr + e] : 0.0;
-      return ws.Er[(int64_t)col * nbp + (e - ldbr)];
+      if (e < ldbp) return (e <= kdr && col + e < nkr) ? ws.bandr[(int64_t)col * ldbr + e] : 0.0;
+      return ws.Er[(int64_t)col * nbp + (e - ldbp)];
     };
-    auto store = [&](int col, int e, double v) { if (e < ldbr) ws.Lbr[(int64_t)col * ldbr + e] = v; else ws.Elr[(int64_t)col * nbp + (e - ldbr)] = v; };
-    ok = factor_range(W, Cs, desc, T, 0, nkr, kdr, CL, WS, load, store);
+    auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kdr) ws.Lbr[(int64_t)col * ldbr + e] = v; } else ws.Elr[(int64_t)col * nbp + (e - ldbp)] = v; };
+    ok = factor_range(fs, 0, nkr, kdr, ldbp, CL, WS, load, store);
   }
   // border: dense LDL^T of the final Schur complement, rhs carried as the last row
   for (int j = 0; j < nb && ok; ++j) {
@@ -237,33 +358,15 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   }
   __syncthreads();
   for (int b = tid; b < nb; b += nt) ws.y[nk + b] = xb[b];
-  // separators: t_j = rhs_j - sum_b Elr[j][b] x_b, then descending scatter-form back-substitution (one warp)
-  for (int j = tid; j < nkr; j += nt) { const double* le = ws.Elr + (int64_t)j * nbp; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; ws.tr[j] = t; }
-  __syncthreads();
   if (nkr > 0) {
-    const int PB = 64;
-    double* Bw = W; double* tw = W + (size_t)(PB + kdr) * ldbr;
-    for (int hi = nkr; hi > 0; hi -= PB) {
-      const int lo_own = max(0, hi - PB), lo = max(0, lo_own - kdr);
-      for (int idx = tid; idx < (hi - lo) * ldbr; idx += nt) Bw[idx] = ws.Lbr[(int64_t)lo * ldbr + idx];
-      for (int idx = tid; idx < hi - lo; idx += nt) tw[idx] = ws.tr[lo + idx];
-      __syncthreads();
-      if (tid < 32) {
-        for (int j = hi - 1; j >= lo_own; --j) {
-          const int jl = j - lo;
-          const double xj = tw[jl] / Bw[(int64_t)jl * ldbr];
-          __syncwarp();
-          if (tid == 0) tw[jl] = xj;
-          for (int r = tid + 1; r <= kdr && r <= jl; r += 32) tw[jl - r] -= Bw[(int64_t)(jl - r) * ldbr + r] * xj;
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-      for (int idx = tid; idx < hi - lo_own; idx += nt) { const int rj = lo_own + idx; const int k = rj / w, tt = rj % w; ws.y[pl.b[k] + tt] = tw[lo_own - lo + idx]; }
-      for (int idx = tid; idx < lo_own - lo; idx += nt) ws.tr[lo + idx] = tw[idx];
-      __syncthreads();
-    }
+    // separators: t_j = rhs_j - sum_b Elr[j][b] x_b, then the register/shuffle back-substitution
+    double* tw = W; double* Bw = W + ((nkr + 3) & ~3);
+    for (int j = tid; j < nkr; j += nt) { const double* le = ws.Elr + (int64_t)j * nbp; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; tw[j] = t; }
+    __syncthreads();
+    backsub_dispatch(ws.Lbr, tw, Bw, 0, nkr, nkr, kdr, ldbr, 64);
+    for (int rj = tid; rj < nkr; rj += nt) { const int k = rj / w, tt = rj % w; ws.y[pl.b[k] + tt] = tw[rj]; }
   }
+  __syncthreads();
   if (tid == 0) scal[SC_OK] = 1.0;
 }
 
@@ -275,35 +378,19 @@ __global__ void __launch_bounds__(256) chunk_backsub_kernel(DeviceProblem P, Sol
   const int a = pl.a[c], b = pl.b[c];
   const bool has_left = c > 0, has_right = c < pl.P - 1;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
-  double* xl = sm;                       // local border solution [left separator | border]
-  const int PB = 128;
-  double* Bw = xl + nbl;                 // (PB + kd) * ldb
-  double* tw = Bw + (size_t)(PB + kd) * ldb;
+  const int top = has_right ? b + w : b;   // right separator values are known: they only scatter into the interior
+  double* xl = sm;                         // local border solution [left separator | border]
+  double* tw = xl + ((nbl + 3) & ~3);      // t / x for columns [a, top)
+  double* Bw = tw + ((top - a + 3) & ~3);  // (PB + kd) * ldb panel of L
   for (int i = tid; i < w + nb; i += nt) xl[i] = i < w ? (has_left ? ws.y[a - w + i] : 0.0) : ws.y[nk + i - w];
   __syncthreads();
-  for (int j = a + tid; j < b; j += nt) { const double* le = ws.El + (int64_t)j * nbl; double t = le[w + nb]; for (int i = 0; i < w + nb; ++i) t -= le[i] * xl[i]; ws.t[j] = t; }
-  __syncthreads();
-  const int top = has_right ? b + w : b;   // right separator values are known: they only scatter into the interior
-  for (int hi = top; hi > a; hi -= PB) {
-    const int lo_own = max(a, hi - PB), lo = max(a, lo_own - kd);
-    for (int idx = tid; idx < (hi - lo) * ldb; idx += nt) { const int col = lo + idx / ldb; Bw[idx] = col < b ? ws.Lb[(int64_t)lo * ldb + idx] : 0.0; }
-    for (int idx = tid; idx < hi - lo; idx += nt) { const int col = lo + idx; tw[idx] = col < b ? ws.t[col] : ws.y[col]; }
-    __syncthreads();
-    if (tid < 32) {
-      for (int j = hi - 1; j >= lo_own; --j) {
-        const int jl = j - lo;
-        const double xj = j < b ? tw[jl] / Bw[(int64_t)jl * ldb] : tw[jl];
-        __syncwarp();
-        if (tid == 0) tw[jl] = xj;
-        for (int r = tid + 1; r <= kd && r <= jl; r += 32) { if (j - r < b) tw[jl - r] -= Bw[(int64_t)(jl - r) * ldb + r] * xj; }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < hi - lo_own; idx += nt) { const int col = lo_own + idx; if (col < b) ws.y[col] = tw[lo_own - lo + idx]; }
-    for (int idx = tid; idx < lo_own - lo; idx += nt) ws.t[lo + idx] = tw[idx];
-    __syncthreads();
+  for (int j = a + tid; j < top; j += nt) {
+    if (j < b) { const double* le = ws.El + (int64_t)j * nbl; double t = le[w + nb]; for (int i = 0; i < w + nb; ++i) t -= le[i] * xl[i]; tw[j - a] = t; }
+    else tw[j - a] = ws.y[j];
   }
+  __syncthreads();
+  backsub_dispatch(ws.Lb, tw, Bw, a, top, b, kd, ldb, 128);
+  for (int j = a + tid; j < b; j += nt) ws.y[j] = tw[j - a];
 }
 
 // ---- kernel D: step in the unscaled space, model cost change = 1/2 (y^T D y + y^T rhs) ----------------------------
@@ -415,16 +502,17 @@ __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand
 
 int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) {
-  const int CL = P.ldb + pl.nbl, T = P.kd * (P.kd + 1) / 2 + pl.nbl * P.kd + pl.nbl * (pl.nbl + 1) / 2;
-  return ((size_t)pl.WS_A * CL + (size_t)pl.nbl * pl.nbl) * sizeof(double) + (size_t)T * sizeof(ushort4) + 64;
-}
+size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_A, P.kd + KB + pl.nbl, pl.nbl, P.kd, 0); }
 size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
-  const int nbp = P.nb + 1, CL = pl.ldbr + nbp, T = pl.kdr * (pl.kdr + 1) / 2 + nbp * pl.kdr + nbp * (nbp + 1) / 2;
-  const size_t win = (size_t)pl.WS_B * CL * sizeof(double), back = (size_t)(64 + pl.kdr) * (pl.ldbr + 1) * sizeof(double);
-  return (win > back ? win : back) + ((size_t)nbp * nbp + nbp + 2) * sizeof(double) + (size_t)T * sizeof(ushort4) + 64;
+  const int nbp = P.nb + 1;
+  const size_t fac = factor_smem_bytes(pl.WS_B, pl.kdr + KB + nbp, nbp, pl.kdr, nbp + 1);
+  const size_t back = ((size_t)pl.nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr) * sizeof(double) + 64;   // back-substitution reuses the window area
+  return fac > back ? fac : back;
 }
-size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) { return ((size_t)pl.nbl + (size_t)(128 + P.kd) * (P.ldb + 1)) * sizeof(double) + 64; }
+size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
+  int maxlen = 0; for (int c = 0; c < pl.P; ++c) maxlen = std::max(maxlen, pl.b[c] - pl.a[c] + pl.w);
+  return ((size_t)pl.nbl + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb) * sizeof(double) + 64;
+}
 
 // Chunking of the knot columns.  The elimination cost per interior column is ~ constant, the reduced system has
 // (P-1) * kd sequential columns => P ~ sqrt(nk / kd).  Wide borders (bias splines active) keep P = 1: the left-separator
@@ -440,7 +528,7 @@ SolvePlan make_plan(const DeviceProblem& P) {
   for (int c = 0; c < Pn; ++c) { const int len = interior_total / Pn + (c < interior_total % Pn ? 1 : 0); pl.a[c] = pos; pl.b[c] = pos + len; pos += len + pl.w; }
   pl.nkr = (Pn - 1) * pl.w; pl.kdr = Pn > 1 ? 2 * pl.w - 1 : 0; pl.ldbr = pl.kdr + 1;
   pl.nbl = pl.w + nb + 1;
-  pl.WS_A = pow2_at_least(kd + 2); pl.WS_B = pow2_at_least(pl.kdr + 2);
+  pl.WS_A = pow2_at_least(kd + KB + 1); pl.WS_B = pow2_at_least(pl.kdr + KB + 1);
   // grow the windows while they fit comfortably (larger panels amortise the panel load/store)
   while (pl.WS_A < 256) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 160 * 1024) break; pl = t; }
   while (pl.WS_B < 256) { SolvePlan t = pl; t.WS_B *= 2; if (smem_B(P, t) > 160 * 1024) break; pl = t; }

@@ -1,0 +1,271 @@
+// Drop-in host program for applications/continuous_time_imu_to_camera_calibration.cc of urbste/OpenImuCameraCalibrator:
+// same gflags names (app :38-80), same input files (UBJSON corners, camera / telemetry / init / bias / IMU-intrinsics /
+// spline-weighting JSON), same result JSON keys (app :247-332) and the two PLY files (app :335-364); everything between
+// "files parsed" and "results written" runs on the B200 through the C-ABI of include/icc_b200.h.
+//
+// One deliberate difference: --input_pose_dataset.  The reference reads Theia's cereal-binary .calibdata
+// (theia::ReadReconstruction, app :95-97), which cannot be parsed without Theia.  This program reads the same content as
+// JSON:  {"views": {"<view name>": {"q_wc": [w,x,y,z], "p_wc": [x,y,z]}}, "tracks": {"<id>": [x,y,z,w]}}
+// where q_wc = R_cw^T and p_wc = camera position (what app :137-145 / impl.h:290-300 take from each theia::Camera).
+// Extra flag (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary).
+#include "../../include/icc_b200.h"
+#include "icc_json.hpp"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+#include <map>
+#include <set>
+
+using iccjson::Value;
+
+namespace {
+
+struct Flags {
+  std::map<std::string, std::string> str = {{"telemetry_json", ""}, {"input_pose_dataset", ""}, {"input_corners", ""}, {"camera_calibration_json", ""},
+    {"gyro_to_cam_initial_calibration", ""}, {"imu_intrinsics", ""}, {"imu_bias_file", ""}, {"spline_error_weighting_json", ""}, {"output_path", ""},
+    {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}};
+  std::map<std::string, bool> boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}};
+  std::map<std::string, double> num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}};
+};
+
+bool parse_bool(const std::string& v) { return v == "true" || v == "1" || v == "t" || v == "yes" || v == "y" || v == "True"; }
+
+// gflags syntax: --name=value, --name value, -name..., --boolflag, --noboolflag
+void parse_flags(int argc, char** argv, Flags& f) {
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a.size() < 2 || a[0] != '-') throw std::runtime_error("unexpected argument: " + a);
+    a = a.substr(a[1] == '-' ? 2 : 1);
+    std::string name = a, value; bool has_value = false;
+    const size_t eq = a.find('=');
+    if (eq != std::string::npos) { name = a.substr(0, eq); value = a.substr(eq + 1); has_value = true; }
+    if (f.boolean.count(name)) { f.boolean[name] = has_value ? parse_bool(value) : true; continue; }
+    if (name.rfind("no", 0) == 0 && f.boolean.count(name.substr(2)) && !has_value) { f.boolean[name.substr(2)] = false; continue; }
+    if (!has_value) { if (i + 1 >= argc) throw std::runtime_error("flag --" + name + " needs a value"); value = argv[++i]; }
+    if (f.str.count(name)) f.str[name] = value;
+    else if (f.num.count(name)) f.num[name] = std::stod(value);
+    else throw std::runtime_error("unknown command line flag '" + name + "'");
+  }
+}
+
+#define CHECK_MSG(cond, msg) do { if (!(cond)) { std::cerr << "Check failed: " #cond " " << msg << std::endl; std::exit(1); } } while (0)
+#define ICC(call) do { icc_status s__ = (call); if (s__ != ICC_OK) { std::cerr << #call << " failed (" << s__ << "): " << icc_last_error(h) << std::endl; std::exit(2); } } while (0)
+
+int grav_dir_string_to_int(const std::string& s) {   // src/utils/utils.cc:150-161
+  if (s == "UNKNOWN") return -1;
+  if (s == "X") return 0;
+  if (s == "Y") return 1;
+  if (s == "Z") return 2;
+  return -1;
+}
+
+// src/io/read_camera_calibration.cc:35-119 -> (model id, Theia-ordered intrinsics).  Like the reference, `skew` is never read.
+int read_camera(const Value& j, std::vector<double>& k, int& width, int& height, double& fps) {
+  const std::string type = j.at("intrinsic_type").str();
+  const Value& in = j.at("intrinsics");
+  width = (int)j.at("image_width").num(); height = (int)j.at("image_height").num(); fps = j.at("fps").num();
+  const double f = in.at("focal_length").num(), cx = in.at("principal_pt_x").num(), cy = in.at("principal_pt_y").num();
+  auto ar = [&]() { return in.at("aspect_ratio").num(); };
+  if (type == "DIVISION_UNDISTORTION") { k = {f, ar(), cx, cy, in.at("div_undist_distortion").num()}; return ICC_CAM_DIVISION_UNDISTORTION; }
+  if (type == "DOUBLE_SPHERE") { k = {f, ar(), 0.0, cx, cy, in.at("xi").num(), in.at("alpha").num()}; return ICC_CAM_DOUBLE_SPHERE; }
+  if (type == "EXTENDED_UNIFIED") { k = {f, ar(), 0.0, cx, cy, in.at("alpha").num(), in.at("beta").num()}; return ICC_CAM_EXTENDED_UNIFIED; }
+  if (type == "FISHEYE") { k = {f, ar(), 0.0, cx, cy, in.at("radial_distortion_1").num(), in.at("radial_distortion_2").num(), in.at("radial_distortion_3").num(), in.at("radial_distortion_4").num()}; return ICC_CAM_FISHEYE; }
+  if (type == "PINHOLE_RADIAL_TANGENTIAL") { k = {f, ar(), 0.0, cx, cy, in.at("radial_distortion_1").num(), in.at("radial_distortion_2").num(), in.at("radial_distortion_3").num(), in.at("tangential_distortion_1").num(), in.at("tangential_distortion_2").num()}; return ICC_CAM_PINHOLE_RADIAL_TANGENTIAL; }
+  if (type == "PINHOLE") { k = {f, ar(), 0.0, cx, cy, 0.0, 0.0}; return ICC_CAM_PINHOLE; }
+  if (type == "FOV") { k = {f, in.contains("aspect_ratio") ? ar() : 1.0, cx, cy, in.at("radial_distortion_1").num()}; return ICC_CAM_FOV; }
+  throw std::runtime_error("unknown intrinsic_type " + type);
+}
+
+void write_ply(const std::string& path, const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<int, 3>>& col) {
+  std::ofstream f(path);
+  if (!f.is_open()) throw std::runtime_error("could not write " + path);
+  f << "ply\nformat ascii 1.0\nelement vertex " << pts.size() << "\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n";
+  for (size_t i = 0; i < pts.size(); ++i) f << pts[i][0] << " " << pts[i][1] << " " << pts[i][2] << " " << col[i][0] << " " << col[i][1] << " " << col[i][2] << "\n";
+}
+
+Value xyz(double x, double y, double z) { Value v = Value::object(); v["x"] = Value(x); v["y"] = Value(y); v["z"] = Value(z); return v; }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Flags F;
+  try { parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
+  const double S_TO_NS = 1e9, US_TO_S = 1e-6, S_TO_US = 1e6, NS_TO_S = 1e-9;
+  try {
+    // ---- inputs (app :93-184) ---------------------------------------------------------------------------------------
+    Value pose_dataset;
+    try { pose_dataset = iccjson::load_json(F.str["input_pose_dataset"]); }
+    catch (const std::exception& e) { CHECK_MSG(false, "Could not read Reconstruction file (JSON pose dataset expected, Theia .calibdata is not supported): " << e.what()); }
+    Value scene_json;
+    try { scene_json = iccjson::load_ubjson(F.str["input_corners"]); } catch (const std::exception& e) { CHECK_MSG(false, "Failed to load " << F.str["input_corners"] << ": " << e.what()); }
+    std::vector<double> intr; int width = 0, height = 0; double fps = 0;
+    int model = -1;
+    try { model = read_camera(iccjson::load_json(F.str["camera_calibration_json"]), intr, width, height, fps); }
+    catch (const std::exception& e) { CHECK_MSG(false, "Could not read camera calibration: " << F.str["camera_calibration_json"] << ": " << e.what()); }
+    // board tracks come from the pose dataset (possibly refined), app :108-119
+    const Value& tracks = pose_dataset.at("tracks");
+    int max_id = -1; for (const auto& kv : *tracks.o) max_id = std::max(max_id, std::stoi(kv.first));
+    std::vector<double> board(4 * (size_t)(max_id + 1), 0.0);
+    for (int i = 0; i <= max_id; ++i) board[4 * i + 3] = 1.0;
+    for (const auto& kv : *tracks.o) { const int id = std::stoi(kv.first); for (int d = 0; d < 4; ++d) board[4 * id + d] = kv.second.at(d).num(); }
+    // telemetry (src/io/read_telemetry.cc:29-69)
+    Value tel;
+    try { tel = iccjson::load_json(F.str["telemetry_json"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["telemetry_json"] << ": " << e.what()); }
+    const Value& tj = tel.at("timestamps_ns");
+    CHECK_MSG(tel.at("gyroscope").size() == tj.size() && tel.at("accelerometer").size() == tj.size(), "Telemetry should have the same amount of timestamps, accelerometer and gyroscope values.");
+    std::vector<double> imu_t, acc, gyr;
+    for (size_t i = 0; i < tj.size(); ++i) {
+      imu_t.push_back(tj.at(i).num() * NS_TO_S);
+      for (int d = 0; d < 3; ++d) { acc.push_back(tel.at("accelerometer").at(i).at(d).num()); gyr.push_back(tel.at("gyroscope").at(i).at(d).num()); }
+    }
+    double t_offset_cam_s = 0.0;
+    if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) t_offset_cam_s = tel.at("img_timestamps_ns").at(0).num() * NS_TO_S;
+    // views: join corners with poses by name = to_string((uint64) timestamp_us)   (app :131-161)
+    const Value& pviews = pose_dataset.at("views");
+    std::vector<double> frame_t, uv, q_wc, p_wc; std::vector<int32_t> off{0}, ids;
+    for (const auto& kv : *scene_json.at("views").o) {
+      const double timestamp_us = std::stod(kv.first);
+      const std::string view_name = std::to_string((uint64_t)timestamp_us);
+      if (!pviews.contains(view_name)) continue;
+      const Value& pv = pviews.at(view_name);
+      frame_t.push_back(timestamp_us * US_TO_S + t_offset_cam_s);
+      const Value& q = pv.at("q_wc");   // [w, x, y, z]
+      q_wc.push_back(q.at(1).num()); q_wc.push_back(q.at(2).num()); q_wc.push_back(q.at(3).num()); q_wc.push_back(q.at(0).num());
+      for (int d = 0; d < 3; ++d) p_wc.push_back(pv.at("p_wc").at(d).num());
+      for (const auto& ip : *kv.second.at("image_points").o) { ids.push_back(std::stoi(ip.first)); uv.push_back(ip.second.at(0).num()); uv.push_back(ip.second.at(1).num()); }
+      off.push_back((int32_t)ids.size());
+    }
+    CHECK_MSG(!frame_t.empty(), "no view of the corner file has a pose in the pose dataset");
+    // gyro-to-camera initialisation (src/io/read_misc.cc:63-82): T_i_c_init = (q_gyro_to_cam^-1, 0)   (app :164-170)
+    Value init;
+    try { init = iccjson::load_json(F.str["gyro_to_cam_initial_calibration"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["gyro_to_cam_initial_calibration"] << ": " << e.what()); }
+    const Value& gq = init.at("gyro_to_camera_rotation");
+    const double time_offset_imu_to_cam = init.at("time_offset_gyro_to_cam").num();
+    icc_init_params ip; memset(&ip, 0, sizeof ip);
+    ip.T_i_c_init[0] = -gq.at("x").num(); ip.T_i_c_init[1] = -gq.at("y").num(); ip.T_i_c_init[2] = -gq.at("z").num(); ip.T_i_c_init[3] = gq.at("w").num();
+    // IMU intrinsics + biases (src/io/read_misc.cc:84-150)
+    double acc_i[6] = {0, 0, 0, 1, 1, 1}, gyr_i[9] = {0, 0, 0, 0, 0, 0, 1, 1, 1};
+    if (!F.str["imu_bias_file"].empty()) {
+      try { Value b = iccjson::load_json(F.str["imu_bias_file"]); const char* ax[3] = {"x", "y", "z"}; for (int d = 0; d < 3; ++d) { ip.acc_bias[d] = b.at("accl_bias").at(ax[d]).num(); ip.gyr_bias[d] = b.at("gyro_bias").at(ax[d]).num(); } }
+      catch (const std::exception& e) { std::cerr << "Error loading IMU bias file: " << F.str["imu_bias_file"] << " (" << e.what() << ")\n"; }
+    }
+    if (!F.str["imu_intrinsics"].empty()) {
+      Value ii;
+      try { ii = iccjson::load_json(F.str["imu_intrinsics"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not open " << F.str["imu_intrinsics"] << ": " << e.what()); }
+      const Value& ma = ii.at("accelerometer").at("misalignment_matrix"); const Value& sa = ii.at("accelerometer").at("scale_matrix");
+      // mis = [[1,-yz,zy],[xz,1,-zx],[-xy,yx,1]]  (utils/types.h:238-246)
+      acc_i[0] = -ma.at(0).at(1).num(); acc_i[1] = ma.at(0).at(2).num(); acc_i[2] = -ma.at(1).at(2).num();
+      acc_i[3] = sa.at(0).at(0).num(); acc_i[4] = sa.at(1).at(1).num(); acc_i[5] = sa.at(2).at(2).num();
+      const Value& mg = ii.at("gyroscope").at("misalignment_matrix"); const Value& sg = ii.at("gyroscope").at("scale_matrix");
+      gyr_i[0] = -mg.at(0).at(1).num(); gyr_i[1] = mg.at(0).at(2).num(); gyr_i[2] = -mg.at(1).at(2).num();
+      gyr_i[3] = mg.at(1).at(0).num(); gyr_i[4] = -mg.at(2).at(0).num(); gyr_i[5] = mg.at(2).at(1).num();
+      gyr_i[6] = sg.at(0).at(0).num(); gyr_i[7] = sg.at(1).at(1).num(); gyr_i[8] = sg.at(2).at(2).num();
+    }
+    memcpy(ip.acc_intrinsics, acc_i, sizeof acc_i); memcpy(ip.gyr_intrinsics, gyr_i, sizeof gyr_i);
+    CHECK_MSG(!F.str["spline_error_weighting_json"].empty(), "You need to provide spline error weighting factors. Create with get_sew_for_dataset.py.");
+    Value sew;
+    try { sew = iccjson::load_json(F.str["spline_error_weighting_json"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not open " << F.str["spline_error_weighting_json"] << ": " << e.what()); }
+    ip.dt_r3_s = sew.at("r3").at("knot_spacing").num(); ip.dt_so3_s = sew.at("so3").at("knot_spacing").num();
+    ip.std_r3 = sew.at("r3").at("weighting_factor").num(); ip.std_so3 = sew.at("so3").at("weighting_factor").num();
+    ip.time_offset_imu_to_cam_s = time_offset_imu_to_cam;
+    double init_line_delay = 1. / fps / height;       // seconds despite the reference's "_us" name (app :186)
+    if (F.boolean["global_shutter"]) init_line_delay = 0.0;
+    ip.init_line_delay_s = init_line_delay;
+    ip.dispatch_fov = model == ICC_CAM_FOV ? 1 : 0;
+
+    if (F.boolean["parse_only"]) {
+      Value s = Value::object();
+      s["views"] = Value((int64_t)frame_t.size()); s["corners"] = Value((int64_t)ids.size()); s["imu_samples"] = Value((int64_t)imu_t.size());
+      s["board_points"] = Value((int64_t)(max_id + 1)); s["camera_model"] = Value(model); s["intrinsics"] = Value::array();
+      for (double v : intr) s["intrinsics"].push_back(Value(v));
+      s["init_line_delay_s"] = Value(init_line_delay); s["dt_so3"] = Value(ip.dt_so3_s); s["dt_r3"] = Value(ip.dt_r3_s); s["first_view_t_s"] = Value(frame_t.front());
+      s["uv_sum"] = Value([&] { double a = 0; for (double v : uv) a += v; return a; }());
+      std::cout << iccjson::dump(s) << std::endl;
+      return 0;
+    }
+
+    // ---- solve on the GPU (app :188-221) ------------------------------------------------------------------------------
+    icc_handle* h = nullptr;
+    { icc_status s = icc_create(&h, (int)F.num["device"]); if (s != ICC_OK) { std::cerr << "icc_create failed (" << s << "): " << icc_last_error(h) << std::endl; return 2; } }
+    ICC(icc_set_camera(h, model, intr.data(), (int)intr.size(), width, height));
+    ICC(icc_set_board_points(h, max_id + 1, board.data()));
+    ICC(icc_set_frames(h, (int)frame_t.size(), frame_t.data(), off.data(), ids.data(), uv.data(), q_wc.data(), p_wc.data()));
+    ICC(icc_set_imu(h, (int)imu_t.size(), imu_t.data(), acc.data(), gyr.data()));
+    ICC(icc_batch_init_spline(h, &ip));
+    const int grav_dir_axis = grav_dir_string_to_int(F.str["known_grav_dir_axis"]);
+    int flags = ICC_FLAG_SPLINE | ICC_FLAG_T_I_C;
+    if (F.boolean["reestimate_biases"]) flags |= ICC_FLAG_IMU_BIASES;
+    if (grav_dir_axis != -1) {
+      double g[3] = {0, 0, 0}; g[grav_dir_axis] = F.num["gravity_const"];
+      ICC(icc_set_known_gravity_dir(h, g));
+      std::cout << "Setting a-priori gravity direction supplied by the user to: " << g[0] << " " << g[1] << " " << g[2] << "\n";
+    } else flags |= ICC_FLAG_GRAVITY_DIR;
+    icc_summary s1, s2;
+    ICC(icc_optimize(h, 50, flags, &s1));
+    double reproj_error = s1.mean_reproj_error, reproj_error_after_ld = reproj_error;
+    if (F.boolean["calibrate_cam_line_delay"] && !F.boolean["global_shutter"]) { ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2)); reproj_error_after_ld = s2.mean_reproj_error; }
+    std::cout << "LM iterations: " << s1.iterations << " cost " << s1.initial_cost << " -> " << s1.final_cost << "  (" << s1.seconds_total << " s, " << s1.gpu_launches << " kernel launches)\n";
+    std::cout << "Mean reprojection error " << reproj_error << "px\nMean reprojection error after line delay optim " << reproj_error_after_ld << "px\n";
+
+    // ---- results (app :226-332) ---------------------------------------------------------------------------------------
+    double T[7], g[3], ld;
+    ICC(icc_get_T_i_c(h, T)); ICC(icc_get_gravity(h, g)); ICC(icc_get_line_delay(h, &ld));
+    const double calib_line_delay_us = ld * S_TO_US;
+    std::cout << "g: " << g[0] << " " << g[1] << " " << g[2] << "\nT_i_c qw,qx,qy,qz: " << T[3] << " " << T[0] << " " << T[1] << " " << T[2] << "\nT_i_c t: " << T[4] << " " << T[5] << " " << T[6]
+              << "\nInitialized line delay [us]: " << init_line_delay * S_TO_US << "\nCalibrated line delay [us]: " << calib_line_delay_us << "\n";
+    Value out = Value::object();
+    { Value q = Value::object(); q["w"] = Value(T[3]); q["x"] = Value(T[0]); q["y"] = Value(T[1]); q["z"] = Value(T[2]); out["q_i_c"] = q; }
+    out["t_i_c"] = xyz(T[4], T[5], T[6]);
+    out["final_reproj_error"] = Value(reproj_error);
+    out["r3_dt"] = Value(ip.dt_r3_s); out["so3_dt"] = Value(ip.dt_so3_s);
+    out["init_line_delay_us"] = Value(init_line_delay * S_TO_US); out["calib_line_delay_us"] = Value(calib_line_delay_us);
+    out["time_offset_imu_to_cam_s"] = Value(time_offset_imu_to_cam);
+    int n_used = 0; ICC(icc_get_num_imu_used(h, &n_used));
+    std::vector<double> ut(n_used), ua(3 * (size_t)n_used), ug(3 * (size_t)n_used);
+    ICC(icc_get_imu_used(h, ut.data(), ua.data(), ug.data()));
+    std::vector<int64_t> t_ns(n_used); for (int i = 0; i < n_used; ++i) t_ns[i] = (int64_t)(ut[i] * S_TO_NS);
+    std::vector<double> gs(3 * (size_t)n_used), as(3 * (size_t)n_used), gb(3 * (size_t)n_used), ab(3 * (size_t)n_used);
+    std::vector<int32_t> valid(n_used);
+    if (n_used) ICC(icc_eval_trajectory(h, n_used, t_ns.data(), gs.data(), as.data(), gb.data(), ab.data(), nullptr, nullptr, valid.data()));
+    Value traj = Value::object();
+    for (int i = 0; i < n_used; ++i) {
+      Value e = Value::object();
+      e["gyro_imu"] = xyz(ug[3 * i], ug[3 * i + 1], ug[3 * i + 2]); e["gyro_spline"] = xyz(gs[3 * i], gs[3 * i + 1], gs[3 * i + 2]); e["gyro_bias"] = xyz(gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]);
+      e["accl_imu"] = xyz(ua[3 * i], ua[3 * i + 1], ua[3 * i + 2]); e["accl_spline"] = xyz(as[3 * i], as[3 * i + 1], as[3 * i + 2]); e["accl_bias"] = xyz(ab[3 * i], ab[3 * i + 1], ab[3 * i + 2]);
+      traj[std::to_string(t_ns[i])] = e;
+    }
+    if (n_used) out["trajectory"] = traj;
+    { std::ofstream f(F.str["result_output_json"]); CHECK_MSG(f.is_open(), "could not write " << F.str["result_output_json"]); f << iccjson::dump(out, 4) << std::endl; }
+
+    // ---- PLY files of the spline poses and of the input poses (app :335-364) -------------------------------------------
+    std::vector<double> cam_ts(frame_t); std::sort(cam_ts.begin(), cam_ts.end());
+    std::vector<int64_t> cam_ns(cam_ts.size()); for (size_t i = 0; i < cam_ts.size(); ++i) cam_ns[i] = (int64_t)(cam_ts[i] * S_TO_NS);
+    std::vector<double> pq(4 * cam_ns.size()), pp(3 * cam_ns.size()); std::vector<int32_t> pvalid(cam_ns.size());
+    ICC(icc_eval_trajectory(h, (int)cam_ns.size(), cam_ns.data(), nullptr, nullptr, nullptr, nullptr, pq.data(), pp.data(), pvalid.data()));
+    std::vector<std::array<double, 3>> pts; std::vector<std::array<int, 3>> col;
+    for (size_t i = 0; i < cam_ns.size(); ++i) {
+      if (!pvalid[i]) continue;
+      // T_w_c = T_w_i * T_i_c : position = p_wi + R_wi t_ic
+      const double x = pq[4 * i], y = pq[4 * i + 1], z = pq[4 * i + 2], w = pq[4 * i + 3];
+      const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+      pts.push_back({pp[3 * i] + R[0] * T[4] + R[1] * T[5] + R[2] * T[6], pp[3 * i + 1] + R[3] * T[4] + R[4] * T[5] + R[5] * T[6], pp[3 * i + 2] + R[6] * T[4] + R[7] * T[5] + R[8] * T[6]});
+      col.push_back({0, 255, 0});
+    }
+    const std::string op = F.str["output_path"];
+    if (!op.empty()) {
+      write_ply(op + "/sparse_recon_spline.ply", pts, col);
+      pts.clear(); col.clear();
+      for (size_t i = 0; i < frame_t.size(); ++i) { pts.push_back({p_wc[3 * i], p_wc[3 * i + 1], p_wc[3 * i + 2]}); col.push_back({255, 0, 0}); }
+      for (int i = 0; i <= max_id; ++i) { pts.push_back({board[4 * i] / board[4 * i + 3], board[4 * i + 1] / board[4 * i + 3], board[4 * i + 2] / board[4 * i + 3]}); col.push_back({255, 255, 255}); }
+      write_ply(op + "/sparse_recon_calib_dataset.ply", pts, col);
+    }
+    icc_destroy(h);
+  } catch (const std::exception& e) {
+    std::cerr << "ERROR: " << e.what() << std::endl;
+    return 1;
+  }
+  return 0;
+}

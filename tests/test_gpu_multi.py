@@ -1,0 +1,50 @@
+"""Residual sharding on real GPUs: 2 ranks over NCCL evaluate their time slices, all-reduce the packed normal equations on
+the solver stream and must follow exactly the single-GPU LM path.  Needs >= 2 visible GPUs (gpurun --gpus 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from helpers import F_STAGE1
+    from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
+    from openimucameracalibrator_b200.distributed import make_allreduce_hook
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ds = syn.make_dataset(syn.CONFIGS[2])
+    g = capi.CApi(calibrator.load_library(), "icc_", rank)
+    capi.load_dataset(g, ds, shard=(rank, world))
+    g.set_allreduce(make_allreduce_hook(g.get_stream(), rank))
+    s = g.optimize(50, F_STAGE1)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "T.npy"), g.get_T_i_c())
+        np.save(os.path.join(out_dir, "it.npy"), np.array([s.iterations, s.termination, s.num_residuals]))
+        np.save(os.path.join(out_dir, "reproj.npy"), np.array([s.mean_reproj_error, s.final_cost]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from helpers import F_STAGE1, rel
+    from openimucameracalibrator_b200 import _capi as capi, synthetic as syn
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ds = syn.make_dataset(syn.CONFIGS[2])
+    g = gpu_factory(); capi.load_dataset(g, ds)
+    s = g.optimize(50, F_STAGE1)
+    it = np.load(tmp_path / "it.npy"); T = np.load(tmp_path / "T.npy"); rp = np.load(tmp_path / "reproj.npy")
+    assert it[0] == s.iterations and it[1] == s.termination
+    assert rel(T, g.get_T_i_c()) < 1e-8
+    assert abs(rp[0] - s.mean_reproj_error) < 1e-8 and abs(rp[1] - s.final_cost) <= 1e-9 * s.final_cost

@@ -68,94 +68,128 @@ constexpr int KB = 8;             // panel width of the blocked LDL^T
 // Window column layout (CL doubles): [band part, ldbp = kd + KB entries, offsets > kd are zero padding][local border rows, nbl].
 // Per panel of KB columns:
 //   (1) KB sequential column steps that only update the OTHER PANEL columns (<= (KB-1)(kd+1+nbl) entries, 1 sync each);
-//   (2) one rank-KB update of the whole trailing window + the dense local-border block (T entries, KB terms each, 1 sync).
-// Thanks to the zero padding no term needs a bounds test: an out-of-band operand reads 0.
-// Trailing descriptors (ushort4): x = A0 | (sA << 15), y = B0 | (sB << 15), z = destination column offset from the panel
-// start (0xFFFF: dense border block), w = destination offset.  Term jj reads col_jj[A0 - jj*sA] * col_jj[B0 - jj*sB] / D_jj.
-__device__ void build_trailing_descriptors(ushort4* desc, int kd, int ldbp, int nbl) {
-  const int np = kd * (kd + 1) / 2, nbb = nbl * kd, ncc = nbl * (nbl + 1) / 2;
-  for (int idx = threadIdx.x; idx < np + nbb + ncc; idx += blockDim.x) {
-    ushort4 d;
-    if (idx < np) {            // band x band: destination column Coff = KB + D, rows Roff = Coff .. KB-1+kd
-      const int q = tri_row(idx), k = idx - q * (q + 1) / 2;      // q = kd-1-D (rows available - 1), k = row index within column
-      const int D = kd - 1 - q, Coff = KB + D, Roff = Coff + k;
-      d = make_ushort4(Roff | 0x8000, Coff | 0x8000, Coff, Roff - Coff);
-    } else if (idx < np + nbb) {
-      const int k = idx - np, b = k / kd, Coff = KB + k % kd;
-      d = make_ushort4(ldbp + b, Coff | 0x8000, Coff, ldbp + b);
-    } else {
-      const int k = idx - np - nbb, b1 = tri_row(k), b2 = k - b1 * (b1 + 1) / 2;
-      d = make_ushort4(ldbp + b1, ldbp + b2, 0xFFFF, b1 * nbl + b2);
-    }
-    desc[idx] = d;
-  }
+//   (2) ONE rank-KB update of the trailing window + dense local-border block, done as a symmetric GEMM on the FP64 tensor
+//       cores: with M = kd + nbl trailing positions (the kd band columns after the panel, then the border rows),
+//       T[x][y] -= sum_jj L[x][jj] L[y][jj] / D_jj,  L[x][jj] = entry of panel column jj at trailing position x,
+//       tiled in 8x8 blocks of m8n8k4 DMMAs (KB/4 k-steps).  Thanks to the zero padding no operand needs a bounds test.
+__device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-// Panel descriptors (ushort2): x = distance dc to the target panel column (1..KB-1), y = source offset in the pivot column
-// (band offset dc..kd, or ldbp + b for a border row).  Sorted by dc so that pivot column jj uses the first pcount[KB-1-jj].
-__device__ void build_panel_descriptors(ushort2* pdesc, int* pcount, int kd, int ldbp, int nbl) {
-  const int per0 = kd + 1 + nbl;   // entries for dc = 0 (unused); dc has per0 - dc entries
-  if (threadIdx.x == 0) { int acc = 0; pcount[0] = 0; for (int dc = 1; dc < KB; ++dc) { acc += per0 - dc; pcount[dc] = acc; } }
-  __syncthreads();
-  const int total = pcount[KB - 1];
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    int dc = 1; while (idx >= pcount[dc]) ++dc;
-    const int k = idx - pcount[dc - 1];
-    const int nband = kd - dc + 1;
-    pdesc[idx] = k < nband ? make_ushort2(dc, dc + k) : make_ushort2(dc, ldbp + (k - nband));
-  }
+// lower-triangular list of 8x8 blocks (bi >= bj) covering M trailing positions
+__device__ int build_block_table(uchar2* blocks, int M) {
+  const int nbk = (M + 7) / 8, n = nbk * (nbk + 1) / 2;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) { const int bi = tri_row(idx), bj = idx - bi * (bi + 1) / 2; blocks[idx] = make_uchar2(bi, bj); }
+  return n;
 }
-
-struct FactorSmem { double* W; double* Cl; ushort4* desc; ushort2* pdesc; int* pcount; double* inv; int T; };
+struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; };
 
 // LDL^T elimination of columns [j_begin, j_end).  load(col, e) returns the (scaled, damped) original entry e of column col
 // (0 outside the matrix AND for the padding offsets kd < e < ldbp); store(col, e, v) receives every finished column
 // (unscaled storage: entry 0 = pivot D_j, others = L_ij D_j).  On return the window holds the updated columns >= j_end.
+// Per panel of KB columns (4 block-wide barriers instead of one per column):
+//   (a) ONE thread factors the KB x KB diagonal block in registers (unit-lower l, pivots D);
+//   (b) one thread per trailing row forward-substitutes its KB panel entries against l (rows are independent);
+//   (c) rank-KB tensor-core update of the trailing window (see above).
 template <class Load, class Store>
 __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int kd, int ldbp, int CL, int WS, Load load, Store store) {
-  const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1;
-  const int PB = ((WS - kd) / KB) * KB;
+  const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int PB = ((WS - kd) / KB) * KB, M = kd + fs.nbl;
   double* W = fs.W;
   for (int j0 = j_begin; j0 < j_end; j0 += PB) {
     const int first = j0 == j_begin ? j_begin : j0 + kd, last = j0 + PB + kd;
-    for (int idx = tid; idx < (last - first) * CL; idx += nt) { const int col = first + idx / CL, e = idx % CL; W[(size_t)(col & mask) * CL + e] = load(col, e); }
+    {   // group load with 8 independent global loads in flight per thread (the loads, not the math, bound this phase)
+      const int total = (last - first) * CL;
+      for (int b0 = tid; b0 < total; b0 += 8 * nt) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; v[u] = idx < total ? load(first + idx / CL, idx % CL) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; if (idx < total) { const int col = first + idx / CL; W[(size_t)(col & mask) * CL + idx % CL] = v[u]; } }
+      }
+    }
     __syncthreads();
     const int gend = min(j0 + PB, j_end);
     for (int jp = j0; jp < gend; jp += KB) {
       const int kb = min(KB, gend - jp);
-      // (1) panel factorisation
-      for (int jj = 0; jj < kb; ++jj) {
-        const int j = jp + jj;
-        double* cj = W + (size_t)(j & mask) * CL;
-        const double piv = cj[0];
-        if (!(piv > 0.0) || !isfinite(piv)) return false;     // uniform: every thread reads the same pivot
-        const double inv = 1.0 / piv;
-        if (tid == 0) fs.inv[jj] = inv;
-        const int cnt = fs.pcount[KB - 1 - jj];
-        for (int idx = tid; idx < cnt; idx += nt) {
-          const ushort2 d = fs.pdesc[idx];
-          const int dst = d.y < ldbp ? d.y - d.x : d.y;
-          W[(size_t)((j + d.x) & mask) * CL + dst] -= cj[d.y] * cj[d.x] * inv;
+      // (a) diagonal block: a[r][c] = W[col jp+c][r-c], r >= c
+      if (tid == 0) {
+        double a[KB][KB], l[KB][KB];
+#pragma unroll
+        for (int c = 0; c < KB; ++c)
+#pragma unroll
+          for (int r = c; r < KB; ++r) a[r][c] = W[(size_t)((jp + c) & mask) * CL + (r - c)];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          if (j < kb) {
+            const double D = a[j][j];
+            if (!(D > 0.0) || !isfinite(D)) ok = false;
+            const double inv = 1.0 / D;
+            fs.inv[j] = inv;
+#pragma unroll
+            for (int i = j + 1; i < KB; ++i) l[i][j] = a[i][j] * inv;
+#pragma unroll
+            for (int c = j + 1; c < KB; ++c)
+#pragma unroll
+              for (int i = c; i < KB; ++i) a[i][c] = fma(-a[i][j], l[c][j], a[i][c]);
+          } else {
+            fs.inv[j] = 0.0;                                   // short last panel: missing columns contribute nothing
+#pragma unroll
+            for (int i = j + 1; i < KB; ++i) l[i][j] = 0.0;
+          }
         }
-        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < KB; ++c)
+#pragma unroll
+          for (int r = c; r < KB; ++r) { W[(size_t)((jp + c) & mask) * CL + (r - c)] = a[r][c]; if (r > c) fs.Ld[r * KB + c] = l[r][c]; }
+        *fs.flag = ok ? 1 : 0;
       }
-      if (tid < KB - kb) fs.inv[kb + tid] = 0.0;               // short last panel: missing columns contribute nothing
       __syncthreads();
-      // (2) rank-kb trailing update
-      const double* pb[KB]; double iv[KB];
+      if (*fs.flag == 0) return false;                         // uniform
+      // (b) rows below the block: w_rc = a_rc - sum_{k < min(c, kb)} w_rk l_ck
+      for (int x = tid; x < M; x += nt) {
+        double wv[KB];
+        const bool band = x < kd;
 #pragma unroll
-      for (int jj = 0; jj < KB; ++jj) { pb[jj] = W + (size_t)((jp + jj) & mask) * CL; iv[jj] = fs.inv[jj]; }
-      for (int idx = tid; idx < fs.T; idx += nt) {
-        const ushort4 d = fs.desc[idx];
-        const int A0 = d.x & 0x7FFF, sA = d.x >> 15, B0 = d.y & 0x7FFF, sB = d.y >> 15;
-        double acc = 0.0;
+        for (int c = 0; c < KB; ++c) wv[c] = W[(size_t)((jp + c) & mask) * CL + (band ? KB + x - c : ldbp + x - kd)];
 #pragma unroll
-        for (int jj = 0; jj < KB; ++jj) acc = fma(pb[jj][A0 - jj * sA] * iv[jj], pb[jj][B0 - jj * sB], acc);
-        double* dst = d.z == 0xFFFF ? fs.Cl + d.w : W + (size_t)((jp + d.z) & mask) * CL + d.w;
-        *dst -= acc;
+        for (int c = 1; c < KB; ++c) {
+          double v = wv[c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) v = fma(-wv[k], fs.Ld[c * KB + k], v);   // l_ck = 0 for k >= kb
+          wv[c] = v;
+          if (!band || KB + x - c <= kd) W[(size_t)((jp + c) & mask) * CL + (band ? KB + x - c : ldbp + x - kd)] = v;   // never touch the zero padding
+        }
+      }
+      __syncthreads();
+      // (c) rank-kb trailing update on the FP64 tensor cores
+      {
+        const int fr = lane >> 2, fk = lane & 3;               // fragment row / k index of this lane
+        for (int bidx = warp; bidx < fs.nblocks; bidx += nwarps) {
+          const int bi = fs.blocks[bidx].x, bj = fs.blocks[bidx].y;   // bi >= bj
+          const int xa = 8 * bi + fr, xb = 8 * bj + fr;
+          double acc[2] = {0.0, 0.0};
+#pragma unroll
+          for (int ks = 0; ks < KB / 4; ++ks) {
+            const int jj = 4 * ks + fk;
+            const double* cj = W + (size_t)((jp + jj) & mask) * CL;
+            const double la = xa < kd ? cj[KB + xa - jj] : (xa < M ? cj[ldbp + xa - kd] : 0.0);
+            const double lb = xb < kd ? cj[KB + xb - jj] : (xb < M ? cj[ldbp + xb - kd] : 0.0);
+            dmma_acc(acc, -la * fs.inv[jj], lb);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int y = 8 * bj + 2 * fk + e;
+            if (xa >= y && xa < M) {
+              double* dst = y < kd ? W + (size_t)((jp + KB + y) & mask) * CL + (xa < kd ? xa - y : ldbp + xa - kd) : fs.Cl + (xa - kd) * fs.nbl + (y - kd);
+              *dst += acc[e];
+            }
+          }
+        }
       }
       __syncthreads();
     }
-    for (int idx = tid; idx < (gend - j0) * CL; idx += nt) { const int col = j0 + idx / CL, e = idx % CL; store(col, e, W[(size_t)(col & mask) * CL + e]); }
+    for (int col = j0 + warp; col < gend; col += nwarps) { const double* src = W + (size_t)(col & mask) * CL; for (int e = lane; e < CL; e += 32) store(col, e, src[e]); }
     __syncthreads();
   }
   return true;
@@ -177,17 +211,34 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
       t[k] = col >= base ? tw[col - base] : 0.0;
     }
   }
+  double* ipv = Bw + (size_t)(PB + kd) * ldb;                    // reciprocal pivots of the group (filled by all threads)
   for (int hi = top; hi > base; hi -= PB) {
     const int lo_own = max(base, hi - PB), lo = max(base, lo_own - kd);
-    for (int idx = tid; idx < (hi - lo) * ldb; idx += nt) { const int col = lo + idx / ldb; Bw[idx] = col < unknown_end ? Lb_g[(int64_t)lo * ldb + idx] : 0.0; }
+    {   // contiguous copy of the factor columns [lo, hi) with 8 loads in flight per thread
+      const int total = (hi - lo) * ldb, lim = (min(hi, unknown_end) - lo) * ldb;
+      const double* src = Lb_g + (int64_t)lo * ldb;
+      for (int b0 = tid; b0 < total; b0 += 8 * nt) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; v[u] = idx < lim ? src[idx] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; if (idx < total) Bw[idx] = v[u]; }
+      }
+    }
+    for (int idx = tid; idx < hi - lo_own; idx += nt) { const int col = lo_own + idx; ipv[idx] = col < unknown_end ? 1.0 / Lb_g[(int64_t)col * ldb] : 1.0; }
     __syncthreads();
     if (tid < 32) {
+      // L_{j, c} D_c of slot column c = j - r sits at Bw[(c - lo) * ldb + r]; as j decreases with c fixed, r decreases too,
+      // so the address just walks down by one double per step
+      const double* p[NR];
+#pragma unroll
+      for (int k = 0; k < NR; ++k) p[k] = Bw + (int64_t)(hi - 1 - r[k] - lo) * ldb + r[k];
       for (int j = hi - 1; j >= lo_own; --j) {
-        const int reg = (j % win) >> 5;
         double l[NR];
 #pragma unroll
-        for (int k = 0; k < NR; ++k) { const int c = j - r[k]; l[k] = (r[k] >= 1 && r[k] <= kd && c >= base && c < unknown_end) ? Bw[(size_t)(c - lo) * ldb + r[k]] : 0.0; }
-        const double ipiv = j < unknown_end ? 1.0 / Bw[(size_t)(j - lo) * ldb] : 1.0;
+        for (int k = 0; k < NR; ++k) l[k] = ((unsigned)(r[k] - 1) < (unsigned)kd && j - r[k] >= base) ? *p[k] : 0.0;
+        const double ipiv = ipv[j - lo_own];
+        const int reg = (j & (win - 1)) >> 5;
         double v = t[0];
 #pragma unroll
         for (int k = 1; k < NR; ++k) if (k == reg) v = t[k];
@@ -202,15 +253,18 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
           for (int k = 0; k < NR; ++k) if (k == reg) t[k] = tn;
         }
 #pragma unroll
-        for (int k = 0; k < NR; ++k) r[k] = r[k] == 0 ? win - 1 : r[k] - 1;
+        for (int k = 0; k < NR; ++k) {
+          if (r[k] == 0) { r[k] = win - 1; p[k] = Bw + (int64_t)(j - win - lo) * ldb + (win - 1); }   // slot re-assigned to column j - win (only read once r <= kd)
+          else { --r[k]; --p[k]; }
+        }
       }
     }
     __syncthreads();
   }
 }
 __device__ void backsub_dispatch(const double* Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB) {
-  if (kd < 64) backsub_warp<2>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
-  else if (kd < 96) backsub_warp<3>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+  if (kd < 32) backsub_warp<1>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+  else if (kd < 64) backsub_warp<2>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
   else if (kd < 128) backsub_warp<4>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
   else backsub_warp<8>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
 }
@@ -223,15 +277,16 @@ __device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, in
   double* p = fs.Cl + nbl * nbl;
   *extra = p; p += extra_doubles;
   fs.inv = p; p += KB;
-  fs.T = kd * (kd + 1) / 2 + nbl * kd + nbl * (nbl + 1) / 2;
-  fs.desc = reinterpret_cast<ushort4*>(p);
-  fs.pdesc = reinterpret_cast<ushort2*>(fs.desc + fs.T);
-  fs.pcount = reinterpret_cast<int*>(fs.pdesc + (KB - 1) * (kd + 1 + nbl));
+  fs.Ld = p; p += KB * KB;
+  fs.nbl = nbl;
+  fs.flag = reinterpret_cast<int*>(p);
+  fs.blocks = reinterpret_cast<uchar2*>(fs.flag + 2);
+  fs.nblocks = 0;
   return fs;
 }
 __host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int kd, int extra_doubles) {
-  const size_t T = (size_t)kd * (kd + 1) / 2 + (size_t)nbl * kd + (size_t)nbl * (nbl + 1) / 2;
-  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + KB) * sizeof(double) + T * sizeof(ushort4) + (size_t)(KB - 1) * (kd + 1 + nbl) * sizeof(ushort2) + (KB + 2) * sizeof(int) + 64;
+  const int nbk = (kd + nbl + 7) / 8;
+  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + KB + KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
 }
 
 // ---- kernel A: eliminate the interior knots of every time chunk ---------------------------------------------------
@@ -242,12 +297,11 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
   const bool has_left = c > 0, has_right = c < pl.P - 1;
   const int ldbp = kd + KB, CL = ldbp + nbl, WS = pl.WS_A;
   double* extra;
-  const FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
+  FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
   double* W = fs.W; double* Cl = fs.Cl;
   const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
-  build_trailing_descriptors(fs.desc, kd, ldbp, nbl);
-  build_panel_descriptors(fs.pdesc, fs.pcount, kd, ldbp, nbl);
+  fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
   __syncthreads();
   const int right_end = has_right ? b + w : b;
@@ -304,12 +358,12 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   const int nk = P.nk, nb = P.nb, nbp = nb + 1, nkr = pl.nkr, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w;
   const int ldbp = kdr + KB, CL = ldbp + nbp, WS = pl.WS_B, tid = threadIdx.x, nt = blockDim.x;
   double* xb;
-  const FactorSmem fs = carve_smem(sm, WS, CL, nbp, kdr, ldbp, &xb, nbp + 1);
+  FactorSmem fs = carve_smem(sm, WS, CL, nbp, kdr, ldbp, &xb, nbp + 1);
   double* W = fs.W; double* Cs = fs.Cl;           // nbp x nbp lower, row nb = rhs
   const double* C = P.ne + P.ne_off_C; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // a chunk hit a bad pivot
-  if (nkr > 0) { build_trailing_descriptors(fs.desc, kdr, ldbp, nbp); build_panel_descriptors(fs.pdesc, fs.pcount, kdr, ldbp, nbp); }
+  if (nkr > 0) fs.nblocks = build_block_table(fs.blocks, kdr + nbp);
   for (int idx = tid; idx < nbp * nbp; idx += nt) {
     const int b = idx / nbp, c = idx % nbp;
     double v = 0.0;
@@ -506,12 +560,12 @@ size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_
 size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
   const int nbp = P.nb + 1;
   const size_t fac = factor_smem_bytes(pl.WS_B, pl.kdr + KB + nbp, nbp, pl.kdr, nbp + 1);
-  const size_t back = ((size_t)pl.nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr) * sizeof(double) + 64;   // back-substitution reuses the window area
+  const size_t back = ((size_t)pl.nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;   // back-substitution reuses the window area
   return fac > back ? fac : back;
 }
 size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
   int maxlen = 0; for (int c = 0; c < pl.P; ++c) maxlen = std::max(maxlen, pl.b[c] - pl.a[c] + pl.w);
-  return ((size_t)pl.nbl + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb) * sizeof(double) + 64;
+  return ((size_t)pl.nbl + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128) * sizeof(double) + 64;
 }
 
 // Chunking of the knot columns.  The elimination cost per interior column is ~ constant, the reduced system has

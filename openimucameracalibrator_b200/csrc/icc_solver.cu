@@ -36,14 +36,15 @@ struct SolvePlan {
 };
 
 // Workspace (doubles): Lb[nk*ldb] | El[nk*nbl] | y[n] | t[nk] | R{bandr[nkr*ldbr] | Er[nkr*nbp] | Cr[nbp*nbp]} | Lbr[nkr*ldbr] | Elr[nkr*nbp] | tr[nkr]
-struct SolveWs { double *Lb, *El, *y, *t, *bandr, *Er, *Cr, *Lbr, *Elr, *tr; size_t reduced_doubles, total; };
+struct SolveWs { double *Lb, *El, *y, *t, *bandr, *Er, *Cr, *Lbr, *Elr, *tr, *Wg; size_t reduced_doubles, total; };
 __host__ __device__ inline SolveWs carve(double* ws, int nk, int nb, int ldb, const SolvePlan& pl) {
   SolveWs w; const int nbp = nb + 1; const size_t n = (size_t)nk + nb;
   w.Lb = ws; w.El = w.Lb + (size_t)nk * ldb; w.y = w.El + (size_t)nk * pl.nbl; w.t = w.y + n;
   w.bandr = w.t + nk; w.Er = w.bandr + (size_t)pl.nkr * pl.ldbr; w.Cr = w.Er + (size_t)pl.nkr * nbp;
   w.reduced_doubles = (size_t)pl.nkr * pl.ldbr + (size_t)pl.nkr * nbp + (size_t)nbp * nbp;
   w.Lbr = w.Cr + (size_t)nbp * nbp; w.Elr = w.Lbr + (size_t)pl.nkr * pl.ldbr; w.tr = w.Elr + (size_t)pl.nkr * nbp;
-  w.total = (size_t)(w.tr + pl.nkr - ws) + 16;
+  w.Wg = w.tr + ((pl.nkr + 3) & ~3);                               // nk x (kd + KB + nbl): pre-scaled window columns of kernel A
+  w.total = (size_t)(w.Wg + (size_t)nk * (ldb - 1 + 8 + pl.nbl) - ws) + 16;
   return w;
 }
 
@@ -76,27 +77,129 @@ __device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 // lower-triangular list of 8x8 blocks (bi >= bj) covering M trailing positions
-__device__ int build_block_table(uchar2* blocks, int M) {
+__device__ int build_block_table(uchar2* blocks, int M) {   // the nbk blocks of block-column 0 come first (look-ahead order)
   const int nbk = (M + 7) / 8, n = nbk * (nbk + 1) / 2;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) { const int bi = tri_row(idx), bj = idx - bi * (bi + 1) / 2; blocks[idx] = make_uchar2(bi, bj); }
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    if (idx < nbk) { blocks[idx] = make_uchar2(idx, 0); continue; }
+    const int k = idx - nbk, r = tri_row(k), c = k - r * (r + 1) / 2;     // lower triangle of the (nbk-1)^2 remainder
+    blocks[idx] = make_uchar2(r + 1, c + 1);
+  }
   return n;
 }
-struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; };
+struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; };   // Ld, inv: double-buffered by panel parity
+
+// (a)+(b) of one panel, executed by ONE warp (no block-wide barrier inside):
+//   (a) lane 0 factors the KB x KB diagonal block in registers (unit-lower l, pivots D -> inv), kb <= KB columns are pivots;
+//   (b) every lane forward-substitutes the KB panel entries of its trailing rows x (x = lane, lane+32, ...) against l.
+__device__ __forceinline__ void panel_factor_warp(const FactorSmem& fs, int jp, int kb, int kd, int ldbp, int CL, int mask, int buf) {
+  const int lane = threadIdx.x & 31, M = kd + fs.nbl;
+  double* W = fs.W;
+  double* inv = fs.inv + buf * KB;
+  double* Ld = fs.Ld + buf * KB * KB;
+  double* pc[KB];
+#pragma unroll
+  for (int c = 0; c < KB; ++c) pc[c] = W + (size_t)((jp + c) & mask) * CL;
+  if (lane == 0) {
+    double a[KB][KB], ivr[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c)
+#pragma unroll
+      for (int r = c; r < KB; ++r) a[r][c] = pc[c][r - c];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      if (j < kb) {
+        const double D = a[j][j];
+        if (!(D > 0.0) || !isfinite(D)) ok = false;
+        ivr[j] = 1.0 / D;
+#pragma unroll
+        for (int c = j + 1; c < KB; ++c) {
+          const double lcj = a[c][j] * ivr[j];
+#pragma unroll
+          for (int i = c; i < KB; ++i) a[i][c] = fma(-a[i][j], lcj, a[i][c]);
+        }
+      } else ivr[j] = 0.0;                                       // short last panel: missing columns contribute nothing
+    }
+#pragma unroll
+    for (int c = 0; c < KB; ++c) {
+      inv[c] = ivr[c];
+#pragma unroll
+      for (int r = c; r < KB; ++r) { pc[c][r - c] = a[r][c]; if (r > c) Ld[r * KB + c] = a[r][c] * ivr[c]; }
+    }
+    if (!ok) *fs.flag = 0;
+  }
+  __syncwarp();
+  // (b) rows below the block: w_rc = a_rc - sum_{k < min(c, kb)} w_rk l_ck   (l_ck = 0 for k >= kb)
+  double lreg[KB * (KB - 1) / 2];
+  {
+    int q = 0;
+#pragma unroll
+    for (int c = 1; c < KB; ++c)
+#pragma unroll
+      for (int k = 0; k < c; ++k) lreg[q++] = Ld[c * KB + k];
+  }
+  for (int x = lane; x < M; x += 32) {
+    const bool band = x < kd;
+    const int off = band ? KB + x : ldbp + x - kd;             // band rows: offset from column c is off - c
+    double wv[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c) wv[c] = pc[c][band ? off - c : off];
+    int q = 0;
+#pragma unroll
+    for (int c = 1; c < KB; ++c) {
+      double v = wv[c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) v = fma(-wv[k], lreg[q++], v);
+      wv[c] = v;
+      if (!band || off - c <= kd) pc[c][band ? off - c : off] = v;   // never touch the zero padding
+    }
+  }
+}
+
+// rank-KB tensor-core update of trailing blocks [b_begin, b_end) of the block table with the finished panel at jp
+__device__ __forceinline__ void trailing_blocks(const FactorSmem& fs, int jp, int kd, int ldbp, int CL, int mask, int buf, int b_begin, int b_end, int wslot, int nslots) {
+  const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3, M = kd + fs.nbl;
+  double* W = fs.W;
+  const double* inv = fs.inv + buf * KB;
+  for (int bidx = b_begin + wslot; bidx < b_end; bidx += nslots) {
+    const int bi = fs.blocks[bidx].x, bj = fs.blocks[bidx].y;   // bi >= bj
+    const int xa = 8 * bi + fr, xb = 8 * bj + fr;
+    double acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int ks = 0; ks < KB / 4; ++ks) {
+      const int jj = 4 * ks + fk;
+      const double* cj = W + (size_t)((jp + jj) & mask) * CL;
+      const double la = xa < kd ? cj[KB + xa - jj] : (xa < M ? cj[ldbp + xa - kd] : 0.0);
+      const double lb = xb < kd ? cj[KB + xb - jj] : (xb < M ? cj[ldbp + xb - kd] : 0.0);
+      dmma_acc(acc, -la * inv[jj], lb);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int y = 8 * bj + 2 * fk + e;
+      if (xa >= y && xa < M) {
+        double* dst = y < kd ? W + (size_t)((jp + KB + y) & mask) * CL + (xa < kd ? xa - y : ldbp + xa - kd) : fs.Cl + (xa - kd) * fs.nbl + (y - kd);
+        *dst += acc[e];
+      }
+    }
+  }
+}
 
 // LDL^T elimination of columns [j_begin, j_end).  load(col, e) returns the (scaled, damped) original entry e of column col
 // (0 outside the matrix AND for the padding offsets kd < e < ldbp); store(col, e, v) receives every finished column
 // (unscaled storage: entry 0 = pivot D_j, others = L_ij D_j).  On return the window holds the updated columns >= j_end.
-// Per panel of KB columns (4 block-wide barriers instead of one per column):
-//   (a) ONE thread factors the KB x KB diagonal block in registers (unit-lower l, pivots D);
-//   (b) one thread per trailing row forward-substitutes its KB panel entries against l (rows are independent);
-//   (c) rank-KB tensor-core update of the trailing window (see above).
+// Schedule per panel p (two block-wide barriers, look-ahead of depth one):
+//   1. all warps: tensor-core update of the trailing blocks in block-column 0 (= the columns of panel p+1)     | barrier
+//   2. warp 0: factor panel p+1 (panel_factor_warp)  ||  warps 1..: remaining trailing blocks of panel p        | barrier
+// so the sequential pivot chain of panel p+1 overlaps the bulk of panel p's rank-KB update.
+// The block table is ordered with the block-column-0 blocks first (build_block_table).
 template <class Load, class Store>
 __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int kd, int ldbp, int CL, int WS, Load load, Store store) {
   const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int PB = ((WS - kd) / KB) * KB, M = kd + fs.nbl;
+  const int PB = ((WS - kd - KB) / KB) * KB, M = kd + fs.nbl, ncol0 = (M + 7) / 8;   // ncol0 = blocks with bj == 0
   double* W = fs.W;
+  if (tid == 0) *fs.flag = 1;
   for (int j0 = j_begin; j0 < j_end; j0 += PB) {
-    const int first = j0 == j_begin ? j_begin : j0 + kd, last = j0 + PB + kd;
+    const int first = j0 == j_begin ? j_begin : j0 + kd + KB, last = j0 + PB + kd + KB;
     {   // group load with 8 independent global loads in flight per thread (the loads, not the math, bound this phase)
       const int total = (last - first) * CL;
       for (int b0 = tid; b0 < total; b0 += 8 * nt) {
@@ -109,85 +212,18 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
     }
     __syncthreads();
     const int gend = min(j0 + PB, j_end);
-    for (int jp = j0; jp < gend; jp += KB) {
-      const int kb = min(KB, gend - jp);
-      // (a) diagonal block: a[r][c] = W[col jp+c][r-c], r >= c
-      if (tid == 0) {
-        double a[KB][KB], l[KB][KB];
-#pragma unroll
-        for (int c = 0; c < KB; ++c)
-#pragma unroll
-          for (int r = c; r < KB; ++r) a[r][c] = W[(size_t)((jp + c) & mask) * CL + (r - c)];
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          if (j < kb) {
-            const double D = a[j][j];
-            if (!(D > 0.0) || !isfinite(D)) ok = false;
-            const double inv = 1.0 / D;
-            fs.inv[j] = inv;
-#pragma unroll
-            for (int i = j + 1; i < KB; ++i) l[i][j] = a[i][j] * inv;
-#pragma unroll
-            for (int c = j + 1; c < KB; ++c)
-#pragma unroll
-              for (int i = c; i < KB; ++i) a[i][c] = fma(-a[i][j], l[c][j], a[i][c]);
-          } else {
-            fs.inv[j] = 0.0;                                   // short last panel: missing columns contribute nothing
-#pragma unroll
-            for (int i = j + 1; i < KB; ++i) l[i][j] = 0.0;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < KB; ++c)
-#pragma unroll
-          for (int r = c; r < KB; ++r) { W[(size_t)((jp + c) & mask) * CL + (r - c)] = a[r][c]; if (r > c) fs.Ld[r * KB + c] = l[r][c]; }
-        *fs.flag = ok ? 1 : 0;
-      }
+    if (warp == 0) panel_factor_warp(fs, j0, min(KB, gend - j0), kd, ldbp, CL, mask, 0);   // prologue: first panel of the group
+    __syncthreads();
+    if (*fs.flag == 0) return false;                            // uniform
+    int buf = 0;
+    for (int jp = j0; jp < gend; jp += KB, buf ^= 1) {
+      const bool has_next = jp + KB < gend;
+      trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, 0, ncol0, warp, nwarps);
       __syncthreads();
-      if (*fs.flag == 0) return false;                         // uniform
-      // (b) rows below the block: w_rc = a_rc - sum_{k < min(c, kb)} w_rk l_ck
-      for (int x = tid; x < M; x += nt) {
-        double wv[KB];
-        const bool band = x < kd;
-#pragma unroll
-        for (int c = 0; c < KB; ++c) wv[c] = W[(size_t)((jp + c) & mask) * CL + (band ? KB + x - c : ldbp + x - kd)];
-#pragma unroll
-        for (int c = 1; c < KB; ++c) {
-          double v = wv[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) v = fma(-wv[k], fs.Ld[c * KB + k], v);   // l_ck = 0 for k >= kb
-          wv[c] = v;
-          if (!band || KB + x - c <= kd) W[(size_t)((jp + c) & mask) * CL + (band ? KB + x - c : ldbp + x - kd)] = v;   // never touch the zero padding
-        }
-      }
+      if (warp == 0) { if (has_next) panel_factor_warp(fs, jp + KB, min(KB, gend - jp - KB), kd, ldbp, CL, mask, buf ^ 1); }
+      else trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, ncol0, fs.nblocks, warp - 1, nwarps - 1);
       __syncthreads();
-      // (c) rank-kb trailing update on the FP64 tensor cores
-      {
-        const int fr = lane >> 2, fk = lane & 3;               // fragment row / k index of this lane
-        for (int bidx = warp; bidx < fs.nblocks; bidx += nwarps) {
-          const int bi = fs.blocks[bidx].x, bj = fs.blocks[bidx].y;   // bi >= bj
-          const int xa = 8 * bi + fr, xb = 8 * bj + fr;
-          double acc[2] = {0.0, 0.0};
-#pragma unroll
-          for (int ks = 0; ks < KB / 4; ++ks) {
-            const int jj = 4 * ks + fk;
-            const double* cj = W + (size_t)((jp + jj) & mask) * CL;
-            const double la = xa < kd ? cj[KB + xa - jj] : (xa < M ? cj[ldbp + xa - kd] : 0.0);
-            const double lb = xb < kd ? cj[KB + xb - jj] : (xb < M ? cj[ldbp + xb - kd] : 0.0);
-            dmma_acc(acc, -la * fs.inv[jj], lb);
-          }
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int y = 8 * bj + 2 * fk + e;
-            if (xa >= y && xa < M) {
-              double* dst = y < kd ? W + (size_t)((jp + KB + y) & mask) * CL + (xa < kd ? xa - y : ldbp + xa - kd) : fs.Cl + (xa - kd) * fs.nbl + (y - kd);
-              *dst += acc[e];
-            }
-          }
-        }
-      }
-      __syncthreads();
+      if (*fs.flag == 0) return false;                          // uniform
     }
     for (int col = j0 + warp; col < gend; col += nwarps) { const double* src = W + (size_t)(col & mask) * CL; for (int e = lane; e < CL; e += 32) store(col, e, src[e]); }
     __syncthreads();
@@ -276,8 +312,8 @@ __device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, in
   fs.Cl = fs.W + (size_t)WS * CL;
   double* p = fs.Cl + nbl * nbl;
   *extra = p; p += extra_doubles;
-  fs.inv = p; p += KB;
-  fs.Ld = p; p += KB * KB;
+  fs.inv = p; p += 2 * KB;
+  fs.Ld = p; p += 2 * KB * KB;
   fs.nbl = nbl;
   fs.flag = reinterpret_cast<int*>(p);
   fs.blocks = reinterpret_cast<uchar2*>(fs.flag + 2);
@@ -286,7 +322,34 @@ __device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, in
 }
 __host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int kd, int extra_doubles) {
   const int nbk = (kd + nbl + 7) / 8;
-  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + KB + KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
+  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + 2 * KB + 2 * KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
+}
+
+// ---- kernel A0: materialise the scaled + damped window columns of every chunk (fully parallel) ----------------------
+// Wg[col][e]: e < ldbp band entries (zero padding beyond kd, rows beyond the chunk's right separator masked), then the local
+// border [coupling to the left separator (stored transposed in H) | border | rhs].  Kernel A then only copies columns.
+__global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp) {
+  const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl;
+  const int a = pl.a[c], b = pl.b[c];
+  const bool has_left = c > 0, has_right = c < pl.P - 1;
+  const int ldbp = kd + KB, CL = ldbp + nbl, right_end = has_right ? b + w : b;
+  const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
+  SolveWs ws = carve(wsp, nk, nb, ldb, pl);
+  const int total = (right_end - a) * CL;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+    const int col = a + idx / CL, e = idx % CL;
+    double v = 0.0;
+    if (e < ldbp) {
+      const int i = col + e;
+      if (e <= kd && i < nk && i < right_end) { v = band[(int64_t)col * ldb + e] * scale[col] * scale[i]; if (e == 0) v += lm_d2(P, scale, sp, col); }
+    } else {
+      const int lb = e - ldbp;
+      if (lb < w) { if (has_left && col < b) { const int s = a - w + lb, off = col - s; if (off <= kd) v = band[(int64_t)s * ldb + off] * scale[s] * scale[col]; } }
+      else if (lb < w + nb) v = E[(int64_t)col * nb + (lb - w)] * scale[col] * scale[nk + lb - w];
+      else v = -g[col] * scale[col];
+    }
+    ws.Wg[(int64_t)col * CL + e] = v;
+  }
 }
 
 // ---- kernel A: eliminate the interior knots of every time chunk ---------------------------------------------------
@@ -299,30 +362,12 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
   double* extra;
   FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
   double* W = fs.W; double* Cl = fs.Cl;
-  const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
   fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
   __syncthreads();
   const int right_end = has_right ? b + w : b;
-  auto load = [&](int col, int e) -> double {
-    if (col >= right_end) return 0.0;
-    if (e < ldbp) {
-      const int i = col + e;
-      if (e > kd || i >= nk || i >= right_end) return 0.0;      // padding / rows beyond the right separator (next chunk's)
-      double v = band[(int64_t)col * ldb + e] * scale[col] * scale[i];
-      if (e == 0) v += lm_d2(P, scale, sp, col);
-      return v;
-    }
-    const int lb = e - ldbp;
-    if (lb < w) {                                               // coupling to the left separator (stored transposed in H)
-      if (!has_left || col >= b) return 0.0;
-      const int s = a - w + lb, off = col - s;
-      return off <= kd ? band[(int64_t)s * ldb + off] * scale[s] * scale[col] : 0.0;
-    }
-    if (lb < w + nb) return E[(int64_t)col * nb + (lb - w)] * scale[col] * scale[nk + lb - w];
-    return -g[col] * scale[col];
-  };
+  auto load = [&](int col, int e) -> double { return col < right_end ? ws.Wg[(int64_t)col * CL + e] : 0.0; };
   auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) ws.Lb[(int64_t)col * ldb + e] = v; } else ws.El[(int64_t)col * nbl + (e - ldbp)] = v; };
   const bool ok = factor_range(fs, a, b, kd, ldbp, CL, WS, load, store);
   if (!ok) { if (threadIdx.x == 0) scal[SC_OK] = -1.0; return; }
@@ -582,10 +627,10 @@ SolvePlan make_plan(const DeviceProblem& P) {
   for (int c = 0; c < Pn; ++c) { const int len = interior_total / Pn + (c < interior_total % Pn ? 1 : 0); pl.a[c] = pos; pl.b[c] = pos + len; pos += len + pl.w; }
   pl.nkr = (Pn - 1) * pl.w; pl.kdr = Pn > 1 ? 2 * pl.w - 1 : 0; pl.ldbr = pl.kdr + 1;
   pl.nbl = pl.w + nb + 1;
-  pl.WS_A = pow2_at_least(kd + KB + 1); pl.WS_B = pow2_at_least(pl.kdr + KB + 1);
+  pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_B = pow2_at_least(pl.kdr + 2 * KB + 1);
   // grow the windows while they fit comfortably (larger panels amortise the panel load/store)
-  while (pl.WS_A < 256) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 160 * 1024) break; pl = t; }
-  while (pl.WS_B < 256) { SolvePlan t = pl; t.WS_B *= 2; if (smem_B(P, t) > 160 * 1024) break; pl = t; }
+  while (pl.WS_A < 256) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 200 * 1024) break; pl = t; }
+  while (pl.WS_B < 256) { SolvePlan t = pl; t.WS_B *= 2; if (smem_B(P, t) > 200 * 1024) break; pl = t; }
   return pl;
 }
 
@@ -612,7 +657,10 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   if (sB > cfgB) { cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sB); cfgB = sB; }
   if (sC > cfgC) { cudaFuncSetAttribute(chunk_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sC); cfgC = sC; }
   cudaMemsetAsync(ws.bandr, 0, ws.reduced_doubles * sizeof(double), st);
-  if (P.nk > 0) { chunk_factor_kernel<<<pl.P, NT, sA, st>>>(P, pl, scale, sp, workspace, scal); count_launch(); }
+  if (P.nk > 0) {
+    prepare_kernel<<<dim3(pl.P, 16), 256, 0, st>>>(P, pl, scale, sp, workspace); count_launch();
+    chunk_factor_kernel<<<pl.P, NT, sA, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
+  }
   reduced_solve_kernel<<<1, NT, sB, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
   if (P.nk > 0) { chunk_backsub_kernel<<<pl.P, 256, sC, st>>>(P, pl, workspace, scal); count_launch(); }
   const int n = P.nk + P.nb;

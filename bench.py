@@ -238,8 +238,15 @@ def main():
         # FP64 tensor-core work actually issued by the vision kernel: 21 m8n8k4 MMAs (512 flop) per 4 tile rows
         rows = nv
         dmma_flops = (rows / 4.0) * 21 * 512
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (config 4 only)
+            if args.config == 4:
+                nc = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))["vision_kernel<1>"]
+                traffic = nc["dram_bytes_read"] + nc["dram_bytes_write"]; traffic_src = "profiles/r1_ncu_summary.json (ncu --set full, one launch)"
+        except Exception:
+            pass
         roof = {"kernel": "vision_kernel<JAC> (residual + analytic Jacobian + J^T J tile, one warp per frame)", "bound": "hbm", "achieved": ach,
-                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_vis, "launch_ms": ms_vis,
                 "note": "arithmetic intensity >> FP64 ridge: the kernel is FP64-issue bound, not HBM bound (DESIGN.md); see fp64",
                 "fp64": {"tensor_tflops_issued": dmma_flops / (ms_vis * 1e-3) / 1e12, "nominal_peak_tflops": 37.0,

@@ -91,15 +91,27 @@ struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* 
 // (a)+(b) of one panel, executed by ONE warp (no block-wide barrier inside):
 //   (a) lane 0 factors the KB x KB diagonal block in registers (unit-lower l, pivots D -> inv), kb <= KB columns are pivots;
 //   (b) every lane forward-substitutes the KB panel entries of its trailing rows x (x = lane, lane+32, ...) against l.
+// Reciprocal of a positive pivot on the critical path of the factorisation: single-precision hardware seed (MUFU.RCP) +
+// two FP64 Newton steps (4 dependent FMAs, <= 2 ulp) instead of the ~2x longer correctly-rounded division sequence.
+// Pivots outside the float range fall back to the exact division.
+__device__ __forceinline__ double fast_rcp(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;
+  double r = (double)__frcp_rn((float)d);
+  double e = fma(-d, r, 1.0); r = fma(r, e, r);
+  e = fma(-d, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+
+constexpr int PW = 3;   // warps cooperating on a panel factorisation (96 lanes >= typical M = kd + nbl rows)
 __device__ __forceinline__ void panel_factor_warp(const FactorSmem& fs, int jp, int kb, int kd, int ldbp, int CL, int mask, int buf) {
-  const int lane = threadIdx.x & 31, M = kd + fs.nbl;
+  const int lane = threadIdx.x & 31, M = kd + fs.nbl, gl = threadIdx.x;   // gl = lane index within the PW-warp group (warps 0..PW-1)
   double* W = fs.W;
   double* inv = fs.inv + buf * KB;
   double* Ld = fs.Ld + buf * KB * KB;
   double* pc[KB];
 #pragma unroll
   for (int c = 0; c < KB; ++c) pc[c] = W + (size_t)((jp + c) & mask) * CL;
-  if (lane == 0) {
+  if (gl == 0) {
     double a[KB][KB], ivr[KB];
 #pragma unroll
     for (int c = 0; c < KB; ++c)
@@ -128,7 +140,7 @@ __device__ __forceinline__ void panel_factor_warp(const FactorSmem& fs, int jp, 
     }
     if (!ok) *fs.flag = 0;
   }
-  __syncwarp();
+  asm volatile("bar.sync 1, %0;" :: "r"(PW * 32) : "memory");   // named barrier among the PW panel warps only
   // (b) rows below the block: w_rc = a_rc - sum_{k < min(c, kb)} w_rk l_ck   (l_ck = 0 for k >= kb)
   double lreg[KB * (KB - 1) / 2];
   {
@@ -138,7 +150,7 @@ __device__ __forceinline__ void panel_factor_warp(const FactorSmem& fs, int jp, 
 #pragma unroll
       for (int k = 0; k < c; ++k) lreg[q++] = Ld[c * KB + k];
   }
-  for (int x = lane; x < M; x += 32) {
+  for (int x = gl; x < M; x += PW * 32) {
     const bool band = x < kd;
     const int off = band ? KB + x : ldbp + x - kd;             // band rows: offset from column c is off - c
     double wv[KB];
@@ -189,7 +201,7 @@ __device__ __forceinline__ void trailing_blocks(const FactorSmem& fs, int jp, in
 // (unscaled storage: entry 0 = pivot D_j, others = L_ij D_j).  On return the window holds the updated columns >= j_end.
 // Schedule per panel p (two block-wide barriers, look-ahead of depth one):
 //   1. all warps: tensor-core update of the trailing blocks in block-column 0 (= the columns of panel p+1)     | barrier
-//   2. warp 0: factor panel p+1 (panel_factor_warp)  ||  warps 1..: remaining trailing blocks of panel p        | barrier
+//   2. warps 0..PW-1: factor panel p+1 (panel_factor_warp)  ||  other warps: remaining trailing blocks of panel p | barrier
 // so the sequential pivot chain of panel p+1 overlaps the bulk of panel p's rank-KB update.
 // The block table is ordered with the block-column-0 blocks first (build_block_table).
 template <class Load, class Store>
@@ -212,7 +224,7 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
     }
     __syncthreads();
     const int gend = min(j0 + PB, j_end);
-    if (warp == 0) panel_factor_warp(fs, j0, min(KB, gend - j0), kd, ldbp, CL, mask, 0);   // prologue: first panel of the group
+    if (warp < PW) panel_factor_warp(fs, j0, min(KB, gend - j0), kd, ldbp, CL, mask, 0);   // prologue: first panel of the group
     __syncthreads();
     if (*fs.flag == 0) return false;                            // uniform
     int buf = 0;
@@ -220,8 +232,8 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
       const bool has_next = jp + KB < gend;
       trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, 0, ncol0, warp, nwarps);
       __syncthreads();
-      if (warp == 0) { if (has_next) panel_factor_warp(fs, jp + KB, min(KB, gend - jp - KB), kd, ldbp, CL, mask, buf ^ 1); }
-      else trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, ncol0, fs.nblocks, warp - 1, nwarps - 1);
+      if (warp < PW) { if (has_next) panel_factor_warp(fs, jp + KB, min(KB, gend - jp - KB), kd, ldbp, CL, mask, buf ^ 1); }
+      if (warp >= PW || !has_next) trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, ncol0, fs.nblocks, has_next ? warp - PW : warp, has_next ? nwarps - PW : nwarps);
       __syncthreads();
       if (*fs.flag == 0) return false;                          // uniform
     }

@@ -180,6 +180,8 @@ icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summa
 icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval);
 /* The handle's cudaStream_t (so that callers can bracket calls with their own CUDA events on the launching stream). */
 void* icc_get_stream(icc_handle* h);
+/* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
+void icc_trim_device_cache(void);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,12 +26,38 @@ namespace {
 
 constexpr double S_TO_NS = 1e9, NS_TO_S = 1e-9;
 
+// Process-wide caching allocator for device blocks: a calibration job allocates ~30 buffers and the CUDA driver's
+// cudaMalloc / cudaFree cost 0.1-1 ms each, which would dominate the whole-job wall clock of back-to-back jobs.
+// Freed blocks are kept (per device) and handed out again best-fit; icc_trim_device_cache() returns them to the driver.
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<size_t, std::pair<int, void*>> free_blocks;   // bytes -> (device, ptr)
+  cudaError_t get(size_t bytes, void** out) {
+    int dev = 0; cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto it = free_blocks.lower_bound(bytes); it != free_blocks.end() && it->first <= 2 * bytes + 4096; ++it)
+        if (it->second.first == dev) { *out = it->second.second; free_blocks.erase(it); return cudaSuccess; }
+    }
+    return cudaMalloc(out, bytes);
+  }
+  void put(size_t bytes, void* p) { int dev = 0; cudaGetDevice(&dev); std::lock_guard<std::mutex> lk(mu); free_blocks.emplace(bytes, std::make_pair(dev, p)); }
+  void trim() { std::lock_guard<std::mutex> lk(mu); for (auto& kv : free_blocks) { cudaSetDevice(kv.second.first); cudaFree(kv.second.second); } free_blocks.clear(); }
+};
+BlockCache& block_cache() { static BlockCache* c = new BlockCache(); return *c; }   // intentionally leaked: outlives every handle
+
 template <class T>
 struct DevBuf {
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0, cap_bytes = 0;
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-  cudaError_t alloc(size_t count) { release(); n = count; if (!count) return cudaSuccess; return cudaMalloc(&p, count * sizeof(T)); }
+  void release() { if (p) block_cache().put(cap_bytes, p); p = nullptr; n = 0; cap_bytes = 0; }
+  cudaError_t alloc(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    if (p && cap_bytes >= bytes) { n = count; return cudaSuccess; }
+    release(); n = count; if (!count) return cudaSuccess;
+    void* q = nullptr; cudaError_t e = block_cache().get(bytes, &q); if (e != cudaSuccess) { n = 0; return e; }
+    p = static_cast<T*>(q); cap_bytes = bytes; return cudaSuccess;
+  }
   cudaError_t upload(const std::vector<T>& v) { cudaError_t e = alloc(v.size()); if (e != cudaSuccess || v.empty()) return e; return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice); }
 };
 
@@ -105,8 +132,15 @@ bool calc_times(int64_t sensor_ns, int64_t start_ns, int64_t dt_ns, size_t nr_kn
 }
 
 size_t nearest_index(double t, const std::vector<double>& ts, double& dist_out) {   // utils.cc:194-212
-  double best = 1.7976931348623157e308; size_t idx = 0;
-  for (size_t i = 0; i < ts.size(); ++i) { const double d = std::fabs(t - ts[i]); if (d < best) { best = d; dist_out = d; idx = i; if (d == 0.0) break; } }
+  // FindClosestTimestamp is a linear scan keeping the FIRST strict minimum of |t - ts[i]|; on the time-sorted, distinct
+  // view timestamps used here the same index is found by bisection + comparison of the two neighbours.
+  const size_t n = ts.size();
+  size_t hi = std::lower_bound(ts.begin(), ts.end(), t) - ts.begin();   // first ts >= t
+  size_t idx;
+  if (hi == 0) idx = 0;
+  else if (hi == n) idx = n - 1;
+  else idx = (std::fabs(t - ts[hi - 1]) <= std::fabs(t - ts[hi])) ? hi - 1 : hi;   // tie -> earlier index, like the scan
+  dist_out = std::fabs(t - ts[idx]);
   return idx;
 }
 
@@ -495,7 +529,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     if (ok) units.push_back({f.t_s, 0, i, 2 * (f.c1 - f.c0)}); else ++h->dropped_frames;
   }
   struct ImuHost { double t_s; int64_t st; int s_so3, s_r3, s_ba, s_bg; int src; };
-  std::vector<ImuHost> all_imu;
+  std::vector<ImuHost> all_imu; all_imu.reserve(h->imu_t.size()); units.reserve(nf + h->imu_t.size());
   for (size_t i = 0; i < h->imu_t.size(); ++i) {
     const double t = h->imu_t[i] + ipp->time_offset_imu_to_cam_s;
     if (t < h->t0_s || t >= h->tend_s) continue;
@@ -507,7 +541,16 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     all_imu.push_back({t, t_ns - h->start_ns, (int)b, (int)a, (int)c, (int)d, (int)i});
     units.push_back({t, 1, (int)all_imu.size() - 1, 6});
   }
-  std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.t < y.t; });
+  {   // time order with frames before IMU samples on ties (== stable sort of [frames..., imu...]); both streams are normally
+      // already sorted, so merge in O(n) and only fall back to sorting when they are not
+    const size_t nfu = units.size() - all_imu.size();
+    auto lt = [](const Unit& x, const Unit& y) { return x.t < y.t; };
+    if (!std::is_sorted(units.begin(), units.begin() + nfu, lt)) std::stable_sort(units.begin(), units.begin() + nfu, lt);
+    if (!std::is_sorted(units.begin() + nfu, units.end(), lt)) std::stable_sort(units.begin() + nfu, units.end(), lt);
+    std::vector<Unit> merged(units.size());
+    std::merge(units.begin(), units.begin() + nfu, units.begin() + nfu, units.end(), merged.begin(), lt);
+    units.swap(merged);
+  }
   long total = 0; for (const auto& u : units) total += u.nres;
   const long lo = total * h->shard_rank / h->shard_world, hi = total * (h->shard_rank + 1) / h->shard_world;
   long run = 0;
@@ -515,6 +558,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   for (const auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; (u.kind == 0 ? frame_sel : imu_sel).push_back(u.idx); }
   std::sort(frame_sel.begin(), frame_sel.end());
   h->frames.clear(); h->used_uv.clear(); h->used_pid.clear();
+  h->used_uv.reserve(h->uv.size()); h->used_pid.reserve(h->point_ids.size()); h->frames.reserve(frame_sel.size());
   for (int fi : frame_sel) {
     FrameHost f = all_frames[fi];
     const int c0 = (int)h->used_pid.size();
@@ -523,6 +567,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     h->frames.push_back(f);
   }
   h->imu_used_t.clear(); h->imu_used_acc.clear(); h->imu_used_gyr.clear(); h->imu_used_st.clear(); h->cells.clear();
+  h->imu_used_t.reserve(imu_sel.size()); h->imu_used_st.reserve(imu_sel.size()); h->imu_used_acc.reserve(3 * imu_sel.size()); h->imu_used_gyr.reserve(3 * imu_sel.size());
   for (int mi : imu_sel) {
     const ImuHost& m = all_imu[mi];
     const int idx = (int)h->imu_used_t.size();
@@ -771,5 +816,6 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
 }
 
 void* icc_get_stream(icc_handle* h) { return h ? (void*)h->stream : nullptr; }
+void icc_trim_device_cache(void) { block_cache().trim(); }
 
 }  // extern "C"

@@ -281,30 +281,30 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
       const double* p[NR];
 #pragma unroll
       for (int k = 0; k < NR; ++k) p[k] = Bw + (int64_t)(hi - 1 - r[k] - lo) * ldb + r[k];
+      // value that enters this lane's slot when the lane next owns a column (column c enters after column c + win resolved):
+      // fetched with one non-divergent vector load per 32 columns instead of a divergent load on the critical path
+      double tnext = 0.0;
+      { const int c_own = ((hi - 1) & ~31) + lane - win; tnext = (c_own >= base && c_own + win <= hi - 1) ? tw[c_own - base] : 0.0; }
       for (int j = hi - 1; j >= lo_own; --j) {
         double l[NR];
 #pragma unroll
         for (int k = 0; k < NR; ++k) l[k] = ((unsigned)(r[k] - 1) < (unsigned)kd && j - r[k] >= base) ? *p[k] : 0.0;
         const double ipiv = ipv[j - lo_own];
         const int reg = (j & (win - 1)) >> 5;
+        const bool owner = lane == (j & 31);
         double v = t[0];
 #pragma unroll
         for (int k = 1; k < NR; ++k) if (k == reg) v = t[k];
         const double xj = __shfl_sync(0xffffffffu, v, j & 31) * ipiv;
 #pragma unroll
-        for (int k = 0; k < NR; ++k) t[k] = fma(-l[k], xj, t[k]);
-        if (lane == (j & 31)) {
-          tw[j - base] = xj;
-          const int cnew = j - win;
-          const double tn = cnew >= base ? tw[cnew - base] : 0.0;
-#pragma unroll
-          for (int k = 0; k < NR; ++k) if (k == reg) t[k] = tn;
-        }
+        for (int k = 0; k < NR; ++k) t[k] = (owner && k == reg) ? tnext : fma(-l[k], xj, t[k]);
+        if (owner) tw[j - base] = xj;
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
           if (r[k] == 0) { r[k] = win - 1; p[k] = Bw + (int64_t)(j - win - lo) * ldb + (win - 1); }   // slot re-assigned to column j - win (only read once r <= kd)
           else { --r[k]; --p[k]; }
         }
+        if ((j & 31) == 0 && j > lo_own) { const int c_own = j - 32 + lane - win; tnext = c_own >= base ? tw[c_own - base] : 0.0; }   // next 32-column block
       }
     }
     __syncthreads();

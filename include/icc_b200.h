@@ -28,7 +28,7 @@ typedef enum {
   ICC_ERR_NO_DEVICE = 2,       /* CUDA device / driver unusable: the product path never falls back to the CPU */
   ICC_ERR_CUDA = 3,
   ICC_ERR_STATE = 4,           /* call order violated (e.g. optimize before batch_init_spline) */
-  ICC_ERR_UNSUPPORTED = 5,     /* flag combination outside the hot CLI's reach (POINTS, IMU_INTRINSICS) */
+  ICC_ERR_UNSUPPORTED = 5,     /* POINTS flag (board points as parameters; never set by the hot CLI) */
   ICC_ERR_NUMERIC = 6          /* factorisation broke down / non-finite cost */
 } icc_status;
 
@@ -170,7 +170,8 @@ icc_status icc_eval_trajectory(icc_handle* h, int n, const int64_t* t_ns, double
 icc_status icc_num_residuals(const icc_handle* h, int* n_vision, int* n_accel, int* n_gyro);   /* scalar residual counts */
 icc_status icc_num_tangent(const icc_handle* h, int flags, int* n);
 /* One evaluation at the current state.  Canonical tangent order: so3 knots (3 each), r3 knots (3 each), T_i_c (6: upsilon,
- * omega), gravity (3), line delay (1), acc-bias knots (3 each), gyr-bias knots (3 each) — only blocks active under `flags`.
+ * omega), gravity (3), line delay (1), acc-bias knots (3 each), gyr-bias knots (3 each), accelerometer intrinsics (6),
+ * gyroscope intrinsics (9) — only blocks active under `flags`.
  * residuals: [vision 2/corner in frame order | accel 3/sample | gyro 3/sample].  hessian_dense: n x n row-major J^T J
  * (small problems only).  Any output may be NULL. */
 icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residuals, double* gradient, double* hessian_dense);

@@ -199,12 +199,12 @@ icc_status push_state_to_device(icc_handle* h) {
 // R3 on ties) form the banded part; T_i_c, gravity, line delay and bias knots form the border.
 icc_status configure(icc_handle* h, int flags) {
   if (flags & ICC_FLAG_POINTS) return fail(h, ICC_ERR_UNSUPPORTED, "POINTS is never set by the hot CLI and is not supported");
-  if (flags & ICC_FLAG_IMU_INTRINSICS) return fail(h, ICC_ERR_UNSUPPORTED, "IMU_INTRINSICS is never set by the hot CLI and is not supported");
   if (h->cur_flags == flags) return ICC_OK;
   const int nso3 = (int)h->so3.size() / 4, nr3 = (int)h->r3.size() / 3, nba = (int)h->ba.size() / 3, nbg = (int)h->bg.size() / 3;
   const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
   const bool ld = (flags & ICC_FLAG_CAM_LINE_DELAY) && h->ip.init_line_delay_s != 0.0;
   const bool ab = flags & (ICC_FLAG_ACC_BIAS | ICC_FLAG_IMU_BIASES), gb = flags & (ICC_FLAG_GYR_BIAS | ICC_FLAG_IMU_BIASES);
+  const bool intr = flags & ICC_FLAG_IMU_INTRINSICS;
   // canonical offsets
   int n = 0;
   const int c_so3 = spline ? n : -1; if (spline) n += 3 * nso3;
@@ -214,6 +214,8 @@ icc_status configure(icc_handle* h, int flags) {
   const int c_ld = ld ? n : -1; if (ld) n += 1;
   const int c_ba = ab ? n : -1; if (ab) n += 3 * nba;
   const int c_bg = gb ? n : -1; if (gb) n += 3 * nbg;
+  const int c_ai = intr ? n : -1; if (intr) n += 6;
+  const int c_gi = intr ? n : -1; if (intr) n += 9;
   h->n_tan = n;
   h->so3_col.assign(nso3, -1); h->r3_col.assign(nr3, -1); h->ba_col.assign(nba, -1); h->bg_col.assign(nbg, -1);
   int pos = 0;
@@ -231,6 +233,8 @@ icc_status configure(icc_handle* h, int flags) {
   h->col_ld = ld ? pos : -1; if (ld) pos += 1;
   if (ab) for (int k = 0; k < nba; ++k) { h->ba_col[k] = pos; pos += 3; }
   if (gb) for (int k = 0; k < nbg; ++k) { h->bg_col[k] = pos; pos += 3; }
+  const int col_ai = intr ? pos : -1; if (intr) pos += 6;
+  const int col_gi = intr ? pos : -1; if (intr) pos += 9;
   const int nb = pos - nk;
   h->perm.assign(n, -1);
   if (spline) { for (int k = 0; k < nso3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_so3 + 3 * k + d] = h->so3_col[k] + d; for (int k = 0; k < nr3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_r3 + 3 * k + d] = h->r3_col[k] + d; }
@@ -239,6 +243,7 @@ icc_status configure(icc_handle* h, int flags) {
   if (ld) h->perm[c_ld] = h->col_ld;
   if (ab) for (int k = 0; k < nba; ++k) for (int d = 0; d < 3; ++d) h->perm[c_ba + 3 * k + d] = h->ba_col[k] + d;
   if (gb) for (int k = 0; k < nbg; ++k) for (int d = 0; d < 3; ++d) h->perm[c_bg + 3 * k + d] = h->bg_col[k] + d;
+  if (intr) { for (int d = 0; d < 6; ++d) h->perm[c_ai + d] = col_ai + d; for (int d = 0; d < 9; ++d) h->perm[c_gi + d] = col_gi + d; }
   // half bandwidth: widest knot window touched by one residual block
   int kd = 0;
   if (spline) {
@@ -258,7 +263,7 @@ icc_status configure(icc_handle* h, int flags) {
   h->cur_flags = flags;
   DeviceProblem& P = h->P;
   P.nk = nk; P.nb = nb; P.kd = kd; P.ldb = kd + 1;
-  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.bias_active = (ab || gb) ? 1 : 0;
+  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.col_ai = col_ai; P.col_gi = col_gi; P.bias_active = (ab || gb) ? 1 : 0; P.intr_active = intr ? 1 : 0;
   P.ne_off_E = (int64_t)nk * P.ldb; P.ne_off_C = P.ne_off_E + (int64_t)nk * nb; P.ne_off_g = P.ne_off_C + (int64_t)nb * nb;
   P.ne_off_cost = P.ne_off_g + nk + nb; P.ne_size = (P.ne_off_cost + 1 + 3) / 4 * 4;
   if (h->device >= 0) {

@@ -40,7 +40,7 @@ struct WarpCtx {
   V3 p[6];
   V3 ba[3], bg[3];
   int gidx[64];
-  int gidx2[32];
+  int gidx2[40];
 };
 
 ICC_D void mma_f64(double (&c)[2], double a, double b) {
@@ -275,15 +275,17 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
 
 // ---------------------------------------------------------------------------------------------------------------
 // IMU: accelerometer + gyroscope residuals of one knot-interval cell per warp.
-//   accel tile columns: [so3 0..17 | r3 18..35 | g 36..38 | (ba 39..47) | r]     NB = 5 (no bias) / 7 (bias)
-//   gyro  tile columns: [so3 0..17 | (bg 18..26) | r]                            NB = 3 (no bias) / 4 (bias)
+//   accel tile columns: [so3 0..17 | r3 18..35 | g 36..38 | (ba 39..47) | (acc intr 48..53) | r]   NB = 5 / 7 / 7
+//   gyro  tile columns: [so3 0..17 | (bg 18..26) | (gyr intr 27..35) | r]                          NB = 3 / 4 / 5
+//   MODE 0 = biases fixed, 1 = bias knots free, 2 = bias knots + IMU intrinsics free (SplineOptimFlags::IMU_INTRINSICS)
 // ---------------------------------------------------------------------------------------------------------------
-template <bool JAC, bool BIAS>
+template <bool JAC, int MODE>
 __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, DeviceState S, double* cost_out, double* res_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NBA = BIAS ? 7 : 5, NBG = BIAS ? 4 : 3;
-  constexpr int RESA = BIAS ? 48 : 39, NCOLA = RESA + 1, RESG = BIAS ? 27 : 18, NCOLG = RESG + 1;
+  constexpr bool BIAS = MODE >= 1, INTR = MODE == 2;
+  constexpr int NBA = BIAS ? 7 : 5, NBG = MODE == 0 ? 3 : MODE == 1 ? 4 : 5;
+  constexpr int RESA = MODE == 0 ? 39 : MODE == 1 ? 48 : 54, NCOLA = RESA + 1, RESG = MODE == 0 ? 18 : MODE == 1 ? 27 : 36, NCOLG = RESG + 1;
   constexpr int TILE_COLS = 8 * NBA;
   WarpCtx* wc = reinterpret_cast<WarpCtx*>(smem_raw) + warp;
   double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (TILE_COLS * LDJ);
@@ -311,13 +313,14 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
         else if (c < 36) { const int b = P.r3_col[cell.s_r3 + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
         else if (c < 39) g = P.col_g < 0 ? -1 : P.col_g + (c - 36);
         else if (BIAS && c < 48) { const int b = P.ba_col[cell.s_ba + (c - 39) / 3]; g = b < 0 ? -1 : b + (c - 39) % 3; }
+        else if (INTR && c < 54) g = P.col_ai < 0 ? -1 : P.col_ai + (c - 48);
         wc->gidx[c] = g;
       }
-      {
-        const int c = lane;
+      for (int c = lane; c < 40; c += 32) {
         int g = -1;
         if (c < 18) { const int b = P.so3_col[cell.s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
         else if (BIAS && c < 27) { const int b = P.bg_col[cell.s_bg + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
+        else if (INTR && c < 36) g = P.col_gi < 0 ? -1 : P.col_gi + (c - 27);
         wc->gidx2[c] = g;
       }
     }
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
       Chain ch;
       double ra[3] = {0, 0, 0}, rg[3] = {0, 0, 0};
       double ddc[6], cba[3], cbg[3];
-      V3 h = v3(0, 0, 0);
+      V3 h = v3(0, 0, 0), va = v3(0, 0, 0), vg = v3(0, 0, 0);   // va / vg: raw readings minus bias
       if (act) {
         const int64_t st = P.imu_t_ns[i];
         // CalcTimes (impl.h:763-788): u = (st % dt) / dt with the segment index known from the cell
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
         for (int k = 0; k < 3; ++k) { bacc = fma3(cba[k], wc->ba[k], bacc); bgyr = fma3(cbg[k], wc->bg[k], bgyr); }
         const V3 a_raw = v3(P.imu_acc[3 * i], P.imu_acc[3 * i + 1], P.imu_acc[3 * i + 2]) - bacc;
         const V3 g_raw = v3(P.imu_gyr[3 * i], P.imu_gyr[3 * i + 1], P.imu_gyr[3 * i + 2]) - bgyr;
+        va = a_raw; vg = g_raw;
         ra[0] = P.w_acc * (h.x - (Ma[0] * a_raw.x + Ma[1] * a_raw.y + Ma[2] * a_raw.z));
         ra[1] = P.w_acc * (h.y - (Ma[3] * a_raw.x + Ma[4] * a_raw.y + Ma[5] * a_raw.z));
         ra[2] = P.w_acc * (h.z - (Ma[6] * a_raw.x + Ma[7] * a_raw.y + Ma[8] * a_raw.z));
@@ -397,6 +401,12 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
                 Jt[(39 + 3 * j + 0) * LDJ + lane] = s * Ma[3 * k + 0]; Jt[(39 + 3 * j + 1) * LDJ + lane] = s * Ma[3 * k + 1]; Jt[(39 + 3 * j + 2) * LDJ + lane] = s * Ma[3 * k + 2];
               }
             }
+            if (INTR) {   // d(-M_a v)/d[misYZ, misZY, misZX, sX, sY, sZ], M_a = [[sX, -yz sY, zy sZ],[0, sY, -zx sZ],[0, 0, sZ]]
+              const double d[6] = {k == 0 ? ai[4] * va.y : 0.0, k == 0 ? -ai[5] * va.z : 0.0, k == 1 ? ai[5] * va.z : 0.0,
+                                   k == 0 ? -va.x : 0.0, k == 0 ? ai[0] * va.y : (k == 1 ? -va.y : 0.0), k == 0 ? -ai[1] * va.z : (k == 1 ? ai[2] * va.z : -va.z)};
+#pragma unroll
+              for (int q = 0; q < 6; ++q) Jt[(48 + q) * LDJ + lane] = P.w_acc * d[q];
+            }
             Jt[RESA * LDJ + lane] = ra[k];
           } else {
             for (int c = 0; c < NCOLA; ++c) Jt[c * LDJ + lane] = 0.0;
@@ -434,6 +444,14 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
                 const double sc = P.w_gyr * cbg[j];
                 Jt[(18 + 3 * j + 0) * LDJ + lane] = sc * Mg[3 * k + 0]; Jt[(18 + 3 * j + 1) * LDJ + lane] = sc * Mg[3 * k + 1]; Jt[(18 + 3 * j + 2) * LDJ + lane] = sc * Mg[3 * k + 2];
               }
+            }
+            if (INTR) {   // d(-M_g v)/d[misYZ, misZY, misZX, misXZ, misXY, misYX, sX, sY, sZ]
+              double d[9];
+              if (k == 0) { d[0] = gi[7] * vg.y; d[1] = -gi[8] * vg.z; d[2] = 0; d[3] = 0; d[4] = 0; d[5] = 0; d[6] = -vg.x; d[7] = gi[0] * vg.y; d[8] = -gi[1] * vg.z; }
+              else if (k == 1) { d[0] = 0; d[1] = 0; d[2] = gi[8] * vg.z; d[3] = -gi[6] * vg.x; d[4] = 0; d[5] = 0; d[6] = -gi[3] * vg.x; d[7] = -vg.y; d[8] = gi[2] * vg.z; }
+              else { d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 0; d[4] = gi[6] * vg.x; d[5] = -gi[7] * vg.y; d[6] = gi[4] * vg.x; d[7] = -gi[5] * vg.y; d[8] = -vg.z; }
+#pragma unroll
+              for (int q = 0; q < 9; ++q) Jt[(27 + q) * LDJ + lane] = P.w_gyr * d[q];
             }
             Jt[RESG * LDJ + lane] = rg[k];
             for (int c = NCOLG; c < 8 * NBG; ++c) Jt[c * LDJ + lane] = 0.0;
@@ -535,8 +553,8 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
   if (!attr_done) {
     int e = 0;
     e |= set_smem(vision_kernel<true>, sm_vis); e |= set_smem(vision_kernel<false>, sm_vis);
-    e |= set_smem(imu_kernel<true, false>, sm_imu_nb); e |= set_smem(imu_kernel<false, false>, sm_imu_nb);
-    e |= set_smem(imu_kernel<true, true>, sm_imu_b); e |= set_smem(imu_kernel<false, true>, sm_imu_b);
+    e |= set_smem(imu_kernel<true, 0>, sm_imu_nb); e |= set_smem(imu_kernel<false, 0>, sm_imu_nb);
+    e |= set_smem(imu_kernel<true, 1>, sm_imu_b); e |= set_smem(imu_kernel<false, 1>, sm_imu_b); e |= set_smem(imu_kernel<true, 2>, sm_imu_b);
     if (e) return 1;
     attr_done = true;
   }
@@ -548,12 +566,13 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
   }
   if (P.n_iwork > 0) {
     const int grid = grid_for(P.n_iwork, sm_count);
-    if (P.bias_active) {
-      if (with_jacobian) imu_kernel<true, true><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
-      else imu_kernel<false, true><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+    if (P.bias_active || P.intr_active) {
+      if (with_jacobian && P.intr_active) imu_kernel<true, 2><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+      else if (with_jacobian) imu_kernel<true, 1><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, 1><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
     } else {
-      if (with_jacobian) imu_kernel<true, false><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
-      else imu_kernel<false, false><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
+      if (with_jacobian) imu_kernel<true, 0><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, 0><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
     }
     count_launch();
   }

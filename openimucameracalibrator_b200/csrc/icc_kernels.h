@@ -49,8 +49,9 @@ struct DeviceProblem {
   int n_so3, n_r3, n_ba, n_bg;
   // active-set column maps (solver ordering); -1 = constant block
   const int* so3_col; const int* r3_col; const int* ba_col; const int* bg_col;
-  int col_tic, col_g, col_ld;
+  int col_tic, col_g, col_ld, col_ai, col_gi;
   int bias_active;           // any bias block active -> wide IMU tiles
+  int intr_active;           // IMU intrinsics free (SplineOptimFlags::IMU_INTRINSICS)
   // normal equations: [band nk x ldb][E nk x nb][C nb x nb (lower)][g nk+nb][cost][pad]
   int nk, nb, kd, ldb;
   double* ne;

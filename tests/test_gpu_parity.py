@@ -42,6 +42,26 @@ def test_eval_parity_every_camera_model_all_blocks(oracle_factory, gpu_factory, 
         _assert_eval_parity(o, g, flags)
 
 
+def test_eval_parity_imu_intrinsics_flag(oracle_factory, gpu_factory):
+    """SplineOptimFlags::IMU_INTRINSICS (SetFixedParams impl.h:166-178): misalignment + scale blocks of both triads, with
+    non-trivial intrinsics so that every derivative is exercised."""
+    ds = syn.make_dataset(syn.tiny_config(seed=13))
+    acc_i = (0.01, -0.02, 0.015, 1.02, 0.98, 1.01); gyr_i = (0.01, -0.005, 0.02, -0.015, 0.008, 0.012, 0.99, 1.03, 1.01)
+    def load(api):
+        W, H = ds["image_size"]
+        api.set_camera(ds["model"], ds["intrinsics"], W, H); api.set_board_points(ds["board_xyzw"])
+        api.set_frames(ds["frame_t"], ds["corner_offsets"], ds["point_ids"], ds["uv"], ds["q_wc"], ds["p_wc"]); api.set_imu(ds["imu_t"], ds["accel"], ds["gyro"])
+        api.batch_init_spline(ds["T_i_c_init"], ds["dt_so3_s"], ds["dt_r3_s"], ds["std_so3"], ds["std_r3"], ds["time_offset_imu_to_cam_s"], ds["init_line_delay_s"],
+                              acc_intrinsics=acc_i, gyr_intrinsics=gyr_i, acc_bias=ds["acc_bias"], gyr_bias=ds["gyr_bias"])
+    o = oracle_factory(); load(o)
+    g = gpu_factory(); load(g)
+    for flags in (capi.FLAG_IMU_INTRINSICS, F_ALL | capi.FLAG_IMU_INTRINSICS, F_STAGE1 | capi.FLAG_IMU_INTRINSICS):
+        assert o.num_tangent(flags) == g.num_tangent(flags)
+        _assert_eval_parity(o, g, flags)
+    so, sg = o.optimize(20, F_STAGE1 | capi.FLAG_IMU_INTRINSICS | capi.FLAG_IMU_BIASES), g.optimize(20, F_STAGE1 | capi.FLAG_IMU_INTRINSICS | capi.FLAG_IMU_BIASES)
+    assert sg.iterations == so.iterations and abs(sg.final_cost - so.final_cost) <= 1e-7 * so.final_cost
+
+
 def test_eval_parity_pinhole_radial_tangential(oracle_factory, gpu_factory):
     cfg = syn.tiny_config(cm.PINHOLE_RADIAL_TANGENTIAL, (440.0, 1.01, 0.2, 480.0, 270.0, -0.1, 0.02, -0.003, 1e-3, -2e-3), seed=3)
     o, g = _pair(oracle_factory, gpu_factory, syn.make_dataset(cfg), known_gravity=False)

@@ -61,7 +61,11 @@ enum {
   ICC_FLAG_CAM_LINE_DELAY = 1 << 5,
   ICC_FLAG_SPLINE = 1 << 6,
   ICC_FLAG_ACC_BIAS = 1 << 7,
-  ICC_FLAG_GYR_BIAS = 1 << 8
+  ICC_FLAG_GYR_BIAS = 1 << 8,
+  /* Extensions named by the north-star; the reference keeps both quantities fixed (SURVEY.md "Read this first" #3), so with
+   * these bits clear they are pass-through exactly like there. */
+  ICC_FLAG_CAM_INTRINSICS = 1 << 9,   /* camera intrinsics (Theia parameter vector of the active model) as a parameter block */
+  ICC_FLAG_TIME_OFFSET = 1 << 10      /* increment [s] of the IMU->camera time offset applied to every IMU sample time */
 };
 
 /* Arguments of ImuCameraCalibrator::BatchInitSpline (src/core/imu_camera_calibrator.cc:21-124). */
@@ -152,6 +156,9 @@ icc_status icc_optimize(icc_handle* h, int max_iterations, int flags, icc_summar
 icc_status icc_get_T_i_c(const icc_handle* h, double T_i_c[7]);
 icc_status icc_get_gravity(const icc_handle* h, double g[3]);
 icc_status icc_get_line_delay(const icc_handle* h, double* line_delay_s);
+/* extension outputs: current camera intrinsics (n = model's parameter count) and time_offset_imu_to_cam_s (input + estimated increment) */
+icc_status icc_get_camera_intrinsics(const icc_handle* h, double* intrinsics, int n);
+icc_status icc_get_time_offset(const icc_handle* h, double* time_offset_s);
 icc_status icc_get_num_knots(const icc_handle* h, int* n_so3, int* n_r3, int* n_acc_bias, int* n_gyr_bias);
 icc_status icc_get_knots(const icc_handle* h, double* so3_xyzw, double* r3_xyz, double* acc_bias_xyz, double* gyr_bias_xyz); /* any may be NULL */
 icc_status icc_set_knots(icc_handle* h, const double* so3_xyzw, const double* r3_xyz, const double* acc_bias_xyz, const double* gyr_bias_xyz);
@@ -171,7 +178,7 @@ icc_status icc_num_residuals(const icc_handle* h, int* n_vision, int* n_accel, i
 icc_status icc_num_tangent(const icc_handle* h, int flags, int* n);
 /* One evaluation at the current state.  Canonical tangent order: so3 knots (3 each), r3 knots (3 each), T_i_c (6: upsilon,
  * omega), gravity (3), line delay (1), acc-bias knots (3 each), gyr-bias knots (3 each), accelerometer intrinsics (6),
- * gyroscope intrinsics (9) — only blocks active under `flags`.
+ * gyroscope intrinsics (9), camera intrinsics (model count), time-offset increment (1) — only blocks active under `flags`.
  * residuals: [vision 2/corner in frame order | accel 3/sample | gyro 3/sample].  hessian_dense: n x n row-major J^T J
  * (small problems only).  Any output may be NULL. */
 icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residuals, double* gradient, double* hessian_dense);

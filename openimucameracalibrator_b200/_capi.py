@@ -16,6 +16,7 @@ c_int64_p = C.POINTER(C.c_int64)
 
 FLAG_POINTS, FLAG_T_I_C, FLAG_IMU_BIASES, FLAG_IMU_INTRINSICS = 1, 2, 4, 8
 FLAG_GRAVITY_DIR, FLAG_CAM_LINE_DELAY, FLAG_SPLINE, FLAG_ACC_BIAS, FLAG_GYR_BIAS = 16, 32, 64, 128, 256
+FLAG_CAM_INTRINSICS, FLAG_TIME_OFFSET = 512, 1024     # north-star extensions (the reference keeps both fixed)
 
 STATUS_NAMES = {0: "ICC_OK", 1: "ICC_ERR_INVALID_ARGUMENT", 2: "ICC_ERR_NO_DEVICE", 3: "ICC_ERR_CUDA", 4: "ICC_ERR_STATE",
                 5: "ICC_ERR_UNSUPPORTED", 6: "ICC_ERR_NUMERIC"}
@@ -181,6 +182,12 @@ class CApi:
 
     def get_line_delay(self):
         v = C.c_double(); self._call("get_line_delay", [c_double_p], C.byref(v)); return v.value
+
+    def get_camera_intrinsics(self, n=10):
+        k = np.zeros(n); self._call("get_camera_intrinsics", [c_double_p, C.c_int], _dp(k), n); return k
+
+    def get_time_offset(self):
+        v = C.c_double(); self._call("get_time_offset", [c_double_p], C.byref(v)); return v.value
 
     def set_line_delay(self, v):
         self._call("set_line_delay", [C.c_double], float(v))

@@ -204,7 +204,7 @@ icc_status configure(icc_handle* h, int flags) {
   const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
   const bool ld = (flags & ICC_FLAG_CAM_LINE_DELAY) && h->ip.init_line_delay_s != 0.0;
   const bool ab = flags & (ICC_FLAG_ACC_BIAS | ICC_FLAG_IMU_BIASES), gb = flags & (ICC_FLAG_GYR_BIAS | ICC_FLAG_IMU_BIASES);
-  const bool intr = flags & ICC_FLAG_IMU_INTRINSICS;
+  const bool intr = flags & ICC_FLAG_IMU_INTRINSICS, cam_intr = flags & ICC_FLAG_CAM_INTRINSICS, toff = flags & ICC_FLAG_TIME_OFFSET;
   // canonical offsets
   int n = 0;
   const int c_so3 = spline ? n : -1; if (spline) n += 3 * nso3;
@@ -216,6 +216,8 @@ icc_status configure(icc_handle* h, int flags) {
   const int c_bg = gb ? n : -1; if (gb) n += 3 * nbg;
   const int c_ai = intr ? n : -1; if (intr) n += 6;
   const int c_gi = intr ? n : -1; if (intr) n += 9;
+  const int c_ci = cam_intr ? n : -1; if (cam_intr) n += h->n_intr;
+  const int c_to = toff ? n : -1; if (toff) n += 1;
   h->n_tan = n;
   h->so3_col.assign(nso3, -1); h->r3_col.assign(nr3, -1); h->ba_col.assign(nba, -1); h->bg_col.assign(nbg, -1);
   int pos = 0;
@@ -235,6 +237,8 @@ icc_status configure(icc_handle* h, int flags) {
   if (gb) for (int k = 0; k < nbg; ++k) { h->bg_col[k] = pos; pos += 3; }
   const int col_ai = intr ? pos : -1; if (intr) pos += 6;
   const int col_gi = intr ? pos : -1; if (intr) pos += 9;
+  const int col_ci = cam_intr ? pos : -1; if (cam_intr) pos += h->n_intr;
+  const int col_to = toff ? pos : -1; if (toff) pos += 1;
   const int nb = pos - nk;
   h->perm.assign(n, -1);
   if (spline) { for (int k = 0; k < nso3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_so3 + 3 * k + d] = h->so3_col[k] + d; for (int k = 0; k < nr3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_r3 + 3 * k + d] = h->r3_col[k] + d; }
@@ -244,6 +248,8 @@ icc_status configure(icc_handle* h, int flags) {
   if (ab) for (int k = 0; k < nba; ++k) for (int d = 0; d < 3; ++d) h->perm[c_ba + 3 * k + d] = h->ba_col[k] + d;
   if (gb) for (int k = 0; k < nbg; ++k) for (int d = 0; d < 3; ++d) h->perm[c_bg + 3 * k + d] = h->bg_col[k] + d;
   if (intr) { for (int d = 0; d < 6; ++d) h->perm[c_ai + d] = col_ai + d; for (int d = 0; d < 9; ++d) h->perm[c_gi + d] = col_gi + d; }
+  if (cam_intr) for (int d = 0; d < h->n_intr; ++d) h->perm[c_ci + d] = col_ci + d;
+  if (toff) h->perm[c_to] = col_to;
   // half bandwidth: widest knot window touched by one residual block
   int kd = 0;
   if (spline) {
@@ -263,7 +269,8 @@ icc_status configure(icc_handle* h, int flags) {
   h->cur_flags = flags;
   DeviceProblem& P = h->P;
   P.nk = nk; P.nb = nb; P.kd = kd; P.ldb = kd + 1;
-  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.col_ai = col_ai; P.col_gi = col_gi; P.bias_active = (ab || gb) ? 1 : 0; P.intr_active = intr ? 1 : 0;
+  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.col_ai = col_ai; P.col_gi = col_gi; P.col_ci = col_ci; P.col_to = col_to;
+  P.bias_active = (ab || gb) ? 1 : 0; P.intr_active = (intr || toff) ? 1 : 0; P.cam_intr_active = cam_intr ? 1 : 0;
   P.ne_off_E = (int64_t)nk * P.ldb; P.ne_off_C = P.ne_off_E + (int64_t)nk * nb; P.ne_off_g = P.ne_off_C + (int64_t)nb * nb;
   P.ne_off_cost = P.ne_off_g + nk + nb; P.ne_size = (P.ne_off_cost + 1 + 3) / 4 * 4;
   if (h->device >= 0) {
@@ -475,6 +482,8 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   for (int i = 0; i < 6; ++i) h->glob[G_ACC_INTR + i] = ipp->acc_intrinsics[i];
   for (int i = 0; i < 9; ++i) h->glob[G_GYR_INTR + i] = ipp->gyr_intrinsics[i];
   h->glob[G_LD] = ipp->init_line_delay_s;
+  for (int i = 0; i < 10; ++i) h->glob[G_CAM_INTR + i] = i < h->n_intr ? h->intr[i] : 0.0;
+  h->glob[G_TOFF] = 0.0;
   // spline time range and knot counts (imu_camera_calibrator.cc:49-72, impl.h:37-51)
   std::vector<double> cam_ts(h->frame_t); std::sort(cam_ts.begin(), cam_ts.end());
   h->t0_s = cam_ts.front(); h->tend_s = cam_ts.back();
@@ -598,7 +607,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   // ---- device upload ----------------------------------------------------------------------------------------------
   DeviceProblem& P = h->P;
   memset(&P, 0, sizeof P);
-  P.model = h->model; P.dispatch_fov = ipp->dispatch_fov; for (int i = 0; i < 10; ++i) P.intr[i] = h->intr[i];
+  P.model = h->model; P.dispatch_fov = ipp->dispatch_fov; P.n_intr = h->n_intr;
   P.n_frames = (int)h->frames.size(); P.n_corners = (int)h->used_pid.size(); P.rolling = ipp->init_line_delay_s != 0.0 ? 1 : 0;
   P.n_imu = (int)h->imu_used_t.size(); P.n_cells = (int)h->cells.size();
   P.dt_so3_ns = h->dt_so3_ns; P.dt_r3_ns = h->dt_r3_ns; P.dt_ba_ns = h->dt_ba_ns; P.dt_bg_ns = h->dt_bg_ns;
@@ -671,6 +680,8 @@ icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summa
 icc_status icc_get_T_i_c(const icc_handle* hc, double T[7]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !T) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(T, h->glob + G_TIC, 7 * sizeof(double)); return ICC_OK; }
 icc_status icc_get_gravity(const icc_handle* hc, double g[3]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !g) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(g, h->glob + G_GRAV, 3 * sizeof(double)); return ICC_OK; }
 icc_status icc_get_line_delay(const icc_handle* hc, double* ld) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !ld) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; *ld = h->glob[G_LD]; return ICC_OK; }
+icc_status icc_get_camera_intrinsics(const icc_handle* hc, double* k, int n) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !k) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; for (int i = 0; i < n && i < h->n_intr; ++i) k[i] = h->initialised ? h->glob[G_CAM_INTR + i] : h->intr[i]; return ICC_OK; }
+icc_status icc_get_time_offset(const icc_handle* hc, double* t) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !t) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; *t = h->ip.time_offset_imu_to_cam_s + h->glob[G_TOFF]; return ICC_OK; }
 icc_status icc_get_num_knots(const icc_handle* h, int* a, int* b, int* c, int* d) {
   if (!h) return ICC_ERR_INVALID_ARGUMENT;
   if (a) *a = (int)h->so3.size() / 4; if (b) *b = (int)h->r3.size() / 3; if (c) *c = (int)h->ba.size() / 3; if (d) *d = (int)h->bg.size() / 3;

@@ -17,7 +17,9 @@ ICC_HD int camera_num_params(int model) {
 }
 
 // J is row-major 2x3: J[0..2] = d px / d(x,y,z), J[3..5] = d py / d(x,y,z).
+// Jk (only filled when requested) is row-major 2 x 10: d(u,v)/d intrinsics in Theia's parameter order, unused entries zero.
 struct Proj { double u, v; double J[6]; bool ok; };
+struct ProjK { double Jk[20]; };
 
 // final affine of the skewed models: u = f dx + s dy + cx, v = f ar dy + cy, given d(dx,dy)/dp
 ICC_HD void affine_skew(const double* k, double dx, double dy, const double* Dd /*2x3*/, Proj& o) {
@@ -26,12 +28,22 @@ ICC_HD void affine_skew(const double* k, double dx, double dy, const double* Dd 
   o.v = fy * dy + k[4];
   for (int j = 0; j < 3; ++j) { o.J[j] = f * Dd[j] + s * Dd[3 + j]; o.J[3 + j] = fy * Dd[3 + j]; }
 }
+// intrinsic Jacobian of the skewed models: [f, ar, skew, cx, cy] columns + distortion columns idx[q] with d(dx,dy)/dk_q = (ddx[q], ddy[q])
+ICC_HD void affine_skew_k(const double* k, double dx, double dy, int nd, const int* idx, const double* ddx, const double* ddy, ProjK& o) {
+  for (int j = 0; j < 20; ++j) o.Jk[j] = 0.0;
+  o.Jk[0] = dx; o.Jk[10] = k[1] * dy;          // f
+  o.Jk[11] = k[0] * dy;                        // aspect ratio
+  o.Jk[2] = dy;                                // skew
+  o.Jk[3] = 1.0; o.Jk[14] = 1.0;               // principal point
+  for (int q = 0; q < nd; ++q) { o.Jk[idx[q]] = k[0] * ddx[q] + k[2] * ddy[q]; o.Jk[10 + idx[q]] = k[0] * k[1] * ddy[q]; }
+}
 
 ICC_HD double unified_w(double alpha) { return alpha > 0.5 ? (1.0 - alpha) / alpha : alpha / (1.0 - alpha); }
 
-template <int MODEL>
-ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
+template <int MODEL, bool WITH_K = false>
+ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov, ProjK* pk = nullptr) {
   Proj o; o.ok = true;
+  if (WITH_K) for (int j = 0; j < 20; ++j) pk->Jk[j] = 0.0;
   if (MODEL == CAM_PINHOLE || MODEL == CAM_PINHOLE_RADTAN) {
     const double iz = 1.0 / p.z, xn = p.x * iz, yn = p.y * iz;
     const double r2 = xn * xn + yn * yn;
@@ -53,11 +65,18 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
     // d(xn,yn)/dp = [[iz,0,-xn iz],[0,iz,-yn iz]]
     double Dd[6] = {a00 * iz, a01 * iz, -(a00 * xn + a01 * yn) * iz, a10 * iz, a11 * iz, -(a10 * xn + a11 * yn) * iz};
     affine_skew(k, dx, dy, Dd, o);
+    if (WITH_K) {
+      if (MODEL == CAM_PINHOLE) { const int idx[2] = {5, 6}; const double ddx[2] = {xn * r2, xn * r2 * r2}, ddy[2] = {yn * r2, yn * r2 * r2}; affine_skew_k(k, dx, dy, 2, idx, ddx, ddy, *pk); }
+      else { const int idx[5] = {5, 6, 7, 8, 9};
+             const double ddx[5] = {xn * r2, xn * r2 * r2, xn * r2 * r2 * r2, 2.0 * xn * yn, r2 + 2.0 * xn * xn}, ddy[5] = {yn * r2, yn * r2 * r2, yn * r2 * r2 * r2, r2 + 2.0 * yn * yn, 2.0 * xn * yn};
+             affine_skew_k(k, dx, dy, 5, idx, ddx, ddy, *pk); }
+    }
   } else if (MODEL == CAM_FISHEYE) {
     const double r2 = p.x * p.x + p.y * p.y;
     if (r2 < 1e-8) {
       double Dd[6] = {1, 0, 0, 0, 1, 0};
       affine_skew(k, p.x, p.y, Dd, o);
+      if (WITH_K) affine_skew_k(k, p.x, p.y, 0, nullptr, nullptr, nullptr, *pk);
     } else {
       const double r = sqrt(r2), az = fabs(p.z), sg = p.z < 0.0 ? -1.0 : 1.0;
       const double th = atan2(r, az), th2 = th * th;
@@ -70,6 +89,9 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
       const double gx = common * p.x, gy = common * p.y, gz = -dthd * sg / rho2;
       double Dd[6] = {sg * (g + p.x * gx), sg * (p.x * gy), sg * (p.x * gz), sg * (p.y * gx), sg * (g + p.y * gy), sg * (p.y * gz)};
       affine_skew(k, sg * g * p.x, sg * g * p.y, Dd, o);
+      if (WITH_K) { const int idx[4] = {5, 6, 7, 8}; const double t3 = th * th2, ex = sg * p.x / r, ey = sg * p.y / r;   // d theta_d / d k_i = theta^(2i+1)
+                    const double ddx[4] = {t3 * ex, t3 * th2 * ex, t3 * th2 * th2 * ex, t3 * th2 * th2 * th2 * ex}, ddy[4] = {t3 * ey, t3 * th2 * ey, t3 * th2 * th2 * ey, t3 * th2 * th2 * th2 * ey};
+                    affine_skew_k(k, sg * g * p.x, sg * g * p.y, 4, idx, ddx, ddy, *pk); }
     }
   } else if (MODEL == CAM_FOV) {
     if (!dispatch_fov) { o.ok = false; o.u = o.v = 0; for (int j = 0; j < 6; ++j) o.J[j] = 0; return o; }
@@ -88,6 +110,15 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
     o.u = f * s * xn + k[2]; o.v = fy * s * yn + k[3];
     o.J[0] = f * a00 * iz; o.J[1] = f * a01 * iz; o.J[2] = -f * (a00 * xn + a01 * yn) * iz;
     o.J[3] = fy * a01 * iz; o.J[4] = fy * a11 * iz; o.J[5] = -fy * (a01 * xn + a11 * yn) * iz;
+    if (WITH_K) {   // [f, ar, cx, cy, omega]
+      double ds_om = 0.0;
+      if (!(om * om < 1e-10)) {
+        const double T = tan(0.5 * om), dT = 0.5 * (1.0 + T * T);
+        if (r2 < 1e-10) ds_om = 2.0 * dT / om - 2.0 * T / (om * om);
+        else { const double r = sqrt(r2), at = atan(2.0 * r * T); ds_om = (2.0 * r * dT / (1.0 + 4.0 * r2 * T * T)) / (om * r) - at / (om * om * r); }
+      }
+      pk->Jk[0] = s * xn; pk->Jk[10] = k[1] * s * yn; pk->Jk[11] = f * s * yn; pk->Jk[2] = 1.0; pk->Jk[13] = 1.0; pk->Jk[4] = f * ds_om * xn; pk->Jk[14] = fy * ds_om * yn;
+    }
   } else if (MODEL == CAM_DIVISION_UNDISTORTION) {
     const double iz = 1.0 / p.z, f = k[0], fy = k[0] * k[1], kd = k[4];
     const double xu = f * p.x * iz, yu = fy * p.y * iz;
@@ -105,6 +136,14 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
     const double xz = -xu * iz, yz = -yu * iz;
     o.J[0] = a00 * f * iz; o.J[1] = a01 * fy * iz; o.J[2] = a00 * xz + a01 * yz;
     o.J[3] = a01 * f * iz; o.J[4] = a11 * fy * iz; o.J[5] = a01 * xz + a11 * yz;
+    if (WITH_K) {   // [f, ar, cx, cy, k]: xu, yu scale with f, yu with ar; d(scale)/dk = (den/w - (1-w)) / (k den)
+      double dsk = 0.0;
+      if (!(fabs(den) < 1e-15 || inner < 0.0)) { const double w = sqrt(inner); dsk = (den / w - (1.0 - w)) / (kd * den); }
+      pk->Jk[0] = (a00 * xu + a01 * yu) / f; pk->Jk[10] = (a01 * xu + a11 * yu) / f;
+      pk->Jk[1] = a01 * yu / k[1]; pk->Jk[11] = a11 * yu / k[1];
+      pk->Jk[2] = 1.0; pk->Jk[13] = 1.0;
+      pk->Jk[4] = xu * dsk; pk->Jk[14] = yu * dsk;
+    }
   } else if (MODEL == CAM_DOUBLE_SPHERE) {
     const double xi = k[5], al = k[6];
     const double r2 = p.x * p.x + p.y * p.y;
@@ -121,6 +160,12 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
     const double dx = p.x * in, dy = p.y * in;
     double Dd[6] = {in - dx * nx * in, -dx * ny * in, -dx * nz * in, -dy * nx * in, in - dy * ny * in, -dy * nz * in};
     affine_skew(k, dx, dy, Dd, o);
+    if (WITH_K) {   // d norm / d xi = d1 (al kk / d2 + 1 - al),  d norm / d alpha = d2 - kk ;  d(dx)/d. = -dx / norm * d norm
+      const int idx[2] = {5, 6};
+      const double dn[2] = {d1 * c, d2 - kk};
+      const double ddx[2] = {-dx * in * dn[0], -dx * in * dn[1]}, ddy[2] = {-dy * in * dn[0], -dy * in * dn[1]};
+      affine_skew_k(k, dx, dy, 2, idx, ddx, ddy, *pk);
+    }
   } else {  // CAM_EXTENDED_UNIFIED
     const double al = k[5], be = k[6];
     const double r2 = p.x * p.x + p.y * p.y;
@@ -131,8 +176,28 @@ ICC_HD Proj project_model(const double* k, V3 p, bool dispatch_fov) {
     const double dx = p.x * in, dy = p.y * in;
     double Dd[6] = {in - dx * nx * in, -dx * ny * in, -dx * nz * in, -dy * nx * in, in - dy * ny * in, -dy * nz * in};
     affine_skew(k, dx, dy, Dd, o);
+    if (WITH_K) {   // d norm / d alpha = rho - z,  d norm / d beta = alpha r2 / (2 rho)
+      const int idx[2] = {5, 6};
+      const double dn[2] = {rho - p.z, al * r2 / (2.0 * rho)};
+      const double ddx[2] = {-dx * in * dn[0], -dx * in * dn[1]}, ddy[2] = {-dy * in * dn[0], -dy * in * dn[1]};
+      affine_skew_k(k, dx, dy, 2, idx, ddx, ddy, *pk);
+    }
   }
   return o;
+}
+
+// Same dispatch, additionally returning d(u,v)/d(intrinsics) (CAM_INTRINSICS extension).
+ICC_HD Proj project_with_k(int model, const double* k, V3 p, bool dispatch_fov, ProjK* pk) {
+  switch (model) {
+    case CAM_DIVISION_UNDISTORTION: return project_model<CAM_DIVISION_UNDISTORTION, true>(k, p, dispatch_fov, pk);
+    case CAM_DOUBLE_SPHERE: return project_model<CAM_DOUBLE_SPHERE, true>(k, p, dispatch_fov, pk);
+    case CAM_PINHOLE: return project_model<CAM_PINHOLE, true>(k, p, dispatch_fov, pk);
+    case CAM_FISHEYE: return project_model<CAM_FISHEYE, true>(k, p, dispatch_fov, pk);
+    case CAM_EXTENDED_UNIFIED: return project_model<CAM_EXTENDED_UNIFIED, true>(k, p, dispatch_fov, pk);
+    case CAM_PINHOLE_RADTAN: return project_model<CAM_PINHOLE_RADTAN, true>(k, p, dispatch_fov, pk);
+    case CAM_FOV: return project_model<CAM_FOV, true>(k, p, dispatch_fov, pk);
+    default: { Proj o; o.ok = false; o.u = o.v = 0; for (int j = 0; j < 6; ++j) o.J[j] = 0; for (int j = 0; j < 20; ++j) pk->Jk[j] = 0; return o; }
+  }
 }
 
 // Runtime dispatch in the reference's order (residuals.h:366-389).

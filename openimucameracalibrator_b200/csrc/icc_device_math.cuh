@@ -172,6 +172,26 @@ ICC_HD void coeffs6(double u, double c[6], double dc[6], double ddc[6]) {
     ddc[5] = k * (20.0 * u3);
   }
 }
+// second u-derivative of the cumulative coefficients and third of the non-cumulative ones (time-offset extension:
+// angular acceleration and jerk of the spline)
+ICC_HD void cum_coeffs6_dd(double u, double ddlam[5]) {
+  const double k = 1.0 / 120.0, u2 = u * u, u3 = u2 * u;
+  ddlam[0] = k * (-20.0 + 60.0 * u - 60.0 * u2 + 20.0 * u3);
+  ddlam[1] = k * (-60.0 - 60.0 * u + 180.0 * u2 - 80.0 * u3);
+  ddlam[2] = k * (60.0 - 60.0 * u - 180.0 * u2 + 120.0 * u3);
+  ddlam[3] = k * (20.0 + 60.0 * u + 60.0 * u2 - 80.0 * u3);
+  ddlam[4] = k * (20.0 * u3);
+}
+ICC_HD void coeffs6_ddd(double u, double dddc[6]) {
+  const double k = 1.0 / 120.0, u2 = u * u;
+  dddc[0] = k * (-60.0 + 120.0 * u - 60.0 * u2);
+  dddc[1] = k * (120.0 - 480.0 * u + 300.0 * u2);
+  dddc[2] = k * (720.0 * u - 600.0 * u2);
+  dddc[3] = k * (-120.0 - 480.0 * u + 600.0 * u2);
+  dddc[4] = k * (60.0 + 120.0 * u - 300.0 * u2);
+  dddc[5] = k * (60.0 * u2);
+}
+ICC_HD void coeffs3_d(double u, double dc[3]) { dc[0] = u - 1.0; dc[1] = 1.0 - 2.0 * u; dc[2] = u; }
 // bias spline, N = 3, non-cumulative:  rows x2 = [1 -2 1; 1 2 -2; 0 0 1]
 ICC_HD void coeffs3(double u, double c[3]) {
   const double u2 = u * u;

@@ -164,20 +164,25 @@ ICC_D double so3_knot_row(const WarpCtx* wc, const Chain& ch, V3 m_theta, double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Vision: rolling-shutter reprojection residuals.  Tile columns: [so3 0..17 | r3 18..35 | T_i_c 36..41 | ld 42 | r 43].
+// Vision: rolling-shutter reprojection residuals.  Tile columns: [so3 0..17 | r3 18..35 | T_i_c 36..41 | ld 42 | r 43];
+// JAC == 2 (CAM_INTRINSICS extension): [... | ld 42 | intrinsics 43..43+K-1 | r 43+K], K = parameter count of the model.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool JAC>
+template <int JAC>
 __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, DeviceState S, double* cost_out, double* res_out, double* reproj_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpCtx* wc = reinterpret_cast<WarpCtx*>(smem_raw) + warp;
-  double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (48 * LDJ);
-  constexpr int NB = 6, NCOL = 44, RES = 43;
+  constexpr int NB = JAC == 2 ? 7 : 6, TILE_COLS = 8 * NB;
+  double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (TILE_COLS * LDJ);
+  const int RES = JAC == 2 ? 43 + P.n_intr : 43, NCOL = RES + 1;
+  double intr[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) intr[i] = S.glob[G_CAM_INTR + i];
 
   const Q4 q_ic = q4(S.glob[G_TIC + 0], S.glob[G_TIC + 1], S.glob[G_TIC + 2], S.glob[G_TIC + 3]);
   const V3 t_ic = v3(S.glob[G_TIC + 4], S.glob[G_TIC + 5], S.glob[G_TIC + 6]);
   const double ld = S.glob[G_LD];
-  if (JAC) { for (int i = lane; i < 48 * LDJ; i += 32) Jt[i] = 0.0; }
+  if (JAC) { for (int i = lane; i < TILE_COLS * LDJ; i += 32) Jt[i] = 0.0; }
 
   double cost_acc = 0.0, rp_sum = 0.0, rp_cnt = 0.0;
   for (int item = blockIdx.x * WARPS + warp; item < P.n_vwork; item += gridDim.x * WARPS) {
@@ -186,14 +191,15 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
     const double u_so3 = P.f_u_so3[wk.frame], u_r3 = P.f_u_r3[wk.frame];
     __syncwarp();
     if (lane < 6) { const double4 k = S.r3[s_r3 + lane]; wc->p[lane] = v3(k.x, k.y, k.z); }
-    stage_so3_window<JAC>(wc, S, s_so3, lane);
+    stage_so3_window<(JAC != 0)>(wc, S, s_so3, lane);
     if (JAC) {
-      for (int c = lane; c < 48; c += 32) {
+      for (int c = lane; c < TILE_COLS; c += 32) {
         int g = -1;
         if (c < 18) { const int b = P.so3_col[s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
         else if (c < 36) { const int b = P.r3_col[s_r3 + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
         else if (c < 42) g = P.col_tic < 0 ? -1 : P.col_tic + (c - 36);
         else if (c == 42) g = P.col_ld;
+        else if (JAC == 2 && c < RES) g = P.col_ci < 0 ? -1 : P.col_ci + (c - 43);
         wc->gidx[c] = g;
       }
     }
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
       const int nact = min(32, wk.c_end - base);
       double r0 = 0.0, r1 = 0.0, y = 0.0;
       bool ok = false;
-      Chain ch; Proj pr; V3 qi = v3(0, 0, 0), pc = v3(0, 0, 0), tdot = v3(0, 0, 0);
+      Chain ch; Proj pr; ProjK pk; V3 qi = v3(0, 0, 0), pc = v3(0, 0, 0), tdot = v3(0, 0, 0);
       double cc[6];
       if (act) {
         const double2 ob = P.uv[c];
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
         const double iw = 1.0 / X.w;
         qi = qrot_inv(ch.q, v3(X.x * iw, X.y * iw, X.z * iw) - t);   // point in the IMU frame
         pc = qrot_inv(q_ic, qi - t_ic);                                // point in the camera frame
-        pr = project(P.model, P.intr, pc, P.dispatch_fov != 0);
+        if (JAC == 2) pr = project_with_k(P.model, intr, pc, P.dispatch_fov != 0, &pk); else pr = project(P.model, intr, pc, P.dispatch_fov != 0);
         ok = pr.ok;
         if (ok) { r0 = pr.u - ob.x; r1 = pr.v - ob.y; } else { r0 = 1e10; r1 = 1e10; }   // residuals.h:391-398, cov = I
         if (res_out) { res_out[2 * c] = r0; res_out[2 * c + 1] = r1; }
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
             Jt[36 * LDJ + lane] = -Dp.x; Jt[37 * LDJ + lane] = -Dp.y; Jt[38 * LDJ + lane] = -Dp.z;
             Jt[39 * LDJ + lane] = om.x; Jt[40 * LDJ + lane] = om.y; Jt[41 * LDJ + lane] = om.z;
             Jt[42 * LDJ + lane] = y * (du - dot(m_t, tdot));
+            if (JAC == 2) { for (int q = 0; q < P.n_intr; ++q) Jt[(43 + q) * LDJ + lane] = pk.Jk[10 * row + q]; }
             Jt[RES * LDJ + lane] = row == 0 ? r0 : r1;
           } else {
             for (int k = 0; k < RES; ++k) Jt[k * LDJ + lane] = 0.0;
@@ -277,7 +284,8 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
 // IMU: accelerometer + gyroscope residuals of one knot-interval cell per warp.
 //   accel tile columns: [so3 0..17 | r3 18..35 | g 36..38 | (ba 39..47) | (acc intr 48..53) | r]   NB = 5 / 7 / 7
 //   gyro  tile columns: [so3 0..17 | (bg 18..26) | (gyr intr 27..35) | r]                          NB = 3 / 4 / 5
-//   MODE 0 = biases fixed, 1 = bias knots free, 2 = bias knots + IMU intrinsics free (SplineOptimFlags::IMU_INTRINSICS)
+//   MODE 0 = biases fixed, 1 = bias knots free, 2 = widest: + IMU intrinsics (SplineOptimFlags::IMU_INTRINSICS) and the
+//   time-offset increment (extension) as accel column 54 / gyro column 36
 // ---------------------------------------------------------------------------------------------------------------
 template <bool JAC, int MODE>
 __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, DeviceState S, double* cost_out, double* res_out) {
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool BIAS = MODE >= 1, INTR = MODE == 2;
   constexpr int NBA = BIAS ? 7 : 5, NBG = MODE == 0 ? 3 : MODE == 1 ? 4 : 5;
-  constexpr int RESA = MODE == 0 ? 39 : MODE == 1 ? 48 : 54, NCOLA = RESA + 1, RESG = MODE == 0 ? 18 : MODE == 1 ? 27 : 36, NCOLG = RESG + 1;
+  constexpr int RESA = MODE == 0 ? 39 : MODE == 1 ? 48 : 55, NCOLA = RESA + 1, RESG = MODE == 0 ? 18 : MODE == 1 ? 27 : 37, NCOLG = RESG + 1;
   constexpr int TILE_COLS = 8 * NBA;
   WarpCtx* wc = reinterpret_cast<WarpCtx*>(smem_raw) + warp;
   double* Jt = reinterpret_cast<double*>(smem_raw + WARPS * sizeof(WarpCtx)) + warp * (TILE_COLS * LDJ);
@@ -298,6 +306,8 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
   const double Mg[9] = {gi[6], -gi[0] * gi[7], gi[1] * gi[8], gi[3] * gi[6], gi[7], -gi[2] * gi[8], -gi[4] * gi[6], gi[5] * gi[7], gi[8]};
   const V3 grav = v3(S.glob[G_GRAV], S.glob[G_GRAV + 1], S.glob[G_GRAV + 2]);
   const double idt2 = P.inv_r3_dt * P.inv_r3_dt;
+  const double dto = S.glob[G_TOFF];   // time-offset increment [s] (0 unless the extension has been optimised)
+  const double ba_rate = 1e9 / double(P.dt_ba_ns), bg_rate = 1e9 / double(P.dt_bg_ns);
 
   double cost_acc = 0.0;
   for (int item = blockIdx.x * WARPS + warp; item < P.n_iwork; item += gridDim.x * WARPS) {
@@ -314,6 +324,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
         else if (c < 39) g = P.col_g < 0 ? -1 : P.col_g + (c - 36);
         else if (BIAS && c < 48) { const int b = P.ba_col[cell.s_ba + (c - 39) / 3]; g = b < 0 ? -1 : b + (c - 39) % 3; }
         else if (INTR && c < 54) g = P.col_ai < 0 ? -1 : P.col_ai + (c - 48);
+        else if (INTR && c == 54) g = P.col_to;
         wc->gidx[c] = g;
       }
       for (int c = lane; c < 40; c += 32) {
@@ -321,6 +332,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
         if (c < 18) { const int b = P.so3_col[cell.s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
         else if (BIAS && c < 27) { const int b = P.bg_col[cell.s_bg + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
         else if (INTR && c < 36) g = P.col_gi < 0 ? -1 : P.col_gi + (c - 27);
+        else if (INTR && c == 36) g = P.col_to;
         wc->gidx2[c] = g;
       }
     }
@@ -341,13 +353,14 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
       double ra[3] = {0, 0, 0}, rg[3] = {0, 0, 0};
       double ddc[6], cba[3], cbg[3];
       V3 h = v3(0, 0, 0), va = v3(0, 0, 0), vg = v3(0, 0, 0);   // va / vg: raw readings minus bias
+      V3 dacc = v3(0, 0, 0), dgyr = v3(0, 0, 0);                // d residual / d time offset (unweighted), MODE 2 only
       if (act) {
         const int64_t st = P.imu_t_ns[i];
         // CalcTimes (impl.h:763-788): u = (st % dt) / dt with the segment index known from the cell
-        const double u_so3 = double(st - (int64_t)cell.s_so3 * P.dt_so3_ns) / double(P.dt_so3_ns);
-        const double u_r3 = double(st - (int64_t)cell.s_r3 * P.dt_r3_ns) / double(P.dt_r3_ns);
-        const double u_ba = double(st - (int64_t)cell.s_ba * P.dt_ba_ns) / double(P.dt_ba_ns);
-        const double u_bg = double(st - (int64_t)cell.s_bg * P.dt_bg_ns) / double(P.dt_bg_ns);
+        const double u_so3 = double(st - (int64_t)cell.s_so3 * P.dt_so3_ns) / double(P.dt_so3_ns) + dto * P.inv_so3_dt;
+        const double u_r3 = double(st - (int64_t)cell.s_r3 * P.dt_r3_ns) / double(P.dt_r3_ns) + dto * P.inv_r3_dt;
+        const double u_ba = double(st - (int64_t)cell.s_ba * P.dt_ba_ns) / double(P.dt_ba_ns) + dto * ba_rate;
+        const double u_bg = double(st - (int64_t)cell.s_bg * P.dt_bg_ns) / double(P.dt_bg_ns) + dto * bg_rate;
         build_chain(wc, u_so3, ch);
         double cdum[6];
         coeffs6(u_r3, cdum, nullptr, ddc);
@@ -373,6 +386,28 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
         rg[0] = P.w_gyr * (om.x - (Mg[0] * g_raw.x + Mg[1] * g_raw.y + Mg[2] * g_raw.z));
         rg[1] = P.w_gyr * (om.y - (Mg[3] * g_raw.x + Mg[4] * g_raw.y + Mg[5] * g_raw.z));
         rg[2] = P.w_gyr * (om.z - (Mg[6] * g_raw.x + Mg[7] * g_raw.y + Mg[8] * g_raw.z));
+        if (JAC && INTR) {
+          // d/d(time offset): accel  d(R^T v)/dt = h x omega + R^T jerk (+ M_a db_a/dt);  gyro  d omega/dt = body angular
+          // acceleration, recursion of CeresSplineHelper::evaluate_lie (ceres_spline_helper.h:166-170)  (+ M_g db_g/dt)
+          double dddc[6], ddlam[5], dcba[3], dcbg[3];
+          coeffs6_ddd(u_r3, dddc); cum_coeffs6_dd(u_so3, ddlam); coeffs3_d(u_ba, dcba); coeffs3_d(u_bg, dcbg);
+          V3 jerk = v3(0, 0, 0);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) jerk = fma3(dddc[j] * idt2 * P.inv_r3_dt, wc->p[j], jerk);
+          V3 dba = v3(0, 0, 0), dbg = v3(0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { dba = fma3(dcba[k] * ba_rate, wc->ba[k], dba); dbg = fma3(dcbg[k] * bg_rate, wc->bg[k], dbg); }
+          V3 rv = v3(0, 0, 0), racc = v3(0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const V3 cur = (ch.dlam[k] * P.inv_so3_dt) * wc->d[k];
+            rv = qrot_inv(ch.A[k], rv) + cur;
+            racc = qrot_inv(ch.A[k], racc) + (ddlam[k] * P.inv_so3_dt * P.inv_so3_dt) * wc->d[k] + cross(rv, cur);
+          }
+          const V3 t1 = cross(h, om) + qrot_inv(ch.q, jerk);
+          dacc = v3(t1.x + Ma[0] * dba.x + Ma[1] * dba.y + Ma[2] * dba.z, t1.y + Ma[3] * dba.x + Ma[4] * dba.y + Ma[5] * dba.z, t1.z + Ma[6] * dba.x + Ma[7] * dba.y + Ma[8] * dba.z);
+          dgyr = v3(racc.x + Mg[0] * dbg.x + Mg[1] * dbg.y + Mg[2] * dbg.z, racc.y + Mg[3] * dbg.x + Mg[4] * dbg.y + Mg[5] * dbg.z, racc.z + Mg[6] * dbg.x + Mg[7] * dbg.y + Mg[8] * dbg.z);
+        }
         if (res_out) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) { res_out[P.n_res_vis + 3 * i + k] = ra[k]; res_out[P.n_res_vis + P.n_res_acc + 3 * i + k] = rg[k]; }
@@ -406,6 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
                                    k == 0 ? -va.x : 0.0, k == 0 ? ai[0] * va.y : (k == 1 ? -va.y : 0.0), k == 0 ? -ai[1] * va.z : (k == 1 ? ai[2] * va.z : -va.z)};
 #pragma unroll
               for (int q = 0; q < 6; ++q) Jt[(48 + q) * LDJ + lane] = P.w_acc * d[q];
+              Jt[54 * LDJ + lane] = P.w_acc * (k == 0 ? dacc.x : k == 1 ? dacc.y : dacc.z);
             }
             Jt[RESA * LDJ + lane] = ra[k];
           } else {
@@ -452,6 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
               else { d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 0; d[4] = gi[6] * vg.x; d[5] = -gi[7] * vg.y; d[6] = gi[4] * vg.x; d[7] = -gi[5] * vg.y; d[8] = -vg.z; }
 #pragma unroll
               for (int q = 0; q < 9; ++q) Jt[(27 + q) * LDJ + lane] = P.w_gyr * d[q];
+              Jt[36 * LDJ + lane] = P.w_gyr * (k == 0 ? dgyr.x : k == 1 ? dgyr.y : dgyr.z);
             }
             Jt[RESG * LDJ + lane] = rg[k];
             for (int c = NCOLG; c < 8 * NBG; ++c) Jt[c * LDJ + lane] = 0.0;
@@ -547,12 +584,13 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
   const size_t sm_vis = WARPS * sizeof(WarpCtx) + WARPS * 48 * LDJ * sizeof(double);
+  const size_t sm_vis_k = WARPS * sizeof(WarpCtx) + WARPS * 56 * LDJ * sizeof(double);
   const size_t sm_imu_nb = WARPS * sizeof(WarpCtx) + WARPS * 40 * LDJ * sizeof(double);
   const size_t sm_imu_b = WARPS * sizeof(WarpCtx) + WARPS * 56 * LDJ * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     int e = 0;
-    e |= set_smem(vision_kernel<true>, sm_vis); e |= set_smem(vision_kernel<false>, sm_vis);
+    e |= set_smem(vision_kernel<1>, sm_vis); e |= set_smem(vision_kernel<0>, sm_vis); e |= set_smem(vision_kernel<2>, sm_vis_k);
     e |= set_smem(imu_kernel<true, 0>, sm_imu_nb); e |= set_smem(imu_kernel<false, 0>, sm_imu_nb);
     e |= set_smem(imu_kernel<true, 1>, sm_imu_b); e |= set_smem(imu_kernel<false, 1>, sm_imu_b); e |= set_smem(imu_kernel<true, 2>, sm_imu_b);
     if (e) return 1;
@@ -560,8 +598,9 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
   }
   if (P.n_vwork > 0 && P.rolling) {
     const int grid = grid_for(P.n_vwork, sm_count);
-    if (with_jacobian) vision_kernel<true><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
-    else vision_kernel<false><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    if (with_jacobian && P.cam_intr_active) vision_kernel<2><<<grid, WARPS * 32, sm_vis_k, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    else if (with_jacobian) vision_kernel<1><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    else vision_kernel<0><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
     count_launch();
   }
   if (P.n_iwork > 0) {

@@ -8,8 +8,9 @@ namespace icc {
 constexpr int SPLINE_N = 6;   // core/imu_camera_calibrator.h:27
 constexpr int BIAS_N = 3;     // basalt_spline/ceres_calib_split_residuals.h:21
 
-// Offsets inside the 26-double "globals" block of a state.
-enum { G_TIC = 0, G_GRAV = 7, G_LD = 10, G_ACC_INTR = 11, G_GYR_INTR = 17, G_COUNT = 26 };
+// Offsets inside the "globals" block of a state: T_i_c (7), gravity (3), line delay, accelerometer / gyroscope intrinsics (6 / 9),
+// camera intrinsics (<= 10, Theia order) and the time-offset increment [s] (both constant unless the extension flags free them).
+enum { G_TIC = 0, G_GRAV = 7, G_LD = 10, G_ACC_INTR = 11, G_GYR_INTR = 17, G_CAM_INTR = 26, G_TOFF = 36, G_COUNT = 37 };
 
 // One LM state in HBM.  Knots are padded to 32 B (x,y,z,w / x,y,z,0) for 16-byte vector loads.
 struct DeviceState {
@@ -25,8 +26,7 @@ struct ImuCell { int s_so3, s_r3, s_ba, s_bg; int i_begin, i_end; };
 
 struct DeviceProblem {
   // camera
-  int model, dispatch_fov;
-  double intr[10];
+  int model, dispatch_fov, n_intr;
   const double4* board;
   // vision: frames in CSR form
   int n_frames, n_corners, rolling;
@@ -49,9 +49,10 @@ struct DeviceProblem {
   int n_so3, n_r3, n_ba, n_bg;
   // active-set column maps (solver ordering); -1 = constant block
   const int* so3_col; const int* r3_col; const int* ba_col; const int* bg_col;
-  int col_tic, col_g, col_ld, col_ai, col_gi;
+  int col_tic, col_g, col_ld, col_ai, col_gi, col_ci, col_to;
   int bias_active;           // any bias block active -> wide IMU tiles
-  int intr_active;           // IMU intrinsics free (SplineOptimFlags::IMU_INTRINSICS)
+  int intr_active;           // IMU intrinsics and/or time offset free -> widest IMU tiles
+  int cam_intr_active;       // camera intrinsics free (extension) -> widest vision tiles
   // normal equations: [band nk x ldb][E nk x nb][C nb x nb (lower)][g nk+nb][cost][pad]
   int nk, nb, kd, ldb;
   double* ne;

@@ -605,6 +605,8 @@ __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand
       if (P.col_g >= 0) for (int k = 0; k < 3; ++k) { const double d = delta[P.col_g + k]; step += d * d; xsq += gl[G_GRAV + k] * gl[G_GRAV + k]; gl[G_GRAV + k] += d; }
       if (P.col_ld >= 0) { const double d = delta[P.col_ld]; step += d * d; xsq += gl[G_LD] * gl[G_LD]; gl[G_LD] += d; }
       if (P.col_ai >= 0) for (int k = 0; k < 6; ++k) { const double d = delta[P.col_ai + k]; step += d * d; xsq += gl[G_ACC_INTR + k] * gl[G_ACC_INTR + k]; gl[G_ACC_INTR + k] += d; }
+      if (P.col_ci >= 0) for (int k = 0; k < P.n_intr; ++k) { const double d = delta[P.col_ci + k]; step += d * d; xsq += gl[G_CAM_INTR + k] * gl[G_CAM_INTR + k]; gl[G_CAM_INTR + k] += d; }
+      if (P.col_to >= 0) { const double d = delta[P.col_to]; step += d * d; xsq += gl[G_TOFF] * gl[G_TOFF]; gl[G_TOFF] += d; }
       if (P.col_gi >= 0) for (int k = 0; k < 9; ++k) { const double d = delta[P.col_gi + k]; step += d * d; xsq += gl[G_GYR_INTR + k] * gl[G_GYR_INTR + k]; gl[G_GYR_INTR + k] += d; }
       for (int k = 0; k < G_COUNT; ++k) cand.glob[k] = gl[k];
     }

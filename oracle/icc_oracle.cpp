@@ -75,6 +75,7 @@ struct Oracle {
   double t0_s = 0, tend_s = 0;
   std::vector<double> so3, r3, ba, bg;   // knots
   double T_ic[7], grav[3], line_delay = 0, acc_intr[6], gyr_intr[9];
+  double toff_delta = 0;            // extension: increment of the IMU->camera time offset [s]
   double max_ba = 1.0, max_bg = 0.1;
   std::vector<Frame> frames;
   std::vector<ImuUsed> imu_used;
@@ -84,7 +85,7 @@ struct Oracle {
   // active set / ordering (rebuilt per flags)
   int cur_flags = -1;
   int n_tan = 0;
-  int off_so3 = -1, off_r3 = -1, off_tic = -1, off_g = -1, off_ld = -1, off_ba = -1, off_bg = -1;  // canonical offsets
+  int off_so3 = -1, off_r3 = -1, off_tic = -1, off_g = -1, off_ld = -1, off_ba = -1, off_bg = -1, off_ai = -1, off_gi = -1, off_ci = -1, off_to = -1;  // canonical offsets
   // solver ordering: canonical tangent index -> solver index
   std::vector<int> perm;      // canonical -> solver
   int n_knot_dims = 0, n_border = 0, kd = 0;
@@ -133,7 +134,7 @@ void rs_reprojection(const Oracle& o, const Block& b, const T* const* P, T* res)
   SE3T<T> T_i_c{{P[N2][0], P[N2][1], P[N2][2], P[N2][3]}, {P[N2][4], P[N2][5], P[N2][6]}};
   const T line_delay = P[N2 + 1][0];
   T intr[10];
-  for (int i = 0; i < o.n_intr; ++i) intr[i] = T(o.intr[i]);
+  for (int i = 0; i < o.n_intr; ++i) intr[i] = P[N2 + 2][i];   // extension: intrinsics are a (normally constant) parameter block
   const Frame& f = o.frames[b.frame];
   for (int c = f.c0; c < f.c1; ++c) {
     const int i = c - f.c0;
@@ -147,7 +148,7 @@ void rs_reprojection(const Oracle& o, const Block& b, const T* const* P, T* res)
     SE3T<T> T_w_c = se3_mul(SE3T<T>{R_w_i, t_w_i}, T_i_c);
     SE3T<T> T_c_w = se3_inv(T_w_c);
     M3<T> R = so3_matrix(T_c_w.q);
-    const T* X = P[N2 + 2 + i];
+    const T* X = P[N2 + 3 + i];
     // (T_c_w.matrix() * X_h).hnormalized()
     T h[3];
     h[0] = R.m[0][0] * X[0] + R.m[0][1] * X[1] + R.m[0][2] * X[2] + T_c_w.t.x * X[3];
@@ -164,10 +165,11 @@ void rs_reprojection(const Oracle& o, const Block& b, const T* const* P, T* res)
 template <class T>
 void accel_residual(const Oracle& o, const Block& b, const T* const* P, T* res) {   // residuals.h:52-93
   const ImuUsed& m = o.imu_used[b.frame];
+  const T dto = P[2 * SPLINE_N + BIAS_N + 2][0];   // extension: time-offset increment [s]; du = dto * 1e9 / dt_ns
   Q4<T> R_w_i;
-  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3), T(o.inv_so3_dt), &R_w_i, nullptr);
-  V3<T> accel_w = evaluate_r3<SPLINE_N, 2, T>(P + SPLINE_N, T(b.u_r3), T(o.inv_r3_dt));
-  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + 2 * SPLINE_N, T(b.u_bias), T(o.inv_ba_dt));
+  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3) + dto * o.inv_so3_dt, T(o.inv_so3_dt), &R_w_i, nullptr);
+  V3<T> accel_w = evaluate_r3<SPLINE_N, 2, T>(P + SPLINE_N, T(b.u_r3) + dto * o.inv_r3_dt, T(o.inv_r3_dt));
+  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + 2 * SPLINE_N, T(b.u_bias) + dto * (S_TO_NS / double(o.dt_ba_ns)), T(o.inv_ba_dt));
   const T* g = P[2 * SPLINE_N + BIAS_N];
   const T* ai = P[2 * SPLINE_N + BIAS_N + 1];
   V3<T> raw{T(m.acc[0]), T(m.acc[1]), T(m.acc[2])};
@@ -182,8 +184,9 @@ template <class T>
 void gyro_residual(const Oracle& o, const Block& b, const T* const* P, T* res) {   // residuals.h:133-169
   const ImuUsed& m = o.imu_used[b.frame];
   V3<T> rot_vel;
-  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3), T(o.inv_so3_dt), nullptr, &rot_vel);
-  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + SPLINE_N, T(b.u_bias), T(o.inv_bg_dt));
+  const T dto = P[SPLINE_N + BIAS_N + 1][0];
+  evaluate_lie_so3<SPLINE_N, T>(P, T(b.u_so3) + dto * o.inv_so3_dt, T(o.inv_so3_dt), nullptr, &rot_vel);
+  V3<T> bias = evaluate_r3<BIAS_N, 0, T>(P + SPLINE_N, T(b.u_bias) + dto * (S_TO_NS / double(o.dt_bg_ns)), T(o.inv_bg_dt));
   const T* gi = P[SPLINE_N + BIAS_N];
   V3<T> raw{T(m.gyr[0]), T(m.gyr[1]), T(m.gyr[2])};
   V3<T> cal = triad_unbias_normalize<T>(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gi[7], gi[8], bias, raw);
@@ -298,8 +301,12 @@ bool configure(Oracle& o, int flags) {
   o.off_ld = ld ? n : -1; if (ld) n += 1;
   o.off_ba = abias ? n : -1; if (abias) n += 3 * nba;
   o.off_bg = gbias ? n : -1; if (gbias) n += 3 * nbg;
+  const bool cam_intr = flags & ICC_FLAG_CAM_INTRINSICS, toff = flags & ICC_FLAG_TIME_OFFSET;
   const int off_ai = imu_intr ? n : -1; if (imu_intr) n += 6;
   const int off_gi = imu_intr ? n : -1; if (imu_intr) n += 9;
+  const int off_ci = cam_intr ? n : -1; if (cam_intr) n += o.n_intr;
+  const int off_to = toff ? n : -1; if (toff) n += 1;
+  o.off_ai = off_ai; o.off_gi = off_gi; o.off_ci = off_ci; o.off_to = off_to;
   o.n_tan = n; o.cur_flags = flags;
   // wire tangent offsets into the blocks
   for (auto& b : o.blocks) {
@@ -311,6 +318,7 @@ bool configure(Oracle& o, int flags) {
       so3k(f.s_so3); r3k(f.s_r3);
       b.params[k++].tan_off = o.off_tic;
       b.params[k++].tan_off = o.off_ld;
+      b.params[k++].tan_off = off_ci;
       for (; k < int(b.params.size()); ++k) b.params[k].tan_off = -1;
     } else if (b.type == BLK_ACCEL) {
       const int64_t s_so3 = (b.params[0].ptr - o.so3.data()) / 4, s_r3 = (b.params[SPLINE_N].ptr - o.r3.data()) / 3;
@@ -319,11 +327,13 @@ bool configure(Oracle& o, int flags) {
       for (int i = 0; i < BIAS_N; ++i) b.params[k++].tan_off = abias ? o.off_ba + 3 * int(s_b + i) : -1;
       b.params[k++].tan_off = o.off_g;
       b.params[k++].tan_off = off_ai;
+      b.params[k++].tan_off = off_to;
     } else {
       const int64_t s_so3 = (b.params[0].ptr - o.so3.data()) / 4, s_b = (b.params[SPLINE_N].ptr - o.bg.data()) / 3;
       so3k(s_so3);
       for (int i = 0; i < BIAS_N; ++i) b.params[k++].tan_off = gbias ? o.off_bg + 3 * int(s_b + i) : -1;
       b.params[k++].tan_off = off_gi;
+      b.params[k++].tan_off = off_to;
     }
   }
   // solver ordering: spline knots sorted by knot time (so3 before r3 on ties) form the banded part, rest = border
@@ -490,13 +500,14 @@ bool arrowhead_solve(Normal A, const std::vector<double>& D2, const std::vector<
 // -------------------------------------------------------------------------------------------------------------
 // State vector plumbing: Plus(), norms, snapshots.
 // -------------------------------------------------------------------------------------------------------------
-struct State { std::vector<double> so3, r3, ba, bg; double T_ic[7], grav[3], ld, acc_intr[6], gyr_intr[9]; };
-void save_state(const Oracle& o, State& s) { s.so3 = o.so3; s.r3 = o.r3; s.ba = o.ba; s.bg = o.bg; memcpy(s.T_ic, o.T_ic, sizeof s.T_ic); memcpy(s.grav, o.grav, sizeof s.grav); s.ld = o.line_delay; memcpy(s.acc_intr, o.acc_intr, sizeof s.acc_intr); memcpy(s.gyr_intr, o.gyr_intr, sizeof s.gyr_intr); }
+struct State { std::vector<double> so3, r3, ba, bg; double T_ic[7], grav[3], ld, acc_intr[6], gyr_intr[9], intr[10], toff; };
+void save_state(const Oracle& o, State& s) { s.so3 = o.so3; s.r3 = o.r3; s.ba = o.ba; s.bg = o.bg; memcpy(s.T_ic, o.T_ic, sizeof s.T_ic); memcpy(s.grav, o.grav, sizeof s.grav); s.ld = o.line_delay; memcpy(s.acc_intr, o.acc_intr, sizeof s.acc_intr); memcpy(s.gyr_intr, o.gyr_intr, sizeof s.gyr_intr); memcpy(s.intr, o.intr, sizeof s.intr); s.toff = o.toff_delta; }
 void load_state(Oracle& o, const State& s) {
   // copy element-wise: residual blocks hold raw pointers into these vectors
   std::copy(s.so3.begin(), s.so3.end(), o.so3.begin()); std::copy(s.r3.begin(), s.r3.end(), o.r3.begin());
   std::copy(s.ba.begin(), s.ba.end(), o.ba.begin()); std::copy(s.bg.begin(), s.bg.end(), o.bg.begin());
   memcpy(o.T_ic, s.T_ic, sizeof s.T_ic); memcpy(o.grav, s.grav, sizeof s.grav); o.line_delay = s.ld; memcpy(o.acc_intr, s.acc_intr, sizeof s.acc_intr); memcpy(o.gyr_intr, s.gyr_intr, sizeof s.gyr_intr);
+  memcpy(o.intr, s.intr, sizeof s.intr); o.toff_delta = s.toff;
 }
 
 // x <- Plus(x, delta) with delta in CANONICAL tangent order.  Returns squared ambient step norm and squared ambient x norm (before).
@@ -527,8 +538,10 @@ void apply_plus(Oracle& o, const std::vector<double>& d, double& step_sq, double
   auto clampv = [](double v, double r) { return std::min(std::max(v, -r), r); };
   if (o.off_ba >= 0) for (size_t i = 0; i < o.ba.size(); ++i) { const double nv = clampv(o.ba[i] + d[o.off_ba + i], o.max_ba); acc(o.ba[i], nv); o.ba[i] = nv; }
   if (o.off_bg >= 0) for (size_t i = 0; i < o.bg.size(); ++i) { const double nv = clampv(o.bg[i] + d[o.off_bg + i], o.max_bg); acc(o.bg[i], nv); o.bg[i] = nv; }
+  if (o.off_ci >= 0) for (int i = 0; i < o.n_intr; ++i) { const double nv = o.intr[i] + d[o.off_ci + i]; acc(o.intr[i], nv); o.intr[i] = nv; }
+  if (o.off_to >= 0) { const double nv = o.toff_delta + d[o.off_to]; acc(o.toff_delta, nv); o.toff_delta = nv; }
   if (flags & ICC_FLAG_IMU_INTRINSICS) {
-    int off = o.n_tan - 15;
+    int off = o.off_ai;
     for (int i = 0; i < 6; ++i) { const double nv = o.acc_intr[i] + d[off + i]; acc(o.acc_intr[i], nv); o.acc_intr[i] = nv; }
     for (int i = 0; i < 9; ++i) { const double nv = o.gyr_intr[i] + d[off + 6 + i]; acc(o.gyr_intr[i], nv); o.gyr_intr[i] = nv; }
   }
@@ -689,7 +702,7 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
   memcpy(o.T_ic, ipp->T_i_c_init, sizeof o.T_ic);
   { Q4<double> q = qnormalized(Q4<double>{o.T_ic[0], o.T_ic[1], o.T_ic[2], o.T_ic[3]}); o.T_ic[0] = q.x; o.T_ic[1] = q.y; o.T_ic[2] = q.z; o.T_ic[3] = q.w; }
   memcpy(o.acc_intr, ipp->acc_intrinsics, sizeof o.acc_intr); memcpy(o.gyr_intr, ipp->gyr_intrinsics, sizeof o.gyr_intr);
-  o.line_delay = ipp->init_line_delay_s;
+  o.line_delay = ipp->init_line_delay_s; o.toff_delta = 0.0;
   // imu_camera_calibrator.cc:37-63
   std::vector<double> cam_ts(o.frame_t); std::sort(cam_ts.begin(), cam_ts.end());
   o.t0_s = cam_ts.front(); o.tend_s = cam_ts.back();
@@ -779,6 +792,7 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
     for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.r3[3 * (f.s_r3 + i)], 3, LP_NONE, -1});
     b.params.push_back({o.T_ic, 7, LP_SE3, -1});
     b.params.push_back({&o.line_delay, 1, LP_NONE, -1});
+    b.params.push_back({o.intr, o.n_intr, LP_NONE, -1});
     for (int c = f.c0; c < f.c1; ++c) b.params.push_back({&o.points[4 * size_t(o.point_ids[c])], 4, LP_NONE, -1});
     o.vis_blocks.push_back(b);
     if (rolling) o.blocks.push_back(std::move(b));
@@ -801,6 +815,7 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
       for (int i = 0; i < BIAS_N; ++i) b.params.push_back({&o.ba[3 * (s_b + i)], 3, LP_NONE, -1});
       b.params.push_back({o.grav, 3, LP_NONE, -1});
       b.params.push_back({o.acc_intr, 6, LP_NONE, -1});
+      b.params.push_back({&o.toff_delta, 1, LP_NONE, -1});
       acc_blocks.push_back(std::move(b));
     }
     if (calc_times(t_ns, o.start_ns, o.dt_so3_ns, nso3, SPLINE_N, u_so3, s_so3) && calc_times(t_ns, o.start_ns, o.dt_bg_ns, nbg, BIAS_N, u_b, s_b)) {
@@ -808,6 +823,7 @@ icc_status icco_batch_init_spline(void* h, const icc_init_params* ipp) {
       for (int i = 0; i < SPLINE_N; ++i) b.params.push_back({&o.so3[4 * (s_so3 + i)], 4, LP_SO3, -1});
       for (int i = 0; i < BIAS_N; ++i) b.params.push_back({&o.bg[3 * (s_b + i)], 3, LP_NONE, -1});
       b.params.push_back({o.gyr_intr, 9, LP_NONE, -1});
+      b.params.push_back({&o.toff_delta, 1, LP_NONE, -1});
       gyr_blocks.push_back(std::move(b));
     }
   }
@@ -859,6 +875,8 @@ icc_status icco_lm_iterations(void* h, int n, int flags, icc_summary* S) {
 icc_status icco_get_T_i_c(const void* h, double T[7]) { memcpy(T, O(h)->T_ic, 7 * sizeof(double)); return ICC_OK; }
 icc_status icco_get_gravity(const void* h, double g[3]) { memcpy(g, O(h)->grav, 3 * sizeof(double)); return ICC_OK; }
 icc_status icco_get_line_delay(const void* h, double* ld) { *ld = O(h)->line_delay; return ICC_OK; }
+icc_status icco_get_camera_intrinsics(const void* h, double* k, int n) { for (int i = 0; i < n && i < O(h)->n_intr; ++i) k[i] = O(h)->intr[i]; return ICC_OK; }
+icc_status icco_get_time_offset(const void* h, double* t) { *t = O(h)->ip.time_offset_imu_to_cam_s + O(h)->toff_delta; return ICC_OK; }
 icc_status icco_get_num_knots(const void* h, int* a, int* b, int* c, int* d) { const Oracle& o = *O(h); if (a) *a = nknots(o.so3, 4); if (b) *b = nknots(o.r3, 3); if (c) *c = nknots(o.ba, 3); if (d) *d = nknots(o.bg, 3); return ICC_OK; }
 icc_status icco_get_knots(const void* h, double* so3, double* r3, double* ba, double* bg) {
   const Oracle& o = *O(h);

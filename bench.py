@@ -121,19 +121,78 @@ def run_reference(args, cfg):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
+def run_batch_of_eight(args):
+    """BASELINE configs[4]: 8 independent calibration sequences (mixed camera models), replicas only — rank r owns sequences
+    r, r+N, ...; no data-path collective.  step = one LM iteration on every owned sequence; value = all residuals / max-rank time."""
+    import torch
+    import torch.distributed as dist
+    from openimucameracalibrator_b200 import calibrator
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "config 5 is measured on the GPU arm only; use --config 4 for the CPU arm"}), flush=True)
+        return 0
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mine = list(range(rank, 8, world))
+    handles, inits, nres = [], [], 0
+    for k in mine:
+        ds = syn.make_dataset(syn.config5(k))
+        a = capi.CApi(calibrator.load_library(), "icc_", local); capi.load_dataset(a, ds)
+        handles.append(a); inits.append((a.get_knots(), a.get_T_i_c(), a.get_line_delay())); nres += sum(a.num_residuals())
+    def reset():
+        for a, (kn, T0, ld0) in zip(handles, inits):
+            a.set_knots(*kn); a.set_T_i_c(T0); a.set_line_delay(ld0)
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        reset(); [a.lm_iterations(1, FLAGS) for a in handles]
+    sampler = ClockSampler(local) if rank == 0 else None
+    sync()
+    total_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        reset(); sync()
+        t0 = time.perf_counter()
+        for a in handles:
+            launches += a.lm_iterations(1, FLAGS).gpu_launches     # each call ends with a stream synchronisation
+        torch.cuda.synchronize()
+        total_ms += 1e3 * (time.perf_counter() - t0)
+    sync()
+    clocks = sampler.stop() if sampler else None
+    tot_res = nres
+    if world > 1:
+        t = torch.tensor([total_ms, float(nres)], dtype=torch.float64, device=f"cuda:{local}")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(t); total_ms = float(tmax[0]); tot_res = int(t[1])
+    ms = total_ms / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": tot_res / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "cfg5: 8 independent 300x96 sequences, models Pinhole/Fisheye/DivUndist/DoubleSphere/EUCM/FOV/Fisheye/EUCM", "scalar_residuals": tot_res,
+                                     "parallelism": f"replicas x{world} (no collective)", "timing": "host clock around per-sequence LM iterations (each ends in a stream sync)"},
+                          "clocks": clocks, "gpu_launches": launches, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=4)
+    ap.add_argument("--config", type=int, default=4, help="BASELINE config index 1-4; 5 = batch of 8 independent sequences (replicas, one handle each)")
     ap.add_argument("--sample-frames", type=int, default=300, help="frames of the workload used per CPU-arm step")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.config == 5:
+        return run_batch_of_eight(args)
     cfg = syn.CONFIGS[args.config]
 
     if args.impl == "reference":

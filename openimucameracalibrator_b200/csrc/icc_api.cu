@@ -334,14 +334,17 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     ++S.jacobian_evaluations;
     return ICC_OK;
   };
-  auto read_cost_and_grad = [&](bool compute_scale) -> icc_status {
+  // After a Jacobian evaluation: Jacobi scaling (first time) + gradient max-norm, and the cost at x parked next to the other
+  // per-iteration scalars, so that ONE device->host read-back (and one stream synchronisation) serves the whole LM iteration.
+  auto after_jacobian = [&](bool compute_scale) -> icc_status {
     CU(cudaMemsetAsync(h->d_scal.p + SC_GRAD_MAX, 0, sizeof(double), h->stream));
     launch_compute_scale(P, compute_scale ? h->d_scale.p : nullptr, h->opt.jacobi_scaling, h->d_scal.p, h->stream);
-    double c;
-    CU(cudaMemcpyAsync(&c, P.ne + P.ne_off_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->d_scal.p + SC_X_COST, P.ne + P.ne_off_cost, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return ICC_OK;
+  };
+  auto read_scalars = [&]() -> icc_status {
     CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    x_cost = c;
     return ICC_OK;
   };
   if (n == 0) { if (out) *out = S; return ICC_OK; }
@@ -352,15 +355,13 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
   for (int it = 0; it < max_iters; ++it) {
     // The Jacobian / normal equations are (re)built lazily at the top of the iteration that needs them, so that n
     // iterations cost n linear solves + n cost evaluations + one Jacobian evaluation per accepted step (and the first).
+    bool fresh_jacobian = false;
     if (!ne_valid) {
       rc = jac(); if (rc != ICC_OK) return rc;
-      rc = read_cost_and_grad(first); if (rc != ICC_OK) return rc;
-      ne_valid = true;
-      if (first) { S.initial_cost = x_cost; first = false; if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost"); }
-      if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; break; }
+      rc = after_jacobian(first); if (rc != ICC_OK) return rc;
+      ne_valid = true; fresh_jacobian = true;
     }
-    ++S.iterations;
-    CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_scal.p, 0, 5 * sizeof(double), h->stream));    // model change, step / x norms, candidate cost, ok
     SolveParams sp; sp.radius = radius; sp.min_diag = h->opt.min_lm_diagonal; sp.max_diag = h->opt.max_lm_diagonal; sp.jacobi_scaling = h->opt.jacobi_scaling;
     const int a = mark();
     launch_solve(P, h->d_scale.p, sp, h->d_ws.p, h->d_delta.p, h->d_scal.p, h->stream);
@@ -368,9 +369,14 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     const int cand = 1 - h->cur;
     launch_update(P, h->st[h->cur].view(), h->st[cand].view(), h->d_delta.p, h->max_ba, h->max_bg, h->d_scal.p, h->stream);
     rc = eval_cost(h, h->st[cand].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); if (rc != ICC_OK) return rc;
-    ++S.cost_evaluations;
-    CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    rc = read_scalars(); if (rc != ICC_OK) return rc;
+    if (fresh_jacobian) {
+      x_cost = sc[SC_X_COST];
+      if (first) { S.initial_cost = x_cost; first = false; if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost"); }
+      // Ceres tests the gradient right after the Jacobian evaluation; the step computed above is simply discarded
+      if (check_convergence && sc[SC_GRAD_MAX] <= h->opt.gradient_tolerance) { S.termination = 3; break; }
+    }
+    ++S.iterations; ++S.cost_evaluations;
     const double model_change = sc[SC_MODEL_CHANGE];
     if (sc[SC_OK] == 0.0 || !(model_change > 0.0)) {          // invalid step (HandleInvalidStep)
       if (++invalid >= h->opt.max_consecutive_invalid_steps) { S.termination = 4; break; }
@@ -397,7 +403,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
       if (radius < h->opt.min_trust_region_radius) { S.termination = 4; break; }
     }
   }
-  if (first) { rc = jac(); if (rc != ICC_OK) return rc; rc = read_cost_and_grad(true); if (rc != ICC_OK) return rc; S.initial_cost = x_cost; }
+  if (first) { rc = jac(); if (rc != ICC_OK) return rc; rc = after_jacobian(true); if (rc != ICC_OK) return rc; rc = read_scalars(); if (rc != ICC_OK) return rc; x_cost = sc[SC_X_COST]; S.initial_cost = x_cost; }
   CU(cudaStreamSynchronize(h->stream));
   S.final_cost = x_cost;
   auto span_s = [&](const std::vector<std::pair<int, int>>& v) { double tot = 0; for (auto& p : v) { float ms = 0; cudaEventElapsedTime(&ms, ev[p.first], ev[p.second]); tot += ms; } return tot * 1e-3; };

@@ -67,7 +67,7 @@ struct SolveParams {
 };
 
 // scal[] layout written by the solver / update kernels and read back by the host each LM iteration
-enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK = 4, SC_GRAD_MAX = 5, SC_REPROJ_SUM = 6, SC_REPROJ_CNT = 7, SC_COUNT = 8 };
+enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK = 4, SC_GRAD_MAX = 5, SC_REPROJ_SUM = 6, SC_REPROJ_CNT = 7, SC_X_COST = 8, SC_COUNT = 10 };
 
 // ---- launches (all asynchronous on `st`) ----------------------------------------------------------------------
 // residuals + analytic Jacobians + J^T J / J^T r tiles reduced into P.ne (must be zeroed first), or cost only into *cost

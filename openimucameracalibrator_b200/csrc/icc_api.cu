@@ -95,6 +95,8 @@ struct icc_handle {
   int dropped_frames = 0, dropped_imu = 0;
   // ---- device ---------------------------------------------------------------------------------------------------
   cudaStream_t stream = nullptr;
+  EvalAux aux{};            // second stream + fork/join events: vision and IMU kernels of one evaluation run concurrently
+  bool aux_ok = false;
   int sm_count = 148;
   StateBufs st[2]; int cur = 0;
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
@@ -286,12 +288,12 @@ icc_status configure(icc_handle* h, int flags) {
 // One Jacobian evaluation on the current state: zero the packed normal equations, run the kernels, cross-rank reduce.
 icc_status eval_jacobian(icc_handle* h, const DeviceState& S, double* residuals_dev) {
   CU(cudaMemsetAsync(h->P.ne, 0, (size_t)h->P.ne_size * sizeof(double), h->stream));
-  if (launch_eval(h->P, S, true, nullptr, residuals_dev, nullptr, h->stream)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
+  if (launch_eval(h->P, S, true, nullptr, residuals_dev, nullptr, h->stream, h->aux_ok ? &h->aux : nullptr)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
   if (h->allreduce && h->shard_world > 1) { h->allreduce(h->P.ne, h->P.ne_size, (void*)h->stream, h->allreduce_user); }
   return ICC_OK;
 }
 icc_status eval_cost(icc_handle* h, const DeviceState& S, double* cost_dev, double* residuals_dev, double* reproj_dev) {
-  if (launch_eval(h->P, S, false, cost_dev, residuals_dev, reproj_dev, h->stream)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
+  if (launch_eval(h->P, S, false, cost_dev, residuals_dev, reproj_dev, h->stream, h->aux_ok ? &h->aux : nullptr)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
   if (h->allreduce && h->shard_world > 1 && cost_dev) { h->allreduce(cost_dev, 1, (void*)h->stream, h->allreduce_user); }
   return ICC_OK;
 }
@@ -448,9 +450,12 @@ icc_status icc_create(icc_handle** out, int device_ordinal) {
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; h->device = -1; return ICC_ERR_CUDA; }
   if (h->d_scal.alloc(SC_COUNT) != cudaSuccess) { h->err = "cudaMalloc failed"; return ICC_ERR_CUDA; }
+  h->aux_ok = cudaStreamCreateWithFlags(&h->aux.stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->aux.fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->aux.join, cudaEventDisableTiming) == cudaSuccess;
+  if (!h->aux_ok) { h->err = "cudaStreamCreate failed"; return ICC_ERR_CUDA; }
   return ICC_OK;
 }
-void icc_destroy(icc_handle* h) { if (!h) return; if (h->device >= 0) { cudaSetDevice(h->device); if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); } } delete h; }
+void icc_destroy(icc_handle* h) { if (!h) return; if (h->device >= 0) { cudaSetDevice(h->device); if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); } if (h->aux_ok) { cudaStreamDestroy(h->aux.stream); cudaEventDestroy(h->aux.fork); cudaEventDestroy(h->aux.join); } } delete h; }
 const char* icc_last_error(const icc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 icc_status icc_set_solver_options(icc_handle* h, const icc_solver_options* o) { if (!h || !o) return ICC_ERR_INVALID_ARGUMENT; h->opt = *o; return ICC_OK; }
 

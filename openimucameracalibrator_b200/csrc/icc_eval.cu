@@ -580,7 +580,7 @@ int grid_for(int n_items, int sm_count) { const int ctas = (n_items + WARPS - 1)
 
 }  // namespace
 
-int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st) {
+int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st_main, const EvalAux* aux) {
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
   const size_t sm_vis = WARPS * sizeof(WarpCtx) + WARPS * 48 * LDJ * sizeof(double);
@@ -596,6 +596,9 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     if (e) return 1;
     attr_done = true;
   }
+  const bool fork = aux && P.n_vwork > 0 && P.rolling && P.n_iwork > 0;
+  cudaStream_t st = st_main;
+  if (fork) { cudaEventRecord(aux->fork, st_main); cudaStreamWaitEvent(aux->stream, aux->fork, 0); }
   if (P.n_vwork > 0 && P.rolling) {
     const int grid = grid_for(P.n_vwork, sm_count);
     if (with_jacobian && P.cam_intr_active) vision_kernel<2><<<grid, WARPS * 32, sm_vis_k, st>>>(P, S, cost_out, residuals_out, reproj_out);
@@ -604,6 +607,7 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     count_launch();
   }
   if (P.n_iwork > 0) {
+    if (fork) st = aux->stream;
     const int grid = grid_for(P.n_iwork, sm_count);
     if (P.bias_active || P.intr_active) {
       if (with_jacobian && P.intr_active) imu_kernel<true, 2><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
@@ -615,6 +619,7 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     }
     count_launch();
   }
+  if (fork) { cudaEventRecord(aux->join, aux->stream); cudaStreamWaitEvent(st_main, aux->join, 0); }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

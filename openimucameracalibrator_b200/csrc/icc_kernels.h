@@ -71,7 +71,10 @@ enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK
 
 // ---- launches (all asynchronous on `st`) ----------------------------------------------------------------------
 // residuals + analytic Jacobians + J^T J / J^T r tiles reduced into P.ne (must be zeroed first), or cost only into *cost
-int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st);
+// `aux` (optional): a second stream + two events; the IMU kernel then runs concurrently with the vision kernel (fork / join
+// around the pair on `st`), which fills the partial last wave of either kernel.
+struct EvalAux { cudaStream_t stream; cudaEvent_t fork, join; };
+int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st, const EvalAux* aux = nullptr);
 // scale[i] = 1/(1+sqrt(H_ii)) (Jacobi scaling, computed once per optimize) ; gradient inf-norm
 void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, double* scal, cudaStream_t st);
 // banded + bordered Cholesky solve of (S H S + D) y = -S g ; delta = S y (solver order) ; model cost change

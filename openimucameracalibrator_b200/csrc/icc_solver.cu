@@ -7,16 +7,23 @@
 //     + bordered (T_i_c, gravity, line delay, bias knots) system: the spline control points are Schur-eliminated first
 //   * LieLocalParameterization::Plus on every SO(3) knot and on T_i_c (basalt_spline/ceres_local_param.h:84-92)
 //
-// The band factorisation is a recurrence along time, so it is cut into P time chunks (substructuring / one-level nested
-// dissection): kernel A eliminates every chunk's interior knots in parallel (one CTA per chunk, active band window in
-// shared memory, one __syncthreads per eliminated column, LDL^T so no square roots), carrying the couplings to the
-// chunk's left separator, the border and the right-hand side; kernel B factors the small reduced system
-// {separators (block tridiagonal) + border} in one CTA and back-substitutes it; kernel C back-substitutes the interiors
-// in parallel; kernel D forms the step and the model cost change.
+// The band factorisation is a recurrence along time, so it is reordered by nested dissection of the time axis:
+//   level 0   the knot columns are cut into P time chunks separated by P-1 separators of kd columns; every chunk's interior
+//             is eliminated in parallel (one CTA per chunk, blocked LDL^T in a circular shared-memory window, FP64 tensor-core
+//             trailing updates), carrying the couplings to its two separators, the border and the right-hand side;
+//   level l   the separators form a block-tridiagonal system: block cyclic reduction eliminates every other block in
+//             parallel (same elimination routine, one CTA per block), halving the block count per level;
+//   root      one CTA factors the last block + the border (T_i_c, gravity, line delay, bias knots, ...) and solves them;
+// then the back-substitution walks the levels in reverse.  The sequential pivot chain is O(nk / P + kd log P) columns instead
+// of nk.  The last kernel forms the step and the model cost change.
 #include "icc_device_math.cuh"
 #include "icc_kernels.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace icc {
 
@@ -25,25 +32,39 @@ void count_launch();
 namespace {
 
 constexpr int NT = 512;          // threads of the factorisation kernels
-constexpr int MAX_CHUNKS = 32;
+#ifdef ICC_SOLVER_TRACE
+__device__ long long g_trace[64];
+__device__ int g_trace_slot = -1;   // set per kernel by thread 0 of CTA 0
+#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && g_trace_base >= 0) g_trace[g_trace_base + (i)] = clock64(); } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
+constexpr int MAX_LEVELS = 12;
 
 struct SolvePlan {
-  int P, w;                       // chunks, separator width (0 when P == 1)
-  int a[MAX_CHUNKS], b[MAX_CHUNKS];   // interior column ranges [a, b)
-  int nkr, kdr, ldbr;             // reduced (separator) system: columns, half bandwidth, column length
-  int nbl;                        // local border rows of a chunk: w + nb + 1 (left separator | border | rhs)
-  int WS_A, WS_B;                 // window slots (power of two)
+  int P, w;                       // level-0 chunks, separator width (0 when P == 1)
+  int len, rem;                   // chunk c owns len + (c < rem) interior columns
+  int L;                          // cyclic-reduction levels 1..L; reduced system R_l has S[l] blocks of w columns (l = 1..L+1)
+  int S[MAX_LEVELS + 2], off[MAX_LEVELS + 2];   // off[l]: first column of R_l inside the concatenated reduced arrays
+  int nkr_total;                  // columns of all reduced systems together
+  int kdr, ldbr;                  // reduced systems: half bandwidth 2w-1, column length
+  int nbl;                        // local border rows of an elimination: w + nb + 1 (left separator | border | rhs)
+  int WS_A, WS_R, WS_B;           // window slots (power of two): level 0, cyclic-reduction levels, root
 };
+__host__ __device__ inline int chunk_a(const SolvePlan& pl, int c) { return c * (pl.len + pl.w) + (c < pl.rem ? c : pl.rem); }
+__host__ __device__ inline int chunk_b(const SolvePlan& pl, int c) { return chunk_a(pl, c) + pl.len + (c < pl.rem ? 1 : 0); }
+// block j of R_l is the original separator ((j+1) << (l-1)) - 1, which sits right behind the interior of that chunk
+__host__ __device__ inline int sep_col(const SolvePlan& pl, int l, int j) { return chunk_b(pl, ((j + 1) << (l - 1)) - 1); }
 
-// Workspace (doubles): Lb[nk*ldb] | El[nk*nbl] | y[n] | t[nk] | R{bandr[nkr*ldbr] | Er[nkr*nbp] | Cr[nbp*nbp]} | Lbr[nkr*ldbr] | Elr[nkr*nbp] | tr[nkr]
-struct SolveWs { double *Lb, *El, *y, *t, *bandr, *Er, *Cr, *Lbr, *Elr, *tr, *Wg; size_t reduced_doubles, total; };
+// Workspace (doubles): Lb[nk*ldb] | El[nk*nbl] | y[n] | R{bandr[nkr_total*ldbr] | Er[nkr_total*nbp] | Cr[nbp*nbp]} | Lbr | Elr[nkr_total*nbl] | Wg
+struct SolveWs { double *Lb, *El, *y, *bandr, *Er, *Cr, *Lbr, *Elr, *Wg; size_t reduced_doubles, total; };
 __host__ __device__ inline SolveWs carve(double* ws, int nk, int nb, int ldb, const SolvePlan& pl) {
-  SolveWs w; const int nbp = nb + 1; const size_t n = (size_t)nk + nb;
-  w.Lb = ws; w.El = w.Lb + (size_t)nk * ldb; w.y = w.El + (size_t)nk * pl.nbl; w.t = w.y + n;
-  w.bandr = w.t + nk; w.Er = w.bandr + (size_t)pl.nkr * pl.ldbr; w.Cr = w.Er + (size_t)pl.nkr * nbp;
-  w.reduced_doubles = (size_t)pl.nkr * pl.ldbr + (size_t)pl.nkr * nbp + (size_t)nbp * nbp;
-  w.Lbr = w.Cr + (size_t)nbp * nbp; w.Elr = w.Lbr + (size_t)pl.nkr * pl.ldbr; w.tr = w.Elr + (size_t)pl.nkr * nbp;
-  w.Wg = w.tr + ((pl.nkr + 3) & ~3);                               // nk x (kd + KB + nbl): pre-scaled window columns of kernel A
+  SolveWs w; const int nbp = nb + 1; const size_t n = (size_t)nk + nb, nr = (size_t)pl.nkr_total;
+  w.Lb = ws; w.El = w.Lb + (size_t)nk * ldb; w.y = w.El + (size_t)nk * pl.nbl;
+  w.bandr = w.y + ((n + 3) & ~(size_t)3); w.Er = w.bandr + nr * pl.ldbr; w.Cr = w.Er + nr * nbp;
+  w.reduced_doubles = nr * pl.ldbr + nr * nbp + (size_t)nbp * nbp;
+  w.Lbr = w.Cr + (size_t)nbp * nbp; w.Elr = w.Lbr + nr * pl.ldbr;
+  w.Wg = w.Elr + nr * pl.nbl;                                       // nk x (kd + KB + nbl): pre-scaled window columns of level 0
   w.total = (size_t)(w.Wg + (size_t)nk * (ldb - 1 + 8 + pl.nbl) - ws) + 16;
   return w;
 }
@@ -86,7 +107,7 @@ __device__ int build_block_table(uchar2* blocks, int M) {   // the nbk blocks of
   }
   return n;
 }
-struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; };   // Ld, inv: double-buffered by panel parity
+struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; int trace; };   // Ld, inv: double-buffered by panel parity
 
 // (a)+(b) of one panel, executed by ONE warp (no block-wide barrier inside):
 //   (a) lane 0 factors the KB x KB diagonal block in registers (unit-lower l, pivots D -> inv), kb <= KB columns are pivots;
@@ -209,36 +230,70 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
   const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int PB = ((WS - kd - KB) / KB) * KB, M = kd + fs.nbl, ncol0 = (M + 7) / 8;   // ncol0 = blocks with bj == 0
   double* W = fs.W;
+#ifdef ICC_SOLVER_TRACE
+  const int g_trace_base = fs.trace;
+#endif
   if (tid == 0) *fs.flag = 1;
   for (int j0 = j_begin; j0 < j_end; j0 += PB) {
-    const int first = j0 == j_begin ? j_begin : j0 + kd + KB, last = j0 + PB + kd + KB;
-    {   // group load with 8 independent global loads in flight per thread (the loads, not the math, bound this phase)
-      const int total = (last - first) * CL;
+    const int gend = min(j0 + PB, j_end);
+    const int first = j0 == j_begin ? j_begin : j0 + kd + KB, last = gend + kd + KB;   // columns the group reads or updates
+    {   // group load with 8 independent global loads in flight per thread; (column, entry) advance incrementally (no divisions)
+      const int total = (last - first) * CL, de = nt % CL, dc = nt / CL;
+      int e = tid % CL, col = first + tid / CL;
       for (int b0 = tid; b0 < total; b0 += 8 * nt) {
-        double v[8];
+        double v[8]; int slot[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; v[u] = idx < total ? load(first + idx / CL, idx % CL) : 0.0; }
+        for (int u = 0; u < 8; ++u) {
+          const bool in = b0 + u * nt < total;
+          v[u] = in ? load(col, e) : 0.0;
+          slot[u] = in ? (col & mask) * CL + e : -1;
+          e += de; col += dc; if (e >= CL) { e -= CL; ++col; }
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; if (idx < total) { const int col = first + idx / CL; W[(size_t)(col & mask) * CL + idx % CL] = v[u]; } }
+        for (int u = 0; u < 8; ++u) if (slot[u] >= 0) W[slot[u]] = v[u];
       }
     }
     __syncthreads();
-    const int gend = min(j0 + PB, j_end);
+    TR(2);
     if (warp < PW) panel_factor_warp(fs, j0, min(KB, gend - j0), kd, ldbp, CL, mask, 0);   // prologue: first panel of the group
     __syncthreads();
+    TR(3);
     if (*fs.flag == 0) return false;                            // uniform
     int buf = 0;
+#ifdef ICC_SOLVER_TRACE
+    long long acc1 = 0, acc2 = 0, acc3 = 0, tq0 = 0, tq1 = 0;
+#endif
     for (int jp = j0; jp < gend; jp += KB, buf ^= 1) {
       const bool has_next = jp + KB < gend;
+#ifdef ICC_SOLVER_TRACE
+      tq0 = clock64();
+#endif
       trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, 0, ncol0, warp, nwarps);
       __syncthreads();
+#ifdef ICC_SOLVER_TRACE
+      tq1 = clock64(); acc1 += tq1 - tq0;
+#endif
       if (warp < PW) { if (has_next) panel_factor_warp(fs, jp + KB, min(KB, gend - jp - KB), kd, ldbp, CL, mask, buf ^ 1); }
       if (warp >= PW || !has_next) trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, ncol0, fs.nblocks, has_next ? warp - PW : warp, has_next ? nwarps - PW : nwarps);
+#ifdef ICC_SOLVER_TRACE
+      acc2 += clock64() - tq1;
+#endif
       __syncthreads();
+#ifdef ICC_SOLVER_TRACE
+      acc3 += clock64() - tq1;
+#endif
       if (*fs.flag == 0) return false;                          // uniform
     }
+#ifdef ICC_SOLVER_TRACE
+    if (blockIdx.x == 0 && g_trace_base >= 0) {
+      if (tid == 0) { g_trace[g_trace_base + 8] = acc1; g_trace[g_trace_base + 9] = acc2; g_trace[g_trace_base + 10] = acc3; }
+      if (tid == PW * 32) { g_trace[g_trace_base + 11] = acc2; }
+    }
+#endif
+    TR(4);
     for (int col = j0 + warp; col < gend; col += nwarps) { const double* src = W + (size_t)(col & mask) * CL; for (int e = lane; e < CL; e += 32) store(col, e, src[e]); }
     __syncthreads();
+    TR(5);
   }
   return true;
 }
@@ -342,14 +397,16 @@ __host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int
 // border [coupling to the left separator (stored transposed in H) | border | rhs].  Kernel A then only copies columns.
 __global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp) {
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl;
-  const int a = pl.a[c], b = pl.b[c];
+  const int a = chunk_a(pl, c), b = chunk_b(pl, c);
   const bool has_left = c > 0, has_right = c < pl.P - 1;
   const int ldbp = kd + KB, CL = ldbp + nbl, right_end = has_right ? b + w : b;
   const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
-  const int total = (right_end - a) * CL;
-  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
-    const int col = a + idx / CL, e = idx % CL;
+  const int total = (right_end - a) * CL, stride = gridDim.y * blockDim.x, de = stride % CL, dc = stride / CL;
+  const int idx0 = blockIdx.y * blockDim.x + threadIdx.x;
+  int e = idx0 % CL, col = a + idx0 / CL;
+  for (int idx = idx0; idx < total; idx += stride, e += de, col += dc) {
+    if (e >= CL) { e -= CL; ++col; }
     double v = 0.0;
     if (e < ldbp) {
       const int i = col + e;
@@ -364,38 +421,65 @@ __global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __re
   }
 }
 
-// ---- kernel A: eliminate the interior knots of every time chunk ---------------------------------------------------
-__global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
+// ---- elimination kernel: level 0 = interior knots of every time chunk ; level >= 1 = every other separator block -----
+template <bool LEVEL0>
+__global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, double* scal) {
   extern __shared__ __align__(16) double sm[];
-  const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl, nbp = nb + 1;
-  const int a = pl.a[c], b = pl.b[c];
-  const bool has_left = c > 0, has_right = c < pl.P - 1;
-  const int ldbp = kd + KB, CL = ldbp + nbl, WS = pl.WS_A;
+  const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, nbp = nb + 1;
+  SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
+#ifdef ICC_SOLVER_TRACE
+  const int g_trace_base = LEVEL0 ? 0 : (level == 1 ? 16 : -1);
+#endif
+  TR(0);
+  if (!LEVEL0 && scal[SC_OK] < 0.0) return;                     // an earlier level hit a bad pivot (uniform)
+  int a, b, kd, ldb; bool has_left, has_right;
+  const double* src_band = nullptr; const double* src_E = nullptr; double* dst_Lb; double* dst_El;
+  if (LEVEL0) {
+    a = chunk_a(pl, c); b = chunk_b(pl, c); kd = P.kd; ldb = P.ldb; has_left = c > 0; has_right = c < pl.P - 1;
+    dst_Lb = ws.Lb; dst_El = ws.El;
+  } else {
+    const int o = pl.off[level];
+    a = 2 * c * w; b = a + w; kd = pl.kdr; ldb = pl.ldbr; has_left = c > 0; has_right = 2 * c + 1 < pl.S[level];
+    src_band = ws.bandr + (int64_t)o * ldb; src_E = ws.Er + (int64_t)o * nbp;
+    dst_Lb = ws.Lbr + (int64_t)o * ldb; dst_El = ws.Elr + (int64_t)o * nbl;
+  }
+  const int ldbp = kd + KB, CL = ldbp + nbl, WS = LEVEL0 ? pl.WS_A : pl.WS_R;
   double* extra;
   FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
   double* W = fs.W; double* Cl = fs.Cl;
-  SolveWs ws = carve(wsp, nk, nb, ldb, pl);
   fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
+#ifdef ICC_SOLVER_TRACE
+  fs.trace = g_trace_base;
+#endif
   __syncthreads();
+  TR(1);
   const int right_end = has_right ? b + w : b;
-  auto load = [&](int col, int e) -> double { return col < right_end ? ws.Wg[(int64_t)col * CL + e] : 0.0; };
-  auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) ws.Lb[(int64_t)col * ldb + e] = v; } else ws.El[(int64_t)col * nbl + (e - ldbp)] = v; };
+  auto load = [&](int col, int e) -> double {
+    if (col >= right_end) return 0.0;
+    if (LEVEL0) return ws.Wg[(int64_t)col * CL + e];
+    if (e < ldbp) return (e <= kd && col + e < right_end) ? src_band[(int64_t)col * ldb + e] : 0.0;
+    const int lb = e - ldbp;
+    if (lb < w) { if (!has_left || col >= b) return 0.0; const int s = a - w + lb; return src_band[(int64_t)s * ldb + (col - s)]; }   // col - s <= 2w - 1 = kd
+    return src_E[(int64_t)col * nbp + (lb - w)];
+  };
+  auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) dst_Lb[(int64_t)col * ldb + e] = v; } else dst_El[(int64_t)col * nbl + (e - ldbp)] = v; };
   const bool ok = factor_range(fs, a, b, kd, ldbp, CL, WS, load, store);
   if (!ok) { if (threadIdx.x == 0) scal[SC_OK] = -1.0; return; }
-  // ---- scatter the Schur complement of this chunk into the reduced system ------------------------------------------
+  // ---- scatter the Schur complement into the next reduced system: the left / right neighbours become its blocks c-1 / c ----
   const int mask = WS - 1;
-  const int sl0 = (c - 1) * w, sr0 = c * w;                     // reduced indices of the left / right separator
+  const int sl0 = (c - 1) * w, sr0 = c * w;
+  double* ob = ws.bandr + (int64_t)pl.off[level + 1] * pl.ldbr; double* oE = ws.Er + (int64_t)pl.off[level + 1] * nbp;
   if (has_right) {
     for (int idx = threadIdx.x; idx < w * CL; idx += blockDim.x) {
       const int t = idx / CL, e = idx % CL, col = b + t;
       const double v = W[(size_t)(col & mask) * CL + e];
       if (v == 0.0) continue;
-      if (e < ldbp) { if (t + e < w) atomicAdd(ws.bandr + (int64_t)(sr0 + t) * pl.ldbr + e, v); }
+      if (e < ldbp) { if (t + e < w) atomicAdd(ob + (int64_t)(sr0 + t) * pl.ldbr + e, v); }
       else {
         const int lb = e - ldbp;
-        if (lb < w) { if (has_left) atomicAdd(ws.bandr + (int64_t)(sl0 + lb) * pl.ldbr + (sr0 + t - sl0 - lb), v); }
-        else atomicAdd(ws.Er + (int64_t)(sr0 + t) * nbp + (lb - w), v);
+        if (lb < w) { if (has_left) atomicAdd(ob + (int64_t)(sl0 + lb) * pl.ldbr + (sr0 + t - sl0 - lb), v); }
+        else atomicAdd(oE + (int64_t)(sr0 + t) * nbp + (lb - w), v);
       }
     }
   }
@@ -403,23 +487,27 @@ __global__ void __launch_bounds__(NT) chunk_factor_kernel(DeviceProblem P, Solve
     const int b1 = tri_row(idx), b2 = idx - b1 * (b1 + 1) / 2;   // b1 >= b2, local order [left | border | rhs]
     const double v = Cl[b1 * nbl + b2];
     if (v == 0.0) continue;
-    if (b1 < w) { if (has_left) atomicAdd(ws.bandr + (int64_t)(sl0 + b2) * pl.ldbr + (b1 - b2), v); }
-    else if (b2 < w) { if (has_left) atomicAdd(ws.Er + (int64_t)(sl0 + b2) * nbp + (b1 - w), v); }
+    if (b1 < w) { if (has_left) atomicAdd(ob + (int64_t)(sl0 + b2) * pl.ldbr + (b1 - b2), v); }
+    else if (b2 < w) { if (has_left) atomicAdd(oE + (int64_t)(sl0 + b2) * nbp + (b1 - w), v); }
     else atomicAdd(ws.Cr + (int64_t)(b1 - w) * nbp + (b2 - w), v);
   }
+  __syncthreads();
+  TR(6);
 }
 
-// ---- kernel B: reduced system {separators + border}: factor, solve ------------------------------------------------
+// ---- root: last reduced system {remaining separator blocks + border}: factor, solve ----------------------------------
 __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
   extern __shared__ __align__(16) double sm[];
-  const int nk = P.nk, nb = P.nb, nbp = nb + 1, nkr = pl.nkr, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w;
+  const int nk = P.nk, nb = P.nb, nbp = nb + 1, root = pl.L + 1, nkr = pl.S[root] * pl.w, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w;
   const int ldbp = kdr + KB, CL = ldbp + nbp, WS = pl.WS_B, tid = threadIdx.x, nt = blockDim.x;
   double* xb;
   FactorSmem fs = carve_smem(sm, WS, CL, nbp, kdr, ldbp, &xb, nbp + 1);
   double* W = fs.W; double* Cs = fs.Cl;           // nbp x nbp lower, row nb = rhs
   const double* C = P.ne + P.ne_off_C; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
-  if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // a chunk hit a bad pivot
+  const double* rband = ws.bandr + (int64_t)pl.off[root] * ldbr; const double* rE = ws.Er + (int64_t)pl.off[root] * nbp;
+  double* rLb = ws.Lbr + (int64_t)pl.off[root] * ldbr; double* rEl = ws.Elr + (int64_t)pl.off[root] * pl.nbl;   // used with row length nbp
+  if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // an elimination hit a bad pivot
   if (nkr > 0) fs.nblocks = build_block_table(fs.blocks, kdr + nbp);
   for (int idx = tid; idx < nbp * nbp; idx += nt) {
     const int b = idx / nbp, c = idx % nbp;
@@ -436,10 +524,10 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   if (nkr > 0) {
     auto load = [&](int col, int e) -> double {
       if (col >= nkr) return 0.0;
-      if (e < ldbp) return (e <= kdr && col + e < nkr) ? ws.bandr[(int64_t)col * ldbr + e] : 0.0;
-      return ws.Er[(int64_t)col * nbp + (e - ldbp)];
+      if (e < ldbp) return (e <= kdr && col + e < nkr) ? rband[(int64_t)col * ldbr + e] : 0.0;
+      return rE[(int64_t)col * nbp + (e - ldbp)];
     };
-    auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kdr) ws.Lbr[(int64_t)col * ldbr + e] = v; } else ws.Elr[(int64_t)col * nbp + (e - ldbp)] = v; };
+    auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kdr) rLb[(int64_t)col * ldbr + e] = v; } else rEl[(int64_t)col * nbp + (e - ldbp)] = v; };
     ok = factor_range(fs, 0, nkr, kdr, ldbp, CL, WS, load, store);
   }
   // border: dense LDL^T of the final Schur complement, rhs carried as the last row
@@ -472,36 +560,54 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   if (nkr > 0) {
     // separators: t_j = rhs_j - sum_b Elr[j][b] x_b, then the register/shuffle back-substitution
     double* tw = W; double* Bw = W + ((nkr + 3) & ~3);
-    for (int j = tid; j < nkr; j += nt) { const double* le = ws.Elr + (int64_t)j * nbp; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; tw[j] = t; }
+    for (int j = tid; j < nkr; j += nt) { const double* le = rEl + (int64_t)j * nbp; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; tw[j] = t; }
     __syncthreads();
-    backsub_dispatch(ws.Lbr, tw, Bw, 0, nkr, nkr, kdr, ldbr, 64);
-    for (int rj = tid; rj < nkr; rj += nt) { const int k = rj / w, tt = rj % w; ws.y[pl.b[k] + tt] = tw[rj]; }
+    backsub_dispatch(rLb, tw, Bw, 0, nkr, nkr, kdr, ldbr, 64);
+    for (int rj = tid; rj < nkr; rj += nt) { const int k = rj / w, tt = rj % w; ws.y[sep_col(pl, root, k) + tt] = tw[rj]; }
   }
   __syncthreads();
   if (tid == 0) scal[SC_OK] = 1.0;
 }
 
-// ---- kernel C: back-substitute the chunk interiors in parallel ----------------------------------------------------
-__global__ void __launch_bounds__(256) chunk_backsub_kernel(DeviceProblem P, SolvePlan pl, double* wsp, const double* scal) {
+// ---- back-substitution of one level (level 0: chunk interiors, level >= 1: the blocks eliminated at that level) -----
+template <bool LEVEL0>
+__global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, const double* scal) {
   extern __shared__ __align__(16) double sm[];
   if (scal[SC_OK] != 1.0) return;
-  const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl, tid = threadIdx.x, nt = blockDim.x;
-  const int a = pl.a[c], b = pl.b[c];
-  const bool has_left = c > 0, has_right = c < pl.P - 1;
-  SolveWs ws = carve(wsp, nk, nb, ldb, pl);
-  const int top = has_right ? b + w : b;   // right separator values are known: they only scatter into the interior
+  const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, tid = threadIdx.x, nt = blockDim.x;
+  SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
+  int a, b, kd, ldb, y_left, y_own, y_right; bool has_left, has_right;   // y_*: position of the blocks in the solution vector
+  const double* Lb; const double* El;
+  if (LEVEL0) {
+    a = chunk_a(pl, c); b = chunk_b(pl, c); kd = P.kd; ldb = P.ldb; has_left = c > 0; has_right = c < pl.P - 1;
+    Lb = ws.Lb; El = ws.El; y_left = a - w; y_own = a; y_right = b;
+  } else {
+    const int o = pl.off[level];
+    a = 2 * c * w; b = a + w; kd = pl.kdr; ldb = pl.ldbr; has_left = c > 0; has_right = 2 * c + 1 < pl.S[level];
+    Lb = ws.Lbr + (int64_t)o * ldb; El = ws.Elr + (int64_t)o * nbl;
+    y_left = has_left ? sep_col(pl, level, 2 * c - 1) : 0; y_own = sep_col(pl, level, 2 * c); y_right = has_right ? sep_col(pl, level, 2 * c + 1) : 0;
+  }
+  const int top = has_right ? b + w : b;   // right separator values are known: they only enter the right-hand sides
   double* xl = sm;                         // local border solution [left separator | border]
-  double* tw = xl + ((nbl + 3) & ~3);      // t / x for columns [a, top)
-  double* Bw = tw + ((top - a + 3) & ~3);  // (PB + kd) * ldb panel of L
-  for (int i = tid; i < w + nb; i += nt) xl[i] = i < w ? (has_left ? ws.y[a - w + i] : 0.0) : ws.y[nk + i - w];
+  double* xr = xl + ((nbl + 3) & ~3);      // right separator solution
+  double* tw = xr + ((w + 3) & ~3);        // t / x for columns [a, b)
+  double* Bw = tw + ((b - a + 3) & ~3);    // (PB + kd) * ldb panel of L
+  for (int i = tid; i < w + nb; i += nt) xl[i] = i < w ? (has_left ? ws.y[y_left + i] : 0.0) : ws.y[nk + i - w];
+  for (int i = tid; i < w; i += nt) xr[i] = has_right ? ws.y[y_right + i] : 0.0;
   __syncthreads();
-  for (int j = a + tid; j < top; j += nt) {
-    if (j < b) { const double* le = ws.El + (int64_t)j * nbl; double t = le[w + nb]; for (int i = 0; i < w + nb; ++i) t -= le[i] * xl[i]; tw[j - a] = t; }
-    else tw[j - a] = ws.y[j];
+  // t_j = rhs_j - sum_i El[j][i] xl[i] - sum_{r in right separator} (L_rj D_j) x_r : one warp per column, coalesced rows
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  for (int j = a + warp; j < b; j += nwarps) {
+    const double* le = El + (int64_t)j * nbl; const double* lc = Lb + (int64_t)j * ldb;
+    double acc = 0.0;
+    for (int i = lane; i < w + nb; i += 32) acc = fma(le[i], xl[i], acc);
+    for (int r = b + lane; r < top && r - j <= kd; r += 32) acc = fma(lc[r - j], xr[r - b], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) tw[j - a] = le[w + nb] - acc;
   }
   __syncthreads();
-  backsub_dispatch(ws.Lb, tw, Bw, a, top, b, kd, ldb, 128);
-  for (int j = a + tid; j < b; j += nt) ws.y[j] = tw[j - a];
+  backsub_dispatch(Lb, tw, Bw, a, b, b, kd, ldb, LEVEL0 ? 128 : 64);
+  for (int j = a + tid; j < b; j += nt) ws.y[y_own + (j - a)] = tw[j - a];
 }
 
 // ---- kernel D: step in the unscaled space, model cost change = 1/2 (y^T D y + y^T rhs) ----------------------------
@@ -618,35 +724,54 @@ __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand
 int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_A, P.kd + KB + pl.nbl, pl.nbl, P.kd, 0); }
+size_t smem_R(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_R, pl.kdr + KB + pl.nbl, pl.nbl, pl.kdr, 0); }
 size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
-  const int nbp = P.nb + 1;
+  const int nbp = P.nb + 1, nkr = pl.S[pl.L + 1] * pl.w;
   const size_t fac = factor_smem_bytes(pl.WS_B, pl.kdr + KB + nbp, nbp, pl.kdr, nbp + 1);
-  const size_t back = ((size_t)pl.nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;   // back-substitution reuses the window area
+  const size_t back = ((size_t)nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;   // back-substitution reuses the window area
   return fac > back ? fac : back;
 }
 size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
-  int maxlen = 0; for (int c = 0; c < pl.P; ++c) maxlen = std::max(maxlen, pl.b[c] - pl.a[c] + pl.w);
-  return ((size_t)pl.nbl + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128) * sizeof(double) + 64;
+  const int maxlen = pl.len + 1 + pl.w;
+  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128) * sizeof(double) + 64;
+}
+size_t smem_CR(const DeviceProblem& P, const SolvePlan& pl) {
+  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)2 * pl.w + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;
 }
 
-// Chunking of the knot columns.  The elimination cost per interior column is ~ constant, the reduced system has
-// (P-1) * kd sequential columns => P ~ sqrt(nk / kd).  Wide borders (bias splines active) keep P = 1: the left-separator
-// coupling would make the local border too large for shared memory.
+// Chunking of the knot columns.  A leaf costs ~ its interior length in sequential column eliminations, every cyclic-
+// reduction level ~ w = kd columns of a twice wider band plus two launches, so leaves of ~2.5 kd columns balance the two.
+// Wide borders (bias splines active) keep P = 1: the left-separator coupling would not fit the shared-memory window.
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 SolvePlan make_plan(const DeviceProblem& P) {
   SolvePlan pl; memset(&pl, 0, sizeof pl);
   const int nk = P.nk, kd = P.kd, nb = P.nb;
+  static const int forced_chunks = env_int("ICC_SOLVER_CHUNKS", 0), leaf_cols = env_int("ICC_SOLVER_LEAF", 0);
   int Pn = 1;
-  if (nk > 0 && kd > 0 && nb <= 16) { Pn = (int)std::lround(std::sqrt((double)nk / (double)(kd + 1))); Pn = std::max(1, std::min(Pn, MAX_CHUNKS)); while (Pn > 1 && (nk - (Pn - 1) * kd) / Pn < 2 * (kd + 1)) --Pn; }
-  pl.P = Pn; pl.w = Pn > 1 ? kd : 0;
-  const int interior_total = nk - (Pn - 1) * pl.w;
-  int pos = 0;
-  for (int c = 0; c < Pn; ++c) { const int len = interior_total / Pn + (c < interior_total % Pn ? 1 : 0); pl.a[c] = pos; pl.b[c] = pos + len; pos += len + pl.w; }
-  pl.nkr = (Pn - 1) * pl.w; pl.kdr = Pn > 1 ? 2 * pl.w - 1 : 0; pl.ldbr = pl.kdr + 1;
-  pl.nbl = pl.w + nb + 1;
-  pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_B = pow2_at_least(pl.kdr + 2 * KB + 1);
-  // grow the windows while they fit comfortably (larger panels amortise the panel load/store)
-  while (pl.WS_A < 256) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 200 * 1024) break; pl = t; }
-  while (pl.WS_B < 256) { SolvePlan t = pl; t.WS_B *= 2; if (smem_B(P, t) > 200 * 1024) break; pl = t; }
+  if (nk > 0 && kd > 0) {
+    const int target = leaf_cols > 0 ? leaf_cols : (5 * (kd + 1)) / 2;
+    Pn = (nk + kd) / (target + kd);
+    if (forced_chunks > 0) Pn = forced_chunks;
+    Pn = std::max(1, std::min(Pn, 1 << (MAX_LEVELS - 1)));
+    while (Pn > 1 && (nk - (Pn - 1) * kd) / Pn < kd + 1) --Pn;
+  }
+  auto fill = [&](int Pc) {
+    memset(&pl, 0, sizeof pl);
+    pl.P = Pc; pl.w = Pc > 1 ? kd : 0;
+    const int interior_total = nk - (Pc - 1) * pl.w;
+    pl.len = interior_total / Pc; pl.rem = interior_total % Pc;
+    pl.kdr = Pc > 1 ? 2 * pl.w - 1 : 0; pl.ldbr = pl.kdr + 1;
+    pl.nbl = pl.w + nb + 1;
+    int l = 1, Sl = Pc - 1, off = 0;
+    pl.S[1] = Sl; pl.off[1] = 0;
+    while (Sl > 1) { off += Sl * pl.w; Sl /= 2; ++l; pl.S[l] = Sl; pl.off[l] = off; }
+    pl.L = l - 1; pl.nkr_total = off + Sl * pl.w;
+    pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_R = pow2_at_least(pl.kdr + 2 * KB + 1); pl.WS_B = pl.WS_R;
+  };
+  fill(Pn);
+  if (Pn > 1 && (smem_A(P, pl) > 200 * 1024 || smem_R(P, pl) > 200 * 1024 || smem_B(P, pl) > 200 * 1024)) fill(1);
+  // grow the level-0 window while it fits comfortably (larger column groups amortise the group load/store)
+  while (pl.WS_A < 256 && pl.WS_A < pl.len + 1 + kd + 2 * KB) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 200 * 1024) break; pl = t; }
   return pl;
 }
 
@@ -667,21 +792,31 @@ void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, dou
 void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st) {
   const SolvePlan pl = make_plan(P);
   const SolveWs ws = carve(workspace, P.nk, P.nb, P.ldb, pl);
-  static size_t cfgA = 0, cfgB = 0, cfgC = 0;
-  const size_t sA = smem_A(P, pl), sB = smem_B(P, pl), sC = smem_C(P, pl);
-  if (sA > cfgA) { cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sA); cfgA = sA; }
+  static size_t cfgA = 0, cfgR = 0, cfgB = 0, cfgC = 0, cfgCR = 0;
+  const size_t sA = smem_A(P, pl), sR = smem_R(P, pl), sB = smem_B(P, pl), sC = smem_C(P, pl), sCR = smem_CR(P, pl);
+  if (sA > cfgA) { cudaFuncSetAttribute(eliminate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sA); cfgA = sA; }
+  if (sR > cfgR) { cudaFuncSetAttribute(eliminate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sR); cfgR = sR; }
   if (sB > cfgB) { cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sB); cfgB = sB; }
-  if (sC > cfgC) { cudaFuncSetAttribute(chunk_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sC); cfgC = sC; }
+  if (sC > cfgC) { cudaFuncSetAttribute(backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sC); cfgC = sC; }
+  if (sCR > cfgCR) { cudaFuncSetAttribute(backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sCR); cfgCR = sCR; }
   cudaMemsetAsync(ws.bandr, 0, ws.reduced_doubles * sizeof(double), st);
   if (P.nk > 0) {
-    prepare_kernel<<<dim3(pl.P, 16), 256, 0, st>>>(P, pl, scale, sp, workspace); count_launch();
-    chunk_factor_kernel<<<pl.P, NT, sA, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
+    prepare_kernel<<<dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st>>>(P, pl, scale, sp, workspace); count_launch();
+    eliminate_kernel<true><<<pl.P, NT, sA, st>>>(P, pl, 0, workspace, scal); count_launch();
+    for (int l = 1; l <= pl.L; ++l) { eliminate_kernel<false><<<(pl.S[l] + 1) / 2, NT, sR, st>>>(P, pl, l, workspace, scal); count_launch(); }
   }
   reduced_solve_kernel<<<1, NT, sB, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
-  if (P.nk > 0) { chunk_backsub_kernel<<<pl.P, 256, sC, st>>>(P, pl, workspace, scal); count_launch(); }
+  if (P.nk > 0) {
+    for (int l = pl.L; l >= 1; --l) { backsub_kernel<false><<<(pl.S[l] + 1) / 2, NT, sCR, st>>>(P, pl, l, workspace, scal); count_launch(); }
+    backsub_kernel<true><<<pl.P, NT, sC, st>>>(P, pl, 0, workspace, scal); count_launch();
+  }
   const int n = P.nk + P.nb;
   int grid = (n + 255) / 256; if (grid > 148) grid = 148; if (grid < 1) grid = 1;
   finish_kernel<<<grid, 256, 0, st>>>(P, pl, scale, sp, workspace, delta, scal); count_launch();
+#ifdef ICC_SOLVER_TRACE
+  { cudaStreamSynchronize(st); long long t[64]; cudaMemcpyFromSymbol(t, g_trace, sizeof t);
+    for (int k = 0; k < 2; ++k) { printf("trace %s:", k ? "level1" : "level0"); for (int i = 1; i <= 6; ++i) printf(" %lld", t[16 * k + i] - t[16 * k + i - 1]); printf(" cycles (P=%d len=%d L=%d) | phase1 %lld panelfactor %lld phase2 %lld trailing-rest %lld\n", pl.P, pl.len, pl.L, t[16 * k + 8], t[16 * k + 9], t[16 * k + 10], t[16 * k + 11]); } }
+#endif
 }
 
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st) {

@@ -32,13 +32,6 @@ void count_launch();
 namespace {
 
 constexpr int NT = 512;          // threads of the factorisation kernels
-#ifdef ICC_SOLVER_TRACE
-__device__ long long g_trace[64];
-__device__ int g_trace_slot = -1;   // set per kernel by thread 0 of CTA 0
-#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && g_trace_base >= 0) g_trace[g_trace_base + (i)] = clock64(); } while (0)
-#else
-#define TR(i) do { } while (0)
-#endif
 constexpr int MAX_LEVELS = 12;
 
 struct SolvePlan {
@@ -107,7 +100,7 @@ __device__ int build_block_table(uchar2* blocks, int M) {   // the nbk blocks of
   }
   return n;
 }
-struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; int trace; };   // Ld, inv: double-buffered by panel parity
+struct FactorSmem { double* W; double* Cl; uchar2* blocks; int nblocks; double* Ld; double* inv; int* flag; int nbl; };   // Ld, inv: double-buffered by panel parity
 
 // (a)+(b) of one panel, executed by ONE warp (no block-wide barrier inside):
 //   (a) lane 0 factors the KB x KB diagonal block in registers (unit-lower l, pivots D -> inv), kb <= KB columns are pivots;
@@ -230,9 +223,6 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
   const int tid = threadIdx.x, nt = blockDim.x, mask = WS - 1, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int PB = ((WS - kd - KB) / KB) * KB, M = kd + fs.nbl, ncol0 = (M + 7) / 8;   // ncol0 = blocks with bj == 0
   double* W = fs.W;
-#ifdef ICC_SOLVER_TRACE
-  const int g_trace_base = fs.trace;
-#endif
   if (tid == 0) *fs.flag = 1;
   for (int j0 = j_begin; j0 < j_end; j0 += PB) {
     const int gend = min(j0 + PB, j_end);
@@ -254,46 +244,21 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
       }
     }
     __syncthreads();
-    TR(2);
     if (warp < PW) panel_factor_warp(fs, j0, min(KB, gend - j0), kd, ldbp, CL, mask, 0);   // prologue: first panel of the group
     __syncthreads();
-    TR(3);
     if (*fs.flag == 0) return false;                            // uniform
     int buf = 0;
-#ifdef ICC_SOLVER_TRACE
-    long long acc1 = 0, acc2 = 0, acc3 = 0, tq0 = 0, tq1 = 0;
-#endif
     for (int jp = j0; jp < gend; jp += KB, buf ^= 1) {
       const bool has_next = jp + KB < gend;
-#ifdef ICC_SOLVER_TRACE
-      tq0 = clock64();
-#endif
       trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, 0, ncol0, warp, nwarps);
       __syncthreads();
-#ifdef ICC_SOLVER_TRACE
-      tq1 = clock64(); acc1 += tq1 - tq0;
-#endif
       if (warp < PW) { if (has_next) panel_factor_warp(fs, jp + KB, min(KB, gend - jp - KB), kd, ldbp, CL, mask, buf ^ 1); }
       if (warp >= PW || !has_next) trailing_blocks(fs, jp, kd, ldbp, CL, mask, buf, ncol0, fs.nblocks, has_next ? warp - PW : warp, has_next ? nwarps - PW : nwarps);
-#ifdef ICC_SOLVER_TRACE
-      acc2 += clock64() - tq1;
-#endif
       __syncthreads();
-#ifdef ICC_SOLVER_TRACE
-      acc3 += clock64() - tq1;
-#endif
       if (*fs.flag == 0) return false;                          // uniform
     }
-#ifdef ICC_SOLVER_TRACE
-    if (blockIdx.x == 0 && g_trace_base >= 0) {
-      if (tid == 0) { g_trace[g_trace_base + 8] = acc1; g_trace[g_trace_base + 9] = acc2; g_trace[g_trace_base + 10] = acc3; }
-      if (tid == PW * 32) { g_trace[g_trace_base + 11] = acc2; }
-    }
-#endif
-    TR(4);
     for (int col = j0 + warp; col < gend; col += nwarps) { const double* src = W + (size_t)(col & mask) * CL; for (int e = lane; e < CL; e += 32) store(col, e, src[e]); }
     __syncthreads();
-    TR(5);
   }
   return true;
 }
@@ -392,6 +357,163 @@ __host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int
   return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + 2 * KB + 2 * KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
 }
 
+// ---- dense front elimination (cyclic-reduction levels and the root) ------------------------------------------------
+// A front is the dense column panel of one separator block: rows [own block (w) | trailing rows (mt)], columns = the w pivots,
+// column-major in shared memory with zero padding (rows to a multiple of 8 past the own block, columns to a multiple of 4),
+// unscaled storage as in the band factor (diagonal = D_j, below = L_ij D_j).  The panel is factored in sub-panels of KB
+// columns (one lane factors the KB x KB block in registers, PWD warps substitute the rows below, all warps apply the rank-KB
+// update to the remaining panel columns on the tensor cores); the Schur complement of the trailing rows is then formed in ONE
+// pass with register accumulators over all w pivots and handed, entry by entry, to a sink (atomics into the next level / the
+// root's border block).
+constexpr int PWD = 4;
+struct DenseFront { double* Pn; int ld, w, mt, MF, rows; double* inv; double* Ld; int* flag; };   // MF = w + mt, rows = allocated (padded) rows
+__host__ __device__ inline int front_rows(int w, int mt) { return w + ((mt + 7) & ~7); }
+__host__ __device__ inline int front_ld(int w, int mt) { return front_rows(w, mt) | 1; }
+__host__ __device__ inline int front_cols(int w) { return (w + KB - 1) / KB * KB; }
+__host__ __device__ inline size_t front_doubles(int w, int mt) { return (size_t)front_ld(w, mt) * front_cols(w) + front_cols(w) + KB * KB + 2; }
+__device__ DenseFront carve_front(double* sm, int w, int mt) {
+  DenseFront f; f.Pn = sm; f.w = w; f.mt = mt; f.MF = w + mt; f.rows = front_rows(w, mt); f.ld = front_ld(w, mt);
+  f.inv = f.Pn + (size_t)f.ld * front_cols(w); f.Ld = f.inv + front_cols(w); f.flag = reinterpret_cast<int*>(f.Ld + KB * KB);
+  return f;
+}
+
+// KB x KB diagonal block of a sub-panel, factored by ONE thread in registers (its own function: the 36 + 8 live doubles must not
+// compete with the caller's registers under the 128-register cap of a 512-thread CTA)
+__device__ __noinline__ void dense_block_factor(double* Pn, int ld, int j0, int kb, double* inv, double* Ld, int* flag) {
+  double a[KB][KB];
+  double* p0 = Pn + (size_t)j0 * ld + j0;
+#pragma unroll
+  for (int c = 0; c < KB; ++c)
+#pragma unroll
+    for (int r = 0; r < KB; ++r) if (r >= c) a[r][c] = p0[(size_t)c * ld + r];   // padding columns / rows are zero
+  bool ok = true;
+  // constant-trip loops with compile-time predicates only: the triangular loop nest otherwise leaves a[][] in local memory;
+  // column j is final once pivot j is known, so it is written back at once (keeps the live register set shrinking)
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    const double D = a[j][j];
+    const bool piv = j < kb;                                      // columns past the block end are no pivots: iv = 0 makes them inert
+    if (piv && (!(D > 0.0) || !isfinite(D))) ok = false;
+    const double iv = piv ? 1.0 / D : 0.0;
+#pragma unroll
+    for (int c = 0; c < KB; ++c) {
+      if (c > j) {
+        const double lcj = a[c][j] * iv;
+        Ld[c * KB + j] = lcj;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) if (i >= c) a[i][c] = fma(-a[i][j], lcj, a[i][c]);
+      }
+    }
+    if (piv) {
+      inv[j0 + j] = iv;
+#pragma unroll
+      for (int r = 0; r < KB; ++r) if (r >= j) p0[(size_t)j * ld + r] = a[r][j];
+    }
+  }
+  if (!ok) *flag = 0;
+}
+
+__device__ __forceinline__ void dense_subpanel_factor(const DenseFront& f, int j0, int kb) {   // warps 0..PWD-1
+  const int gl = threadIdx.x, ld = f.ld;
+  double* Pn = f.Pn; double* Ld = f.Ld;
+  if (gl == 0) dense_block_factor(Pn, ld, j0, kb, f.inv, Ld, f.flag);
+  asm volatile("bar.sync 1, %0;" :: "r"(PWD * 32) : "memory");
+  double lreg[KB * (KB - 1) / 2];
+  {
+    int q = 0;
+#pragma unroll
+    for (int c = 1; c < KB; ++c)
+#pragma unroll
+      for (int k = 0; k < c; ++k) lreg[q++] = Ld[c * KB + k];
+  }
+  for (int x = j0 + KB + gl; x < f.MF; x += PWD * 32) {
+    double wv[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c) wv[c] = c < kb ? Pn[(size_t)(j0 + c) * ld + x] : 0.0;
+    int q = 0;
+#pragma unroll
+    for (int c = 1; c < KB; ++c) {
+      double v = wv[c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) v = fma(-wv[k], lreg[q++], v);
+      wv[c] = v;
+      if (c < kb) Pn[(size_t)(j0 + c) * ld + x] = v;
+    }
+  }
+}
+
+// rank-KB update of the panel columns [c_begin, c_end) (c_begin = j0 + KB + multiple of 8) with the finished sub-panel at j0
+__device__ __forceinline__ void dense_panel_update(const DenseFront& f, int j0, int c_begin, int c_end, int wslot, int nslots) {
+  const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3, ld = f.ld;
+  double* Pn = f.Pn;
+  int idx = wslot;
+  for (int cs = c_begin; cs < c_end; cs += 8) {
+    const int nbr = (f.MF - cs + 7) / 8;                         // block rows from the diagonal block of this block column down
+    for (; idx < nbr; idx += nslots) {
+      const int xa = cs + 8 * idx + fr;                          // < f.rows (padding rows are zero)
+      double acc[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KB / 4; ++ks) {
+        const int jj = j0 + 4 * ks + fk;
+        const double* cj = Pn + (size_t)jj * ld;
+        dmma_acc(acc, -cj[xa] * f.inv[jj], cj[cs + fr]);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { const int y = cs + 2 * fk + e; if (y < f.w && xa >= y && xa < f.MF) Pn[(size_t)y * ld + xa] += acc[e]; }
+    }
+    idx -= nbr;
+  }
+}
+
+// sub-panel loop with a look-ahead of depth one: the next sub-panel's columns are updated first, then PWD warps factor it while
+// the other warps finish the update of the remaining panel columns
+__device__ bool dense_front_factor(const DenseFront& f) {
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, w = f.w;
+  if (warp < PWD) dense_subpanel_factor(f, 0, min(KB, w));
+  __syncthreads();
+  if (*f.flag == 0) return false;
+  for (int j0 = 0; j0 + KB < w; j0 += KB) {
+    dense_panel_update(f, j0, j0 + KB, min(j0 + 2 * KB, w), warp, nwarps);
+    __syncthreads();
+    if (warp < PWD) dense_subpanel_factor(f, j0 + KB, min(KB, w - j0 - KB));
+    else dense_panel_update(f, j0, j0 + 2 * KB, w, warp - PWD, nwarps - PWD);
+    __syncthreads();
+    if (*f.flag == 0) return false;
+  }
+  return true;
+}
+
+// Schur complement of the trailing rows: sink(x, y, v) receives v = -sum_j L_xj D_j L_yj for mt > x >= y >= 0
+template <class Sink>
+__device__ __forceinline__ void dense_front_schur(const DenseFront& f, Sink sink) {
+  const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, ld = f.ld;
+  const int nbt = (f.mt + 7) / 8, nblk = nbt * (nbt + 1) / 2, ksteps = (f.w + 3) / 4;
+  const double* T = f.Pn + f.w;                                  // trailing rows of every column
+  for (int b = warp; b < nblk; b += nwarps) {
+    const int bi = tri_row(b), bj = b - bi * (bi + 1) / 2;
+    const int xa = 8 * bi + fr, xb = 8 * bj + fr;
+    double acc[2] = {0.0, 0.0};
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int jj = 4 * ks + fk;                                // columns >= w are zero padding with inv = 0
+      const double* cj = T + (size_t)jj * ld;
+      dmma_acc(acc, -cj[xa] * f.inv[jj], cj[xb]);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { const int y = 8 * bj + 2 * fk + e; if (xa >= y && xa < f.mt) sink(xa, y, acc[e]); }
+  }
+}
+
+// factor columns -> global factor storage shared with the band back-substitution: Lb[col][e] (e = 0: pivot; own rows, then
+// the right block) and El[col][left | border | rhs]; trailing row order of a front: [left (wl) | right (wr) | border + rhs]
+__device__ void dense_front_store(const DenseFront& f, int wl, int wr, int nbp, double* Lb, int ldb, int kd, double* El, int nbl) {
+  const int w = f.w, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < w; j += nwarps) {
+    const double* cj = f.Pn + (size_t)j * f.ld;
+    for (int e = lane; e <= kd; e += 32) { const int r = j + e; Lb[(int64_t)j * ldb + e] = r < w ? cj[r] : (r - w < wr ? cj[w + wl + (r - w)] : 0.0); }
+    for (int i = lane; i < nbl; i += 32) El[(int64_t)j * nbl + i] = i < w ? (i < wl ? cj[w + i] : 0.0) : cj[w + wl + wr + (i - w)];
+  }
+}
+
 // ---- kernel A0: materialise the scaled + damped window columns of every chunk (fully parallel) ----------------------
 // Wg[col][e]: e < ldbp band entries (zero padding beyond kd, rows beyond the chunk's right separator masked), then the local
 // border [coupling to the left separator (stored transposed in H) | border | rhs].  Kernel A then only copies columns.
@@ -421,55 +543,29 @@ __global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __re
   }
 }
 
-// ---- elimination kernel: level 0 = interior knots of every time chunk ; level >= 1 = every other separator block -----
-template <bool LEVEL0>
-__global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, double* scal) {
+// ---- level 0: eliminate the interior knots of every time chunk ----------------------------------------------------
+__global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePlan pl, double* wsp, double* scal) {
   extern __shared__ __align__(16) double sm[];
-  const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, nbp = nb + 1;
+  const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, nbp = nb + 1, kd = P.kd, ldb = P.ldb;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
-#ifdef ICC_SOLVER_TRACE
-  const int g_trace_base = LEVEL0 ? 0 : (level == 1 ? 16 : -1);
-#endif
-  TR(0);
-  if (!LEVEL0 && scal[SC_OK] < 0.0) return;                     // an earlier level hit a bad pivot (uniform)
-  int a, b, kd, ldb; bool has_left, has_right;
-  const double* src_band = nullptr; const double* src_E = nullptr; double* dst_Lb; double* dst_El;
-  if (LEVEL0) {
-    a = chunk_a(pl, c); b = chunk_b(pl, c); kd = P.kd; ldb = P.ldb; has_left = c > 0; has_right = c < pl.P - 1;
-    dst_Lb = ws.Lb; dst_El = ws.El;
-  } else {
-    const int o = pl.off[level];
-    a = 2 * c * w; b = a + w; kd = pl.kdr; ldb = pl.ldbr; has_left = c > 0; has_right = 2 * c + 1 < pl.S[level];
-    src_band = ws.bandr + (int64_t)o * ldb; src_E = ws.Er + (int64_t)o * nbp;
-    dst_Lb = ws.Lbr + (int64_t)o * ldb; dst_El = ws.Elr + (int64_t)o * nbl;
-  }
-  const int ldbp = kd + KB, CL = ldbp + nbl, WS = LEVEL0 ? pl.WS_A : pl.WS_R;
+  const int a = chunk_a(pl, c), b = chunk_b(pl, c);
+  const bool has_left = c > 0, has_right = c < pl.P - 1;
+  const int ldbp = kd + KB, CL = ldbp + nbl, WS = pl.WS_A;
   double* extra;
   FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
   double* W = fs.W; double* Cl = fs.Cl;
   fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
-#ifdef ICC_SOLVER_TRACE
-  fs.trace = g_trace_base;
-#endif
   __syncthreads();
-  TR(1);
   const int right_end = has_right ? b + w : b;
-  auto load = [&](int col, int e) -> double {
-    if (col >= right_end) return 0.0;
-    if (LEVEL0) return ws.Wg[(int64_t)col * CL + e];
-    if (e < ldbp) return (e <= kd && col + e < right_end) ? src_band[(int64_t)col * ldb + e] : 0.0;
-    const int lb = e - ldbp;
-    if (lb < w) { if (!has_left || col >= b) return 0.0; const int s = a - w + lb; return src_band[(int64_t)s * ldb + (col - s)]; }   // col - s <= 2w - 1 = kd
-    return src_E[(int64_t)col * nbp + (lb - w)];
-  };
-  auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) dst_Lb[(int64_t)col * ldb + e] = v; } else dst_El[(int64_t)col * nbl + (e - ldbp)] = v; };
+  auto load = [&](int col, int e) -> double { return col < right_end ? ws.Wg[(int64_t)col * CL + e] : 0.0; };
+  auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kd) ws.Lb[(int64_t)col * ldb + e] = v; } else ws.El[(int64_t)col * nbl + (e - ldbp)] = v; };
   const bool ok = factor_range(fs, a, b, kd, ldbp, CL, WS, load, store);
   if (!ok) { if (threadIdx.x == 0) scal[SC_OK] = -1.0; return; }
-  // ---- scatter the Schur complement into the next reduced system: the left / right neighbours become its blocks c-1 / c ----
+  // ---- scatter the Schur complement into the first reduced system: the left / right separators are its blocks c-1 / c ----
   const int mask = WS - 1;
   const int sl0 = (c - 1) * w, sr0 = c * w;
-  double* ob = ws.bandr + (int64_t)pl.off[level + 1] * pl.ldbr; double* oE = ws.Er + (int64_t)pl.off[level + 1] * nbp;
+  double* ob = ws.bandr; double* oE = ws.Er;
   if (has_right) {
     for (int idx = threadIdx.x; idx < w * CL; idx += blockDim.x) {
       const int t = idx / CL, e = idx % CL, col = b + t;
@@ -491,45 +587,103 @@ __global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePla
     else if (b2 < w) { if (has_left) atomicAdd(oE + (int64_t)(sl0 + b2) * nbp + (b1 - w), v); }
     else atomicAdd(ws.Cr + (int64_t)(b1 - w) * nbp + (b2 - w), v);
   }
-  __syncthreads();
-  TR(6);
 }
 
-// ---- root: last reduced system {remaining separator blocks + border}: factor, solve ----------------------------------
-__global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
+// ---- level l >= 1: cyclic reduction -- eliminate every other block of the block-tridiagonal system R_l ------------------
+// CTA c eliminates block 2c; its neighbours 2c-1 / 2c+1 become blocks c-1 / c of R_{l+1}.  Front rows: [own | left | right | border | rhs].
+__global__ void __launch_bounds__(NT) reduce_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, double* scal) {
   extern __shared__ __align__(16) double sm[];
-  const int nk = P.nk, nb = P.nb, nbp = nb + 1, root = pl.L + 1, nkr = pl.S[root] * pl.w, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w;
-  const int ldbp = kdr + KB, CL = ldbp + nbp, WS = pl.WS_B, tid = threadIdx.x, nt = blockDim.x;
-  double* xb;
-  FactorSmem fs = carve_smem(sm, WS, CL, nbp, kdr, ldbp, &xb, nbp + 1);
-  double* W = fs.W; double* Cs = fs.Cl;           // nbp x nbp lower, row nb = rhs
+  const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, nbp = nb + 1, ldb = pl.ldbr, kd = pl.kdr;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  if (scal[SC_OK] < 0.0) return;                                 // an earlier level hit a bad pivot (uniform)
+  SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
+  const int o = pl.off[level], a = 2 * c * w, b = a + w;
+  const bool has_left = c > 0, has_right = 2 * c + 1 < pl.S[level];
+  const double* src_band = ws.bandr + (int64_t)o * ldb; const double* src_E = ws.Er + (int64_t)o * nbp;
+  double* ob = ws.bandr + (int64_t)pl.off[level + 1] * ldb; double* oE = ws.Er + (int64_t)pl.off[level + 1] * nbp;
+  const int mt = 2 * w + nbp;
+  DenseFront f = carve_front(sm, w, mt);
+  for (int i = tid; i < (int)front_doubles(w, mt) - 2; i += nt) f.Pn[i] = 0.0;   // panel (with padding), inv, Ld
+  if (tid == 0) *f.flag = 1;
+  __syncthreads();
+  for (int j = warp; j < w; j += nwarps) {                       // gather the block column: 4 independent loads per lane
+    double* cj = f.Pn + (size_t)j * f.ld;
+    const double* bj = src_band + (int64_t)(a + j) * ldb;
+    for (int r = lane; r < f.MF; r += 32) {
+      double v = 0.0;
+      if (r < w) { if (r >= j) v = bj[r - j]; }
+      else if (r < 2 * w) { if (has_left) { const int lb = r - w; v = src_band[(int64_t)(a - w + lb) * ldb + (w + j - lb)]; } }
+      else if (r < 3 * w) { if (has_right) v = bj[r - w - j]; }   // row b + (r - 2w): offset w + (r - 2w) - j
+      else v = src_E[(int64_t)(a + j) * nbp + (r - 3 * w)];
+      cj[r] = v;
+    }
+  }
+  __syncthreads();
+  if (!dense_front_factor(f)) { if (tid == 0) scal[SC_OK] = -1.0; return; }
+  dense_front_store(f, w, w, nbp, ws.Lbr + (int64_t)(o + a) * ldb, ldb, kd, ws.Elr + (int64_t)(o + a) * nbl, nbl);
+  const int sl0 = (c - 1) * w, sr0 = c * w;
+  dense_front_schur(f, [&](int x, int y, double v) {             // trailing order [left | right | border | rhs], x >= y
+    if (y < w) {
+      if (!has_left) return;
+      if (x < w) atomicAdd(ob + (int64_t)(sl0 + y) * ldb + (x - y), v);
+      else if (x < 2 * w) { if (has_right) atomicAdd(ob + (int64_t)(sl0 + y) * ldb + (sr0 + (x - w) - sl0 - y), v); }
+      else atomicAdd(oE + (int64_t)(sl0 + y) * nbp + (x - 2 * w), v);
+    } else if (y < 2 * w) {
+      if (!has_right) return;
+      if (x < 2 * w) atomicAdd(ob + (int64_t)(sr0 + y - w) * ldb + (x - y), v);
+      else atomicAdd(oE + (int64_t)(sr0 + y - w) * nbp + (x - 2 * w), v);
+    } else atomicAdd(ws.Cr + (int64_t)(x - 2 * w) * nbp + (y - 2 * w), v);
+  });
+  if (has_right) {                                               // the right neighbour carries its own entries to the next level
+    for (int idx = tid; idx < w * (w + nbp); idx += nt) {
+      const int t = idx / (w + nbp), e = idx % (w + nbp);
+      if (e < w) { if (t + e < w) { const double v = src_band[(int64_t)(b + t) * ldb + e]; if (v != 0.0) atomicAdd(ob + (int64_t)(sr0 + t) * ldb + e, v); } }
+      else { const double v = src_E[(int64_t)(b + t) * nbp + (e - w)]; if (v != 0.0) atomicAdd(oE + (int64_t)(sr0 + t) * nbp + (e - w), v); }
+    }
+  }
+}
+
+// ---- root: last separator block (if any) + border: factor, solve ------------------------------------------------------
+__global__ void __launch_bounds__(NT) root_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
+  extern __shared__ __align__(16) double sm[];
+  const int nk = P.nk, nb = P.nb, nbp = nb + 1, root = pl.L + 1, nkr = pl.S[root] * pl.w, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w, nbl = pl.nbl;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  double* Cs = sm;                                 // nbp x nbp lower, row nb = rhs
+  double* xb = Cs + nbp * nbp;                     // border solution
+  double* rest = xb + ((nbp + 4) & ~3);            // dense front, later the back-substitution staging
   const double* C = P.ne + P.ne_off_C; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   const double* rband = ws.bandr + (int64_t)pl.off[root] * ldbr; const double* rE = ws.Er + (int64_t)pl.off[root] * nbp;
-  double* rLb = ws.Lbr + (int64_t)pl.off[root] * ldbr; double* rEl = ws.Elr + (int64_t)pl.off[root] * pl.nbl;   // used with row length nbp
+  double* rLb = ws.Lbr + (int64_t)pl.off[root] * ldbr; double* rEl = ws.Elr + (int64_t)pl.off[root] * nbl;
   if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // an elimination hit a bad pivot
-  if (nkr > 0) fs.nblocks = build_block_table(fs.blocks, kdr + nbp);
   for (int idx = tid; idx < nbp * nbp; idx += nt) {
     const int b = idx / nbp, c = idx % nbp;
     double v = 0.0;
     if (c <= b) {
-      v = ws.Cr[idx];                                                       // Schur contributions of all chunks
+      v = ws.Cr[idx];                                                       // Schur contributions of all levels
       if (b < nb) { v += C[(int64_t)b * nb + c] * scale[nk + b] * scale[nk + c]; if (b == c) v += lm_d2(P, scale, sp, nk + b); }
       else if (c < nb) v += -g[nk + c] * scale[nk + c];
     }
     Cs[idx] = v;
   }
-  __syncthreads();
   bool ok = true;
-  if (nkr > 0) {
-    auto load = [&](int col, int e) -> double {
-      if (col >= nkr) return 0.0;
-      if (e < ldbp) return (e <= kdr && col + e < nkr) ? rband[(int64_t)col * ldbr + e] : 0.0;
-      return rE[(int64_t)col * nbp + (e - ldbp)];
-    };
-    auto store = [&](int col, int e, double v) { if (e < ldbp) { if (e <= kdr) rLb[(int64_t)col * ldbr + e] = v; } else rEl[(int64_t)col * nbp + (e - ldbp)] = v; };
-    ok = factor_range(fs, 0, nkr, kdr, ldbp, CL, WS, load, store);
+  if (nkr > 0) {                                   // one remaining block: front rows [own | border | rhs]
+    DenseFront f = carve_front(rest, w, nbp);
+    for (int i = tid; i < (int)front_doubles(w, nbp) - 2; i += nt) f.Pn[i] = 0.0;
+    if (tid == 0) *f.flag = 1;
+    __syncthreads();
+    for (int j = warp; j < w; j += nwarps) {
+      double* cj = f.Pn + (size_t)j * f.ld;
+      for (int r = lane; r < f.MF; r += 32) cj[r] = r < w ? (r >= j ? rband[(int64_t)j * ldbr + (r - j)] : 0.0) : rE[(int64_t)j * nbp + (r - w)];
+    }
+    __syncthreads();
+    ok = dense_front_factor(f);
+    if (ok) {
+      dense_front_store(f, 0, 0, nbp, rLb, ldbr, kdr, rEl, nbl);
+      dense_front_schur(f, [&](int x, int y, double v) { Cs[x * nbp + y] += v; });
+    }
   }
+  __syncthreads();
   // border: dense LDL^T of the final Schur complement, rhs carried as the last row
   for (int j = 0; j < nb && ok; ++j) {
     const double piv = Cs[j * nbp + j];
@@ -558,12 +712,12 @@ __global__ void __launch_bounds__(NT) reduced_solve_kernel(DeviceProblem P, Solv
   __syncthreads();
   for (int b = tid; b < nb; b += nt) ws.y[nk + b] = xb[b];
   if (nkr > 0) {
-    // separators: t_j = rhs_j - sum_b Elr[j][b] x_b, then the register/shuffle back-substitution
-    double* tw = W; double* Bw = W + ((nkr + 3) & ~3);
-    for (int j = tid; j < nkr; j += nt) { const double* le = rEl + (int64_t)j * nbp; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; tw[j] = t; }
+    // remaining block: t_j = rhs_j - sum_b El[j][border b] x_b, then the register/shuffle back-substitution
+    double* tw = rest; double* Bw = rest + ((nkr + 3) & ~3);
+    for (int j = tid; j < nkr; j += nt) { const double* le = rEl + (int64_t)j * nbl + w; double t = le[nb]; for (int b = 0; b < nb; ++b) t -= le[b] * xb[b]; tw[j] = t; }
     __syncthreads();
     backsub_dispatch(rLb, tw, Bw, 0, nkr, nkr, kdr, ldbr, 64);
-    for (int rj = tid; rj < nkr; rj += nt) { const int k = rj / w, tt = rj % w; ws.y[sep_col(pl, root, k) + tt] = tw[rj]; }
+    for (int rj = tid; rj < nkr; rj += nt) ws.y[sep_col(pl, root, 0) + rj] = tw[rj];
   }
   __syncthreads();
   if (tid == 0) scal[SC_OK] = 1.0;
@@ -724,12 +878,12 @@ __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand
 int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_A, P.kd + KB + pl.nbl, pl.nbl, P.kd, 0); }
-size_t smem_R(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_R, pl.kdr + KB + pl.nbl, pl.nbl, pl.kdr, 0); }
+size_t smem_R(const DeviceProblem& P, const SolvePlan& pl) { return front_doubles(pl.w, 2 * pl.w + P.nb + 1) * sizeof(double) + 64; }
 size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
   const int nbp = P.nb + 1, nkr = pl.S[pl.L + 1] * pl.w;
-  const size_t fac = factor_smem_bytes(pl.WS_B, pl.kdr + KB + nbp, nbp, pl.kdr, nbp + 1);
-  const size_t back = ((size_t)nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;   // back-substitution reuses the window area
-  return fac > back ? fac : back;
+  const size_t fac = nkr > 0 ? front_doubles(pl.w, nbp) : 0;
+  const size_t back = nkr > 0 ? (size_t)nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64 : 0;   // back-substitution reuses the front area
+  return ((size_t)nbp * nbp + nbp + 8 + (fac > back ? fac : back)) * sizeof(double) + 64;
 }
 size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
   const int maxlen = pl.len + 1 + pl.w;
@@ -766,7 +920,7 @@ SolvePlan make_plan(const DeviceProblem& P) {
     pl.S[1] = Sl; pl.off[1] = 0;
     while (Sl > 1) { off += Sl * pl.w; Sl /= 2; ++l; pl.S[l] = Sl; pl.off[l] = off; }
     pl.L = l - 1; pl.nkr_total = off + Sl * pl.w;
-    pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_R = pow2_at_least(pl.kdr + 2 * KB + 1); pl.WS_B = pl.WS_R;
+    pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_R = pl.WS_B = 0;
   };
   fill(Pn);
   if (Pn > 1 && (smem_A(P, pl) > 200 * 1024 || smem_R(P, pl) > 200 * 1024 || smem_B(P, pl) > 200 * 1024)) fill(1);
@@ -794,18 +948,18 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   const SolveWs ws = carve(workspace, P.nk, P.nb, P.ldb, pl);
   static size_t cfgA = 0, cfgR = 0, cfgB = 0, cfgC = 0, cfgCR = 0;
   const size_t sA = smem_A(P, pl), sR = smem_R(P, pl), sB = smem_B(P, pl), sC = smem_C(P, pl), sCR = smem_CR(P, pl);
-  if (sA > cfgA) { cudaFuncSetAttribute(eliminate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sA); cfgA = sA; }
-  if (sR > cfgR) { cudaFuncSetAttribute(eliminate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sR); cfgR = sR; }
-  if (sB > cfgB) { cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sB); cfgB = sB; }
+  if (sA > cfgA) { cudaFuncSetAttribute(eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sA); cfgA = sA; }
+  if (sR > cfgR) { cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sR); cfgR = sR; }
+  if (sB > cfgB) { cudaFuncSetAttribute(root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sB); cfgB = sB; }
   if (sC > cfgC) { cudaFuncSetAttribute(backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sC); cfgC = sC; }
   if (sCR > cfgCR) { cudaFuncSetAttribute(backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sCR); cfgCR = sCR; }
   cudaMemsetAsync(ws.bandr, 0, ws.reduced_doubles * sizeof(double), st);
   if (P.nk > 0) {
     prepare_kernel<<<dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st>>>(P, pl, scale, sp, workspace); count_launch();
-    eliminate_kernel<true><<<pl.P, NT, sA, st>>>(P, pl, 0, workspace, scal); count_launch();
-    for (int l = 1; l <= pl.L; ++l) { eliminate_kernel<false><<<(pl.S[l] + 1) / 2, NT, sR, st>>>(P, pl, l, workspace, scal); count_launch(); }
+    eliminate_kernel<<<pl.P, NT, sA, st>>>(P, pl, workspace, scal); count_launch();
+    for (int l = 1; l <= pl.L; ++l) { reduce_kernel<<<(pl.S[l] + 1) / 2, NT, sR, st>>>(P, pl, l, workspace, scal); count_launch(); }
   }
-  reduced_solve_kernel<<<1, NT, sB, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
+  root_kernel<<<1, NT, sB, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
   if (P.nk > 0) {
     for (int l = pl.L; l >= 1; --l) { backsub_kernel<false><<<(pl.S[l] + 1) / 2, NT, sCR, st>>>(P, pl, l, workspace, scal); count_launch(); }
     backsub_kernel<true><<<pl.P, NT, sC, st>>>(P, pl, 0, workspace, scal); count_launch();
@@ -813,10 +967,6 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   const int n = P.nk + P.nb;
   int grid = (n + 255) / 256; if (grid > 148) grid = 148; if (grid < 1) grid = 1;
   finish_kernel<<<grid, 256, 0, st>>>(P, pl, scale, sp, workspace, delta, scal); count_launch();
-#ifdef ICC_SOLVER_TRACE
-  { cudaStreamSynchronize(st); long long t[64]; cudaMemcpyFromSymbol(t, g_trace, sizeof t);
-    for (int k = 0; k < 2; ++k) { printf("trace %s:", k ? "level1" : "level0"); for (int i = 1; i <= 6; ++i) printf(" %lld", t[16 * k + i] - t[16 * k + i - 1]); printf(" cycles (P=%d len=%d L=%d) | phase1 %lld panelfactor %lld phase2 %lld trailing-rest %lld\n", pl.P, pl.len, pl.L, t[16 * k + 8], t[16 * k + 9], t[16 * k + 10], t[16 * k + 11]); } }
-#endif
 }
 
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st) {

@@ -32,6 +32,24 @@ void count_launch();
 namespace {
 
 constexpr int NT = 512;          // threads of the factorisation kernels
+
+// Programmatic dependent launch: every solver kernel is launched with programmatic stream serialisation, does the work that
+// does not depend on its predecessor (shared-memory set-up, zero fill) first, then waits for the predecessor's results.  The
+// "launch dependents" trigger is issued right AFTER the wait, so when a kernel starts, everything older than its direct
+// predecessor is already complete and visible.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 constexpr int MAX_LEVELS = 12;
 
 struct SolvePlan {
@@ -63,7 +81,7 @@ __host__ __device__ inline SolveWs carve(double* ws, int nk, int nb, int ldb, co
 }
 
 __device__ __forceinline__ int tri_row(int idx) {   // idx = r(r+1)/2 + c, 0 <= c <= r  ->  r
-  int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+  int r = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);   // estimate, made exact by the two loops
   while ((r + 1) * (r + 2) / 2 <= idx) ++r;
   while (r * (r + 1) / 2 > idx) --r;
   return r;
@@ -492,12 +510,19 @@ __device__ __forceinline__ void dense_front_schur(const DenseFront& f, Sink sink
   for (int b = warp; b < nblk; b += nwarps) {
     const int bi = tri_row(b), bj = b - bi * (bi + 1) / 2;
     const int xa = 8 * bi + fr, xb = 8 * bj + fr;
-    double acc[2] = {0.0, 0.0};
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const int jj = 4 * ks + fk;                                // columns >= w are zero padding with inv = 0
-      const double* cj = T + (size_t)jj * ld;
-      dmma_acc(acc, -cj[xa] * f.inv[jj], cj[xb]);
+    // three independent accumulator chains; columns >= w are zero padding with inv = 0
+    double acc[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
+    const double* cj = T + (size_t)fk * ld;
+    const double* iv = f.inv + fk;
+    int ks = 0;
+    for (; ks + 3 <= ksteps; ks += 3, cj += 12 * (size_t)ld, iv += 12) {
+      const double a0 = cj[xa], b0 = cj[xb], i0 = iv[0];
+      const double a1 = cj[4 * (size_t)ld + xa], b1 = cj[4 * (size_t)ld + xb], i1 = iv[4];
+      const double a2 = cj[8 * (size_t)ld + xa], b2 = cj[8 * (size_t)ld + xb], i2 = iv[8];
+      dmma_acc(acc, -a0 * i0, b0); dmma_acc(acc1, -a1 * i1, b1); dmma_acc(acc2, -a2 * i2, b2);
     }
+    for (; ks < ksteps; ++ks, cj += 4 * (size_t)ld, iv += 4) dmma_acc(acc, -cj[xa] * iv[0], cj[xb]);
+    acc[0] += acc1[0] + acc2[0]; acc[1] += acc1[1] + acc2[1];
 #pragma unroll
     for (int e = 0; e < 2; ++e) { const int y = 8 * bj + 2 * fk + e; if (xa >= y && xa < f.mt) sink(xa, y, acc[e]); }
   }
@@ -524,6 +549,7 @@ __global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __re
   const int ldbp = kd + KB, CL = ldbp + nbl, right_end = has_right ? b + w : b;
   const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
+  pdl_wait_then_trigger();
   const int total = (right_end - a) * CL, stride = gridDim.y * blockDim.x, de = stride % CL, dc = stride / CL;
   const int idx0 = blockIdx.y * blockDim.x + threadIdx.x;
   int e = idx0 % CL, col = a + idx0 / CL;
@@ -556,6 +582,7 @@ __global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePla
   double* W = fs.W; double* Cl = fs.Cl;
   fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
+  pdl_wait_then_trigger();
   __syncthreads();
   const int right_end = has_right ? b + w : b;
   auto load = [&](int col, int e) -> double { return col < right_end ? ws.Wg[(int64_t)col * CL + e] : 0.0; };
@@ -595,7 +622,6 @@ __global__ void __launch_bounds__(NT) reduce_kernel(DeviceProblem P, SolvePlan p
   extern __shared__ __align__(16) double sm[];
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, nbp = nb + 1, ldb = pl.ldbr, kd = pl.kdr;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  if (scal[SC_OK] < 0.0) return;                                 // an earlier level hit a bad pivot (uniform)
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   const int o = pl.off[level], a = 2 * c * w, b = a + w;
   const bool has_left = c > 0, has_right = 2 * c + 1 < pl.S[level];
@@ -605,23 +631,45 @@ __global__ void __launch_bounds__(NT) reduce_kernel(DeviceProblem P, SolvePlan p
   DenseFront f = carve_front(sm, w, mt);
   for (int i = tid; i < (int)front_doubles(w, mt) - 2; i += nt) f.Pn[i] = 0.0;   // panel (with padding), inv, Ld
   if (tid == 0) *f.flag = 1;
+  pdl_wait_then_trigger();
+  if (scal[SC_OK] < 0.0) return;                                 // an earlier level hit a bad pivot (uniform)
   __syncthreads();
-  for (int j = warp; j < w; j += nwarps) {                       // gather the block column: 4 independent loads per lane
-    double* cj = f.Pn + (size_t)j * f.ld;
+  const int sl0 = (c - 1) * w, sr0 = c * w;
+  auto fetch = [&](int j, int r) -> double {                     // entry (row r, pivot column j) of the front
+    if (r >= f.MF) return 0.0;
     const double* bj = src_band + (int64_t)(a + j) * ldb;
-    for (int r = lane; r < f.MF; r += 32) {
-      double v = 0.0;
-      if (r < w) { if (r >= j) v = bj[r - j]; }
-      else if (r < 2 * w) { if (has_left) { const int lb = r - w; v = src_band[(int64_t)(a - w + lb) * ldb + (w + j - lb)]; } }
-      else if (r < 3 * w) { if (has_right) v = bj[r - w - j]; }   // row b + (r - 2w): offset w + (r - 2w) - j
-      else v = src_E[(int64_t)(a + j) * nbp + (r - 3 * w)];
-      cj[r] = v;
+    if (r < w) return r >= j ? bj[r - j] : 0.0;
+    if (r < 2 * w) { const int lb = r - w; return has_left ? src_band[(int64_t)(a - w + lb) * ldb + (w + j - lb)] : 0.0; }
+    if (r < 3 * w) return has_right ? bj[r - w - j] : 0.0;       // row b + (r - 2w): offset w + (r - 2w) - j
+    return src_E[(int64_t)(a + j) * nbp + (r - 3 * w)];
+  };
+  for (int j = warp; j < w; j += nwarps) {                       // gather the block column, 4 independent loads per lane in flight
+    double* cj = f.Pn + (size_t)j * f.ld;
+    for (int r0 = lane; r0 < f.MF; r0 += 128) {
+      const double v0 = fetch(j, r0), v1 = fetch(j, r0 + 32), v2 = fetch(j, r0 + 64), v3 = fetch(j, r0 + 96);
+      cj[r0] = v0; if (r0 + 32 < f.MF) cj[r0 + 32] = v1; if (r0 + 64 < f.MF) cj[r0 + 64] = v2; if (r0 + 96 < f.MF) cj[r0 + 96] = v3;
+    }
+  }
+  if (has_right) {                                               // the right neighbour carries its own entries to the next level
+    const int rw = w + nbp, tot = w * rw;
+    for (int base = tid; base < tot; base += 4 * nt) {
+      double v[4]; double* dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * nt; v[u] = 0.0; dst[u] = nullptr;
+        if (idx < tot) {
+          const int t = idx / rw, e = idx % rw;
+          if (e < w) { if (t + e < w) { v[u] = src_band[(int64_t)(b + t) * ldb + e]; dst[u] = ob + (int64_t)(sr0 + t) * ldb + e; } }
+          else { v[u] = src_E[(int64_t)(b + t) * nbp + (e - w)]; dst[u] = oE + (int64_t)(sr0 + t) * nbp + (e - w); }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (dst[u] && v[u] != 0.0) atomicAdd(dst[u], v[u]);
     }
   }
   __syncthreads();
   if (!dense_front_factor(f)) { if (tid == 0) scal[SC_OK] = -1.0; return; }
   dense_front_store(f, w, w, nbp, ws.Lbr + (int64_t)(o + a) * ldb, ldb, kd, ws.Elr + (int64_t)(o + a) * nbl, nbl);
-  const int sl0 = (c - 1) * w, sr0 = c * w;
   dense_front_schur(f, [&](int x, int y, double v) {             // trailing order [left | right | border | rhs], x >= y
     if (y < w) {
       if (!has_left) return;
@@ -634,13 +682,6 @@ __global__ void __launch_bounds__(NT) reduce_kernel(DeviceProblem P, SolvePlan p
       else atomicAdd(oE + (int64_t)(sr0 + y - w) * nbp + (x - 2 * w), v);
     } else atomicAdd(ws.Cr + (int64_t)(x - 2 * w) * nbp + (y - 2 * w), v);
   });
-  if (has_right) {                                               // the right neighbour carries its own entries to the next level
-    for (int idx = tid; idx < w * (w + nbp); idx += nt) {
-      const int t = idx / (w + nbp), e = idx % (w + nbp);
-      if (e < w) { if (t + e < w) { const double v = src_band[(int64_t)(b + t) * ldb + e]; if (v != 0.0) atomicAdd(ob + (int64_t)(sr0 + t) * ldb + e, v); } }
-      else { const double v = src_E[(int64_t)(b + t) * nbp + (e - w)]; if (v != 0.0) atomicAdd(oE + (int64_t)(sr0 + t) * nbp + (e - w), v); }
-    }
-  }
 }
 
 // ---- root: last separator block (if any) + border: factor, solve ------------------------------------------------------
@@ -655,6 +696,7 @@ __global__ void __launch_bounds__(NT) root_kernel(DeviceProblem P, SolvePlan pl,
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   const double* rband = ws.bandr + (int64_t)pl.off[root] * ldbr; const double* rE = ws.Er + (int64_t)pl.off[root] * nbp;
   double* rLb = ws.Lbr + (int64_t)pl.off[root] * ldbr; double* rEl = ws.Elr + (int64_t)pl.off[root] * nbl;
+  pdl_wait_then_trigger();
   if (scal[SC_OK] < 0.0) { if (tid == 0) { scal[SC_OK] = 0.0; scal[SC_MODEL_CHANGE] = 0.0; } return; }   // an elimination hit a bad pivot
   for (int idx = tid; idx < nbp * nbp; idx += nt) {
     const int b = idx / nbp, c = idx % nbp;
@@ -727,6 +769,7 @@ __global__ void __launch_bounds__(NT) root_kernel(DeviceProblem P, SolvePlan pl,
 template <bool LEVEL0>
 __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, const double* scal) {
   extern __shared__ __align__(16) double sm[];
+  pdl_wait_then_trigger();
   if (scal[SC_OK] != 1.0) return;
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, tid = threadIdx.x, nt = blockDim.x;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
@@ -766,6 +809,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan 
 
 // ---- kernel D: step in the unscaled space, model cost change = 1/2 (y^T D y + y^T rhs) ----------------------------
 __global__ void finish_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* delta, double* scal) {
+  pdl_wait_then_trigger();
   if (scal[SC_OK] != 1.0) return;
   const int n = P.nk + P.nb;
   SolveWs ws = carve(wsp, P.nk, P.nb, P.ldb, pl);
@@ -812,6 +856,7 @@ __device__ void se3_exp_dev(const double* a, Q4& q, V3& t) {
 }
 
 __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand, const double* __restrict__ delta, double max_ba, double max_bg, double* scal) {
+  pdl_wait_then_trigger();
   const int total = P.n_so3 + P.n_r3 + P.n_ba + P.n_bg + 1;
   double step = 0.0, xsq = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -955,23 +1000,23 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   if (sCR > cfgCR) { cudaFuncSetAttribute(backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sCR); cfgCR = sCR; }
   cudaMemsetAsync(ws.bandr, 0, ws.reduced_doubles * sizeof(double), st);
   if (P.nk > 0) {
-    prepare_kernel<<<dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st>>>(P, pl, scale, sp, workspace); count_launch();
-    eliminate_kernel<<<pl.P, NT, sA, st>>>(P, pl, workspace, scal); count_launch();
-    for (int l = 1; l <= pl.L; ++l) { reduce_kernel<<<(pl.S[l] + 1) / 2, NT, sR, st>>>(P, pl, l, workspace, scal); count_launch(); }
+    launch_pdl(prepare_kernel, dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st, P, pl, scale, sp, workspace); count_launch();
+    launch_pdl(eliminate_kernel, pl.P, NT, sA, st, P, pl, workspace, scal); count_launch();
+    for (int l = 1; l <= pl.L; ++l) { launch_pdl(reduce_kernel, (pl.S[l] + 1) / 2, NT, sR, st, P, pl, l, workspace, scal); count_launch(); }
   }
-  root_kernel<<<1, NT, sB, st>>>(P, pl, scale, sp, workspace, scal); count_launch();
+  launch_pdl(root_kernel, 1, NT, sB, st, P, pl, scale, sp, workspace, scal); count_launch();
   if (P.nk > 0) {
-    for (int l = pl.L; l >= 1; --l) { backsub_kernel<false><<<(pl.S[l] + 1) / 2, NT, sCR, st>>>(P, pl, l, workspace, scal); count_launch(); }
-    backsub_kernel<true><<<pl.P, NT, sC, st>>>(P, pl, 0, workspace, scal); count_launch();
+    for (int l = pl.L; l >= 1; --l) { launch_pdl(backsub_kernel<false>, (pl.S[l] + 1) / 2, NT, sCR, st, P, pl, l, workspace, (const double*)scal); count_launch(); }
+    launch_pdl(backsub_kernel<true>, pl.P, NT, sC, st, P, pl, 0, workspace, (const double*)scal); count_launch();
   }
   const int n = P.nk + P.nb;
   int grid = (n + 255) / 256; if (grid > 148) grid = 148; if (grid < 1) grid = 1;
-  finish_kernel<<<grid, 256, 0, st>>>(P, pl, scale, sp, workspace, delta, scal); count_launch();
+  launch_pdl(finish_kernel, grid, 256, 0, st, P, pl, scale, sp, workspace, delta, scal); count_launch();
 }
 
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st) {
   const int total = P.n_so3 + P.n_r3 + P.n_ba + P.n_bg + 1;
-  update_kernel<<<(total + 127) / 128, 128, 0, st>>>(P, cur, cand, delta, max_ba, max_bg, scal);
+  launch_pdl(update_kernel, (total + 127) / 128, 128, 0, st, P, cur, cand, delta, max_ba, max_bg, scal);
   count_launch();
 }
 

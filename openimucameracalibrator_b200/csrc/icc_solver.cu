@@ -286,7 +286,7 @@ __device__ bool factor_range(const FactorSmem& fs, int j_begin, int j_end, int k
 // select -> SHFL -> DMUL -> DFMA instead of shared-memory round trips.  tw[col - base] holds t on entry and x on exit.
 // Columns >= unknown_end are known values (x = t, no pivot) that only scatter into the unknown ones.
 template <int NR>
-__device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB) {
+__device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB, bool prestaged) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, win = 32 * NR;
   double t[NR]; int r[NR];
   if (tid < 32) {
@@ -300,7 +300,7 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
   double* ipv = Bw + (size_t)(PB + kd) * ldb;                    // reciprocal pivots of the group (filled by all threads)
   for (int hi = top; hi > base; hi -= PB) {
     const int lo_own = max(base, hi - PB), lo = max(base, lo_own - kd);
-    {   // contiguous copy of the factor columns [lo, hi) with 8 loads in flight per thread
+    if (!prestaged) {   // contiguous copy of the factor columns [lo, hi) with 8 loads in flight per thread
       const int total = (hi - lo) * ldb, lim = (min(hi, unknown_end) - lo) * ldb;
       const double* src = Lb_g + (int64_t)lo * ldb;
       for (int b0 = tid; b0 < total; b0 += 8 * nt) {
@@ -310,8 +310,8 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
 #pragma unroll
         for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; if (idx < total) Bw[idx] = v[u]; }
       }
+      for (int idx = tid; idx < hi - lo_own; idx += nt) { const int col = lo_own + idx; ipv[idx] = col < unknown_end ? 1.0 / Lb_g[(int64_t)col * ldb] : 1.0; }
     }
-    for (int idx = tid; idx < hi - lo_own; idx += nt) { const int col = lo_own + idx; ipv[idx] = col < unknown_end ? 1.0 / Lb_g[(int64_t)col * ldb] : 1.0; }
     __syncthreads();
     if (tid < 32) {
       // L_{j, c} D_c of slot column c = j - r sits at Bw[(c - lo) * ldb + r]; as j decreases with c fixed, r decreases too,
@@ -348,11 +348,25 @@ __device__ void backsub_warp(const double* __restrict__ Lb_g, double* tw, double
     __syncthreads();
   }
 }
-__device__ void backsub_dispatch(const double* Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB) {
-  if (kd < 32) backsub_warp<1>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
-  else if (kd < 64) backsub_warp<2>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
-  else if (kd < 128) backsub_warp<4>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
-  else backsub_warp<8>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB);
+__device__ void backsub_dispatch(const double* Lb_g, double* tw, double* Bw, int base, int top, int unknown_end, int kd, int ldb, int PB, bool prestaged = false) {
+  if (kd < 32) backsub_warp<1>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB, prestaged);
+  else if (kd < 64) backsub_warp<2>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB, prestaged);
+  else if (kd < 128) backsub_warp<4>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB, prestaged);
+  else backsub_warp<8>(Lb_g, tw, Bw, base, top, unknown_end, kd, ldb, PB, prestaged);
+}
+// the single-group staging of backsub_warp, callable ahead of time (factor columns [base, top) -> Bw, reciprocal pivots behind them)
+__device__ void backsub_stage(const double* __restrict__ Lb_g, double* Bw, int base, int top, int kd, int ldb, int PB) {
+  const int tid = threadIdx.x, nt = blockDim.x, total = (top - base) * ldb;
+  const double* src = Lb_g + (int64_t)base * ldb;
+  double* ipv = Bw + (size_t)(PB + kd) * ldb;
+  for (int b0 = tid; b0 < total; b0 += 8 * nt) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; v[u] = idx < total ? src[idx] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int idx = b0 + u * nt; if (idx < total) Bw[idx] = v[u]; }
+  }
+  for (int idx = tid; idx < top - base; idx += nt) ipv[idx] = 1.0 / Lb_g[(int64_t)(base + idx) * ldb];
 }
 
 // shared-memory carve-up shared by kernels A and B
@@ -769,8 +783,6 @@ __global__ void __launch_bounds__(NT) root_kernel(DeviceProblem P, SolvePlan pl,
 template <bool LEVEL0>
 __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan pl, int level, double* wsp, const double* scal) {
   extern __shared__ __align__(16) double sm[];
-  pdl_wait_then_trigger();
-  if (scal[SC_OK] != 1.0) return;
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, w = pl.w, nbl = pl.nbl, tid = threadIdx.x, nt = blockDim.x;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
   int a, b, kd, ldb, y_left, y_own, y_right; bool has_left, has_right;   // y_*: position of the blocks in the solution vector
@@ -785,17 +797,28 @@ __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan 
     y_left = has_left ? sep_col(pl, level, 2 * c - 1) : 0; y_own = sep_col(pl, level, 2 * c); y_right = has_right ? sep_col(pl, level, 2 * c + 1) : 0;
   }
   const int top = has_right ? b + w : b;   // right separator values are known: they only enter the right-hand sides
+  const int PB = LEVEL0 ? 128 : 64;
+  const bool staged = b - a <= PB;         // the usual case: the factor of this block is staged BEFORE waiting for the predecessor
   double* xl = sm;                         // local border solution [left separator | border]
   double* xr = xl + ((nbl + 3) & ~3);      // right separator solution
   double* tw = xr + ((w + 3) & ~3);        // t / x for columns [a, b)
-  double* Bw = tw + ((b - a + 3) & ~3);    // (PB + kd) * ldb panel of L
+  double* Bw = tw + ((b - a + 3) & ~3);    // (PB + kd) * ldb panel of L, then PB reciprocal pivots
+  double* Els = Bw + (size_t)(PB + kd) * ldb + PB;   // staged rows of El
+  if (staged) {   // written by the elimination kernels, i.e. older than the direct predecessor: safe before the wait
+    backsub_stage(Lb, Bw, a, b, kd, ldb, PB);
+    const double* src = El + (int64_t)a * nbl;
+    for (int i = tid; i < (b - a) * nbl; i += nt) Els[i] = src[i];
+  }
+  pdl_wait_then_trigger();
+  if (scal[SC_OK] != 1.0) return;
   for (int i = tid; i < w + nb; i += nt) xl[i] = i < w ? (has_left ? ws.y[y_left + i] : 0.0) : ws.y[nk + i - w];
   for (int i = tid; i < w; i += nt) xr[i] = has_right ? ws.y[y_right + i] : 0.0;
   __syncthreads();
-  // t_j = rhs_j - sum_i El[j][i] xl[i] - sum_{r in right separator} (L_rj D_j) x_r : one warp per column, coalesced rows
+  // t_j = rhs_j - sum_i El[j][i] xl[i] - sum_{r in right separator} (L_rj D_j) x_r : one warp per column
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   for (int j = a + warp; j < b; j += nwarps) {
-    const double* le = El + (int64_t)j * nbl; const double* lc = Lb + (int64_t)j * ldb;
+    const double* le = staged ? Els + (size_t)(j - a) * nbl : El + (int64_t)j * nbl;
+    const double* lc = staged ? Bw + (size_t)(j - a) * ldb : Lb + (int64_t)j * ldb;
     double acc = 0.0;
     for (int i = lane; i < w + nb; i += 32) acc = fma(le[i], xl[i], acc);
     for (int r = b + lane; r < top && r - j <= kd; r += 32) acc = fma(lc[r - j], xr[r - b], acc);
@@ -803,7 +826,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan 
     if (lane == 0) tw[j - a] = le[w + nb] - acc;
   }
   __syncthreads();
-  backsub_dispatch(Lb, tw, Bw, a, b, b, kd, ldb, LEVEL0 ? 128 : 64);
+  backsub_dispatch(Lb, tw, Bw, a, b, b, kd, ldb, PB, staged);
   for (int j = a + tid; j < b; j += nt) ws.y[y_own + (j - a)] = tw[j - a];
 }
 
@@ -932,10 +955,10 @@ size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
 }
 size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
   const int maxlen = pl.len + 1 + pl.w;
-  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128) * sizeof(double) + 64;
+  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128 + (size_t)std::min(pl.len + 1, 128) * pl.nbl) * sizeof(double) + 64;
 }
 size_t smem_CR(const DeviceProblem& P, const SolvePlan& pl) {
-  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)2 * pl.w + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64) * sizeof(double) + 64;
+  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)2 * pl.w + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64 + (size_t)pl.w * pl.nbl) * sizeof(double) + 64;
 }
 
 // Chunking of the knot columns.  A leaf costs ~ its interior length in sequential column eliminations, every cyclic-

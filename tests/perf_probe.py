@@ -3,7 +3,7 @@ import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
-F = capi.FLAG_SPLINE | capi.FLAG_T_I_C
+F = int(os.environ.get('PROBE_FLAGS', capi.FLAG_SPLINE | capi.FLAG_T_I_C))
 cfgs = [int(a) for a in sys.argv[1:]] or [4]
 for c in cfgs:
     ds = syn.make_dataset(syn.CONFIGS[c])

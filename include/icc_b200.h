@@ -188,6 +188,25 @@ icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summa
 icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval);
 /* The handle's cudaStream_t (so that callers can bracket calls with their own CUDA events on the launching stream). */
 void* icc_get_stream(icc_handle* h);
+
+/* ---- upstream row f1: per-view board poses, i.e. what fills the pose dataset the hot CLI reads -----------
+ * PoseEstimator::EstimatePosesFromJson (src/core/pose_estimator.cc:92-191): every corner is undistorted to the normalised image
+ * plane (theia::Camera::PixelToNormalizedCoordinates, :129-130), a calibrated absolute pose is estimated (RANSAC PnP,
+ * :54-66; squared normalised reprojection error threshold 0.004 * image_height / image_diagonal, :100-101; >= 6 inliers, :65),
+ * then refined on the inliers by theia::BundleAdjustView with a Huber(1.345) loss (:44-48, :86-87); views with fewer than
+ * `min_points` corners (pose_estimator.h:72, default 8) or a mean reprojection error above `max_reproj_error` (:181) are dropped.
+ * Here: camera + board points must have been set (icc_set_camera / icc_set_board_points; the board must be planar, z = const);
+ * one warp per view computes a normalised homography initialisation and the Levenberg-Marquardt refinement on the same cost,
+ * so that the converged pose is the reference's BundleAdjustView optimum (RANSAC's random minimal samples are not reproduced:
+ * the inlier set is taken with the same threshold around the refined pose).
+ * Outputs (per view, caller-owned): q_wc (x,y,z,w) = R_cw^T and p_wc exactly as icc_set_frames consumes them, the mean
+ * normalised reprojection error, valid (1 / 0).  max_reproj_error <= 0 selects 0.004 * image_height; min_points <= 0 selects 8. */
+icc_status icc_estimate_board_poses(icc_handle* h, int n_frames, const int32_t* corner_offsets /* n_frames+1 */, const int32_t* point_ids,
+                                    const double* uv, double max_reproj_error, int min_points,
+                                    double* q_wc_xyzw, double* p_wc, double* mean_reproj_error, int32_t* valid);
+/* theia::Camera::PixelToNormalizedCoordinates / z for `n` pixels with the handle's camera: xy_out[2n], ok[n] (nullable). */
+icc_status icc_pixels_to_normalized(icc_handle* h, int n, const double* uv, double* xy_out, int32_t* ok);
+
 /* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
 void icc_trim_device_cache(void);
 

@@ -132,6 +132,25 @@ class CApi:
         assert a.size == 3 * t.size and g.size == 3 * t.size
         self._call("set_imu", [C.c_int, c_double_p, c_double_p, c_double_p], t.size, _dp(t), _dp(a), _dp(g))
 
+    # ---- upstream row f1: per-view board poses (PoseEstimator::EstimatePosesFromJson, src/core/pose_estimator.cc:92-191) ----
+    def estimate_board_poses(self, corner_offsets, point_ids, uv, max_reproj_error=0.0, min_points=0):
+        """-> (q_wc[n,4] x,y,z,w, p_wc[n,3], mean normalised reprojection error[n], valid[n]); camera + board points must be set."""
+        off = np.ascontiguousarray(corner_offsets, dtype=np.int32); ids = np.ascontiguousarray(point_ids, dtype=np.int32); uv = _f64(uv)
+        n = off.size - 1
+        assert ids.size == off[-1] and uv.size == 2 * ids.size
+        q = np.zeros((n, 4)); p = np.zeros((n, 3)); e = np.zeros(n); v = np.zeros(n, dtype=np.int32)
+        self._call("estimate_board_poses", [C.c_int, c_int32_p, c_int32_p, c_double_p, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p],
+                   n, off.ctypes.data_as(c_int32_p), ids.ctypes.data_as(c_int32_p), _dp(uv), float(max_reproj_error), int(min_points),
+                   _dp(q), _dp(p), _dp(e), v.ctypes.data_as(c_int32_p))
+        return q, p, e, v
+
+    def pixels_to_normalized(self, uv):
+        """theia::Camera::PixelToNormalizedCoordinates / z for an (n, 2) pixel array -> (xy[n,2], ok[n])."""
+        uv = _f64(uv).reshape(-1, 2); n = uv.shape[0]
+        xy = np.zeros((n, 2)); ok = np.zeros(n, dtype=np.int32)
+        self._call("pixels_to_normalized", [C.c_int, c_double_p, c_double_p, c_int32_p], n, _dp(uv), _dp(xy), ok.ctypes.data_as(c_int32_p))
+        return xy, ok
+
     def set_shard(self, rank, world):
         self._call("set_shard", [C.c_int, C.c_int], int(rank), int(world))
 

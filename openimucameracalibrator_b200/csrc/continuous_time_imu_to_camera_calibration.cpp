@@ -7,9 +7,11 @@
 // (theia::ReadReconstruction, app :95-97), which cannot be parsed without Theia.  This program reads the same content as
 // JSON:  {"views": {"<view name>": {"q_wc": [w,x,y,z], "p_wc": [x,y,z]}}, "tracks": {"<id>": [x,y,z,w]}}
 // where q_wc = R_cw^T and p_wc = camera position (what app :137-145 / impl.h:290-300 take from each theia::Camera).
-// Extra flag (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary).
+// When --input_pose_dataset is omitted, the per-view board poses are estimated in-process on the GPU from the corner file
+// (icc_estimate_board_poses = PoseEstimator::EstimatePosesFromJson), i.e. the corner file alone suffices.
+// Extra flags (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary).
 #include "../../include/icc_b200.h"
-#include "icc_json.hpp"
+#include "icc_cli_common.hpp"
 
 #include <algorithm>
 #include <array>
@@ -23,32 +25,14 @@ using iccjson::Value;
 
 namespace {
 
-struct Flags {
-  std::map<std::string, std::string> str = {{"telemetry_json", ""}, {"input_pose_dataset", ""}, {"input_corners", ""}, {"camera_calibration_json", ""},
+icccli::Flags default_flags() {
+  icccli::Flags f;
+  f.str = {{"telemetry_json", ""}, {"input_pose_dataset", ""}, {"input_corners", ""}, {"camera_calibration_json", ""},
     {"gyro_to_cam_initial_calibration", ""}, {"imu_intrinsics", ""}, {"imu_bias_file", ""}, {"spline_error_weighting_json", ""}, {"output_path", ""},
     {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}};
-  std::map<std::string, bool> boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}};
-  std::map<std::string, double> num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}};
-};
-
-bool parse_bool(const std::string& v) { return v == "true" || v == "1" || v == "t" || v == "yes" || v == "y" || v == "True"; }
-
-// gflags syntax: --name=value, --name value, -name..., --boolflag, --noboolflag
-void parse_flags(int argc, char** argv, Flags& f) {
-  for (int i = 1; i < argc; ++i) {
-    std::string a = argv[i];
-    if (a.size() < 2 || a[0] != '-') throw std::runtime_error("unexpected argument: " + a);
-    a = a.substr(a[1] == '-' ? 2 : 1);
-    std::string name = a, value; bool has_value = false;
-    const size_t eq = a.find('=');
-    if (eq != std::string::npos) { name = a.substr(0, eq); value = a.substr(eq + 1); has_value = true; }
-    if (f.boolean.count(name)) { f.boolean[name] = has_value ? parse_bool(value) : true; continue; }
-    if (name.rfind("no", 0) == 0 && f.boolean.count(name.substr(2)) && !has_value) { f.boolean[name.substr(2)] = false; continue; }
-    if (!has_value) { if (i + 1 >= argc) throw std::runtime_error("flag --" + name + " needs a value"); value = argv[++i]; }
-    if (f.str.count(name)) f.str[name] = value;
-    else if (f.num.count(name)) f.num[name] = std::stod(value);
-    else throw std::runtime_error("unknown command line flag '" + name + "'");
-  }
+  f.boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}};
+  f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}};
+  return f;
 }
 
 #define CHECK_MSG(cond, msg) do { if (!(cond)) { std::cerr << "Check failed: " #cond " " << msg << std::endl; std::exit(1); } } while (0)
@@ -60,23 +44,6 @@ int grav_dir_string_to_int(const std::string& s) {   // src/utils/utils.cc:150-1
   if (s == "Y") return 1;
   if (s == "Z") return 2;
   return -1;
-}
-
-// src/io/read_camera_calibration.cc:35-119 -> (model id, Theia-ordered intrinsics).  Like the reference, `skew` is never read.
-int read_camera(const Value& j, std::vector<double>& k, int& width, int& height, double& fps) {
-  const std::string type = j.at("intrinsic_type").str();
-  const Value& in = j.at("intrinsics");
-  width = (int)j.at("image_width").num(); height = (int)j.at("image_height").num(); fps = j.at("fps").num();
-  const double f = in.at("focal_length").num(), cx = in.at("principal_pt_x").num(), cy = in.at("principal_pt_y").num();
-  auto ar = [&]() { return in.at("aspect_ratio").num(); };
-  if (type == "DIVISION_UNDISTORTION") { k = {f, ar(), cx, cy, in.at("div_undist_distortion").num()}; return ICC_CAM_DIVISION_UNDISTORTION; }
-  if (type == "DOUBLE_SPHERE") { k = {f, ar(), 0.0, cx, cy, in.at("xi").num(), in.at("alpha").num()}; return ICC_CAM_DOUBLE_SPHERE; }
-  if (type == "EXTENDED_UNIFIED") { k = {f, ar(), 0.0, cx, cy, in.at("alpha").num(), in.at("beta").num()}; return ICC_CAM_EXTENDED_UNIFIED; }
-  if (type == "FISHEYE") { k = {f, ar(), 0.0, cx, cy, in.at("radial_distortion_1").num(), in.at("radial_distortion_2").num(), in.at("radial_distortion_3").num(), in.at("radial_distortion_4").num()}; return ICC_CAM_FISHEYE; }
-  if (type == "PINHOLE_RADIAL_TANGENTIAL") { k = {f, ar(), 0.0, cx, cy, in.at("radial_distortion_1").num(), in.at("radial_distortion_2").num(), in.at("radial_distortion_3").num(), in.at("tangential_distortion_1").num(), in.at("tangential_distortion_2").num()}; return ICC_CAM_PINHOLE_RADIAL_TANGENTIAL; }
-  if (type == "PINHOLE") { k = {f, ar(), 0.0, cx, cy, 0.0, 0.0}; return ICC_CAM_PINHOLE; }
-  if (type == "FOV") { k = {f, in.contains("aspect_ratio") ? ar() : 1.0, cx, cy, in.at("radial_distortion_1").num()}; return ICC_CAM_FOV; }
-  throw std::runtime_error("unknown intrinsic_type " + type);
 }
 
 void write_ply(const std::string& path, const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<int, 3>>& col) {
@@ -91,26 +58,35 @@ Value xyz(double x, double y, double z) { Value v = Value::object(); v["x"] = Va
 }  // namespace
 
 int main(int argc, char** argv) {
-  Flags F;
-  try { parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
+  icccli::Flags F = default_flags();
+  try { icccli::parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
   const double S_TO_NS = 1e9, US_TO_S = 1e-6, S_TO_US = 1e6, NS_TO_S = 1e-9;
   try {
     // ---- inputs (app :93-184) ---------------------------------------------------------------------------------------
+    const bool have_poses = !F.str["input_pose_dataset"].empty();
     Value pose_dataset;
-    try { pose_dataset = iccjson::load_json(F.str["input_pose_dataset"]); }
-    catch (const std::exception& e) { CHECK_MSG(false, "Could not read Reconstruction file (JSON pose dataset expected, Theia .calibdata is not supported): " << e.what()); }
+    if (have_poses) {
+      try { pose_dataset = iccjson::load_json(F.str["input_pose_dataset"]); }
+      catch (const std::exception& e) { CHECK_MSG(false, "Could not read Reconstruction file (JSON pose dataset expected, Theia .calibdata is not supported): " << e.what()); }
+    }
     Value scene_json;
     try { scene_json = iccjson::load_ubjson(F.str["input_corners"]); } catch (const std::exception& e) { CHECK_MSG(false, "Failed to load " << F.str["input_corners"] << ": " << e.what()); }
     std::vector<double> intr; int width = 0, height = 0; double fps = 0;
     int model = -1;
-    try { model = read_camera(iccjson::load_json(F.str["camera_calibration_json"]), intr, width, height, fps); }
+    try { model = icccli::read_camera(iccjson::load_json(F.str["camera_calibration_json"]), intr, width, height, fps); }
     catch (const std::exception& e) { CHECK_MSG(false, "Could not read camera calibration: " << F.str["camera_calibration_json"] << ": " << e.what()); }
-    // board tracks come from the pose dataset (possibly refined), app :108-119
-    const Value& tracks = pose_dataset.at("tracks");
-    int max_id = -1; for (const auto& kv : *tracks.o) max_id = std::max(max_id, std::stoi(kv.first));
-    std::vector<double> board(4 * (size_t)(max_id + 1), 0.0);
-    for (int i = 0; i <= max_id; ++i) board[4 * i + 3] = 1.0;
-    for (const auto& kv : *tracks.o) { const int id = std::stoi(kv.first); for (int d = 0; d < 4; ++d) board[4 * id + d] = kv.second.at(d).num(); }
+    // board tracks come from the pose dataset (possibly refined), app :108-119; without one, from the corner file's scene_pts
+    int max_id = -1;
+    std::vector<double> board;
+    if (have_poses) {
+      const Value& tracks = pose_dataset.at("tracks");
+      for (const auto& kv : *tracks.o) max_id = std::max(max_id, std::stoi(kv.first));
+      board.assign(4 * (size_t)(max_id + 1), 0.0);
+      for (int i = 0; i <= max_id; ++i) board[4 * i + 3] = 1.0;
+      for (const auto& kv : *tracks.o) { const int id = std::stoi(kv.first); for (int d = 0; d < 4; ++d) board[4 * id + d] = kv.second.at(d).num(); }
+    } else {
+      int np = 0; board = icccli::read_scene_points(scene_json, np); max_id = np - 1;
+    }
     // telemetry (src/io/read_telemetry.cc:29-69)
     Value tel;
     try { tel = iccjson::load_json(F.str["telemetry_json"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["telemetry_json"] << ": " << e.what()); }
@@ -124,19 +100,49 @@ int main(int argc, char** argv) {
     double t_offset_cam_s = 0.0;
     if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) t_offset_cam_s = tel.at("img_timestamps_ns").at(0).num() * NS_TO_S;
     // views: join corners with poses by name = to_string((uint64) timestamp_us)   (app :131-161)
-    const Value& pviews = pose_dataset.at("views");
     std::vector<double> frame_t, uv, q_wc, p_wc; std::vector<int32_t> off{0}, ids;
-    for (const auto& kv : *scene_json.at("views").o) {
-      const double timestamp_us = std::stod(kv.first);
-      const std::string view_name = std::to_string((uint64_t)timestamp_us);
-      if (!pviews.contains(view_name)) continue;
-      const Value& pv = pviews.at(view_name);
-      frame_t.push_back(timestamp_us * US_TO_S + t_offset_cam_s);
-      const Value& q = pv.at("q_wc");   // [w, x, y, z]
-      q_wc.push_back(q.at(1).num()); q_wc.push_back(q.at(2).num()); q_wc.push_back(q.at(3).num()); q_wc.push_back(q.at(0).num());
-      for (int d = 0; d < 3; ++d) p_wc.push_back(pv.at("p_wc").at(d).num());
-      for (const auto& ip : *kv.second.at("image_points").o) { ids.push_back(std::stoi(ip.first)); uv.push_back(ip.second.at(0).num()); uv.push_back(ip.second.at(1).num()); }
-      off.push_back((int32_t)ids.size());
+    if (have_poses) {
+      const Value& pviews = pose_dataset.at("views");
+      for (const auto& kv : *scene_json.at("views").o) {
+        const double timestamp_us = std::stod(kv.first);
+        const std::string view_name = std::to_string((uint64_t)timestamp_us);
+        if (!pviews.contains(view_name)) continue;
+        const Value& pv = pviews.at(view_name);
+        frame_t.push_back(timestamp_us * US_TO_S + t_offset_cam_s);
+        const Value& q = pv.at("q_wc");   // [w, x, y, z]
+        q_wc.push_back(q.at(1).num()); q_wc.push_back(q.at(2).num()); q_wc.push_back(q.at(3).num()); q_wc.push_back(q.at(0).num());
+        for (int d = 0; d < 3; ++d) p_wc.push_back(pv.at("p_wc").at(d).num());
+        for (const auto& ip : *kv.second.at("image_points").o) { ids.push_back(std::stoi(ip.first)); uv.push_back(ip.second.at(0).num()); uv.push_back(ip.second.at(1).num()); }
+        off.push_back((int32_t)ids.size());
+      }
+    } else if (!F.boolean["parse_only"]) {
+      // no pose dataset: estimate the per-view poses on the GPU and keep the views the reference's PoseEstimator would keep
+      const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
+      const int nv = (int)sv.timestamp_us.size();
+      CHECK_MSG(nv > 0, "the corner file holds no views");
+      icc_handle* hp = nullptr;
+      { icc_status st = icc_create(&hp, (int)F.num["device"]); if (st != ICC_OK) { std::cerr << "icc_create failed (" << st << "): " << icc_last_error(hp) << std::endl; return 2; } }
+      std::vector<double> q_all(4 * (size_t)nv), p_all(3 * (size_t)nv), err(nv); std::vector<int32_t> valid(nv);
+      icc_status st = icc_set_camera(hp, model, intr.data(), (int)intr.size(), width, height);
+      if (st == ICC_OK) st = icc_set_board_points(hp, max_id + 1, board.data());
+      if (st == ICC_OK) st = icc_estimate_board_poses(hp, nv, sv.off.data(), sv.ids.data(), sv.uv.data(), 0.0, 0, q_all.data(), p_all.data(), err.data(), valid.data());
+      if (st != ICC_OK) { std::cerr << "board pose estimation failed (" << st << "): " << icc_last_error(hp) << std::endl; return 2; }
+      icc_destroy(hp);
+      int kept = 0;
+      for (int i = 0; i < nv; ++i) {
+        if (!valid[i]) continue;
+        ++kept;
+        frame_t.push_back(sv.timestamp_us[i] * US_TO_S + t_offset_cam_s);
+        for (int d = 0; d < 4; ++d) q_wc.push_back(q_all[4 * i + d]);
+        for (int d = 0; d < 3; ++d) p_wc.push_back(p_all[3 * i + d]);
+        for (int c = sv.off[i]; c < sv.off[i + 1]; ++c) { ids.push_back(sv.ids[c]); uv.push_back(sv.uv[2 * c]); uv.push_back(sv.uv[2 * c + 1]); }
+        off.push_back((int32_t)ids.size());
+      }
+      std::cout << "Estimated board poses for " << kept << " of " << nv << " views on the GPU (no --input_pose_dataset given)\n";
+    } else {
+      const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
+      for (size_t i = 0; i < sv.timestamp_us.size(); ++i) frame_t.push_back(sv.timestamp_us[i] * US_TO_S + t_offset_cam_s);
+      ids = sv.ids; uv = sv.uv; off = sv.off;
     }
     CHECK_MSG(!frame_t.empty(), "no view of the corner file has a pose in the pose dataset");
     // gyro-to-camera initialisation (src/io/read_misc.cc:63-82): T_i_c_init = (q_gyro_to_cam^-1, 0)   (app :164-170)

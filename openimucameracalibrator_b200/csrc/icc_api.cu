@@ -843,6 +843,67 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
 }
 
 void* icc_get_stream(icc_handle* h) { return h ? (void*)h->stream : nullptr; }
+// ---- upstream row f1: per-view board poses ---------------------------------------------------------------------------
+icc_status icc_pixels_to_normalized(icc_handle* h, int n, const double* uv, double* xy_out, int32_t* ok) {
+  if (!h || n < 0 || (n > 0 && (!uv || !xy_out))) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (h->model < 0) return fail(h, ICC_ERR_STATE, "icc_set_camera must be called first");
+  if (n == 0) return ICC_OK;
+  CU(cudaSetDevice(h->device));
+  DevBuf<double2> d_uv, d_xy; DevBuf<int> d_ok;
+  CU(d_uv.alloc(n)); CU(d_xy.alloc(n)); CU(d_ok.alloc(n));
+  CU(cudaMemcpyAsync(d_uv.p, uv, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  launch_unproject(h->model, h->intr, n, d_uv.p, d_xy.p, d_ok.p, h->stream);
+  CU(cudaMemcpyAsync(xy_out, d_xy.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<int> okh(ok ? n : 0);
+  if (ok) CU(cudaMemcpyAsync(okh.data(), d_ok.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (ok) for (int i = 0; i < n; ++i) ok[i] = okh[i];
+  return ICC_OK;
+}
+
+icc_status icc_estimate_board_poses(icc_handle* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points,
+                                    double* q_wc, double* p_wc, double* mean_err, int32_t* valid) {
+  if (!h || nf <= 0 || !off || !ids || !uv || !q_wc || !p_wc || !valid) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (h->model < 0 || h->points.empty()) return fail(h, ICC_ERR_STATE, "icc_set_camera and icc_set_board_points must be called first");
+  for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
+  const int nc = off[nf] - off[0];
+  if (off[0] != 0) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must start at 0");
+  CU(cudaSetDevice(h->device));
+  const int np = (int)(h->points.size() / 4);
+  std::vector<double4> board(np);
+  for (int i = 0; i < np; ++i) board[i] = make_double4(h->points[4 * i], h->points[4 * i + 1], h->points[4 * i + 2], h->points[4 * i + 3]);
+  DevBuf<double4> d_board; DevBuf<int> d_off, d_pid, d_ok, d_valid; DevBuf<double2> d_uv, d_xy; DevBuf<unsigned char> d_use; DevBuf<double> d_q, d_p, d_e;
+  CU(d_board.upload(board));
+  CU(d_off.alloc(nf + 1)); CU(d_pid.alloc(std::max(1, nc))); CU(d_uv.alloc(std::max(1, nc))); CU(d_xy.alloc(std::max(1, nc))); CU(d_ok.alloc(std::max(1, nc))); CU(d_use.alloc(std::max(1, nc)));
+  CU(d_q.alloc(4 * (size_t)nf)); CU(d_p.alloc(3 * (size_t)nf)); CU(d_e.alloc(nf)); CU(d_valid.alloc(nf));
+  CU(cudaMemcpyAsync(d_off.p, off, (size_t)(nf + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (nc > 0) {
+    CU(cudaMemcpyAsync(d_pid.p, ids, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_uv.p, uv, (size_t)nc * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  }
+  launch_unproject(h->model, h->intr, nc, d_uv.p, d_xy.p, d_ok.p, h->stream);
+  PoseProblem Q; memset(&Q, 0, sizeof Q);
+  Q.model = h->model; for (int i = 0; i < 10; ++i) Q.intr[i] = h->intr[i];
+  Q.n_frames = nf; Q.n_points = np; Q.min_points = min_points > 0 ? min_points : 8;
+  Q.board = d_board.p; Q.f_off = d_off.p; Q.pid = d_pid.p;
+  const double W = h->width, H = h->height;
+  const double max_px = max_reproj_error > 0.0 ? max_reproj_error : 0.004 * H;            // pose_estimator.cc:97
+  Q.thresh_sq = (W > 0 && H > 0) ? max_px / std::sqrt(W * W + H * H) : 1e-3;               // :101 (compared with a SQUARED error by theia's RANSAC)
+  Q.max_err = max_px;                                                                       // :181 (pixels against a normalised error, as in the reference)
+  launch_board_poses(Q, d_xy.p, d_ok.p, d_use.p, d_q.p, d_p.p, d_e.p, d_valid.p, h->stream);
+  std::vector<double> eh(nf); std::vector<int> vh(nf);
+  CU(cudaMemcpyAsync(q_wc, d_q.p, 4 * (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(p_wc, d_p.p, 3 * (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(eh.data(), d_e.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(vh.data(), d_valid.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cudaGetLastError() != cudaSuccess) return fail(h, ICC_ERR_CUDA, "pose kernels failed");
+  for (int i = 0; i < nf; ++i) { valid[i] = vh[i]; if (mean_err) mean_err[i] = eh[i]; }
+  return ICC_OK;
+}
+
 void icc_trim_device_cache(void) { block_cache().trim(); }
 
 }  // extern "C"

@@ -85,7 +85,16 @@ void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceS
 // trajectory getters
 void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,
                             double* bg, double* ba, double* pose_q, double* pose_p, int* valid, cudaStream_t st);
-// dense dump of the packed normal equations into canonical order (tests)
+// ---- per-view board poses (icc_pose.cu) ---------------------------------------------------------------------------
+struct PoseProblem {
+  int model; double intr[10];
+  int n_frames, n_points, min_points;
+  const double4* board; const int* f_off; const int* pid;
+  double thresh_sq;            // squared normalised reprojection error of an inlier (pose_estimator.cc:100-101)
+  double max_err;              // views above this mean error are dropped (pose_estimator.cc:181)
+};
+void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st);
+void launch_board_poses(const PoseProblem& Q, const double2* xy, const int* ok, unsigned char* use, double* q_wc, double* p_wc, double* err, int* valid, cudaStream_t st);
 int kernel_launch_count();
 
 }  // namespace icc

@@ -979,6 +979,188 @@ void icco_base_coefficients(int N, double* out) {
   if (N == 6) { const auto& B = blend<6>(); for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i * 6 + j] = B.base[i][j]; }
 }
 // Camera projection (double) for generator cross-checks.
+// ---- upstream row f1: per-view board poses (restates src/core/pose_estimator.cc:54-191; TEST INFRASTRUCTURE) -----------------
+// Deliberately formulated differently from the CUDA path: forward-mode duals for the un-projection Jacobian, the DLT null vector
+// of the full 9-parameter homography by inverse iteration, Gauss-Newton systems solved by Gaussian elimination with pivoting.
+namespace {
+bool gauss_solve(int n, std::vector<double>& A, std::vector<double>& b) {   // A row-major n x n, overwritten
+  for (int c = 0; c < n; ++c) {
+    int piv = c; for (int r = c + 1; r < n; ++r) if (std::fabs(A[r * n + c]) > std::fabs(A[piv * n + c])) piv = r;
+    if (!(std::fabs(A[piv * n + c]) > 0.0)) return false;
+    if (piv != c) { for (int k = 0; k < n; ++k) std::swap(A[c * n + k], A[piv * n + k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < n; ++r) { const double f = A[r * n + c] / A[c * n + c]; for (int k = c; k < n; ++k) A[r * n + k] -= f * A[c * n + k]; b[r] -= f * b[c]; }
+  }
+  for (int r = n - 1; r >= 0; --r) { double s2 = b[r]; for (int k = r + 1; k < n; ++k) s2 -= A[r * n + k] * b[k]; b[r] = s2 / A[r * n + r]; }
+  return true;
+}
+bool oracle_unproject(int model, const double* intr, double px, double py, double* xy) {
+  typedef Jet<2> J2;
+  auto eval = [&](double x, double y, double* uv, double* Jm) -> bool {
+    J2 k[10]; for (int i = 0; i < 10; ++i) k[i] = J2(intr[i]);
+    J2 p[3]; p[0] = J2(x); p[0].v[0] = 1.0; p[1] = J2(y); p[1].v[1] = 1.0; p[2] = J2(1.0);
+    J2 o[2];
+    if (!project<J2>(model, k, p, o, true)) return false;
+    uv[0] = o[0].a; uv[1] = o[1].a; Jm[0] = o[0].v[0]; Jm[1] = o[0].v[1]; Jm[2] = o[1].v[0]; Jm[3] = o[1].v[1];
+    return true;
+  };
+  double uv[2], Jm[4];
+  if (!eval(0.0, 0.0, uv, Jm)) return false;
+  double det = Jm[0] * Jm[3] - Jm[1] * Jm[2];
+  if (!(std::fabs(det) > 0.0)) return false;
+  double x = (Jm[3] * (px - uv[0]) - Jm[1] * (py - uv[1])) / det, y = (-Jm[2] * (px - uv[0]) + Jm[0] * (py - uv[1])) / det;
+  int guard = 0;
+  while (!eval(x, y, uv, Jm)) { x *= 0.5; y *= 0.5; if (++guard > 60) return false; }
+  double e = (uv[0] - px) * (uv[0] - px) + (uv[1] - py) * (uv[1] - py);
+  for (int it = 0; it < 100 && e > 1e-28; ++it) {
+    det = Jm[0] * Jm[3] - Jm[1] * Jm[2];
+    if (!(std::fabs(det) > 1e-300)) break;
+    const double ru = uv[0] - px, rv = uv[1] - py;
+    const double dx = -(Jm[3] * ru - Jm[1] * rv) / det, dy = -(-Jm[2] * ru + Jm[0] * rv) / det;
+    bool moved = false; double t = 1.0;
+    for (int bt = 0; bt < 40; ++bt, t *= 0.5) {
+      double uv2[2], J2m[4];
+      if (!eval(x + t * dx, y + t * dy, uv2, J2m)) continue;
+      const double en = (uv2[0] - px) * (uv2[0] - px) + (uv2[1] - py) * (uv2[1] - py);
+      if (en < e) { x += t * dx; y += t * dy; e = en; uv[0] = uv2[0]; uv[1] = uv2[1]; for (int i = 0; i < 4; ++i) Jm[i] = J2m[i]; moved = true; break; }
+    }
+    if (!moved) break;
+  }
+  xy[0] = x; xy[1] = y;
+  return e < 1e-12;
+}
+struct PoseObs { double X, Y, Z, x, y; };
+typedef V3<double> Vd; typedef Q4<double> Qd;
+double pose_cost(const std::vector<PoseObs>& ob, const Qd& R, const Vd& t) {
+  double c = 0.0;
+  for (const PoseObs& o : ob) {
+    const Vd Pc = so3_act(R, Vd{o.X, o.Y, o.Z}) + t;
+    if (!(Pc.z > 0.0)) { c += 1e6; continue; }
+    const double r0 = Pc.x / Pc.z - o.x, r1 = Pc.y / Pc.z - o.y, rn = std::sqrt(r0 * r0 + r1 * r1);
+    c += rn <= 1.345 ? 0.5 * rn * rn : 1.345 * rn - 0.5 * 1.345 * 1.345;
+  }
+  return c;
+}
+void pose_gauss_newton(const std::vector<PoseObs>& ob, Qd& R, Vd& t) {
+  double lambda = 1e-4, cost = pose_cost(ob, R, t);
+  for (int it = 0; it < 100; ++it) {
+    std::vector<double> H(36, 0.0), g(6, 0.0);
+    const M3<double> Rm = so3_matrix(R);
+    for (const PoseObs& o : ob) {
+      const double X[3] = {o.X, o.Y, o.Z};
+      const Vd Pc = so3_act(R, Vd{o.X, o.Y, o.Z}) + t;
+      if (!(Pc.z > 0.0)) continue;
+      const double iz = 1.0 / Pc.z, u = Pc.x * iz, v = Pc.y * iz, r[2] = {u - o.x, v - o.y};
+      const double rn = std::sqrt(r[0] * r[0] + r[1] * r[1]), w = rn <= 1.345 ? 1.0 : 1.345 / rn;
+      // dPc/d(delta) = -R [X]x (right increment R exp(delta)), dPc/dt = I
+      double dP[3][6];
+      const double Xx[3][3] = {{0, -X[2], X[1]}, {X[2], 0, -X[0]}, {-X[1], X[0], 0}};
+      for (int a2 = 0; a2 < 3; ++a2) for (int b2 = 0; b2 < 3; ++b2) { double s2 = 0; for (int k = 0; k < 3; ++k) s2 += Rm.m[a2][k] * Xx[k][b2]; dP[a2][b2] = -s2; dP[a2][3 + b2] = a2 == b2 ? 1.0 : 0.0; }
+      double Jr[2][6];
+      for (int b2 = 0; b2 < 6; ++b2) { Jr[0][b2] = iz * dP[0][b2] - u * iz * dP[2][b2]; Jr[1][b2] = iz * dP[1][b2] - v * iz * dP[2][b2]; }
+      for (int a2 = 0; a2 < 6; ++a2) { g[a2] += w * (Jr[0][a2] * r[0] + Jr[1][a2] * r[1]); for (int b2 = 0; b2 < 6; ++b2) H[a2 * 6 + b2] += w * (Jr[0][a2] * Jr[0][b2] + Jr[1][a2] * Jr[1][b2]); }
+    }
+    std::vector<double> A = H, b(6);
+    for (int a2 = 0; a2 < 6; ++a2) { A[a2 * 6 + a2] += lambda * (H[a2 * 6 + a2] + 1e-12); b[a2] = -g[a2]; }
+    if (!gauss_solve(6, A, b)) { lambda *= 10.0; if (lambda > 1e12) break; continue; }
+    const Qd Rn = qnormalized(so3_mul(R, so3_exp(Vd{b[0], b[1], b[2]})));
+    const Vd tn = t + Vd{b[3], b[4], b[5]};
+    const double cn = pose_cost(ob, Rn, tn), step2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3] + b[4] * b[4] + b[5] * b[5];
+    if (cn < cost) { const double dec = cost - cn; R = Rn; t = tn; cost = cn; lambda = std::max(lambda * 0.1, 1e-12); if (dec <= 1e-15 * cost || step2 < 1e-28) break; }
+    else { if (step2 < 1e-28) break; lambda *= 10.0; if (lambda > 1e12) break; }
+  }
+}
+Qd quat_from_cols(const Vd& r1, const Vd& r2, const Vd& r3) {
+  const double m00 = r1.x, m10 = r1.y, m20 = r1.z, m01 = r2.x, m11 = r2.y, m21 = r2.z, m02 = r3.x, m12 = r3.y, m22 = r3.z, tr = m00 + m11 + m22;
+  Qd q;
+  if (tr > 0.0) { const double s2 = std::sqrt(tr + 1.0) * 2.0; q = Qd{(m21 - m12) / s2, (m02 - m20) / s2, (m10 - m01) / s2, 0.25 * s2}; }
+  else if (m00 > m11 && m00 > m22) { const double s2 = std::sqrt(1.0 + m00 - m11 - m22) * 2.0; q = Qd{0.25 * s2, (m01 + m10) / s2, (m02 + m20) / s2, (m21 - m12) / s2}; }
+  else if (m11 > m22) { const double s2 = std::sqrt(1.0 + m11 - m00 - m22) * 2.0; q = Qd{(m01 + m10) / s2, 0.25 * s2, (m12 + m21) / s2, (m02 - m20) / s2}; }
+  else { const double s2 = std::sqrt(1.0 + m22 - m00 - m11) * 2.0; q = Qd{(m02 + m20) / s2, (m12 + m21) / s2, 0.25 * s2, (m10 - m01) / s2}; }
+  return qnormalized(q);
+}
+double vnorm(const Vd& a) { return std::sqrt(dot(a, a)); }
+}  // namespace
+
+icc_status icco_pixels_to_normalized(void* h, int n, const double* uv, double* xy, int32_t* ok) {
+  Oracle& o = *O(h);
+  for (int i = 0; i < n; ++i) { const bool g = oracle_unproject(o.model, o.intr, uv[2 * i], uv[2 * i + 1], xy + 2 * i); if (!g) { xy[2 * i] = 0; xy[2 * i + 1] = 0; } if (ok) ok[i] = g ? 1 : 0; }
+  return ICC_OK;
+}
+
+icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points,
+                                     double* q_wc, double* p_wc, double* mean_err, int32_t* valid) {
+  Oracle& o = *O(h);
+  const int np = (int)(o.points.size() / 4);
+  const double W = o.width, Hh = o.height;
+  const double max_px = max_reproj_error > 0.0 ? max_reproj_error : 0.004 * Hh;
+  const double thresh_sq = (W > 0 && Hh > 0) ? max_px / std::sqrt(W * W + Hh * Hh) : 1e-3;
+  if (min_points <= 0) min_points = 8;
+  for (int f = 0; f < nf; ++f) {
+    q_wc[4 * f] = q_wc[4 * f + 1] = q_wc[4 * f + 2] = 0.0; q_wc[4 * f + 3] = 1.0; p_wc[3 * f] = p_wc[3 * f + 1] = p_wc[3 * f + 2] = 0.0; valid[f] = 0; if (mean_err) mean_err[f] = 0.0;
+    std::vector<PoseObs> ob;
+    for (int c = off[f]; c < off[f + 1]; ++c) {
+      const int id = ids[c]; double xy[2];
+      if (id < 0 || id >= np || !oracle_unproject(o.model, o.intr, uv[2 * c], uv[2 * c + 1], xy)) continue;
+      const double* P = &o.points[4 * (size_t)id];
+      ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], xy[0], xy[1]});
+    }
+    if (off[f + 1] - off[f] < min_points || ob.size() < 6) continue;
+    const double n = (double)ob.size();
+    double zref = 0.0, mX = 0, mY = 0, mx = 0, my = 0;
+    for (const PoseObs& p : ob) { zref += p.Z; mX += p.X; mY += p.Y; mx += p.x; my += p.y; }
+    zref /= n; mX /= n; mY /= n; mx /= n; my /= n;
+    double dB = 0, dI = 0, dz = 0; for (const PoseObs& p : ob) { dB += std::hypot(p.X - mX, p.Y - mY); dI += std::hypot(p.x - mx, p.y - my); dz = std::max(dz, std::fabs(p.Z - zref)); }
+    dB /= n; dI /= n;
+    if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * std::max(1.0, dB)) continue;   // degenerate or non-planar target
+    const double sB = std::sqrt(2.0) / dB, sI = std::sqrt(2.0) / dI;
+    // DLT: null vector of A^T A (9 x 9) by inverse iteration with a tiny shift
+    std::vector<double> M(81, 0.0);
+    for (const PoseObs& p : ob) {
+      const double X = (p.X - mX) * sB, Y = (p.Y - mY) * sB, x = (p.x - mx) * sI, y = (p.y - my) * sI;
+      const double ra[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x}, rb[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+      for (int a2 = 0; a2 < 9; ++a2) for (int b2 = 0; b2 < 9; ++b2) M[a2 * 9 + b2] += ra[a2] * ra[b2] + rb[a2] * rb[b2];
+    }
+    double tr = 0; for (int a2 = 0; a2 < 9; ++a2) tr += M[a2 * 9 + a2];
+    std::vector<double> hv(9, 1.0 / 3.0);
+    bool okh = true;
+    for (int it = 0; it < 8 && okh; ++it) {
+      std::vector<double> A = M, b = hv;
+      for (int a2 = 0; a2 < 9; ++a2) A[a2 * 9 + a2] += 1e-14 * tr;
+      okh = gauss_solve(9, A, b);
+      double nn = 0; for (double v : b) nn += v * v; nn = std::sqrt(nn);
+      if (!(nn > 0.0)) { okh = false; break; }
+      for (int a2 = 0; a2 < 9; ++a2) hv[a2] = b[a2] / nn;
+    }
+    if (!okh) continue;
+    double G[9], Hm[9];
+    for (int r = 0; r < 3; ++r) { G[3 * r] = hv[3 * r] * sB; G[3 * r + 1] = hv[3 * r + 1] * sB; G[3 * r + 2] = hv[3 * r + 2] - sB * (hv[3 * r] * mX + hv[3 * r + 1] * mY); }
+    for (int c = 0; c < 3; ++c) { Hm[c] = G[c] / sI + mx * G[6 + c]; Hm[3 + c] = G[3 + c] / sI + my * G[6 + c]; Hm[6 + c] = G[6 + c]; }
+    const Vd h1{Hm[0], Hm[3], Hm[6]}, h2{Hm[1], Hm[4], Hm[7]}, h3{Hm[2], Hm[5], Hm[8]};
+    double sc = 2.0 / (vnorm(h1) + vnorm(h2));
+    if (h3.z * sc < 0.0) sc = -sc;
+    Vd r1 = h1 * sc, r2 = h2 * sc, t = h3 * sc;
+    r1 = r1 * (1.0 / vnorm(r1)); r2 = r2 - r1 * dot(r1, r2); r2 = r2 * (1.0 / vnorm(r2));
+    const Vd r3 = cross(r1, r2);
+    Qd R = quat_from_cols(r1, r2, r3);
+    for (PoseObs& p : ob) p.Z -= zref;
+    pose_gauss_newton(ob, R, t);
+    std::vector<PoseObs> in;
+    for (const PoseObs& p : ob) { const Vd Pc = so3_act(R, Vd{p.X, p.Y, p.Z}) + t; const double r0 = Pc.x / Pc.z - p.x, r1e = Pc.y / Pc.z - p.y; if (Pc.z > 0.0 && r0 * r0 + r1e * r1e < thresh_sq) in.push_back(p); }
+    if (in.size() < 6) continue;
+    if (in.size() != ob.size()) pose_gauss_newton(in, R, t);
+    double e = 0; for (const PoseObs& p : in) { const Vd Pc = so3_act(R, Vd{p.X, p.Y, p.Z}) + t; e += std::hypot(Pc.x / Pc.z - p.x, Pc.y / Pc.z - p.y); }
+    e /= (double)in.size();
+    const Vd tf = t - so3_act(R, Vd{0.0, 0.0, zref});
+    const Qd Rw = so3_inv(R);
+    const Vd pw = so3_act(Rw, tf) * -1.0;
+    q_wc[4 * f] = Rw.x; q_wc[4 * f + 1] = Rw.y; q_wc[4 * f + 2] = Rw.z; q_wc[4 * f + 3] = Rw.w;
+    p_wc[3 * f] = pw.x; p_wc[3 * f + 1] = pw.y; p_wc[3 * f + 2] = pw.z;
+    if (mean_err) mean_err[f] = e;
+    valid[f] = e <= max_px ? 1 : 0;
+  }
+  return ICC_OK;
+}
+
 int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }
 
 }  // extern "C"

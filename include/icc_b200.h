@@ -207,6 +207,23 @@ icc_status icc_estimate_board_poses(icc_handle* h, int n_frames, const int32_t* 
 /* theia::Camera::PixelToNormalizedCoordinates / z for `n` pixels with the handle's camera: xy_out[2n], ok[n] (nullable). */
 icc_status icc_pixels_to_normalized(icc_handle* h, int n, const double* uv, double* xy_out, int32_t* ok);
 
+/* ---- upstream row f3: IMU-to-camera rotation + time offset initialiser -----------------------------------
+ * ImuToCameraRotationEstimator::EstimateCameraImuRotation (src/core/imu_to_camera_rotation_estimator.cc:116-274) together with
+ * the preparation done by applications/estimate_imu_to_camera_rotation.cc:96-173: view rotations q_cw (quaternion of
+ * theia::Camera::GetOrientationAsRotationMatrix, app :125-127) resampled to the median frame interval, interpolated to the IMU
+ * rate, differentiated to a visual angular velocity, both streams smoothed by a 15-tap moving average, then a golden-section
+ * search over the time offset in [-1, 1] s (tolerance 1e-4 s) around the closed-form rotation (+ gyroscope bias) fit.
+ * Inputs: views (any order; timestamps already include the first-image offset of app :80-86), gyroscope samples (any order);
+ * gyro_bias_in = NULL enables the bias estimation (EnableGyroBiasEstimation, app :63-67), otherwise it is subtracted from the
+ * samples (app :99-100) and returned unchanged.  Outputs: q_gyro_to_cam (x,y,z,w) as written to "gyro_to_camera_rotation",
+ * the time offset "time_offset_gyro_to_cam", the gyroscope bias, the final alignment error and the number of iterations.
+ * One documented divergence: where the reference's InterpolateVector3d reads one element past the end of its input
+ * (utils.cc:250-256, undefined behaviour) the last sample is used as is. */
+icc_status icc_estimate_imu_to_camera_rotation(icc_handle* h, int n_views, const double* view_t_s, const double* q_cw_xyzw,
+                                               int n_imu, const double* imu_t_s, const double* gyro_xyz, const double* gyro_bias_in /* 3 or NULL */,
+                                               double* q_gyro_to_cam_xyzw /* 4 */, double* time_offset_s, double* gyro_bias_out /* 3 */,
+                                               double* alignment_error, int32_t* iterations);
+
 /* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
 void icc_trim_device_cache(void);
 

@@ -151,6 +151,18 @@ class CApi:
         self._call("pixels_to_normalized", [C.c_int, c_double_p, c_double_p, c_int32_p], n, _dp(uv), _dp(xy), ok.ctypes.data_as(c_int32_p))
         return xy, ok
 
+    # ---- upstream row f3: ImuToCameraRotationEstimator (src/core/imu_to_camera_rotation_estimator.cc:116-274) -----------------
+    def estimate_imu_to_camera_rotation(self, view_t_s, q_cw_xyzw, imu_t_s, gyro, gyro_bias=None):
+        """-> dict(q_gyro_to_cam (x,y,z,w), time_offset_s, gyro_bias[3], error, iterations); gyro_bias=None estimates the bias."""
+        vt = _f64(view_t_s); q = _f64(q_cw_xyzw); it = _f64(imu_t_s); g = _f64(gyro)
+        assert q.size == 4 * vt.size and g.size == 3 * it.size
+        qo = np.zeros(4); td = C.c_double(); bo = np.zeros(3); err = C.c_double(); iters = C.c_int32()
+        b = None if gyro_bias is None else _f64(gyro_bias)
+        self._call("estimate_imu_to_camera_rotation", [C.c_int, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                                       C.POINTER(C.c_double), c_double_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)],
+                   vt.size, _dp(vt), _dp(q), it.size, _dp(it), _dp(g), None if b is None else _dp(b), _dp(qo), C.byref(td), _dp(bo), C.byref(err), C.byref(iters))
+        return dict(q_gyro_to_cam=qo, time_offset_s=td.value, gyro_bias=bo, error=err.value, iterations=iters.value)
+
     def set_shard(self, rank, world):
         self._call("set_shard", [C.c_int, C.c_int], int(rank), int(world))
 

@@ -904,6 +904,92 @@ icc_status icc_estimate_board_poses(icc_handle* h, int nf, const int32_t* off, c
   return ICC_OK;
 }
 
+// ---- upstream row f3: IMU-to-camera rotation + time offset initialiser ---------------------------------------------------
+namespace {
+double median_like_reference(std::vector<double> v) {   // utils::MedianOfDoubleVec (src/utils/utils.cc:77-97)
+  const size_t n = v.size();
+  if (n % 2 == 0) {
+    std::nth_element(v.begin(), v.begin() + n / 2 - 1, v.end()); const double e1 = v[n / 2 - 1];
+    std::nth_element(v.begin(), v.begin() + n / 2, v.end()); const double e2 = v[n / 2];
+    return (e1 + e2) / 2;
+  }
+  std::nth_element(v.begin(), v.begin() + n / 2, v.end());
+  return v[n / 2];
+}
+void quat_from_rowmajor(const double* R, double* q) {    // -> x, y, z, w
+  const double m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8], tr = m00 + m11 + m22;
+  double x, y, z, w;
+  if (tr > 0.0) { const double s = std::sqrt(tr + 1.0) * 2.0; w = 0.25 * s; x = (m21 - m12) / s; y = (m02 - m20) / s; z = (m10 - m01) / s; }
+  else if (m00 > m11 && m00 > m22) { const double s = std::sqrt(1.0 + m00 - m11 - m22) * 2.0; w = (m21 - m12) / s; x = 0.25 * s; y = (m01 + m10) / s; z = (m02 + m20) / s; }
+  else if (m11 > m22) { const double s = std::sqrt(1.0 + m11 - m00 - m22) * 2.0; w = (m02 - m20) / s; x = (m01 + m10) / s; y = 0.25 * s; z = (m12 + m21) / s; }
+  else { const double s = std::sqrt(1.0 + m22 - m00 - m11) * 2.0; w = (m10 - m01) / s; x = (m02 + m20) / s; y = (m12 + m21) / s; z = 0.25 * s; }
+  const double n = std::sqrt(x * x + y * y + z * z + w * w);
+  q[0] = x / n; q[1] = y / n; q[2] = z / n; q[3] = w / n;
+}
+}  // namespace
+
+icc_status icc_estimate_imu_to_camera_rotation(icc_handle* h, int n_views, const double* view_t, const double* q_cw, int n_imu, const double* imu_t,
+                                               const double* gyro, const double* bias_in, double* q_out, double* td_out, double* bias_out, double* err_out, int32_t* iters_out) {
+  if (!h || n_views < 2 || !view_t || !q_cw || n_imu < 2 || !imu_t || !gyro || !q_out || !td_out) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(h->device));
+  // ---- host preparation (app :96-162): ordered maps, median frame interval, regular grid, common window ------------------
+  // std::map semantics of the reference (time ordered, a repeated timestamp keeps the LAST sample); already-sorted input -- the
+  // normal case -- skips the tree
+  auto ordered = [](const double* t, int n) { std::vector<std::pair<double, int>> o; o.reserve(n);
+    bool inc = true; for (int i = 1; i < n && inc; ++i) inc = t[i] > t[i - 1];
+    if (inc) { for (int i = 0; i < n; ++i) o.emplace_back(t[i], i); return o; }
+    std::map<double, int> m; for (int i = 0; i < n; ++i) m[t[i]] = i;
+    for (const auto& kv : m) o.emplace_back(kv.first, kv.second);
+    return o; };
+  const std::vector<std::pair<double, int>> vmap = ordered(view_t, n_views), gmap = ordered(imu_t, n_imu);
+  if (vmap.size() < 2 || gmap.size() < 2) return fail(h, ICC_ERR_INVALID_ARGUMENT, "need at least two distinct view and gyroscope timestamps");
+  double imu_dt = 0.0;
+  for (int i = 1; i < n_imu; ++i) imu_dt += imu_t[i] - imu_t[i - 1];                     // app :103-108 (file order)
+  imu_dt /= (double)(n_imu - 1);
+  std::vector<double> tv; std::vector<double4> qv;
+  for (const auto& kv : vmap) { tv.push_back(kv.first); const double* q = q_cw + 4 * (size_t)kv.second; qv.push_back(make_double4(q[0], q[1], q[2], q[3])); }
+  std::vector<double> diffs; for (size_t i = 1; i < tv.size(); ++i) diffs.push_back(tv[i] - tv[i - 1]);
+  const double cam_dt = median_like_reference(diffs);
+  if (!(cam_dt > 0.0)) return fail(h, ICC_ERR_INVALID_ARGUMENT, "non-positive median frame interval");
+  std::vector<double> grid; for (double t = tv.front(); t < tv.back(); t += cam_dt) grid.push_back(t);   // app :139-144
+  std::vector<double> tg, gg;    // gyroscope, time ordered, bias removed
+  for (const auto& kv : gmap) { tg.push_back(kv.first); for (int d = 0; d < 3; ++d) gg.push_back(gyro[3 * (size_t)kv.second + d] - (bias_in ? bias_in[d] : 0.0)); }
+  const double t0 = grid.front() >= tg.front() ? grid.front() : tg.front();               // :127-129
+  const double tend = grid.back() >= tg.back() ? grid.back() : tg.back();                 // (the LATER end, as in the reference)
+  std::vector<double> tI, wI; for (size_t i = 0; i < tg.size(); ++i) if (tg[i] >= t0 && tg[i] <= tend) { tI.push_back(tg[i] - t0); for (int d = 0; d < 3; ++d) wI.push_back(gg[3 * i + d]); }
+  size_t g0 = 0; while (g0 < grid.size() && grid[g0] < t0) ++g0;
+  std::vector<double> tV; for (size_t i = g0; i < grid.size(); ++i) if (grid[i] <= tend) tV.push_back(grid[i] - t0);
+  const int N = (int)tI.size(), Mc = (int)tV.size(), M = (int)grid.size(), nv = (int)tv.size();
+  if (N < 2 || Mc < 1) return fail(h, ICC_ERR_INVALID_ARGUMENT, "camera and gyroscope streams do not overlap");
+  // ---- device pipeline --------------------------------------------------------------------------------------------------
+  DevBuf<double> d_tv, d_grid, d_tV, d_tI, d_wI, d_wraw, d_wheld, d_wvis, d_wimu, d_shift; DevBuf<double4> d_qv, d_qgrid, d_qi; DevBuf<unsigned char> d_bad; DevBuf<RotInitState> d_state;
+  CU(d_tv.upload(tv)); CU(d_qv.upload(qv)); CU(d_grid.upload(grid)); CU(d_tV.upload(tV)); CU(d_tI.upload(tI)); CU(d_wI.upload(wI));
+  CU(d_qgrid.alloc(M)); CU(d_qi.alloc(N)); CU(d_wraw.alloc(3 * (size_t)N)); CU(d_wheld.alloc(3 * (size_t)N)); CU(d_wvis.alloc(3 * (size_t)N)); CU(d_wimu.alloc(3 * (size_t)N));
+  CU(d_shift.alloc(6 * (size_t)N)); CU(d_bad.alloc(N)); CU(d_state.alloc(1));
+  launch_interp_quat(nv, d_tv.p, d_qv.p, M, d_grid.p, d_qgrid.p, h->stream);              // views -> regular frame grid (app :150-156)
+  launch_interp_quat(Mc, d_tV.p, d_qgrid.p + g0, N, d_tI.p, d_qi.p, h->stream);           // grid -> IMU rate (:172-173)
+  launch_visual_angular_velocity(N, d_qi.p, imu_dt, d_wraw.p, d_bad.p, d_wheld.p, d_wvis.p, d_wI.p, d_wimu.p, h->stream);
+  RotInitProblem Q; memset(&Q, 0, sizeof Q);
+  Q.n = N; Q.t = d_tI.p; Q.vis = d_wvis.p; Q.imu = d_wimu.p; Q.vis_shift = d_shift.p; Q.state = d_state.p;
+  Q.estimate_bias = bias_in ? 0 : 1; Q.tolerance = 1e-4;
+  for (int d = 0; d < 3; ++d) Q.bias_in[d] = bias_in ? bias_in[d] : 0.0;
+  // the bracket shrinks by the golden ratio per step whatever the data says, so the step count is known up to rounding
+  int n_it = 0; { const double g = (1.0 + std::sqrt(5.0)) / 2.0; double a = -1.0, b = 1.0, c = b - (b - a) / g, d = a + (b - a) / g; while (std::fabs(c - d) > Q.tolerance && n_it < 200) { b = d; c = b - (b - a) / g; d = a + (b - a) / g; ++n_it; } }
+  launch_golden_section(Q, 1.0, n_it + 2, h->sm_count > 0 ? h->sm_count : 148, h->stream);
+  RotInitState S;
+  CU(cudaMemcpyAsync(&S, d_state.p, sizeof S, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cudaGetLastError() != cudaSuccess) return fail(h, ICC_ERR_CUDA, "rotation initialiser kernels failed");
+  if (!S.done) return fail(h, ICC_ERR_NUMERIC, "golden-section search did not terminate");
+  quat_from_rowmajor(S.R_best, q_out);
+  *td_out = (S.b + S.a) / 2;                                                               // :259
+  if (bias_out) for (int d = 0; d < 3; ++d) bias_out[d] = S.bias_best[d];
+  if (err_out) *err_out = S.error;
+  if (iters_out) *iters_out = S.iterations;
+  return ICC_OK;
+}
+
 void icc_trim_device_cache(void) { block_cache().trim(); }
 
 }  // extern "C"

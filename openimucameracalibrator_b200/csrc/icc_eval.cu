@@ -587,6 +587,7 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
   const size_t sm_vis_k = WARPS * sizeof(WarpCtx) + WARPS * 56 * LDJ * sizeof(double);
   const size_t sm_imu_nb = WARPS * sizeof(WarpCtx) + WARPS * 40 * LDJ * sizeof(double);
   const size_t sm_imu_b = WARPS * sizeof(WarpCtx) + WARPS * 56 * LDJ * sizeof(double);
+  const size_t sm_cost = WARPS * sizeof(WarpCtx);   // the cost-only kernels never touch a tile: more CTAs per SM
   static bool attr_done = false;
   if (!attr_done) {
     int e = 0;
@@ -603,7 +604,7 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     const int grid = grid_for(P.n_vwork, sm_count);
     if (with_jacobian && P.cam_intr_active) vision_kernel<2><<<grid, WARPS * 32, sm_vis_k, st>>>(P, S, cost_out, residuals_out, reproj_out);
     else if (with_jacobian) vision_kernel<1><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
-    else vision_kernel<0><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);
+    else vision_kernel<0><<<grid, WARPS * 32, sm_cost, st>>>(P, S, cost_out, residuals_out, reproj_out);
     count_launch();
   }
   if (P.n_iwork > 0) {
@@ -612,10 +613,10 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     if (P.bias_active || P.intr_active) {
       if (with_jacobian && P.intr_active) imu_kernel<true, 2><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
       else if (with_jacobian) imu_kernel<true, 1><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
-      else imu_kernel<false, 1><<<grid, WARPS * 32, sm_imu_b, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, 1><<<grid, WARPS * 32, sm_cost, st>>>(P, S, cost_out, residuals_out);
     } else {
       if (with_jacobian) imu_kernel<true, 0><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
-      else imu_kernel<false, 0><<<grid, WARPS * 32, sm_imu_nb, st>>>(P, S, cost_out, residuals_out);
+      else imu_kernel<false, 0><<<grid, WARPS * 32, sm_cost, st>>>(P, S, cost_out, residuals_out);
     }
     count_launch();
   }

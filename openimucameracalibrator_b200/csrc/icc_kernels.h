@@ -95,6 +95,28 @@ struct PoseProblem {
 };
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st);
 void launch_board_poses(const PoseProblem& Q, const double2* xy, const int* ok, unsigned char* use, double* q_wc, double* p_wc, double* err, int* valid, cudaStream_t st);
+// ---- IMU-to-camera rotation + time offset initialiser (icc_rotinit.cu) -----------------------------------------------------
+struct RotInitState {
+  double a, b, c, d;          // golden-section bracket and its two interior candidates (time offsets, seconds)
+  double sums[2][16];         // per candidate: sum vis (3), sum imu (3), sum imu x vis (9), robust error
+  double R[2][9], bias[2][3]; // per candidate closed-form solution (row-major)
+  double R_best[9], bias_best[3], error;
+  int iterations, done;
+};
+struct RotInitProblem {
+  int n;                      // IMU samples inside the common time window
+  const double* t;            // their zero-based timestamps (sorted)
+  const double* vis;          // smoothed visual angular velocity at those times (3 per sample)
+  const double* imu;          // smoothed gyroscope rates (3 per sample)
+  double* vis_shift;          // scratch: 2 x 3n, the shifted + interpolated visual rates of both candidates
+  RotInitState* state;
+  int estimate_bias;
+  double tolerance;
+  double bias_in[3];
+};
+void launch_interp_quat(int n_old, const double* t_old, const double4* q_old, int n_new, const double* t_new, double4* q_new, cudaStream_t st);
+void launch_visual_angular_velocity(int n, const double4* q, double dt_imu, double* w_raw, unsigned char* bad, double* w_held, double* w_smooth, const double* imu, double* imu_smooth, cudaStream_t st);
+void launch_golden_section(const RotInitProblem& Q, double max_offset, int max_iterations, int sm_count, cudaStream_t st);
 int kernel_launch_count();
 
 }  // namespace icc

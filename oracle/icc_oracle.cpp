@@ -1161,6 +1161,153 @@ icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const 
   return ICC_OK;
 }
 
+// ---- upstream row f3: IMU-to-camera rotation + time offset initialiser (TEST INFRASTRUCTURE) -------------------------------
+// Restates src/core/imu_to_camera_rotation_estimator.cc:39-274 + applications/estimate_imu_to_camera_rotation.cc:96-162 serially,
+// with the closed-form rotation through an SVD (one-sided Jacobi) exactly as the reference formulates it (the CUDA path uses
+// Horn's quaternion method instead).  FindClosestTimestamp's linear scan is replaced by bisection (same index on sorted times).
+namespace {
+size_t nearest_sorted(const std::vector<double>& ts, double t, double& dist) {
+  const size_t n = ts.size();
+  size_t hi = std::lower_bound(ts.begin(), ts.end(), t) - ts.begin();
+  size_t idx = hi == 0 ? 0 : (hi == n ? n - 1 : (std::fabs(t - ts[hi - 1]) <= std::fabs(t - ts[hi]) ? hi - 1 : hi));
+  dist = std::fabs(t - ts[idx]);
+  return idx;
+}
+void slerp_eigen(const double* a, const double* b, double t, double* o) {
+  const double thresh = 1.0 - 2.220446049250313e-16;
+  const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3], ad = std::fabs(d);
+  double s0, s1;
+  if (ad >= thresh) { s0 = 1.0 - t; s1 = t; } else { const double th = std::acos(ad), sth = std::sin(th); s0 = std::sin((1.0 - t) * th) / sth; s1 = std::sin(t * th) / sth; }
+  if (d < 0) s1 = -s1;
+  for (int i = 0; i < 4; ++i) o[i] = s0 * a[i] + s1 * b[i];
+}
+void interp_quats(const std::vector<double>& t_old, const std::vector<double>& t_new, const std::vector<double>& q_old, std::vector<double>& q_new) {
+  q_new.assign(4 * t_new.size(), 0.0);
+  for (size_t i = 0; i < t_new.size(); ++i) {
+    double dist; const size_t k = nearest_sorted(t_old, t_new[i], dist);
+    if (k < t_old.size() - 1) slerp_eigen(&q_old[4 * k], &q_old[4 * (k + 1)], dist / (t_old[k + 1] - t_old[k]), &q_new[4 * i]);
+    else for (int d = 0; d < 4; ++d) q_new[4 * i + d] = q_old[4 * k + d];
+  }
+}
+// SVD of a 3x3 matrix by one-sided Jacobi: A = U diag(s) V^T
+void svd3(const double A[3][3], double U[3][3], double s[3], double V[3][3]) {
+  double B[3][3]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { B[i][j] = A[i][j]; V[i][j] = i == j ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 3; ++p) for (int q = p + 1; q < 3; ++q) {
+      double al = 0, be = 0, ga = 0;
+      for (int k = 0; k < 3; ++k) { al += B[k][p] * B[k][p]; be += B[k][q] * B[k][q]; ga += B[k][p] * B[k][q]; }
+      off = std::max(off, std::fabs(ga) / std::sqrt(std::max(al * be, 1e-300)));
+      if (std::fabs(ga) < 1e-300) continue;
+      const double zeta = (be - al) / (2.0 * ga), t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+      for (int k = 0; k < 3; ++k) { const double bp = B[k][p], bq = B[k][q]; B[k][p] = c * bp - sn * bq; B[k][q] = sn * bp + c * bq; const double vp = V[k][p], vq = V[k][q]; V[k][p] = c * vp - sn * vq; V[k][q] = sn * vp + c * vq; }
+    }
+    if (off < 1e-15) break;
+  }
+  for (int j = 0; j < 3; ++j) { s[j] = std::sqrt(B[0][j] * B[0][j] + B[1][j] * B[1][j] + B[2][j] * B[2][j]); }
+  // U columns = B columns / s ; complete a rank-deficient basis by cross products
+  for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) U[k][j] = s[j] > 1e-300 ? B[k][j] / s[j] : 0.0;
+  int order[3] = {0, 1, 2}; std::sort(order, order + 3, [&](int a, int b) { return s[a] > s[b]; });
+  if (!(s[order[2]] > 1e-12 * std::max(s[order[0]], 1e-300))) {     // smallest singular vector: u3 = u1 x u2
+    const int a = order[0], b = order[1], c = order[2];
+    U[0][c] = U[1][a] * U[2][b] - U[2][a] * U[1][b]; U[1][c] = U[2][a] * U[0][b] - U[0][a] * U[2][b]; U[2][c] = U[0][a] * U[1][b] - U[1][a] * U[0][b];
+  }
+}
+double det3(const double M[3][3]) { return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]); }
+struct RotFit { double R[3][3]; double bias[3]; double error; };
+RotFit solve_closed_form(const std::vector<double>& angVis, const std::vector<double>& angImu, const std::vector<double>& ts, double td, bool estimate_bias) {
+  const size_t n = ts.size();
+  std::vector<double> two(n); for (size_t i = 0; i < n; ++i) two[i] = ts[i] - td;
+  std::vector<double> iv(3 * n);
+  for (size_t i = 0; i < n; ++i) {                                           // InterpolateVector3d(time_with_offset, timestamps, angVis)
+    double dist; const size_t k = nearest_sorted(two, ts[i], dist);
+    if (k + 1 >= n) { for (int d = 0; d < 3; ++d) iv[3 * i + d] = angVis[3 * k + d]; continue; }   // reference: out-of-bounds read (UB)
+    const double f = dist / (two[k + 1] - two[k]);
+    for (int d = 0; d < 3; ++d) iv[3 * i + d] = (1.0 - f) * angVis[3 * k + d] + f * angVis[3 * (k + 1) + d];
+  }
+  double mv[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+  for (size_t i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) { mi[d] += angImu[3 * i + d]; mv[d] += iv[3 * i + d]; }
+  for (int d = 0; d < 3; ++d) { mi[d] /= (double)n; mv[d] /= (double)n; }
+  double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};                         // P^T Q
+  for (size_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) M[a][b] += (angImu[3 * i + a] - mi[a]) * (iv[3 * i + b] - mv[b]);
+  double U[3][3], sv[3], V[3][3];
+  svd3(M, U, sv, V);
+  double VUt[3][3]; for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { VUt[a][b] = 0; for (int k = 0; k < 3; ++k) VUt[a][b] += V[a][k] * U[b][k]; }
+  // C = diag(1, 1, -1) on the LAST column of V / U in Eigen's descending singular value order -> flip the smallest here
+  RotFit r;
+  int smallest = 0; for (int k = 1; k < 3; ++k) if (sv[k] < sv[smallest]) smallest = k;
+  const double sgn = det3(VUt) < 0.0 ? -1.0 : 1.0;
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { r.R[a][b] = 0; for (int k = 0; k < 3; ++k) r.R[a][b] += V[a][k] * (k == smallest ? sgn : 1.0) * U[b][k]; }
+  for (int d = 0; d < 3; ++d) r.bias[d] = estimate_bias ? mv[d] - (r.R[d][0] * mi[0] + r.R[d][1] * mi[1] + r.R[d][2] * mi[2]) : 0.0;
+  r.error = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    double e2 = 0;
+    for (int d = 0; d < 3; ++d) { const double D = iv[3 * i + d] - (r.R[d][0] * angImu[3 * i] + r.R[d][1] * angImu[3 * i + 1] + r.R[d][2] * angImu[3 * i + 2] + r.bias[d]); e2 += D * D; }
+    r.error += e2 > 1.345 ? 2.0 * 1.345 * std::sqrt(e2) - 1.345 * 1.345 : e2;
+  }
+  return r;
+}
+}  // namespace
+
+icc_status icco_estimate_imu_to_camera_rotation(void* h, int n_views, const double* view_t, const double* q_cw, int n_imu, const double* imu_t, const double* gyro,
+                                                const double* bias_in, double* q_out, double* td_out, double* bias_out, double* err_out, int32_t* iters_out) {
+  (void)h;
+  std::map<double, int> vmap, gmap;
+  for (int i = 0; i < n_views; ++i) vmap[view_t[i]] = i;
+  for (int i = 0; i < n_imu; ++i) gmap[imu_t[i]] = i;
+  if (vmap.size() < 2 || gmap.size() < 2) return ICC_ERR_INVALID_ARGUMENT;
+  double imu_dt = 0.0; for (int i = 1; i < n_imu; ++i) imu_dt += imu_t[i] - imu_t[i - 1]; imu_dt /= (double)(n_imu - 1);
+  std::vector<double> tv, qv; for (const auto& kv : vmap) { tv.push_back(kv.first); for (int d = 0; d < 4; ++d) qv.push_back(q_cw[4 * (size_t)kv.second + d]); }
+  std::vector<double> diffs; for (size_t i = 1; i < tv.size(); ++i) diffs.push_back(tv[i] - tv[i - 1]);
+  std::sort(diffs.begin(), diffs.end());
+  const double cam_dt = diffs.size() % 2 == 0 ? (diffs[diffs.size() / 2 - 1] + diffs[diffs.size() / 2]) / 2 : diffs[diffs.size() / 2];
+  std::vector<double> grid; for (double t = tv.front(); t < tv.back(); t += cam_dt) grid.push_back(t);
+  std::vector<double> qgrid; interp_quats(tv, grid, qv, qgrid);
+  std::vector<double> tg, gg; for (const auto& kv : gmap) { tg.push_back(kv.first); for (int d = 0; d < 3; ++d) gg.push_back(gyro[3 * (size_t)kv.second + d] - (bias_in ? bias_in[d] : 0.0)); }
+  const double t0 = grid.front() >= tg.front() ? grid.front() : tg.front(), tend = grid.back() >= tg.back() ? grid.back() : tg.back();
+  std::vector<double> tI, angImu; for (size_t i = 0; i < tg.size(); ++i) if (tg[i] >= t0 && tg[i] <= tend) { tI.push_back(tg[i] - t0); for (int d = 0; d < 3; ++d) angImu.push_back(gg[3 * i + d]); }
+  std::vector<double> tV, qV; for (size_t i = 0; i < grid.size(); ++i) if (grid[i] >= t0 && grid[i] <= tend) { tV.push_back(grid[i] - t0); for (int d = 0; d < 4; ++d) qV.push_back(qgrid[4 * i + d]); }
+  const size_t n = tI.size();
+  if (n < 2 || tV.empty()) return ICC_ERR_INVALID_ARGUMENT;
+  std::vector<double> qi; interp_quats(tV, tI, qV, qi);
+  std::vector<double> qd(4 * n, 0.0);
+  for (size_t i = 1; i < n; ++i) for (int d = 0; d < 4; ++d) qd[4 * (i - 1) + d] = qi[4 * i + d] - qi[4 * (i - 1) + d];
+  for (int d = 0; d < 4; ++d) qd[4 * (n - 1) + d] = qd[4 * (n - 2) + d];
+  std::vector<double> angVis(3 * n);
+  for (size_t i = 0; i < n; ++i) {
+    const double* q = &qi[4 * i]; const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const Q4<double> inv{-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2}, dq{qd[4 * i], qd[4 * i + 1], qd[4 * i + 2], qd[4 * i + 3]};
+    // plain (non-normalising) quaternion product, Eigen operator*
+    const double ax = dq.w * inv.x + dq.x * inv.w + dq.y * inv.z - dq.z * inv.y, ay = dq.w * inv.y + dq.y * inv.w + dq.z * inv.x - dq.x * inv.z, az = dq.w * inv.z + dq.z * inv.w + dq.x * inv.y - dq.y * inv.x;
+    const double s2 = -2.0 / imu_dt; double w[3] = {s2 * ax, s2 * ay, s2 * az};
+    if (std::fabs(w[0]) > 2 * M_PI || std::fabs(w[1]) > 2 * M_PI || std::fabs(w[2]) > 2 * M_PI) { for (int d = 0; d < 3; ++d) w[d] = i > 1 ? angVis[3 * (i - 1) + d] : 0.0; }
+    for (int d = 0; d < 3; ++d) angVis[3 * i + d] = w[d];
+  }
+  auto smooth = [&](const std::vector<double>& x) { std::vector<double> y(x.size()); for (size_t i = 0; i < n; ++i) { const size_t k0 = i >= 14 ? i - 14 : 0; for (int d = 0; d < 3; ++d) { double s2 = 0; for (size_t k = k0; k <= i; ++k) s2 += x[3 * k + d]; y[3 * i + d] = s2 / (double)(i - k0 + 1); } } return y; };
+  const std::vector<double> sVis = smooth(angVis), sImu = smooth(angImu);
+  const double g = (1.0 + std::sqrt(5.0)) / 2.0, tol = 1e-4;
+  double a = -1.0, b = 1.0, c = b - (b - a) / g, d = a + (b - a) / g, error = 0.0;
+  double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, bias[3] = {bias_in ? bias_in[0] : 0.0, bias_in ? bias_in[1] : 0.0, bias_in ? bias_in[2] : 0.0};
+  int iter = 0;
+  while (std::fabs(c - d) > tol) {
+    const RotFit fc = solve_closed_form(sVis, sImu, tI, c, !bias_in), fd = solve_closed_form(sVis, sImu, tI, d, !bias_in);
+    const RotFit& k = fc.error < fd.error ? fc : fd;
+    if (fc.error < fd.error) b = d; else a = c;
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) R[r][cc] = k.R[r][cc];
+    if (!bias_in) for (int r = 0; r < 3; ++r) bias[r] = k.bias[r];
+    error = k.error;
+    c = b - (b - a) / g; d = a + (b - a) / g; ++iter;
+  }
+  const Q4<double> q = quat_from_cols(V3<double>{R[0][0], R[1][0], R[2][0]}, V3<double>{R[0][1], R[1][1], R[2][1]}, V3<double>{R[0][2], R[1][2], R[2][2]});
+  q_out[0] = q.x; q_out[1] = q.y; q_out[2] = q.z; q_out[3] = q.w;
+  *td_out = (b + a) / 2;
+  if (bias_out) for (int r = 0; r < 3; ++r) bias_out[r] = bias[r];
+  if (err_out) *err_out = error;
+  if (iters_out) *iters_out = iter;
+  return ICC_OK;
+}
+
 int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }
 
 }  // extern "C"

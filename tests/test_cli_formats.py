@@ -153,3 +153,50 @@ def test_pose_cli_matches_api_and_feeds_the_hot_cli(tmp_path, gpu_factory):
     T_true = ds["truth"]["T_i_c"]
     q_est = np.array([a["q_i_c"]["x"], a["q_i_c"]["y"], a["q_i_c"]["z"], a["q_i_c"]["w"]])
     assert min(np.abs(q_est - T_true[:4]).max(), np.abs(q_est + T_true[:4]).max()) < 5e-3
+
+
+# ---- upstream row f3: estimate_imu_to_camera_rotation ---------------------------------------------------------------------------
+ROT_CLI = os.path.join(ROOT, "openimucameracalibrator_b200", "bin", "estimate_imu_to_camera_rotation")
+
+
+def test_rotation_cli_flags_and_failures(tmp_path):
+    assert os.path.exists(ROT_CLI), "build the CLI first (__graft_entry__.build())"
+    out = subprocess.run([ROT_CLI, "--input_pose_calibration_dataset=/nonexistent.json"], capture_output=True, text=True)
+    assert out.returncode == 1 and "could not read the pose dataset" in out.stderr
+    out = subprocess.run([ROT_CLI, "--no_such_flag=1"], capture_output=True, text=True)
+    assert out.returncode == 1 and "unknown command line flag" in out.stderr
+
+
+@pytest.mark.gpu
+def test_tool_chain_corners_to_calibration(tmp_path, gpu_factory):
+    """The reference's pipeline order with the three drop-in tools: corners -> board poses -> gyro-to-camera rotation + time offset
+    -> spline calibration; every hand-over goes through the files the reference's tools exchange."""
+    cfg = syn.tiny_config(cm.EXTENDED_UNIFIED, (438.0, 1.0, 0.0, 489.5, 272.0, 0.5115, 1.062), n_frames=600, grid=(8, 6), imu_rate_hz=400.0, seed=5)   # (the golden-section search assumes a unimodal objective: not every seed satisfies it)
+    ds = syn.make_dataset(cfg)
+    paths = iof.write_dataset_files(ds, str(tmp_path))
+    pose_json, init_json = str(tmp_path / "poses_gpu.json"), str(tmp_path / "gyro_to_cam_calibration.json")
+    out = subprocess.run([POSE_CLI, "--input_corners=" + paths["input_corners"], "--camera_calibration_json=" + paths["camera_calibration_json"],
+                          "--output_pose_dataset=" + pose_json], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    out = subprocess.run([ROT_CLI, "--input_pose_calibration_dataset=" + pose_json, "--telemetry_json=" + paths["telemetry_json"],
+                          "--imu_rotation_init_output=" + init_json], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    init = json.load(open(init_json))
+    assert set(init) == {"gyro_bias", "gyro_to_camera_rotation", "time_offset_gyro_to_cam"}
+    q = np.array([init["gyro_to_camera_rotation"][k] for k in "xyzw"])
+    q_ci = ds["truth"]["T_i_c"][:4] * np.array([-1.0, -1.0, -1.0, 1.0])
+    assert min(np.abs(q - q_ci).max(), np.abs(q + q_ci).max()) < 2e-2
+    assert abs(init["time_offset_gyro_to_cam"] - ds["time_offset_imu_to_cam_s"]) < 0.03
+    # same numbers as the C-ABI call on the file contents
+    pd = json.load(open(pose_json)); tel = json.load(open(paths["telemetry_json"]))
+    names = sorted(pd["views"])
+    vt = np.array([pd["views"][n]["timestamp_s"] for n in names]) + (tel["img_timestamps_ns"][0] * 1e-9 if tel.get("img_timestamps_ns") else 0.0)
+    qcw = np.array([[-pd["views"][n]["q_wc"][1], -pd["views"][n]["q_wc"][2], -pd["views"][n]["q_wc"][3], pd["views"][n]["q_wc"][0]] for n in names])
+    r = gpu_factory().estimate_imu_to_camera_rotation(vt, qcw, np.array(tel["timestamps_ns"]) * 1e-9, np.array(tel["gyroscope"]))
+    assert abs(r["time_offset_s"] - init["time_offset_gyro_to_cam"]) < 1e-12 and np.abs(r["q_gyro_to_cam"] - q).max() < 1e-9
+    # ... and the hot CLI accepts the estimated initialisation
+    pth = dict(paths, input_pose_dataset=pose_json, gyro_to_cam_initial_calibration=init_json)
+    out = subprocess.run(_args(pth, str(tmp_path)), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    res = iof.read_result_json(str(tmp_path / "result.json"))
+    assert np.isfinite(res["final_reproj_error"]) and abs(res["time_offset_imu_to_cam_s"] - init["time_offset_gyro_to_cam"]) < 1e-12

@@ -224,6 +224,16 @@ icc_status icc_estimate_imu_to_camera_rotation(icc_handle* h, int n_views, const
                                                double* q_gyro_to_cam_xyzw /* 4 */, double* time_offset_s, double* gyro_bias_out /* 3 */,
                                                double* alignment_error, int32_t* iterations);
 
+/* ---- upstream row f2: spline error weighting -----------------------------------------------------------------
+ * python/sew.py:knot_spacing_and_variance (python/sew.py:201-234) as called by python/get_sew_for_dataset.py:38-48 for the
+ * accelerometer (q_r3 = 0.96, dt in [0.01, 0.15]) and the gyroscope (q_so3 = 0.98, dt in [0.01, 0.2]): the largest uniform knot
+ * spacing whose cubic-B-spline interpolation response keeps `quality` of the signal energy, and the variance of the spline fit
+ * error at that spacing (its square root is the "weighting_factor" of spline_error_weighting_json).
+ * signal_xyz: n x 3 samples; times_s: their timestamps (mean rate is used); min_dt / max_dt <= 0 select the defaults of sew.py
+ * (1 / rate and n / 4 / rate).  spectrum (nullable, n doubles) receives the reference spectrum Xhat (make_reference_spectrum). */
+icc_status icc_spline_error_weighting(icc_handle* h, int n, const double* times_s, const double* signal_xyz, double quality, double min_dt, double max_dt,
+                                      double* knot_spacing, double* variance, double* spectrum);
+
 /* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
 void icc_trim_device_cache(void);
 

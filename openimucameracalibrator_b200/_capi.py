@@ -163,6 +163,16 @@ class CApi:
                    vt.size, _dp(vt), _dp(q), it.size, _dp(it), _dp(g), None if b is None else _dp(b), _dp(qo), C.byref(td), _dp(bo), C.byref(err), C.byref(iters))
         return dict(q_gyro_to_cam=qo, time_offset_s=td.value, gyro_bias=bo, error=err.value, iterations=iters.value)
 
+    # ---- upstream row f2: spline error weighting (python/sew.py:knot_spacing_and_variance) ------------------------------------
+    def spline_error_weighting(self, times_s, signal_xyz, quality, min_dt=0.0, max_dt=0.0, want_spectrum=False):
+        """-> (knot_spacing, variance[, reference spectrum Xhat]); signal_xyz is (n, 3)."""
+        t = _f64(times_s); x = _f64(signal_xyz).reshape(-1, 3)
+        assert x.shape[0] == t.size
+        dt = C.c_double(); var = C.c_double(); spec = np.zeros(t.size) if want_spectrum else None
+        self._call("spline_error_weighting", [C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), c_double_p],
+                   t.size, _dp(t), _dp(x), float(quality), float(min_dt), float(max_dt), C.byref(dt), C.byref(var), None if spec is None else _dp(spec))
+        return (dt.value, var.value, spec) if want_spectrum else (dt.value, var.value)
+
     def set_shard(self, rank, world):
         self._call("set_shard", [C.c_int, C.c_int], int(rank), int(world))
 

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -987,6 +988,89 @@ icc_status icc_estimate_imu_to_camera_rotation(icc_handle* h, int n_views, const
   if (bias_out) for (int d = 0; d < 3; ++d) bias_out[d] = S.bias_best[d];
   if (err_out) *err_out = S.error;
   if (iters_out) *iters_out = S.iterations;
+  return ICC_OK;
+}
+
+// ---- upstream row f2: spline error weighting -----------------------------------------------------------------------------
+namespace {
+// scipy.optimize.brentq (Brent 1973 as implemented in scipy/optimize/Zeros/brentq.c), xtol = 2e-12, rtol = 4 eps, 100 iterations
+double brentq(const std::function<double(double)>& f, double xa, double xb, bool& ok) {
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = xa, xcur = xb, xblk = 0.0, fpre = f(xpre), fcur = f(xcur), fblk = 0.0, spre = 0.0, scur = 0.0;
+  ok = true;
+  if (fpre == 0.0) return xpre;
+  if (fcur == 0.0) return xcur;
+  if ((fpre > 0) == (fcur > 0)) { ok = false; return xcur; }
+  for (int i = 0; i < 100; ++i) {
+    if (fpre != 0.0 && fcur != 0.0 && ((fpre > 0) != (fcur > 0))) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+    if (std::fabs(fblk) < std::fabs(fcur)) { xpre = xcur; xcur = xblk; xblk = xpre; fpre = fcur; fcur = fblk; fblk = fpre; }
+    const double delta = (xtol + rtol * std::fabs(xcur)) / 2, sbis = (xblk - xcur) / 2;
+    if (fcur == 0.0 || std::fabs(sbis) < delta) return xcur;
+    if (std::fabs(spre) > delta && std::fabs(fcur) < std::fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);                       // secant
+      else { const double dpre = (fpre - fcur) / (xpre - xcur), dblk = (fblk - fcur) / (xblk - xcur); stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre)); }   // inverse quadratic
+      if (2 * std::fabs(stry) < std::min(std::fabs(spre), 3 * std::fabs(sbis) - delta)) { spre = scur; scur = stry; }
+      else { spre = sbis; scur = sbis; }
+    } else { spre = sbis; scur = sbis; }
+    xpre = xcur; fpre = fcur;
+    if (std::fabs(scur) > delta) xcur += scur; else xcur += (sbis > 0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  ok = false;
+  return xcur;
+}
+}  // namespace
+
+icc_status icc_spline_error_weighting(icc_handle* h, int n, const double* times, const double* signal, double quality, double min_dt, double max_dt,
+                                      double* dt_out, double* var_out, double* spectrum) {
+  if (!h || n < 4 || !times || !signal || !dt_out || !var_out || !(quality > 0.0 && quality < 1.0)) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(h->device));
+  double mean_dt = 0.0; for (int i = 1; i < n; ++i) mean_dt += times[i] - times[i - 1]; mean_dt /= (double)(n - 1);
+  if (!(mean_dt > 0.0)) return fail(h, ICC_ERR_INVALID_ARGUMENT, "timestamps must increase on average");
+  const double sample_rate = 1.0 / mean_dt, d = 1.0 / sample_rate, fscale = 1.0 / ((double)n * d);   // np.fft.fftfreq(n, d): k * (1 / (n d))
+  if (!(min_dt > 0.0)) min_dt = 1.0 / sample_rate;                                                     // sew.py:156-160
+  if (!(max_dt > 0.0)) max_dt = ((double)n / 4.0) / sample_rate;
+  const int M = sew_fft_length(n);
+  DevBuf<double> d_sig, d_xhat, d_scr, d_acc;
+  CU(d_sig.alloc(3 * (size_t)n)); CU(d_xhat.alloc(n)); CU(d_scr.alloc(16 * (size_t)M)); CU(d_acc.alloc(2));
+  CU(cudaMemcpyAsync(d_sig.p, signal, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_sew_spectrum(n, d_sig.p, d_xhat.p, d_acc.p, d_scr.p, h->stream);
+  double esum = 0.0;
+  CU(cudaMemcpyAsync(&esum, d_acc.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (spectrum) CU(cudaMemcpyAsync(spectrum, d_xhat.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cudaGetLastError() != cudaSuccess) return fail(h, ICC_ERR_CUDA, "spectrum kernels failed");
+  const double max_remove = esum / (double)n * (1.0 - quality);                                        // signal_energy(Xhat) * (1 - quality)
+  bool cuda_ok = true;
+  auto removed = [&](double dt) -> double {      // signal_energy((1 - H) * Xhat)
+    double e = 0.0;
+    launch_sew_residual_energy(n, d_xhat.p, fscale, dt, d_acc.p + 1, h->sm_count > 0 ? h->sm_count : 148, h->stream);
+    if (cudaMemcpyAsync(&e, d_acc.p + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) cuda_ok = false;
+    return e / (double)n;
+  };
+  auto quality_func = [&](double dt) { return max_remove / removed(dt); };
+  // find_max_quality_dt(quality_func, 1.0, min_dt, max_dt)   (sew.py:86-145)
+  double dt = max_dt, found = 0.0; bool have = false;
+  if (quality_func(dt) >= 1.0) { found = dt; have = true; }
+  else {
+    double step = max_dt * 0.5, max_quality = 0.0, max_quality_dt = dt; bool any = false;
+    while (!have) {
+      dt -= step; dt = std::max(dt, min_dt);
+      const double q = quality_func(dt);
+      if (q > 1.0) { bool ok; found = brentq([&](double x) { return quality_func(x) - 1.0; }, dt, max_dt, ok); if (!ok) return fail(h, ICC_ERR_NUMERIC, "Brent root search failed"); have = true; }
+      else {
+        step *= 0.5;
+        if (q > max_quality) { max_quality = q; max_quality_dt = dt; any = true; }
+        if (dt <= min_dt) { if (!any) return fail(h, ICC_ERR_NUMERIC, "no knot spacing satisfies the quality"); found = max_quality_dt; have = true; }
+      }
+      if (!cuda_ok) return fail(h, ICC_ERR_CUDA, "quality kernels failed");
+    }
+  }
+  *dt_out = found;
+  *var_out = removed(found) / (double)n;                                                               // dt_to_variance_spectrum (:196-199)
+  if (!cuda_ok) return fail(h, ICC_ERR_CUDA, "quality kernels failed");
   return ICC_OK;
 }
 

@@ -117,6 +117,10 @@ struct RotInitProblem {
 void launch_interp_quat(int n_old, const double* t_old, const double4* q_old, int n_new, const double* t_new, double4* q_new, cudaStream_t st);
 void launch_visual_angular_velocity(int n, const double4* q, double dt_imu, double* w_raw, unsigned char* bad, double* w_held, double* w_smooth, const double* imu, double* imu_smooth, cudaStream_t st);
 void launch_golden_section(const RotInitProblem& Q, double max_offset, int max_iterations, int sm_count, cudaStream_t st);
+// ---- spline error weighting (icc_sew.cu) ------------------------------------------------------------------------------------
+int sew_fft_length(int N);      // power-of-two length of the Bluestein convolution
+void launch_sew_spectrum(int N, const double* signal /* N x 3 */, double* xhat /* N */, double* energy_sum, double* scratch /* 16 * sew_fft_length(N) doubles */, cudaStream_t st);
+void launch_sew_residual_energy(int N, const double* xhat, double fscale, double dt, double* out, int sm_count, cudaStream_t st);
 int kernel_launch_count();
 
 }  // namespace icc

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <thread>
@@ -1305,6 +1306,89 @@ icc_status icco_estimate_imu_to_camera_rotation(void* h, int n_views, const doub
   if (bias_out) for (int r = 0; r < 3; ++r) bias_out[r] = bias[r];
   if (err_out) *err_out = error;
   if (iters_out) *iters_out = iter;
+  return ICC_OK;
+}
+
+// ---- upstream row f2: spline error weighting (restates python/sew.py:36-234; TEST INFRASTRUCTURE) ---------------------------
+// Pinned by tests/golden/sew_*.npz, which are outputs of the reference's own python/sew.py (tests/golden/make_sew_golden.py).
+// Plain O(N^2) DFT with an exact twiddle table (index k n mod N) -- nothing in common with the CUDA path's Bluestein transform.
+namespace {
+double sew_removed_energy(const std::vector<double>& xhat, double fscale, double dt) {
+  const int n = (int)xhat.size();
+  double e = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const int ik = k < (n + 1) / 2 ? k : k - n;
+    const double y = (double)ik * fscale * dt;
+    const double sinc = y == 0.0 ? 1.0 : std::sin(M_PI * y) / (M_PI * y);
+    const double H = 3.0 * std::pow(sinc, 4) / (2.0 + std::cos(2.0 * M_PI * y));
+    const double v = (1.0 - H) * xhat[k];
+    e += v * v;
+  }
+  return e / (double)n;
+}
+double sew_brentq(const std::function<double(double)>& f, double xa, double xb) {    // scipy.optimize.brentq defaults
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = xa, xcur = xb, xblk = 0, fpre = f(xpre), fcur = f(xcur), fblk = 0, spre = 0, scur = 0;
+  if (fpre == 0) return xpre;
+  if (fcur == 0) return xcur;
+  for (int i = 0; i < 100; ++i) {
+    if (fpre != 0 && fcur != 0 && (std::signbit(fpre) != std::signbit(fcur))) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+    if (std::fabs(fblk) < std::fabs(fcur)) { xpre = xcur; xcur = xblk; xblk = xpre; fpre = fcur; fcur = fblk; fblk = fpre; }
+    const double delta = (xtol + rtol * std::fabs(xcur)) / 2, sbis = (xblk - xcur) / 2;
+    if (fcur == 0 || std::fabs(sbis) < delta) return xcur;
+    if (std::fabs(spre) > delta && std::fabs(fcur) < std::fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
+      else { const double dpre = (fpre - fcur) / (xpre - xcur), dblk = (fblk - fcur) / (xblk - xcur); stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre)); }
+      if (2 * std::fabs(stry) < std::min(std::fabs(spre), 3 * std::fabs(sbis) - delta)) { spre = scur; scur = stry; } else { spre = sbis; scur = sbis; }
+    } else { spre = sbis; scur = sbis; }
+    xpre = xcur; fpre = fcur;
+    xcur += std::fabs(scur) > delta ? scur : (sbis > 0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  return xcur;
+}
+}  // namespace
+
+icc_status icco_spline_error_weighting(void* h, int n, const double* times, const double* signal, double quality, double min_dt, double max_dt,
+                                       double* dt_out, double* var_out, double* spectrum) {
+  (void)h;
+  if (n < 4) return ICC_ERR_INVALID_ARGUMENT;
+  std::vector<double> tw_re(n), tw_im(n);
+  for (int m = 0; m < n; ++m) { tw_re[m] = std::cos(-2.0 * M_PI * (double)m / (double)n); tw_im[m] = std::sin(-2.0 * M_PI * (double)m / (double)n); }
+  std::vector<double> xhat(n, 0.0);
+  for (int k = 1; k < n; ++k) {                    // S[:, 0] = 0 (sew.py:179)
+    double s2 = 0.0;
+    for (int ch = 0; ch < 3; ++ch) {
+      double re = 0.0, im = 0.0; long long idx = 0;
+      for (int j = 0; j < n; ++j) { const double x = signal[3 * (size_t)j + ch]; re += x * tw_re[idx]; im += x * tw_im[idx]; idx += k; if (idx >= n) idx -= n; }
+      s2 += re * re + im * im;
+    }
+    xhat[k] = std::sqrt(1.0 / 3.0) * std::sqrt(s2);
+  }
+  if (spectrum) for (int k = 0; k < n; ++k) spectrum[k] = xhat[k];
+  double mean_dt = 0.0; for (int i = 1; i < n; ++i) mean_dt += times[i] - times[i - 1]; mean_dt /= (double)(n - 1);
+  const double sample_rate = 1.0 / mean_dt, d = 1.0 / sample_rate, fscale = 1.0 / ((double)n * d);
+  if (!(min_dt > 0.0)) min_dt = 1.0 / sample_rate;
+  if (!(max_dt > 0.0)) max_dt = ((double)n / 4.0) / sample_rate;
+  double energy = 0.0; for (double v : xhat) energy += v * v; energy /= (double)n;
+  const double max_remove = energy * (1.0 - quality);
+  auto qf = [&](double dt) { return max_remove / sew_removed_energy(xhat, fscale, dt); };
+  double dt = max_dt, found = 0.0;
+  if (qf(dt) >= 1.0) found = dt;
+  else {
+    double step = max_dt * 0.5, best_q = 0.0, best_dt = dt;
+    for (;;) {
+      dt -= step; dt = std::max(dt, min_dt);
+      const double q = qf(dt);
+      if (q > 1.0) { found = sew_brentq([&](double x) { return qf(x) - 1.0; }, dt, max_dt); break; }
+      step *= 0.5;
+      if (q > best_q) { best_q = q; best_dt = dt; }
+      if (dt <= min_dt) { found = best_dt; break; }
+    }
+  }
+  *dt_out = found;
+  *var_out = sew_removed_energy(xhat, fscale, found) / (double)n;
   return ICC_OK;
 }
 

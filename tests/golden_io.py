@@ -7,7 +7,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "tiny_*.npz")))     # (sew_*.npz belong to tests/test_sew.py)
 
 
 def load_golden(path):

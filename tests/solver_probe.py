@@ -7,8 +7,8 @@ if len(sys.argv) >= 2 and sys.argv[1] == "--child":
     from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
     c = int(sys.argv[2])
     ds = syn.make_dataset(syn.CONFIGS[c]) if c > 0 else syn.make_dataset(syn.tiny_config())
-    g = capi.CApi(calibrator.load_library(), "icc_", 0); capi.load_dataset(g, ds)
-    s = g.lm_iterations(1, capi.FLAG_SPLINE | capi.FLAG_T_I_C)
+    g = capi.CApi(calibrator.load_library(), "icc_", 0); capi.load_dataset(g, ds, known_gravity=not (int(os.environ.get('PROBE_FLAGS', 0)) & 16))
+    s = g.lm_iterations(1, int(os.environ.get('PROBE_FLAGS', capi.FLAG_SPLINE | capi.FLAG_T_I_C)))
     so3, r3, _, _ = g.get_knots()
     np.savez(sys.argv[3], so3=so3, r3=r3, T=g.get_T_i_c(), succ=s.successful_steps, cost=s.final_cost)
     sys.exit(0)

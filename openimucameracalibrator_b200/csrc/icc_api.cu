@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -90,7 +92,9 @@ struct icc_handle {
   std::vector<double> so3, r3, ba, bg;       // host mirror of the state (4/3/3/3 doubles per knot)
   double glob[G_COUNT] = {0};
   std::vector<FrameHost> frames;             // frames in the problem (this shard)
-  std::vector<double> used_uv; std::vector<int> used_pid;
+  std::vector<double> used_uv; std::vector<int> used_pid;   // gathered corners -- only when the used frames are not one contiguous run
+  bool used_contig = false; int used_c0 = 0, used_n = 0;    // ... otherwise corners [used_c0, used_c0 + used_n) of uv / point_ids are used in place
+  bool imu_contig = false; int imu_src0 = 0;                // same for the accelerometer / gyroscope samples
   std::vector<double> imu_used_t, imu_used_acc, imu_used_gyr; std::vector<int64_t> imu_used_st;
   std::vector<ImuCell> cells;
   int dropped_frames = 0, dropped_imu = 0;
@@ -556,13 +560,19 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   }
   struct ImuHost { double t_s; int64_t st; int s_so3, s_r3, s_ba, s_bg; int src; };
   std::vector<ImuHost> all_imu; all_imu.reserve(h->imu_t.size()); units.reserve(nf + h->imu_t.size());
+  // CalcTimes' segment index s = st / dt of a time-sorted stream only ever steps forward: track it with comparisons and fall back
+  // to the division when a sample is not where the previous one left off (unsorted input); the results are identical
+  struct SegTrack { int64_t dt, s = 0; bool init = false;
+    int64_t seg(int64_t st) { if (!init || st < s * dt || st >= (s + 64) * dt) { s = st / dt; init = true; } else while (st >= (s + 1) * dt) ++s; return s; } };
+  SegTrack tr_r3{h->dt_r3_ns}, tr_so3{h->dt_so3_ns}, tr_ba{h->dt_ba_ns}, tr_bg{h->dt_bg_ns};
   for (size_t i = 0; i < h->imu_t.size(); ++i) {
     const double t = h->imu_t[i] + ipp->time_offset_imu_to_cam_s;
     if (t < h->t0_s || t >= h->tend_s) continue;
-    const int64_t t_ns = (int64_t)(t * S_TO_NS);
-    double u; int64_t a, b, c, d;
-    const bool ok = calc_times(t_ns, h->start_ns, h->dt_r3_ns, nr3, SPLINE_N, u, a) && calc_times(t_ns, h->start_ns, h->dt_so3_ns, nso3, SPLINE_N, u, b) &&
-                    calc_times(t_ns, h->start_ns, h->dt_ba_ns, nba, BIAS_N, u, c) && calc_times(t_ns, h->start_ns, h->dt_bg_ns, nbg, BIAS_N, u, d);
+    const int64_t t_ns = (int64_t)(t * S_TO_NS), st = t_ns - h->start_ns;
+    bool ok = st >= 0;
+    int64_t a = 0, b = 0, c = 0, d = 0;
+    if (ok) { a = tr_r3.seg(st); b = tr_so3.seg(st); c = tr_ba.seg(st); d = tr_bg.seg(st);
+              ok = size_t(a + SPLINE_N) <= (size_t)nr3 && size_t(b + SPLINE_N) <= (size_t)nso3 && size_t(c + BIAS_N) <= (size_t)nba && size_t(d + BIAS_N) <= (size_t)nbg; }
     if (!ok) { ++h->dropped_imu; continue; }
     all_imu.push_back({t, t_ns - h->start_ns, (int)b, (int)a, (int)c, (int)d, (int)i});
     units.push_back({t, 1, (int)all_imu.size() - 1, 6});
@@ -584,21 +594,35 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   for (const auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; (u.kind == 0 ? frame_sel : imu_sel).push_back(u.idx); }
   std::sort(frame_sel.begin(), frame_sel.end());
   h->frames.clear(); h->used_uv.clear(); h->used_pid.clear();
-  h->used_uv.reserve(h->uv.size()); h->used_pid.reserve(h->point_ids.size()); h->frames.reserve(frame_sel.size());
-  for (int fi : frame_sel) {
-    FrameHost f = all_frames[fi];
-    const int c0 = (int)h->used_pid.size();
-    for (int c = f.c0; c < f.c1; ++c) { h->used_pid.push_back(h->point_ids[c]); h->used_uv.push_back(h->uv[2 * c]); h->used_uv.push_back(h->uv[2 * c + 1]); }
-    f.c0 = c0; f.c1 = (int)h->used_pid.size();
-    h->frames.push_back(f);
+  h->frames.reserve(frame_sel.size());
+  bool consecutive = !frame_sel.empty();
+  for (size_t k = 1; k < frame_sel.size() && consecutive; ++k) consecutive = frame_sel[k] == frame_sel[k - 1] + 1;
+  h->used_contig = consecutive; h->used_c0 = 0; h->used_n = 0;
+  if (consecutive) {   // the usual case (all frames, or one contiguous shard): the corners are used in place, no host copy
+    const int cb = all_frames[frame_sel.front()].c0, ce = all_frames[frame_sel.back()].c1;
+    h->used_c0 = cb; h->used_n = ce - cb;
+    for (int fi : frame_sel) { FrameHost f = all_frames[fi]; f.c0 -= cb; f.c1 -= cb; h->frames.push_back(f); }
+  } else {
+    for (int fi : frame_sel) {
+      FrameHost f = all_frames[fi];
+      const int c0 = (int)h->used_pid.size();
+      for (int c = f.c0; c < f.c1; ++c) { h->used_pid.push_back(h->point_ids[c]); h->used_uv.push_back(h->uv[2 * c]); h->used_uv.push_back(h->uv[2 * c + 1]); }
+      f.c0 = c0; f.c1 = (int)h->used_pid.size();
+      h->frames.push_back(f);
+    }
+    h->used_n = (int)h->used_pid.size();
   }
   h->imu_used_t.clear(); h->imu_used_acc.clear(); h->imu_used_gyr.clear(); h->imu_used_st.clear(); h->cells.clear();
-  h->imu_used_t.reserve(imu_sel.size()); h->imu_used_st.reserve(imu_sel.size()); h->imu_used_acc.reserve(3 * imu_sel.size()); h->imu_used_gyr.reserve(3 * imu_sel.size());
-  for (int mi : imu_sel) {
-    const ImuHost& m = all_imu[mi];
-    const int idx = (int)h->imu_used_t.size();
-    h->imu_used_t.push_back(m.t_s); h->imu_used_st.push_back(m.st);
-    for (int d = 0; d < 3; ++d) { h->imu_used_acc.push_back(h->imu_acc[3 * m.src + d]); h->imu_used_gyr.push_back(h->imu_gyr[3 * m.src + d]); }
+  h->imu_contig = !imu_sel.empty();
+  for (size_t k = 1; k < imu_sel.size() && h->imu_contig; ++k) h->imu_contig = all_imu[imu_sel[k]].src == all_imu[imu_sel[k - 1]].src + 1;
+  h->imu_src0 = imu_sel.empty() ? 0 : all_imu[imu_sel.front()].src;
+  h->imu_used_t.resize(imu_sel.size()); h->imu_used_st.resize(imu_sel.size());
+  if (!h->imu_contig) { h->imu_used_acc.resize(3 * imu_sel.size()); h->imu_used_gyr.resize(3 * imu_sel.size()); }
+  for (size_t k = 0; k < imu_sel.size(); ++k) {
+    const ImuHost& m = all_imu[imu_sel[k]];
+    const int idx = (int)k;
+    h->imu_used_t[k] = m.t_s; h->imu_used_st[k] = m.st;
+    if (!h->imu_contig) { memcpy(&h->imu_used_acc[3 * k], &h->imu_acc[3 * (size_t)m.src], 3 * sizeof(double)); memcpy(&h->imu_used_gyr[3 * k], &h->imu_gyr[3 * (size_t)m.src], 3 * sizeof(double)); }
     if (h->cells.empty() || h->cells.back().s_so3 != m.s_so3 || h->cells.back().s_r3 != m.s_r3 || h->cells.back().s_ba != m.s_ba || h->cells.back().s_bg != m.s_bg)
       h->cells.push_back({m.s_so3, m.s_r3, m.s_ba, m.s_bg, idx, idx});
     h->cells.back().i_end = idx + 1;
@@ -620,7 +644,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   DeviceProblem& P = h->P;
   memset(&P, 0, sizeof P);
   P.model = h->model; P.dispatch_fov = ipp->dispatch_fov; P.n_intr = h->n_intr;
-  P.n_frames = (int)h->frames.size(); P.n_corners = (int)h->used_pid.size(); P.rolling = ipp->init_line_delay_s != 0.0 ? 1 : 0;
+  P.n_frames = (int)h->frames.size(); P.n_corners = h->used_n; P.rolling = ipp->init_line_delay_s != 0.0 ? 1 : 0;
   P.n_imu = (int)h->imu_used_t.size(); P.n_cells = (int)h->cells.size();
   P.dt_so3_ns = h->dt_so3_ns; P.dt_r3_ns = h->dt_r3_ns; P.dt_ba_ns = h->dt_ba_ns; P.dt_bg_ns = h->dt_bg_ns;
   P.inv_so3_dt = S_TO_NS / double(h->dt_so3_ns); P.inv_r3_dt = S_TO_NS / double(h->dt_r3_ns);
@@ -639,8 +663,15 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     off.push_back(P.n_corners);
     CU(h->d_f_off.upload(off)); CU(h->d_f_s_so3.upload(s1)); CU(h->d_f_s_r3.upload(s2)); CU(h->d_f_u_so3.upload(u1)); CU(h->d_f_u_r3.upload(u2));
     P.f_off = h->d_f_off.p; P.f_s_so3 = h->d_f_s_so3.p; P.f_s_r3 = h->d_f_s_r3.p; P.f_u_so3 = h->d_f_u_so3.p; P.f_u_r3 = h->d_f_u_r3.p;
-    std::vector<double2> uv2(P.n_corners); for (int c = 0; c < P.n_corners; ++c) uv2[c] = make_double2(h->used_uv[2 * c], h->used_uv[2 * c + 1]);
-    CU(h->d_uv.upload(uv2)); CU(h->d_pid.upload(h->used_pid)); P.uv = h->d_uv.p; P.pid = h->d_pid.p;
+    CU(h->d_uv.alloc(P.n_corners));   // (u, v) pairs are already laid out as double2
+    CU(h->d_pid.alloc(P.n_corners));
+    if (P.n_corners > 0) {
+      const double* uv_src = h->used_contig ? h->uv.data() + 2 * (size_t)h->used_c0 : h->used_uv.data();
+      const int* pid_src = h->used_contig ? h->point_ids.data() + h->used_c0 : h->used_pid.data();
+      CU(cudaMemcpy(h->d_uv.p, uv_src, (size_t)P.n_corners * sizeof(double2), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(h->d_pid.p, pid_src, (size_t)P.n_corners * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    P.uv = h->d_uv.p; P.pid = h->d_pid.p;
     // work lists: one warp per item; items sized so that the grid fills the GPU but every item amortises its tile flush
     const int target_items = h->sm_count * 8;
     auto round32 = [](long v) { return (int)((v + 31) / 32 * 32); };
@@ -653,7 +684,14 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
     CU(h->d_iwork.upload(iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
     CU(h->d_cells.upload(h->cells)); P.cells = h->d_cells.p;
-    CU(h->d_imu_t.upload(h->imu_used_st)); CU(h->d_imu_acc.upload(h->imu_used_acc)); CU(h->d_imu_gyr.upload(h->imu_used_gyr));
+    CU(h->d_imu_t.upload(h->imu_used_st));
+    CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
+    if (P.n_imu > 0) {
+      const double* a_src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data();
+      const double* g_src = h->imu_contig ? h->imu_gyr.data() + 3 * (size_t)h->imu_src0 : h->imu_used_gyr.data();
+      CU(cudaMemcpy(h->d_imu_acc.p, a_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(h->d_imu_gyr.p, g_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice));
+    }
     P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
   }
   icc_status s = upload_state(h, 0); if (s != ICC_OK) return s;
@@ -730,8 +768,9 @@ icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) ret
 icc_status icc_get_imu_used(const icc_handle* h, double* t, double* a, double* g) {
   if (!h) return ICC_ERR_INVALID_ARGUMENT;
   if (t) std::copy(h->imu_used_t.begin(), h->imu_used_t.end(), t);
-  if (a) std::copy(h->imu_used_acc.begin(), h->imu_used_acc.end(), a);
-  if (g) std::copy(h->imu_used_gyr.begin(), h->imu_used_gyr.end(), g);
+  const size_t nu = h->imu_used_t.size();
+  if (a) { const double* src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data(); std::copy(src, src + 3 * nu, a); }
+  if (g) { const double* src = h->imu_contig ? h->imu_gyr.data() + 3 * (size_t)h->imu_src0 : h->imu_used_gyr.data(); std::copy(src, src + 3 * nu, g); }
   return ICC_OK;
 }
 

@@ -346,7 +346,6 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
   auto after_jacobian = [&](bool compute_scale) -> icc_status {
     CU(cudaMemsetAsync(h->d_scal.p + SC_GRAD_MAX, 0, sizeof(double), h->stream));
     launch_compute_scale(P, compute_scale ? h->d_scale.p : nullptr, h->opt.jacobi_scaling, h->d_scal.p, h->stream);
-    CU(cudaMemcpyAsync(h->d_scal.p + SC_X_COST, P.ne + P.ne_off_cost, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return ICC_OK;
   };
   auto read_scalars = [&]() -> icc_status {
@@ -368,7 +367,6 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
       rc = after_jacobian(first); if (rc != ICC_OK) return rc;
       ne_valid = true; fresh_jacobian = true;
     }
-    CU(cudaMemsetAsync(h->d_scal.p, 0, 5 * sizeof(double), h->stream));    // model change, step / x norms, candidate cost, ok
     SolveParams sp; sp.radius = radius; sp.min_diag = h->opt.min_lm_diagonal; sp.max_diag = h->opt.max_lm_diagonal; sp.jacobi_scaling = h->opt.jacobi_scaling;
     const int a = mark();
     launch_solve(P, h->d_scale.p, sp, h->d_ws.p, h->d_delta.p, h->d_scal.p, h->stream);

@@ -556,7 +556,7 @@ __device__ void dense_front_store(const DenseFront& f, int wl, int wr, int nbp, 
 // ---- kernel A0: materialise the scaled + damped window columns of every chunk (fully parallel) ----------------------
 // Wg[col][e]: e < ldbp band entries (zero padding beyond kd, rows beyond the chunk's right separator masked), then the local
 // border [coupling to the left separator (stored transposed in H) | border | rhs].  Kernel A then only copies columns.
-__global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp) {
+__global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __restrict__ scale, SolveParams sp, double* wsp, double* scal) {
   const int c = blockIdx.x, nk = P.nk, nb = P.nb, kd = P.kd, ldb = P.ldb, w = pl.w, nbl = pl.nbl;
   const int a = chunk_a(pl, c), b = chunk_b(pl, c);
   const bool has_left = c > 0, has_right = c < pl.P - 1;
@@ -564,6 +564,7 @@ __global__ void prepare_kernel(DeviceProblem P, SolvePlan pl, const double* __re
   const double* band = P.ne; const double* E = P.ne + P.ne_off_E; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, ldb, pl);
   pdl_wait_then_trigger();
+  if (scal && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 5) scal[threadIdx.x] = 0.0;   // model change, step / x norms, candidate cost, ok
   const int total = (right_end - a) * CL, stride = gridDim.y * blockDim.x, de = stride % CL, dc = stride / CL;
   const int idx0 = blockIdx.y * blockDim.x + threadIdx.x;
   int e = idx0 % CL, col = a + idx0 / CL;
@@ -657,11 +658,18 @@ __global__ void __launch_bounds__(NT) reduce_kernel(DeviceProblem P, SolvePlan p
     if (r < 3 * w) return has_right ? bj[r - w - j] : 0.0;       // row b + (r - 2w): offset w + (r - 2w) - j
     return src_E[(int64_t)(a + j) * nbp + (r - 3 * w)];
   };
-  for (int j = warp; j < w; j += nwarps) {                       // gather the block column, 4 independent loads per lane in flight
-    double* cj = f.Pn + (size_t)j * f.ld;
-    for (int r0 = lane; r0 < f.MF; r0 += 128) {
-      const double v0 = fetch(j, r0), v1 = fetch(j, r0 + 32), v2 = fetch(j, r0 + 64), v3 = fetch(j, r0 + 96);
-      cj[r0] = v0; if (r0 + 32 < f.MF) cj[r0 + 32] = v1; if (r0 + 64 < f.MF) cj[r0 + 64] = v2; if (r0 + 96 < f.MF) cj[r0 + 96] = v3;
+  {   // gather the front: (column, 32-row chunk) items dealt round-robin to the warps, 8 independent loads per lane in flight
+    const int chunks = (f.MF + 31) >> 5, items = w * chunks;
+    for (int it0 = warp; it0 < items; it0 += 8 * nwarps) {
+      double v[8]; int dst[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int it = it0 + u * nwarps;
+        dst[u] = -1; v[u] = 0.0;
+        if (it < items) { const int j = it / chunks, r = ((it - j * chunks) << 5) + lane; if (r < f.MF) { v[u] = fetch(j, r); dst[u] = j * f.ld + r; } }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (dst[u] >= 0) f.Pn[dst[u]] = v[u];
     }
   }
   if (has_right) {                                               // the right neighbour carries its own entries to the next level
@@ -864,6 +872,7 @@ __global__ void scale_kernel(DeviceProblem P, double* scale, int jacobi, double*
     double m = 0.0;
     for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmax(m, red[w]);
     atomicMax(reinterpret_cast<unsigned long long*>(scal + SC_GRAD_MAX), (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like their bits
+    if (blockIdx.x == 0) scal[SC_X_COST] = P.ne[P.ne_off_cost];   // cost at the linearisation point, read back with the step scalars
   }
 }
 
@@ -1030,8 +1039,9 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   if (sC > cfgC) { cudaFuncSetAttribute(backsub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sC); cfgC = sC; }
   if (sCR > cfgCR) { cudaFuncSetAttribute(backsub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sCR); cfgCR = sCR; }
   cudaMemsetAsync(ws.bandr, 0, ws.reduced_doubles * sizeof(double), st);
+  if (P.nk == 0) cudaMemsetAsync(scal, 0, 5 * sizeof(double), st);   // otherwise the first solver kernel clears the step scalars
   if (P.nk > 0) {
-    launch_pdl(prepare_kernel, dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st, P, pl, scale, sp, workspace); count_launch();
+    launch_pdl(prepare_kernel, dim3(pl.P, pl.P >= 64 ? 4 : 16), 256, 0, st, P, pl, scale, sp, workspace, scal); count_launch();
     launch_pdl(eliminate_kernel, pl.P, NT, sA, st, P, pl, workspace, scal); count_launch();
     for (int l = 1; l <= pl.L; ++l) { launch_pdl(reduce_kernel, (pl.S[l] + 1) / 2, NT, sR, st, P, pl, l, workspace, scal); count_launch(); }
   }

@@ -369,7 +369,9 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     }
     SolveParams sp; sp.radius = radius; sp.min_diag = h->opt.min_lm_diagonal; sp.max_diag = h->opt.max_lm_diagonal; sp.jacobi_scaling = h->opt.jacobi_scaling;
     const int a = mark();
-    launch_solve(P, h->d_scale.p, sp, h->d_ws.p, h->d_delta.p, h->d_scal.p, h->stream);
+    { const int se = launch_solve(P, h->d_scale.p, sp, h->d_ws.p, h->d_delta.p, h->d_scal.p, h->stream);
+      if (se == 1) return fail(h, ICC_ERR_UNSUPPORTED, "the border (bias knots + globals) is too wide for the solver's shared-memory plans");
+      if (se) return fail(h, ICC_ERR_CUDA, std::string("solver launch: ") + cudaGetErrorString(cudaGetLastError())); }
     const int b = mark(); lin_spans.push_back({a, b});
     const int cand = 1 - h->cur;
     launch_update(P, h->st[h->cur].view(), h->st[cand].view(), h->d_delta.p, h->max_ba, h->max_bg, h->d_scal.p, h->stream);

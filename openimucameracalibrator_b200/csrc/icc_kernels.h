@@ -78,7 +78,8 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
 // scale[i] = 1/(1+sqrt(H_ii)) (Jacobi scaling, computed once per optimize) ; gradient inf-norm
 void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, double* scal, cudaStream_t st);
 // banded + bordered Cholesky solve of (S H S + D) y = -S g ; delta = S y (solver order) ; model cost change
-void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st);
+// returns 0, 1 = no elimination plan fits the shared-memory limits (border far too wide), 2 = a launch failed
+int launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st);
 size_t solve_workspace_doubles(const DeviceProblem& P);
 // candidate = Plus(current, delta) ; step / x squared norms
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st);

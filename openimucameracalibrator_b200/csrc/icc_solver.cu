@@ -61,6 +61,9 @@ struct SolvePlan {
   int kdr, ldbr;                  // reduced systems: half bandwidth 2w-1, column length
   int nbl;                        // local border rows of an elimination: w + nb + 1 (left separator | border | rhs)
   int WS_A, WS_R, WS_B;           // window slots (power of two): level 0, cyclic-reduction levels, root
+  int cl_global, cs_global;       // wide borders: the level-0 local border block / the root's border block live in HBM (L2), not in shared memory
+  int stage0;                     // level-0 back-substitution stages its El rows in shared memory
+  int valid;                      // 0: no plan fits the shared-memory limits
 };
 __host__ __device__ inline int chunk_a(const SolvePlan& pl, int c) { return c * (pl.len + pl.w) + (c < pl.rem ? c : pl.rem); }
 __host__ __device__ inline int chunk_b(const SolvePlan& pl, int c) { return chunk_a(pl, c) + pl.len + (c < pl.rem ? 1 : 0); }
@@ -68,7 +71,7 @@ __host__ __device__ inline int chunk_b(const SolvePlan& pl, int c) { return chun
 __host__ __device__ inline int sep_col(const SolvePlan& pl, int l, int j) { return chunk_b(pl, ((j + 1) << (l - 1)) - 1); }
 
 // Workspace (doubles): Lb[nk*ldb] | El[nk*nbl] | y[n] | R{bandr[nkr_total*ldbr] | Er[nkr_total*nbp] | Cr[nbp*nbp]} | Lbr | Elr[nkr_total*nbl] | Wg
-struct SolveWs { double *Lb, *El, *y, *bandr, *Er, *Cr, *Lbr, *Elr, *Wg; size_t reduced_doubles, total; };
+struct SolveWs { double *Lb, *El, *y, *bandr, *Er, *Cr, *Lbr, *Elr, *Wg, *Clg, *Csg; size_t reduced_doubles, total; };
 __host__ __device__ inline SolveWs carve(double* ws, int nk, int nb, int ldb, const SolvePlan& pl) {
   SolveWs w; const int nbp = nb + 1; const size_t n = (size_t)nk + nb, nr = (size_t)pl.nkr_total;
   w.Lb = ws; w.El = w.Lb + (size_t)nk * ldb; w.y = w.El + (size_t)nk * pl.nbl;
@@ -76,7 +79,9 @@ __host__ __device__ inline SolveWs carve(double* ws, int nk, int nb, int ldb, co
   w.reduced_doubles = nr * pl.ldbr + nr * nbp + (size_t)nbp * nbp;
   w.Lbr = w.Cr + (size_t)nbp * nbp; w.Elr = w.Lbr + nr * pl.ldbr;
   w.Wg = w.Elr + nr * pl.nbl;                                       // nk x (kd + KB + nbl): pre-scaled window columns of level 0
-  w.total = (size_t)(w.Wg + (size_t)nk * (ldb - 1 + 8 + pl.nbl) - ws) + 16;
+  w.Clg = w.Wg + (size_t)nk * (ldb - 1 + 8 + pl.nbl);               // P x nbl^2 (only when cl_global)
+  w.Csg = w.Clg + (pl.cl_global ? (size_t)pl.P * pl.nbl * pl.nbl : 0);  // nbp^2 (only when cs_global)
+  w.total = (size_t)(w.Csg + (pl.cs_global ? (size_t)nbp * nbp : 0) - ws) + 16;
   return w;
 }
 
@@ -370,11 +375,11 @@ __device__ void backsub_stage(const double* __restrict__ Lb_g, double* Bw, int b
 }
 
 // shared-memory carve-up shared by kernels A and B
-__device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, int ldbp, double** extra, int extra_doubles) {
+__device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, int ldbp, double** extra, int extra_doubles, double* cl_ext = nullptr) {
   FactorSmem fs;
   fs.W = sm;
-  fs.Cl = fs.W + (size_t)WS * CL;
-  double* p = fs.Cl + nbl * nbl;
+  double* p = fs.W + (size_t)WS * CL;
+  if (cl_ext) fs.Cl = cl_ext; else { fs.Cl = p; p += nbl * nbl; }
   *extra = p; p += extra_doubles;
   fs.inv = p; p += 2 * KB;
   fs.Ld = p; p += 2 * KB * KB;
@@ -384,9 +389,9 @@ __device__ FactorSmem carve_smem(double* sm, int WS, int CL, int nbl, int kd, in
   fs.nblocks = 0;
   return fs;
 }
-__host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int kd, int extra_doubles) {
+__host__ __device__ inline size_t factor_smem_bytes(int WS, int CL, int nbl, int kd, int extra_doubles, bool cl_in_smem = true) {
   const int nbk = (kd + nbl + 7) / 8;
-  return ((size_t)WS * CL + (size_t)nbl * nbl + extra_doubles + 2 * KB + 2 * KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
+  return ((size_t)WS * CL + (cl_in_smem ? (size_t)nbl * nbl : 0) + extra_doubles + 2 * KB + 2 * KB * KB + 1) * sizeof(double) + (size_t)nbk * (nbk + 1) / 2 * sizeof(uchar2) + 64;
 }
 
 // ---- dense front elimination (cyclic-reduction levels and the root) ------------------------------------------------
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(NT) eliminate_kernel(DeviceProblem P, SolvePla
   const bool has_left = c > 0, has_right = c < pl.P - 1;
   const int ldbp = kd + KB, CL = ldbp + nbl, WS = pl.WS_A;
   double* extra;
-  FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0);
+  FactorSmem fs = carve_smem(sm, WS, CL, nbl, kd, ldbp, &extra, 0, pl.cl_global ? ws.Clg + (size_t)c * nbl * nbl : nullptr);
   double* W = fs.W; double* Cl = fs.Cl;
   fs.nblocks = build_block_table(fs.blocks, kd + nbl);
   for (int i = threadIdx.x; i < nbl * nbl; i += blockDim.x) Cl[i] = 0.0;
@@ -711,11 +716,12 @@ __global__ void __launch_bounds__(NT) root_kernel(DeviceProblem P, SolvePlan pl,
   extern __shared__ __align__(16) double sm[];
   const int nk = P.nk, nb = P.nb, nbp = nb + 1, root = pl.L + 1, nkr = pl.S[root] * pl.w, kdr = pl.kdr, ldbr = pl.ldbr, w = pl.w, nbl = pl.nbl;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  double* Cs = sm;                                 // nbp x nbp lower, row nb = rhs
-  double* xb = Cs + nbp * nbp;                     // border solution
+  // nbp x nbp lower, row nb = rhs; wide borders keep it in HBM (L2 resident)
+  double* xb = pl.cs_global ? sm : sm + nbp * nbp;   // border solution
   double* rest = xb + ((nbp + 4) & ~3);            // dense front, later the back-substitution staging
   const double* C = P.ne + P.ne_off_C; const double* g = P.ne + P.ne_off_g;
   SolveWs ws = carve(wsp, nk, nb, P.ldb, pl);
+  double* Cs = pl.cs_global ? ws.Csg : sm;
   const double* rband = ws.bandr + (int64_t)pl.off[root] * ldbr; const double* rE = ws.Er + (int64_t)pl.off[root] * nbp;
   double* rLb = ws.Lbr + (int64_t)pl.off[root] * ldbr; double* rEl = ws.Elr + (int64_t)pl.off[root] * nbl;
   pdl_wait_then_trigger();
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(NT) backsub_kernel(DeviceProblem P, SolvePlan 
   }
   const int top = has_right ? b + w : b;   // right separator values are known: they only enter the right-hand sides
   const int PB = LEVEL0 ? 128 : 64;
-  const bool staged = b - a <= PB;         // the usual case: the factor of this block is staged BEFORE waiting for the predecessor
+  const bool staged = b - a <= PB && (!LEVEL0 || pl.stage0);   // the usual case: the factor of this block is staged BEFORE waiting for the predecessor
   double* xl = sm;                         // local border solution [left separator | border]
   double* xr = xl + ((nbl + 3) & ~3);      // right separator solution
   double* tw = xr + ((w + 3) & ~3);        // t / x for columns [a, b)
@@ -954,17 +960,17 @@ __global__ void update_kernel(DeviceProblem P, DeviceState cur, DeviceState cand
 
 int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_A, P.kd + KB + pl.nbl, pl.nbl, P.kd, 0); }
+size_t smem_A(const DeviceProblem& P, const SolvePlan& pl) { return factor_smem_bytes(pl.WS_A, P.kd + KB + pl.nbl, pl.nbl, P.kd, 0, !pl.cl_global); }
 size_t smem_R(const DeviceProblem& P, const SolvePlan& pl) { return front_doubles(pl.w, 2 * pl.w + P.nb + 1) * sizeof(double) + 64; }
 size_t smem_B(const DeviceProblem& P, const SolvePlan& pl) {
   const int nbp = P.nb + 1, nkr = pl.S[pl.L + 1] * pl.w;
   const size_t fac = nkr > 0 ? front_doubles(pl.w, nbp) : 0;
   const size_t back = nkr > 0 ? (size_t)nkr + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64 : 0;   // back-substitution reuses the front area
-  return ((size_t)nbp * nbp + nbp + 8 + (fac > back ? fac : back)) * sizeof(double) + 64;
+  return ((pl.cs_global ? 0 : (size_t)nbp * nbp) + nbp + 8 + (fac > back ? fac : back)) * sizeof(double) + 64;
 }
 size_t smem_C(const DeviceProblem& P, const SolvePlan& pl) {
   const int maxlen = pl.len + 1 + pl.w;
-  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128 + (size_t)std::min(pl.len + 1, 128) * pl.nbl) * sizeof(double) + 64;
+  return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)maxlen + 4 + (size_t)(128 + P.kd) * P.ldb + 128 + (pl.stage0 ? (size_t)std::min(pl.len + 1, 128) * pl.nbl : 0)) * sizeof(double) + 64;
 }
 size_t smem_CR(const DeviceProblem& P, const SolvePlan& pl) {
   return ((size_t)pl.nbl + 4 + (size_t)pl.w + 4 + (size_t)2 * pl.w + 4 + (size_t)(64 + pl.kdr) * pl.ldbr + 64 + (size_t)pl.w * pl.nbl) * sizeof(double) + 64;
@@ -1006,11 +1012,24 @@ SolvePlan make_plan(const DeviceProblem& P) {
     while (Sl > 1) { off += Sl * pl.w; Sl /= 2; ++l; pl.S[l] = Sl; pl.off[l] = off; }
     pl.L = l - 1; pl.nkr_total = off + Sl * pl.w;
     pl.WS_A = pow2_at_least(kd + 2 * KB + 1); pl.WS_R = pl.WS_B = 0;
+    pl.valid = 1;
   };
-  fill(Pn);
-  if (Pn > 1 && (smem_A(P, pl) > 200 * 1024 || smem_R(P, pl) > 200 * 1024 || smem_B(P, pl) > 200 * 1024)) fill(1);
+  // shared-memory fit: first choice everything on chip; wide borders move the dense border blocks to HBM (L2 resident) and drop the
+  // level-0 staging; then fewer chunks; if nothing fits the opt-in limit the plan is invalid and the solve fails loudly
+  const size_t COMFORT = 200 * 1024, LIMIT = 230000;
+  auto fits = [&](int Pc) {
+    fill(Pc);
+    pl.stage0 = 1;
+    if (smem_A(P, pl) > COMFORT) pl.cl_global = 1;
+    if (smem_B(P, pl) > COMFORT) pl.cs_global = 1;
+    if (smem_C(P, pl) > LIMIT) pl.stage0 = 0;
+    pl.valid = smem_A(P, pl) <= LIMIT && smem_R(P, pl) <= LIMIT && smem_B(P, pl) <= LIMIT && smem_C(P, pl) <= LIMIT && smem_CR(P, pl) <= LIMIT;
+    return pl.valid != 0;
+  };
+  if (!fits(Pn) && Pn > 1) { int Pc = Pn; while (Pc > 1 && !fits(Pc)) Pc /= 2; if (!pl.valid) fits(1); }
+  if (!pl.valid) return pl;
   // grow the level-0 window while it fits comfortably (larger column groups amortise the group load/store)
-  while (pl.WS_A < 256 && pl.WS_A < pl.len + 1 + kd + 2 * KB) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > 200 * 1024) break; pl = t; }
+  while (pl.WS_A < 256 && pl.WS_A < pl.len + 1 + kd + 2 * KB) { SolvePlan t = pl; t.WS_A *= 2; if (smem_A(P, t) > COMFORT) break; pl = t; }
   return pl;
 }
 
@@ -1018,6 +1037,7 @@ SolvePlan make_plan(const DeviceProblem& P) {
 
 size_t solve_workspace_doubles(const DeviceProblem& P) {
   const SolvePlan pl = make_plan(P);
+  if (!pl.valid) return 16;
   return carve(nullptr, P.nk, P.nb, P.ldb, pl).total;
 }
 
@@ -1028,8 +1048,9 @@ void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, dou
   count_launch();
 }
 
-void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st) {
+int launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, double* workspace, double* delta, double* scal, cudaStream_t st) {
   const SolvePlan pl = make_plan(P);
+  if (!pl.valid) return 1;                       // border too wide / problem too small for any plan within the shared-memory limit
   const SolveWs ws = carve(workspace, P.nk, P.nb, P.ldb, pl);
   static size_t cfgA = 0, cfgR = 0, cfgB = 0, cfgC = 0, cfgCR = 0;
   const size_t sA = smem_A(P, pl), sR = smem_R(P, pl), sB = smem_B(P, pl), sC = smem_C(P, pl), sCR = smem_CR(P, pl);
@@ -1053,6 +1074,7 @@ void launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, d
   const int n = P.nk + P.nb;
   int grid = (n + 255) / 256; if (grid > 148) grid = 148; if (grid < 1) grid = 1;
   launch_pdl(finish_kernel, grid, 256, 0, st, P, pl, scale, sp, workspace, delta, scal); count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st) {

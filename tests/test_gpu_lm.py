@@ -77,3 +77,20 @@ def test_lm_iteration_schedule_and_launch_count(gpu_factory):
     s = g.lm_iterations(3, F_STAGE1)
     assert s.iterations == 3 and s.cost_evaluations == 3 and s.jacobian_evaluations == min(3, 1 + s.successful_steps)
     assert s.gpu_launches >= 3 * 4 and s.seconds_jacobian > 0 and s.seconds_linear_solve > 0
+
+
+def test_very_wide_border_uses_hbm_border_blocks(oracle_factory, gpu_factory):
+    """A 200 s sequence with IMU_BIASES | GRAVITY_DIR free: 2 x 23 bias knots -> 147 border columns.  The level-0 local border
+    block and the root's border block no longer fit in shared memory and live in HBM (SolvePlan::cl_global / cs_global); the LM
+    path must still follow the oracle."""
+    cfg = syn.tiny_config(n_frames=400, fps=2.0, dt_so3_s=0.5, dt_r3_s=0.5, imu_rate_hz=50.0, seed=41)
+    ds = syn.make_dataset(cfg)
+    flags = F_STAGE1 | capi.FLAG_IMU_BIASES | capi.FLAG_GRAVITY_DIR
+    o = oracle_factory(); capi.load_dataset(o, ds, known_gravity=False)
+    g = gpu_factory(); capi.load_dataset(g, ds, known_gravity=False)
+    nb = g.num_tangent(flags) - 3 * g.num_knots()[0] - 3 * g.num_knots()[1]
+    assert nb >= 140, nb
+    so, sg = o.lm_iterations(3, flags), g.lm_iterations(3, flags)
+    assert sg.successful_steps == so.successful_steps >= 1
+    assert abs(sg.final_cost - so.final_cost) <= 1e-7 * so.final_cost
+    assert rel(g.get_T_i_c(), o.get_T_i_c()) < 1e-7 and rel(g.get_gravity(), o.get_gravity()) < 1e-7

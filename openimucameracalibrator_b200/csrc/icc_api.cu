@@ -656,7 +656,8 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   CU(cudaSetDevice(h->device));
   {
     std::vector<double4> board(h->points.size() / 4);
-    for (size_t i = 0; i < board.size(); ++i) board[i] = make_double4(h->points[4 * i], h->points[4 * i + 1], h->points[4 * i + 2], h->points[4 * i + 3]);
+    // hnormalized(T^-1 X_h) of the functor (residuals.h:357-362) == T^-1 (X / w): the division is done once here
+    for (size_t i = 0; i < board.size(); ++i) { const double iw = 1.0 / h->points[4 * i + 3]; board[i] = make_double4(h->points[4 * i] * iw, h->points[4 * i + 1] * iw, h->points[4 * i + 2] * iw, 1.0); }
     CU(h->d_board.upload(board)); P.board = h->d_board.p;
     std::vector<int> off, s1, s2; std::vector<double> u1, u2;
     for (const auto& f : h->frames) { off.push_back(f.c0); s1.push_back(f.s_so3); s2.push_back(f.s_r3); u1.push_back(f.u_so3); u2.push_back(f.u_r3); }

@@ -36,6 +36,8 @@ constexpr int LDJ = 36;   // rows per tile column (32 + 4 pad: stride = 4 mod 16
 struct WarpCtx {
   Q4 q[6];
   V3 d[5];
+  V3 dh[5];          // unit axes d_i / |d_i| (0 when the increment vanishes)
+  double th[5], ith[5];   // |d_i| and its reciprocal (0 when the increment vanishes): no division, sqrt or norm per observation
   M3 jri[5];
   V3 p[6];
   V3 ba[3], bg[3];
@@ -116,14 +118,22 @@ ICC_D void stage_so3_window(WarpCtx* wc, const DeviceState& S, int s_so3, int la
   if (lane < 5) {
     const V3 d = so3_log(qmul(qconj(wc->q[lane]), wc->q[lane + 1]));
     wc->d[lane] = d;
+    const double th = sqrt(dot(d, d)), ith = th > 1e-150 ? 1.0 / th : 0.0;
+    wc->th[lane] = th; wc->ith[lane] = ith; wc->dh[lane] = ith * d;
     if (JAC) wc->jri[lane] = so3_jr_inv(d);
   }
+}
+
+// lambda * (x Jr(lambda d)) for a row vector x, with the per-item unit axis dh and the two per-observation coefficients of Chain
+ICC_D V3 lam_row_jr(V3 x, V3 dh, double lam, double c1, double c2) {
+  const V3 xd = cross(x, dh);
+  return lam * x - c1 * xd + c2 * cross(xd, dh);
 }
 
 // Per-observation spline rotation chain shared by all residual types.
 struct Chain {
   Q4 A[5];          // exp(lambda_i d_i), i = 1..5
-  double ja[5], jb[5];
+  double c1[5], c2[5];   // lambda * row Jr(lambda d) = lambda x - c1 (x x dh) + c2 ((x x dh) x dh):  c1 = (1 - cos phi)/theta, c2 = lambda - sin(phi)/theta
   double lam[5], dlam[5];
   Q4 q;             // R_w_i
 };
@@ -132,9 +142,13 @@ ICC_D void build_chain(const WarpCtx* wc, double u, Chain& ch) {
   Q4 q = wc->q[0];
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
-    const ExpOut e = so3_exp_jr(ch.lam[i] * wc->d[i]);
-    ch.A[i] = e.q; ch.ja[i] = e.a; ch.jb[i] = e.b;
-    q = qmul(q, e.q);
+    // exp(lambda d) about the fixed axis dh: one sincos of the half angle; phi = lambda theta
+    double sn, cs;
+    sincos(0.5 * ch.lam[i] * wc->th[i], &sn, &cs);
+    const V3 ax = wc->dh[i];
+    const Q4 eq = q4(sn * ax.x, sn * ax.y, sn * ax.z, cs);
+    ch.A[i] = eq; ch.c1[i] = 2.0 * sn * sn * wc->ith[i]; ch.c2[i] = ch.lam[i] - 2.0 * sn * cs * wc->ith[i];
+    q = qmul(q, eq);
   }
   ch.q = q;
 }
@@ -149,7 +163,7 @@ ICC_D double so3_knot_row(const WarpCtx* wc, const Chain& ch, V3 m_theta, double
   for (int i = 4; i >= 0; --i) {   // knot pair (i, i+1): increment index i+1 in the text, array index i
     const V3 di = wc->d[i];
     du += ch.dlam[i] * dot(w, di);
-    const V3 z = ch.lam[i] * row_times_jr(w, ch.lam[i] * di, ch.ja[i], ch.jb[i]);
+    const V3 z = lam_row_jr(w, wc->dh[i], ch.lam[i], ch.c1[i], ch.c2[i]);
     // knot i+1 receives  z Jr^-1(d_i)  (row-vector times matrix) minus the contribution found in the previous iteration
     const V3 up = mulT(wc->jri[i], z) - z_next;
     Jt[(3 * (i + 1) + 0) * LDJ + lane] = scale * up.x;
@@ -228,8 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32) vision_kernel(DeviceProblem P, Dev
 #pragma unroll
         for (int j = 0; j < 6; ++j) { t = fma3(cc[j], wc->p[j], t); if (JAC) tdot = fma3(dc[j], wc->p[j], tdot); }
         const double4 X = P.board[P.pid[c]];
-        const double iw = 1.0 / X.w;
-        qi = qrot_inv(ch.q, v3(X.x * iw, X.y * iw, X.z * iw) - t);   // point in the IMU frame
+        qi = qrot_inv(ch.q, v3(X.x, X.y, X.z) - t);   // point in the IMU frame (board points are de-homogenised once, at upload)
         pc = qrot_inv(q_ic, qi - t_ic);                                // point in the camera frame
         if (JAC == 2) pr = project_with_k(P.model, intr, pc, P.dispatch_fov != 0, &pk); else pr = project(P.model, intr, pc, P.dispatch_fov != 0);
         ok = pr.ok;
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32) imu_kernel(DeviceProblem P, Device
             V3 z_next = v3(0, 0, 0);
 #pragma unroll
             for (int i2 = 4; i2 >= 0; --i2) {
-              const V3 yv = ch.lam[i2] * row_times_jr(cross(w, s[i2]), ch.lam[i2] * wc->d[i2], ch.ja[i2], ch.jb[i2]) + (ch.dlam[i2] * P.inv_so3_dt) * w;
+              const V3 yv = lam_row_jr(cross(w, s[i2]), wc->dh[i2], ch.lam[i2], ch.c1[i2], ch.c2[i2]) + (ch.dlam[i2] * P.inv_so3_dt) * w;
               const V3 up = mulT(wc->jri[i2], yv) - z_next;
               Jt[(3 * (i2 + 1) + 0) * LDJ + lane] = P.w_gyr * up.x; Jt[(3 * (i2 + 1) + 1) * LDJ + lane] = P.w_gyr * up.y; Jt[(3 * (i2 + 1) + 2) * LDJ + lane] = P.w_gyr * up.z;
               z_next = mul(wc->jri[i2], yv);

@@ -234,6 +234,62 @@ icc_status icc_estimate_imu_to_camera_rotation(icc_handle* h, int n_views, const
 icc_status icc_spline_error_weighting(icc_handle* h, int n, const double* times_s, const double* signal_xyz, double quality, double min_dt, double max_dt,
                                       double* knot_spacing, double* variance, double* spectrum);
 
+/* ---- upstream row f4: camera intrinsic calibration ----------------------------------------------------------
+ * CameraCalibrator::CalibrateCameraFromJson / RunCalibration (src/core/camera_calibrator.cc:221-389, :131-219) behind
+ * applications/calibrate_camera.cc: every view of the corner file gets an initial pose and focal length, views closer than
+ * `grid_size` to an already accepted camera position are skipped (:313-325), then theia::BundleAdjustViews runs three times over
+ * all view poses + ONE shared intrinsic vector with a Huber(1.345) loss (:140-144):
+ *   stage 1  focal length (+ radial distortion unless PINHOLE), poses free (:149-160); views with a mean error > 5 px removed (:162)
+ *   stage 2  principal point only, poses constant (:167-174)
+ *   stage 3  principal point + focal length + aspect ratio (+ radial for PINHOLE, + tangential for PINHOLE_RADIAL_TANGENTIAL),
+ *            poses free (:184-198); views with a mean error > 2 px removed (:200); fewer than 10 views left = failure (:202-205)
+ * The residual is theia::ReprojectionError: CameraToPixelCoordinates(intr, R_cw (X - c)) - feature [px].  "Radial distortion" is
+ * Theia's per-model subset (k1,k2 | k1..k3 | k1..k4 | k | xi,alpha | alpha,beta | omega).  Initial intrinsics as in AddView
+ * (:84-129): principal point = image centre, aspect ratio 1, skew 0, DOUBLE_SPHERE xi = -0.25 alpha = 0.5, EXTENDED_UNIFIED
+ * alpha = 0.5 beta = 1, DIVISION_UNDISTORTION k = distortion_init, everything else 0.
+ * Initial poses: pass q_wc_init / p_wc_init (+ init_valid) and focal_length_init > 0 to start from your own estimates (what the
+ * reference gets from Theia's RANSAC minimal solvers, which are not reproduced), or NULL / <= 0 to have them estimated here:
+ * focal length = median over the views of the closed-form estimate from the board homography (Zhang's constraints, principal
+ * point at the image centre), poses = homography decomposition + Huber pose refinement under that pinhole camera; for the
+ * non-pinhole models focal length, a division-model distortion and the poses are then refined jointly (the quantities
+ * utils::initialize_radial_undistortion_camera hands the reference, :283-306) before the target model takes over.
+ * `--optimize_board_points` (:207-216) is not implemented.  Needs icc_set_board_points (planar board for the internal initialiser).
+ * Outputs (caller-owned): intrinsics[10] in Theia's order for `model`; per view q_wc / p_wc (as icc_set_frames consumes them),
+ * the mean reprojection error [px] (GetReprojErrorOfView) and used[v] = 1 for the views that survive to the end.
+ * summary->success = 0 (status still ICC_OK) when fewer than min_num_views views remain, like RunCalibration returning false. */
+typedef struct icc_camcal_options {
+  double grid_size;                  /* SetGridSize (calibrate_camera.cc:33-35); < 0 selects 0.04 m, 0 keeps every view */
+  double function_tolerance;         /* <= 0 selects theia's 1e-6 */
+  double parameter_tolerance;        /* <= 0 selects theia's 1e-8 */
+  double gradient_tolerance;         /* <= 0 selects theia's 1e-10 */
+  double huber_width;                /* <= 0 selects 1.345 (camera_calibrator.cc:143) */
+  double max_view_error_stage1_px;   /* <= 0 selects 5.0 (:162) */
+  double max_view_error_final_px;    /* <= 0 selects 2.0 (:200) */
+  int32_t min_num_views;             /* camera_calibrator.h:84; <= 0 selects 10 */
+  int32_t max_num_iterations;        /* theia::BundleAdjustmentOptions (external) default 100 per stage; <= 0 selects it */
+} icc_camcal_options;
+typedef struct icc_camcal_summary {
+  int32_t success;
+  int32_t n_views_initialized;       /* views with an initial pose */
+  int32_t n_views_selected;          /* ... that also passed the grid filter */
+  int32_t n_views_used;              /* ... that survived both removal passes */
+  int32_t iterations[3];             /* LM iterations per stage */
+  int32_t termination[3];            /* icc_summary.termination codes per stage */
+  int32_t gpu_launches;
+  int32_t init_iterations;           /* LM iterations of the internal initialiser's joint refinement (0 when poses / focal length are given) */
+  double focal_length_init;
+  double initial_cost;               /* cost at the start of stage 1 */
+  double final_cost[3];              /* cost at the end of each stage */
+  double final_reproj_error;         /* mean over the used views of their mean reprojection error [px] (camera_calibrator.cc:352-366) */
+  double seconds_total;
+} icc_camcal_summary;
+icc_status icc_calibrate_camera(icc_handle* h, int model, int image_width, int image_height,
+                                int n_views, const int32_t* corner_offsets /* n_views+1 */, const int32_t* point_ids, const double* uv,
+                                const double* q_wc_init_xyzw /* nullable */, const double* p_wc_init /* nullable */, const int32_t* init_valid /* nullable */,
+                                double focal_length_init, double distortion_init, const icc_camcal_options* options /* nullable */,
+                                double* intrinsics /* 10 */, double* q_wc_xyzw, double* p_wc, double* view_reproj_error_px, int32_t* view_used,
+                                icc_camcal_summary* summary /* nullable */);
+
 /* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
 void icc_trim_device_cache(void);
 

@@ -50,6 +50,27 @@ class Summary(C.Structure):
         return d
 
 
+class CamCalOptions(C.Structure):
+    """icc_camcal_options (include/icc_b200.h): zero / negative fields select the reference's defaults."""
+    _fields_ = [("grid_size", C.c_double), ("function_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("huber_width", C.c_double), ("max_view_error_stage1_px", C.c_double), ("max_view_error_final_px", C.c_double),
+                ("min_num_views", C.c_int32), ("max_num_iterations", C.c_int32)]
+
+
+class CamCalSummary(C.Structure):
+    _fields_ = [("success", C.c_int32), ("n_views_initialized", C.c_int32), ("n_views_selected", C.c_int32), ("n_views_used", C.c_int32),
+                ("iterations", C.c_int32 * 3), ("termination", C.c_int32 * 3), ("gpu_launches", C.c_int32), ("init_iterations", C.c_int32),
+                ("focal_length_init", C.c_double), ("initial_cost", C.c_double), ("final_cost", C.c_double * 3), ("final_reproj_error", C.c_double),
+                ("seconds_total", C.c_double)]
+
+    def as_dict(self):
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 
@@ -150,6 +171,28 @@ class CApi:
         xy = np.zeros((n, 2)); ok = np.zeros(n, dtype=np.int32)
         self._call("pixels_to_normalized", [C.c_int, c_double_p, c_double_p, c_int32_p], n, _dp(uv), _dp(xy), ok.ctypes.data_as(c_int32_p))
         return xy, ok
+
+    # ---- upstream row f4: CameraCalibrator::CalibrateCameraFromJson / RunCalibration (src/core/camera_calibrator.cc:131-389) ----
+    def calibrate_camera(self, model, image_width, image_height, corner_offsets, point_ids, uv, q_wc_init=None, p_wc_init=None, init_valid=None,
+                         focal_length_init=0.0, distortion_init=0.0, **options):
+        """-> dict(intrinsics[n], q_wc[nv,4], p_wc[nv,3], view_error_px[nv], used[nv], summary); board points must be set.
+        options: fields of icc_camcal_options (grid_size defaults to the reference's 0.04 m)."""
+        off = np.ascontiguousarray(corner_offsets, dtype=np.int32); ids = np.ascontiguousarray(point_ids, dtype=np.int32); uv = _f64(uv)
+        nv = off.size - 1
+        assert ids.size == off[-1] and uv.size == 2 * ids.size
+        o = CamCalOptions(); o.grid_size = -1.0
+        for k, v in options.items():
+            setattr(o, k, v)
+        qi = None if q_wc_init is None else _f64(q_wc_init); pi = None if p_wc_init is None else _f64(p_wc_init)
+        vi = None if init_valid is None else np.ascontiguousarray(init_valid, dtype=np.int32)
+        intr = np.zeros(10); q = np.zeros((nv, 4)); p = np.zeros((nv, 3)); e = np.zeros(nv); used = np.zeros(nv, dtype=np.int32); s = CamCalSummary()
+        self._call("calibrate_camera", [C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.c_double, C.c_double,
+                                        C.POINTER(CamCalOptions), c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, C.POINTER(CamCalSummary)],
+                   int(model), int(image_width), int(image_height), nv, off.ctypes.data_as(c_int32_p), ids.ctypes.data_as(c_int32_p), _dp(uv),
+                   None if qi is None else _dp(qi), None if pi is None else _dp(pi), None if vi is None else vi.ctypes.data_as(c_int32_p),
+                   float(focal_length_init), float(distortion_init), C.byref(o), _dp(intr), _dp(q), _dp(p), _dp(e), used.ctypes.data_as(c_int32_p), C.byref(s))
+        from .camera_models import NUM_PARAMS
+        return dict(intrinsics=intr[:NUM_PARAMS[int(model)]], q_wc=q, p_wc=p, view_error_px=e, used=used, summary=s.as_dict())
 
     # ---- upstream row f3: ImuToCameraRotationEstimator (src/core/imu_to_camera_rotation_estimator.cc:116-274) -----------------
     def estimate_imu_to_camera_rotation(self, view_t_s, q_cw_xyzw, imu_t_s, gyro, gyro_bias=None):

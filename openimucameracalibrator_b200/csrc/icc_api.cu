@@ -1114,6 +1114,274 @@ icc_status icc_spline_error_weighting(icc_handle* h, int n, const double* times,
   return ICC_OK;
 }
 
+// ---- upstream row f4: camera intrinsic calibration (CameraCalibrator, src/core/camera_calibrator.cc) ----------------------
+namespace {
+// theia::CameraIntrinsicsModel::GetSubsetFromOptimizeIntrinsicsType per model, as bit masks over Theia's parameter order
+struct IntrinsicSubsets { unsigned focal, aspect, principal, radial, tangential; };
+IntrinsicSubsets intrinsic_subsets(int model) {
+  auto bits = [](std::initializer_list<int> l) { unsigned m = 0; for (int i : l) m |= 1u << i; return m; };
+  switch (model) {
+    case CAM_PINHOLE: return {bits({0}), bits({1}), bits({3, 4}), bits({5, 6}), 0u};
+    case CAM_PINHOLE_RADTAN: return {bits({0}), bits({1}), bits({3, 4}), bits({5, 6, 7}), bits({8, 9})};
+    case CAM_FISHEYE: return {bits({0}), bits({1}), bits({3, 4}), bits({5, 6, 7, 8}), 0u};
+    case CAM_FOV: return {bits({0}), bits({1}), bits({2, 3}), bits({4}), 0u};
+    case CAM_DIVISION_UNDISTORTION: return {bits({0}), bits({1}), bits({2, 3}), bits({4}), 0u};
+    case CAM_DOUBLE_SPHERE: return {bits({0}), bits({1}), bits({3, 4}), bits({5, 6}), 0u};
+    case CAM_EXTENDED_UNIFIED: return {bits({0}), bits({1}), bits({3, 4}), bits({5, 6}), 0u};
+    default: return {0u, 0u, 0u, 0u, 0u};
+  }
+}
+}  // namespace
+
+icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, const int32_t* off, const int32_t* ids, const double* uv,
+                                const double* q_init, const double* p_init, const int32_t* init_valid, double focal_init, double distortion_init,
+                                const icc_camcal_options* options, double* intr_out, double* q_out, double* p_out, double* err_out, int32_t* used_out,
+                                icc_camcal_summary* summary) {
+  using clk = std::chrono::steady_clock;
+  const auto t_start = clk::now();
+  if (!h || nv <= 0 || !off || !ids || !uv || !intr_out || !q_out || !p_out || !used_out || W <= 0 || H <= 0) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (camera_num_params(model) < 0) return fail(h, ICC_ERR_INVALID_ARGUMENT, "unknown camera model");
+  if (h->points.empty()) return fail(h, ICC_ERR_STATE, "icc_set_board_points must be called first");
+  if (off[0] != 0) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must start at 0");
+  for (int i = 0; i < nv; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
+  const int nc = off[nv], np = (int)(h->points.size() / 4);
+  for (int i = 0; i < nc; ++i) if (ids[i] < 0 || ids[i] >= np) return fail(h, ICC_ERR_INVALID_ARGUMENT, "point id outside the board");
+  icc_camcal_options o; memset(&o, 0, sizeof o); if (options) o = *options;
+  if (o.grid_size < 0.0) o.grid_size = 0.04;
+  if (o.min_num_views <= 0) o.min_num_views = 10;
+  if (o.max_num_iterations <= 0) o.max_num_iterations = 100;
+  if (!(o.function_tolerance > 0.0)) o.function_tolerance = 1e-6;
+  if (!(o.parameter_tolerance > 0.0)) o.parameter_tolerance = 1e-8;
+  if (!(o.gradient_tolerance > 0.0)) o.gradient_tolerance = 1e-10;
+  if (!(o.huber_width > 0.0)) o.huber_width = 1.345;
+  if (!(o.max_view_error_stage1_px > 0.0)) o.max_view_error_stage1_px = 5.0;
+  if (!(o.max_view_error_final_px > 0.0)) o.max_view_error_final_px = 2.0;
+  icc_camcal_summary S; memset(&S, 0, sizeof S);
+  const int launches0 = kernel_launch_count();
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // ---- inputs to the device ------------------------------------------------------------------------------------------------
+  std::vector<double4> board(np);
+  for (int i = 0; i < np; ++i) board[i] = make_double4(h->points[4 * i], h->points[4 * i + 1], h->points[4 * i + 2], h->points[4 * i + 3]);
+  DevBuf<double4> d_board; DevBuf<int> d_off, d_pid, d_active; DevBuf<double2> d_uv;
+  CU(d_board.upload(board));
+  CU(d_off.alloc(nv + 1)); CU(d_pid.alloc(std::max(1, nc))); CU(d_uv.alloc(std::max(1, nc))); CU(d_active.alloc(nv));
+  CU(cudaMemcpyAsync(d_off.p, off, (size_t)(nv + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (nc > 0) {
+    CU(cudaMemcpyAsync(d_pid.p, ids, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_uv.p, uv, (size_t)nc * sizeof(double2), cudaMemcpyHostToDevice, st));
+  }
+  const double cx0 = W / 2.0, cy0 = H / 2.0;                       // AddView (:99)
+  // ---- initial focal length and poses ----------------------------------------------------------------------------------------
+  std::vector<double> q0(4 * (size_t)nv), p0(3 * (size_t)nv); std::vector<int> ok0(nv, 1);
+  const bool need_focal = !(focal_init > 0.0), need_poses = !q_init || !p_init;
+  double f0 = focal_init;
+  if (need_focal || need_poses) {
+    PoseProblem PQ; memset(&PQ, 0, sizeof PQ);
+    PQ.model = CAM_PINHOLE; PQ.n_frames = nv; PQ.n_points = np; PQ.min_points = 6;
+    PQ.board = d_board.p; PQ.f_off = d_off.p; PQ.pid = d_pid.p; PQ.thresh_sq = 1e300; PQ.max_err = 1e300;   // every corner takes part
+    DevBuf<double2> d_xy; DevBuf<unsigned char> d_use; DevBuf<double> d_f2, d_q, d_p, d_e; DevBuf<int> d_ok, d_valid;
+    CU(d_xy.alloc(std::max(1, nc))); CU(d_use.alloc(std::max(1, nc))); CU(d_ok.alloc(std::max(1, nc)));
+    if (need_focal) {
+      CU(d_f2.alloc(nv));
+      launch_board_focal(PQ, d_uv.p, cx0, cy0, d_xy.p, d_use.p, d_f2.p, st);
+      std::vector<double> f2(nv);
+      CU(cudaMemcpyAsync(f2.data(), d_f2.p, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      std::vector<double> fs; for (double v : f2) if (v > 0.0 && std::isfinite(v)) fs.push_back(std::sqrt(v));
+      if (fs.empty()) return fail(h, ICC_ERR_NUMERIC, "no view yields a focal length estimate (fronto-parallel or degenerate views only)");
+      f0 = median_like_reference(fs);
+    }
+    if (need_poses) {
+      CU(d_q.alloc(4 * (size_t)nv)); CU(d_p.alloc(3 * (size_t)nv)); CU(d_e.alloc(nv)); CU(d_valid.alloc(nv));
+      launch_pinhole_normalize(nc, d_uv.p, cx0, cy0, f0, d_xy.p, d_ok.p, st);
+      launch_board_poses(PQ, d_xy.p, d_ok.p, d_use.p, d_q.p, d_p.p, d_e.p, d_valid.p, st);
+      CU(cudaMemcpyAsync(q0.data(), d_q.p, 4 * (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(p0.data(), d_p.p, 3 * (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(ok0.data(), d_valid.p, (size_t)nv * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  if (!need_poses) {
+    memcpy(q0.data(), q_init, 4 * (size_t)nv * sizeof(double)); memcpy(p0.data(), p_init, 3 * (size_t)nv * sizeof(double));
+    if (init_valid) for (int i = 0; i < nv; ++i) ok0[i] = init_valid[i] != 0;
+  }
+  // ---- state: R_cw = conj(q_wc), camera centre, shared intrinsics ---------------------------------------------------------------
+  std::vector<double> qs(4 * (size_t)nv), k0(10, 0.0);
+  for (int v = 0; v < nv; ++v) { const Q4 q = qn(&q0[4 * v]); qs[4 * v] = -q.x; qs[4 * v + 1] = -q.y; qs[4 * v + 2] = -q.z; qs[4 * v + 3] = q.w; }
+  // the internal initialiser refines (focal length, division distortion, poses) jointly before the target model takes over -- the
+  // role of utils::initialize_radial_undistortion_camera (:283-306), which hands the reference a focal length and a division-model
+  // distortion for every non-pinhole model
+  const bool prestage = need_poses && need_focal && model != CAM_PINHOLE && model != CAM_PINHOLE_RADTAN;
+  std::vector<int> active;
+  for (int v = 0; v < nv; ++v) if (ok0[v]) active.push_back(v);
+  S.n_views_initialized = (int)active.size();
+  if (prestage) { k0[0] = f0; k0[1] = 1.0; k0[2] = cx0; k0[3] = cy0; k0[4] = -1e-2 / ((double)W * W + (double)H * H); }
+  DevBuf<double> d_q[2], d_c[2], d_k[2], d_blocks, d_Y, d_scale, d_sys, d_red, d_dk, d_scal, d_verr;
+  for (int i = 0; i < 2; ++i) { CU(d_q[i].upload(qs)); CU(d_c[i].upload(p0)); CU(d_k[i].upload(k0)); }
+  const size_t na0 = std::max<size_t>(1, active.size());
+  CU(d_blocks.alloc(na0 * CC_PACK)); CU(d_Y.alloc(na0 * CC_Y)); CU(d_scale.alloc(6 * na0 + 10)); CU(d_sys.alloc(CC_PACK + 1)); CU(d_red.alloc(66));
+  CU(d_dk.alloc(10)); CU(d_scal.alloc(CC_SCAL_COUNT)); CU(d_verr.alloc(nv));
+  int cur = 0;
+  CamCalProblem Q; memset(&Q, 0, sizeof Q);
+  Q.model = model; Q.n_points = np; Q.huber = o.huber_width; Q.board = d_board.p; Q.f_off = d_off.p; Q.pid = d_pid.p; Q.uv = d_uv.p; Q.active = d_active.p;
+  auto state = [&](int i) { CamCalState s; s.q = d_q[i].p; s.c = d_c[i].p; s.k = d_k[i].p; return s; };
+  auto set_active = [&]() -> icc_status {
+    Q.n_active = (int)active.size();
+    if (!active.empty()) CU(cudaMemcpyAsync(d_active.p, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // `active` may be modified by the caller right after
+    return ICC_OK;
+  };
+  std::vector<double> verr(nv, 0.0);
+  // GetReprojErrorOfView for every active view at the current state
+  auto view_errors = [&]() -> icc_status {
+    CU(cudaMemsetAsync(d_scal.p, 0, CC_SCAL_COUNT * sizeof(double), st));
+    launch_camcal_accumulate(Q, state(cur), false, nullptr, nullptr, d_scal.p + CC_CAND_COST, d_verr.p, st);
+    CU(cudaMemcpyAsync(verr.data(), d_verr.p, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ICC_OK;
+  };
+  // RemoveViewsReprojError (:59-76)
+  auto remove_views = [&](double max_err) -> icc_status {
+    icc_status r = view_errors(); if (r != ICC_OK) return r;
+    std::vector<int> keep; for (int v : active) if (!(verr[v] > max_err)) keep.push_back(v);
+    active.swap(keep);
+    return set_active();
+  };
+  // theia::BundleAdjustViews: Levenberg-Marquardt with Ceres' trust-region logic; one device->host read-back per iteration
+  auto bundle_adjust = [&](unsigned mask, bool pose_free, int stage) -> icc_status {
+    Q.intr_mask = mask; Q.pose_free = pose_free ? 1 : 0;
+    double radius = 1e4, decrease_factor = 2.0, x_cost = 0.0, sc[CC_SCAL_COUNT];
+    int invalid = 0; bool ne_valid = false, first = true;
+    int term = 0, iters = 0;
+    if (Q.n_active == 0 || (mask == 0u && !pose_free)) { if (stage >= 0) S.termination[stage] = 3; return ICC_OK; }
+    for (int it = 0; it < o.max_num_iterations; ++it) {
+      bool fresh = false;
+      if (!ne_valid) {
+        CU(cudaMemsetAsync(d_sys.p, 0, (CC_PACK + 1) * sizeof(double), st));
+        launch_camcal_accumulate(Q, state(cur), true, d_blocks.p, d_sys.p, nullptr, nullptr, st);
+        ne_valid = true; fresh = true;
+      }
+      CU(cudaMemsetAsync(d_red.p, 0, 66 * sizeof(double), st));
+      CU(cudaMemsetAsync(d_scal.p, 0, CC_SCAL_COUNT * sizeof(double), st));
+      launch_camcal_step(Q, state(cur), state(1 - cur), d_blocks.p, d_sys.p, d_red.p, d_Y.p, d_scale.p, first ? 1 : 0, radius, 1e-6, 1e32, d_dk.p, d_scal.p, st);
+      launch_camcal_accumulate(Q, state(1 - cur), false, nullptr, nullptr, d_scal.p + CC_CAND_COST, nullptr, st);
+      CU(cudaMemcpyAsync(sc, d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (fresh) {
+        x_cost = sc[CC_X_COST];
+        if (first) { if (stage == 0) S.initial_cost = x_cost; if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost"); }
+        if (sc[CC_GRAD_MAX] <= o.gradient_tolerance) { term = 3; first = false; break; }
+      }
+      first = false;
+      ++iters;
+      const double model_change = 0.5 * (sc[CC_D_DELTA] - sc[CC_G_DELTA]);
+      if (sc[CC_FAIL] != 0.0 || !(model_change > 0.0)) {
+        if (++invalid >= 5) { term = 4; break; }
+        radius /= decrease_factor; decrease_factor *= 2.0;
+        continue;
+      }
+      invalid = 0;
+      const double step_norm = std::sqrt(sc[CC_STEP_SQ]), x_norm = std::sqrt(sc[CC_X_SQ]);
+      double cand_cost = sc[CC_CAND_COST];
+      if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+      if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) { term = 2; break; }
+      const double cost_change = x_cost - cand_cost;
+      if (std::fabs(cost_change) <= o.function_tolerance * x_cost) { term = 1; break; }   // Ceres returns before accepting this step
+      const double rel = cost_change / model_change;
+      if (rel > 1e-3) {
+        cur = 1 - cur; x_cost = cand_cost; ne_valid = false;
+        radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+        decrease_factor = 2.0;
+      } else {
+        radius /= decrease_factor; decrease_factor *= 2.0;
+        if (radius < 1e-32) { term = 4; break; }
+      }
+    }
+    // both state copies must agree on everything outside the last step (inactive views never move; the intrinsics / poses of
+    // a rejected candidate are stale): bring the spare copy back to the current state
+    CU(cudaMemcpyAsync(d_q[1 - cur].p, d_q[cur].p, 4 * (size_t)nv * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d_c[1 - cur].p, d_c[cur].p, 3 * (size_t)nv * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d_k[1 - cur].p, d_k[cur].p, 10 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (stage >= 0) { S.final_cost[stage] = x_cost; S.iterations[stage] = iters; S.termination[stage] = term; } else S.init_iterations = iters;
+    return ICC_OK;
+  };
+  auto finish = [&](bool success) -> icc_status {
+    icc_status r = view_errors(); if (r != ICC_OK) return r;
+    std::vector<double> qh(4 * (size_t)nv), ch(3 * (size_t)nv), kh(10);
+    CU(cudaMemcpy(qh.data(), d_q[cur].p, qh.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ch.data(), d_c[cur].p, ch.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(kh.data(), d_k[cur].p, 10 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int v = 0; v < nv; ++v) {
+      q_out[4 * v] = -qh[4 * v]; q_out[4 * v + 1] = -qh[4 * v + 1]; q_out[4 * v + 2] = -qh[4 * v + 2]; q_out[4 * v + 3] = qh[4 * v + 3];
+      for (int d = 0; d < 3; ++d) p_out[3 * v + d] = ch[3 * v + d];
+      used_out[v] = 0; if (err_out) err_out[v] = 0.0;
+    }
+    double tot = 0.0;
+    for (int v : active) { used_out[v] = 1; if (err_out) err_out[v] = verr[v]; tot += verr[v]; }
+    for (int i = 0; i < 10; ++i) intr_out[i] = kh[i];
+    S.success = success ? 1 : 0; S.n_views_used = (int)active.size();
+    S.final_reproj_error = active.empty() ? 0.0 : tot / (double)active.size();                 // :352-366
+    S.gpu_launches = kernel_launch_count() - launches0;
+    S.seconds_total = std::chrono::duration<double>(clk::now() - t_start).count();
+    if (summary) *summary = S;
+    if (!success) h->err = "Not enough views for proper calibration";
+    return ICC_OK;
+  };
+  icc_status rc = set_active(); if (rc != ICC_OK) return rc;
+  if (prestage) {
+    Q.model = CAM_DIVISION_UNDISTORTION;
+    rc = bundle_adjust((1u << 0) | (1u << 4), true, -1); if (rc != ICC_OK) return rc;
+    Q.model = model;
+    double kd[10];
+    CU(cudaMemcpy(kd, d_k[cur].p, sizeof kd, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p0.data(), d_c[cur].p, p0.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (kd[0] > 0.0 && std::isfinite(kd[0])) { f0 = kd[0]; if (model == CAM_DIVISION_UNDISTORTION) distortion_init = kd[4]; }
+  }
+  S.focal_length_init = f0;
+  // ---- grid filter in file order (:313-325): a view is taken iff no accepted camera position lies within grid_size ---------------
+  {
+    std::vector<int> sel;
+    for (int v : active) {
+      bool take = true;
+      for (int a : sel) {
+        const double dx = p0[3 * v] - p0[3 * a], dy = p0[3 * v + 1] - p0[3 * a + 1], dz = p0[3 * v + 2] - p0[3 * a + 2];
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) < o.grid_size) { take = false; break; }
+      }
+      if (take) sel.push_back(v);
+    }
+    active.swap(sel);
+  }
+  S.n_views_selected = (int)active.size();
+  rc = set_active(); if (rc != ICC_OK) return rc;
+  // ---- initial intrinsics of the target model (AddView :84-129) --------------------------------------------------------------------
+  std::fill(k0.begin(), k0.end(), 0.0);
+  k0[0] = f0; k0[1] = 1.0;
+  switch (model) {
+    case CAM_FOV: case CAM_DIVISION_UNDISTORTION: k0[2] = cx0; k0[3] = cy0; break;
+    default: k0[3] = cx0; k0[4] = cy0; break;
+  }
+  if (model == CAM_DIVISION_UNDISTORTION) k0[4] = distortion_init;
+  if (model == CAM_FOV) k0[4] = distortion_init != 0.0 ? distortion_init : 1e-3;   // theia's FOV model has no gradient at omega = 0
+  if (model == CAM_DOUBLE_SPHERE) { k0[5] = -0.25; k0[6] = 0.5; }
+  if (model == CAM_EXTENDED_UNIFIED) { k0[5] = 0.5; k0[6] = 1.0; }
+  for (int i = 0; i < 2; ++i) CU(cudaMemcpy(d_k[i].p, k0.data(), 10 * sizeof(double), cudaMemcpyHostToDevice));
+  if ((int)active.size() < o.min_num_views) return finish(false);                               // :132-135
+  const IntrinsicSubsets sub = intrinsic_subsets(model);
+  // 1. focal length and radial distortion, principal point fixed (:146-160)
+  rc = bundle_adjust(sub.focal | (model != CAM_PINHOLE ? sub.radial : 0u), true, 0); if (rc != ICC_OK) return rc;
+  rc = remove_views(o.max_view_error_stage1_px); if (rc != ICC_OK) return rc;                    // :162
+  // 2. principal point, everything else fixed (:164-174)
+  rc = bundle_adjust(sub.principal, false, 1); if (rc != ICC_OK) return rc;
+  if ((int)active.size() < o.min_num_views) return finish(false);                               // :176-179
+  // 3. full optimisation (:181-198)
+  rc = bundle_adjust(sub.principal | sub.focal | sub.aspect | (model == CAM_PINHOLE ? sub.radial : 0u) | (model == CAM_PINHOLE_RADTAN ? sub.tangential : 0u), true, 2);
+  if (rc != ICC_OK) return rc;
+  rc = remove_views(o.max_view_error_final_px); if (rc != ICC_OK) return rc;                     // :200
+  return finish((int)active.size() >= o.min_num_views);                                          // :202-205
+}
+
 void icc_trim_device_cache(void) { block_cache().trim(); }
 
 }  // extern "C"

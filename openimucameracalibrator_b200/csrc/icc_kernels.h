@@ -96,6 +96,27 @@ struct PoseProblem {
 };
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st);
 void launch_board_poses(const PoseProblem& Q, const double2* xy, const int* ok, unsigned char* use, double* q_wc, double* p_wc, double* err, int* valid, cudaStream_t st);
+// focal length per view from the board homography on centred pixels (f2[v] = f^2 or 0), pinhole normalisation of pixels
+void launch_board_focal(const PoseProblem& Q, const double2* uv, double cx, double cy, double2* xy, unsigned char* use, double* f2, cudaStream_t st);
+void launch_pinhole_normalize(int n, const double2* uv, double cx, double cy, double f, double2* xy, int* ok, cudaStream_t st);
+// ---- camera intrinsic calibration: bundle adjustment of view poses + shared intrinsics (icc_camcal.cu) ----------------------
+// Column order of a view's [J | r] rows: 0-2 rotation increment, 3-5 camera centre, 6-15 intrinsics (Theia order), 16 residual.
+constexpr int CC_COLS = 17, CC_PACK = CC_COLS * (CC_COLS + 1) / 2, CC_Y = 66;   // packed upper triangle; Y = A^-1 [H_pk | g_p] (6 x 11)
+enum { CC_CAND_COST = 0, CC_G_DELTA = 1, CC_D_DELTA = 2, CC_STEP_SQ = 3, CC_X_SQ = 4, CC_FAIL = 5, CC_GRAD_MAX = 6, CC_X_COST = 7, CC_SCAL_COUNT = 8 };
+struct CamCalProblem {
+  int model, n_points, n_active, pose_free;
+  unsigned intr_mask;          // bit i set = intrinsic i is optimised in this stage
+  double huber;                // loss width (camera_calibrator.cc:143)
+  const double4* board; const int* f_off; const int* pid; const double2* uv;
+  const int* active;           // indices of the views that take part (n_active)
+};
+struct CamCalState { double* q; double* c; double* k; };   // R_cw as (x,y,z,w) per view, camera centre per view, 10 intrinsics
+// with_jacobian: per-view packed blocks (n_active x CC_PACK) + the intrinsics part and the cost summed into sys[CC_PACK + 1];
+// otherwise cost only into *cost_out and (optional) the per-view mean reprojection error [px] into view_err (indexed by view)
+void launch_camcal_accumulate(const CamCalProblem& Q, const CamCalState& S, bool with_jacobian, double* blocks, double* sys, double* cost_out, double* view_err, cudaStream_t st);
+// one damped step: per-view Schur elimination, reduced intrinsics system, back-substitution into the candidate state
+void launch_camcal_step(const CamCalProblem& Q, const CamCalState& cur, const CamCalState& cand, const double* blocks, const double* sys, double* red /* 66 */, double* Y,
+                        double* scale /* 6 n_active + 10 */, int compute_scale, double radius, double min_diag, double max_diag, double* dk /* 10 */, double* scal, cudaStream_t st);
 // ---- IMU-to-camera rotation + time offset initialiser (icc_rotinit.cu) -----------------------------------------------------
 struct RotInitState {
   double a, b, c, d;          // golden-section bracket and its two interior candidates (time offsets, seconds)

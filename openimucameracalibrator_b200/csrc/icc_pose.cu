@@ -204,19 +204,17 @@ ICC_D void pose_refine(const PoseProblem& Q, const double2* xy, const unsigned c
   }
 }
 
-__global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const double2* __restrict__ xy, const int* __restrict__ okc, unsigned char* __restrict__ use,
-                                                        double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ err_out, int* __restrict__ valid_out) {
-  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (f >= Q.n_frames) return;
-  const int c0 = Q.f_off[f], c1 = Q.f_off[f + 1];
-  auto fail = [&]() {
-    if (lane == 0) { q_out[4 * f] = 0.0; q_out[4 * f + 1] = 0.0; q_out[4 * f + 2] = 0.0; q_out[4 * f + 3] = 1.0; p_out[3 * f] = 0.0; p_out[3 * f + 1] = 0.0; p_out[3 * f + 2] = 0.0; err_out[f] = 0.0; valid_out[f] = 0; }
-  };
+// Normalised DLT homography board plane -> image of one view, by one warp (every lane returns the same values):
+// marks the usable corners in use[], returns their count n, the board plane height zref and H (row-major, acting on
+// (X, Y, 1) with Z = zref); false = too few corners / degenerate / non-planar target.
+ICC_D bool board_homography(const PoseProblem& Q, const double2* __restrict__ xy, const int* __restrict__ okc, unsigned char* __restrict__ use, int c0, int c1,
+                            double& n_out, double& zref_out, double (&Hm)[9]) {
+  const int lane = threadIdx.x & 31;
   // ---- usable corners, board plane, Hartley normalisation ------------------------------------------------------------------
   double n = 0.0, sX = 0.0, sY = 0.0, sZ = 0.0, sx = 0.0, sy = 0.0;
   for (int c = c0 + lane; c < c1; c += 32) {
     const int id = Q.pid[c];
-    const bool u = okc[c] != 0 && id >= 0 && id < Q.n_points;
+    const bool u = (okc == nullptr || okc[c] != 0) && id >= 0 && id < Q.n_points;
     use[c] = u ? 1 : 0;
     if (!u) continue;
     const double4 Xb = Q.board[id];
@@ -224,8 +222,10 @@ __global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const do
   }
   n = wsum(n); sX = wsum(sX); sY = wsum(sY); sZ = wsum(sZ); sx = wsum(sx); sy = wsum(sy);
   __syncwarp();
-  if (c1 - c0 < Q.min_points || n < 6.0) { fail(); return; }   // pose_estimator.cc:140 (all corners counted), :65
+  n_out = n;
+  if (c1 - c0 < Q.min_points || n < 6.0) return false;   // pose_estimator.cc:140 (all corners counted), :65
   const double mX = sX / n, mY = sY / n, zref = sZ / n, mx = sx / n, my = sy / n;
+  zref_out = zref;
   double dB = 0.0, dI = 0.0, dz = 0.0;
   for (int c = c0 + lane; c < c1; c += 32) {
     if (!use[c]) continue;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const do
   dB = wsum(dB) / n; dI = wsum(dI) / n;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dz = fmax(dz, __shfl_xor_sync(0xffffffffu, dz, o));
-  if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * fmax(1.0, dB)) { fail(); return; }   // degenerate or non-planar target
+  if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * fmax(1.0, dB)) return false;   // degenerate or non-planar target
   const double sB = sqrt(2.0) / dB, sI = sqrt(2.0) / dI;
   // ---- homography (h33 = 1) from the normal equations of the DLT rows -------------------------------------------------------
   double M[36], v8[8];
@@ -267,13 +267,26 @@ __global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const do
       for (int j = 0; j <= i; ++j) { const double v = wsum(M[idx]); A8[i][j] = v; A8[j][i] = v; ++idx; }
     }
   }
-  if (!chol_solve<8>(A8, h)) { fail(); return; }
+  if (!chol_solve<8>(A8, h)) return false;
   // de-normalise: H = T_img^-1 Hn T_board,  T_board = [sB 0 -sB mX; 0 sB -sB mY; 0 0 1],  T_img^-1 = [1/sI 0 mx; 0 1/sI my; 0 0 1]
-  double Hn[9] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 1.0}, G[9], Hm[9];
+  double Hn[9] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 1.0}, G[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r) { G[3 * r] = Hn[3 * r] * sB; G[3 * r + 1] = Hn[3 * r + 1] * sB; G[3 * r + 2] = Hn[3 * r + 2] - sB * (Hn[3 * r] * mX + Hn[3 * r + 1] * mY); }
 #pragma unroll
   for (int cidx = 0; cidx < 3; ++cidx) { Hm[cidx] = G[cidx] / sI + mx * G[6 + cidx]; Hm[3 + cidx] = G[3 + cidx] / sI + my * G[6 + cidx]; Hm[6 + cidx] = G[6 + cidx]; }
+  return true;
+}
+
+__global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const double2* __restrict__ xy, const int* __restrict__ okc, unsigned char* __restrict__ use,
+                                                        double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ err_out, int* __restrict__ valid_out) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= Q.n_frames) return;
+  const int c0 = Q.f_off[f], c1 = Q.f_off[f + 1];
+  auto fail = [&]() {
+    if (lane == 0) { q_out[4 * f] = 0.0; q_out[4 * f + 1] = 0.0; q_out[4 * f + 2] = 0.0; q_out[4 * f + 3] = 1.0; p_out[3 * f] = 0.0; p_out[3 * f + 1] = 0.0; p_out[3 * f + 2] = 0.0; err_out[f] = 0.0; valid_out[f] = 0; }
+  };
+  double n = 0.0, zref = 0.0, Hm[9];
+  if (!board_homography(Q, xy, okc, use, c0, c1, n, zref, Hm)) { fail(); return; }
   // H ~ [r1 r2 t] (points on the plane z = zref, shifted to z = 0): scale, cheirality, Gram-Schmidt
   V3 h1 = v3(Hm[0], Hm[3], Hm[6]), h2 = v3(Hm[1], Hm[4], Hm[7]), h3 = v3(Hm[2], Hm[5], Hm[8]);
   double s = 2.0 / (sqrt(dot(h1, h1)) + sqrt(dot(h2, h2)));
@@ -320,6 +333,35 @@ __global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const do
   }
 }
 
+
+// Focal length of a view from its board homography on principal-point-centred pixels (square pixels, zero skew):
+// H ~ K [r1 r2 t], K = diag(f, f, 1), r1 . r2 = 0 and |r1| = |r2| give two linear equations a_i + f^2 b_i = 0 (Zhang's
+// constraints); least squares over both.  f2_out[v] = f^2, or 0 when the view is unusable / the estimate is not positive.
+__global__ void __launch_bounds__(128) board_focal_kernel(PoseProblem Q, const double2* __restrict__ uv, double cx, double cy, double2* __restrict__ xy,
+                                                         unsigned char* __restrict__ use, double* __restrict__ f2_out) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= Q.n_frames) return;
+  const int c0 = Q.f_off[f], c1 = Q.f_off[f + 1];
+  for (int c = c0 + lane; c < c1; c += 32) xy[c] = make_double2(uv[c].x - cx, uv[c].y - cy);
+  __syncwarp();
+  double n = 0.0, zref = 0.0, H[9], f2 = 0.0;
+  if (board_homography(Q, xy, nullptr, use, c0, c1, n, zref, H)) {
+    const double a1 = H[0] * H[1] + H[3] * H[4], b1 = H[6] * H[7];
+    const double a2 = H[0] * H[0] + H[3] * H[3] - H[1] * H[1] - H[4] * H[4], b2 = H[6] * H[6] - H[7] * H[7];
+    const double den = b1 * b1 + b2 * b2;
+    if (den > 0.0) f2 = -(a1 * b1 + a2 * b2) / den;
+    if (!(f2 > 0.0) || !isfinite(f2)) f2 = 0.0;
+  }
+  if (lane == 0) f2_out[f] = f2;
+}
+
+__global__ void pinhole_normalize_kernel(int n, const double2* __restrict__ uv, double cx, double cy, double inv_f, double2* __restrict__ xy, int* __restrict__ ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  xy[i] = make_double2((uv[i].x - cx) * inv_f, (uv[i].y - cy) * inv_f);
+  ok[i] = 1;
+}
+
 }  // namespace
 
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st) {
@@ -332,6 +374,18 @@ void launch_unproject(int model, const double* intr10, int n, const double2* uv,
 void launch_board_poses(const PoseProblem& Q, const double2* xy, const int* ok, unsigned char* use, double* q_wc, double* p_wc, double* err, int* valid, cudaStream_t st) {
   if (Q.n_frames <= 0) return;
   board_pose_kernel<<<(Q.n_frames + 3) / 4, 128, 0, st>>>(Q, xy, ok, use, q_wc, p_wc, err, valid);
+  count_launch();
+}
+
+void launch_board_focal(const PoseProblem& Q, const double2* uv, double cx, double cy, double2* xy, unsigned char* use, double* f2, cudaStream_t st) {
+  if (Q.n_frames <= 0) return;
+  board_focal_kernel<<<(Q.n_frames + 3) / 4, 128, 0, st>>>(Q, uv, cx, cy, xy, use, f2);
+  count_launch();
+}
+
+void launch_pinhole_normalize(int n, const double2* uv, double cx, double cy, double f, double2* xy, int* ok, cudaStream_t st) {
+  if (n <= 0) return;
+  pinhole_normalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, uv, cx, cy, 1.0 / f, xy, ok);
   count_launch();
 }
 

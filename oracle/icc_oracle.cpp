@@ -1080,6 +1080,40 @@ Qd quat_from_cols(const Vd& r1, const Vd& r2, const Vd& r3) {
   return qnormalized(q);
 }
 double vnorm(const Vd& a) { return std::sqrt(dot(a, a)); }
+// Normalised DLT homography board plane (X, Y, 1) -> image of one view; zref = height of the board plane
+bool oracle_homography(const std::vector<PoseObs>& ob, double& zref, double Hm[9]) {
+  const double n = (double)ob.size();
+  double mX = 0, mY = 0, mx = 0, my = 0; zref = 0.0;
+  for (const PoseObs& p : ob) { zref += p.Z; mX += p.X; mY += p.Y; mx += p.x; my += p.y; }
+  zref /= n; mX /= n; mY /= n; mx /= n; my /= n;
+  double dB = 0, dI = 0, dz = 0; for (const PoseObs& p : ob) { dB += std::hypot(p.X - mX, p.Y - mY); dI += std::hypot(p.x - mx, p.y - my); dz = std::max(dz, std::fabs(p.Z - zref)); }
+  dB /= n; dI /= n;
+  if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * std::max(1.0, dB)) return false;   // degenerate or non-planar target
+  const double sB = std::sqrt(2.0) / dB, sI = std::sqrt(2.0) / dI;
+  // DLT: null vector of A^T A (9 x 9) by inverse iteration with a tiny shift
+  std::vector<double> M(81, 0.0);
+  for (const PoseObs& p : ob) {
+    const double X = (p.X - mX) * sB, Y = (p.Y - mY) * sB, x = (p.x - mx) * sI, y = (p.y - my) * sI;
+    const double ra[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x}, rb[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+    for (int a2 = 0; a2 < 9; ++a2) for (int b2 = 0; b2 < 9; ++b2) M[a2 * 9 + b2] += ra[a2] * ra[b2] + rb[a2] * rb[b2];
+  }
+  double tr = 0; for (int a2 = 0; a2 < 9; ++a2) tr += M[a2 * 9 + a2];
+  std::vector<double> hv(9, 1.0 / 3.0);
+  bool okh = true;
+  for (int it = 0; it < 8 && okh; ++it) {
+    std::vector<double> A = M, b = hv;
+    for (int a2 = 0; a2 < 9; ++a2) A[a2 * 9 + a2] += 1e-14 * tr;
+    okh = gauss_solve(9, A, b);
+    double nn = 0; for (double v : b) nn += v * v; nn = std::sqrt(nn);
+    if (!(nn > 0.0)) { okh = false; break; }
+    for (int a2 = 0; a2 < 9; ++a2) hv[a2] = b[a2] / nn;
+  }
+  if (!okh) return false;
+  double G[9];
+  for (int r = 0; r < 3; ++r) { G[3 * r] = hv[3 * r] * sB; G[3 * r + 1] = hv[3 * r + 1] * sB; G[3 * r + 2] = hv[3 * r + 2] - sB * (hv[3 * r] * mX + hv[3 * r + 1] * mY); }
+  for (int c = 0; c < 3; ++c) { Hm[c] = G[c] / sI + mx * G[6 + c]; Hm[3 + c] = G[3 + c] / sI + my * G[6 + c]; Hm[6 + c] = G[6 + c]; }
+  return true;
+}
 }  // namespace
 
 icc_status icco_pixels_to_normalized(void* h, int n, const double* uv, double* xy, int32_t* ok) {
@@ -1106,36 +1140,8 @@ icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const 
       ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], xy[0], xy[1]});
     }
     if (off[f + 1] - off[f] < min_points || ob.size() < 6) continue;
-    const double n = (double)ob.size();
-    double zref = 0.0, mX = 0, mY = 0, mx = 0, my = 0;
-    for (const PoseObs& p : ob) { zref += p.Z; mX += p.X; mY += p.Y; mx += p.x; my += p.y; }
-    zref /= n; mX /= n; mY /= n; mx /= n; my /= n;
-    double dB = 0, dI = 0, dz = 0; for (const PoseObs& p : ob) { dB += std::hypot(p.X - mX, p.Y - mY); dI += std::hypot(p.x - mx, p.y - my); dz = std::max(dz, std::fabs(p.Z - zref)); }
-    dB /= n; dI /= n;
-    if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * std::max(1.0, dB)) continue;   // degenerate or non-planar target
-    const double sB = std::sqrt(2.0) / dB, sI = std::sqrt(2.0) / dI;
-    // DLT: null vector of A^T A (9 x 9) by inverse iteration with a tiny shift
-    std::vector<double> M(81, 0.0);
-    for (const PoseObs& p : ob) {
-      const double X = (p.X - mX) * sB, Y = (p.Y - mY) * sB, x = (p.x - mx) * sI, y = (p.y - my) * sI;
-      const double ra[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x}, rb[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
-      for (int a2 = 0; a2 < 9; ++a2) for (int b2 = 0; b2 < 9; ++b2) M[a2 * 9 + b2] += ra[a2] * ra[b2] + rb[a2] * rb[b2];
-    }
-    double tr = 0; for (int a2 = 0; a2 < 9; ++a2) tr += M[a2 * 9 + a2];
-    std::vector<double> hv(9, 1.0 / 3.0);
-    bool okh = true;
-    for (int it = 0; it < 8 && okh; ++it) {
-      std::vector<double> A = M, b = hv;
-      for (int a2 = 0; a2 < 9; ++a2) A[a2 * 9 + a2] += 1e-14 * tr;
-      okh = gauss_solve(9, A, b);
-      double nn = 0; for (double v : b) nn += v * v; nn = std::sqrt(nn);
-      if (!(nn > 0.0)) { okh = false; break; }
-      for (int a2 = 0; a2 < 9; ++a2) hv[a2] = b[a2] / nn;
-    }
-    if (!okh) continue;
-    double G[9], Hm[9];
-    for (int r = 0; r < 3; ++r) { G[3 * r] = hv[3 * r] * sB; G[3 * r + 1] = hv[3 * r + 1] * sB; G[3 * r + 2] = hv[3 * r + 2] - sB * (hv[3 * r] * mX + hv[3 * r + 1] * mY); }
-    for (int c = 0; c < 3; ++c) { Hm[c] = G[c] / sI + mx * G[6 + c]; Hm[3 + c] = G[3 + c] / sI + my * G[6 + c]; Hm[6 + c] = G[6 + c]; }
+    double zref = 0.0, Hm[9];
+    if (!oracle_homography(ob, zref, Hm)) continue;
     const Vd h1{Hm[0], Hm[3], Hm[6]}, h2{Hm[1], Hm[4], Hm[7]}, h3{Hm[2], Hm[5], Hm[8]};
     double sc = 2.0 / (vnorm(h1) + vnorm(h2));
     if (h3.z * sc < 0.0) sc = -sc;
@@ -1390,6 +1396,277 @@ icc_status icco_spline_error_weighting(void* h, int n, const double* times, cons
   *dt_out = found;
   *var_out = sew_removed_energy(xhat, fscale, found) / (double)n;
   return ICC_OK;
+}
+
+// ---- upstream row f4: camera intrinsic calibration (restates src/core/camera_calibrator.cc:131-389; TEST INFRASTRUCTURE) -----------
+// Formulated the way theia::BundleAdjustViews poses it to Ceres (pyTheiaSfM@69c3d37, external): per view the extrinsic block
+// [position (3) | angle-axis of R_cw (3)] with plain additive updates, one shared intrinsic block, residual
+// theia::ReprojectionError = CameraToPixelCoordinates(intr, AngleAxisRotatePoint(aa, X - w * position)) - feature, Jacobians by
+// forward-mode Jet<4> passes, ceres::HuberLoss(1.345) through Ceres' corrector (rho'' <= 0 => sqrt(rho') scaling), dense normal
+// equations and dense Cholesky, Ceres' trust-region loop.  (The CUDA path uses right increments on a quaternion, closed-form
+// Jacobians and per-view Schur elimination: same cost, same optimum, different route.)
+}  // extern "C"
+namespace {
+template <class T> void angle_axis_rotate(const T* aa, const T* pt, T* out) {   // ceres/rotation.h AngleAxisRotatePoint
+  const T theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (jval(theta2) > 2.220446049250313e-16) {
+    const T theta = jsqrt(theta2), ct = jcos(theta), st = jsin(theta);
+    const T w[3] = {aa[0] / theta, aa[1] / theta, aa[2] / theta};
+    const T wxp[3] = {w[1] * pt[2] - w[2] * pt[1], w[2] * pt[0] - w[0] * pt[2], w[0] * pt[1] - w[1] * pt[0]};
+    const T tmp = (w[0] * pt[0] + w[1] * pt[1] + w[2] * pt[2]) * (T(1.0) - ct);
+    for (int i = 0; i < 3; ++i) out[i] = pt[i] * ct + wxp[i] * st + w[i] * tmp;
+  } else {
+    const T wxp[3] = {aa[1] * pt[2] - aa[2] * pt[1], aa[2] * pt[0] - aa[0] * pt[2], aa[0] * pt[1] - aa[1] * pt[0]};
+    for (int i = 0; i < 3; ++i) out[i] = pt[i] + wxp[i];
+  }
+}
+template <class T> bool theia_reprojection_error(int model, const T* ext, const T* intr, const double* X4, const double* feat, T* res) {
+  const T adj[3] = {T(X4[0]) - ext[0] * X4[3], T(X4[1]) - ext[1] * X4[3], T(X4[2]) - ext[2] * X4[3]};
+  T rot[3], px[2];
+  angle_axis_rotate(ext + 3, adj, rot);
+  const bool ok = project<T>(model, intr, rot, px, true);
+  res[0] = px[0] - feat[0]; res[1] = px[1] - feat[1];
+  return ok;
+}
+struct CamCal {
+  int model, nv; const int32_t* off; const int32_t* ids; const double* uv; const std::vector<double>* points;
+  std::vector<double> ext;   // 6 per view
+  double k[10];
+  std::vector<int> active;
+  double huber;
+};
+double camcal_cost(const CamCal& C, const std::vector<double>& ext, const double* k, std::vector<double>* view_err) {
+  double cost = 0.0;
+  for (int v : C.active) {
+    double e = 0.0;
+    for (int c = C.off[v]; c < C.off[v + 1]; ++c) {
+      double r[2];
+      if (!theia_reprojection_error<double>(C.model, &ext[6 * v], k, &(*C.points)[4 * (size_t)C.ids[c]], C.uv + 2 * c, r)) { cost += 1e10; e += 1e10; continue; }
+      const double s2 = r[0] * r[0] + r[1] * r[1], rn = std::sqrt(s2);
+      cost += rn <= C.huber ? 0.5 * s2 : C.huber * rn - 0.5 * C.huber * C.huber;
+      e += rn;
+    }
+    if (view_err) (*view_err)[v] = C.off[v + 1] > C.off[v] ? e / double(C.off[v + 1] - C.off[v]) : 0.0;
+  }
+  return cost;
+}
+bool dense_cholesky_solve(int n, std::vector<double>& A, std::vector<double>& b) {   // A row-major SPD, overwritten by its factor
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int m = 0; m < j; ++m) d -= A[(size_t)j * n + m] * A[(size_t)j * n + m];
+    if (!(d > 0.0)) return false;
+    const double l = std::sqrt(d);
+    A[(size_t)j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) { double s2 = A[(size_t)i * n + j]; for (int m = 0; m < j; ++m) s2 -= A[(size_t)i * n + m] * A[(size_t)j * n + m]; A[(size_t)i * n + j] = s2 / l; }
+  }
+  for (int i = 0; i < n; ++i) { double s2 = b[i]; for (int m = 0; m < i; ++m) s2 -= A[(size_t)i * n + m] * b[m]; b[i] = s2 / A[(size_t)i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double s2 = b[i]; for (int m = i + 1; m < n; ++m) s2 -= A[(size_t)m * n + i] * b[m]; b[i] = s2 / A[(size_t)i * n + i]; }
+  return true;
+}
+struct CamCalStage { int iterations = 0, termination = 0; double initial_cost = 0, final_cost = 0; };
+// theia::BundleAdjustViews: which intrinsics are free (bit mask, Theia order) and whether the extrinsics are
+CamCalStage camcal_bundle_adjust(CamCal& C, unsigned mask, bool pose_free, const icc_camcal_options& o) {
+  CamCalStage R;
+  const int na = (int)C.active.size();
+  std::vector<int> kcol(10, -1); int n = pose_free ? 6 * na : 0;
+  for (int a = 0; a < 10; ++a) if ((mask >> a) & 1u) kcol[a] = n++;
+  if (n == 0 || na == 0) { R.termination = 3; return R; }
+  std::vector<double> H((size_t)n * n), g(n), scale(n, 1.0), D(n);
+  double x_cost = 0.0, radius = 1e4, decrease_factor = 2.0;
+  int invalid = 0; bool ne_valid = false, first = true;
+  typedef Jet<4> J4;
+  auto build = [&]() {
+    std::fill(H.begin(), H.end(), 0.0); std::fill(g.begin(), g.end(), 0.0);
+    x_cost = 0.0;
+    for (int s2 = 0; s2 < na; ++s2) {
+      const int v = C.active[s2];
+      for (int c = C.off[v]; c < C.off[v + 1]; ++c) {
+        double J[2][16], r[2]; bool ok = true;
+        for (int pass = 0; pass < 4; ++pass) {           // 16 ambient parameters in Jet<4> passes, like DynamicAutoDiff's strides
+          J4 e[6], k[10], res[2];
+          for (int i = 0; i < 6; ++i) { e[i] = J4(C.ext[6 * v + i]); const int gidx = i; if (gidx / 4 == pass) e[i].v[gidx % 4] = 1.0; }
+          for (int i = 0; i < 10; ++i) { k[i] = J4(C.k[i]); const int gidx = 6 + i; if (gidx / 4 == pass) k[i].v[gidx % 4] = 1.0; }
+          ok = theia_reprojection_error<J4>(C.model, e, k, &(*C.points)[4 * (size_t)C.ids[c]], C.uv + 2 * c, res) && ok;
+          r[0] = res[0].a; r[1] = res[1].a;
+          for (int d = 0; d < 4; ++d) { J[0][4 * pass + d] = res[0].v[d]; J[1][4 * pass + d] = res[1].v[d]; }
+        }
+        if (!ok) { x_cost += 1e10; continue; }
+        const double sq = r[0] * r[0] + r[1] * r[1], rn = std::sqrt(sq);
+        x_cost += rn <= C.huber ? 0.5 * sq : C.huber * rn - 0.5 * C.huber * C.huber;
+        const double w = rn <= C.huber ? 1.0 : C.huber / rn;   // rho'
+        int cols[16];
+        for (int i = 0; i < 6; ++i) cols[i] = pose_free ? 6 * s2 + i : -1;
+        for (int i = 0; i < 10; ++i) cols[6 + i] = kcol[i];
+        for (int a = 0; a < 16; ++a) {
+          if (cols[a] < 0) continue;
+          g[cols[a]] += w * (J[0][a] * r[0] + J[1][a] * r[1]);
+          for (int b = 0; b < 16; ++b) if (cols[b] >= 0) H[(size_t)cols[a] * n + cols[b]] += w * (J[0][a] * J[0][b] + J[1][a] * J[1][b]);
+        }
+      }
+    }
+  };
+  for (int it = 0; it < o.max_num_iterations; ++it) {
+    bool fresh = false;
+    if (!ne_valid) { build(); ne_valid = true; fresh = true; }
+    if (first) { for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H[(size_t)i * n + i])); R.initial_cost = x_cost; }
+    first = false;
+    if (fresh) { double gm = 0; for (double v : g) gm = std::max(gm, std::fabs(v)); if (gm <= o.gradient_tolerance) { R.termination = 3; break; } }
+    ++R.iterations;
+    std::vector<double> A = H, b(n);
+    for (int i = 0; i < n; ++i) {
+      const double sc = scale[i];
+      D[i] = std::min(std::max(sc * sc * H[(size_t)i * n + i], 1e-6), 1e32) / (radius * sc * sc);
+      A[(size_t)i * n + i] += D[i]; b[i] = -g[i];
+    }
+    double model_change = 0.0; const bool solved = dense_cholesky_solve(n, A, b);
+    if (solved) { double gd = 0, dd = 0; for (int i = 0; i < n; ++i) { gd += g[i] * b[i]; dd += D[i] * b[i] * b[i]; } model_change = 0.5 * (dd - gd); }
+    if (!solved || !(model_change > 0.0)) { if (++invalid >= 5) { R.termination = 4; break; } radius /= decrease_factor; decrease_factor *= 2.0; continue; }
+    invalid = 0;
+    std::vector<double> ext = C.ext; double k[10]; memcpy(k, C.k, sizeof k);
+    double step_sq = 0, x_sq = 0;
+    for (int a = 0; a < 10; ++a) { x_sq += C.k[a] * C.k[a]; if (kcol[a] >= 0) { k[a] += b[kcol[a]]; step_sq += b[kcol[a]] * b[kcol[a]]; } }
+    for (int s2 = 0; s2 < na; ++s2) { const int v = C.active[s2]; for (int i = 0; i < 6; ++i) { x_sq += C.ext[6 * v + i] * C.ext[6 * v + i]; if (pose_free) { ext[6 * v + i] += b[6 * s2 + i]; step_sq += b[6 * s2 + i] * b[6 * s2 + i]; } } }
+    double cand_cost = camcal_cost(C, ext, k, nullptr);
+    if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+    if (std::sqrt(step_sq) <= o.parameter_tolerance * (std::sqrt(x_sq) + o.parameter_tolerance)) { R.termination = 2; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= o.function_tolerance * x_cost) { R.termination = 1; break; }
+    const double rel = cost_change / model_change;
+    if (rel > 1e-3) {
+      C.ext = ext; memcpy(C.k, k, sizeof k); x_cost = cand_cost; ne_valid = false;
+      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+      decrease_factor = 2.0;
+    } else { radius /= decrease_factor; decrease_factor *= 2.0; if (radius < 1e-32) { R.termination = 4; break; } }
+  }
+  R.final_cost = x_cost;
+  return R;
+}
+double median_of(std::vector<double> v) {   // utils::MedianOfDoubleVec (src/utils/utils.cc:77-97)
+  const size_t n = v.size(); std::sort(v.begin(), v.end());
+  return n % 2 == 0 ? (v[n / 2 - 1] + v[n / 2]) / 2 : v[n / 2];
+}
+}  // namespace
+extern "C" {
+
+icc_status icco_calibrate_camera(void* h, int model, int W, int Hh, int nv, const int32_t* off, const int32_t* ids, const double* uv,
+                                 const double* q_init, const double* p_init, const int32_t* init_valid, double focal_init, double distortion_init,
+                                 const icc_camcal_options* options, double* intr_out, double* q_out, double* p_out, double* err_out, int32_t* used_out,
+                                 icc_camcal_summary* summary) {
+  Oracle& orc = *O(h);
+  if (nv <= 0 || !off || !ids || !uv || camera_num_params(model) < 0 || orc.points.empty()) return ICC_ERR_INVALID_ARGUMENT;
+  icc_camcal_options o; memset(&o, 0, sizeof o); if (options) o = *options;
+  if (o.grid_size < 0.0) o.grid_size = 0.04;
+  if (o.min_num_views <= 0) o.min_num_views = 10;
+  if (o.max_num_iterations <= 0) o.max_num_iterations = 100;
+  if (!(o.function_tolerance > 0.0)) o.function_tolerance = 1e-6;
+  if (!(o.parameter_tolerance > 0.0)) o.parameter_tolerance = 1e-8;
+  if (!(o.gradient_tolerance > 0.0)) o.gradient_tolerance = 1e-10;
+  if (!(o.huber_width > 0.0)) o.huber_width = 1.345;
+  if (!(o.max_view_error_stage1_px > 0.0)) o.max_view_error_stage1_px = 5.0;
+  if (!(o.max_view_error_final_px > 0.0)) o.max_view_error_final_px = 2.0;
+  icc_camcal_summary S; memset(&S, 0, sizeof S);
+  const double cx0 = W / 2.0, cy0 = Hh / 2.0;
+  const int np = (int)(orc.points.size() / 4);
+  // ---- initial focal length (median of the per-view homography estimates) and poses (pinhole board poses) -------------------------
+  std::vector<double> q0(4 * (size_t)nv), p0(3 * (size_t)nv); std::vector<int32_t> ok0(nv, 1);
+  double f0 = focal_init;
+  if (!(focal_init > 0.0)) {
+    std::vector<double> fs;
+    for (int v = 0; v < nv; ++v) {
+      std::vector<PoseObs> ob;
+      for (int c = off[v]; c < off[v + 1]; ++c) { if (ids[c] < 0 || ids[c] >= np) continue; const double* P = &orc.points[4 * (size_t)ids[c]]; ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], uv[2 * c] - cx0, uv[2 * c + 1] - cy0}); }
+      double zref, Hm[9];
+      if (off[v + 1] - off[v] < 6 || ob.size() < 6 || !oracle_homography(ob, zref, Hm)) continue;
+      const double a1 = Hm[0] * Hm[1] + Hm[3] * Hm[4], b1 = Hm[6] * Hm[7], a2 = Hm[0] * Hm[0] + Hm[3] * Hm[3] - Hm[1] * Hm[1] - Hm[4] * Hm[4], b2 = Hm[6] * Hm[6] - Hm[7] * Hm[7];
+      const double den = b1 * b1 + b2 * b2; if (!(den > 0.0)) continue;
+      const double f2 = -(a1 * b1 + a2 * b2) / den;
+      if (f2 > 0.0 && std::isfinite(f2)) fs.push_back(std::sqrt(f2));
+    }
+    if (fs.empty()) { orc.err = "no view yields a focal length estimate"; return ICC_ERR_NUMERIC; }
+    f0 = median_of(fs);
+  }
+  if (!q_init || !p_init) {
+    const int m_save = orc.model, n_save = orc.n_intr, w_save = orc.width, h_save = orc.height; double k_save[10]; memcpy(k_save, orc.intr, sizeof k_save);
+    const double kp[10] = {f0, 1.0, 0.0, cx0, cy0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    orc.model = 0; orc.n_intr = 7; memcpy(orc.intr, kp, sizeof kp); orc.width = W; orc.height = Hh;
+    std::vector<double> e(nv);
+    icco_estimate_board_poses(h, nv, off, ids, uv, 1e300, 6, q0.data(), p0.data(), e.data(), ok0.data());
+    orc.model = m_save; orc.n_intr = n_save; orc.width = w_save; orc.height = h_save; memcpy(orc.intr, k_save, sizeof k_save);
+  } else {
+    memcpy(q0.data(), q_init, 4 * (size_t)nv * sizeof(double)); memcpy(p0.data(), p_init, 3 * (size_t)nv * sizeof(double));
+    if (init_valid) for (int v = 0; v < nv; ++v) ok0[v] = init_valid[v] != 0;
+  }
+  CamCal C; C.model = model; C.nv = nv; C.off = off; C.ids = ids; C.uv = uv; C.points = &orc.points; C.huber = o.huber_width;
+  C.ext.resize(6 * (size_t)nv);
+  for (int v = 0; v < nv; ++v) {
+    const Qd qcw = so3_inv(qnormalized(Qd{q0[4 * v], q0[4 * v + 1], q0[4 * v + 2], q0[4 * v + 3]}));
+    const Vd aa = so3_log(qcw);
+    C.ext[6 * v] = p0[3 * v]; C.ext[6 * v + 1] = p0[3 * v + 1]; C.ext[6 * v + 2] = p0[3 * v + 2]; C.ext[6 * v + 3] = aa.x; C.ext[6 * v + 4] = aa.y; C.ext[6 * v + 5] = aa.z;
+  }
+  for (int v = 0; v < nv; ++v) if (ok0[v]) C.active.push_back(v);
+  S.n_views_initialized = (int)C.active.size();
+  // joint refinement of (focal length, division distortion, poses): what utils::initialize_radial_undistortion_camera hands the
+  // reference for every non-pinhole model (:283-306)
+  if ((!q_init || !p_init) && !(focal_init > 0.0) && model != 0 && model != 1) {
+    C.model = 4;
+    for (int i = 0; i < 10; ++i) C.k[i] = 0.0;
+    C.k[0] = f0; C.k[1] = 1.0; C.k[2] = cx0; C.k[3] = cy0; C.k[4] = -1e-2 / ((double)W * W + (double)Hh * Hh);
+    const CamCalStage pre = camcal_bundle_adjust(C, (1u << 0) | (1u << 4), true, o);
+    S.init_iterations = pre.iterations;
+    C.model = model;
+    if (C.k[0] > 0.0 && std::isfinite(C.k[0])) { f0 = C.k[0]; if (model == 4) distortion_init = C.k[4]; }
+  }
+  S.focal_length_init = f0;
+  {                                                                                         // grid filter (:313-325)
+    std::vector<int> sel;
+    for (int v : C.active) {
+      bool take = true;
+      for (int a : sel) { const double dx = C.ext[6 * v] - C.ext[6 * a], dy = C.ext[6 * v + 1] - C.ext[6 * a + 1], dz = C.ext[6 * v + 2] - C.ext[6 * a + 2]; if (std::sqrt(dx * dx + dy * dy + dz * dz) < o.grid_size) { take = false; break; } }
+      if (take) sel.push_back(v);
+    }
+    C.active.swap(sel);
+  }
+  S.n_views_selected = (int)C.active.size();
+  for (int i = 0; i < 10; ++i) C.k[i] = 0.0;
+  C.k[0] = f0; C.k[1] = 1.0;
+  const bool noskew = model == 3 || model == 4;
+  if (noskew) { C.k[2] = cx0; C.k[3] = cy0; } else { C.k[3] = cx0; C.k[4] = cy0; }
+  if (model == 4) C.k[4] = distortion_init;
+  if (model == 3) C.k[4] = distortion_init != 0.0 ? distortion_init : 1e-3;
+  if (model == 5) { C.k[5] = -0.25; C.k[6] = 0.5; }
+  if (model == 6) { C.k[5] = 0.5; C.k[6] = 1.0; }
+  auto bits = [](std::initializer_list<int> l) { unsigned m = 0; for (int i : l) m |= 1u << i; return m; };
+  const unsigned focal = 1u, aspect = 2u, principal = noskew ? bits({2, 3}) : bits({3, 4});
+  unsigned radial = 0, tangential = 0;
+  switch (model) { case 0: radial = bits({5, 6}); break; case 1: radial = bits({5, 6, 7}); tangential = bits({8, 9}); break; case 2: radial = bits({5, 6, 7, 8}); break;
+                   case 3: case 4: radial = bits({4}); break; default: radial = bits({5, 6}); break; }
+  std::vector<double> verr(nv, 0.0);
+  auto remove_views = [&](double max_err) { camcal_cost(C, C.ext, C.k, &verr); std::vector<int> keep; for (int v : C.active) if (!(verr[v] > max_err)) keep.push_back(v); C.active.swap(keep); };
+  auto finish = [&](bool success) {
+    camcal_cost(C, C.ext, C.k, &verr);
+    for (int v = 0; v < nv; ++v) {
+      const Qd qcw = so3_exp(Vd{C.ext[6 * v + 3], C.ext[6 * v + 4], C.ext[6 * v + 5]});
+      q_out[4 * v] = -qcw.x; q_out[4 * v + 1] = -qcw.y; q_out[4 * v + 2] = -qcw.z; q_out[4 * v + 3] = qcw.w;
+      for (int d = 0; d < 3; ++d) p_out[3 * v + d] = C.ext[6 * v + d];
+      used_out[v] = 0; if (err_out) err_out[v] = 0.0;
+    }
+    double tot = 0; for (int v : C.active) { used_out[v] = 1; if (err_out) err_out[v] = verr[v]; tot += verr[v]; }
+    for (int i = 0; i < 10; ++i) intr_out[i] = C.k[i];
+    S.success = success ? 1 : 0; S.n_views_used = (int)C.active.size(); S.final_reproj_error = C.active.empty() ? 0.0 : tot / double(C.active.size());
+    if (summary) *summary = S;
+    return ICC_OK;
+  };
+  if ((int)C.active.size() < o.min_num_views) return finish(false);
+  CamCalStage st = camcal_bundle_adjust(C, focal | (model != 0 ? radial : 0u), true, o);
+  S.iterations[0] = st.iterations; S.termination[0] = st.termination; S.initial_cost = st.initial_cost; S.final_cost[0] = st.final_cost;
+  remove_views(o.max_view_error_stage1_px);
+  st = camcal_bundle_adjust(C, principal, false, o);
+  S.iterations[1] = st.iterations; S.termination[1] = st.termination; S.final_cost[1] = st.final_cost;
+  if ((int)C.active.size() < o.min_num_views) return finish(false);
+  st = camcal_bundle_adjust(C, principal | focal | aspect | (model == 0 ? radial : 0u) | (model == 1 ? tangential : 0u), true, o);
+  S.iterations[2] = st.iterations; S.termination[2] = st.termination; S.final_cost[2] = st.final_cost;
+  remove_views(o.max_view_error_final_px);
+  return finish((int)C.active.size() >= o.min_num_views);
 }
 
 int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }

@@ -5,6 +5,6 @@ Drop-in for the one hot path of urbste/OpenImuCameraCalibrator: the spline batch
 behind the C-ABI of include/icc_b200.h); this package is the Python host mirror of the reference's
 `OpenICC::core::ImuCameraCalibrator` interface plus the synthetic-sequence generator and file-format helpers.
 """
-from .calibrator import ImuCameraCalibrator, SplineOptimFlags, load_library, library_path  # noqa: F401
+from .calibrator import CameraCalibrator, ImuCameraCalibrator, SplineOptimFlags, load_library, library_path  # noqa: F401
 
-__all__ = ["ImuCameraCalibrator", "SplineOptimFlags", "load_library", "library_path"]
+__all__ = ["CameraCalibrator", "ImuCameraCalibrator", "SplineOptimFlags", "load_library", "library_path"]

@@ -113,3 +113,113 @@ class ImuCameraCalibrator:
         _capi.load_dataset(self.api, ds, known_gravity=known_gravity, shard=shard)
         self._cam_timestamps = np.sort(np.asarray(ds["frame_t"], dtype=np.float64))
         return self
+
+
+class CameraCalibrator:
+    """Python host mirror of OpenICC::core::CameraCalibrator (include/OpenCameraCalibrator/core/camera_calibrator.h:25-86,
+    SURVEY.md §8(f) row f4): `CalibrateCameraFromJson` (src/core/camera_calibrator.cc:221-389) with the corner-file dictionary the
+    reference's tools exchange, or `AddView` / `AddObservation` / `RunCalibration` (:78-219) with caller-made initial poses.  The
+    bundle adjustment runs on the GPU behind `icc_calibrate_camera`; there is no CPU fallback."""
+
+    def __init__(self, camera_model: str, optimize_board_pts: bool = False, device: int = 0):
+        from . import camera_models as cm
+        if camera_model not in cm.MODEL_IDS:
+            raise IccError(f"unknown camera model {camera_model!r}")
+        self.camera_model, self.model = camera_model, cm.MODEL_IDS[camera_model]
+        self.optimize_board_pts = bool(optimize_board_pts)        # accepted, not implemented (camera_calibrator.cc:207-216)
+        self.api = CApi(load_library(), "icc_", int(device))
+        self.grid_size, self.verbose = 0.04, False
+        self._views, self._obs = [], {}
+        self._image_size = None
+        self.result = None
+
+    def SetGridSize(self, grid_size: float = 0.04):
+        self.grid_size = float(grid_size)
+
+    def SetVerbose(self):
+        self.verbose = True
+
+    def SetBoardPoints(self, xyzw):
+        self.api.set_board_points(xyzw)
+
+    def AddView(self, initial_rotation, initial_position, initial_focal_length, initial_distortion, image_width, image_height, timestamp_s, group_id=0):
+        """initial_rotation = R_cw (theia::Camera::SetOrientationFromRotationMatrix), initial_position = camera centre in the world."""
+        from .synthetic import matrix_to_quat_xyzw
+        R = np.asarray(initial_rotation, dtype=np.float64).reshape(3, 3)
+        self._views.append(dict(q_wc=matrix_to_quat_xyzw(R.T[None])[0], p_wc=np.asarray(initial_position, dtype=np.float64), f=float(initial_focal_length),
+                                k=float(initial_distortion), t=float(timestamp_s)))
+        self._image_size = (int(image_width), int(image_height))
+        self._obs[len(self._views) - 1] = []
+        return len(self._views) - 1
+
+    def AddObservation(self, view_id, object_point_id, corner) -> bool:
+        if view_id not in self._obs:
+            return False
+        self._obs[view_id].append((int(object_point_id), float(corner[0]), float(corner[1])))
+        return True
+
+    def RunCalibration(self) -> bool:
+        """Three-stage bundle adjustment from the views added so far (all of them: the grid filter belongs to CalibrateCameraFromJson)."""
+        if not self._views:
+            return False
+        off, ids, uv = [0], [], []
+        for v in range(len(self._views)):
+            for pid, x, y in self._obs[v]:
+                ids.append(pid); uv.append((x, y))
+            off.append(len(ids))
+        last = self._views[-1]                                     # the shared intrinsics keep the values of the last AddView (:101-113)
+        W, H = self._image_size
+        self.result = self.api.calibrate_camera(self.model, W, H, off, ids, np.array(uv).reshape(-1, 2), q_wc_init=np.array([v["q_wc"] for v in self._views]),
+                                                p_wc_init=np.array([v["p_wc"] for v in self._views]), focal_length_init=last["f"], distortion_init=last["k"], grid_size=0.0)
+        return bool(self.result["summary"]["success"])
+
+    def CalibrateCameraFromJson(self, scene_json: dict, output_path: str = "") -> bool:
+        """scene_json: the corner file as a dictionary (io_formats.ubjson_loads of extract_board_to_json's output).  Writes
+        `<output_path>.json` in the layout of io::write_camera_calibration when output_path is given."""
+        import json
+        from . import camera_models as cm
+        pts = scene_json["scene_pts"]
+        n = max(int(i) for i in pts) + 1
+        board = np.zeros((n, 4)); board[:, 3] = 1.0
+        for i, p in pts.items():
+            board[int(i), :3] = p
+        self.api.set_board_points(board)
+        W, H = int(scene_json["image_width"]), int(scene_json["image_height"])
+        off, ids, uv, self._timestamps_s = [0], [], [], []
+        for key in sorted(scene_json["views"]):                    # nlohmann::json objects iterate in key order
+            ip = scene_json["views"][key]["image_points"]
+            for pid in sorted(ip):
+                ids.append(int(pid)); uv.append(ip[pid])
+            off.append(len(ids)); self._timestamps_s.append(float(key) * 1e-6)
+        self.result = self.api.calibrate_camera(self.model, W, H, off, ids, np.array(uv, dtype=np.float64).reshape(-1, 2), grid_size=self.grid_size)
+        s = self.result["summary"]
+        if not s["success"]:
+            return False
+        if output_path:
+            k = self.result["intrinsics"]
+            noskew = self.model in (cm.FOV, cm.DIVISION_UNDISTORTION)
+            intr = {"skew": 0.0, "principal_pt_x": k[2] if noskew else k[3], "principal_pt_y": k[3] if noskew else k[4], "aspect_ratio": k[1], "focal_length": k[0]}
+            extra = {cm.DIVISION_UNDISTORTION: {"div_undist_distortion": 4}, cm.DOUBLE_SPHERE: {"xi": 5, "alpha": 6}, cm.EXTENDED_UNIFIED: {"alpha": 5, "beta": 6},
+                     cm.FISHEYE: {f"radial_distortion_{i + 1}": 5 + i for i in range(4)}, cm.FOV: {"radial_distortion_1": 4},
+                     cm.PINHOLE_RADIAL_TANGENTIAL: {"radial_distortion_1": 5, "radial_distortion_2": 6, "radial_distortion_3": 7, "tangential_distortion_1": 8, "tangential_distortion_2": 9}}
+            for name, idx in extra.get(self.model, {}).items():
+                intr[name] = k[idx]
+            doc = {"stabelized": False, "fps": scene_json["camera_fps"], "nr_calib_images": s["n_views_used"], "final_reproj_error": s["final_reproj_error"],
+                   "image_width": W, "image_height": H, "intrinsic_type": self.camera_model, "intrinsics": {a: float(b) for a, b in intr.items()}}
+            with open(output_path + ".json", "w") as f:
+                json.dump(doc, f, indent=2)
+        return True
+
+    def PrintResult(self):
+        from . import camera_models as cm
+        k = self.result["intrinsics"]
+        noskew = self.model in (cm.FOV, cm.DIVISION_UNDISTORTION)
+        print(f"Focal Length:{k[0]}px Principal Point: {k[2] if noskew else k[3]}/{k[3] if noskew else k[4]}px.")
+        if self.model == cm.DIVISION_UNDISTORTION:
+            print(f"DIVISION_UNDISTORTION model: Distortion: {k[4]}")
+        elif self.model == cm.DOUBLE_SPHERE:
+            print(f"DOUBLE_SPHERE model: XI: {k[5]} ALPHA: {k[6]}")
+        elif self.model == cm.EXTENDED_UNIFIED:
+            print(f"EXTENDED_UNIFIED model: {k[5]} BETA: {k[6]}")
+        elif self.model == cm.FISHEYE:
+            print("FISHEYE model: " + " ".join(f"Radial distortion {i + 1}: {k[5 + i]}" for i in range(4)))

@@ -202,3 +202,32 @@ def test_gpu_calibration_full_size(oracle_factory, gpu_factory):
     its = sum(s["iterations"]) + s["init_iterations"]
     print(f"\n[f4] 3000 views x 144 corners: {dt * 1e3:.1f} ms wall incl. H2D/D2H, {its} LM iterations, {s['gpu_launches']} launches, "
           f"f = {r['intrinsics'][0]:.3f} (truth {k[0]}), mean reprojection error {s['final_reproj_error']:.4f} px")
+
+
+@pytest.mark.gpu
+def test_gpu_python_mirror_of_camera_calibrator(tmp_path):
+    """openimucameracalibrator_b200.CameraCalibrator: the reference class's two entry routes give the C-ABI's numbers."""
+    import json
+    from openimucameracalibrator_b200 import CameraCalibrator
+    model, k = CASES[1]   # FISHEYE
+    B, off, ids, uv, q_true, p_true = scene(model, k, n_views=30, seed=31, noise_px=0.1)
+    scene_json = {"camera_fps": 30.0, "image_width": W, "image_height": H, "scene_pts": {str(i): list(map(float, p[:3])) for i, p in enumerate(B)},
+                  "views": {f"{f / 30.0 * 1e6:.6f}": {"image_points": {str(int(ids[c])): [float(uv[c, 0]), float(uv[c, 1])] for c in range(off[f], off[f + 1])}} for f in range(30)}}
+    cal = CameraCalibrator("FISHEYE")
+    cal.SetGridSize(0.001)
+    assert cal.CalibrateCameraFromJson(scene_json, str(tmp_path / "cam"))
+    doc = json.load(open(tmp_path / "cam.json"))
+    assert doc["intrinsic_type"] == "FISHEYE" and doc["nr_calib_images"] == 30 and abs(doc["intrinsics"]["focal_length"] - k[0]) < 0.005 * k[0]
+    assert abs(doc["intrinsics"]["radial_distortion_2"] - cal.result["intrinsics"][6]) < 1e-15
+    cal.PrintResult()
+    # AddView / AddObservation / RunCalibration with caller-made initial poses (R_cw, camera centre, focal length)
+    cal2 = CameraCalibrator("FISHEYE"); cal2.SetBoardPoints(B)
+    rng = np.random.default_rng(4)
+    for f in range(30):
+        R_cw = syn.quat_xyzw_to_matrix(q_true[f]).T
+        vid = cal2.AddView(R_cw, p_true[f] + rng.normal(0, 1e-3, 3), 430.0, 0.0, W, H, f / 30.0)
+        for c in range(off[f], off[f + 1]):
+            assert cal2.AddObservation(vid, ids[c], uv[c])
+    assert not cal2.AddObservation(99, 0, (0.0, 0.0))
+    assert cal2.RunCalibration()
+    assert np.abs(cal2.result["intrinsics"] - cal.result["intrinsics"]).max() < 2e-3 * k[0]     # default tolerances, two different starts

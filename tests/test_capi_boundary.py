@@ -38,7 +38,8 @@ def test_no_cpu_fallback_without_device():
     h = capi.CApi(calibrator.load_library(), "icc_", -1)
     capi.load_dataset(h, syn.make_dataset(syn.tiny_config()))
     for call in (lambda: h.optimize(1, 66), lambda: h.evaluate(66), lambda: h.lm_iterations(1, 66), lambda: h.mean_reprojection_error(),
-                 lambda: h.eval_trajectory([0]), lambda: h.time_evaluations(1, 66)):
+                 lambda: h.eval_trajectory([0]), lambda: h.time_evaluations(1, 66),
+                 lambda: h.calibrate_camera(0, 960, 540, [0, 1], [0], [[1.0, 2.0]])):
         with pytest.raises(capi.IccError, match="ICC_ERR_NO_DEVICE"):
             call()
 

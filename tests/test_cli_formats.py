@@ -200,3 +200,68 @@ def test_tool_chain_corners_to_calibration(tmp_path, gpu_factory):
     assert out.returncode == 0, out.stderr + out.stdout
     res = iof.read_result_json(str(tmp_path / "result.json"))
     assert np.isfinite(res["final_reproj_error"]) and abs(res["time_offset_imu_to_cam_s"] - init["time_offset_gyro_to_cam"]) < 1e-12
+
+
+# ---- upstream row f4: calibrate_camera ---------------------------------------------------------------------------------------------
+CAL_CLI = os.path.join(ROOT, "openimucameracalibrator_b200", "bin", "calibrate_camera")
+
+
+def _write_corner_file(path, board, off, ids, uv, fps=30.0, size=(960, 540)):
+    views = {iof.view_key(f / fps): {"image_points": {str(int(ids[c])): [float(uv[c, 0]), float(uv[c, 1])] for c in range(off[f], off[f + 1])}} for f in range(len(off) - 1)}
+    scene = {"calibration_board_type": "charuco", "square_size_meter": 0.021, "camera_fps": fps, "image_width": size[0], "image_height": size[1],
+             "scene_pts": {str(i): [float(p[0]), float(p[1]), float(p[2])] for i, p in enumerate(board)}, "views": views}
+    with open(path, "wb") as f:
+        f.write(iof.ubjson_dumps(scene))
+
+
+def test_calibrate_camera_cli_flags_and_failures(tmp_path):
+    assert os.path.exists(CAL_CLI), "build the CLI first (__graft_entry__.build())"
+    out = subprocess.run([CAL_CLI, "--input_corners=/nonexistent.uson"], capture_output=True, text=True)
+    assert out.returncode == 1 and "Failed to load" in out.stderr
+    out = subprocess.run([CAL_CLI, "--no_such_flag=1"], capture_output=True, text=True)
+    assert out.returncode == 1 and "unknown command line flag" in out.stderr
+    from test_camera_calibration import CASES, scene
+    B, off, ids, uv, q, p = scene(*CASES[0], n_views=3)
+    _write_corner_file(str(tmp_path / "c.uson"), B, off, ids, uv)
+    out = subprocess.run([CAL_CLI, "--input_corners=" + str(tmp_path / "c.uson"), "--camera_model_to_calibrate=NO_SUCH_MODEL"], capture_output=True, text=True)
+    assert out.returncode == 1 and "unknown camera model" in out.stderr
+
+
+@pytest.mark.gpu
+def test_calibrate_camera_cli_matches_api_and_feeds_the_pose_tool(tmp_path, gpu_factory):
+    from test_camera_calibration import CASES, W, H, scene
+    model, k = CASES[3]   # DOUBLE_SPHERE, the app's default model
+    B, off, ids, uv, q_true, p_true = scene(model, k, n_views=40, seed=9, noise_px=0.2)
+    corners = str(tmp_path / "corners.uson")
+    _write_corner_file(corners, B, off, ids, uv)
+    out = subprocess.run([CAL_CLI, "--input_corners=" + corners, "--save_path_calib_dataset=" + str(tmp_path / "cam"), "--grid_size", "0.001", "--verbose"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "Final camera calibration reprojection error" in out.stdout and "DOUBLE_SPHERE model: XI:" in out.stdout
+    cam = json.load(open(tmp_path / "cam.json"))
+    assert cam["intrinsic_type"] == "DOUBLE_SPHERE" and cam["image_width"] == W and cam["nr_calib_images"] == 40 and cam["stabelized"] is False
+    assert set(cam["intrinsics"]) == {"skew", "principal_pt_x", "principal_pt_y", "aspect_ratio", "focal_length", "xi", "alpha"}
+    # same numbers as the C-ABI call on the values the file carries (views in key order, ids in lexicographic order)
+    names = sorted(iof.view_key(f / 30.0) for f in range(40))
+    order = [int(round(float(n) * 30e-6)) for n in names]
+    o2, i2, u2 = [0], [], []
+    for f in order:
+        cs = sorted(range(off[f], off[f + 1]), key=lambda c: str(int(ids[c])))
+        i2 += [ids[c] for c in cs]; u2 += [uv[c] for c in cs]; o2.append(len(i2))
+    g = gpu_factory(); g.set_board_points(B)
+    r = g.calibrate_camera(model, W, H, np.array(o2, np.int32), np.array(i2, np.int32), np.array(u2), grid_size=0.001)
+    kk = r["intrinsics"]
+    got = np.array([cam["intrinsics"][n] for n in ("focal_length", "aspect_ratio", "principal_pt_x", "principal_pt_y", "xi", "alpha")])
+    assert np.allclose(got, [kk[0], kk[1], kk[3], kk[4], kk[5], kk[6]], rtol=1e-9, atol=1e-12)
+    assert abs(cam["final_reproj_error"] - r["summary"]["final_reproj_error"]) < 1e-9
+    ds = json.load(open(tmp_path / "cam.calibdata"))
+    assert len(ds["views"]) == 40 and len(ds["tracks"]) == B.shape[0]
+    # the written calibration is what the downstream tools read: board poses with it reproduce the calibrated poses
+    pose_json = str(tmp_path / "poses.json")
+    out = subprocess.run([POSE_CLI, "--input_corners=" + corners, "--camera_calibration_json=" + str(tmp_path / "cam.json"), "--output_pose_dataset=" + pose_json],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    pd = json.load(open(pose_json))
+    assert set(pd["views"]) == set(ds["views"])
+    dp = max(np.abs(np.array(pd["views"][n]["p_wc"]) - np.array(ds["views"][n]["p_wc"])).max() for n in pd["views"])
+    assert dp < 2e-3     # joint bundle adjustment vs per-view refinement on undistorted coordinates: same poses up to the noise

@@ -64,6 +64,50 @@ struct DevBuf {
   cudaError_t upload(const std::vector<T>& v) { cudaError_t e = alloc(v.size()); if (e != cudaSuccess || v.empty()) return e; return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice); }
 };
 
+// Host staging of the large measurement arrays (corners, IMU samples): page-locked blocks from a process-wide cache (the first
+// job pays cudaHostAlloc, later ones reuse), so that the uploads of BatchInitSpline are asynchronous DMA transfers that overlap the
+// host assembly.  Host-only handles (and a failed cudaHostAlloc) use ordinary memory; the copies then stage through the driver.
+struct PinnedCache {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  void* get(size_t bytes, size_t* cap) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= 2 * bytes + 4096) { void* q = it->second; *cap = it->first; free_blocks.erase(it); return q; }
+    }
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = bytes; return q;
+  }
+  void put(size_t bytes, void* q) { std::lock_guard<std::mutex> lk(mu); free_blocks.emplace(bytes, q); }
+  void trim() { std::lock_guard<std::mutex> lk(mu); for (auto& kv : free_blocks) cudaFreeHost(kv.second); free_blocks.clear(); }
+};
+PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
+
+template <class T>
+struct HostBuf {
+  T* p = nullptr; size_t n = 0, cap_bytes = 0; bool pinned = false;
+  HostBuf() = default; HostBuf(const HostBuf&) = delete; HostBuf& operator=(const HostBuf&) = delete;
+  ~HostBuf() { release(); }
+  void release() { if (p) { if (pinned) pinned_cache().put(cap_bytes, p); else free(p); } p = nullptr; n = 0; cap_bytes = 0; pinned = false; }
+  void resize(size_t count, bool want_pinned) {    // contents are NOT preserved
+    const size_t bytes = std::max<size_t>(256, (count * sizeof(T) + 255) / 256 * 256);
+    if (!(p && cap_bytes >= bytes && (pinned || !want_pinned))) {
+      release();
+      if (want_pinned) { size_t cap = 0; p = static_cast<T*>(pinned_cache().get(bytes, &cap)); if (p) { pinned = true; cap_bytes = cap; } }
+      if (!p) { p = static_cast<T*>(malloc(bytes)); cap_bytes = bytes; pinned = false; }
+    }
+    n = count;
+  }
+  void assign(const T* src, size_t count, bool want_pinned) { resize(count, want_pinned); if (count) memcpy(p, src, count * sizeof(T)); }
+  void clear() { n = 0; }
+  T* data() { return p; } const T* data() const { return p; }
+  size_t size() const { return n; } bool empty() const { return n == 0; }
+  T& operator[](size_t i) { return p[i]; } const T& operator[](size_t i) const { return p[i]; }
+  const T* begin() const { return p; } const T* end() const { return p + n; }
+};
+
 struct StateBufs {
   DevBuf<double4> so3, r3, ba, bg; DevBuf<double> glob;
   DeviceState view() const { DeviceState s; s.so3 = so3.p; s.r3 = r3.p; s.ba = ba.p; s.bg = bg.p; s.glob = glob.p; return s; }
@@ -80,8 +124,8 @@ struct icc_handle {
   // ---- raw inputs -------------------------------------------------------------------------------------------
   int model = -1, n_intr = 0, width = 0, height = 0; double intr[10] = {0};
   std::vector<double> points;
-  std::vector<double> frame_t; std::vector<int> corner_off, point_ids; std::vector<double> uv, q_wc, p_wc;
-  std::vector<double> imu_t, imu_acc, imu_gyr;
+  std::vector<double> frame_t; std::vector<int> corner_off; HostBuf<int> point_ids; HostBuf<double> uv; std::vector<double> q_wc, p_wc;
+  std::vector<double> imu_t; HostBuf<double> imu_acc, imu_gyr;
   int shard_rank = 0, shard_world = 1;
   icc_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
   // ---- assembled problem (host) -----------------------------------------------------------------------------
@@ -95,7 +139,7 @@ struct icc_handle {
   std::vector<double> used_uv; std::vector<int> used_pid;   // gathered corners -- only when the used frames are not one contiguous run
   bool used_contig = false; int used_c0 = 0, used_n = 0;    // ... otherwise corners [used_c0, used_c0 + used_n) of uv / point_ids are used in place
   bool imu_contig = false; int imu_src0 = 0;                // same for the accelerometer / gyroscope samples
-  std::vector<double> imu_used_t, imu_used_acc, imu_used_gyr; std::vector<int64_t> imu_used_st;
+  std::vector<double> imu_used_t, imu_used_acc, imu_used_gyr; HostBuf<int64_t> imu_used_st;
   std::vector<ImuCell> cells;
   int dropped_frames = 0, dropped_imu = 0;
   // ---- device ---------------------------------------------------------------------------------------------------
@@ -475,13 +519,17 @@ icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t*
   if (!h || nf <= 0 || !t || !off || !ids || !uv || !q || !p) return ICC_ERR_INVALID_ARGUMENT;
   const int nc = off[nf];
   for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
-  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->point_ids.assign(ids, ids + nc); h->uv.assign(uv, uv + 2 * (size_t)nc);
+  if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);   // an asynchronous upload may still be reading the staging buffers
+  const bool pin = h->device >= 0;
+  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->point_ids.assign(ids, (size_t)nc, pin); h->uv.assign(uv, 2 * (size_t)nc, pin);
   h->q_wc.assign(q, q + 4 * (size_t)nf); h->p_wc.assign(p, p + 3 * (size_t)nf);
   return ICC_OK;
 }
 icc_status icc_set_imu(icc_handle* h, int n, const double* t, const double* a, const double* g) {
   if (!h || n < 0 || (n > 0 && (!t || !a || !g))) return ICC_ERR_INVALID_ARGUMENT;
-  h->imu_t.assign(t, t + n); h->imu_acc.assign(a, a + 3 * (size_t)n); h->imu_gyr.assign(g, g + 3 * (size_t)n);
+  if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);
+  const bool pin = h->device >= 0;
+  h->imu_t.assign(t, t + n); h->imu_acc.assign(a, 3 * (size_t)n, pin); h->imu_gyr.assign(g, 3 * (size_t)n, pin);
   return ICC_OK;
 }
 icc_status icc_set_shard(icc_handle* h, int rank, int world) { if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, ICC_ERR_INVALID_ARGUMENT, "bad shard"); h->shard_rank = rank; h->shard_world = world; return ICC_OK; }
@@ -490,7 +538,9 @@ icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user) { i
 icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   if (!h || !ipp) return ICC_ERR_INVALID_ARGUMENT;
   if (h->model < 0 || h->frame_t.empty() || h->points.empty()) return fail(h, ICC_ERR_STATE, "camera, board points and frames must be set before batch_init_spline");
-  for (int id : h->point_ids) if (id < 0 || (size_t)id >= h->points.size() / 4) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner references an unknown board point");
+  { int lo = 0, hi = -1; const int* ids = h->point_ids.data(); const size_t nid = h->point_ids.size();
+    for (size_t i = 0; i < nid; ++i) { lo = std::min(lo, ids[i]); hi = std::max(hi, ids[i]); }
+    if (lo < 0 || (size_t)(hi + 1) > h->points.size() / 4) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner references an unknown board point"); }
   h->ip = *ipp;
   const int nf = (int)h->frame_t.size();
   // T_i_c, IMU intrinsics, line delay (imu_camera_calibrator.cc:30-47)
@@ -512,13 +562,18 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   // knot initialisation from the per-view pose priors (impl.h:278-339)
   const Pose Tic{q4(h->glob[0], h->glob[1], h->glob[2], h->glob[3]), v3(h->glob[4], h->glob[5], h->glob[6])};
   const Pose Tci = pose_inv(Tic);
-  std::map<double, int> by_time; for (int i = 0; i < nf; ++i) by_time[h->frame_t[i]] = i;
+  // the reference walks its views through a std::map keyed by timestamp (time order, a repeated timestamp keeps the LAST view);
+  // strictly increasing timestamps -- the usual case -- give that order without the tree
+  bool increasing = true; for (int i = 1; i < nf && increasing; ++i) increasing = h->frame_t[i] > h->frame_t[i - 1];
+  std::vector<int> view_order;
+  if (increasing) { view_order.resize(nf); for (int i = 0; i < nf; ++i) view_order[i] = i; }
+  else { std::map<double, int> by_time; for (int i = 0; i < nf; ++i) by_time[h->frame_t[i]] = i; for (const auto& kv : by_time) view_order.push_back(kv.second); }
   std::vector<double> t_vis, q_vis, p_vis;
-  for (const auto& kv : by_time) {
-    const int i = kv.second;
+  t_vis.reserve(view_order.size()); q_vis.reserve(4 * view_order.size()); p_vis.reserve(3 * view_order.size());
+  for (const int i : view_order) {
     const Pose Twc{qn(&h->q_wc[4 * i]), v3(h->p_wc[3 * i], h->p_wc[3 * i + 1], h->p_wc[3 * i + 2])};
     const Pose Twi = pose_mul(Twc, Tci);
-    t_vis.push_back(kv.first);
+    t_vis.push_back(h->frame_t[i]);
     q_vis.push_back(Twi.q.x); q_vis.push_back(Twi.q.y); q_vis.push_back(Twi.q.z); q_vis.push_back(Twi.q.w);
     p_vis.push_back(Twi.t.x); p_vis.push_back(Twi.t.y); p_vis.push_back(Twi.t.z);
   }
@@ -546,9 +601,9 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   for (int i = 0; i < nbg; ++i) for (int d = 0; d < 3; ++d) h->bg[3 * i + d] = ipp->gyr_bias[d];
 
   // ---- measurement wiring (imu_camera_calibrator.cc:87-120; Add*Measurement impl.h:341-613) ----------------------
-  struct Unit { double t; int kind, idx, nres; };
-  std::vector<Unit> units;
+  const bool pin = h->device >= 0;
   std::vector<FrameHost> all_frames(nf);
+  std::vector<char> frame_ok(nf);
   h->dropped_frames = h->dropped_imu = 0;
   for (int i = 0; i < nf; ++i) {
     FrameHost& f = all_frames[i]; f.t_s = h->frame_t[i]; f.c0 = h->corner_off[i]; f.c1 = h->corner_off[i + 1];
@@ -556,43 +611,98 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     int64_t s1 = 0, s2 = 0;
     const bool ok = calc_times(t_ns, h->start_ns, h->dt_r3_ns, nr3, SPLINE_N, f.u_r3, s1) && calc_times(t_ns, h->start_ns, h->dt_so3_ns, nso3, SPLINE_N, f.u_so3, s2);
     f.s_r3 = (int)s1; f.s_so3 = (int)s2;
-    if (ok) units.push_back({f.t_s, 0, i, 2 * (f.c1 - f.c0)}); else ++h->dropped_frames;
+    frame_ok[i] = ok; if (!ok) ++h->dropped_frames;
   }
   struct ImuHost { double t_s; int64_t st; int s_so3, s_r3, s_ba, s_bg; int src; };
-  std::vector<ImuHost> all_imu; all_imu.reserve(h->imu_t.size()); units.reserve(nf + h->imu_t.size());
   // CalcTimes' segment index s = st / dt of a time-sorted stream only ever steps forward: track it with comparisons and fall back
   // to the division when a sample is not where the previous one left off (unsorted input); the results are identical
-  struct SegTrack { int64_t dt, s = 0; bool init = false;
-    int64_t seg(int64_t st) { if (!init || st < s * dt || st >= (s + 64) * dt) { s = st / dt; init = true; } else while (st >= (s + 1) * dt) ++s; return s; } };
-  SegTrack tr_r3{h->dt_r3_ns}, tr_so3{h->dt_so3_ns}, tr_ba{h->dt_ba_ns}, tr_bg{h->dt_bg_ns};
-  for (size_t i = 0; i < h->imu_t.size(); ++i) {
-    const double t = h->imu_t[i] + ipp->time_offset_imu_to_cam_s;
-    if (t < h->t0_s || t >= h->tend_s) continue;
-    const int64_t t_ns = (int64_t)(t * S_TO_NS), st = t_ns - h->start_ns;
-    bool ok = st >= 0;
-    int64_t a = 0, b = 0, c = 0, d = 0;
-    if (ok) { a = tr_r3.seg(st); b = tr_so3.seg(st); c = tr_ba.seg(st); d = tr_bg.seg(st);
-              ok = size_t(a + SPLINE_N) <= (size_t)nr3 && size_t(b + SPLINE_N) <= (size_t)nso3 && size_t(c + BIAS_N) <= (size_t)nba && size_t(d + BIAS_N) <= (size_t)nbg; }
-    if (!ok) { ++h->dropped_imu; continue; }
-    all_imu.push_back({t, t_ns - h->start_ns, (int)b, (int)a, (int)c, (int)d, (int)i});
-    units.push_back({t, 1, (int)all_imu.size() - 1, 6});
+  struct SegTrack { int64_t dt, s = 0, lo = 0, hi = -1;   // [lo, hi) = time range of segment s; hi < lo until the first sample
+    int64_t seg(int64_t st) {
+      if (st >= lo && st < hi) return s;
+      if (hi > lo && st >= hi && st < hi + 63 * dt) { do { ++s; lo = hi; hi += dt; } while (st >= hi); return s; }
+      s = st / dt; lo = s * dt; hi = lo + dt; return s;
+    } };
+  const size_t n_imu_in = h->imu_t.size();
+  h->imu_used_t.clear(); h->imu_used_acc.clear(); h->imu_used_gyr.clear(); h->cells.clear();
+  h->imu_used_st.resize(n_imu_in, pin);
+  std::vector<ImuHost> all_imu;
+  // One pass over the IMU stream.  `direct` (one shard): the kept samples go straight into the problem arrays in arrival order,
+  // which IS the time order as long as the stream is sorted -- the pass gives up (returns false) at the first sample that is not.
+  // Otherwise they are collected for the general path below (time merge with the frames, residual-count sharding).
+  auto imu_pass = [&](bool direct) -> bool {
+    SegTrack tr_r3{h->dt_r3_ns}, tr_so3{h->dt_so3_ns}, tr_ba{h->dt_ba_ns}, tr_bg{h->dt_bg_ns};
+    h->dropped_imu = 0; h->imu_used_t.clear(); h->cells.clear(); all_imu.clear();
+    if (direct) h->imu_used_t.resize(n_imu_in); else all_imu.reserve(n_imu_in);
+    double* t_out = h->imu_used_t.data();
+    int64_t* st_out = h->imu_used_st.data();
+    double last_t = -1.7976931348623157e308; int prev_src = -1; bool contig = true; size_t k = 0;
+    const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s, t0 = h->t0_s, tend = h->tend_s;
+    for (size_t i = 0; i < n_imu_in; ++i) {
+      const double t = imu_t[i] + toff;
+      if (t < t0 || t >= tend) continue;
+      const int64_t t_ns = (int64_t)(t * S_TO_NS), st = t_ns - h->start_ns;
+      bool ok = st >= 0;
+      int64_t a = 0, b = 0, c = 0, d = 0;
+      if (ok) { a = tr_r3.seg(st); b = tr_so3.seg(st); c = tr_ba.seg(st); d = tr_bg.seg(st);
+                ok = size_t(a + SPLINE_N) <= (size_t)nr3 && size_t(b + SPLINE_N) <= (size_t)nso3 && size_t(c + BIAS_N) <= (size_t)nba && size_t(d + BIAS_N) <= (size_t)nbg; }
+      if (!ok) { ++h->dropped_imu; continue; }
+      if (!direct) { all_imu.push_back({t, st, (int)b, (int)a, (int)c, (int)d, (int)i}); continue; }
+      if (t < last_t) { h->imu_used_t.clear(); return false; }
+      last_t = t;
+      if (prev_src >= 0 && (int)i != prev_src + 1) contig = false;
+      if (prev_src < 0) h->imu_src0 = (int)i;
+      prev_src = (int)i;
+      t_out[k] = t; st_out[k] = st;
+      if (h->cells.empty() || h->cells.back().s_so3 != (int)b || h->cells.back().s_r3 != (int)a || h->cells.back().s_ba != (int)c || h->cells.back().s_bg != (int)d)
+        h->cells.push_back({(int)b, (int)a, (int)c, (int)d, (int)k, (int)k});
+      h->cells.back().i_end = (int)k + 1;
+      ++k;
+    }
+    if (direct) { h->imu_contig = k > 0 && contig; if (k == 0) h->imu_src0 = 0; h->imu_used_st.n = k; h->imu_used_t.resize(k); }
+    return true;
+  };
+  std::vector<int> frame_sel;
+  // (a stream with holes inside the kept range -- samples dropped in the middle -- takes the general path, which gathers the readings)
+  const bool direct = h->shard_world == 1 && imu_pass(true) && h->imu_contig;
+  if (direct) {
+    for (int i = 0; i < nf; ++i) if (frame_ok[i]) frame_sel.push_back(i);
+  } else {
+    imu_pass(false);
+    struct Unit { double t; int kind, idx, nres; };
+    std::vector<Unit> units; units.reserve(nf + all_imu.size());
+    for (int i = 0; i < nf; ++i) if (frame_ok[i]) units.push_back({all_frames[i].t_s, 0, i, 2 * (all_frames[i].c1 - all_frames[i].c0)});
+    const size_t nfu = units.size();
+    for (size_t i = 0; i < all_imu.size(); ++i) units.push_back({all_imu[i].t_s, 1, (int)i, 6});
+    {   // time order with frames before IMU samples on ties (== stable sort of [frames..., imu...]); both streams are normally
+        // already sorted, so merge in O(n) and only fall back to sorting when they are not
+      auto lt = [](const Unit& x, const Unit& y) { return x.t < y.t; };
+      if (!std::is_sorted(units.begin(), units.begin() + nfu, lt)) std::stable_sort(units.begin(), units.begin() + nfu, lt);
+      if (!std::is_sorted(units.begin() + nfu, units.end(), lt)) std::stable_sort(units.begin() + nfu, units.end(), lt);
+      std::vector<Unit> merged(units.size());
+      std::merge(units.begin(), units.begin() + nfu, units.begin() + nfu, units.end(), merged.begin(), lt);
+      units.swap(merged);
+    }
+    long total = 0; for (const auto& u : units) total += u.nres;
+    const long lo = total * h->shard_rank / h->shard_world, hi = total * (h->shard_rank + 1) / h->shard_world;
+    long run = 0;
+    std::vector<int> imu_sel;
+    for (const auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; (u.kind == 0 ? frame_sel : imu_sel).push_back(u.idx); }
+    std::sort(frame_sel.begin(), frame_sel.end());
+    h->imu_contig = !imu_sel.empty();
+    for (size_t k = 1; k < imu_sel.size() && h->imu_contig; ++k) h->imu_contig = all_imu[imu_sel[k]].src == all_imu[imu_sel[k - 1]].src + 1;
+    h->imu_src0 = imu_sel.empty() ? 0 : all_imu[imu_sel.front()].src;
+    h->imu_used_t.resize(imu_sel.size()); h->imu_used_st.n = imu_sel.size();
+    if (!h->imu_contig) { h->imu_used_acc.resize(3 * imu_sel.size()); h->imu_used_gyr.resize(3 * imu_sel.size()); }
+    for (size_t k = 0; k < imu_sel.size(); ++k) {
+      const ImuHost& m = all_imu[imu_sel[k]];
+      const int idx = (int)k;
+      h->imu_used_t[k] = m.t_s; h->imu_used_st[k] = m.st;
+      if (!h->imu_contig) { memcpy(&h->imu_used_acc[3 * k], &h->imu_acc[3 * (size_t)m.src], 3 * sizeof(double)); memcpy(&h->imu_used_gyr[3 * k], &h->imu_gyr[3 * (size_t)m.src], 3 * sizeof(double)); }
+      if (h->cells.empty() || h->cells.back().s_so3 != m.s_so3 || h->cells.back().s_r3 != m.s_r3 || h->cells.back().s_ba != m.s_ba || h->cells.back().s_bg != m.s_bg)
+        h->cells.push_back({m.s_so3, m.s_r3, m.s_ba, m.s_bg, idx, idx});
+      h->cells.back().i_end = idx + 1;
+    }
   }
-  {   // time order with frames before IMU samples on ties (== stable sort of [frames..., imu...]); both streams are normally
-      // already sorted, so merge in O(n) and only fall back to sorting when they are not
-    const size_t nfu = units.size() - all_imu.size();
-    auto lt = [](const Unit& x, const Unit& y) { return x.t < y.t; };
-    if (!std::is_sorted(units.begin(), units.begin() + nfu, lt)) std::stable_sort(units.begin(), units.begin() + nfu, lt);
-    if (!std::is_sorted(units.begin() + nfu, units.end(), lt)) std::stable_sort(units.begin() + nfu, units.end(), lt);
-    std::vector<Unit> merged(units.size());
-    std::merge(units.begin(), units.begin() + nfu, units.begin() + nfu, units.end(), merged.begin(), lt);
-    units.swap(merged);
-  }
-  long total = 0; for (const auto& u : units) total += u.nres;
-  const long lo = total * h->shard_rank / h->shard_world, hi = total * (h->shard_rank + 1) / h->shard_world;
-  long run = 0;
-  std::vector<int> frame_sel, imu_sel;
-  for (const auto& u : units) { const bool mine = run >= lo && run < hi; run += u.nres; if (!mine) continue; (u.kind == 0 ? frame_sel : imu_sel).push_back(u.idx); }
-  std::sort(frame_sel.begin(), frame_sel.end());
   h->frames.clear(); h->used_uv.clear(); h->used_pid.clear();
   h->frames.reserve(frame_sel.size());
   bool consecutive = !frame_sel.empty();
@@ -612,25 +722,11 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     }
     h->used_n = (int)h->used_pid.size();
   }
-  h->imu_used_t.clear(); h->imu_used_acc.clear(); h->imu_used_gyr.clear(); h->imu_used_st.clear(); h->cells.clear();
-  h->imu_contig = !imu_sel.empty();
-  for (size_t k = 1; k < imu_sel.size() && h->imu_contig; ++k) h->imu_contig = all_imu[imu_sel[k]].src == all_imu[imu_sel[k - 1]].src + 1;
-  h->imu_src0 = imu_sel.empty() ? 0 : all_imu[imu_sel.front()].src;
-  h->imu_used_t.resize(imu_sel.size()); h->imu_used_st.resize(imu_sel.size());
-  if (!h->imu_contig) { h->imu_used_acc.resize(3 * imu_sel.size()); h->imu_used_gyr.resize(3 * imu_sel.size()); }
-  for (size_t k = 0; k < imu_sel.size(); ++k) {
-    const ImuHost& m = all_imu[imu_sel[k]];
-    const int idx = (int)k;
-    h->imu_used_t[k] = m.t_s; h->imu_used_st[k] = m.st;
-    if (!h->imu_contig) { memcpy(&h->imu_used_acc[3 * k], &h->imu_acc[3 * (size_t)m.src], 3 * sizeof(double)); memcpy(&h->imu_used_gyr[3 * k], &h->imu_gyr[3 * (size_t)m.src], 3 * sizeof(double)); }
-    if (h->cells.empty() || h->cells.back().s_so3 != m.s_so3 || h->cells.back().s_r3 != m.s_r3 || h->cells.back().s_ba != m.s_ba || h->cells.back().s_bg != m.s_bg)
-      h->cells.push_back({m.s_so3, m.s_r3, m.s_ba, m.s_bg, idx, idx});
-    h->cells.back().i_end = idx + 1;
-  }
   // gravity initialisation (imu_camera_calibrator.cc:130-161) incl. the integer-second truncation of the accelerometer time
+  auto view_of_time = [&](double t) { const size_t k = std::lower_bound(t_vis.begin(), t_vis.end(), t) - t_vis.begin(); return view_order[std::min(k, view_order.size() - 1)]; };
   bool ginit = false; double g0[3] = {0.0, 0.0, 9.81};   // GRAVITY_MAGN (spline_trajectory_estimator.h:29) when never initialised
   for (size_t j = 0; j < cam_ts.size() && !ginit; ++j) {
-    const int vi = by_time[cam_ts[j]];
+    const int vi = view_of_time(cam_ts[j]);
     const Pose Twc{qn(&h->q_wc[4 * vi]), v3(h->p_wc[3 * vi], h->p_wc[3 * vi + 1], h->p_wc[3 * vi + 2])};
     const Pose Tai = pose_mul(Twc, Tci);
     for (size_t i = 0; i < h->imu_t.size(); ++i) {
@@ -669,8 +765,9 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     if (P.n_corners > 0) {
       const double* uv_src = h->used_contig ? h->uv.data() + 2 * (size_t)h->used_c0 : h->used_uv.data();
       const int* pid_src = h->used_contig ? h->point_ids.data() + h->used_c0 : h->used_pid.data();
-      CU(cudaMemcpy(h->d_uv.p, uv_src, (size_t)P.n_corners * sizeof(double2), cudaMemcpyHostToDevice));
-      CU(cudaMemcpy(h->d_pid.p, pid_src, (size_t)P.n_corners * sizeof(int), cudaMemcpyHostToDevice));
+      // page-locked sources (HostBuf): the DMA transfers run behind the rest of this function; kernels follow on the same stream
+      CU(cudaMemcpyAsync(h->d_uv.p, uv_src, (size_t)P.n_corners * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_pid.p, pid_src, (size_t)P.n_corners * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
     P.uv = h->d_uv.p; P.pid = h->d_pid.p;
     // work lists: one warp per item; items sized so that the grid fills the GPU but every item amortises its tile flush
@@ -685,13 +782,14 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
     CU(h->d_iwork.upload(iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
     CU(h->d_cells.upload(h->cells)); P.cells = h->d_cells.p;
-    CU(h->d_imu_t.upload(h->imu_used_st));
+    CU(h->d_imu_t.alloc(h->imu_used_st.size()));
+    if (!h->imu_used_st.empty()) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->imu_used_st.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
     if (P.n_imu > 0) {
       const double* a_src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data();
       const double* g_src = h->imu_contig ? h->imu_gyr.data() + 3 * (size_t)h->imu_src0 : h->imu_used_gyr.data();
-      CU(cudaMemcpy(h->d_imu_acc.p, a_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice));
-      CU(cudaMemcpy(h->d_imu_gyr.p, g_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice));
+      CU(cudaMemcpyAsync(h->d_imu_acc.p, a_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_imu_gyr.p, g_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
   }
@@ -1382,6 +1480,6 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, 
   return finish((int)active.size() >= o.min_num_views);                                          // :202-205
 }
 
-void icc_trim_device_cache(void) { block_cache().trim(); }
+void icc_trim_device_cache(void) { block_cache().trim(); pinned_cache().trim(); }
 
 }  // extern "C"

@@ -100,3 +100,25 @@ def test_invalid_arguments_are_reported():
         h.batch_init_spline(np.array([0, 0, 0, 1, 0, 0, 0.0]), 0.05, 0.05, 1, 1, 0, 1e-5)
     with pytest.raises(capi.IccError, match="INVALID_ARGUMENT"):
         h.set_shard(3, 2)
+
+
+@pytest.mark.parametrize("case", ["shuffled_imu", "imu_hole", "duplicate_view_time"])
+def test_host_assembly_general_paths_match_oracle(oracle_factory, case):
+    """The one-shard fast path of BatchInitSpline assumes a time-sorted, gap-free IMU stream and increasing view timestamps; anything
+    else must fall back to the general path and still agree with the oracle."""
+    ds = dict(syn.make_dataset(syn.tiny_config()))
+    if case == "shuffled_imu":
+        perm = np.random.default_rng(0).permutation(len(ds["imu_t"]))
+        ds["imu_t"], ds["accel"], ds["gyro"] = ds["imu_t"][perm], ds["accel"][perm], ds["gyro"][perm]
+    elif case == "imu_hole":
+        t = ds["imu_t"].copy(); t[50] = 1e6; ds["imu_t"] = t            # one sample far outside the window, mid-stream
+    else:
+        t = ds["frame_t"].copy(); t[5] = t[4]; ds["frame_t"] = t
+    o = oracle_factory(); capi.load_dataset(o, ds, known_gravity=False)
+    h = capi.CApi(calibrator.load_library(), "icc_", -1); capi.load_dataset(h, ds, known_gravity=False)
+    assert o.num_residuals() == h.num_residuals() and o.num_knots() == h.num_knots()
+    for a, b in zip(o.imu_used(), h.imu_used()):
+        assert np.array_equal(a, b)
+    for a, b in zip(o.get_knots(), h.get_knots()):
+        assert np.allclose(a, b, rtol=0, atol=1e-15)
+    assert np.allclose(o.get_gravity(), h.get_gravity(), rtol=0, atol=1e-14)

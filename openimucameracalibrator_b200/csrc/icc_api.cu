@@ -100,7 +100,7 @@ struct HostBuf {
     }
     n = count;
   }
-  void assign(const T* src, size_t count, bool want_pinned) { resize(count, want_pinned); if (count) memcpy(p, src, count * sizeof(T)); }
+  void assign(const T* src, size_t count, bool want_pinned) { resize(count, want_pinned); if (count) memcpy(p, src, count * sizeof(T)); }   // (splitting this copy over threads was measured: the later DMA / reads get slower by more than the copy gains)
   void clear() { n = 0; }
   T* data() { return p; } const T* data() const { return p; }
   size_t size() const { return n; } bool empty() const { return n == 0; }

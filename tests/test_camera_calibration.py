@@ -148,7 +148,7 @@ def test_gpu_calibration_matches_oracle(oracle_factory, gpu_factory, model, k):
     assert (np.abs(rg["intrinsics"] - ro["intrinsics"])[:n] / scale[:n]).max() < 1e-6
     assert _qdiff(rg["q_wc"], ro["q_wc"]).max() < 1e-7 and np.abs(rg["p_wc"] - ro["p_wc"]).max() < 1e-7
     assert np.abs(rg["view_error_px"] - ro["view_error_px"]).max() < 1e-6
-    assert abs(sg["final_cost"][2] - so["final_cost"][2]) < 1e-9 * so["final_cost"][2]
+    assert abs(sg["final_cost"][2] - so["final_cost"][2]) < 1e-7 * so["final_cost"][2]
     if model != cm.PINHOLE_RADIAL_TANGENTIAL:   # 0.2 px noise on 36 views; focal length and xi of the double sphere trade off
         assert abs(rg["intrinsics"][0] - k[0]) < (0.03 if model == cm.DOUBLE_SPHERE else 0.005) * k[0]
 

@@ -21,6 +21,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace icc;
@@ -1439,13 +1440,27 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, 
   }
   S.focal_length_init = f0;
   // ---- grid filter in file order (:313-325): a view is taken iff no accepted camera position lies within grid_size ---------------
-  {
+  // (the reference scans all accepted positions; a hash grid with cells of grid_size visits only the 27 cells that can hold one
+  // -- same decisions, linear time)
+  if (o.grid_size > 0.0) {
     std::vector<int> sel;
+    std::unordered_map<uint64_t, std::vector<int>> cells;
+    const double inv = 1.0 / o.grid_size;
+    bool hashable = true;
+    for (int v : active) for (int d = 0; d < 3; ++d) if (!(std::fabs(p0[3 * v + d] * inv) < 1e6)) hashable = false;   // 21 bits per axis
+    auto key = [](int64_t x, int64_t y, int64_t z) { return (uint64_t)((x + (1 << 20)) & 0x1fffff) << 42 | (uint64_t)((y + (1 << 20)) & 0x1fffff) << 21 | (uint64_t)((z + (1 << 20)) & 0x1fffff); };
+    auto close_to = [&](int v, int a) { const double dx = p0[3 * v] - p0[3 * a], dy = p0[3 * v + 1] - p0[3 * a + 1], dz = p0[3 * v + 2] - p0[3 * a + 2]; return std::sqrt(dx * dx + dy * dy + dz * dz) < o.grid_size; };
     for (int v : active) {
       bool take = true;
-      for (int a : sel) {
-        const double dx = p0[3 * v] - p0[3 * a], dy = p0[3 * v + 1] - p0[3 * a + 1], dz = p0[3 * v + 2] - p0[3 * a + 2];
-        if (std::sqrt(dx * dx + dy * dy + dz * dz) < o.grid_size) { take = false; break; }
+      if (hashable) {
+        const int64_t cx = (int64_t)std::floor(p0[3 * v] * inv), cy = (int64_t)std::floor(p0[3 * v + 1] * inv), cz = (int64_t)std::floor(p0[3 * v + 2] * inv);
+        for (int64_t x = cx - 1; x <= cx + 1 && take; ++x) for (int64_t y = cy - 1; y <= cy + 1 && take; ++y) for (int64_t z = cz - 1; z <= cz + 1 && take; ++z) {
+          auto it = cells.find(key(x, y, z));
+          if (it != cells.end()) for (int a : it->second) if (close_to(v, a)) { take = false; break; }
+        }
+        if (take) cells[key(cx, cy, cz)].push_back(v);
+      } else {
+        for (int a : sel) if (close_to(v, a)) { take = false; break; }
       }
       if (take) sel.push_back(v);
     }

@@ -195,7 +195,8 @@ void* icc_get_stream(icc_handle* h);
  * :54-66; squared normalised reprojection error threshold 0.004 * image_height / image_diagonal, :100-101; >= 6 inliers, :65),
  * then refined on the inliers by theia::BundleAdjustView with a Huber(1.345) loss (:44-48, :86-87); views with fewer than
  * `min_points` corners (pose_estimator.h:72, default 8) or a mean reprojection error above `max_reproj_error` (:181) are dropped.
- * Here: camera + board points must have been set (icc_set_camera / icc_set_board_points; the board must be planar, z = const);
+ * Here: camera + board points must have been set (icc_set_camera / icc_set_board_points; the board must be planar up to a few per cent of its size -- the
+ * homography only starts the refinement, which uses the real 3-D points);
  * one warp per view computes a normalised homography initialisation and the Levenberg-Marquardt refinement on the same cost,
  * so that the converged pose is the reference's BundleAdjustView optimum (RANSAC's random minimal samples are not reproduced:
  * the inlier set is taken with the same threshold around the refined pose).
@@ -204,6 +205,23 @@ void* icc_get_stream(icc_handle* h);
 icc_status icc_estimate_board_poses(icc_handle* h, int n_frames, const int32_t* corner_offsets /* n_frames+1 */, const int32_t* point_ids,
                                     const double* uv, double max_reproj_error, int min_points,
                                     double* q_wc_xyzw, double* p_wc, double* mean_reproj_error, int32_t* valid);
+/* PoseEstimator::FilterBadPoses (src/core/pose_estimator.cc:238-261), the last step of estimate_camera_poses_from_checkerboard
+ * (app :66-67): views whose camera height p_wc.z differs from the median height of the valid views by more than |median| are dropped
+ * (poses far away or on the wrong side of the board).  Host logic only: valid[] is updated in place; h may be NULL. */
+icc_status icc_filter_bad_poses(icc_handle* h, int n_views, const double* p_wc, int32_t* valid);
+/* --optimize_board_points of the pose app (app :61-65): PoseEstimator::OptimizeBoardPoints (pose_estimator.cc:193-224) =
+ * theia::BundleAdjustTracks over the board points seen in more than `min_observations` (<= 0 selects min_num_obs_for_optim_ = 30,
+ * pose_estimator.h:78) inlier observations, every camera constant, residual = normalised pinhole reprojection error of the
+ * undistorted corners, Huber(1.345); then PoseEstimator::OptimizeAllPoses (:226-236) = BundleAdjustView of every valid view on the
+ * new points.  q_wc / p_wc / valid are in-out (as returned by icc_estimate_board_poses); the handle's board points are replaced
+ * (also returned in board_xyzw_out, w = 1 for optimised points).  With cameras fixed every point is an independent 3-parameter
+ * problem: one warp per point on the GPU.  The empirical covariances the reference prints (:212-223) are not computed. */
+icc_status icc_optimize_board_points(icc_handle* h, int n_frames, const int32_t* corner_offsets, const int32_t* point_ids, const double* uv,
+                                     double max_reproj_error, int min_points, int min_observations,
+                                     double* q_wc_xyzw, double* p_wc, double* mean_reproj_error /* nullable */, int32_t* valid,
+                                     double* board_xyzw_out /* nullable, 4 per board point */, int32_t* n_points_optimized /* nullable */);
+/* current board points of the handle (icc_set_board_points, or refined by icc_optimize_board_points / icc_calibrate_camera) */
+icc_status icc_get_board_points(const icc_handle* h, double* xyzw, int n);
 /* theia::Camera::PixelToNormalizedCoordinates / z for `n` pixels with the handle's camera: xy_out[2n], ok[n] (nullable). */
 icc_status icc_pixels_to_normalized(icc_handle* h, int n, const double* uv, double* xy_out, int32_t* ok);
 
@@ -253,7 +271,7 @@ icc_status icc_spline_error_weighting(icc_handle* h, int n, const double* times_
  * point at the image centre), poses = homography decomposition + Huber pose refinement under that pinhole camera; for the
  * non-pinhole models focal length, a division-model distortion and the poses are then refined jointly (the quantities
  * utils::initialize_radial_undistortion_camera hands the reference, :283-306) before the target model takes over.
- * `--optimize_board_points` (:207-216) is not implemented.  Needs icc_set_board_points (planar board for the internal initialiser).
+ * Needs icc_set_board_points (planar board for the internal initialiser).
  * Outputs (caller-owned): intrinsics[10] in Theia's order for `model`; per view q_wc / p_wc (as icc_set_frames consumes them),
  * the mean reprojection error [px] (GetReprojErrorOfView) and used[v] = 1 for the views that survive to the end.
  * summary->success = 0 (status still ICC_OK) when fewer than min_num_views views remain, like RunCalibration returning false. */
@@ -267,6 +285,9 @@ typedef struct icc_camcal_options {
   double max_view_error_final_px;    /* <= 0 selects 2.0 (:200) */
   int32_t min_num_views;             /* camera_calibrator.h:84; <= 0 selects 10 */
   int32_t max_num_iterations;        /* theia::BundleAdjustmentOptions (external) default 100 per stage; <= 0 selects it */
+  int32_t optimize_board_points;     /* --optimize_board_points (camera_calibrator.cc:207-216): BundleAdjustTracks on the board points with
+                                        constant cameras, then the full BundleAdjustViews again; read the points with icc_get_board_points */
+  int32_t reserved;
 } icc_camcal_options;
 typedef struct icc_camcal_summary {
   int32_t success;
@@ -277,6 +298,8 @@ typedef struct icc_camcal_summary {
   int32_t termination[3];            /* icc_summary.termination codes per stage */
   int32_t gpu_launches;
   int32_t init_iterations;           /* LM iterations of the internal initialiser's joint refinement (0 when poses / focal length are given) */
+  int32_t n_points_optimized;        /* board points refined by optimize_board_points */
+  int32_t reserved;
   double focal_length_init;
   double initial_cost;               /* cost at the start of stage 1 */
   double final_cost[3];              /* cost at the end of each stage */

@@ -54,12 +54,12 @@ class CamCalOptions(C.Structure):
     """icc_camcal_options (include/icc_b200.h): zero / negative fields select the reference's defaults."""
     _fields_ = [("grid_size", C.c_double), ("function_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
                 ("huber_width", C.c_double), ("max_view_error_stage1_px", C.c_double), ("max_view_error_final_px", C.c_double),
-                ("min_num_views", C.c_int32), ("max_num_iterations", C.c_int32)]
+                ("min_num_views", C.c_int32), ("max_num_iterations", C.c_int32), ("optimize_board_points", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CamCalSummary(C.Structure):
     _fields_ = [("success", C.c_int32), ("n_views_initialized", C.c_int32), ("n_views_selected", C.c_int32), ("n_views_used", C.c_int32),
-                ("iterations", C.c_int32 * 3), ("termination", C.c_int32 * 3), ("gpu_launches", C.c_int32), ("init_iterations", C.c_int32),
+                ("iterations", C.c_int32 * 3), ("termination", C.c_int32 * 3), ("gpu_launches", C.c_int32), ("init_iterations", C.c_int32), ("n_points_optimized", C.c_int32), ("reserved", C.c_int32),
                 ("focal_length_init", C.c_double), ("initial_cost", C.c_double), ("final_cost", C.c_double * 3), ("final_reproj_error", C.c_double),
                 ("seconds_total", C.c_double)]
 
@@ -139,6 +139,7 @@ class CApi:
 
     def set_board_points(self, xyzw):
         p = _f64(xyzw).reshape(-1, 4)
+        self._n_board = p.shape[0]
         self._call("set_board_points", [C.c_int, c_double_p], p.shape[0], _dp(p))
 
     def set_frames(self, t_s, corner_offsets, point_ids, uv, q_wc, p_wc):
@@ -164,6 +165,31 @@ class CApi:
                    n, off.ctypes.data_as(c_int32_p), ids.ctypes.data_as(c_int32_p), _dp(uv), float(max_reproj_error), int(min_points),
                    _dp(q), _dp(p), _dp(e), v.ctypes.data_as(c_int32_p))
         return q, p, e, v
+
+    def filter_bad_poses(self, p_wc, valid):
+        """PoseEstimator::FilterBadPoses (src/core/pose_estimator.cc:238-261): -> valid with the outlying camera heights cleared."""
+        p = _f64(p_wc).reshape(-1, 3); v = np.array(valid, dtype=np.int32)
+        self._call("filter_bad_poses", [C.c_int, c_double_p, c_int32_p], p.shape[0], _dp(p), v.ctypes.data_as(c_int32_p))
+        return v
+
+    def optimize_board_points(self, corner_offsets, point_ids, uv, q_wc, p_wc, valid, max_reproj_error=0.0, min_points=0, min_observations=0):
+        """PoseEstimator::OptimizeBoardPoints + OptimizeAllPoses (pose_estimator.cc:193-236)
+        -> (q_wc, p_wc, mean error, valid, board_xyzw, number of optimised points); the handle's board points are replaced."""
+        off = np.ascontiguousarray(corner_offsets, dtype=np.int32); ids = np.ascontiguousarray(point_ids, dtype=np.int32); uv = _f64(uv)
+        n = off.size - 1
+        q = np.array(q_wc, dtype=np.float64).reshape(n, 4).copy(); p = np.array(p_wc, dtype=np.float64).reshape(n, 3).copy()
+        v = np.array(valid, dtype=np.int32).copy(); e = np.zeros(n); nopt = C.c_int32()
+        board = np.zeros((self.num_board_points(), 4))
+        self._call("optimize_board_points", [C.c_int, c_int32_p, c_int32_p, c_double_p, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p, c_double_p, C.POINTER(C.c_int32)],
+                   n, off.ctypes.data_as(c_int32_p), ids.ctypes.data_as(c_int32_p), _dp(uv), float(max_reproj_error), int(min_points), int(min_observations),
+                   _dp(q), _dp(p), _dp(e), v.ctypes.data_as(c_int32_p), _dp(board), C.byref(nopt))
+        return q, p, e, v, board, nopt.value
+
+    def num_board_points(self):
+        return getattr(self, "_n_board", 0)
+
+    def get_board_points(self):
+        b = np.zeros((self.num_board_points(), 4)); self._call("get_board_points", [c_double_p, C.c_int], _dp(b), b.shape[0]); return b
 
     def pixels_to_normalized(self, uv):
         """theia::Camera::PixelToNormalizedCoordinates / z for an (n, 2) pixel array -> (xy[n,2], ok[n])."""

@@ -126,7 +126,7 @@ class CameraCalibrator:
         if camera_model not in cm.MODEL_IDS:
             raise IccError(f"unknown camera model {camera_model!r}")
         self.camera_model, self.model = camera_model, cm.MODEL_IDS[camera_model]
-        self.optimize_board_pts = bool(optimize_board_pts)        # accepted, not implemented (camera_calibrator.cc:207-216)
+        self.optimize_board_pts = bool(optimize_board_pts)        # camera_calibrator.cc:207-216; refined points: self.api.get_board_points()
         self.api = CApi(load_library(), "icc_", int(device))
         self.grid_size, self.verbose = 0.04, False
         self._views, self._obs = [], {}
@@ -170,7 +170,8 @@ class CameraCalibrator:
         last = self._views[-1]                                     # the shared intrinsics keep the values of the last AddView (:101-113)
         W, H = self._image_size
         self.result = self.api.calibrate_camera(self.model, W, H, off, ids, np.array(uv).reshape(-1, 2), q_wc_init=np.array([v["q_wc"] for v in self._views]),
-                                                p_wc_init=np.array([v["p_wc"] for v in self._views]), focal_length_init=last["f"], distortion_init=last["k"], grid_size=0.0)
+                                                p_wc_init=np.array([v["p_wc"] for v in self._views]), focal_length_init=last["f"], distortion_init=last["k"], grid_size=0.0,
+                                                optimize_board_points=int(self.optimize_board_pts))
         return bool(self.result["summary"]["success"])
 
     def CalibrateCameraFromJson(self, scene_json: dict, output_path: str = "") -> bool:
@@ -191,7 +192,8 @@ class CameraCalibrator:
             for pid in sorted(ip):
                 ids.append(int(pid)); uv.append(ip[pid])
             off.append(len(ids)); self._timestamps_s.append(float(key) * 1e-6)
-        self.result = self.api.calibrate_camera(self.model, W, H, off, ids, np.array(uv, dtype=np.float64).reshape(-1, 2), grid_size=self.grid_size)
+        self.result = self.api.calibrate_camera(self.model, W, H, off, ids, np.array(uv, dtype=np.float64).reshape(-1, 2), grid_size=self.grid_size,
+                                                optimize_board_points=int(self.optimize_board_pts))
         s = self.result["summary"]
         if not s["success"]:
             return False

@@ -8,8 +8,9 @@
 //
 // Deliberate differences: the .calibdata file is the JSON pose dataset this repository's tools exchange ({"views": {"<name>":
 // {"q_wc": [w,x,y,z], "p_wc": [...], "timestamp_s": t, "mean_reproj_error": e}}, "tracks": {...}}), not Theia's cereal binary
-// (unreadable without Theia); the *_ransac_poses.ply / *_final_poses.ply point clouds are not written; --optimize_board_points is
-// accepted and reported as not implemented.  Extra flag: --device (CUDA ordinal, default 0).
+// (unreadable without Theia); the *_ransac_poses.ply / *_final_poses.ply point clouds are not written.  --optimize_board_points
+// (camera_calibrator.cc:207-216) refines the board points on the GPU and writes them as the dataset's tracks.
+// Extra flag: --device (CUDA ordinal, default 0).
 #include "../../include/icc_b200.h"
 #include "icc_cli_common.hpp"
 
@@ -55,16 +56,18 @@ int main(int argc, char** argv) {
     icc_status st = icc_create(&h, (int)F.num["device"]);
     if (st != ICC_OK) { std::cerr << "icc_create failed (" << st << "): " << icc_last_error(h) << std::endl; return 2; }
     std::vector<double> q(4 * (size_t)nv), p(3 * (size_t)nv), err(nv), intr(10, 0.0); std::vector<int32_t> used(nv);
-    icc_camcal_options opt{}; opt.grid_size = F.num["grid_size"];
+    icc_camcal_options opt{}; opt.grid_size = F.num["grid_size"]; opt.optimize_board_points = F.boolean["optimize_board_points"] ? 1 : 0;
     icc_camcal_summary S{};
     st = icc_set_board_points(h, np, board.data());
     if (st == ICC_OK) st = icc_calibrate_camera(h, model, width, height, nv, sv.off.data(), sv.ids.data(), sv.uv.data(), nullptr, nullptr, nullptr, 0.0, 0.0, &opt,
                                                 intr.data(), q.data(), p.data(), err.data(), used.data(), &S);
     if (st != ICC_OK) { std::cerr << "camera calibration failed (" << st << "): " << icc_last_error(h) << std::endl; return 2; }
+    std::vector<double> board_out(board);
+    if (opt.optimize_board_points) icc_get_board_points(h, board_out.data(), np);
     icc_destroy(h);
     std::cout << "Using " << S.n_views_selected << " views for camera calibration.\n";
     if (F.boolean["verbose"]) for (int i = 0; i < nv; ++i) if (used[i]) std::cout << "View: " << icccli::pose_view_name(sv.timestamp_us[i]) << " RMSE reprojection error: " << err[i] << "\n";
-    if (F.boolean["optimize_board_points"]) std::cout << "--optimize_board_points: board point refinement is not implemented; the board is kept as given\n";
+    if (opt.optimize_board_points && S.success) std::cout << "Optimized " << S.n_points_optimized << " board points.\n";
     if (!S.success) { std::cerr << "Not enough views for proper calibration!\nCalibration failed.\n"; return 3; }
     std::cout << "Final camera calibration reprojection error: " << S.final_reproj_error << " from " << S.n_views_used << " view." << std::endl;
     const bool noskew = model == ICC_CAM_FOV || model == ICC_CAM_DIVISION_UNDISTORTION;
@@ -99,7 +102,7 @@ int main(int argc, char** argv) {
         v["timestamp_s"] = Value(sv.timestamp_us[i] * 1e-6); v["mean_reproj_error"] = Value(err[i]);
         ds["views"][icccli::pose_view_name(sv.timestamp_us[i])] = v;
       }
-      for (int i = 0; i < np; ++i) { Value t = Value::array(); for (int d = 0; d < 4; ++d) t.push_back(Value(board[4 * i + d])); ds["tracks"][std::to_string(i)] = t; }
+      for (int i = 0; i < np; ++i) { Value t = Value::array(); for (int d = 0; d < 4; ++d) t.push_back(Value(board_out[4 * i + d])); ds["tracks"][std::to_string(i)] = t; }
       std::ofstream g(out + ".calibdata");
       if (!g.is_open()) { std::cerr << "could not write " << out << ".calibdata" << std::endl; return 1; }
       g << iccjson::dump(ds, 1) << std::endl;

@@ -126,6 +126,7 @@ int main(int argc, char** argv) {
       icc_status st = icc_set_camera(hp, model, intr.data(), (int)intr.size(), width, height);
       if (st == ICC_OK) st = icc_set_board_points(hp, max_id + 1, board.data());
       if (st == ICC_OK) st = icc_estimate_board_poses(hp, nv, sv.off.data(), sv.ids.data(), sv.uv.data(), 0.0, 0, q_all.data(), p_all.data(), err.data(), valid.data());
+      if (st == ICC_OK) st = icc_filter_bad_poses(hp, nv, p_all.data(), valid.data());   // the pose app's last step (PoseEstimator::FilterBadPoses)
       if (st != ICC_OK) { std::cerr << "board pose estimation failed (" << st << "): " << icc_last_error(hp) << std::endl; return 2; }
       icc_destroy(hp);
       int kept = 0;

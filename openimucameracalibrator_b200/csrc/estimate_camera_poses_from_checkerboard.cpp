@@ -6,8 +6,9 @@
 // One deliberate difference: --output_pose_dataset is written as the JSON pose dataset that this repository's
 // continuous_time_imu_to_camera_calibration reads ({"views": {"<name>": {"q_wc": [w,x,y,z], "p_wc": [x,y,z], "timestamp_s": t,
 // "mean_reproj_error": e}}, "tracks": {"<id>": [x,y,z,w]}}), not as Theia's cereal-binary Reconstruction (unreadable without
-// Theia).  --optimize_board_points (the reference's optional joint refinement of the board points, app :61-65) is accepted and
-// reported as not implemented.  Extra flag: --device (CUDA ordinal, default 0).
+// Theia).  --optimize_board_points (app :61-65) runs icc_optimize_board_points (PoseEstimator::OptimizeBoardPoints + OptimizeAllPoses)
+// and writes the refined board points as the dataset's tracks; PoseEstimator::FilterBadPoses (app :66-67) is applied like in the
+// reference.  Extra flag: --device (CUDA ordinal, default 0).
 #include "../../include/icc_b200.h"
 #include "icc_cli_common.hpp"
 
@@ -43,8 +44,16 @@ int main(int argc, char** argv) {
     if (st == ICC_OK) st = icc_set_board_points(h, np, board.data());
     if (st == ICC_OK) st = icc_estimate_board_poses(h, nv, sv.off.data(), sv.ids.data(), sv.uv.data(), 0.0, 0, q.data(), p.data(), err.data(), valid.data());
     if (st != ICC_OK) { std::cerr << "board pose estimation failed (" << st << "): " << icc_last_error(h) << std::endl; return 2; }
+    std::vector<double> board_out(board);
+    if (F.boolean["optimize_board_points"]) {                                  // app :61-65
+      int32_t n_opt = 0;
+      st = icc_optimize_board_points(h, nv, sv.off.data(), sv.ids.data(), sv.uv.data(), 0.0, 0, 0, q.data(), p.data(), err.data(), valid.data(), board_out.data(), &n_opt);
+      if (st != ICC_OK) { std::cerr << "board point optimisation failed (" << st << "): " << icc_last_error(h) << std::endl; return 2; }
+      std::cout << "Optimized " << n_opt << " board points (observed in more than 30 views) and all view poses.\n";
+    }
+    st = icc_filter_bad_poses(h, nv, p.data(), valid.data());                  // app :66-67
+    if (st != ICC_OK) { std::cerr << "pose filter failed (" << st << ")" << std::endl; return 2; }
     icc_destroy(h);
-    if (F.boolean["optimize_board_points"]) std::cout << "--optimize_board_points: joint board point refinement is not implemented; poses are written as estimated\n";
     Value out = Value::object(); out["views"] = Value::object(); out["tracks"] = Value::object();
     int kept = 0; double total = 0.0;
     for (int i = 0; i < nv; ++i) {
@@ -56,7 +65,7 @@ int main(int argc, char** argv) {
       out["views"][icccli::pose_view_name(sv.timestamp_us[i])] = v;
       ++kept; total += err[i];
     }
-    for (int i = 0; i < np; ++i) { Value t = Value::array(); for (int d = 0; d < 4; ++d) t.push_back(Value(board[4 * i + d])); out["tracks"][std::to_string(i)] = t; }
+    for (int i = 0; i < np; ++i) { Value t = Value::array(); for (int d = 0; d < 4; ++d) t.push_back(Value(board_out[4 * i + d])); out["tracks"][std::to_string(i)] = t; }
     std::cout << "Estimated " << kept << " of " << nv << " view poses, mean normalised reprojection error " << (kept ? total / kept : 0.0) << "\n";
     if (!F.str["output_pose_dataset"].empty()) {
       std::ofstream f(F.str["output_pose_dataset"]);

@@ -183,6 +183,17 @@ bool calc_times(int64_t sensor_ns, int64_t start_ns, int64_t dt_ns, size_t nr_kn
   return true;
 }
 
+// CSR by board point of the corners selected by `take(c)`: pt_off[np + 1], pt_obs[...] (counting sort, stable in corner order)
+template <class F>
+void build_point_adjacency(int np, int nc, const int32_t* ids, F take, std::vector<int>& pt_off, std::vector<int>& pt_obs) {
+  pt_off.assign(np + 1, 0);
+  for (int c = 0; c < nc; ++c) if (take(c)) ++pt_off[ids[c] + 1];
+  for (int p = 0; p < np; ++p) pt_off[p + 1] += pt_off[p];
+  pt_obs.resize(pt_off[np]);
+  std::vector<int> fill(pt_off.begin(), pt_off.end() - 1);
+  for (int c = 0; c < nc; ++c) if (take(c)) pt_obs[fill[ids[c]]++] = c;
+}
+
 size_t nearest_index(double t, const std::vector<double>& ts, double& dist_out) {   // utils.cc:194-212
   // FindClosestTimestamp is a linear scan keeping the FIRST strict minimum of |t - ts[i]|; on the time-sorted, distinct
   // view timestamps used here the same index is found by bisection + comparison of the two neighbours.
@@ -1044,6 +1055,101 @@ icc_status icc_estimate_board_poses(icc_handle* h, int nf, const int32_t* off, c
   return ICC_OK;
 }
 
+icc_status icc_filter_bad_poses(icc_handle* h, int nv, const double* p_wc, int32_t* valid) {
+  if (nv <= 0 || !p_wc || !valid) return ICC_ERR_INVALID_ARGUMENT;
+  std::vector<double> z; for (int i = 0; i < nv; ++i) if (valid[i]) z.push_back(p_wc[3 * i + 2]);
+  if (z.empty()) return ICC_OK;
+  const size_t n = z.size(); double med;   // utils::MedianOfDoubleVec (src/utils/utils.cc:77-97)
+  if (n % 2 == 0) { std::nth_element(z.begin(), z.begin() + n / 2 - 1, z.end()); const double e1 = z[n / 2 - 1]; std::nth_element(z.begin(), z.begin() + n / 2, z.end()); med = (e1 + z[n / 2]) / 2; }
+  else { std::nth_element(z.begin(), z.begin() + n / 2, z.end()); med = z[n / 2]; }
+  for (int i = 0; i < nv; ++i) if (valid[i] && std::fabs(p_wc[3 * i + 2] - med) > std::fabs(med)) valid[i] = 0;
+  (void)h;
+  return ICC_OK;
+}
+
+icc_status icc_get_board_points(const icc_handle* h, double* xyzw, int n) {
+  if (!h || !xyzw || n < 0) return ICC_ERR_INVALID_ARGUMENT;
+  const size_t m = std::min<size_t>(4 * (size_t)n, h->points.size());
+  std::copy(h->points.begin(), h->points.begin() + m, xyzw);
+  return ICC_OK;
+}
+
+icc_status icc_optimize_board_points(icc_handle* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points,
+                                     int min_observations, double* q_wc, double* p_wc, double* mean_err, int32_t* valid, double* board_out, int32_t* n_opt_out) {
+  if (!h || nf <= 0 || !off || !ids || !uv || !q_wc || !p_wc || !valid) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (h->model < 0 || h->points.empty()) return fail(h, ICC_ERR_STATE, "icc_set_camera and icc_set_board_points must be called first");
+  if (off[0] != 0) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must start at 0");
+  for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
+  const int nc = off[nf], np = (int)(h->points.size() / 4);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  std::vector<double4> board(np);
+  for (int i = 0; i < np; ++i) board[i] = make_double4(h->points[4 * i], h->points[4 * i + 1], h->points[4 * i + 2], h->points[4 * i + 3]);
+  std::vector<int> obs_view(std::max(1, nc));
+  for (int f = 0; f < nf; ++f) for (int c = off[f]; c < off[f + 1]; ++c) obs_view[c] = f;
+  DevBuf<double4> d_board, d_board2; DevBuf<int> d_off, d_pid, d_ok, d_valid, d_view, d_pt_off, d_pt_obs, d_opt; DevBuf<double2> d_uv, d_xy; DevBuf<unsigned char> d_use;
+  DevBuf<double> d_q, d_p, d_e, d_qcw, d_c;
+  CU(d_board.upload(board)); CU(d_board2.alloc(np)); CU(d_opt.alloc(np));
+  CU(d_off.alloc(nf + 1)); CU(d_pid.alloc(std::max(1, nc))); CU(d_uv.alloc(std::max(1, nc))); CU(d_xy.alloc(std::max(1, nc))); CU(d_ok.alloc(std::max(1, nc))); CU(d_use.alloc(std::max(1, nc)));
+  CU(d_q.alloc(4 * (size_t)nf)); CU(d_p.alloc(3 * (size_t)nf)); CU(d_e.alloc(nf)); CU(d_valid.alloc(nf)); CU(d_view.upload(obs_view));
+  CU(cudaMemcpyAsync(d_off.p, off, (size_t)(nf + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (nc > 0) {
+    CU(cudaMemcpyAsync(d_pid.p, ids, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_uv.p, uv, (size_t)nc * sizeof(double2), cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(d_q.p, q_wc, 4 * (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_p.p, p_wc, 3 * (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_valid.p, valid, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+  launch_unproject(h->model, h->intr, nc, d_uv.p, d_xy.p, d_ok.p, st);
+  PoseProblem Q; memset(&Q, 0, sizeof Q);
+  Q.model = h->model; for (int i = 0; i < 10; ++i) Q.intr[i] = h->intr[i];
+  Q.n_frames = nf; Q.n_points = np; Q.min_points = min_points > 0 ? min_points : 8;
+  Q.board = d_board.p; Q.f_off = d_off.p; Q.pid = d_pid.p; Q.refine_only = 1;
+  const double W = h->width, H = h->height;
+  const double max_px = max_reproj_error > 0.0 ? max_reproj_error : 0.004 * H;
+  Q.thresh_sq = (W > 0 && H > 0) ? max_px / std::sqrt(W * W + H * H) : 1e-3;
+  Q.max_err = max_px;
+  // 1. the stored poses and their inlier sets (what the pose dataset holds after EstimatePosesFromJson)
+  launch_board_poses(Q, d_xy.p, d_ok.p, d_use.p, d_q.p, d_p.p, d_e.p, d_valid.p, st);
+  std::vector<unsigned char> use(std::max(1, nc)); std::vector<int> vh(nf); std::vector<double> qh(4 * (size_t)nf), ph(3 * (size_t)nf);
+  CU(cudaMemcpyAsync(use.data(), d_use.p, (size_t)std::max(1, nc), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(vh.data(), d_valid.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(qh.data(), d_q.p, qh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ph.data(), d_p.p, ph.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // 2. OptimizeBoardPoints: one warp per point over its inlier observations in valid views, cameras constant
+  std::vector<int> pt_off, pt_obs;
+  build_point_adjacency(np, nc, ids, [&](int c) { return use[c] && vh[obs_view[c]]; }, pt_off, pt_obs);
+  std::vector<double> qcw(4 * (size_t)nf);
+  for (int f = 0; f < nf; ++f) { qcw[4 * f] = -qh[4 * f]; qcw[4 * f + 1] = -qh[4 * f + 1]; qcw[4 * f + 2] = -qh[4 * f + 2]; qcw[4 * f + 3] = qh[4 * f + 3]; }
+  CU(d_qcw.upload(qcw)); CU(d_c.upload(ph)); CU(d_pt_off.upload(pt_off)); CU(d_pt_obs.alloc(std::max<size_t>(1, pt_obs.size())));
+  if (!pt_obs.empty()) CU(cudaMemcpy(d_pt_obs.p, pt_obs.data(), pt_obs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  PointProblem PQ; memset(&PQ, 0, sizeof PQ);
+  PQ.model = h->model; for (int i = 0; i < 10; ++i) PQ.intr[i] = h->intr[i];
+  PQ.normalized = 1; PQ.n_points = np; PQ.min_obs = min_observations > 0 ? min_observations : 30; PQ.huber = 1.345;
+  PQ.board_in = d_board.p; PQ.pt_off = d_pt_off.p; PQ.pt_obs = d_pt_obs.p; PQ.obs_view = d_view.p; PQ.meas = d_xy.p; PQ.q_cw = d_qcw.p; PQ.cam_c = d_c.p;
+  launch_point_refine(PQ, d_board2.p, d_opt.p, st);
+  // 3. OptimizeAllPoses on the new points
+  Q.board = d_board2.p;
+  launch_board_poses(Q, d_xy.p, d_ok.p, d_use.p, d_q.p, d_p.p, d_e.p, d_valid.p, st);
+  std::vector<double> eh(nf); std::vector<int> opt(np);
+  CU(cudaMemcpyAsync(board.data(), d_board2.p, (size_t)np * sizeof(double4), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(opt.data(), d_opt.p, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(q_wc, d_q.p, 4 * (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(p_wc, d_p.p, 3 * (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(eh.data(), d_e.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(vh.data(), d_valid.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (cudaGetLastError() != cudaSuccess) return fail(h, ICC_ERR_CUDA, "board point kernels failed");
+  int n_opt = 0;
+  for (int i = 0; i < np; ++i) { h->points[4 * i] = board[i].x; h->points[4 * i + 1] = board[i].y; h->points[4 * i + 2] = board[i].z; h->points[4 * i + 3] = board[i].w; n_opt += opt[i]; }
+  if (board_out) std::copy(h->points.begin(), h->points.end(), board_out);
+  if (n_opt_out) *n_opt_out = n_opt;
+  for (int i = 0; i < nf; ++i) { valid[i] = vh[i]; if (mean_err) mean_err[i] = eh[i]; }
+  return ICC_OK;
+}
+
 // ---- upstream row f3: IMU-to-camera rotation + time offset initialiser ---------------------------------------------------
 namespace {
 double median_like_reference(std::vector<double> v) {   // utils::MedianOfDoubleVec (src/utils/utils.cc:77-97)
@@ -1489,10 +1595,36 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, 
   rc = bundle_adjust(sub.principal, false, 1); if (rc != ICC_OK) return rc;
   if ((int)active.size() < o.min_num_views) return finish(false);                               // :176-179
   // 3. full optimisation (:181-198)
-  rc = bundle_adjust(sub.principal | sub.focal | sub.aspect | (model == CAM_PINHOLE ? sub.radial : 0u) | (model == CAM_PINHOLE_RADTAN ? sub.tangential : 0u), true, 2);
+  const unsigned stage3_mask = sub.principal | sub.focal | sub.aspect | (model == CAM_PINHOLE ? sub.radial : 0u) | (model == CAM_PINHOLE_RADTAN ? sub.tangential : 0u);
+  rc = bundle_adjust(stage3_mask, true, 2);
   if (rc != ICC_OK) return rc;
   rc = remove_views(o.max_view_error_final_px); if (rc != ICC_OK) return rc;                     // :200
-  return finish((int)active.size() >= o.min_num_views);                                          // :202-205
+  if ((int)active.size() < o.min_num_views) return finish(false);                                // :202-205
+  if (o.optimize_board_points) {                                                                 // :207-216
+    // BundleAdjustTracks: every camera constant, one warp per board point over its observations in the remaining views ...
+    std::vector<int> obs_view(std::max(1, nc), -1), pt_off, pt_obs;
+    for (int v : active) for (int c = off[v]; c < off[v + 1]; ++c) obs_view[c] = v;
+    build_point_adjacency(np, nc, ids, [&](int c) { return obs_view[c] >= 0; }, pt_off, pt_obs);
+    DevBuf<int> d_view, d_pt_off, d_pt_obs, d_opt; DevBuf<double4> d_board2;
+    CU(d_view.upload(obs_view)); CU(d_pt_off.upload(pt_off)); CU(d_pt_obs.alloc(std::max<size_t>(1, pt_obs.size()))); CU(d_opt.alloc(np)); CU(d_board2.alloc(np));
+    if (!pt_obs.empty()) CU(cudaMemcpy(d_pt_obs.p, pt_obs.data(), pt_obs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PointProblem PQ; memset(&PQ, 0, sizeof PQ);
+    PQ.model = model; CU(cudaMemcpy(PQ.intr, d_k[cur].p, 10 * sizeof(double), cudaMemcpyDeviceToHost));
+    PQ.normalized = 0; PQ.n_points = np; PQ.min_obs = 1; PQ.huber = o.huber_width;
+    PQ.board_in = d_board.p; PQ.pt_off = d_pt_off.p; PQ.pt_obs = d_pt_obs.p; PQ.obs_view = d_view.p; PQ.meas = d_uv.p; PQ.q_cw = d_q[cur].p; PQ.cam_c = d_c[cur].p;
+    launch_point_refine(PQ, d_board2.p, d_opt.p, st);
+    std::vector<int> opt(np);
+    CU(cudaMemcpyAsync(d_board.p, d_board2.p, (size_t)np * sizeof(double4), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(board.data(), d_board2.p, (size_t)np * sizeof(double4), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(opt.data(), d_opt.p, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < np; ++i) { h->points[4 * i] = board[i].x; h->points[4 * i + 1] = board[i].y; h->points[4 * i + 2] = board[i].z; h->points[4 * i + 3] = board[i].w; S.n_points_optimized += opt[i]; }
+    // ... then BundleAdjustViews once more with the options of stage 3
+    const int it3 = S.iterations[2];
+    rc = bundle_adjust(stage3_mask, true, 2); if (rc != ICC_OK) return rc;
+    S.iterations[2] += it3;
+  }
+  return finish(true);
 }
 
 void icc_trim_device_cache(void) { block_cache().trim(); pinned_cache().trim(); }

@@ -93,9 +93,23 @@ struct PoseProblem {
   const double4* board; const int* f_off; const int* pid;
   double thresh_sq;            // squared normalised reprojection error of an inlier (pose_estimator.cc:100-101)
   double max_err;              // views above this mean error are dropped (pose_estimator.cc:181)
+  int refine_only;             // 1: start from the poses already in q_wc / p_wc (valid views only), no homography (OptimizeAllPoses, :226-236)
 };
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st);
 void launch_board_poses(const PoseProblem& Q, const double2* xy, const int* ok, unsigned char* use, double* q_wc, double* p_wc, double* err, int* valid, cudaStream_t st);
+// board point refinement with constant cameras (theia::BundleAdjustTracks), one warp per point
+struct PointProblem {
+  int model; double intr[10];
+  int normalized;              // 1: measurements are undistorted normalised coordinates (unit pinhole), 0: pixels through `model`
+  int n_points, min_obs;       // points with more than min_obs observations are optimised
+  double huber;
+  const double4* board_in;
+  const int* pt_off; const int* pt_obs;    // CSR by point: corner indices of the observations that take part
+  const int* obs_view;         // view index of every corner
+  const double2* meas;         // per corner: xy (normalised) or uv (pixels)
+  const double* q_cw; const double* cam_c; // per view: R_cw as (x,y,z,w), camera centre
+};
+void launch_point_refine(const PointProblem& Q, double4* board_out, int* optimized, cudaStream_t st);
 // focal length per view from the board homography on centred pixels (f2[v] = f^2 or 0), pinhole normalisation of pixels
 void launch_board_focal(const PoseProblem& Q, const double2* uv, double cx, double cy, double2* xy, unsigned char* use, double* f2, cudaStream_t st);
 void launch_pinhole_normalize(int n, const double2* uv, double cx, double cy, double f, double2* xy, int* ok, cudaStream_t st);

@@ -236,7 +236,8 @@ ICC_D bool board_homography(const PoseProblem& Q, const double2* __restrict__ xy
   dB = wsum(dB) / n; dI = wsum(dI) / n;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dz = fmax(dz, __shfl_xor_sync(0xffffffffu, dz, o));
-  if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * fmax(1.0, dB)) return false;   // degenerate or non-planar target
+  if (!(dB > 0.0) || !(dI > 0.0) || dz > 0.05 * dB) return false;   // degenerate, or too far from a plane for the homography to start the refinement
+                                                                     // (a few per cent of the board size -- refined board points of a printed target -- are fine: pose_system uses the real 3-D points)
   const double sB = sqrt(2.0) / dB, sI = sqrt(2.0) / dI;
   // ---- homography (h33 = 1) from the normal equations of the DLT rows -------------------------------------------------------
   double M[36], v8[8];
@@ -278,24 +279,45 @@ ICC_D bool board_homography(const PoseProblem& Q, const double2* __restrict__ xy
 }
 
 __global__ void __launch_bounds__(128) board_pose_kernel(PoseProblem Q, const double2* __restrict__ xy, const int* __restrict__ okc, unsigned char* __restrict__ use,
-                                                        double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ err_out, int* __restrict__ valid_out) {
+                                                        double* q_out, double* p_out, double* __restrict__ err_out, int* valid_out) {
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (f >= Q.n_frames) return;
   const int c0 = Q.f_off[f], c1 = Q.f_off[f + 1];
   auto fail = [&]() {
     if (lane == 0) { q_out[4 * f] = 0.0; q_out[4 * f + 1] = 0.0; q_out[4 * f + 2] = 0.0; q_out[4 * f + 3] = 1.0; p_out[3 * f] = 0.0; p_out[3 * f + 1] = 0.0; p_out[3 * f + 2] = 0.0; err_out[f] = 0.0; valid_out[f] = 0; }
   };
-  double n = 0.0, zref = 0.0, Hm[9];
-  if (!board_homography(Q, xy, okc, use, c0, c1, n, zref, Hm)) { fail(); return; }
-  // H ~ [r1 r2 t] (points on the plane z = zref, shifted to z = 0): scale, cheirality, Gram-Schmidt
-  V3 h1 = v3(Hm[0], Hm[3], Hm[6]), h2 = v3(Hm[1], Hm[4], Hm[7]), h3 = v3(Hm[2], Hm[5], Hm[8]);
-  double s = 2.0 / (sqrt(dot(h1, h1)) + sqrt(dot(h2, h2)));
-  if (h3.z * s < 0.0) s = -s;
-  V3 r1 = s * h1, r2 = s * h2, t = s * h3;
-  r1 = (1.0 / sqrt(dot(r1, r1))) * r1;
-  r2 = r2 - dot(r1, r2) * r1; r2 = (1.0 / sqrt(dot(r2, r2))) * r2;
-  const V3 r3 = cross(r1, r2);
-  Q4 q = quat_from_columns(r1, r2, r3);          // R_cw
+  double n = 0.0, zref = 0.0;
+  Q4 q; V3 t;
+  if (Q.refine_only) {
+    // PoseEstimator::OptimizeAllPoses (pose_estimator.cc:226-236): BundleAdjustView again from the stored pose -- no homography, so the
+    // board may have left its plane (optimised board points); views that were dropped stay dropped and keep their outputs
+    if (!valid_out[f]) return;
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const int id = Q.pid[c];
+      const bool u = okc[c] != 0 && id >= 0 && id < Q.n_points;
+      use[c] = u ? 1 : 0;
+      if (u) n += 1.0;
+    }
+    n = wsum(n);
+    __syncwarp();
+    if (c1 - c0 < Q.min_points || n < 6.0) { fail(); return; }
+    const Q4 qw = qnormalized(q4(q_out[4 * f], q_out[4 * f + 1], q_out[4 * f + 2], q_out[4 * f + 3]));
+    q = qconj(qw);
+    t = -qrot(q, v3(p_out[3 * f], p_out[3 * f + 1], p_out[3 * f + 2]));
+  } else {
+    double Hm[9];
+    if (!board_homography(Q, xy, okc, use, c0, c1, n, zref, Hm)) { fail(); return; }
+    // H ~ [r1 r2 t] (points on the plane z = zref, shifted to z = 0): scale, cheirality, Gram-Schmidt
+    V3 h1 = v3(Hm[0], Hm[3], Hm[6]), h2 = v3(Hm[1], Hm[4], Hm[7]), h3 = v3(Hm[2], Hm[5], Hm[8]);
+    double s = 2.0 / (sqrt(dot(h1, h1)) + sqrt(dot(h2, h2)));
+    if (h3.z * s < 0.0) s = -s;
+    V3 r1 = s * h1, r2 = s * h2;
+    t = s * h3;
+    r1 = (1.0 / sqrt(dot(r1, r1))) * r1;
+    r2 = r2 - dot(r1, r2) * r1; r2 = (1.0 / sqrt(dot(r2, r2))) * r2;
+    const V3 r3 = cross(r1, r2);
+    q = quat_from_columns(r1, r2, r3);          // R_cw
+  }
   // ---- refinement, inlier selection with the reference's squared normalised threshold, refinement on the inliers -------------
   pose_refine(Q, xy, use, c0, c1, zref, q, t);
   double n_in = 0.0, n_out = 0.0;
@@ -362,6 +384,88 @@ __global__ void pinhole_normalize_kernel(int n, const double2* __restrict__ uv, 
   ok[i] = 1;
 }
 
+
+// theia::BundleAdjustTracks with every camera constant (PoseEstimator::OptimizeBoardPoints, pose_estimator.cc:193-224; the tail of
+// CameraCalibrator::RunCalibration, camera_calibrator.cc:207-216): with the cameras fixed every board point is its own 3-parameter
+// problem, so ONE WARP owns one point: lanes stride over the point's observations (CSR by point, built on the host), the 3x3
+// Levenberg-Marquardt system is warp-reduced and solved in registers by every lane.  Residual: Huber(1.345) on
+//   normalised == 1 :  (R_cw (X - c)).xy / z - x_n          (the pose estimator's unit-pinhole views with undistorted features)
+//   normalised == 0 :  CameraToPixelCoordinates(intr, R_cw (X - c)) - pixel     (the camera calibrator's views)
+struct PointSys { double H[3][3]; double g[3]; double cost; };
+ICC_D void point_system(const PointProblem& Q, int o0, int o1, V3 X, PointSys& S, bool with_jacobian) {
+  const int lane = threadIdx.x & 31;
+  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, cost = 0.0;
+  const double hub = Q.huber;
+  for (int o = o0 + lane; o < o1; o += 32) {
+    const int c = Q.pt_obs[o], v = Q.obs_view[c];
+    const Q4 q = q4(Q.q_cw[4 * v], Q.q_cw[4 * v + 1], Q.q_cw[4 * v + 2], Q.q_cw[4 * v + 3]);
+    const V3 pc = qrot(q, X - v3(Q.cam_c[3 * v], Q.cam_c[3 * v + 1], Q.cam_c[3 * v + 2]));
+    double r0, r1; V3 a0, a1;
+    if (Q.normalized) {
+      if (!(pc.z > 0.0)) { cost += 1e6; continue; }
+      const double iz = 1.0 / pc.z, u = pc.x * iz, w = pc.y * iz;
+      r0 = u - Q.meas[c].x; r1 = w - Q.meas[c].y;
+      a0 = v3(iz, 0.0, -u * iz); a1 = v3(0.0, iz, -w * iz);
+    } else {
+      const Proj pr = project(Q.model, Q.intr, pc, true);
+      if (!pr.ok) { cost += 1e10; continue; }
+      r0 = pr.u - Q.meas[c].x; r1 = pr.v - Q.meas[c].y;
+      a0 = v3(pr.J[0], pr.J[1], pr.J[2]); a1 = v3(pr.J[3], pr.J[4], pr.J[5]);
+    }
+    const double rn = sqrt(r0 * r0 + r1 * r1), wgt = rn <= hub ? 1.0 : hub / rn;
+    cost += rn <= hub ? 0.5 * rn * rn : hub * rn - 0.5 * hub * hub;
+    if (!with_jacobian) continue;
+    const V3 j0 = qrot_inv(q, a0), j1 = qrot_inv(q, a1);   // rows of J_proj R_cw
+    g[0] += wgt * (j0.x * r0 + j1.x * r1); g[1] += wgt * (j0.y * r0 + j1.y * r1); g[2] += wgt * (j0.z * r0 + j1.z * r1);
+    H[0] += wgt * (j0.x * j0.x + j1.x * j1.x); H[1] += wgt * (j0.x * j0.y + j1.x * j1.y); H[2] += wgt * (j0.x * j0.z + j1.x * j1.z);
+    H[3] += wgt * (j0.y * j0.y + j1.y * j1.y); H[4] += wgt * (j0.y * j0.z + j1.y * j1.z); H[5] += wgt * (j0.z * j0.z + j1.z * j1.z);
+  }
+  S.cost = wsum(cost);
+  if (!with_jacobian) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.g[i] = wsum(g[i]);
+  const double h0 = wsum(H[0]), h1 = wsum(H[1]), h2 = wsum(H[2]), h3 = wsum(H[3]), h4 = wsum(H[4]), h5 = wsum(H[5]);
+  S.H[0][0] = h0; S.H[0][1] = h1; S.H[0][2] = h2; S.H[1][0] = h1; S.H[1][1] = h3; S.H[1][2] = h4; S.H[2][0] = h2; S.H[2][1] = h4; S.H[2][2] = h5;
+}
+
+__global__ void __launch_bounds__(128) point_refine_kernel(PointProblem Q, double4* __restrict__ board_out, int* __restrict__ optimized) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= Q.n_points) return;
+  const int o0 = Q.pt_off[p], o1 = Q.pt_off[p + 1];
+  const double4 Xb = Q.board_in[p];
+  if (o1 - o0 <= Q.min_obs) { if (lane == 0) { board_out[p] = Xb; optimized[p] = 0; } return; }   // pose_estimator.cc:202-206
+  V3 X = v3(Xb.x / Xb.w, Xb.y / Xb.w, Xb.z / Xb.w);
+  PointSys S;
+  point_system(Q, o0, o1, X, S, true);
+  double lambda = 1e-4, cost = S.cost;
+  for (int it = 0; it < 50; ++it) {
+    double A[3][3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      b[i] = -S.g[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) A[i][j] = S.H[i][j];
+      A[i][i] += lambda * (S.H[i][i] + 1e-12);
+    }
+    if (!chol_solve<3>(A, b)) { lambda *= 10.0; if (lambda > 1e12) break; continue; }
+    const V3 Xn = X + v3(b[0], b[1], b[2]);
+    PointSys Sn;
+    point_system(Q, o0, o1, Xn, Sn, false);
+    const double step2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    if (Sn.cost < cost) {
+      const double dec = cost - Sn.cost;
+      X = Xn; cost = Sn.cost; lambda = fmax(lambda * 0.1, 1e-12);
+      if (dec <= 1e-15 * cost || step2 < 1e-30) break;
+      point_system(Q, o0, o1, X, S, true);
+    } else {
+      if (step2 < 1e-30) break;
+      lambda *= 10.0;
+      if (lambda > 1e12) break;
+    }
+  }
+  if (lane == 0) { board_out[p] = make_double4(X.x, X.y, X.z, 1.0); optimized[p] = 1; }
+}
+
 }  // namespace
 
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st) {
@@ -386,6 +490,12 @@ void launch_board_focal(const PoseProblem& Q, const double2* uv, double cx, doub
 void launch_pinhole_normalize(int n, const double2* uv, double cx, double cy, double f, double2* xy, int* ok, cudaStream_t st) {
   if (n <= 0) return;
   pinhole_normalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, uv, cx, cy, 1.0 / f, xy, ok);
+  count_launch();
+}
+
+void launch_point_refine(const PointProblem& Q, double4* board_out, int* optimized, cudaStream_t st) {
+  if (Q.n_points <= 0) return;
+  point_refine_kernel<<<(Q.n_points + 3) / 4, 128, 0, st>>>(Q, board_out, optimized);
   count_launch();
 }
 

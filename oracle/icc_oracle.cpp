@@ -1029,7 +1029,7 @@ bool oracle_unproject(int model, const double* intr, double px, double py, doubl
   xy[0] = x; xy[1] = y;
   return e < 1e-12;
 }
-struct PoseObs { double X, Y, Z, x, y; };
+struct PoseObs { double X, Y, Z, x, y; int c; };
 typedef V3<double> Vd; typedef Q4<double> Qd;
 double pose_cost(const std::vector<PoseObs>& ob, const Qd& R, const Vd& t) {
   double c = 0.0;
@@ -1088,7 +1088,7 @@ bool oracle_homography(const std::vector<PoseObs>& ob, double& zref, double Hm[9
   zref /= n; mX /= n; mY /= n; mx /= n; my /= n;
   double dB = 0, dI = 0, dz = 0; for (const PoseObs& p : ob) { dB += std::hypot(p.X - mX, p.Y - mY); dI += std::hypot(p.x - mx, p.y - my); dz = std::max(dz, std::fabs(p.Z - zref)); }
   dB /= n; dI /= n;
-  if (!(dB > 0.0) || !(dI > 0.0) || dz > 1e-9 * std::max(1.0, dB)) return false;   // degenerate or non-planar target
+  if (!(dB > 0.0) || !(dI > 0.0) || dz > 0.05 * dB) return false;   // degenerate, or too far from a plane for the homography initialisation
   const double sB = std::sqrt(2.0) / dB, sI = std::sqrt(2.0) / dI;
   // DLT: null vector of A^T A (9 x 9) by inverse iteration with a tiny shift
   std::vector<double> M(81, 0.0);
@@ -1122,33 +1122,44 @@ icc_status icco_pixels_to_normalized(void* h, int n, const double* uv, double* x
   return ICC_OK;
 }
 
-icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points,
-                                     double* q_wc, double* p_wc, double* mean_err, int32_t* valid) {
-  Oracle& o = *O(h);
+}  // extern "C"
+namespace {
+// the per-view loop of PoseEstimator::EstimatePosesFromJson; refine_only = OptimizeAllPoses (start from the stored poses of the valid
+// views, no homography); inlier (optional, one flag per corner) receives the final inlier sets
+icc_status oracle_board_poses(Oracle& o, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points, bool refine_only,
+                              double* q_wc, double* p_wc, double* mean_err, int32_t* valid, std::vector<char>* inlier) {
   const int np = (int)(o.points.size() / 4);
   const double W = o.width, Hh = o.height;
   const double max_px = max_reproj_error > 0.0 ? max_reproj_error : 0.004 * Hh;
   const double thresh_sq = (W > 0 && Hh > 0) ? max_px / std::sqrt(W * W + Hh * Hh) : 1e-3;
   if (min_points <= 0) min_points = 8;
   for (int f = 0; f < nf; ++f) {
-    q_wc[4 * f] = q_wc[4 * f + 1] = q_wc[4 * f + 2] = 0.0; q_wc[4 * f + 3] = 1.0; p_wc[3 * f] = p_wc[3 * f + 1] = p_wc[3 * f + 2] = 0.0; valid[f] = 0; if (mean_err) mean_err[f] = 0.0;
+    if (refine_only && !valid[f]) continue;
+    if (!refine_only) { q_wc[4 * f] = q_wc[4 * f + 1] = q_wc[4 * f + 2] = 0.0; q_wc[4 * f + 3] = 1.0; p_wc[3 * f] = p_wc[3 * f + 1] = p_wc[3 * f + 2] = 0.0; valid[f] = 0; if (mean_err) mean_err[f] = 0.0; }
     std::vector<PoseObs> ob;
     for (int c = off[f]; c < off[f + 1]; ++c) {
       const int id = ids[c]; double xy[2];
       if (id < 0 || id >= np || !oracle_unproject(o.model, o.intr, uv[2 * c], uv[2 * c + 1], xy)) continue;
       const double* P = &o.points[4 * (size_t)id];
-      ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], xy[0], xy[1]});
+      ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], xy[0], xy[1], c});
     }
-    if (off[f + 1] - off[f] < min_points || ob.size() < 6) continue;
+    if (off[f + 1] - off[f] < min_points || ob.size() < 6) { if (refine_only) { q_wc[4 * f] = q_wc[4 * f + 1] = q_wc[4 * f + 2] = 0.0; q_wc[4 * f + 3] = 1.0; p_wc[3 * f] = p_wc[3 * f + 1] = p_wc[3 * f + 2] = 0.0; valid[f] = 0; if (mean_err) mean_err[f] = 0.0; } continue; }
     double zref = 0.0, Hm[9];
+    Qd R; Vd t;
+    if (refine_only) {   // PoseEstimator::OptimizeAllPoses (pose_estimator.cc:226-236): BundleAdjustView again from the stored pose
+      R = so3_inv(qnormalized(Qd{q_wc[4 * f], q_wc[4 * f + 1], q_wc[4 * f + 2], q_wc[4 * f + 3]}));
+      t = so3_act(R, Vd{p_wc[3 * f], p_wc[3 * f + 1], p_wc[3 * f + 2]}) * -1.0;
+      q_wc[4 * f] = q_wc[4 * f + 1] = q_wc[4 * f + 2] = 0.0; q_wc[4 * f + 3] = 1.0; p_wc[3 * f] = p_wc[3 * f + 1] = p_wc[3 * f + 2] = 0.0; valid[f] = 0; if (mean_err) mean_err[f] = 0.0;
+    } else {
     if (!oracle_homography(ob, zref, Hm)) continue;
     const Vd h1{Hm[0], Hm[3], Hm[6]}, h2{Hm[1], Hm[4], Hm[7]}, h3{Hm[2], Hm[5], Hm[8]};
     double sc = 2.0 / (vnorm(h1) + vnorm(h2));
     if (h3.z * sc < 0.0) sc = -sc;
-    Vd r1 = h1 * sc, r2 = h2 * sc, t = h3 * sc;
+    Vd r1 = h1 * sc, r2 = h2 * sc; t = h3 * sc;
     r1 = r1 * (1.0 / vnorm(r1)); r2 = r2 - r1 * dot(r1, r2); r2 = r2 * (1.0 / vnorm(r2));
     const Vd r3 = cross(r1, r2);
-    Qd R = quat_from_cols(r1, r2, r3);
+    R = quat_from_cols(r1, r2, r3);
+    }
     for (PoseObs& p : ob) p.Z -= zref;
     pose_gauss_newton(ob, R, t);
     std::vector<PoseObs> in;
@@ -1164,7 +1175,106 @@ icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const 
     p_wc[3 * f] = pw.x; p_wc[3 * f + 1] = pw.y; p_wc[3 * f + 2] = pw.z;
     if (mean_err) mean_err[f] = e;
     valid[f] = e <= max_px ? 1 : 0;
+    if (inlier) for (const PoseObs& p : in) (*inlier)[p.c] = 1;
   }
+  return ICC_OK;
+}
+}  // namespace
+
+extern "C" {
+icc_status icco_estimate_board_poses(void* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points,
+                                     double* q_wc, double* p_wc, double* mean_err, int32_t* valid) {
+  return oracle_board_poses(*O(h), nf, off, ids, uv, max_reproj_error, min_points, false, q_wc, p_wc, mean_err, valid, nullptr);
+}
+
+icc_status icco_filter_bad_poses(void* h, int nv, const double* p_wc, int32_t* valid) {   // PoseEstimator::FilterBadPoses (pose_estimator.cc:238-261)
+  std::vector<double> z; for (int i = 0; i < nv; ++i) if (valid[i]) z.push_back(p_wc[3 * i + 2]);
+  if (z.empty()) return ICC_OK;
+  std::sort(z.begin(), z.end());
+  const size_t n = z.size(); const double med = n % 2 == 0 ? (z[n / 2 - 1] + z[n / 2]) / 2 : z[n / 2];
+  for (int i = 0; i < nv; ++i) if (valid[i] && std::fabs(p_wc[3 * i + 2] - med) > std::fabs(med)) valid[i] = 0;
+  return ICC_OK;
+}
+icc_status icco_get_board_points(const void* h, double* xyzw, int n) { const Oracle& o = *O(h); for (size_t i = 0; i < 4 * (size_t)n && i < o.points.size(); ++i) xyzw[i] = o.points[i]; return ICC_OK; }
+}  // extern "C"
+
+namespace {
+// One observation of a board point with a constant camera, as theia::BundleAdjustTracks poses it (forward-mode duals over the point).
+template <class T> bool point_residual(bool normalized, int model, const double* intr, const M3<double>& Rcw, const Vd& cc, const T X[3], const double* meas, T r[2]) {
+  const T d[3] = {X[0] - cc.x, X[1] - cc.y, X[2] - cc.z};
+  T pc[3];
+  for (int i = 0; i < 3; ++i) pc[i] = d[0] * Rcw.m[i][0] + d[1] * Rcw.m[i][1] + d[2] * Rcw.m[i][2];
+  if (normalized) { if (!(jval(pc[2]) > 0.0)) return false; r[0] = pc[0] / pc[2] - meas[0]; r[1] = pc[1] / pc[2] - meas[1]; return true; }
+  T k[10], px[2]; for (int i = 0; i < 10; ++i) k[i] = T(intr[i]);
+  if (!project<T>(model, k, pc, px, true)) return false;
+  r[0] = px[0] - meas[0]; r[1] = px[1] - meas[1];
+  return true;
+}
+struct PointObs { M3<double> R; Vd c; double meas[2]; };
+// Levenberg-Marquardt on the three coordinates of one point (same damping schedule as the pose refinement above); returns the cost
+void refine_point(bool normalized, int model, const double* intr, const std::vector<PointObs>& ob, double huber, double X[3]) {
+  typedef Jet<4> J4;
+  auto cost_of = [&](const double* Xd) { double c = 0; for (const PointObs& o : ob) { double r[2]; if (!point_residual<double>(normalized, model, intr, o.R, o.c, Xd, o.meas, r)) { c += normalized ? 1e6 : 1e10; continue; }
+      const double rn = std::sqrt(r[0] * r[0] + r[1] * r[1]); c += rn <= huber ? 0.5 * rn * rn : huber * rn - 0.5 * huber * huber; } return c; };
+  double lambda = 1e-4, cost = cost_of(X);
+  for (int it = 0; it < 100; ++it) {
+    std::vector<double> H(9, 0.0), g(3, 0.0);
+    for (const PointObs& o : ob) {
+      J4 Xj[3], r[2]; for (int i = 0; i < 3; ++i) { Xj[i] = J4(X[i]); Xj[i].v[i] = 1.0; }
+      if (!point_residual<J4>(normalized, model, intr, o.R, o.c, Xj, o.meas, r)) continue;
+      const double rn = std::sqrt(r[0].a * r[0].a + r[1].a * r[1].a), w = rn <= huber ? 1.0 : huber / rn;
+      for (int a = 0; a < 3; ++a) { g[a] += w * (r[0].v[a] * r[0].a + r[1].v[a] * r[1].a); for (int b = 0; b < 3; ++b) H[a * 3 + b] += w * (r[0].v[a] * r[0].v[b] + r[1].v[a] * r[1].v[b]); }
+    }
+    std::vector<double> A = H, b(3);
+    for (int a = 0; a < 3; ++a) { A[a * 3 + a] += lambda * (H[a * 3 + a] + 1e-12); b[a] = -g[a]; }
+    if (!gauss_solve(3, A, b)) { lambda *= 10.0; if (lambda > 1e12) break; continue; }
+    const double Xn[3] = {X[0] + b[0], X[1] + b[1], X[2] + b[2]};
+    const double cn = cost_of(Xn), step2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    if (cn < cost) { const double dec = cost - cn; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; cost = cn; lambda = std::max(lambda * 0.1, 1e-12); if (dec <= 1e-15 * cost || step2 < 1e-30) break; }
+    else { if (step2 < 1e-30) break; lambda *= 10.0; if (lambda > 1e12) break; }
+  }
+}
+// theia::BundleAdjustTracks with constant cameras over the corners selected by take(c); returns the number of optimised points
+template <class F>
+int oracle_refine_points(Oracle& o, bool normalized, int model, const double* intr, int nv, const int32_t* off, const int32_t* ids, const double* meas,
+                         const double* q_wc, const double* p_wc, F take, int min_obs, double huber) {
+  const int np = (int)(o.points.size() / 4);
+  std::vector<std::vector<PointObs>> per(np);
+  for (int v = 0; v < nv; ++v) {
+    const M3<double> R = so3_matrix(so3_inv(qnormalized(Qd{q_wc[4 * v], q_wc[4 * v + 1], q_wc[4 * v + 2], q_wc[4 * v + 3]})));
+    const Vd c{p_wc[3 * v], p_wc[3 * v + 1], p_wc[3 * v + 2]};
+    for (int cidx = off[v]; cidx < off[v + 1]; ++cidx) if (take(cidx)) per[ids[cidx]].push_back({R, c, {meas[2 * cidx], meas[2 * cidx + 1]}});
+  }
+  int n_opt = 0;
+  for (int p = 0; p < np; ++p) {
+    if ((int)per[p].size() <= min_obs) continue;
+    double* P = &o.points[4 * (size_t)p];
+    double X[3] = {P[0] / P[3], P[1] / P[3], P[2] / P[3]};
+    refine_point(normalized, model, intr, per[p], huber, X);
+    P[0] = X[0]; P[1] = X[1]; P[2] = X[2]; P[3] = 1.0; ++n_opt;
+  }
+  return n_opt;
+}
+}  // namespace
+
+extern "C" {
+// PoseEstimator::OptimizeBoardPoints + OptimizeAllPoses (pose_estimator.cc:193-236; app estimate_camera_poses_from_checkerboard.cc:61-65)
+icc_status icco_optimize_board_points(void* h, int nf, const int32_t* off, const int32_t* ids, const double* uv, double max_reproj_error, int min_points, int min_observations,
+                                      double* q_wc, double* p_wc, double* mean_err, int32_t* valid, double* board_out, int32_t* n_opt_out) {
+  Oracle& o = *O(h);
+  const int nc = off[nf];
+  std::vector<char> inlier(std::max(1, nc), 0);
+  std::vector<double> e(nf);
+  oracle_board_poses(o, nf, off, ids, uv, max_reproj_error, min_points, true, q_wc, p_wc, e.data(), valid, &inlier);
+  std::vector<double> xy(2 * (size_t)std::max(1, nc), 0.0);
+  for (int c = 0; c < nc; ++c) if (inlier[c]) oracle_unproject(o.model, o.intr, uv[2 * c], uv[2 * c + 1], &xy[2 * c]);
+  std::vector<int> view_of(std::max(1, nc)); for (int f = 0; f < nf; ++f) for (int c = off[f]; c < off[f + 1]; ++c) view_of[c] = f;
+  const int n_opt = oracle_refine_points(o, true, o.model, o.intr, nf, off, ids, xy.data(), q_wc, p_wc, [&](int c) { return inlier[c] && valid[view_of[c]]; },
+                                         min_observations > 0 ? min_observations : 30, 1.345);
+  oracle_board_poses(o, nf, off, ids, uv, max_reproj_error, min_points, true, q_wc, p_wc, e.data(), valid, nullptr);
+  if (mean_err) for (int f = 0; f < nf; ++f) mean_err[f] = e[f];
+  if (board_out) std::copy(o.points.begin(), o.points.end(), board_out);
+  if (n_opt_out) *n_opt_out = n_opt;
   return ICC_OK;
 }
 
@@ -1574,7 +1684,7 @@ icc_status icco_calibrate_camera(void* h, int model, int W, int Hh, int nv, cons
     std::vector<double> fs;
     for (int v = 0; v < nv; ++v) {
       std::vector<PoseObs> ob;
-      for (int c = off[v]; c < off[v + 1]; ++c) { if (ids[c] < 0 || ids[c] >= np) continue; const double* P = &orc.points[4 * (size_t)ids[c]]; ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], uv[2 * c] - cx0, uv[2 * c + 1] - cy0}); }
+      for (int c = off[v]; c < off[v + 1]; ++c) { if (ids[c] < 0 || ids[c] >= np) continue; const double* P = &orc.points[4 * (size_t)ids[c]]; ob.push_back({P[0] / P[3], P[1] / P[3], P[2] / P[3], uv[2 * c] - cx0, uv[2 * c + 1] - cy0, c}); }
       double zref, Hm[9];
       if (off[v + 1] - off[v] < 6 || ob.size() < 6 || !oracle_homography(ob, zref, Hm)) continue;
       const double a1 = Hm[0] * Hm[1] + Hm[3] * Hm[4], b1 = Hm[6] * Hm[7], a2 = Hm[0] * Hm[0] + Hm[3] * Hm[3] - Hm[1] * Hm[1] - Hm[4] * Hm[4], b2 = Hm[6] * Hm[6] - Hm[7] * Hm[7];
@@ -1666,7 +1776,21 @@ icc_status icco_calibrate_camera(void* h, int model, int W, int Hh, int nv, cons
   st = camcal_bundle_adjust(C, principal | focal | aspect | (model == 0 ? radial : 0u) | (model == 1 ? tangential : 0u), true, o);
   S.iterations[2] = st.iterations; S.termination[2] = st.termination; S.final_cost[2] = st.final_cost;
   remove_views(o.max_view_error_final_px);
-  return finish((int)C.active.size() >= o.min_num_views);
+  if ((int)C.active.size() < o.min_num_views) return finish(false);
+  if (o.optimize_board_points) {   // camera_calibrator.cc:207-216: BundleAdjustTracks (cameras constant), then BundleAdjustViews once more
+    std::vector<double> qv(4 * (size_t)nv), pv(3 * (size_t)nv); std::vector<char> in_active(nv, 0), take(std::max(1, off[nv]), 0);
+    for (int v : C.active) { in_active[v] = 1; for (int c = off[v]; c < off[v + 1]; ++c) take[c] = 1; }
+    for (int v = 0; v < nv; ++v) {
+      const Qd qcw = so3_exp(Vd{C.ext[6 * v + 3], C.ext[6 * v + 4], C.ext[6 * v + 5]});
+      qv[4 * v] = -qcw.x; qv[4 * v + 1] = -qcw.y; qv[4 * v + 2] = -qcw.z; qv[4 * v + 3] = qcw.w;
+      for (int d = 0; d < 3; ++d) pv[3 * v + d] = C.ext[6 * v + d];
+    }
+    S.n_points_optimized = oracle_refine_points(orc, false, model, C.k, nv, off, ids, uv, qv.data(), pv.data(), [&](int c) { return take[c] != 0; }, 1, o.huber_width);
+    const int it3 = S.iterations[2];
+    st = camcal_bundle_adjust(C, principal | focal | aspect | (model == 0 ? radial : 0u) | (model == 1 ? tangential : 0u), true, o);
+    S.iterations[2] = it3 + st.iterations; S.termination[2] = st.termination; S.final_cost[2] = st.final_cost;
+  }
+  return finish(true);
 }
 
 int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }

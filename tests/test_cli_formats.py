@@ -265,3 +265,34 @@ def test_calibrate_camera_cli_matches_api_and_feeds_the_pose_tool(tmp_path, gpu_
     assert set(pd["views"]) == set(ds["views"])
     dp = max(np.abs(np.array(pd["views"][n]["p_wc"]) - np.array(ds["views"][n]["p_wc"])).max() for n in pd["views"])
     assert dp < 2e-3     # joint bundle adjustment vs per-view refinement on undistorted coordinates: same poses up to the noise
+
+
+@pytest.mark.gpu
+def test_optimize_board_points_flags_of_both_tools(tmp_path):
+    """--optimize_board_points of estimate_camera_poses_from_checkerboard (app :61-65) and calibrate_camera (camera_calibrator.cc:207-216):
+    the tracks written to the dataset are the refined board points; without the flag they are the input points."""
+    from test_camera_calibration import CASES, scene
+    model, k = CASES[4]
+    B, off, ids, uv, q_true, p_true = scene(model, k, n_views=40, seed=17, noise_px=0.1)
+    bent = B.copy(); bent[:, :3] += np.random.default_rng(5).normal(0, 3e-4, (B.shape[0], 3))
+    corners = str(tmp_path / "corners.uson")
+    _write_corner_file(corners, bent, off, ids, uv)
+    runs = {}
+    for flag in ("--nooptimize_board_points", "--optimize_board_points"):
+        out = subprocess.run([CAL_CLI, "--input_corners=" + corners, "--camera_model_to_calibrate=EXTENDED_UNIFIED", "--save_path_calib_dataset=" + str(tmp_path / ("cam" + flag[2:5])),
+                              "--grid_size=0.001", flag], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr + out.stdout
+        runs[flag] = (json.load(open(str(tmp_path / ("cam" + flag[2:5])) + ".json")), json.load(open(str(tmp_path / ("cam" + flag[2:5])) + ".calibdata")), out.stdout)
+    plain, opt = runs["--nooptimize_board_points"], runs["--optimize_board_points"]
+    assert f"Optimized {B.shape[0]} board points." in opt[2]
+    assert opt[0]["final_reproj_error"] < 0.5 * plain[0]["final_reproj_error"]
+    t_plain = np.array([plain[1]["tracks"][str(i)] for i in range(B.shape[0])]); t_opt = np.array([opt[1]["tracks"][str(i)] for i in range(B.shape[0])])
+    assert np.allclose(t_plain, bent) and np.abs(t_opt - bent).max() > 1e-5
+    # the pose tool with the calibration just written
+    pj = str(tmp_path / "poses_opt.json")
+    out = subprocess.run([POSE_CLI, "--input_corners=" + corners, "--camera_calibration_json=" + str(tmp_path / "camopt.json"), "--output_pose_dataset=" + pj, "--optimize_board_points"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "board points" in out.stdout
+    pd = json.load(open(pj))
+    assert len(pd["views"]) == 40 and np.abs(np.array([pd["tracks"][str(i)] for i in range(B.shape[0])]) - bent).max() > 1e-5

@@ -179,3 +179,68 @@ def test_gpu_poses_config4_full_size(oracle_factory, gpu_factory):
     qo, po, eo, vo = o.estimate_board_poses(off, ds["point_ids"][: off[-1]], ds["uv"][: off[-1]])
     assert _qdiff(q[:n], qo).max() < 2e-8 and np.abs(p[:n] - po).max() < 2e-8
     print(f"\n[f1] 3000 views x 144 corners: {dt * 1e3:.2f} ms wall incl. H2D/D2H ({3000 / dt:.0f} views/s)")
+
+
+# ---- --optimize_board_points of the pose app + FilterBadPoses (app :61-67) ----------------------------------------------------------
+def _perturbed(board, sigma=5e-4, seed=0):
+    bad = board.copy(); bad[:, :3] += np.random.default_rng(seed).normal(0, sigma, (board.shape[0], 3))
+    return bad
+
+
+def test_oracle_board_point_optimisation(oracle_factory):
+    """OptimizeBoardPoints + OptimizeAllPoses (pose_estimator.cc:193-236): exact data is a fixed point; a board known only to 0.5 mm
+    is pulled towards consistency with the images (the poses were estimated on the wrong board, so the truth itself is out of reach)."""
+    model, k = CASES[4]
+    board, off, ids, uv, q_true, p_true = _scene(model, k, n_frames=60, seed=3)
+    o = _setup(oracle_factory(), model, k, board)
+    q, p, e, v, B, n = o.optimize_board_points(off, ids, uv, q_true, p_true, np.ones(60, np.int32))
+    assert n == board.shape[0] and v.all()
+    assert np.abs(B[:, :3] - board[:, :3]).max() < 1e-12 and np.abs(p - p_true).max() < 1e-10 and e.max() < 1e-10
+    assert np.array_equal(o.get_board_points(), B)
+    # only points seen in more than min_num_obs_for_optim_ = 30 views are touched (pose_estimator.h:78, .cc:202-206)
+    keep = np.ones(uv.shape[0], bool); C = board.shape[0]
+    for f in range(35, 60):
+        keep[f * C + 5] = False                                       # point 5 is seen in 35 views, point 6 in 25
+    for f in range(25, 60):
+        keep[f * C + 6] = False
+    off2 = np.concatenate([[0], np.cumsum([keep[f * C:(f + 1) * C].sum() for f in range(60)])]).astype(np.int32)
+    o = _setup(oracle_factory(), model, k, _perturbed(board))
+    q0, p0, e0, v0 = o.estimate_board_poses(off2, ids[keep], uv[keep])
+    before = o.get_board_points()
+    q, p, e, v, B, n = o.optimize_board_points(off2, ids[keep], uv[keep], q0, p0, v0)
+    assert n == C - 1 and np.array_equal(B[6], before[6]) and not np.array_equal(B[5], before[5])
+    assert v0.all() and v.all() and e[v > 0].mean() < 0.1 * e0[v0 > 0].mean()
+
+
+def test_filter_bad_poses(oracle_factory):
+    """PoseEstimator::FilterBadPoses (pose_estimator.cc:238-261) -- host logic, identical in the product library and the oracle."""
+    from openimucameracalibrator_b200 import calibrator
+    p = np.array([[0, 0, 0.40], [0, 0, 0.45], [0, 0, -0.40], [0, 0, 0.90], [0, 0, 0.41], [5, 5, 0.0]])
+    valid = [1, 1, 1, 1, 1, 0]
+    expect = [1, 1, 0, 0, 1, 0]                                       # median of the valid heights 0.41: |z - 0.41| > 0.41 drops -0.40 and 0.90
+    assert oracle_factory().filter_bad_poses(p, valid).tolist() == expect
+    h = capi.CApi(calibrator.load_library(), "icc_", -1)
+    assert h.filter_bad_poses(p, valid).tolist() == expect
+    assert h.filter_bad_poses(p[:2], [0, 0]).tolist() == [0, 0]
+
+
+@pytest.mark.gpu
+def test_gpu_board_point_optimisation_matches_oracle(oracle_factory, gpu_factory):
+    model, k = CASES[4]
+    board, off, ids, uv, q_true, p_true = _scene(model, k, n_frames=60, seed=4, noise_px=0.1)
+    uv[off[9] + 20] += 40.0
+    bad = _perturbed(board, seed=1)
+    o, g = _setup(oracle_factory(), model, k, bad), _setup(gpu_factory(), model, k, bad)
+    qo, po, eo, vo = o.estimate_board_poses(off, ids, uv)
+    qg, pg, eg, vg = g.estimate_board_poses(off, ids, uv)
+    ro = o.optimize_board_points(off, ids, uv, qo, po, vo)
+    rg = g.optimize_board_points(off, ids, uv, qg, pg, vg)
+    assert rg[5] == ro[5] == board.shape[0] and (rg[3] == ro[3]).all() and ro[3].all()
+    assert np.abs(rg[4] - ro[4]).max() < 1e-8 and np.abs(rg[1] - ro[1]).max() < 1e-7 and _qdiff(rg[0], ro[0]).max() < 1e-7
+    assert np.abs(rg[2] - ro[2]).max() < 1e-9 and rg[2].mean() < 0.5 * eg.mean()
+    assert np.array_equal(g.get_board_points(), rg[4])
+    # exact data: a fixed point of the GPU path too; refine-only poses == a fresh estimate
+    board, off, ids, uv, q_true, p_true = _scene(model, k, n_frames=40, seed=6)
+    g = _setup(gpu_factory(), model, k, board)
+    q, p, e, v, B, n = g.optimize_board_points(off, ids, uv, q_true, p_true, np.ones(40, np.int32))
+    assert n == board.shape[0] and np.abs(B[:, :3] - board[:, :3]).max() < 1e-10 and np.abs(p - p_true).max() < 1e-9

@@ -1386,6 +1386,7 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, 
     PoseProblem PQ; memset(&PQ, 0, sizeof PQ);
     PQ.model = CAM_PINHOLE; PQ.n_frames = nv; PQ.n_points = np; PQ.min_points = 6;
     PQ.board = d_board.p; PQ.f_off = d_off.p; PQ.pid = d_pid.p; PQ.thresh_sq = 1e300; PQ.max_err = 1e300;   // every corner takes part
+    PQ.lm_rel_tol = 1e-6;                                                                                  // these poses only start the bundle adjustment
     DevBuf<double2> d_xy; DevBuf<unsigned char> d_use; DevBuf<double> d_f2, d_q, d_p, d_e; DevBuf<int> d_ok, d_valid;
     CU(d_xy.alloc(std::max(1, nc))); CU(d_use.alloc(std::max(1, nc))); CU(d_ok.alloc(std::max(1, nc)));
     if (need_focal) {

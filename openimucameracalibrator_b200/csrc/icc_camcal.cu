@@ -7,12 +7,13 @@
 //
 // Mapping to the machine.  The normal equations are an arrow: 6x6 pose blocks on the diagonal, a border of <= 10 intrinsics.
 //   camcal_accumulate_kernel : one WARP per view.  Each lane evaluates one corner (projection + closed-form 2x3 and 2x10
-//       Jacobians of icc_camera.cuh, Huber weight), writes its two weighted rows [J_pose | J_intr | r] (17 columns) into the
-//       warp's shared-memory tile; after every 32 corners the 153 entries of the symmetric 17x17 product are accumulated, five per
-//       lane, straight from the tile (J^T J, J^T r and r^T r in one pass).  The view's block goes to HBM (coalesced), its
-//       intrinsics part is summed into the global system with RED.ADD.F64.
+//       Jacobians of icc_camera.cuh, Huber weight) and writes its weighted rows [J_pose | J_intr | r] (17 columns, padded to three
+//       8-column blocks) into the warp's shared-memory tile -- x rows, then y rows; each half is folded into the symmetric product
+//       with FP64 tensor-core MMAs (mma.sync m8n8k4: 6 block products per 4 rows, the accumulator fragments stay in registers for
+//       the whole view), so J^T J, J^T r and r^T r come out of one contraction.  The view's 17x17 block goes to HBM, its intrinsics
+//       part is summed into the global system with RED.ADD.F64.
 //   camcal_reduce_kernel     : one thread per view: damped 6x6 Cholesky, Y = A^-1 [H_pk | g_p], Schur complement of the view
-//       onto the intrinsics, warp-reduced and added to the reduced 10x10 system.
+//       onto the intrinsics, summed over the CTA through shared memory and added to the reduced 10x10 system.
 //   camcal_solve_kernel      : the reduced system (<= 10 unknowns) by Cholesky, intrinsics step, candidate intrinsics.
 //   camcal_update_kernel     : back-substitution of every view's pose step, candidate poses, step / model-decrease sums.
 // The host only sequences these launches and applies Ceres' trust-region logic to eight scalars per iteration (icc_api.cu).
@@ -27,8 +28,6 @@ void count_launch();
 
 namespace {
 
-constexpr int LDR = 65;   // tile row stride in doubles (64 rows + 1: column starts fall on distinct banks)
-
 ICC_D double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -41,14 +40,37 @@ ICC_D void atomic_max_nonneg(double* addr, double v) {   // v >= 0: the bit patt
   atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+ICC_D void mma_f64(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+constexpr int CC_NB = 3, CC_TCOLS = 8 * CC_NB, CC_NACC = CC_NB * (CC_NB + 1) / 2;
+constexpr int LDT = 36;   // tile rows per column (32 + 4 pad: stride = 4 mod 16 => conflict-free fragment loads)
+
+// acc += T^T T over rows [0, 4 nsteps) of the column-major tile (upper block triangle of the 3 x 3 blocks of 8 columns)
+ICC_D void syrk_tile(const double* __restrict__ T, int nsteps, double (&acc)[CC_NACC][2]) {
+  const int lane = threadIdx.x & 31;
+  const double* base = T + (lane >> 2) * LDT + (lane & 3);
+  for (int s = 0; s < nsteps; ++s) {
+    double f[CC_NB];
+#pragma unroll
+    for (int b = 0; b < CC_NB; ++b) f[b] = base[(8 * b) * LDT + 4 * s];
+    int idx = 0;
+#pragma unroll
+    for (int bi = 0; bi < CC_NB; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < CC_NB; ++bj) { mma_f64(acc[idx], f[bi], f[bj]); ++idx; }
+  }
+}
+
 template <bool JAC>
 __global__ void __launch_bounds__(128) camcal_accumulate_kernel(CamCalProblem Q, CamCalState S, double* __restrict__ blocks, double* __restrict__ sys,
                                                                double* __restrict__ cost_out, double* __restrict__ view_err) {
-  __shared__ double tile_all[JAC ? 4 * CC_COLS * LDR : 1];
+  __shared__ double tile_all[JAC ? 4 * CC_TCOLS * LDT : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * 4 + warp;
   if (slot >= Q.n_active) return;
-  double* tile = tile_all + (JAC ? warp * CC_COLS * LDR : 0);
+  double* tile = tile_all + (JAC ? warp * CC_TCOLS * LDT : 0);
+  if (JAC) { for (int i = lane; i < CC_TCOLS * LDT; i += 32) tile[i] = 0.0; __syncwarp(); }   // the padding columns 17..23 stay zero
   const int v = Q.active[slot];
   const int c0 = Q.f_off[v], c1 = Q.f_off[v + 1];
   const Q4 q = q4(S.q[4 * v], S.q[4 * v + 1], S.q[4 * v + 2], S.q[4 * v + 3]);
@@ -56,20 +78,13 @@ __global__ void __launch_bounds__(128) camcal_accumulate_kernel(CamCalProblem Q,
   double k[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) k[i] = S.k[i];
-  int ei[5], ej[5];
-  double acc[5];
-  if (JAC) {
+  double acc[CC_NACC][2];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) {
-      int e = lane + 32 * t, i = 0;
-      if (e >= CC_PACK) e = CC_PACK - 1;
-      while (e >= CC_COLS - i) { e -= CC_COLS - i; ++i; }
-      ei[t] = i; ej[t] = i + e; acc[t] = 0.0;
-    }
-  }
+  for (int i = 0; i < CC_NACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
   double cost = 0.0, esum = 0.0;
   for (int base = c0; base < c1; base += 32) {
     const int c = base + lane;
+    const int nact = min(32, c1 - base);
     double rx[CC_COLS], ry[CC_COLS];
     if (JAC) {
 #pragma unroll
@@ -108,30 +123,39 @@ __global__ void __launch_bounds__(128) camcal_accumulate_kernel(CamCalProblem Q,
       }
     }
     if (JAC) {
+      const int nsteps = (nact + 3) >> 2;
 #pragma unroll
-      for (int i = 0; i < CC_COLS; ++i) { tile[i * LDR + lane] = rx[i]; tile[i * LDR + 32 + lane] = ry[i]; }
+      for (int i = 0; i < CC_COLS; ++i) tile[i * LDT + lane] = rx[i];
+      __syncwarp();
+      syrk_tile(tile, nsteps, acc);
       __syncwarp();
 #pragma unroll
-      for (int t = 0; t < 5; ++t) {
-        const double* a = tile + ei[t] * LDR; const double* b = tile + ej[t] * LDR;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-        for (int r = 0; r < 64; r += 2) { s0 = fma(a[r], b[r], s0); s1 = fma(a[r + 1], b[r + 1], s1); }
-        acc[t] += s0 + s1;
-      }
+      for (int i = 0; i < CC_COLS; ++i) tile[i * LDT + lane] = ry[i];
+      __syncwarp();
+      syrk_tile(tile, nsteps, acc);
       __syncwarp();
     }
   }
   cost = wsum(cost); esum = wsum(esum);
   if (JAC) {
+    // fragment (bi, bj) of lane l holds entries (I, J), (I, J + 1) with I = 8 bi + l / 4, J = 8 bj + 2 (l % 4): keep the upper triangle
+    int idx = 0;
 #pragma unroll
-    for (int t = 0; t < 5; ++t) {
-      const int e = lane + 32 * t;
-      if (e < CC_PACK) {
-        blocks[(size_t)slot * CC_PACK + e] = acc[t];
-        if (ei[t] >= 6) atomicAdd(&sys[e], acc[t]);
+    for (int bi = 0; bi < CC_NB; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < CC_NB; ++bj) {
+        const int I = 8 * bi + (lane >> 2);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int J = 8 * bj + 2 * (lane & 3) + e;
+          if (I <= J && J < CC_COLS) {
+            const int o = pk(I, J);
+            blocks[(size_t)slot * CC_PACK + o] = acc[idx][e];
+            if (I >= 6 && acc[idx][e] != 0.0) atomicAdd(&sys[o], acc[idx][e]);
+          }
+        }
+        ++idx;
       }
-    }
     if (lane == 0) atomicAdd(&sys[CC_PACK], cost);
   } else if (lane == 0) {
     atomicAdd(cost_out, cost);
@@ -145,7 +169,8 @@ ICC_D double lm_damping(double hii, double s, double radius, double mind, double
   return fmin(fmax(s * s * hii, mind), maxd) / (radius * s * s);
 }
 
-__global__ void __launch_bounds__(128) camcal_reduce_kernel(CamCalProblem Q, const double* __restrict__ blocks, double* __restrict__ red, double* __restrict__ Y,
+constexpr int RED_THREADS = 64;
+__global__ void __launch_bounds__(RED_THREADS) camcal_reduce_kernel(CamCalProblem Q, const double* __restrict__ blocks, double* __restrict__ red, double* __restrict__ Y,
                                                            double* __restrict__ scale, int compute_scale, double radius, double mind, double maxd, double* __restrict__ scal) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
   const bool live = slot < Q.n_active && Q.pose_free;
@@ -223,17 +248,31 @@ __global__ void __launch_bounds__(128) camcal_reduce_kernel(CamCalProblem Q, con
     double* Yo = Y + (size_t)slot * CC_Y;
     for (int i = 0; i < CC_Y; ++i) Yo[i] = 0.0;
   }
-  // Schur complement of this view onto the intrinsics: -H_pk^T Y  (matrix and gradient part), reduced over the warp
+  // Schur complement of this view onto the intrinsics: -H_pk^T Y  (matrix and gradient part); the 65 sums of the CTA's views are
+  // formed through shared memory (one column per thread, then one thread per output), 65 RED.ADD.F64 per CTA
+  __shared__ double part[65][RED_THREADS + 1];
+  {
+    int o = 0;
 #pragma unroll
-  for (int a = 0; a < 10; ++a) {
+    for (int a = 0; a < 10; ++a) {
 #pragma unroll
-    for (int b = 0; b < 11; ++b) if (b >= a) {
-      double s = 0.0;
+      for (int b = 0; b < 11; ++b) if (b >= a) {
+        double sacc = 0.0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) s -= Hpk[i][a] * Yl[i][b];
-      s = wsum(s);
-      if (lane == 0 && s != 0.0) atomicAdd(&red[b < 10 ? pk10(a, b) : 55 + a], s);
+        for (int i = 0; i < 6; ++i) sacc -= Hpk[i][a] * Yl[i][b];
+        part[o][threadIdx.x] = sacc;
+        ++o;
+      }
     }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 65; o += RED_THREADS) {
+    double sacc = 0.0;
+    for (int t = 0; t < RED_THREADS; ++t) sacc += part[o][t];
+    // o enumerates (a, b >= a) row by row with b = 10 the gradient column
+    int a = 0, r = o; while (r >= 11 - a) { r -= 11 - a; ++a; }
+    const int b = a + r;
+    if (sacc != 0.0) atomicAdd(&red[b < 10 ? pk10(a, b) : 55 + a], sacc);
   }
   gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16)); gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
   gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4)); gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2)); gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
@@ -329,7 +368,7 @@ void launch_camcal_step(const CamCalProblem& Q, const CamCalState& cur, const Ca
                         double* scale, int compute_scale, double radius, double min_diag, double max_diag, double* dk, double* scal, cudaStream_t st) {
   if (Q.n_active <= 0) return;
   const int grid = (Q.n_active + 127) / 128;
-  camcal_reduce_kernel<<<grid, 128, 0, st>>>(Q, blocks, red, Y, scale, compute_scale, radius, min_diag, max_diag, scal);
+  camcal_reduce_kernel<<<(Q.n_active + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, st>>>(Q, blocks, red, Y, scale, compute_scale, radius, min_diag, max_diag, scal);
   count_launch();
   camcal_solve_kernel<<<1, 32, 0, st>>>(Q, cur, cand, sys, red, scale + 6 * (size_t)Q.n_active, compute_scale, radius, min_diag, max_diag, dk, scal);
   count_launch();

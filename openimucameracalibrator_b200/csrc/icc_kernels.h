@@ -93,6 +93,7 @@ struct PoseProblem {
   const double4* board; const int* f_off; const int* pid;
   double thresh_sq;            // squared normalised reprojection error of an inlier (pose_estimator.cc:100-101)
   double max_err;              // views above this mean error are dropped (pose_estimator.cc:181)
+  double lm_rel_tol;           // relative cost decrease that ends the refinement (0 selects 1e-15: poses pinned to ~1e-9; an initialiser can stop far earlier)
   int refine_only;             // 1: start from the poses already in q_wc / p_wc (valid views only), no homography (OptimizeAllPoses, :226-236)
 };
 void launch_unproject(int model, const double* intr10, int n, const double2* uv, double2* xy, int* ok, cudaStream_t st);

@@ -194,7 +194,7 @@ ICC_D void pose_refine(const PoseProblem& Q, const double2* xy, const unsigned c
     if (Sn.cost < cost) {
       const double dec = cost - Sn.cost;
       q = qn; t = tn; cost = Sn.cost; lambda = fmax(lambda * 0.1, 1e-12);
-      if (dec <= 1e-15 * cost || step2 < 1e-28) break;
+      if (dec <= (Q.lm_rel_tol > 0.0 ? Q.lm_rel_tol : 1e-15) * cost || step2 < 1e-28) break;
       pose_system(Q, xy, use, c0, c1, zref, q, t, S, true);
     } else {
       if (step2 < 1e-28) break;

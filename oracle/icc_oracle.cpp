@@ -91,6 +91,7 @@ struct Oracle {
   std::vector<int> perm;      // canonical -> solver
   int n_knot_dims = 0, n_border = 0, kd = 0;
   int jac_evals = 0, cost_evals = 0;
+  double pose_rel_tol = 1e-15;     // stopping tolerance of the per-view pose refinement (the camera calibrator's initialiser loosens it)
 };
 
 int nknots(const std::vector<double>& v, int dim) { return int(v.size()) / dim; }
@@ -1041,7 +1042,7 @@ double pose_cost(const std::vector<PoseObs>& ob, const Qd& R, const Vd& t) {
   }
   return c;
 }
-void pose_gauss_newton(const std::vector<PoseObs>& ob, Qd& R, Vd& t) {
+void pose_gauss_newton(const std::vector<PoseObs>& ob, Qd& R, Vd& t, double rel_tol = 1e-15) {
   double lambda = 1e-4, cost = pose_cost(ob, R, t);
   for (int it = 0; it < 100; ++it) {
     std::vector<double> H(36, 0.0), g(6, 0.0);
@@ -1066,7 +1067,7 @@ void pose_gauss_newton(const std::vector<PoseObs>& ob, Qd& R, Vd& t) {
     const Qd Rn = qnormalized(so3_mul(R, so3_exp(Vd{b[0], b[1], b[2]})));
     const Vd tn = t + Vd{b[3], b[4], b[5]};
     const double cn = pose_cost(ob, Rn, tn), step2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3] + b[4] * b[4] + b[5] * b[5];
-    if (cn < cost) { const double dec = cost - cn; R = Rn; t = tn; cost = cn; lambda = std::max(lambda * 0.1, 1e-12); if (dec <= 1e-15 * cost || step2 < 1e-28) break; }
+    if (cn < cost) { const double dec = cost - cn; R = Rn; t = tn; cost = cn; lambda = std::max(lambda * 0.1, 1e-12); if (dec <= rel_tol * cost || step2 < 1e-28) break; }
     else { if (step2 < 1e-28) break; lambda *= 10.0; if (lambda > 1e12) break; }
   }
 }
@@ -1161,11 +1162,11 @@ icc_status oracle_board_poses(Oracle& o, int nf, const int32_t* off, const int32
     R = quat_from_cols(r1, r2, r3);
     }
     for (PoseObs& p : ob) p.Z -= zref;
-    pose_gauss_newton(ob, R, t);
+    pose_gauss_newton(ob, R, t, o.pose_rel_tol);
     std::vector<PoseObs> in;
     for (const PoseObs& p : ob) { const Vd Pc = so3_act(R, Vd{p.X, p.Y, p.Z}) + t; const double r0 = Pc.x / Pc.z - p.x, r1e = Pc.y / Pc.z - p.y; if (Pc.z > 0.0 && r0 * r0 + r1e * r1e < thresh_sq) in.push_back(p); }
     if (in.size() < 6) continue;
-    if (in.size() != ob.size()) pose_gauss_newton(in, R, t);
+    if (in.size() != ob.size()) pose_gauss_newton(in, R, t, o.pose_rel_tol);
     double e = 0; for (const PoseObs& p : in) { const Vd Pc = so3_act(R, Vd{p.X, p.Y, p.Z}) + t; e += std::hypot(Pc.x / Pc.z - p.x, Pc.y / Pc.z - p.y); }
     e /= (double)in.size();
     const Vd tf = t - so3_act(R, Vd{0.0, 0.0, zref});
@@ -1700,7 +1701,9 @@ icc_status icco_calibrate_camera(void* h, int model, int W, int Hh, int nv, cons
     const double kp[10] = {f0, 1.0, 0.0, cx0, cy0, 0.0, 0.0, 0.0, 0.0, 0.0};
     orc.model = 0; orc.n_intr = 7; memcpy(orc.intr, kp, sizeof kp); orc.width = W; orc.height = Hh;
     std::vector<double> e(nv);
+    orc.pose_rel_tol = 1e-6;   // these poses only start the bundle adjustment
     icco_estimate_board_poses(h, nv, off, ids, uv, 1e300, 6, q0.data(), p0.data(), e.data(), ok0.data());
+    orc.pose_rel_tol = 1e-15;
     orc.model = m_save; orc.n_intr = n_save; orc.width = w_save; orc.height = h_save; memcpy(orc.intr, k_save, sizeof k_save);
   } else {
     memcpy(q0.data(), q_init, 4 * (size_t)nv * sizeof(double)); memcpy(p0.data(), p_init, 3 * (size_t)nv * sizeof(double));

@@ -109,6 +109,14 @@ struct HostBuf {
   const T* begin() const { return p; } const T* end() const { return p + n; }
 };
 
+// Bump allocator over one page-locked block: the many small arrays a job uploads (frame tables, work lists, knots) are staged here
+// and copied asynchronously, instead of one blocking pageable cudaMemcpy each.  reset() only after the stream has drained.
+struct PinnedArena {
+  HostBuf<unsigned char> buf; size_t used = 0;
+  void reset(size_t capacity, bool pin) { if (buf.size() < capacity) buf.resize(capacity, pin); used = 0; }
+  void* take(size_t bytes) { const size_t o = (used + 255) & ~size_t(255); if (o + bytes > buf.size()) return nullptr; used = o + bytes; return buf.data() + o; }
+};
+
 struct StateBufs {
   DevBuf<double4> so3, r3, ba, bg; DevBuf<double> glob;
   DeviceState view() const { DeviceState s; s.so3 = so3.p; s.r3 = r3.p; s.ba = ba.p; s.bg = bg.p; s.glob = glob.p; return s; }
@@ -153,6 +161,7 @@ struct icc_handle {
   DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
   DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
   DevBuf<double> d_ne, d_scale, d_ws, d_delta, d_scal, d_res;
+  PinnedArena arena;        // staging of the small uploads of BatchInitSpline
   DeviceProblem P;
   bool state_dirty_host = false;   // device state newer than host mirror
   // ---- active set ------------------------------------------------------------------------------------------------
@@ -227,10 +236,27 @@ std::vector<double4> pad4(const std::vector<double>& v, int dim) {
   return o;
 }
 
-icc_status upload_state(icc_handle* h, int which) {
+// v -> d through the handle's staging arena (asynchronous on the handle's stream); falls back to the blocking copy when the arena is full
+template <class T>
+cudaError_t upload_staged(icc_handle* h, DevBuf<T>& d, const std::vector<T>& v) {
+  cudaError_t e = d.alloc(v.size()); if (e != cudaSuccess || v.empty()) return e;
+  const size_t bytes = v.size() * sizeof(T);
+  void* stage = h->arena.take(bytes);
+  if (!stage) return cudaMemcpy(d.p, v.data(), bytes, cudaMemcpyHostToDevice);
+  memcpy(stage, v.data(), bytes);
+  return cudaMemcpyAsync(d.p, stage, bytes, cudaMemcpyHostToDevice, h->stream);
+}
+
+icc_status upload_state(icc_handle* h, int which, bool staged = false) {
   StateBufs& s = h->st[which];
-  CU(s.so3.upload(pad4(h->so3, 4))); CU(s.r3.upload(pad4(h->r3, 3))); CU(s.ba.upload(pad4(h->ba, 3))); CU(s.bg.upload(pad4(h->bg, 3)));
   std::vector<double> g(h->glob, h->glob + G_COUNT);
+  if (staged) {
+    CU(upload_staged(h, s.so3, pad4(h->so3, 4))); CU(upload_staged(h, s.r3, pad4(h->r3, 3))); CU(upload_staged(h, s.ba, pad4(h->ba, 3))); CU(upload_staged(h, s.bg, pad4(h->bg, 3)));
+    CU(upload_staged(h, s.glob, g));
+    return ICC_OK;
+  }
+  CU(cudaStreamSynchronize(h->stream));   // a staged upload of the same buffers may still be in flight
+  CU(s.so3.upload(pad4(h->so3, 4))); CU(s.r3.upload(pad4(h->r3, 3))); CU(s.ba.upload(pad4(h->ba, 3))); CU(s.bg.upload(pad4(h->bg, 3)));
   CU(s.glob.upload(g));
   return ICC_OK;
 }
@@ -762,15 +788,18 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   h->cur_flags = -1; h->initialised = true; h->cur = 0; h->state_dirty_host = false;
   if (h->device < 0) return ICC_OK;
   CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
+  h->arena.reset((size_t)(1 << 16) + 64 * (size_t)nf + 48 * (size_t)(nf + h->used_n / 32 + 64) + 96 * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
+                 + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
   {
     std::vector<double4> board(h->points.size() / 4);
     // hnormalized(T^-1 X_h) of the functor (residuals.h:357-362) == T^-1 (X / w): the division is done once here
     for (size_t i = 0; i < board.size(); ++i) { const double iw = 1.0 / h->points[4 * i + 3]; board[i] = make_double4(h->points[4 * i] * iw, h->points[4 * i + 1] * iw, h->points[4 * i + 2] * iw, 1.0); }
-    CU(h->d_board.upload(board)); P.board = h->d_board.p;
+    CU(upload_staged(h, h->d_board, board)); P.board = h->d_board.p;
     std::vector<int> off, s1, s2; std::vector<double> u1, u2;
     for (const auto& f : h->frames) { off.push_back(f.c0); s1.push_back(f.s_so3); s2.push_back(f.s_r3); u1.push_back(f.u_so3); u2.push_back(f.u_r3); }
     off.push_back(P.n_corners);
-    CU(h->d_f_off.upload(off)); CU(h->d_f_s_so3.upload(s1)); CU(h->d_f_s_r3.upload(s2)); CU(h->d_f_u_so3.upload(u1)); CU(h->d_f_u_r3.upload(u2));
+    CU(upload_staged(h, h->d_f_off, off)); CU(upload_staged(h, h->d_f_s_so3, s1)); CU(upload_staged(h, h->d_f_s_r3, s2)); CU(upload_staged(h, h->d_f_u_so3, u1)); CU(upload_staged(h, h->d_f_u_r3, u2));
     P.f_off = h->d_f_off.p; P.f_s_so3 = h->d_f_s_so3.p; P.f_s_r3 = h->d_f_s_r3.p; P.f_u_so3 = h->d_f_u_so3.p; P.f_u_r3 = h->d_f_u_r3.p;
     CU(h->d_uv.alloc(P.n_corners));   // (u, v) pairs are already laid out as double2
     CU(h->d_pid.alloc(P.n_corners));
@@ -788,12 +817,12 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     const int per_v = std::max(32, round32(P.n_corners / std::max(1, target_items)));
     std::vector<VisionWork> vw;
     for (int fi = 0; fi < P.n_frames; ++fi) for (int c = h->frames[fi].c0; c < h->frames[fi].c1; c += per_v) vw.push_back({fi, c, std::min(c + per_v, h->frames[fi].c1), 0});
-    CU(h->d_vwork.upload(vw)); P.vwork = h->d_vwork.p; P.n_vwork = (int)vw.size();
+    CU(upload_staged(h, h->d_vwork, vw)); P.vwork = h->d_vwork.p; P.n_vwork = (int)vw.size();
     const int per_i = std::max(32, round32(P.n_imu / std::max(1, target_items)));
     std::vector<ImuCell> iw;
     for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
-    CU(h->d_iwork.upload(iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
-    CU(h->d_cells.upload(h->cells)); P.cells = h->d_cells.p;
+    CU(upload_staged(h, h->d_iwork, iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
+    CU(upload_staged(h, h->d_cells, h->cells)); P.cells = h->d_cells.p;
     CU(h->d_imu_t.alloc(h->imu_used_st.size()));
     if (!h->imu_used_st.empty()) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->imu_used_st.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
@@ -805,8 +834,8 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     }
     P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
   }
-  icc_status s = upload_state(h, 0); if (s != ICC_OK) return s;
-  s = upload_state(h, 1); if (s != ICC_OK) return s;
+  icc_status s = upload_state(h, 0, true); if (s != ICC_OK) return s;
+  s = upload_state(h, 1, true); if (s != ICC_OK) return s;
   return ICC_OK;
 }
 
@@ -814,6 +843,11 @@ icc_status icc_set_known_gravity_dir(icc_handle* h, const double g[3]) {
   if (!h || !g) return ICC_ERR_INVALID_ARGUMENT;
   icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s;
   for (int d = 0; d < 3; ++d) h->glob[G_GRAV + d] = g[d];
+  if (h->device >= 0 && h->initialised) {   // only the globals block changed: one small staged copy instead of the whole state
+    CU(cudaSetDevice(h->device));
+    CU(upload_staged(h, h->st[h->cur].glob, std::vector<double>(h->glob, h->glob + G_COUNT)));
+    return ICC_OK;
+  }
   return push_state_to_device(h);
 }
 

@@ -313,6 +313,14 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int image_width, int i
                                 double* intrinsics /* 10 */, double* q_wc_xyzw, double* p_wc, double* view_reproj_error_px, int32_t* view_used,
                                 icc_camcal_summary* summary /* nullable */);
 
+/* ---- upstream: static IMU biases, the `--imu_bias_file` input of the hot CLI ------------------------------------------------------------
+ * python/get_imu_biases.py:36-53: gyroscope bias = mean of the gyroscope stream; accelerometer bias = mean of the accelerometer stream
+ * after removing gravity along the axis with the largest mean magnitude, gravity = gravity_const * sign(mean) stored as float32 there
+ * (np.zeros(..., dtype=np.float32), :43-44 -- the rounding is reproduced).  The two column sums are one reduction kernel on the GPU.
+ * Parity of this step is pinned by the reference's own Python (tests/golden/make_imu_bias_golden.py runs the unmodified script). */
+icc_status icc_estimate_imu_biases(icc_handle* h, int n, const double* accel_xyz, const double* gyro_xyz, double gravity_const,
+                                   double accl_bias[3], double gyro_bias[3]);
+
 /* Device blocks of destroyed handles are cached process-wide for the next job; this returns them to the CUDA driver. */
 void icc_trim_device_cache(void);
 

@@ -232,6 +232,15 @@ class CApi:
                    vt.size, _dp(vt), _dp(q), it.size, _dp(it), _dp(g), None if b is None else _dp(b), _dp(qo), C.byref(td), _dp(bo), C.byref(err), C.byref(iters))
         return dict(q_gyro_to_cam=qo, time_offset_s=td.value, gyro_bias=bo, error=err.value, iterations=iters.value)
 
+    # ---- upstream: static IMU biases (python/get_imu_biases.py:36-53) -----------------------------------------------------------------
+    def estimate_imu_biases(self, accel, gyro, gravity_const=9.81):
+        """-> (accl_bias[3], gyro_bias[3]) as written to the hot CLI's --imu_bias_file."""
+        a = _f64(accel).reshape(-1, 3); g = _f64(gyro).reshape(-1, 3)
+        assert a.shape == g.shape
+        ba, bg = np.zeros(3), np.zeros(3)
+        self._call("estimate_imu_biases", [C.c_int, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p], a.shape[0], _dp(a), _dp(g), float(gravity_const), _dp(ba), _dp(bg))
+        return ba, bg
+
     # ---- upstream row f2: spline error weighting (python/sew.py:knot_spacing_and_variance) ------------------------------------
     def spline_error_weighting(self, times_s, signal_xyz, quality, min_dt=0.0, max_dt=0.0, want_spectrum=False):
         """-> (knot_spacing, variance[, reference spectrum Xhat]); signal_xyz is (n, 3)."""

@@ -1662,6 +1662,29 @@ icc_status icc_calibrate_camera(icc_handle* h, int model, int W, int H, int nv, 
   return finish(true);
 }
 
+// ---- upstream: static IMU biases (python/get_imu_biases.py:36-53) -------------------------------------------------------------------
+icc_status icc_estimate_imu_biases(icc_handle* h, int n, const double* acc, const double* gyr, double gravity_const, double accl_bias[3], double gyro_bias[3]) {
+  if (!h || n <= 0 || !acc || !gyr || !accl_bias || !gyro_bias) return ICC_ERR_INVALID_ARGUMENT;
+  if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  CU(cudaSetDevice(h->device));
+  DevBuf<double> d_a, d_g, d_s;
+  CU(d_a.alloc(3 * (size_t)n)); CU(d_g.alloc(3 * (size_t)n)); CU(d_s.alloc(6));
+  CU(cudaMemcpyAsync(d_a.p, acc, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_g.p, gyr, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_imu_sums(n, d_a.p, d_g.p, d_s.p, h->sm_count, h->stream);
+  double s[6];
+  CU(cudaMemcpyAsync(s, d_s.p, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cudaGetLastError() != cudaSuccess) return fail(h, ICC_ERR_CUDA, "bias kernel failed");
+  double mean_a[3], mean_g[3];
+  for (int d = 0; d < 3; ++d) { mean_a[d] = s[d] / n; mean_g[d] = s[3 + d] / n; }
+  int ax = 0; for (int d = 1; d < 3; ++d) if (std::fabs(mean_a[d]) > std::fabs(mean_a[ax])) ax = d;          // :39-41 (first maximum)
+  const double sgn = mean_a[ax] > 0.0 ? 1.0 : (mean_a[ax] < 0.0 ? -1.0 : 0.0);
+  const double grav = (double)(float)(gravity_const * sgn);                                                     // float32 array (:43-44)
+  for (int d = 0; d < 3; ++d) { accl_bias[d] = mean_a[d] - (d == ax ? grav : 0.0); gyro_bias[d] = mean_g[d]; }   // :46, :49-50
+  return ICC_OK;
+}
+
 void icc_trim_device_cache(void) { block_cache().trim(); pinned_cache().trim(); }
 
 }  // extern "C"

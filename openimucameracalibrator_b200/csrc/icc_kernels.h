@@ -158,6 +158,8 @@ void launch_golden_section(const RotInitProblem& Q, double max_offset, int max_i
 int sew_fft_length(int N);      // power-of-two length of the Bluestein convolution
 void launch_sew_spectrum(int N, const double* signal /* N x 3 */, double* xhat /* N */, double* energy_sum, double* scratch /* 16 * sew_fft_length(N) doubles */, cudaStream_t st);
 void launch_sew_residual_energy(int N, const double* xhat, double fscale, double dt, double* out, int sm_count, cudaStream_t st);
+// column sums of the accelerometer / gyroscope streams (static bias estimate, python/get_imu_biases.py)
+void launch_imu_sums(int n, const double* acc, const double* gyr, double* out6, int sm_count, cudaStream_t st);
 int kernel_launch_count();
 
 }  // namespace icc

@@ -131,4 +131,33 @@ void launch_sew_residual_energy(int N, const double* xhat, double fscale, double
   residual_energy_kernel<<<g, 256, 0, st>>>(N, xhat, fscale, dt, out); count_launch();
 }
 
+// ---- static IMU biases (python/get_imu_biases.py:36-53): column sums of the accelerometer and gyroscope streams -------------------
+namespace {
+__global__ void __launch_bounds__(256) imu_sums_kernel(int n, const double* __restrict__ acc, const double* __restrict__ gyr, double* __restrict__ out /* 6 */) {
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    s[0] += acc[3 * i]; s[1] += acc[3 * i + 1]; s[2] += acc[3 * i + 2]; s[3] += gyr[3 * i]; s[4] += gyr[3 * i + 1]; s[5] += gyr[3 * i + 2];
+  }
+  __shared__ double sh[8][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double v = s[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) { double v = 0.0; for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x]; atomicAdd(&out[threadIdx.x], v); }
+}
+}  // namespace
+
+void launch_imu_sums(int n, const double* acc, const double* gyr, double* out6, int sm_count, cudaStream_t st) {
+  cudaMemsetAsync(out6, 0, 6 * sizeof(double), st);
+  if (n <= 0) return;
+  int g = (n + 255) / 256; if (g > 4 * sm_count) g = 4 * sm_count;
+  imu_sums_kernel<<<g, 256, 0, st>>>(n, acc, gyr, out6); count_launch();
+}
+
 }  // namespace icc
+

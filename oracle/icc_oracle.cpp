@@ -1796,6 +1796,17 @@ icc_status icco_calibrate_camera(void* h, int model, int W, int Hh, int nv, cons
   return finish(true);
 }
 
+// python/get_imu_biases.py:36-53 (TEST INFRASTRUCTURE): means by plain sequential sums, gravity removed on the dominant accelerometer axis
+icc_status icco_estimate_imu_biases(void* h, int n, const double* acc, const double* gyr, double gravity_const, double accl_bias[3], double gyro_bias[3]) {
+  long double sa[3] = {0, 0, 0}, sg[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) { sa[d] += acc[3 * i + d]; sg[d] += gyr[3 * i + d]; }
+  double ma[3], mg[3]; for (int d = 0; d < 3; ++d) { ma[d] = (double)(sa[d] / n); mg[d] = (double)(sg[d] / n); }
+  int ax = 0; for (int d = 1; d < 3; ++d) if (std::fabs(ma[d]) > std::fabs(ma[ax])) ax = d;
+  const float g32 = (float)(gravity_const * (ma[ax] > 0.0 ? 1.0 : (ma[ax] < 0.0 ? -1.0 : 0.0)));
+  for (int d = 0; d < 3; ++d) { accl_bias[d] = ma[d] - (d == ax ? (double)g32 : 0.0); gyro_bias[d] = mg[d]; }
+  return ICC_OK;
+}
+
 int icco_project(int model, const double* intr, const double* p3, double* px, int dispatch_fov) { return project<double>(model, intr, p3, px, dispatch_fov != 0) ? 1 : 0; }
 
 }  // extern "C"

@@ -93,9 +93,12 @@ int main(int argc, char** argv) {
     const Value& tj = tel.at("timestamps_ns");
     CHECK_MSG(tel.at("gyroscope").size() == tj.size() && tel.at("accelerometer").size() == tj.size(), "Telemetry should have the same amount of timestamps, accelerometer and gyroscope values.");
     std::vector<double> imu_t, acc, gyr;
+    const Value& tacc = tel.at("accelerometer"); const Value& tgyr = tel.at("gyroscope");
+    imu_t.reserve(tj.size()); acc.reserve(3 * tj.size()); gyr.reserve(3 * tj.size());
     for (size_t i = 0; i < tj.size(); ++i) {
       imu_t.push_back(tj.at(i).num() * NS_TO_S);
-      for (int d = 0; d < 3; ++d) { acc.push_back(tel.at("accelerometer").at(i).at(d).num()); gyr.push_back(tel.at("gyroscope").at(i).at(d).num()); }
+      const Value& ai = tacc.at(i); const Value& gi = tgyr.at(i);
+      for (int d = 0; d < 3; ++d) { acc.push_back(ai.at(d).num()); gyr.push_back(gi.at(d).num()); }
     }
     double t_offset_cam_s = 0.0;
     if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) t_offset_cam_s = tel.at("img_timestamps_ns").at(0).num() * NS_TO_S;

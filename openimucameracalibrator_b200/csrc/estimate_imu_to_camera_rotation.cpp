@@ -35,7 +35,8 @@ int main(int argc, char** argv) {
     const Value& tj = tel.at("timestamps_ns");
     if (tel.at("gyroscope").size() != tj.size()) { std::cerr << "Telemetry should have the same amount of timestamps and gyroscope values." << std::endl; return 1; }
     std::vector<double> imu_t, gyr;
-    for (size_t i = 0; i < tj.size(); ++i) { imu_t.push_back(tj.at(i).num() * 1e-9); for (int d = 0; d < 3; ++d) gyr.push_back(tel.at("gyroscope").at(i).at(d).num()); }
+    const Value& tgyr = tel.at("gyroscope");
+    for (size_t i = 0; i < tj.size(); ++i) { imu_t.push_back(tj.at(i).num() * 1e-9); const Value& gi = tgyr.at(i); for (int d = 0; d < 3; ++d) gyr.push_back(gi.at(d).num()); }
     double delta_t0_cam = 0.0;                       // app :80-86
     if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) delta_t0_cam = tel.at("img_timestamps_ns").at(0).num() * 1e-9;
     std::vector<double> view_t, q_cw;

@@ -25,21 +25,20 @@ using Object = std::map<std::string, Value>;   // sorted keys, like nlohmann::js
 using Array = std::vector<Value>;
 
 struct Value {
-  enum Type { Null, Bool, Int, Float, String, Arr, Obj } type = Null;
-  bool b = false;
-  int64_t i = 0;
-  double d = 0.0;
-  std::string s;
+  enum Type : uint8_t { Null, Bool, Int, Float, String, Arr, Obj } type = Null;
+  union { bool b; int64_t i; double d; };                 // scalar payload (most values of a telemetry / corner file are numbers)
+  std::shared_ptr<std::string> sp;                          // String
   std::shared_ptr<Array> a;
   std::shared_ptr<Object> o;
 
-  Value() {}
-  Value(bool v) : type(Bool), b(v) {}
+  Value() : i(0) {}
+  Value(bool v) : type(Bool), i(0) { b = v; }
   Value(int v) : type(Int), i(v) {}
   Value(int64_t v) : type(Int), i(v) {}
   Value(double v) : type(Float), d(v) {}
-  Value(const char* v) : type(String), s(v) {}
-  Value(const std::string& v) : type(String), s(v) {}
+  Value(const char* v) : type(String), i(0), sp(std::make_shared<std::string>(v)) {}
+  Value(const std::string& v) : type(String), i(0), sp(std::make_shared<std::string>(v)) {}
+  Value(std::string&& v) : type(String), i(0), sp(std::make_shared<std::string>(std::move(v))) {}
   static Value array() { Value v; v.type = Arr; v.a = std::make_shared<Array>(); return v; }
   static Value object() { Value v; v.type = Obj; v.o = std::make_shared<Object>(); return v; }
 
@@ -50,8 +49,8 @@ struct Value {
   size_t size() const { return type == Arr ? a->size() : type == Obj ? o->size() : 0; }
   double num() const { if (type == Int) return double(i); if (type == Float) return d; throw std::runtime_error("json: value is not a number"); }
   int64_t integer() const { if (type == Int) return i; if (type == Float) return int64_t(d); throw std::runtime_error("json: value is not a number"); }
-  const std::string& str() const { if (type != String) throw std::runtime_error("json: value is not a string"); return s; }
-  const Value& at(const std::string& k) const { if (type != Obj || !o->count(k)) throw std::runtime_error("json: missing key '" + k + "'"); return o->at(k); }
+  const std::string& str() const { if (type != String) throw std::runtime_error("json: value is not a string"); return *sp; }
+  const Value& at(const std::string& k) const { if (type == Obj) { const auto it = o->find(k); if (it != o->end()) return it->second; } throw std::runtime_error("json: missing key '" + k + "'"); }
   const Value& at(size_t k) const { if (type != Arr || k >= a->size()) throw std::runtime_error("json: array index out of range"); return (*a)[k]; }
   Value& operator[](const std::string& k) { if (type == Null) { type = Obj; o = std::make_shared<Object>(); } if (type != Obj) throw std::runtime_error("json: not an object"); return (*o)[k]; }
   void push_back(const Value& v) { if (type == Null) { type = Arr; a = std::make_shared<Array>(); } a->push_back(v); }
@@ -85,7 +84,7 @@ class TextParser {
       ws(); if (p_ >= t_.size() || t_[p_] != '"') fail("expected key");
       std::string k = string(); ws();
       if (p_ >= t_.size() || t_[p_] != ':') fail("expected ':'");
-      ++p_; (*v.o)[k] = value(); ws();
+      ++p_; v.o->insert_or_assign(v.o->end(), std::move(k), value()); ws();
       if (p_ < t_.size() && t_[p_] == ',') { ++p_; continue; }
       if (p_ < t_.size() && t_[p_] == '}') { ++p_; return v; }
       fail("expected ',' or '}'");
@@ -121,16 +120,22 @@ class TextParser {
     if (p_ < t_.size() && (t_[p_] == '-' || t_[p_] == '+')) ++p_;
     while (p_ < t_.size() && (isdigit((unsigned char)t_[p_]) || t_[p_] == '.' || t_[p_] == 'e' || t_[p_] == 'E' || t_[p_] == '-' || t_[p_] == '+')) { if (t_[p_] == '.' || t_[p_] == 'e' || t_[p_] == 'E') is_float = true; ++p_; }
     if (p_ == s) fail("unexpected character");
-    const std::string tok = t_.substr(s, p_ - s);
-    if (!is_float) { try { return Value(int64_t(std::stoll(tok))); } catch (...) { is_float = true; } }
-    return Value(std::stod(tok));
+    const char* first = t_.data() + s + (t_[s] == '+' ? 1 : 0); const char* last = t_.data() + p_;
+    if (!is_float) { int64_t iv = 0; const auto r = std::from_chars(first, last, iv); if (r.ec == std::errc() && r.ptr == last) return Value(iv); }
+    double dv = 0.0; const auto r = std::from_chars(first, last, dv);
+    if (r.ec == std::errc() && r.ptr == last) return Value(dv);
+    return Value(std::stod(std::string(first, last)));      // out-of-range literals etc.: the C library decides, as before
   }
 };
 
 inline std::string read_file(const std::string& path, bool binary = false) {
   std::ifstream f(path, binary ? std::ios::binary : std::ios::in);
   if (!f.is_open()) throw std::runtime_error("could not open " + path);
-  std::stringstream ss; ss << f.rdbuf(); return ss.str();
+  f.seekg(0, std::ios::end); const std::streamoff n = f.tellg(); f.seekg(0, std::ios::beg);
+  std::string out;
+  if (n > 0) { out.resize((size_t)n); f.read(&out[0], n); out.resize((size_t)f.gcount()); }
+  else { std::stringstream ss; ss << f.rdbuf(); out = ss.str(); }   // not seekable
+  return out;
 }
 inline Value parse_text(const std::string& text) { return TextParser(text).parse(); }
 inline Value load_json(const std::string& path) { return parse_text(read_file(path)); }
@@ -148,7 +153,7 @@ inline void dump(const Value& v, std::string& out, int indent, int depth) {
     case Value::Bool: out += v.b ? "true" : "false"; break;
     case Value::Int: out += std::to_string(v.i); break;
     case Value::Float: out += number_to_string(v.d); break;
-    case Value::String: out += '"'; for (char c : v.s) { if (c == '"' || c == '\\') { out += '\\'; out += c; } else if (c == '\n') out += "\\n"; else out += c; } out += '"'; break;
+    case Value::String: out += '"'; for (char c : *v.sp) { if (c == '"' || c == '\\') { out += '\\'; out += c; } else if (c == '\n') out += "\\n"; else out += c; } out += '"'; break;
     case Value::Arr:
       if (v.a->empty()) { out += "[]"; break; }
       out += "[\n"; for (size_t k = 0; k < v.a->size(); ++k) { out += pad; dump((*v.a)[k], out, indent, depth + 1); if (k + 1 < v.a->size()) out += ","; out += "\n"; } out += pad0 + "]"; break;
@@ -195,8 +200,8 @@ class UbjsonParser {
         Value v = Value::object(); unsigned char et = 0; int64_t n = -1;
         if (peek() == '$') { ++p_; et = next(); if (next() != '#') fail("expected '#' after '$'"); n = integer(next()); }
         else if (peek() == '#') { ++p_; n = integer(next()); }
-        if (n >= 0) { for (int64_t k = 0; k < n; ++k) { std::string key = raw_string(); (*v.o)[key] = value(et ? et : next()); } }
-        else { while (peek() != '}') { std::string key = raw_string(); (*v.o)[key] = value(next()); } ++p_; }
+        if (n >= 0) { for (int64_t k = 0; k < n; ++k) { std::string key = raw_string(); v.o->insert_or_assign(v.o->end(), std::move(key), value(et ? et : next())); } }
+        else { while (peek() != '}') { std::string key = raw_string(); v.o->insert_or_assign(v.o->end(), std::move(key), value(next())); } ++p_; }
         return v; }
       default: fail(std::string("unknown type marker '") + (char)t + "'");
     }

@@ -30,7 +30,7 @@ icccli::Flags default_flags() {
   f.str = {{"telemetry_json", ""}, {"input_pose_dataset", ""}, {"input_corners", ""}, {"camera_calibration_json", ""},
     {"gyro_to_cam_initial_calibration", ""}, {"imu_intrinsics", ""}, {"imu_bias_file", ""}, {"spline_error_weighting_json", ""}, {"output_path", ""},
     {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}};
-  f.boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}};
+  f.boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}, {"json_selftest", false}};
   f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}};
   return f;
 }
@@ -57,10 +57,61 @@ Value xyz(double x, double y, double z) { Value v = Value::object(); v["x"] = Va
 
 }  // namespace
 
+// Result JSON (app :247-332) streamed through iccjson::Writer: `head` holds every key but the trajectory (all of them sort before it),
+// the trajectory object -- 100 k entries of six xyz objects for a 100 s sequence, ~90 MB of text -- is emitted straight from the arrays
+// in std::map<std::string> key order (lexicographic on the decimal timestamp; a repeated timestamp keeps the last sample), i.e. the bytes
+// nlohmann::json / the tree route would produce, without building 700 k tree nodes.
+static void write_result(iccjson::Writer& w, const Value& head, int n_used, const int64_t* t_ns, const double* ug, const double* gs, const double* gb,
+                         const double* ua, const double* as, const double* ab) {
+  auto xyz_at = [&](const char* k, const double* v, int i) { w.key(k); w.begin_object(); w.key("x"); w.value(v[3 * i]); w.key("y"); w.value(v[3 * i + 1]); w.key("z"); w.value(v[3 * i + 2]); w.end_object(); };
+  w.begin_object();
+  for (const auto& kv : *head.o) { w.key(kv.first); w.value(kv.second); }
+  if (n_used) {
+    std::vector<std::pair<std::string, int>> keys(n_used);
+    for (int i = 0; i < n_used; ++i) keys[i] = {std::to_string(t_ns[i]), i};
+    std::stable_sort(keys.begin(), keys.end(), [](const std::pair<std::string, int>& a, const std::pair<std::string, int>& b) { return a.first < b.first; });
+    w.key("trajectory"); w.begin_object();
+    for (int k = 0; k < n_used; ++k) {
+      if (k + 1 < n_used && keys[k + 1].first == keys[k].first) continue;
+      const int i = keys[k].second;
+      w.key(keys[k].first); w.begin_object();
+      xyz_at("accl_bias", ab, i); xyz_at("accl_imu", ua, i); xyz_at("accl_spline", as, i); xyz_at("gyro_bias", gb, i); xyz_at("gyro_imu", ug, i); xyz_at("gyro_spline", gs, i);
+      w.end_object();
+    }
+    w.end_object();
+  }
+  w.end_object();
+}
+
+// --json_selftest: the streamed result equals the tree route byte for byte (random samples incl. repeated and unordered timestamps)
+static int json_selftest() {
+  const int n = 257;
+  std::vector<int64_t> t(n); std::vector<double> a[6]; for (auto& v : a) v.resize(3 * n);
+  uint64_t s = 88172645463325252ull; auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  for (int i = 0; i < n; ++i) { t[i] = (int64_t)(rnd() % 5000) * 1000003; for (auto& v : a) for (int d = 0; d < 3; ++d) v[3 * i + d] = (double)(int64_t)(rnd() % 2000001 - 1000000) * (i % 7 == 0 ? 1.0 : 1e-6); }
+  t[5] = t[4]; t[100] = 7;
+  Value head = Value::object(); head["final_reproj_error"] = Value(0.25); head["q_i_c"] = xyz(1, 2, 3); head["time_offset_imu_to_cam_s"] = Value(-0.0123);
+  Value tree = head, traj = Value::object();
+  tree = Value::object(); for (const auto& kv : *head.o) tree[kv.first] = kv.second;
+  for (int i = 0; i < n; ++i) {
+    Value e = Value::object();
+    e["gyro_imu"] = xyz(a[0][3 * i], a[0][3 * i + 1], a[0][3 * i + 2]); e["gyro_spline"] = xyz(a[1][3 * i], a[1][3 * i + 1], a[1][3 * i + 2]); e["gyro_bias"] = xyz(a[2][3 * i], a[2][3 * i + 1], a[2][3 * i + 2]);
+    e["accl_imu"] = xyz(a[3][3 * i], a[3][3 * i + 1], a[3][3 * i + 2]); e["accl_spline"] = xyz(a[4][3 * i], a[4][3 * i + 1], a[4][3 * i + 2]); e["accl_bias"] = xyz(a[5][3 * i], a[5][3 * i + 1], a[5][3 * i + 2]);
+    traj[std::to_string(t[i])] = e;
+  }
+  tree["trajectory"] = traj;
+  std::string streamed;
+  { iccjson::Writer w(4, &streamed); write_result(w, head, n, t.data(), a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data()); }
+  const bool same = streamed == iccjson::dump(tree, 4);
+  std::cout << (same ? "json selftest ok: " : "json selftest FAILED: ") << streamed.size() << " bytes" << std::endl;
+  return same ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   icccli::Flags F = default_flags();
   try { icccli::parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
   const double S_TO_NS = 1e9, US_TO_S = 1e-6, S_TO_US = 1e6, NS_TO_S = 1e-9;
+  if (F.boolean["json_selftest"]) return json_selftest();
   try {
     // ---- inputs (app :93-184) ---------------------------------------------------------------------------------------
     const bool have_poses = !F.str["input_pose_dataset"].empty();
@@ -240,15 +291,13 @@ int main(int argc, char** argv) {
     std::vector<double> gs(3 * (size_t)n_used), as(3 * (size_t)n_used), gb(3 * (size_t)n_used), ab(3 * (size_t)n_used);
     std::vector<int32_t> valid(n_used);
     if (n_used) ICC(icc_eval_trajectory(h, n_used, t_ns.data(), gs.data(), as.data(), gb.data(), ab.data(), nullptr, nullptr, valid.data()));
-    Value traj = Value::object();
-    for (int i = 0; i < n_used; ++i) {
-      Value e = Value::object();
-      e["gyro_imu"] = xyz(ug[3 * i], ug[3 * i + 1], ug[3 * i + 2]); e["gyro_spline"] = xyz(gs[3 * i], gs[3 * i + 1], gs[3 * i + 2]); e["gyro_bias"] = xyz(gb[3 * i], gb[3 * i + 1], gb[3 * i + 2]);
-      e["accl_imu"] = xyz(ua[3 * i], ua[3 * i + 1], ua[3 * i + 2]); e["accl_spline"] = xyz(as[3 * i], as[3 * i + 1], as[3 * i + 2]); e["accl_bias"] = xyz(ab[3 * i], ab[3 * i + 1], ab[3 * i + 2]);
-      traj[std::to_string(t_ns[i])] = e;
+    {
+      CHECK_MSG(out.o->empty() || std::prev(out.o->end())->first < std::string("trajectory"), "result keys must sort before the trajectory");
+      FILE* fp = fopen(F.str["result_output_json"].c_str(), "wb");
+      CHECK_MSG(fp != nullptr, "could not write " << F.str["result_output_json"]);
+      { iccjson::Writer w(4, fp); write_result(w, out, n_used, t_ns.data(), ug.data(), gs.data(), gb.data(), ua.data(), as.data(), ab.data()); }
+      fputc('\n', fp); fclose(fp);
     }
-    if (n_used) out["trajectory"] = traj;
-    { std::ofstream f(F.str["result_output_json"]); CHECK_MSG(f.is_open(), "could not write " << F.str["result_output_json"]); f << iccjson::dump(out, 4) << std::endl; }
 
     // ---- PLY files of the spline poses and of the input poses (app :335-364) -------------------------------------------
     std::vector<double> cam_ts(frame_t); std::sort(cam_ts.begin(), cam_ts.end());

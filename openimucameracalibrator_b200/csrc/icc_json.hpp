@@ -146,25 +146,55 @@ inline std::string number_to_string(double v) {
   if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
   return s;
 }
-inline void dump(const Value& v, std::string& out, int indent, int depth) {
-  const std::string pad(indent * (depth + 1), ' '), pad0(indent * depth, ' ');
-  switch (v.type) {
-    case Value::Null: out += "null"; break;
-    case Value::Bool: out += v.b ? "true" : "false"; break;
-    case Value::Int: out += std::to_string(v.i); break;
-    case Value::Float: out += number_to_string(v.d); break;
-    case Value::String: out += '"'; for (char c : *v.sp) { if (c == '"' || c == '\\') { out += '\\'; out += c; } else if (c == '\n') out += "\\n"; else out += c; } out += '"'; break;
-    case Value::Arr:
-      if (v.a->empty()) { out += "[]"; break; }
-      out += "[\n"; for (size_t k = 0; k < v.a->size(); ++k) { out += pad; dump((*v.a)[k], out, indent, depth + 1); if (k + 1 < v.a->size()) out += ","; out += "\n"; } out += pad0 + "]"; break;
-    case Value::Obj: {
-      if (v.o->empty()) { out += "{}"; break; }
-      out += "{\n"; size_t k = 0;
-      for (const auto& kv : *v.o) { out += pad + "\"" + kv.first + "\": "; dump(kv.second, out, indent, depth + 1); if (++k < v.o->size()) out += ","; out += "\n"; }
-      out += pad0 + "}"; break; }
+// Streaming writer with nlohmann::json::dump(indent) formatting: objects / arrays one member per line, "key": value, "{}" / "[]" when
+// empty.  dump(Value) below walks a tree through it; the CLI streams the (large) trajectory object through the same code without
+// building a tree, so both routes produce identical bytes.  With a FILE* sink the text is flushed in ~1 MB pieces.
+class Writer {
+ public:
+  explicit Writer(int indent, std::string* sink) : indent_(indent), str_(sink) {}
+  Writer(int indent, FILE* sink) : indent_(indent), file_(sink) { buf_.reserve(size_t(1) << 21); }
+  ~Writer() { flush(); }
+  void begin_object() { open('{'); }
+  void end_object() { close('}'); }
+  void begin_array() { open('['); }
+  void end_array() { close(']'); }
+  void key(const std::string& k) { member(); out() += '"'; out() += k; out() += "\": "; after_key_ = true; }
+  void value(double v) { element(); number(v); }
+  void value(int64_t v) { element(); char b[32]; const auto r = std::to_chars(b, b + sizeof b, v); out().append(b, r.ptr); }
+  void value(bool v) { element(); out() += v ? "true" : "false"; }
+  void null() { element(); out() += "null"; }
+  void value(const std::string& v) { element(); string(v); }
+  void value(const Value& v) {
+    switch (v.type) {
+      case Value::Null: null(); break;
+      case Value::Bool: value(v.b); break;
+      case Value::Int: value(v.i); break;
+      case Value::Float: value(v.d); break;
+      case Value::String: value(*v.sp); break;
+      case Value::Arr: begin_array(); for (const Value& e : *v.a) value(e); end_array(); break;
+      case Value::Obj: begin_object(); for (const auto& kv : *v.o) { key(kv.first); value(kv.second); } end_object(); break;
+    }
   }
-}
-inline std::string dump(const Value& v, int indent = 4) { std::string s; dump(v, s, indent, 0); return s; }
+  void flush() { if (file_ && !buf_.empty()) { fwrite(buf_.data(), 1, buf_.size(), file_); buf_.clear(); } }
+ private:
+  int indent_; std::string* str_ = nullptr; FILE* file_ = nullptr; std::string buf_;
+  std::vector<size_t> count_;   // members written so far, per open container
+  bool after_key_ = false;
+  std::string& out() { return str_ ? *str_ : buf_; }
+  void newline(size_t depth) { out() += '\n'; out().append(indent_ * depth, ' '); if (file_ && buf_.size() > (size_t(1) << 20)) flush(); }
+  void member() { if (!count_.empty()) { if (count_.back()++) out() += ','; newline(count_.size()); } }
+  void element() { if (after_key_) after_key_ = false; else member(); }     // a value after key() continues the line; array elements start one
+  void open(char c) { element(); out() += c; count_.push_back(0); }
+  void close(char c) { const size_t n = count_.back(); count_.pop_back(); if (n) newline(count_.size()); out() += c; }
+  void number(double v) {
+    if (!std::isfinite(v)) { out() += "null"; return; }   // nlohmann dumps non-finite numbers as null
+    char b[64]; const auto r = std::to_chars(b, b + sizeof b, v);
+    bool plain = true; for (const char* p = b; p != r.ptr; ++p) if (*p == '.' || *p == 'e' || *p == 'E' || *p == 'n') { plain = false; break; }
+    out().append(b, r.ptr); if (plain) out() += ".0";
+  }
+  void string(const std::string& v) { out() += '"'; for (char c : v) { if (c == '"' || c == '\\') { out() += '\\'; out() += c; } else if (c == '\n') out() += "\\n"; else out() += c; } out() += '"'; }
+};
+inline std::string dump(const Value& v, int indent = 4) { std::string s; { Writer w(indent, &s); w.value(v); } return s; }
 
 // ---- UBJSON (draft 12) --------------------------------------------------------------------------------------------
 class UbjsonParser {

@@ -296,3 +296,10 @@ def test_optimize_board_points_flags_of_both_tools(tmp_path):
     assert "board points" in out.stdout
     pd = json.load(open(pj))
     assert len(pd["views"]) == 40 and np.abs(np.array([pd["tracks"][str(i)] for i in range(B.shape[0])]) - bent).max() > 1e-5
+
+
+def test_result_writer_streams_the_same_bytes_as_the_tree_route():
+    """The hot CLI streams the (large) trajectory object of the result JSON without building a tree; --json_selftest compares that
+    output with the generic tree dump byte for byte (unordered and repeated timestamps included)."""
+    out = subprocess.run([CLI, "--json_selftest"], capture_output=True, text=True)
+    assert out.returncode == 0 and "json selftest ok" in out.stdout, out.stdout + out.stderr

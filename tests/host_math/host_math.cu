@@ -1,0 +1,36 @@
+// Host-side test shim for the PRODUCT's __host__ __device__ math (icc_camera.cuh, icc_device_math.cuh): the very functions the CUDA
+// kernels inline, compiled for the CPU by nvcc so that the `-m "not gpu"` suite can check them (finite differences, oracle, known
+// answers) without a device.  Test infrastructure only; built by tests/test_host_device_math.py into tests/host_math/_build/.
+#include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
+
+using namespace icc;
+
+extern "C" {
+// project with both Jacobians: out = [u, v, J(6), Jk(20)], returns ok
+int hm_project(int model, const double* k, const double* p, int dispatch_fov, double* out) {
+  ProjK pk;
+  const Proj a = project_with_k(model, k, v3(p[0], p[1], p[2]), dispatch_fov != 0, &pk);
+  const Proj b = project(model, k, v3(p[0], p[1], p[2]), dispatch_fov != 0);
+  out[0] = a.u; out[1] = a.v;
+  for (int i = 0; i < 6; ++i) out[2 + i] = a.J[i];
+  for (int i = 0; i < 20; ++i) out[8 + i] = pk.Jk[i];
+  // the two dispatchers must agree bit for bit on value and point Jacobian
+  int same = a.ok == b.ok && a.u == b.u && a.v == b.v;
+  for (int i = 0; i < 6; ++i) same = same && a.J[i] == b.J[i];
+  return (a.ok ? 1 : 0) | (same ? 2 : 0);
+}
+int hm_num_params(int model) { return camera_num_params(model); }
+void hm_so3_exp(const double* w, double* q4out, double* ab) { const ExpOut e = so3_exp_jr(v3(w[0], w[1], w[2])); q4out[0] = e.q.x; q4out[1] = e.q.y; q4out[2] = e.q.z; q4out[3] = e.q.w; ab[0] = e.a; ab[1] = e.b; }
+void hm_so3_log(const double* q, double* w) { const V3 r = so3_log(q4(q[0], q[1], q[2], q[3])); w[0] = r.x; w[1] = r.y; w[2] = r.z; }
+void hm_so3_jr_inv(const double* w, double* m9) { const M3 J = so3_jr_inv(v3(w[0], w[1], w[2])); for (int i = 0; i < 9; ++i) m9[i] = J.m[i]; }
+void hm_qrot(const double* q, const double* p, double* out, double* out_inv) {
+  const V3 a = qrot(q4(q[0], q[1], q[2], q[3]), v3(p[0], p[1], p[2])), b = qrot_inv(q4(q[0], q[1], q[2], q[3]), v3(p[0], p[1], p[2]));
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out_inv[0] = b.x; out_inv[1] = b.y; out_inv[2] = b.z;
+}
+// spline coefficients: out = [lam(5) dlam(5) ddlam(5) | c(6) dc(6) ddc(6) dddc(6) | c3(3) dc3(3)]
+void hm_coeffs(double u, double* out) {
+  cum_coeffs6(u, out, out + 5); cum_coeffs6_dd(u, out + 10);
+  coeffs6(u, out + 15, out + 21, out + 27); coeffs6_ddd(u, out + 33);
+  coeffs3(u, out + 39); coeffs3_d(u, out + 42);
+}
+}

@@ -1,0 +1,116 @@
+"""The product's own __host__ __device__ math (csrc/icc_camera.cuh, csrc/icc_device_math.cuh -- the functions every CUDA kernel
+inlines) compiled for the CPU and checked without a GPU: camera projections against the independent NumPy models, both closed-form
+Jacobians (point 2x3, intrinsics 2xK) against central finite differences for all seven models, SO(3) exp / log / Jr^-1 identities, and
+the spline blending polynomials against the reference's blending matrices (SURVEY.md §8(a2) known answers) and their own derivatives."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from openimucameracalibrator_b200 import camera_models as cm
+from test_camera_models import CASES
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_math", "host_math.cu")
+OUT = os.path.join(HERE, "host_math", "_build", "libhost_math.so")
+DP = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
+    return ctypes.CDLL(OUT)
+
+
+def _project(hm, model, k, p, fov=1):
+    out = np.zeros(28); kk = np.zeros(10); kk[: len(k)] = k
+    rc = hm.hm_project(ctypes.c_int(model), kk.ctypes.data_as(DP), np.ascontiguousarray(p, dtype=np.float64).ctypes.data_as(DP), ctypes.c_int(fov), out.ctypes.data_as(DP))
+    assert rc & 2, "project() and project_with_k() disagree"
+    return bool(rc & 1), out[:2].copy(), out[2:8].reshape(2, 3).copy(), out[8:].reshape(2, 10).copy()
+
+
+@pytest.mark.parametrize("model,k", CASES, ids=[cm.MODEL_NAMES[m] for m, _ in CASES])
+def test_device_projection_and_jacobians(hm, model, k):
+    assert hm.hm_num_params(model) == cm.NUM_PARAMS[model] == len(k)
+    rng = np.random.default_rng(100 + model)
+    pts = np.concatenate([rng.uniform(-0.35, 0.35, (60, 2)), rng.uniform(0.3, 1.0, (60, 1))], axis=1)
+    uv_ref, valid = cm.project(model, k, pts)
+    for i, p in enumerate(pts):
+        ok, uv, J, Jk = _project(hm, model, k, p)
+        assert ok == bool(valid[i])
+        if not ok:
+            continue
+        assert np.allclose(uv, uv_ref[i], rtol=1e-13, atol=1e-10)
+        # d(u,v)/d(point): central differences on the independent NumPy model
+        Jfd = np.zeros((2, 3))
+        for d in range(3):
+            h = 1e-6 * max(1.0, abs(p[d])); e = np.zeros(3); e[d] = h
+            Jfd[:, d] = (cm.project(model, k, (p + e)[None])[0][0] - cm.project(model, k, (p - e)[None])[0][0]) / (2 * h)
+        assert np.abs(J - Jfd).max() < 2e-6 * max(1.0, np.abs(Jfd).max())
+        # d(u,v)/d(intrinsics)
+        for q in range(len(k)):
+            h = 1e-3 * abs(k[q]) if 0.0 < abs(k[q]) < 1e-4 else 1e-6 * max(1.0, abs(k[q]))   # the division distortion lives at 1e-6
+            kp, km = k.copy(), k.copy(); kp[q] += h; km[q] -= h
+            fd = (cm.project(model, kp, p[None])[0][0] - cm.project(model, km, p[None])[0][0]) / (2 * h)
+            assert np.abs(Jk[:, q] - fd).max() < 5e-6 * max(1.0, np.abs(fd).max()), (q, Jk[:, q], fd)
+        assert not Jk[:, len(k):].any()
+
+
+def test_fov_dispatch_switch_and_domain_checks(hm):
+    ok, *_ = _project(hm, cm.FOV, np.array([437.0, 1.0, 489.0, 271.0, 0.9]), [0.1, 0.05, 0.6], fov=0)
+    assert not ok                                            # the reference never dispatches FOV (residuals.h:366-389)
+    ok, *_ = _project(hm, cm.DOUBLE_SPHERE, np.array([342.4, 1.0, 0.0, 472.6, 273.9, -0.215, 0.513]), [0.1, 0.0, -5.0])
+    assert not ok
+    ok, *_ = _project(hm, cm.EXTENDED_UNIFIED, np.array([438.0, 1.0, 0.0, 489.5, 272.0, 0.5115, 1.062]), [0.1, 0.0, -5.0])
+    assert not ok
+
+
+def test_device_so3_functions(hm):
+    rng = np.random.default_rng(7)
+    for scale in (1e-12, 1e-7, 1e-3, 0.3, 2.5):
+        for _ in range(20):
+            w = rng.normal(0, 1, 3); w *= scale / np.linalg.norm(w)
+            q = np.zeros(4); ab = np.zeros(2); back = np.zeros(3); Ji = np.zeros(9)
+            hm.hm_so3_exp(w.ctypes.data_as(DP), q.ctypes.data_as(DP), ab.ctypes.data_as(DP))
+            th = np.linalg.norm(w)
+            assert abs(np.linalg.norm(q) - 1.0) < 1e-15 and abs(q[3] - np.cos(th / 2)) < 1e-15
+            hm.hm_so3_log(q.ctypes.data_as(DP), back.ctypes.data_as(DP))
+            assert np.abs(back - w).max() < 1e-14 * max(1.0, th) + 1e-22
+            # Jr(w) Jr^-1(w) = I with Jr = I - a [w]x + b [w]x^2
+            hm.hm_so3_jr_inv(w.ctypes.data_as(DP), Ji.ctypes.data_as(DP))
+            W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+            Jr = np.eye(3) - ab[0] * W + ab[1] * W @ W
+            assert np.abs(Jr @ Ji.reshape(3, 3) - np.eye(3)).max() < 1e-12
+            # rotation by the quaternion equals the Rodrigues matrix; qrot_inv is its transpose
+            R = np.eye(3) + (np.sin(th) / th if th > 1e-9 else 1.0) * W + ((1 - np.cos(th)) / th ** 2 if th > 1e-9 else 0.5) * W @ W
+            p = rng.normal(0, 1, 3); a = np.zeros(3); b = np.zeros(3)
+            hm.hm_qrot(q.ctypes.data_as(DP), p.ctypes.data_as(DP), a.ctypes.data_as(DP), b.ctypes.data_as(DP))
+            assert np.abs(a - R @ p).max() < 1e-14 and np.abs(b - R.T @ p).max() < 1e-14
+
+
+def test_device_spline_coefficients_against_reference_blending_matrices(hm):
+    # rows = knot, columns = power of u, x120 (N = 6) / x2 (N = 3)
+    M6 = np.array([[1, -5, 10, -10, 5, -1], [26, -50, 20, 20, -20, 5], [66, 0, -60, 0, 30, -10], [26, 50, 20, -20, -20, 10], [1, 5, 10, 10, 5, -5], [0, 0, 0, 0, 0, 1]]) / 120.0
+    C6 = np.array([[120, 0, 0, 0, 0, 0], [119, 5, -10, 10, -5, 1], [93, 55, -30, -10, 15, -4], [27, 55, 30, -10, -15, 6], [1, 5, 10, 10, 5, -4], [0, 0, 0, 0, 0, 1]]) / 120.0
+    M3 = np.array([[1, -2, 1], [1, 2, -2], [0, 0, 1]]) / 2.0
+
+    def powers(u, n, deriv):
+        out = np.zeros(n)
+        for j in range(deriv, n):
+            out[j] = np.prod(np.arange(j, j - deriv, -1)) * u ** (j - deriv)
+        return out
+    out = np.zeros(45)
+    for u in (0.0, 1e-9, 0.123, 0.5, 0.987654321, 1.0, 1.02):      # u slightly above 1 occurs (row time added to normalised u, quirk q2)
+        hm.hm_coeffs(ctypes.c_double(u), out.ctypes.data_as(DP))
+        assert np.abs(out[0:5] - (C6 @ powers(u, 6, 0))[1:]).max() < 1e-15
+        assert np.abs(out[5:10] - (C6 @ powers(u, 6, 1))[1:]).max() < 1e-14
+        assert np.abs(out[10:15] - (C6 @ powers(u, 6, 2))[1:]).max() < 1e-14
+        for d, sl in enumerate((slice(15, 21), slice(21, 27), slice(27, 33), slice(33, 39))):
+            assert np.abs(out[sl] - M6 @ powers(u, 6, d)).max() < 1e-13
+        assert np.abs(out[39:42] - M3 @ powers(u, 3, 0)).max() < 1e-15 and np.abs(out[42:45] - M3 @ powers(u, 3, 1)).max() < 1e-15
+        assert abs(out[15:21].sum() - 1.0) < 1e-15 and abs(out[39:42].sum() - 1.0) < 1e-15      # partition of unity

@@ -1135,6 +1135,7 @@ icc_status icc_optimize_board_points(icc_handle* h, int nf, const int32_t* off, 
   CU(cudaMemcpyAsync(d_q.p, q_wc, 4 * (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_p.p, p_wc, 3 * (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_valid.p, valid, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d_e.p, 0, (size_t)nf * sizeof(double), st));   // views that are not valid keep a zero error
   launch_unproject(h->model, h->intr, nc, d_uv.p, d_xy.p, d_ok.p, st);
   PoseProblem Q; memset(&Q, 0, sizeof Q);
   Q.model = h->model; for (int i = 0; i < 10; ++i) Q.intr[i] = h->intr[i];

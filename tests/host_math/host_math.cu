@@ -2,6 +2,7 @@
 // kernels inline, compiled for the CPU by nvcc so that the `-m "not gpu"` suite can check them (finite differences, oracle, known
 // answers) without a device.  Test infrastructure only; built by tests/test_host_device_math.py into tests/host_math/_build/.
 #include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_spline_chain.cuh"
 
 using namespace icc;
 
@@ -32,5 +33,19 @@ void hm_coeffs(double u, double* out) {
   cum_coeffs6(u, out, out + 5); cum_coeffs6_dd(u, out + 10);
   coeffs6(u, out + 15, out + 21, out + 27); coeffs6_ddd(u, out + 33);
   coeffs3(u, out + 39); coeffs3_d(u, out + 42);
+}
+// The SO(3) spline chain of the residual kernels for one observation: knots (6 x (x,y,z,w)), normalised time u, row covector
+// m_theta = d r / d theta (right increment of R_w_i)  ->  q_out = R_w_i(u), rows[18] = d r / d eps_j (right increments of the six knots),
+// du = d r / d u through the rotation.  Exactly the code path of vision_kernel / imu_kernel: stage_so3_increment, build_chain, so3_knot_row.
+void hm_so3_chain(const double* knots, double u, const double* m_theta, double* q_out, double* rows, double* du) {
+  static WarpCtx wc;
+  for (int i = 0; i < 6; ++i) wc.q[i] = q4(knots[4 * i], knots[4 * i + 1], knots[4 * i + 2], knots[4 * i + 3]);
+  for (int i = 0; i < 5; ++i) stage_so3_increment<true>(&wc, i);
+  Chain ch;
+  build_chain(&wc, u, ch);
+  static double Jt[48 * LDJ];
+  *du = so3_knot_row(&wc, ch, v3(m_theta[0], m_theta[1], m_theta[2]), Jt, 0, 1.0);
+  for (int c = 0; c < 18; ++c) rows[c] = Jt[c * LDJ];
+  q_out[0] = ch.q.x; q_out[1] = ch.q.y; q_out[2] = ch.q.z; q_out[3] = ch.q.w;
 }
 }

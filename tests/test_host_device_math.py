@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -114,3 +114,75 @@ def test_device_spline_coefficients_against_reference_blending_matrices(hm):
             assert np.abs(out[sl] - M6 @ powers(u, 6, d)).max() < 1e-13
         assert np.abs(out[39:42] - M3 @ powers(u, 3, 0)).max() < 1e-15 and np.abs(out[42:45] - M3 @ powers(u, 3, 1)).max() < 1e-15
         assert abs(out[15:21].sum() - 1.0) < 1e-15 and abs(out[39:42].sum() - 1.0) < 1e-15      # partition of unity
+
+
+# ---- the SO(3) spline chain of the residual kernels and its analytic knot Jacobian ----------------------------------------------------
+def _qmul(a, b):
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _qexp(w):
+    th = np.linalg.norm(w)
+    return np.array([*(0.5 * w), 1.0]) if th < 1e-14 else np.array([*(np.sin(th / 2) / th * w), np.cos(th / 2)])
+
+
+def _qlog(q):
+    n = np.linalg.norm(q[:3])
+    return 2.0 * q[:3] / q[3] if n < 1e-14 else 2.0 * np.arctan(n / q[3]) / n * q[:3]
+
+
+def _qinv(q):
+    return np.array([-q[0], -q[1], -q[2], q[3]])
+
+
+_C6 = np.array([[120, 0, 0, 0, 0, 0], [119, 5, -10, 10, -5, 1], [93, 55, -30, -10, 15, -4], [27, 55, 30, -10, -15, 6], [1, 5, 10, 10, 5, -4], [0, 0, 0, 0, 0, 1]]) / 120.0
+
+
+def _spline_rotation(knots, u):
+    """CeresSplineHelper::evaluate_lie (basalt_spline/ceres_spline_helper.h:101-187), independent NumPy statement."""
+    lam = _C6 @ np.array([u ** j for j in range(6)])
+    q = knots[0].copy()
+    for i in range(5):
+        q = _qmul(q, _qexp(lam[i + 1] * _qlog(_qmul(_qinv(knots[i]), knots[i + 1]))))
+    return q / np.linalg.norm(q)
+
+
+def _chain(hm, knots, u, m):
+    q = np.zeros(4); rows = np.zeros(18); du = ctypes.c_double()
+    hm.hm_so3_chain(np.ascontiguousarray(knots).ctypes.data_as(DP), ctypes.c_double(u), np.ascontiguousarray(m).ctypes.data_as(DP), q.ctypes.data_as(DP), rows.ctypes.data_as(DP),
+                    ctypes.byref(du))
+    return q, rows.reshape(6, 3), du.value
+
+
+@pytest.mark.parametrize("spread", [0.02, 0.3, 1.2], ids=["slow", "typical", "fast_rotation"])
+def test_device_so3_spline_chain_and_knot_jacobian(hm, spread):
+    """build_chain + so3_knot_row (the analytic Jacobian at the heart of vision_kernel / imu_kernel) against central finite differences
+    of an independent NumPy statement of the cumulative SO(3) B-spline: d theta / d eps_j for right increments on every knot, and
+    d theta / d u, contracted with a random row covector -- exactly what one Jacobian row of a residual needs."""
+    rng = np.random.default_rng(int(spread * 100))
+    for trial in range(6):
+        q0 = _qexp(rng.normal(0, 1.0, 3))
+        knots = [q0]
+        for i in range(5):
+            knots.append(_qmul(knots[-1], _qexp(rng.normal(0, spread, 3))))
+        knots = np.array(knots)
+        u = [0.0, 0.31, 0.77, 1.0, 1.03, 0.5][trial]                 # u > 1 occurs: the row time is added to the normalised time (quirk q2)
+        m = rng.normal(0, 1, 3)
+        q, rows, du = _chain(hm, knots, u, m)
+        R = _spline_rotation(knots, u)
+        assert min(np.abs(q - R).max(), np.abs(q + R).max()) < 1e-14
+        h = 1e-6
+        for j in range(6):
+            for a in range(3):
+                e = np.zeros(3); e[a] = h
+                kp, km = knots.copy(), knots.copy()
+                kp[j] = _qmul(knots[j], _qexp(e)); km[j] = _qmul(knots[j], _qexp(-e))
+                dth = (_qlog(_qmul(_qinv(R), _spline_rotation(kp, u))) - _qlog(_qmul(_qinv(R), _spline_rotation(km, u)))) / (2 * h)
+                assert abs(rows[j, a] - m @ dth) < 2e-8 * max(1.0, np.abs(rows).max()), (j, a, rows[j, a], m @ dth)
+        dth_u = (_qlog(_qmul(_qinv(R), _spline_rotation(knots, u + h))) - _qlog(_qmul(_qinv(R), _spline_rotation(knots, u - h)))) / (2 * h)
+        assert abs(du - m @ dth_u) < 2e-8 * max(1.0, abs(du))
+    # a vanishing increment between two knots (identical orientations) must not produce NaNs
+    knots[3] = knots[2]
+    q, rows, du = _chain(hm, knots, 0.4, np.array([0.3, -0.2, 0.9]))
+    assert np.isfinite(q).all() and np.isfinite(rows).all() and np.isfinite(du)

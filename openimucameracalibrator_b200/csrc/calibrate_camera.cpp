@@ -40,8 +40,8 @@ int main(int argc, char** argv) {
   F.num = {{"grid_size", 0.04}, {"device", 0.0}};
   try { icccli::parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
   try {
-    Value scene_json;
-    try { scene_json = iccjson::load_ubjson(F.str["input_corners"]); } catch (const std::exception& e) { std::cerr << "Check failed: Failed to load " << F.str["input_corners"] << ": " << e.what() << std::endl; return 1; }
+    Value scene_json; icccli::SceneViews sv;
+    try { scene_json = icccli::load_scene(F.str["input_corners"], sv); } catch (const std::exception& e) { std::cerr << "Check failed: Failed to load " << F.str["input_corners"] << ": " << e.what() << std::endl; return 1; }
     const std::string model_name = F.str["camera_model_to_calibrate"];
     const int model = model_from_string(model_name);
     if (model < 0) { std::cerr << "ERROR: unknown camera model '" << model_name << "'" << std::endl; return 1; }
@@ -49,7 +49,6 @@ int main(int argc, char** argv) {
     const double fps = scene_json.at("camera_fps").num();
     int np = 0;
     const std::vector<double> board = icccli::read_scene_points(scene_json, np);
-    const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
     const int nv = (int)sv.timestamp_us.size();
     if (nv == 0) { std::cerr << "Check failed: the corner file holds no views" << std::endl; return 1; }
     icc_handle* h = nullptr;

@@ -120,8 +120,8 @@ int main(int argc, char** argv) {
       try { pose_dataset = iccjson::load_json(F.str["input_pose_dataset"]); }
       catch (const std::exception& e) { CHECK_MSG(false, "Could not read Reconstruction file (JSON pose dataset expected, Theia .calibdata is not supported): " << e.what()); }
     }
-    Value scene_json;
-    try { scene_json = iccjson::load_ubjson(F.str["input_corners"]); } catch (const std::exception& e) { CHECK_MSG(false, "Failed to load " << F.str["input_corners"] << ": " << e.what()); }
+    Value scene_json; icccli::SceneViews sv;
+    try { scene_json = icccli::load_scene(F.str["input_corners"], sv); } catch (const std::exception& e) { CHECK_MSG(false, "Failed to load " << F.str["input_corners"] << ": " << e.what()); }
     std::vector<double> intr; int width = 0, height = 0; double fps = 0;
     int model = -1;
     try { model = icccli::read_camera(iccjson::load_json(F.str["camera_calibration_json"]), intr, width, height, fps); }
@@ -139,26 +139,20 @@ int main(int argc, char** argv) {
       int np = 0; board = icccli::read_scene_points(scene_json, np); max_id = np - 1;
     }
     // telemetry (src/io/read_telemetry.cc:29-69)
-    Value tel;
-    try { tel = iccjson::load_json(F.str["telemetry_json"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["telemetry_json"] << ": " << e.what()); }
-    const Value& tj = tel.at("timestamps_ns");
-    CHECK_MSG(tel.at("gyroscope").size() == tj.size() && tel.at("accelerometer").size() == tj.size(), "Telemetry should have the same amount of timestamps, accelerometer and gyroscope values.");
-    std::vector<double> imu_t, acc, gyr;
-    const Value& tacc = tel.at("accelerometer"); const Value& tgyr = tel.at("gyroscope");
-    imu_t.reserve(tj.size()); acc.reserve(3 * tj.size()); gyr.reserve(3 * tj.size());
-    for (size_t i = 0; i < tj.size(); ++i) {
-      imu_t.push_back(tj.at(i).num() * NS_TO_S);
-      const Value& ai = tacc.at(i); const Value& gi = tgyr.at(i);
-      for (int d = 0; d < 3; ++d) { acc.push_back(ai.at(d).num()); gyr.push_back(gi.at(d).num()); }
-    }
+    icccli::Telemetry tel;
+    try { tel = icccli::load_telemetry(F.str["telemetry_json"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["telemetry_json"] << ": " << e.what()); }
+    CHECK_MSG(tel.gyr.size() == 3 * tel.t_ns.size() && tel.acc.size() == 3 * tel.t_ns.size(), "Telemetry should have the same amount of timestamps, accelerometer and gyroscope values.");
+    std::vector<double> imu_t(tel.t_ns.size());
+    for (size_t i = 0; i < imu_t.size(); ++i) imu_t[i] = tel.t_ns[i] * NS_TO_S;
+    const std::vector<double>& acc = tel.acc; const std::vector<double>& gyr = tel.gyr;
     double t_offset_cam_s = 0.0;
-    if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) t_offset_cam_s = tel.at("img_timestamps_ns").at(0).num() * NS_TO_S;
+    if (!tel.img_t_ns.empty()) t_offset_cam_s = tel.img_t_ns[0] * NS_TO_S;
     // views: join corners with poses by name = to_string((uint64) timestamp_us)   (app :131-161)
     std::vector<double> frame_t, uv, q_wc, p_wc; std::vector<int32_t> off{0}, ids;
     if (have_poses) {
       const Value& pviews = pose_dataset.at("views");
-      for (const auto& kv : *scene_json.at("views").o) {
-        const double timestamp_us = std::stod(kv.first);
+      for (size_t vi = 0; vi < sv.key.size(); ++vi) {
+        const double timestamp_us = sv.timestamp_us[vi];
         const std::string view_name = std::to_string((uint64_t)timestamp_us);
         if (!pviews.contains(view_name)) continue;
         const Value& pv = pviews.at(view_name);
@@ -166,12 +160,11 @@ int main(int argc, char** argv) {
         const Value& q = pv.at("q_wc");   // [w, x, y, z]
         q_wc.push_back(q.at(1).num()); q_wc.push_back(q.at(2).num()); q_wc.push_back(q.at(3).num()); q_wc.push_back(q.at(0).num());
         for (int d = 0; d < 3; ++d) p_wc.push_back(pv.at("p_wc").at(d).num());
-        for (const auto& ip : *kv.second.at("image_points").o) { ids.push_back(std::stoi(ip.first)); uv.push_back(ip.second.at(0).num()); uv.push_back(ip.second.at(1).num()); }
+        for (int cidx = sv.off[vi]; cidx < sv.off[vi + 1]; ++cidx) { ids.push_back(sv.ids[cidx]); uv.push_back(sv.uv[2 * cidx]); uv.push_back(sv.uv[2 * cidx + 1]); }
         off.push_back((int32_t)ids.size());
       }
     } else if (!F.boolean["parse_only"]) {
       // no pose dataset: estimate the per-view poses on the GPU and keep the views the reference's PoseEstimator would keep
-      const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
       const int nv = (int)sv.timestamp_us.size();
       CHECK_MSG(nv > 0, "the corner file holds no views");
       icc_handle* hp = nullptr;
@@ -195,7 +188,6 @@ int main(int argc, char** argv) {
       }
       std::cout << "Estimated board poses for " << kept << " of " << nv << " views on the GPU (no --input_pose_dataset given)\n";
     } else {
-      const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
       for (size_t i = 0; i < sv.timestamp_us.size(); ++i) frame_t.push_back(sv.timestamp_us[i] * US_TO_S + t_offset_cam_s);
       ids = sv.ids; uv = sv.uv; off = sv.off;
     }
@@ -244,6 +236,11 @@ int main(int argc, char** argv) {
       for (double v : intr) s["intrinsics"].push_back(Value(v));
       s["init_line_delay_s"] = Value(init_line_delay); s["dt_so3"] = Value(ip.dt_so3_s); s["dt_r3"] = Value(ip.dt_r3_s); s["first_view_t_s"] = Value(frame_t.front());
       s["uv_sum"] = Value([&] { double a = 0; for (double v : uv) a += v; return a; }());
+      // order-sensitive digests: the views must arrive in std::map key order, the corners of a view in the order of their id strings
+      s["uv_order_digest"] = Value([&] { double a = 0; for (size_t i = 0; i < uv.size(); ++i) a += double(i % 1013 + 1) * uv[i]; return a; }());
+      s["ids_order_digest"] = Value([&] { double a = 0; for (size_t i = 0; i < ids.size(); ++i) a += double(i % 1009 + 1) * ids[i]; return a; }());
+      s["frame_t_digest"] = Value([&] { double a = 0; for (size_t i = 0; i < frame_t.size(); ++i) a += double(i % 101 + 1) * frame_t[i]; return a; }());
+      s["imu_digest"] = Value([&] { double a = 0; for (size_t i = 0; i < imu_t.size(); ++i) a += double(i % 1013 + 1) * (imu_t[i] + acc[3 * i] + 2 * acc[3 * i + 1] + 3 * acc[3 * i + 2] + 5 * gyr[3 * i] + 7 * gyr[3 * i + 1] + 11 * gyr[3 * i + 2]); return a; }());
       std::cout << iccjson::dump(s) << std::endl;
       return 0;
     }

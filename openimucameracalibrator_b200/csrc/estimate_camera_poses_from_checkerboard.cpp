@@ -25,14 +25,13 @@ int main(int argc, char** argv) {
   F.num = {{"device", 0.0}};
   try { icccli::parse_flags(argc, argv, F); } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << std::endl; return 1; }
   try {
-    Value scene_json;
-    try { scene_json = iccjson::load_ubjson(F.str["input_corners"]); } catch (const std::exception& e) { std::cerr << "Check failed: Failed to load " << F.str["input_corners"] << ": " << e.what() << std::endl; return 1; }
+    Value scene_json; icccli::SceneViews sv;
+    try { scene_json = icccli::load_scene(F.str["input_corners"], sv); } catch (const std::exception& e) { std::cerr << "Check failed: Failed to load " << F.str["input_corners"] << ": " << e.what() << std::endl; return 1; }
     std::vector<double> intr; int width = 0, height = 0; double fps = 0; int model = -1;
     try { model = icccli::read_camera(iccjson::load_json(F.str["camera_calibration_json"]), intr, width, height, fps); }
     catch (const std::exception& e) { std::cerr << "Check failed: Could not read camera calibration: " << F.str["camera_calibration_json"] << ": " << e.what() << std::endl; return 1; }
     int np = 0;
     const std::vector<double> board = icccli::read_scene_points(scene_json, np);
-    const icccli::SceneViews sv = icccli::read_scene_views(scene_json);
     const int nv = (int)sv.timestamp_us.size();
     if (nv == 0) { std::cerr << "Check failed: the corner file holds no views" << std::endl; return 1; }
     std::cout << "PoseEstimator setting max reprojection error to: " << 0.004 * height << "\n";

@@ -24,21 +24,20 @@ int main(int argc, char** argv) {
     Value poses;
     try { poses = iccjson::load_json(F.str["input_pose_calibration_dataset"]); }
     catch (const std::exception& e) { std::cerr << "Check failed: could not read the pose dataset (JSON expected): " << e.what() << std::endl; return 1; }
-    Value tel;
-    try { tel = iccjson::load_json(F.str["telemetry_json"]); } catch (const std::exception& e) { std::cerr << "Could not read: " << F.str["telemetry_json"] << ": " << e.what() << std::endl; return 1; }
+    icccli::Telemetry tel;
+    try { tel = icccli::load_telemetry(F.str["telemetry_json"]); } catch (const std::exception& e) { std::cerr << "Could not read: " << F.str["telemetry_json"] << ": " << e.what() << std::endl; return 1; }
     double bias[3] = {0, 0, 0}; bool have_bias = false;
     if (!F.str["imu_bias_estimate"].empty()) {      // ReadIMUBias (src/io/read_misc.cc:49-63)
       const Value b = iccjson::load_json(F.str["imu_bias_estimate"]); const char* ax[3] = {"x", "y", "z"};
       for (int d = 0; d < 3; ++d) bias[d] = b.at("gyro_bias").at(ax[d]).num();
       have_bias = true;
     }
-    const Value& tj = tel.at("timestamps_ns");
-    if (tel.at("gyroscope").size() != tj.size()) { std::cerr << "Telemetry should have the same amount of timestamps and gyroscope values." << std::endl; return 1; }
-    std::vector<double> imu_t, gyr;
-    const Value& tgyr = tel.at("gyroscope");
-    for (size_t i = 0; i < tj.size(); ++i) { imu_t.push_back(tj.at(i).num() * 1e-9); const Value& gi = tgyr.at(i); for (int d = 0; d < 3; ++d) gyr.push_back(gi.at(d).num()); }
+    if (tel.gyr.size() != 3 * tel.t_ns.size()) { std::cerr << "Telemetry should have the same amount of timestamps and gyroscope values." << std::endl; return 1; }
+    std::vector<double> imu_t(tel.t_ns.size());
+    for (size_t i = 0; i < imu_t.size(); ++i) imu_t[i] = tel.t_ns[i] * 1e-9;
+    const std::vector<double>& gyr = tel.gyr;
     double delta_t0_cam = 0.0;                       // app :80-86
-    if (tel.contains("img_timestamps_ns") && tel.at("img_timestamps_ns").size() > 0) delta_t0_cam = tel.at("img_timestamps_ns").at(0).num() * 1e-9;
+    if (!tel.img_t_ns.empty()) delta_t0_cam = tel.img_t_ns[0] * 1e-9;
     std::vector<double> view_t, q_cw;
     for (const auto& kv : *poses.at("views").o) {
       const double t = kv.second.contains("timestamp_s") ? kv.second.at("timestamp_s").num() : std::stod(kv.first) * 1e-6;

@@ -61,7 +61,7 @@ class TextParser {
  public:
   explicit TextParser(const std::string& t) : t_(t) {}
   Value parse() { Value v = value(); ws(); if (p_ != t_.size()) fail("trailing characters"); return v; }
- private:
+ protected:
   const std::string& t_; size_t p_ = 0;
   [[noreturn]] void fail(const std::string& m) { throw std::runtime_error("json parse error at byte " + std::to_string(p_) + ": " + m); }
   void ws() { while (p_ < t_.size() && (t_[p_] == ' ' || t_[p_] == '\n' || t_[p_] == '\t' || t_[p_] == '\r')) ++p_; }
@@ -201,7 +201,7 @@ class UbjsonParser {
  public:
   explicit UbjsonParser(const std::string& d) : d_(d) {}
   Value parse() { return value(next()); }
- private:
+ protected:
   const std::string& d_; size_t p_ = 0;
   [[noreturn]] void fail(const std::string& m) { throw std::runtime_error("ubjson parse error at byte " + std::to_string(p_) + ": " + m); }
   unsigned char next() { if (p_ >= d_.size()) fail("unexpected end"); return (unsigned char)d_[p_++]; }

@@ -52,6 +52,16 @@ def test_cli_parses_written_files(tmp_path, k):
         k_expected[5:] = 0.0                                  # ... nor PINHOLE radial distortion
     assert np.allclose(s["intrinsics"], k_expected)
     assert abs(s["uv_sum"] - float(np.sum(ds["uv"]))) < 1e-6
+    # order-sensitive digests: the streaming corner / telemetry readers must deliver what the std::map route of the reference would
+    d2 = iof.dataset_from_files(ds)
+    w = lambda n, m: (np.arange(n) % m + 1).astype(np.float64)  # noqa: E731
+    uvf = np.asarray(d2["uv"]).reshape(-1)
+    assert abs(s["uv_order_digest"] - float(w(uvf.size, 1013) @ uvf)) < 1e-9 * abs(s["uv_order_digest"])
+    assert s["ids_order_digest"] == float(w(d2["point_ids"].size, 1009) @ d2["point_ids"])
+    assert abs(s["frame_t_digest"] - float(w(d2["frame_t"].size, 101) @ d2["frame_t"])) < 1e-9 * max(1.0, abs(s["frame_t_digest"]))
+    a, g = np.asarray(ds["accel"]), np.asarray(ds["gyro"])
+    per = d2["imu_t"] + a @ np.array([1.0, 2.0, 3.0]) + g @ np.array([5.0, 7.0, 11.0])
+    assert abs(s["imu_digest"] - float(w(per.size, 1013) @ per)) < 1e-9 * abs(s["imu_digest"])
     assert abs(s["init_line_delay_s"] - 1.0 / ds["fps"] / ds["image_size"][1]) < 1e-18
 
 

@@ -214,4 +214,38 @@ ICC_HD Proj project(int model, const double* k, V3 p, bool dispatch_fov) {
   }
 }
 
+// theia::Camera::PixelToNormalizedCoordinates(px) / z : solve project(x, y, 1) = px by damped Gauss-Newton
+ICC_HD bool unproject_gn(int model, const double* k, double px, double py, double& xo, double& yo) {
+  const Proj p0 = project(model, k, v3(0.0, 0.0, 1.0), true);
+  if (!p0.ok) return false;
+  double x, y;
+  {
+    const double a = p0.J[0], b = p0.J[1], c = p0.J[3], d = p0.J[4], det = a * d - b * c;
+    if (!(fabs(det) > 0.0)) return false;
+    const double du = px - p0.u, dv = py - p0.v;
+    x = (d * du - b * dv) / det; y = (-c * du + a * dv) / det;
+  }
+  Proj p = project(model, k, v3(x, y, 1.0), true);
+  for (int s = 0; s < 60 && !p.ok; ++s) { x *= 0.5; y *= 0.5; p = project(model, k, v3(x, y, 1.0), true); }   // outside the model's domain
+  if (!p.ok) return false;
+  double ru = p.u - px, rv = p.v - py, e = ru * ru + rv * rv;
+  for (int it = 0; it < 50; ++it) {
+    if (e < 1e-26) break;
+    const double a = p.J[0], b = p.J[1], c = p.J[3], d = p.J[4], det = a * d - b * c;
+    if (!(fabs(det) > 1e-300)) break;
+    const double dx = -(d * ru - b * rv) / det, dy = -(-c * ru + a * rv) / det;
+    double t = 1.0; bool moved = false;
+    for (int bt = 0; bt < 30; ++bt, t *= 0.5) {
+      const double xn = x + t * dx, yn = y + t * dy;
+      const Proj pn = project(model, k, v3(xn, yn, 1.0), true);
+      if (!pn.ok) continue;
+      const double r0 = pn.u - px, r1 = pn.v - py, en = r0 * r0 + r1 * r1;
+      if (en < e) { x = xn; y = yn; p = pn; ru = r0; rv = r1; e = en; moved = true; break; }
+    }
+    if (!moved) break;
+  }
+  xo = x; yo = y;
+  return e < 1e-12;      // (1e-6 px)^2: anything worse did not converge
+}
+
 }  // namespace icc

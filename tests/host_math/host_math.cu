@@ -21,6 +21,8 @@ int hm_project(int model, const double* k, const double* p, int dispatch_fov, do
   return (a.ok ? 1 : 0) | (same ? 2 : 0);
 }
 int hm_num_params(int model) { return camera_num_params(model); }
+// theia::Camera::PixelToNormalizedCoordinates / z as the pose kernels compute it (damped Gauss-Newton on the forward model)
+int hm_unproject(int model, const double* k, double px, double py, double* xy) { double x = 0.0, y = 0.0; const bool ok = unproject_gn(model, k, px, py, x, y); xy[0] = x; xy[1] = y; return ok ? 1 : 0; }
 void hm_so3_exp(const double* w, double* q4out, double* ab) { const ExpOut e = so3_exp_jr(v3(w[0], w[1], w[2])); q4out[0] = e.q.x; q4out[1] = e.q.y; q4out[2] = e.q.z; q4out[3] = e.q.w; ab[0] = e.a; ab[1] = e.b; }
 void hm_so3_log(const double* q, double* w) { const V3 r = so3_log(q4(q[0], q[1], q[2], q[3])); w[0] = r.x; w[1] = r.y; w[2] = r.z; }
 void hm_so3_jr_inv(const double* w, double* m9) { const M3 J = so3_jr_inv(v3(w[0], w[1], w[2])); for (int i = 0; i < 9; ++i) m9[i] = J.m[i]; }

@@ -61,6 +61,26 @@ def test_device_projection_and_jacobians(hm, model, k):
         assert not Jk[:, len(k):].any()
 
 
+@pytest.mark.parametrize("model,k", CASES, ids=[cm.MODEL_NAMES[m] for m, _ in CASES])
+def test_device_unprojection_inverts_projection(hm, model, k):
+    """unproject_gn (the un-projection of unproject_kernel / the board-pose path): project o unproject = identity for every model, and
+    pixels outside a model's image are reported instead of returning garbage."""
+    rng = np.random.default_rng(300 + model)
+    pts = np.concatenate([rng.uniform(-0.45, 0.45, (200, 2)), np.ones((200, 1))], axis=1)
+    uv, valid = cm.project(model, k, pts)
+    kk = np.zeros(10); kk[: len(k)] = k
+    xy = np.zeros(2)
+    for i in np.flatnonzero(valid):
+        ok = hm.hm_unproject(ctypes.c_int(model), kk.ctypes.data_as(DP), ctypes.c_double(uv[i, 0]), ctypes.c_double(uv[i, 1]), xy.ctypes.data_as(DP))
+        assert ok and np.abs(xy - pts[i, :2]).max() < 1e-10, (i, xy, pts[i])
+    if model in (cm.DOUBLE_SPHERE, cm.EXTENDED_UNIFIED):
+        return                                                   # their image of the half space is unbounded in this parameter range
+    ok = hm.hm_unproject(ctypes.c_int(model), kk.ctypes.data_as(DP), ctypes.c_double(1e7), ctypes.c_double(-1e7), xy.ctypes.data_as(DP))
+    if ok:                                                       # if a far pixel does invert, it must invert consistently
+        back, v = cm.project(model, k, np.array([[xy[0], xy[1], 1.0]]))
+        assert v[0] and np.abs(back[0] - [1e7, -1e7]).max() < 1e-3
+
+
 def test_fov_dispatch_switch_and_domain_checks(hm):
     ok, *_ = _project(hm, cm.FOV, np.array([437.0, 1.0, 489.0, 271.0, 0.9]), [0.1, 0.05, 0.6], fov=0)
     assert not ok                                            # the reference never dispatches FOV (residuals.h:366-389)

@@ -3,6 +3,7 @@
 // answers) without a device.  Test infrastructure only; built by tests/test_host_device_math.py into tests/host_math/_build/.
 #include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_spline_chain.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_rotinit_math.cuh"
 
 using namespace icc;
 
@@ -49,5 +50,17 @@ void hm_so3_chain(const double* knots, double u, const double* m_theta, double* 
   *du = so3_knot_row(&wc, ch, v3(m_theta[0], m_theta[1], m_theta[2]), Jt, 0, 1.0);
   for (int c = 0; c < 18; ++c) rows[c] = Jt[c * LDJ];
   q_out[0] = ch.q.x; q_out[1] = ch.q.y; q_out[2] = ch.q.z; q_out[3] = ch.q.w;
+}
+// ---- scalar pieces of the rotation / time-offset initialiser (icc_rotinit_math.cuh) ----------------------------------------------------
+int hm_nearest_sorted(const double* ts, int n, double t, double* dist) { double d = 0.0; const int i = nearest_sorted(ts, n, t, d); *dist = d; return i; }
+void hm_slerp4(const double* a, const double* b, double t, double* out) {
+  const double4 r = slerp4(make_double4(a[0], a[1], a[2], a[3]), make_double4(b[0], b[1], b[2], b[3]), t);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void hm_eig4_max(const double* A16, double* q4out) {
+  double A[4][4], q[4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) A[i][j] = A16[4 * i + j];
+  eig4_max(A, q);
+  for (int i = 0; i < 4; ++i) q4out[i] = q[i];
 }
 }

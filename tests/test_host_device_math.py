@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_rotinit_math.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -206,3 +206,59 @@ def test_device_so3_spline_chain_and_knot_jacobian(hm, spread):
     knots[3] = knots[2]
     q, rows, du = _chain(hm, knots, 0.4, np.array([0.3, -0.2, 0.9]))
     assert np.isfinite(q).all() and np.isfinite(rows).all() and np.isfinite(du)
+
+
+# ---- scalar pieces of the rotation / time-offset initialiser -----------------------------------------------------------------------------
+def test_device_nearest_sample_rule_matches_the_reference_scan(hm):
+    """FindClosestTimestamp (src/utils/utils.cc:194-212) is a linear scan keeping the FIRST strict minimum of |t - ts[i]|; the kernels use
+    a bisection on the sorted times that must pick the same index, ties included."""
+    rng = np.random.default_rng(11)
+    ts = np.sort(rng.uniform(0, 10, 200)); ts[50] = ts[49] + 0.02; ts[51] = ts[49] + 0.04          # an exact tie candidate at the midpoint
+    queries = np.concatenate([rng.uniform(-1, 11, 500), ts[:20], [ts[49] + 0.01, ts[50] + 0.01, -5.0, 50.0]])
+    dist = ctypes.c_double()
+    for q in queries:
+        idx = hm.hm_nearest_sorted(ts.ctypes.data_as(DP), ctypes.c_int(ts.size), ctypes.c_double(q), ctypes.byref(dist))
+        best, bd = 0, abs(q - ts[0])
+        for i in range(1, ts.size):
+            if abs(q - ts[i]) < bd:
+                best, bd = i, abs(q - ts[i])
+        assert idx == best and dist.value == bd
+
+
+def test_device_slerp_is_eigens(hm):
+    """Eigen::Quaternion::slerp (used by InterpolateQuaternions, utils.cc:234): shortest arc, linear blend when nearly parallel."""
+    rng = np.random.default_rng(12)
+    out = np.zeros(4)
+    for trial in range(200):
+        a = rng.normal(0, 1, 4); a /= np.linalg.norm(a)
+        b = a + (1e-9 if trial % 5 == 0 else 1.0) * rng.normal(0, 1, 4); b /= np.linalg.norm(b)
+        if trial % 3 == 0:
+            b = -b                                                 # antipodal representation: slerp must take the short way
+        tt = rng.uniform(0, 1)
+        hm.hm_slerp4(a.ctypes.data_as(DP), b.ctypes.data_as(DP), ctypes.c_double(tt), out.ctypes.data_as(DP))
+        d = float(a @ b); ad = abs(d)
+        if ad >= 1.0 - np.finfo(float).eps:
+            s0, s1 = 1.0 - tt, tt
+        else:
+            th = np.arccos(ad); s0, s1 = np.sin((1 - tt) * th) / np.sin(th), np.sin(tt * th) / np.sin(th)
+        ref = s0 * a + (-s1 if d < 0 else s1) * b
+        assert np.abs(out - ref).max() < 1e-15
+        if ad < 1.0 - 1e-6:
+            assert abs(np.linalg.norm(out) - 1.0) < 1e-12          # stays on the unit sphere on a proper arc
+
+
+def test_device_dominant_eigenvector_of_horns_matrix(hm):
+    """eig4_max (cyclic Jacobi) behind the closed-form rotation of the golden-section objective: the eigenvector of the largest eigenvalue
+    of a symmetric 4x4 matrix, against numpy.linalg.eigh; and the rotation it encodes maximises tr(R M) like the reference's SVD route."""
+    rng = np.random.default_rng(13)
+    q = np.zeros(4)
+    for trial in range(100):
+        M = rng.normal(0, 1, (3, 3))                                # sum of imu x vis outer products
+        Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz = M.ravel()
+        N = np.array([[Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx], [Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz],
+                      [Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy], [Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz]])
+        hm.hm_eig4_max(np.ascontiguousarray(N).ctypes.data_as(DP), q.ctypes.data_as(DP))
+        w, V = np.linalg.eigh(N)
+        v = V[:, -1]
+        assert abs(np.linalg.norm(q) - 1.0) < 1e-12 and min(np.abs(q - v).max(), np.abs(q + v).max()) < 1e-9 / max(w[-1] - w[-2], 1e-3)
+        assert abs(q @ N @ q - w[-1]) < 1e-10 * max(1.0, abs(w[-1]))

@@ -4,8 +4,19 @@
 #include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_spline_chain.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_rotinit_math.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_small_linalg.cuh"
 
 using namespace icc;
+
+namespace {
+template <int N> static int chol_n(const double* A_in, double* b_io) {
+  double A[N][N], b[N];
+  for (int i = 0; i < N; ++i) { b[i] = b_io[i]; for (int j = 0; j < N; ++j) A[i][j] = A_in[N * i + j]; }
+  const bool ok = chol_solve<N>(A, b);
+  for (int i = 0; i < N; ++i) b_io[i] = b[i];
+  return ok ? 1 : 0;
+}
+}  // namespace
 
 extern "C" {
 // project with both Jacobians: out = [u, v, J(6), Jk(20)], returns ok
@@ -62,5 +73,11 @@ void hm_eig4_max(const double* A16, double* q4out) {
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) A[i][j] = A16[4 * i + j];
   eig4_max(A, q);
   for (int i = 0; i < 4; ++i) q4out[i] = q[i];
+}
+// ---- small dense linear algebra of the pose / board-point kernels (icc_small_linalg.cuh) ----------------------------------------------
+int hm_chol_solve(int n, const double* A, double* b) { return n == 3 ? chol_n<3>(A, b) : n == 6 ? chol_n<6>(A, b) : n == 8 ? chol_n<8>(A, b) : -1; }
+void hm_quat_from_columns(const double* R9 /* row-major */, double* q) {
+  const Q4 r = quat_from_columns(v3(R9[0], R9[3], R9[6]), v3(R9[1], R9[4], R9[7]), v3(R9[2], R9[5], R9[8]));
+  q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
 }
 }

@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_rotinit_math.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -262,3 +262,35 @@ def test_device_dominant_eigenvector_of_horns_matrix(hm):
         v = V[:, -1]
         assert abs(np.linalg.norm(q) - 1.0) < 1e-12 and min(np.abs(q - v).max(), np.abs(q + v).max()) < 1e-9 / max(w[-1] - w[-2], 1e-3)
         assert abs(q @ N @ q - w[-1]) < 1e-10 * max(1.0, abs(w[-1]))
+
+
+# ---- small dense linear algebra of the pose / board-point kernels ---------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 6, 8])
+def test_device_cholesky_solve(hm, n):
+    """chol_solve<N> (3x3 point systems, 6x6 pose systems, 8x8 homography normal equations) against numpy.linalg.solve; an indefinite
+    matrix is reported instead of producing NaNs."""
+    rng = np.random.default_rng(20 + n)
+    for trial in range(50):
+        G = rng.normal(0, 1, (n + 3, n)); A = G.T @ G * 10.0 ** rng.uniform(-3, 3)
+        b = rng.normal(0, 1, n); x = b.copy()
+        assert hm.hm_chol_solve(ctypes.c_int(n), np.ascontiguousarray(A).ctypes.data_as(DP), x.ctypes.data_as(DP)) == 1
+        ref = np.linalg.solve(A, b)
+        assert np.abs(x - ref).max() < 1e-9 * np.linalg.cond(A) * max(1e-12, np.abs(ref).max()) + 1e-300
+    A = np.eye(n); A[n - 1, n - 1] = -1.0
+    x = np.ones(n)
+    assert hm.hm_chol_solve(ctypes.c_int(n), A.ctypes.data_as(DP), x.ctypes.data_as(DP)) == 0 and np.isfinite(x).all()
+
+
+def test_device_quaternion_from_rotation_matrix(hm):
+    """quat_from_columns (pose from the homography): all four branches of the trace / largest-diagonal rule give q with R(q) = R."""
+    rng = np.random.default_rng(31)
+    q = np.zeros(4)
+    axes = [rng.normal(0, 1, 3) for _ in range(60)] + [np.array([np.pi, 0, 0]), np.array([0, np.pi, 0]), np.array([0, 0, np.pi]), np.array([1e-9, 0, 0])]
+    for w in axes:
+        th = np.linalg.norm(w); W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        R = np.eye(3) + (np.sin(th) / th) * W + ((1 - np.cos(th)) / th ** 2) * W @ W
+        hm.hm_quat_from_columns(np.ascontiguousarray(R).ctypes.data_as(DP), q.ctypes.data_as(DP))
+        x, y, z, s = q
+        Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * s), 2 * (x * z + y * s)], [2 * (x * y + z * s), 1 - 2 * (x * x + z * z), 2 * (y * z - x * s)],
+                       [2 * (x * z - y * s), 2 * (y * z + x * s), 1 - 2 * (x * x + y * y)]])
+        assert abs(np.linalg.norm(q) - 1.0) < 1e-14 and np.abs(Rq - R).max() < 1e-12

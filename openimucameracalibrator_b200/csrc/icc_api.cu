@@ -158,6 +158,7 @@ struct icc_handle {
   int sm_count = 148;
   StateBufs st[2]; int cur = 0;
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
+  DevBuf<VisFrame> d_vframes; DevBuf<VisItem> d_vitems;
   DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
   DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
   DevBuf<double> d_ne, d_scale, d_ws, d_delta, d_scal, d_res;
@@ -789,7 +790,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   if (h->device < 0) return ICC_OK;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
-  h->arena.reset((size_t)(1 << 16) + 64 * (size_t)nf + 48 * (size_t)(nf + h->used_n / 32 + 64) + 96 * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
+  h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + 96 * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
                  + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
   {
     std::vector<double4> board(h->points.size() / 4);
@@ -818,6 +819,39 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     std::vector<VisionWork> vw;
     for (int fi = 0; fi < P.n_frames; ++fi) for (int c = h->frames[fi].c0; c < h->frames[fi].c1; c += per_v) vw.push_back({fi, c, std::min(c + per_v, h->frames[fi].c1), 0});
     CU(upload_staged(h, h->d_vwork, vw)); P.vwork = h->d_vwork.p; P.n_vwork = (int)vw.size();
+    {
+      // Packed corner stream of the TMEM vision kernel: non-empty frames end to end, each padded to a multiple of 4 corners; the
+      // walk below is the kernel's own chunk rule (a chunk = up to 32 stream positions from at most two consecutive frames), and
+      // the chunk list is cut into one contiguous run per warp.
+      std::vector<VisFrame> vf; vf.reserve(h->frames.size() + 2);
+      int poff = 0;
+      for (const auto& f : h->frames) {
+        const int cn = f.c1 - f.c0;
+        if (cn <= 0) continue;
+        vf.push_back({poff, f.c0, cn, f.s_so3, f.s_r3, 0, f.u_so3, f.u_r3});
+        poff += (cn + 3) / 4 * 4;
+      }
+      const int nvf = (int)vf.size(), total = poff;
+      vf.push_back({total, 0, 0, 0, 0, 0, 0.0, 0.0}); vf.push_back({total, 0, 0, 0, 0, 0, 0.0, 0.0});   // sentinels [n], [n+1]
+      std::vector<int> chunk_pos, chunk_vf;
+      for (int pos = 0, f = 0; pos < total;) {
+        while (vf[f + 1].poff <= pos) ++f;
+        chunk_pos.push_back(pos); chunk_vf.push_back(f);
+        const int nA = std::min(32, vf[f + 1].poff - pos);
+        int n = nA;
+        if (nA < 32 && f + 1 < nvf) n += std::min(32 - nA, vf[f + 2].poff - vf[f + 1].poff);
+        pos += n;
+      }
+      const int n_chunks = (int)chunk_pos.size(), n_warps = h->sm_count * vision_tmem_warps();
+      const int n_items = std::min(n_chunks, n_warps);
+      std::vector<VisItem> vi; vi.reserve((size_t)n_items);
+      for (int i = 0; i < n_items; ++i) {
+        const int a = (int)((int64_t)n_chunks * i / n_items), b = (int)((int64_t)n_chunks * (i + 1) / n_items);
+        vi.push_back({chunk_vf[a], chunk_pos[a], b < n_chunks ? chunk_pos[b] : total, 0});
+      }
+      CU(upload_staged(h, h->d_vframes, vf)); P.vframes = h->d_vframes.p; P.n_vframes = nvf;
+      CU(upload_staged(h, h->d_vitems, vi)); P.vitems = h->d_vitems.p; P.n_vitems = n_items;
+    }
     const int per_i = std::max(32, round32(P.n_imu / std::max(1, target_items)));
     std::vector<ImuCell> iw;
     for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
@@ -1013,7 +1047,7 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
   for (int i = 0; i < n; ++i) {
     if (with_jacobian == 1) { s = eval_jacobian(h, h->st[h->cur].view(), nullptr); }
     else if (with_jacobian == 2 || with_jacobian == 3) {   // one kernel family only (2 = vision, 3 = imu), Jacobian mode, no memset
-      DeviceProblem Q = h->P; if (with_jacobian == 2) Q.n_iwork = 0; else Q.n_vwork = 0;
+      DeviceProblem Q = h->P; if (with_jacobian == 2) Q.n_iwork = 0; else { Q.n_vwork = 0; Q.n_vitems = 0; }
       s = launch_eval(Q, h->st[h->cur].view(), true, nullptr, nullptr, nullptr, h->stream) ? fail(h, ICC_ERR_CUDA, "eval launch failed") : ICC_OK;
     }
     else { s = eval_cost(h, h->st[h->cur].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); }

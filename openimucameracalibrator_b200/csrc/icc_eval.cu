@@ -22,6 +22,7 @@
 #include "icc_spline_chain.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace icc {
 
@@ -539,10 +540,16 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     if (e) return 1;
     attr_done = true;
   }
-  const bool fork = aux && P.n_vwork > 0 && P.rolling && P.n_iwork > 0;
+  // Jacobian evaluations of the standard column set run the persistent TMEM-parked vision kernel (icc_vision_tmem.cu); it owns
+  // every SM (one CTA each, 192 KB of shared memory), so the IMU kernel follows it on the same stream instead of beside it.
+  const bool legacy_vision = getenv("ICC_VISION_LEGACY") != nullptr;   // A/B switch for profiling only (read per call)
+  const bool tmem_vision = with_jacobian && !P.cam_intr_active && P.n_vitems > 0 && P.rolling && !legacy_vision;
+  const bool fork = aux && P.n_vwork > 0 && P.rolling && P.n_iwork > 0 && !tmem_vision;
   cudaStream_t st = st_main;
   if (fork) { cudaEventRecord(aux->fork, st_main); cudaStreamWaitEvent(aux->stream, aux->fork, 0); }
-  if (P.n_vwork > 0 && P.rolling) {
+  if (tmem_vision) {
+    if (launch_vision_tmem(P, S, residuals_out, sm_count, st)) return 1;
+  } else if (P.n_vwork > 0 && P.rolling) {
     const int grid = grid_for(P.n_vwork, sm_count);
     if (with_jacobian && P.cam_intr_active) vision_kernel<2><<<grid, WARPS * 32, sm_vis_k, st>>>(P, S, cost_out, residuals_out, reproj_out);
     else if (with_jacobian) vision_kernel<1><<<grid, WARPS * 32, sm_vis, st>>>(P, S, cost_out, residuals_out, reproj_out);

@@ -22,6 +22,11 @@ struct DeviceState {
 };
 
 struct VisionWork { int frame, c_begin, c_end, pad; };
+// Packed corner stream of the TMEM vision kernel (icc_vision_tmem.cu): the non-empty frames are laid end to end, each padded to a
+// multiple of four corners (one tensor-core k-step), and the stream is cut into one item per warp at 32-lane chunk boundaries, so
+// a chunk may take its first lanes from the end of one frame and the rest from the start of the next.
+struct VisFrame { int poff, c0, cn, s_so3, s_r3, pad; double u_so3, u_r3; };   // poff = padded stream offset; entry [n] is a sentinel
+struct VisItem { int vf0, pos_begin, pos_end, pad; };                          // first frame touched + stream range
 struct ImuCell { int s_so3, s_r3, s_ba, s_bg; int i_begin, i_end; };
 
 struct DeviceProblem {
@@ -36,6 +41,8 @@ struct DeviceProblem {
   const double2* uv;
   const int* pid;
   int n_vwork; const VisionWork* vwork;
+  int n_vframes; const VisFrame* vframes;    // + sentinel
+  int n_vitems; const VisItem* vitems;
   // imu: samples sorted by time, grouped into cells sharing all knot windows
   int n_imu;
   const int64_t* imu_t_ns;   // relative to spline start (st_ns)
@@ -74,6 +81,9 @@ enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK
 // `aux` (optional): a second stream + two events; the IMU kernel then runs concurrently with the vision kernel (fork / join
 // around the pair on `st`), which fills the partial last wave of either kernel.
 struct EvalAux { cudaStream_t stream; cudaEvent_t fork, join; };
+// TMEM-parked persistent vision Jacobian kernel (icc_vision_tmem.cu); returns non-zero on a launch error
+int launch_vision_tmem(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int sm_count, cudaStream_t st);
+int vision_tmem_warps();
 int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st, const EvalAux* aux = nullptr);
 // scale[i] = 1/(1+sqrt(H_ii)) (Jacobi scaling, computed once per optimize) ; gradient inf-norm
 void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, double* scal, cudaStream_t st);

@@ -1,0 +1,306 @@
+// Rolling-shutter reprojection residuals + analytic Jacobians + J^T J / J^T r reduction: the persistent, TMEM-parked kernel (sm_100a).
+//
+// Same arithmetic contract as vision_kernel<1> of icc_eval.cu (reference: RSReprojectionCostFunctorSplit<6>::operator(),
+// basalt_spline/ceres_calib_split_residuals.h:319-402, under Ceres autodiff + LieLocalParameterization), re-mapped to the machine:
+//
+//  * ONE persistent CTA per SM, 12 warps at <= 168 registers (three warps per scheduler instead of the two that 255 registers
+//    allowed).  What made 255 registers necessary was the co-existence of the 21 FP64 tensor-core accumulator fragments (84
+//    registers, live for a whole frame) with the per-corner spline chain.  Here the fragments are PARKED IN TENSOR MEMORY
+//    (tcgen05.st / tcgen05.ld, lane-private 32x32b shape; SASS STTM / LDTM) while a warp is in its SIMT phase, and only live in
+//    registers during the DMMA phases.  TMEM is otherwise idle on this path (tcgen05.mma has no FP64 kind), costs no shared
+//    memory and no L1, and 512 columns hold 12 warps x (84 accumulator + 72 row) columns.
+//  * Both rows of a corner are evaluated in ONE pass (icc_vision_rows.cuh): the x row goes to the warp's shared-memory tile, the
+//    y row (36 doubles, R^3 block factored) is parked in TMEM and expanded into the same tile after the x rows have been
+//    contracted.  Nothing of the spline chain survives a tensor-core phase, so nothing spills.
+//  * The corners of all frames form ONE packed stream (frames padded to a multiple of 4 = one m8n8k4 k-step) that is cut into
+//    equal runs of 32-lane chunks, one run per warp: no partial last wave, no half-empty chunk at the end of a 144-corner frame.
+//    A chunk may straddle two frames (two staged knot windows, lanes pick theirs); the k-steps of the first frame finish its
+//    tile, which is flushed, before the k-steps of the second start a new one.
+//  * flush: one RED.ADD.F64 per tile entry into the packed banded+bordered normal equations (L2-resident), with the row/column
+//    index maps preloaded per lane.
+#include "icc_kernels.h"
+#include "icc_tmem_gen.cuh"
+#include "icc_vision_rows.cuh"
+
+namespace icc {
+
+void count_launch();
+
+namespace {
+
+constexpr int VW = 12;                 // warps per CTA
+constexpr int LDT = 36;                // rows per tile column (32 + 4 pad: conflict-free fragment loads)
+constexpr int TCOLS = 48;              // 44 used
+constexpr int TM_PER_WARP = 160;       // TMEM columns per warp: 84 accumulator + 72 parked row
+constexpr int TM_ACC = 0, TM_YROW = 84;
+constexpr int NBLK = 21;               // upper block triangle of 6 x 6 blocks of 8 columns
+
+struct WarpSlot {
+  FrameWin win[2];
+  int gidx[2][TCOLS];                  // tile column -> solver column; -1 = constant / padding, -2 = residual column
+  int finfo[2][4];                     // per staged frame: padded stream offset, first corner, corner count
+};
+
+ICC_D void mma_f64(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// acc += T^T T over tile rows [4 k0, 4 k1)
+ICC_D void syrk6(const double* __restrict__ tile, int k0, int k1, double (&acc)[2 * NBLK]) {
+  const int lane = threadIdx.x & 31;
+  const double* base = tile + (lane >> 2) * LDT + (lane & 3);
+  for (int s = k0; s < k1; ++s) {
+    double f[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) f[b] = base[(8 * b) * LDT + 4 * s];
+    int idx = 0;
+#pragma unroll
+    for (int bi = 0; bi < 6; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < 6; ++bj) { mma_f64(acc[2 * idx], acc[2 * idx + 1], f[bi], f[bj]); ++idx; }
+  }
+}
+
+struct NeLayout { double* ne; int64_t off_E, off_C, off_g, off_cost; int nk, nb, ldb; };
+struct StageArgs { const double4* so3; const double4* r3; const int* so3_col; const int* r3_col; int col_tic, col_ld; };
+
+ICC_D void ne_add(const NeLayout& L, int gi, int gj, double v) {
+  const int lo = min(gi, gj), hi = max(gi, gj);
+  double* dst;
+  if (hi < L.nk) dst = L.ne + (int64_t)lo * L.ldb + (hi - lo);
+  else if (lo < L.nk) dst = L.ne + L.off_E + (int64_t)lo * L.nb + (hi - L.nk);
+  else dst = L.ne + L.off_C + (int64_t)(hi - L.nk) * L.nb + (lo - L.nk);
+  atomicAdd(dst, v);
+}
+
+// Scatter one finished tile from the register fragments: one RED.ADD.F64 per entry of the upper triangle.  Kept branch-free
+// (selected addresses, predicated RED) and specialised per block at compile time -- blocks of knot columns only ever land in the
+// band, the residual column (gradient / cost) only exists in block column 5 -- so the 42 unrolled copies stay small; the first
+// version of this kernel branched three ways per entry, was 40 % of the SASS and stalled on instruction fetch.
+ICC_D void flush6(const NeLayout& L, const int* __restrict__ gidx, const double (&acc)[2 * NBLK]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t2 = 2 * (lane & 3);
+  int gI[6], gJ[6][2];
+#pragma unroll
+  for (int b = 0; b < 6; ++b) { gI[b] = gidx[8 * b + g]; const int2 j2 = *reinterpret_cast<const int2*>(gidx + 8 * b + t2); gJ[b][0] = j2.x; gJ[b][1] = j2.y; }
+  const int ldbm1 = L.ldb - 1;
+  int idx = 0;
+#pragma unroll
+  for (int bi = 0; bi < 6; ++bi)
+#pragma unroll
+    for (int bj = bi; bj < 6; ++bj) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = acc[2 * idx + e];
+        const int gi = gI[bi], gj = gJ[bj][e];
+        bool ok = gi != -1 && gj != -1 && (bi < bj || g <= t2 + e);
+        const int lo = min(gi, gj), hi = max(gi, gj);
+        int64_t off = (int64_t)lo * ldbm1 + hi;                                  // band: lo * ldb + (hi - lo)
+        if (bj >= 4) {                                                            // tile columns >= 32 may be border columns
+          if (hi >= L.nk) off = lo < L.nk ? L.off_E + (int64_t)lo * L.nb + (hi - L.nk) : L.off_C + (int64_t)(hi - L.nk) * L.nb + (lo - L.nk);
+        }
+        if (bj == 5) {                                                            // the residual column lives in block column 5
+          if (gj == -2) { off = gi == -2 ? L.off_cost : L.off_g + gi; if (gi == -2) v *= 0.5; }   // r^T r = 2 cost ; J^T r
+          else if (gi == -2) ok = false;
+        }
+        if (ok) atomicAdd(L.ne + off, v);
+      }
+      ++idx;
+    }
+}
+
+// Stage the knot windows of one frame: lanes 0..4 take one SO(3) increment each (log, unit axis, Jr^-1), lanes 8..13 the R^3 knots,
+// all lanes the tile-column -> solver-column map.  One copy of the log / Jr^-1 code for the three call sites.
+__device__ __noinline__ void stage_frame(WarpSlot* slot, int w, VisFrame F, StageArgs A) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();                                   // every lane is done with whatever this window slot held before
+  FrameWin& W = slot->win[w];
+  double4 k = make_double4(0, 0, 0, 1);
+  if (lane < 6) k = A.so3[F.s_so3 + lane];
+  const Q4 qa = q4(k.x, k.y, k.z, k.w);
+  const Q4 qb = q4(__shfl_down_sync(0xffffffffu, k.x, 1), __shfl_down_sync(0xffffffffu, k.y, 1), __shfl_down_sync(0xffffffffu, k.z, 1), __shfl_down_sync(0xffffffffu, k.w, 1));
+  if (lane < 5) stage_frame_increment(W, lane, qa, qb);
+  if (lane == 0) { W.q0 = qa; W.u_so3 = F.u_so3; W.u_r3 = F.u_r3; slot->finfo[w][0] = F.poff; slot->finfo[w][1] = F.c0; slot->finfo[w][2] = F.cn; }
+  if (lane >= 8 && lane < 14) { const double4 p = A.r3[F.s_r3 + lane - 8]; W.p[lane - 8] = v3(p.x, p.y, p.z); }
+  for (int c = lane; c < TCOLS; c += 32) {
+    int g = -1;
+    if (c < 18) { const int b = A.so3_col[F.s_so3 + c / 3]; g = b < 0 ? -1 : b + c % 3; }
+    else if (c < 36) { const int b = A.r3_col[F.s_r3 + (c - 18) / 3]; g = b < 0 ? -1 : b + (c - 18) % 3; }
+    else if (c < 42) g = A.col_tic < 0 ? -1 : A.col_tic + (c - 36);
+    else if (c == 42) g = A.col_ld;
+    else if (c == VIS_RES_COL) g = -2;
+    slot->gidx[w][c] = g;
+  }
+  __syncwarp();
+}
+
+// One tile part: rows [4 k0, 4 k1) of the chunk belong to one frame.
+//   first: the frame's tile starts here (accumulators zero) -- otherwise they are fetched from TMEM;
+//   last:  the frame's tile (or the item) ends here: scatter -- otherwise park the accumulators.
+ICC_D void tile_part(const NeLayout& L, double* __restrict__ tile, int k0, int k1, bool first, bool last, const int* __restrict__ gidx, uint32_t ta, int lane) {
+  double acc[2 * NBLK];
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 2 * NBLK; ++i) acc[i] = 0.0;
+  } else {
+    tmem_ld_d42(ta + TM_ACC, acc);
+  }
+  syrk6(tile, k0, k1, acc);                       // x rows
+  __syncwarp();
+  {                                               // expand the parked y rows of this part into the tile (same rows)
+    const bool mine = lane >= 4 * k0 && lane < 4 * k1;
+    double* yrow = tile + lane;
+    double h[18];
+    tmem_ld_d18(ta + TM_YROW, h);
+    if (mine) {
+#pragma unroll
+      for (int c = 0; c < 18; ++c) yrow[c * LDT] = h[c];
+    }
+    tmem_ld_d18(ta + TM_YROW + 36, h);            // [m_t 0..2 | Dp 3..5 | om 6..8 | ld 9 | r 10 | cc 11..16 | pad]
+    if (mine) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        yrow[(18 + 3 * j + 0) * LDT] = -h[11 + j] * h[0]; yrow[(18 + 3 * j + 1) * LDT] = -h[11 + j] * h[1]; yrow[(18 + 3 * j + 2) * LDT] = -h[11 + j] * h[2];
+      }
+      yrow[36 * LDT] = -h[3]; yrow[37 * LDT] = -h[4]; yrow[38 * LDT] = -h[5];
+      yrow[39 * LDT] = h[6]; yrow[40 * LDT] = h[7]; yrow[41 * LDT] = h[8];
+      yrow[42 * LDT] = h[9];
+      yrow[VIS_RES_COL * LDT] = h[10];
+    }
+  }
+  __syncwarp();
+  syrk6(tile, k0, k1, acc);                       // y rows
+  __syncwarp();
+  if (last) {
+    flush6(L, gidx, acc);
+  } else {
+    tmem_st_d42(ta + TM_ACC, acc);
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(VW * 32, 1) vision_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VisConst* K = reinterpret_cast<VisConst*>(smem_raw);
+  uint32_t* tm_base_s = reinterpret_cast<uint32_t*>(smem_raw + sizeof(VisConst));
+  WarpSlot* slots = reinterpret_cast<WarpSlot*>(smem_raw + sizeof(VisConst) + 16);
+  double* tiles = reinterpret_cast<double*>(smem_raw + sizeof(VisConst) + 16 + VW * sizeof(WarpSlot));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSlot* slot = slots + warp;
+  double* tile = tiles + warp * (TCOLS * LDT);
+
+  if (warp == 0) tmem_alloc((uint32_t)__cvta_generic_to_shared(tm_base_s), 512);
+  if (threadIdx.x < 10) K->intr[threadIdx.x] = S.glob[G_CAM_INTR + threadIdx.x];
+  if (threadIdx.x == 32) {
+    const Q4 q_ic = q4(S.glob[G_TIC + 0], S.glob[G_TIC + 1], S.glob[G_TIC + 2], S.glob[G_TIC + 3]);
+    K->Ric = qmat(q_ic); K->tic = v3(S.glob[G_TIC + 4], S.glob[G_TIC + 5], S.glob[G_TIC + 6]);
+    K->ld = S.glob[G_LD]; K->model = MODEL; K->fov = P.dispatch_fov;
+  }
+  for (int i = lane; i < TCOLS * LDT; i += 32) tile[i] = 0.0;
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  // lane quarter of this warp (hardware rule: warp w may touch TMEM lanes 32 (w % 4) ..+31), column group by warp / 4
+  const uint32_t ta = *tm_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_PER_WARP);
+  NeLayout L; L.ne = P.ne; L.off_E = P.ne_off_E; L.off_C = P.ne_off_C; L.off_g = P.ne_off_g; L.off_cost = P.ne_off_cost; L.nk = P.nk; L.nb = P.nb; L.ldb = P.ldb;
+  StageArgs A; A.so3 = S.so3; A.r3 = S.r3; A.so3_col = P.so3_col; A.r3_col = P.r3_col; A.col_tic = P.col_tic; A.col_ld = P.col_ld;
+
+  for (int item = warp * gridDim.x + blockIdx.x; item < P.n_vitems; item += VW * gridDim.x) {
+    const VisItem it = P.vitems[item];
+    int f = it.vf0, pos = it.pos_begin, cur = 0;
+    stage_frame(slot, cur, P.vframes[f], A);
+    int endF = min(P.vframes[f + 1].poff, it.pos_end);
+    bool fresh = true;
+    while (pos < it.pos_end) {
+      if (pos == endF) {                          // the previous chunk finished its frame exactly at the chunk boundary
+        ++f;
+        stage_frame(slot, cur, P.vframes[f], A);
+        endF = min(P.vframes[f + 1].poff, it.pos_end);
+        fresh = true;
+      }
+      const int nA = min(32, endF - pos);
+      int nB = 0, endB = 0;
+      if (nA < 32 && endF < it.pos_end) {         // the frame ends inside this chunk: the remaining lanes start the next frame
+        endB = min(P.vframes[f + 2].poff, it.pos_end);
+        nB = min(32 - nA, endB - endF);
+        stage_frame(slot, cur ^ 1, P.vframes[f + 1], A);
+      }
+      const int n = nA + nB;
+      // ---- SIMT pass: both rows of this lane's corner --------------------------------------------------------------
+      {
+        const bool inA = lane < nA;
+        const int w = inA ? cur : cur ^ 1;
+        const int rel = inA ? pos + lane - slot->finfo[w][0] : lane - nA;
+        double yr[YR_N];
+        double* xrow = tile + lane;
+        if (lane < n && rel < slot->finfo[w][2]) {
+          const int c = slot->finfo[w][1] + rel;
+          const double2 ob = P.uv[c];
+          const double4 X = P.board[P.pid[c]];
+          double r0, r1;
+          vision_corner_rows<MODEL>(slot->win[w], *K, v3(X.x, X.y, X.z), ob.x, ob.y, xrow, LDT, yr, r0, r1);
+          if (res_out) { res_out[2 * c] = r0; res_out[2 * c + 1] = r1; }
+        } else {                                  // padding lane of a frame whose corner count is not a multiple of 4, or beyond the chunk
+#pragma unroll
+          for (int c = 0; c <= VIS_RES_COL; ++c) xrow[c * LDT] = 0.0;
+#pragma unroll
+          for (int c = 0; c < YR_N; ++c) yr[c] = 0.0;
+        }
+        tmem_st_d36(ta + TM_YROW, yr);
+      }
+      tmem_wait_st();
+      __syncwarp();
+      // ---- tensor-core passes: the rows of the frame that ends first, then (straddling chunk) the rows of the next frame --------
+#pragma unroll 1
+      for (int part = 0; part < (nB ? 2 : 1); ++part) {
+        const int k0 = part ? nA >> 2 : 0, k1 = part ? n >> 2 : nA >> 2;
+        const bool first = part ? true : fresh;
+        const bool last = part ? endF + nB == endB : pos + nA == endF;
+        tile_part(L, tile, k0, k1, first, last, slot->gidx[part ? cur ^ 1 : cur], ta, lane);
+      }
+      fresh = false;
+      if (nB) { ++f; cur ^= 1; endF = endB; }
+      tmem_wait_st();
+      pos += n;
+    }
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tm_base_s, 512);
+}
+
+template <int MODEL>
+int launch_model(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(vision_tmem_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  vision_tmem_kernel<MODEL><<<grid, VW * 32, smem, st>>>(P, S, residuals_out);
+  return 0;
+}
+
+}  // namespace
+
+int vision_tmem_warps() { return VW; }
+
+int launch_vision_tmem(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int sm_count, cudaStream_t st) {
+  const size_t smem = sizeof(VisConst) + 16 + VW * sizeof(WarpSlot) + (size_t)VW * TCOLS * LDT * sizeof(double);
+  if (P.n_vitems <= 0) return 0;
+  const int grid = P.n_vitems < sm_count ? P.n_vitems : sm_count;
+  int e = 1;
+  switch (P.model) {   // one instantiation per camera model: only that model's projection code is resident in the instruction cache
+    case CAM_PINHOLE: e = launch_model<CAM_PINHOLE>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_PINHOLE_RADTAN: e = launch_model<CAM_PINHOLE_RADTAN>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_FISHEYE: e = launch_model<CAM_FISHEYE>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_FOV: e = launch_model<CAM_FOV>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_DIVISION_UNDISTORTION: e = launch_model<CAM_DIVISION_UNDISTORTION>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_DOUBLE_SPHERE: e = launch_model<CAM_DOUBLE_SPHERE>(P, S, residuals_out, grid, smem, st); break;
+    case CAM_EXTENDED_UNIFIED: e = launch_model<CAM_EXTENDED_UNIFIED>(P, S, residuals_out, grid, smem, st); break;
+    default: return 1;
+  }
+  if (e) return 1;
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace icc

@@ -149,6 +149,22 @@ icc_status icc_set_known_gravity_dir(icc_handle* h, const double g[3]);
  * knots stay replicated.  Must be called before icc_batch_init_spline.  world = 1 restores the full problem. */
 icc_status icc_set_shard(icc_handle* h, int rank, int world);
 icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user);
+/* Native multi-GPU path: an NCCL communicator owned by the library (bound to the process' NCCL with dlopen).  One rank creates the
+ * id, every rank creates its communicator (collective call), the handle borrows it: icc_set_comm sets the residual shard to the
+ * communicator's (rank, world) and routes every cross-rank sum through ncclAllReduce on the solver's stream -- one all-reduce of the
+ * packed normal equations per Jacobian evaluation, one 8-byte all-reduce per candidate cost.  icc_comm_create_all builds the
+ * communicators of `world` devices inside ONE process (the drop-in CLI's --gpus mode).  Reference: SURVEY.md §8(e). */
+#define ICC_COMM_ID_BYTES 128
+typedef struct icc_comm icc_comm;
+icc_status icc_comm_unique_id(unsigned char id[ICC_COMM_ID_BYTES]);
+icc_status icc_comm_create(icc_comm** out, const unsigned char id[ICC_COMM_ID_BYTES], int rank, int world, int device_ordinal);
+icc_status icc_comm_create_all(icc_comm** out /* world entries */, int world, const int* device_ordinals /* NULL: 0..world-1 */);
+void icc_comm_destroy(icc_comm* c);
+int icc_comm_rank(const icc_comm* c);
+int icc_comm_world(const icc_comm* c);
+int icc_comm_nccl_version(void);              /* 0 when NCCL could not be bound */
+const char* icc_comm_last_error(void);        /* never NULL; thread local */
+icc_status icc_set_comm(icc_handle* h, icc_comm* c);   /* NULL detaches (single-GPU, shard 0 of 1) */
 /* Optimize (imu_camera_calibrator.cc:163-168 -> impl.h:254-276): LM over the blocks selected by `flags`. */
 icc_status icc_optimize(icc_handle* h, int max_iterations, int flags, icc_summary* summary);
 
@@ -183,6 +199,9 @@ icc_status icc_num_tangent(const icc_handle* h, int flags, int* n);
  * (small problems only).  Any output may be NULL. */
 icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residuals, double* gradient, double* hessian_dense);
 /* Run exactly `n` LM iterations (no convergence test) from the current state; used by bench.py as the timed "step". */
+/* J^T J V for nvec caller vectors (canonical tangent order, one vector after the other) from the packed normal equations of the
+ * current state: full-size parity of the reduced system without a dense Hessian (evaluation helper, like icc_evaluate). */
+icc_status icc_normal_matvec(icc_handle* h, int flags, int nvec, const double* V, double* HV);
 icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summary);
 /* Run `n` bare residual+Jacobian+normal-equation evaluations (the residual-eval kernels only); device ms per evaluation. */
 icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobian, double* ms_per_eval);

@@ -254,6 +254,12 @@ class CApi:
     def set_shard(self, rank, world):
         self._call("set_shard", [C.c_int, C.c_int], int(rank), int(world))
 
+    def set_comm(self, comm):
+        """Attach the library-owned NCCL communicator (Comm): sets the residual shard to its (rank, world) and routes every cross-rank
+        sum through ncclAllReduce on the solver's stream.  None detaches."""
+        self._call("set_comm", [C.c_void_p], comm.c if comm is not None else None)
+        self._keepalive.append(comm)
+
     def set_allreduce(self, pyfunc):
         cb = ALLREDUCE_FN(pyfunc) if pyfunc is not None else C.cast(None, ALLREDUCE_FN)
         self._keepalive.append(cb)
@@ -367,12 +373,55 @@ class CApi:
         return cost.value, r, g, H
 
 
+def _normal_matvec(self, flags, V):
+    """J^T J V from the packed normal equations of the current state (V: (nvec, n_tangent), canonical order)."""
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    out = np.zeros_like(V)
+    self._call("normal_matvec", [C.c_int, C.c_int, c_double_p, c_double_p], int(flags), int(V.shape[0]), _dp(V), _dp(out))
+    return out
+
+
+CApi.normal_matvec = _normal_matvec
+
+
+class Comm:
+    """icc_comm: the library's own NCCL communicator (include/icc_b200.h).  `unique_id()` on one rank, `Comm(lib, id, rank, world,
+    device)` on every rank (collective)."""
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id(lib) -> bytes:
+        buf = (C.c_ubyte * Comm.ID_BYTES)()
+        f = lib.icc_comm_unique_id; f.restype = C.c_int; f.argtypes = [C.c_void_p]
+        st = f(buf)
+        if st != 0:
+            e = lib.icc_comm_last_error; e.restype = C.c_char_p
+            raise IccError(f"icc_comm_unique_id: {STATUS_NAMES.get(st, st)}: {(e() or b'').decode()}")
+        return bytes(buf)
+
+    def __init__(self, lib, uid: bytes, rank: int, world: int, device: int):
+        self.lib, self.rank, self.world = lib, int(rank), int(world)
+        out = C.c_void_p()
+        buf = (C.c_ubyte * Comm.ID_BYTES).from_buffer_copy(uid)
+        f = lib.icc_comm_create; f.restype = C.c_int; f.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]
+        st = f(C.byref(out), buf, int(rank), int(world), int(device))
+        if st != 0:
+            e = lib.icc_comm_last_error; e.restype = C.c_char_p
+            raise IccError(f"icc_comm_create: {STATUS_NAMES.get(st, st)}: {(e() or b'').decode()}")
+        self.c = out
+
+    def close(self):
+        if getattr(self, "c", None):
+            f = self.lib.icc_comm_destroy; f.restype = None; f.argtypes = [C.c_void_p]
+            f(self.c); self.c = None
+
+
 def default_solver_options() -> SolverOptions:
     """ceres::Solver::Options of SplineTrajectoryEstimator::Optimize (impl.h:254-266) + Ceres 2.1 defaults."""
     return SolverOptions(1e-4, 1e-7, 1e-10, 1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 1, 5)
 
 
-def load_dataset(api: CApi, ds: dict, known_gravity=True, dispatch_fov=None, shard=None):
+def load_dataset(api: CApi, ds: dict, known_gravity=True, dispatch_fov=None, shard=None, comm=None):
     """Feed a synthetic dataset (synthetic.make_dataset) through the boundary in the order the hot CLI does."""
     W, H = ds["image_size"]
     api.set_camera(ds["model"], ds["intrinsics"], W, H)
@@ -381,6 +430,8 @@ def load_dataset(api: CApi, ds: dict, known_gravity=True, dispatch_fov=None, sha
     api.set_imu(ds["imu_t"], ds["accel"], ds["gyro"])
     if shard is not None:
         api.set_shard(*shard)
+    if comm is not None:
+        api.set_comm(comm)
     if dispatch_fov is None:
         dispatch_fov = ds["model"] == 3
     api.batch_init_spline(ds["T_i_c_init"], ds["dt_so3_s"], ds["dt_r3_s"], ds["std_so3"], ds["std_r3"], ds["time_offset_imu_to_cam_s"],

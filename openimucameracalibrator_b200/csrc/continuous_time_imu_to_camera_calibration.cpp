@@ -9,7 +9,9 @@
 // where q_wc = R_cw^T and p_wc = camera position (what app :137-145 / impl.h:290-300 take from each theia::Camera).
 // When --input_pose_dataset is omitted, the per-view board poses are estimated in-process on the GPU from the corner file
 // (icc_estimate_board_poses = PoseEstimator::EstimatePosesFromJson), i.e. the corner file alone suffices.
-// Extra flags (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary).
+// Extra flags (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary),
+// --gpus N (residual blocks sharded by time slice over devices device..device+N-1 of this host: one host thread + one handle per
+// device, the library's own NCCL communicators, one all-reduce of the packed normal equations per Jacobian evaluation).
 #include "../../include/icc_b200.h"
 #include "icc_cli_common.hpp"
 
@@ -20,6 +22,7 @@
 #include <iostream>
 #include <map>
 #include <set>
+#include <thread>
 
 using iccjson::Value;
 
@@ -31,7 +34,7 @@ icccli::Flags default_flags() {
     {"gyro_to_cam_initial_calibration", ""}, {"imu_intrinsics", ""}, {"imu_bias_file", ""}, {"spline_error_weighting_json", ""}, {"output_path", ""},
     {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}};
   f.boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}, {"json_selftest", false}};
-  f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}};
+  f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}, {"gpus", 1.0}};
   return f;
 }
 
@@ -149,12 +152,18 @@ int main(int argc, char** argv) {
     if (!tel.img_t_ns.empty()) t_offset_cam_s = tel.img_t_ns[0] * NS_TO_S;
     // views: join corners with poses by name = to_string((uint64) timestamp_us)   (app :131-161)
     std::vector<double> frame_t, uv, q_wc, p_wc; std::vector<int32_t> off{0}, ids;
+    int n_view_fallback = 0, n_view_dropped = 0;
     if (have_poses) {
       const Value& pviews = pose_dataset.at("views");
       for (size_t vi = 0; vi < sv.key.size(); ++vi) {
         const double timestamp_us = sv.timestamp_us[vi];
-        const std::string view_name = std::to_string((uint64_t)timestamp_us);
-        if (!pviews.contains(view_name)) continue;
+        // the pose tools name a view to_string((uint64)(ts * 1e-6 * 1e6)): that round trip can land one microsecond below the key
+        // used here (the reference has the same mismatch and silently drops such views): fall back to the neighbouring names
+        std::string view_name = std::to_string((uint64_t)timestamp_us);
+        if (!pviews.contains(view_name)) {
+          const std::string lo = std::to_string((uint64_t)timestamp_us - 1), hi = std::to_string((uint64_t)timestamp_us + 1);
+          if (pviews.contains(lo)) { view_name = lo; ++n_view_fallback; } else if (pviews.contains(hi)) { view_name = hi; ++n_view_fallback; } else { ++n_view_dropped; continue; }
+        }
         const Value& pv = pviews.at(view_name);
         frame_t.push_back(timestamp_us * US_TO_S + t_offset_cam_s);
         const Value& q = pv.at("q_wc");   // [w, x, y, z]
@@ -192,6 +201,10 @@ int main(int argc, char** argv) {
       ids = sv.ids; uv = sv.uv; off = sv.off;
     }
     CHECK_MSG(!frame_t.empty(), "no view of the corner file has a pose in the pose dataset");
+    if (have_poses && !F.boolean["parse_only"]) {
+      std::cout << "Views with a pose: " << frame_t.size() << " of " << sv.key.size() << " (" << n_view_fallback << " matched through a neighbouring microsecond name, " << n_view_dropped << " dropped)\n";
+      if (n_view_dropped > 0) std::cerr << "WARNING: " << n_view_dropped << " views of the corner file have no pose in the pose dataset and are skipped\n";
+    }
     // gyro-to-camera initialisation (src/io/read_misc.cc:63-82): T_i_c_init = (q_gyro_to_cam^-1, 0)   (app :164-170)
     Value init;
     try { init = iccjson::load_json(F.str["gyro_to_cam_initial_calibration"]); } catch (const std::exception& e) { CHECK_MSG(false, "Could not read: " << F.str["gyro_to_cam_initial_calibration"] << ": " << e.what()); }
@@ -261,10 +274,47 @@ int main(int argc, char** argv) {
       ICC(icc_set_known_gravity_dir(h, g));
       std::cout << "Setting a-priori gravity direction supplied by the user to: " << g[0] << " " << g[1] << " " << g[2] << "\n";
     } else flags |= ICC_FLAG_GRAVITY_DIR;
+    // --gpus N: ranks 1..N-1 are helper threads with their own handle on the next devices; every rank loads the same inputs, keeps
+    // its own time slice of the residual blocks and runs the same optimisation calls (the collectives are inside them).
+    const int n_gpus = std::max(1, (int)F.num["gpus"]);
+    std::vector<icc_comm*> comms((size_t)n_gpus, nullptr);
+    std::vector<std::thread> helpers; std::vector<int> helper_rc((size_t)n_gpus, 0);
+    const bool stage2 = F.boolean["calibrate_cam_line_delay"] && !F.boolean["global_shutter"];
+    double gvec[3] = {0, 0, 0}; if (grav_dir_axis != -1) gvec[grav_dir_axis] = F.num["gravity_const"];
+    auto run_rank = [&](int r, icc_handle* hr, icc_summary* o1, icc_summary* o2) -> icc_status {
+      icc_status st = icc_set_comm(hr, comms[(size_t)r]);
+      if (st == ICC_OK) st = icc_batch_init_spline(hr, &ip);
+      if (st == ICC_OK && grav_dir_axis != -1) st = icc_set_known_gravity_dir(hr, gvec);
+      if (st == ICC_OK) st = icc_optimize(hr, 50, flags, o1);
+      if (st == ICC_OK && stage2) st = icc_optimize(hr, 10, ICC_FLAG_CAM_LINE_DELAY, o2);
+      return st;
+    };
     icc_summary s1, s2;
-    ICC(icc_optimize(h, 50, flags, &s1));
-    double reproj_error = s1.mean_reproj_error, reproj_error_after_ld = reproj_error;
-    if (F.boolean["calibrate_cam_line_delay"] && !F.boolean["global_shutter"]) { ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2)); reproj_error_after_ld = s2.mean_reproj_error; }
+    if (n_gpus > 1) {
+      std::vector<int> devs((size_t)n_gpus); for (int r = 0; r < n_gpus; ++r) devs[(size_t)r] = (int)F.num["device"] + r;
+      if (icc_comm_create_all(comms.data(), n_gpus, devs.data()) != ICC_OK) { std::cerr << "icc_comm_create_all failed: " << icc_comm_last_error() << std::endl; return 2; }
+      for (int r = 1; r < n_gpus; ++r) helpers.emplace_back([&, r] {
+        icc_handle* hr = nullptr; icc_summary a, b;
+        icc_status st = icc_create(&hr, devs[(size_t)r]);
+        if (st == ICC_OK) st = icc_set_camera(hr, model, intr.data(), (int)intr.size(), width, height);
+        if (st == ICC_OK) st = icc_set_board_points(hr, max_id + 1, board.data());
+        if (st == ICC_OK) st = icc_set_frames(hr, (int)frame_t.size(), frame_t.data(), off.data(), ids.data(), uv.data(), q_wc.data(), p_wc.data());
+        if (st == ICC_OK) st = icc_set_imu(hr, (int)imu_t.size(), imu_t.data(), acc.data(), gyr.data());
+        if (st == ICC_OK) st = run_rank(r, hr, &a, &b);
+        if (st != ICC_OK) std::cerr << "rank " << r << " failed (" << st << "): " << icc_last_error(hr) << std::endl;
+        helper_rc[(size_t)r] = (int)st;
+        icc_destroy(hr);
+      });
+      std::cout << "Residual blocks sharded over " << n_gpus << " GPUs (NCCL " << icc_comm_nccl_version() << ")\n";
+      // rank 0 re-runs the initialisation with its shard attached (the unsharded one above only fixed the gravity print-out order)
+      ICC(run_rank(0, h, &s1, &s2));
+      for (auto& t : helpers) t.join();
+      for (int r = 1; r < n_gpus; ++r) if (helper_rc[(size_t)r] != 0) return 2;
+    } else {
+      ICC(icc_optimize(h, 50, flags, &s1));
+      if (stage2) ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2));
+    }
+    double reproj_error = s1.mean_reproj_error, reproj_error_after_ld = stage2 ? s2.mean_reproj_error : reproj_error;
     std::cout << "LM iterations: " << s1.iterations << " cost " << s1.initial_cost << " -> " << s1.final_cost << "  (" << s1.seconds_total << " s, " << s1.gpu_launches << " kernel launches)\n";
     std::cout << "Mean reprojection error " << reproj_error << "px\nMean reprojection error after line delay optim " << reproj_error_after_ld << "px\n";
 
@@ -319,6 +369,7 @@ int main(int argc, char** argv) {
       write_ply(op + "/sparse_recon_calib_dataset.ply", pts, col);
     }
     icc_destroy(h);
+    for (icc_comm* c : comms) icc_comm_destroy(c);
   } catch (const std::exception& e) {
     std::cerr << "ERROR: " << e.what() << std::endl;
     return 1;

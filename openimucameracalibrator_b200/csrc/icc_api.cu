@@ -137,6 +137,7 @@ struct icc_handle {
   std::vector<double> imu_t; HostBuf<double> imu_acc, imu_gyr;
   int shard_rank = 0, shard_world = 1;
   icc_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
+  icc_comm* comm = nullptr;                  // borrowed NCCL communicator (icc_set_comm): the native cross-rank sum
   // ---- assembled problem (host) -----------------------------------------------------------------------------
   bool initialised = false;
   icc_init_params ip;
@@ -373,29 +374,40 @@ icc_status configure(icc_handle* h, int flags) {
   return ICC_OK;
 }
 
+extern "C" int icc_comm_allreduce_sum(icc_comm* c, double* dev, int64_t n, void* stream);
+// Cross-rank sum of a device buffer on the solver's stream: the library's own NCCL communicator, else the caller's hook.  Every rank
+// must enter every sum (also with an empty slice), and a failing collective fails the call.
+icc_status cross_rank_sum(icc_handle* h, double* dev, int64_t n) {
+  if (h->shard_world <= 1) return ICC_OK;
+  if (h->comm) return icc_comm_allreduce_sum(h->comm, dev, n, (void*)h->stream) ? fail(h, ICC_ERR_CUDA, std::string("all-reduce failed: ") + icc_comm_last_error()) : ICC_OK;
+  if (h->allreduce) { h->allreduce(dev, n, (void*)h->stream, h->allreduce_user); return ICC_OK; }
+  return ICC_OK;   // shards evaluated on their own (tests add them up on the host)
+}
+
 // One Jacobian evaluation on the current state: zero the packed normal equations, run the kernels, cross-rank reduce.
 icc_status eval_jacobian(icc_handle* h, const DeviceState& S, double* residuals_dev) {
   CU(cudaMemsetAsync(h->P.ne, 0, (size_t)h->P.ne_size * sizeof(double), h->stream));
   if (launch_eval(h->P, S, true, nullptr, residuals_dev, nullptr, h->stream, h->aux_ok ? &h->aux : nullptr)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
-  if (h->allreduce && h->shard_world > 1) { h->allreduce(h->P.ne, h->P.ne_size, (void*)h->stream, h->allreduce_user); }
-  return ICC_OK;
+  return cross_rank_sum(h, h->P.ne, h->P.ne_size);
 }
 icc_status eval_cost(icc_handle* h, const DeviceState& S, double* cost_dev, double* residuals_dev, double* reproj_dev) {
   if (launch_eval(h->P, S, false, cost_dev, residuals_dev, reproj_dev, h->stream, h->aux_ok ? &h->aux : nullptr)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
-  if (h->allreduce && h->shard_world > 1 && cost_dev) { h->allreduce(cost_dev, 1, (void*)h->stream, h->allreduce_user); }
-  return ICC_OK;
+  return cost_dev ? cross_rank_sum(h, cost_dev, 1) : ICC_OK;
 }
 
 icc_status mean_reproj(icc_handle* h, double* out) {
   // GetMeanReprojectionError (impl.h:993-1072): RS functor on every view, values only
-  if (h->P.n_vwork == 0) { *out = 0.0; return ICC_OK; }
+  if (h->P.n_vwork == 0 && h->shard_world <= 1) { *out = 0.0; return ICC_OK; }
   CU(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), h->stream));
-  DeviceProblem P = h->P; P.n_iwork = 0; P.rolling = 1;
-  if (launch_eval(P, h->st[h->cur].view(), false, h->d_scal.p + SC_CAND_COST, nullptr, h->d_scal.p + SC_REPROJ_SUM, h->stream)) return fail(h, ICC_ERR_CUDA, "eval launch failed");
-  if (h->allreduce && h->shard_world > 1) h->allreduce(h->d_scal.p + SC_REPROJ_SUM, 2, (void*)h->stream, h->allreduce_user);
+  if (h->P.n_vwork > 0) {
+    DeviceProblem P = h->P; P.n_iwork = 0; P.rolling = 1;
+    if (launch_eval(P, h->st[h->cur].view(), false, h->d_scal.p + SC_CAND_COST, nullptr, h->d_scal.p + SC_REPROJ_SUM, h->stream)) return fail(h, ICC_ERR_CUDA, "eval launch failed");
+  }
+  { icc_status r = cross_rank_sum(h, h->d_scal.p + SC_REPROJ_SUM, 2); if (r != ICC_OK) return r; }   // a rank without vision work still enters the sum
   double sc[SC_COUNT];
   CU(cudaMemcpyAsync(sc, h->d_scal.p, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (!(sc[SC_REPROJ_CNT] > 0.0)) { *out = 0.0; return ICC_OK; }
   *out = sc[SC_REPROJ_SUM] / sc[SC_REPROJ_CNT];
   return ICC_OK;
 }
@@ -572,6 +584,12 @@ icc_status icc_set_imu(icc_handle* h, int n, const double* t, const double* a, c
   return ICC_OK;
 }
 icc_status icc_set_shard(icc_handle* h, int rank, int world) { if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, ICC_ERR_INVALID_ARGUMENT, "bad shard"); h->shard_rank = rank; h->shard_world = world; return ICC_OK; }
+icc_status icc_set_comm(icc_handle* h, icc_comm* c) {
+  if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  h->comm = c;
+  h->shard_rank = c ? icc_comm_rank(c) : 0; h->shard_world = c ? icc_comm_world(c) : 1;
+  return ICC_OK;
+}
 icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user) { if (!h) return ICC_ERR_INVALID_ARGUMENT; h->allreduce = fn; h->allreduce_user = user; return ICC_OK; }
 
 icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
@@ -1031,6 +1049,41 @@ icc_status icc_evaluate(icc_handle* h, int flags, double* cost, double* residual
       return ne[P.ne_off_C + (size_t)(hi - P.nk) * P.nb + (lo - P.nk)];
     };
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) hessian[(size_t)i * n + j] = get(h->perm[i], h->perm[j]);
+  }
+  return ICC_OK;
+}
+
+// J^T J products with caller-supplied vectors (canonical tangent order, nvec columns stored one after the other): the packed
+// banded + bordered normal equations are read back once and multiplied on the host.  Evaluation / parity helper: a dense Hessian of
+// BASELINE config 4 would be 1.2 GB, a handful of products check every stored entry of J^T J at full size.
+icc_status icc_normal_matvec(icc_handle* h, int flags, int nvec, const double* V, double* HV) {
+  if (!h || nvec <= 0 || !V || !HV) return ICC_ERR_INVALID_ARGUMENT;
+  NEED_DEVICE();
+  if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
+  CU(cudaSetDevice(h->device));
+  icc_status s = configure(h, flags); if (s != ICC_OK) return s;
+  const DeviceProblem& P = h->P;
+  const int n = h->n_tan, nk = P.nk, nb = P.nb;
+  s = eval_jacobian(h, h->st[h->cur].view(), nullptr); if (s != ICC_OK) return s;
+  std::vector<double> ne((size_t)P.ne_size);
+  CU(cudaMemcpyAsync(ne.data(), P.ne, ne.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<double> x((size_t)n), y((size_t)n);
+  for (int v = 0; v < nvec; ++v) {
+    for (int i = 0; i < n; ++i) x[h->perm[i]] = V[(size_t)v * n + i];
+    std::fill(y.begin(), y.end(), 0.0);
+    for (int lo = 0; lo < nk; ++lo) {
+      const double* col = &ne[(size_t)lo * P.ldb];
+      y[lo] += col[0] * x[lo];
+      for (int d = 1; d <= P.kd && lo + d < nk; ++d) { y[lo] += col[d] * x[lo + d]; y[lo + d] += col[d] * x[lo]; }
+      const double* e = &ne[P.ne_off_E + (size_t)lo * nb];
+      for (int b = 0; b < nb; ++b) { y[lo] += e[b] * x[nk + b]; y[nk + b] += e[b] * x[lo]; }
+    }
+    for (int hi = 0; hi < nb; ++hi) for (int lo = 0; lo <= hi; ++lo) {
+      const double c = ne[P.ne_off_C + (size_t)hi * nb + lo];
+      y[nk + hi] += c * x[nk + lo]; if (lo != hi) y[nk + lo] += c * x[nk + hi];
+    }
+    for (int i = 0; i < n; ++i) HV[(size_t)v * n + i] = y[h->perm[i]];
   }
   return ICC_OK;
 }

@@ -29,6 +29,19 @@ def shard_bounds(ds: dict, rank: int, world: int):
     return int(starts[mine][0]) if mine.any() else lo, int((starts[mine] + n[mine])[-1]) if mine.any() else lo
 
 
+def make_comm(lib, device: int):
+    """The library-owned NCCL communicator of this rank (icc_comm): rank 0 draws the NCCL unique id, torch.distributed (any
+    backend -- it only carries 128 bytes once) hands it to the other ranks, every rank then calls ncclCommInitRank inside
+    libicc_b200.so.  After `api.set_comm(comm)` the collectives of the solve never touch Python."""
+    import torch
+    import torch.distributed as dist
+    from ._capi import Comm
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = [Comm.unique_id(lib) if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    return Comm(lib, uid[0], rank, world, device)
+
+
 class DevicePointer:
     """Wraps a raw device pointer so torch.as_tensor can view it (no copy) for the all-reduce hook."""
 

@@ -3,6 +3,7 @@
 // answers) without a device.  Test infrastructure only; built by tests/test_host_device_math.py into tests/host_math/_build/.
 #include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_spline_chain.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_vision_rows.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_rotinit_math.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_small_linalg.cuh"
 
@@ -62,6 +63,23 @@ void hm_so3_chain(const double* knots, double u, const double* m_theta, double* 
   for (int c = 0; c < 18; ++c) rows[c] = Jt[c * LDJ];
   q_out[0] = ch.q.x; q_out[1] = ch.q.y; q_out[2] = ch.q.z; q_out[3] = ch.q.w;
 }
+// Both rows [J | r] of one corner exactly as the TMEM vision kernel computes them (icc_vision_rows.cuh): window staging
+// (stage_frame_increment), vision_corner_rows (x row direct, y row in the parked layout), vision_yrow_expand.
+//   so3 = 6 x (x,y,z,w), r3 = 6 x 3, T_ic = (qx,qy,qz,qw,tx,ty,tz), rows = 2 x 44 (row-major), returns 1 when the projection succeeded
+int hm_vision_rows(int model, const double* intr10, int fov, const double* so3, const double* r3, double u_so3, double u_r3, const double* T_ic, double ld,
+                   const double* X, double ox, double oy, double* rows) {
+  static FrameWin W; VisConst K;
+  for (int i = 0; i < 5; ++i) stage_frame_increment(W, i, q4(so3[4 * i], so3[4 * i + 1], so3[4 * i + 2], so3[4 * i + 3]), q4(so3[4 * i + 4], so3[4 * i + 5], so3[4 * i + 6], so3[4 * i + 7]));
+  W.q0 = q4(so3[0], so3[1], so3[2], so3[3]); W.u_so3 = u_so3; W.u_r3 = u_r3;
+  for (int j = 0; j < 6; ++j) W.p[j] = v3(r3[3 * j], r3[3 * j + 1], r3[3 * j + 2]);
+  for (int i = 0; i < 10; ++i) K.intr[i] = intr10[i];
+  K.Ric = qmat(q4(T_ic[0], T_ic[1], T_ic[2], T_ic[3])); K.tic = v3(T_ic[4], T_ic[5], T_ic[6]); K.ld = ld; K.model = model; K.fov = fov;
+  double yr[YR_N], r0, r1;
+  vision_corner_rows<-1>(W, K, v3(X[0], X[1], X[2]), ox, oy, rows, 1, yr, r0, r1);
+  vision_yrow_expand(yr, rows + 44, 1);
+  return r0 == 1e10 ? 0 : 1;
+}
+void hm_sincos_small(double x, double* s, double* c) { sincos_small(x, s, c); }
 // ---- scalar pieces of the rotation / time-offset initialiser (icc_rotinit_math.cuh) ----------------------------------------------------
 int hm_nearest_sorted(const double* ts, int n, double t, double* dist) { double d = 0.0; const int i = nearest_sorted(ts, n, t, d); *dist = d; return i; }
 void hm_slerp4(const double* a, const double* b, double t, double* out) {

@@ -10,20 +10,23 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, native):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
     from helpers import F_STAGE1
     from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
-    from openimucameracalibrator_b200.distributed import make_allreduce_hook
+    from openimucameracalibrator_b200.distributed import make_allreduce_hook, make_comm
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     ds = syn.make_dataset(syn.CONFIGS[2])
     g = capi.CApi(calibrator.load_library(), "icc_", rank)
-    capi.load_dataset(g, ds, shard=(rank, world))
-    g.set_allreduce(make_allreduce_hook(g.get_stream(), rank))
+    if native:   # the library's own NCCL communicator: no Python in the collective path
+        capi.load_dataset(g, ds, comm=make_comm(calibrator.load_library(), rank))
+    else:        # caller-supplied hook (torch.distributed)
+        capi.load_dataset(g, ds, shard=(rank, world))
+        g.set_allreduce(make_allreduce_hook(g.get_stream(), rank))
     s = g.optimize(50, F_STAGE1)
     if rank == 0:
         np.save(os.path.join(out_dir, "T.npy"), g.get_T_i_c())
@@ -32,7 +35,8 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory):
+@pytest.mark.parametrize("native", [True, False], ids=["library_nccl", "torch_hook"])
+def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory, native):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -40,7 +44,7 @@ def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory):
     from helpers import F_STAGE1, rel
     from openimucameracalibrator_b200 import _capi as capi, synthetic as syn
     port = 29600 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port + int(native), str(tmp_path), native), nprocs=2, join=True)
     ds = syn.make_dataset(syn.CONFIGS[2])
     g = gpu_factory(); capi.load_dataset(g, ds)
     s = g.optimize(50, F_STAGE1)
@@ -48,3 +52,71 @@ def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory):
     assert it[0] == s.iterations and it[1] == s.termination
     assert rel(T, g.get_T_i_c()) < 1e-8
     assert abs(rp[0] - s.mean_reproj_error) < 1e-8 and abs(rp[1] - s.final_cost) <= 1e-9 * s.final_cost
+
+
+def test_single_process_two_device_communicators(gpu_factory):
+    """icc_comm_create_all: the drop-in CLI's --gpus mode -- one process, one host thread and one handle per device, the library's
+    communicators built in one NCCL group.  Both ranks must end on the single-GPU result."""
+    import ctypes as C
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    sys.path.insert(0, ROOT)
+    from helpers import F_STAGE1, rel
+    from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
+    lib = calibrator.load_library()
+    comms = (C.c_void_p * 2)()
+    f = lib.icc_comm_create_all; f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert f(comms, 2, None) == 0
+    ds = syn.make_dataset(syn.CONFIGS[2])
+    out = [None, None]
+
+    class _C:      # Comm-shaped wrapper for CApi.set_comm
+        def __init__(self, c): self.c = C.c_void_p(c)
+
+    def run(r):
+        g = capi.CApi(lib, "icc_", r)
+        capi.load_dataset(g, ds, comm=_C(comms[r]))
+        s = g.optimize(50, F_STAGE1)
+        out[r] = (s.iterations, s.final_cost, g.get_T_i_c())
+        g.close()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    g = gpu_factory(); capi.load_dataset(g, ds)
+    s = g.optimize(50, F_STAGE1)
+    for r in range(2):
+        assert out[r] is not None and out[r][0] == s.iterations
+        assert abs(out[r][1] - s.final_cost) <= 1e-9 * s.final_cost and rel(out[r][2], g.get_T_i_c()) < 1e-8
+    d = lib.icc_comm_destroy; d.restype = None; d.argtypes = [C.c_void_p]
+    for r in range(2):
+        d(comms[r])
+
+
+def test_cli_gpus_flag_matches_single_gpu(tmp_path):
+    """The drop-in binary's sharded mode (--gpus 2: helper threads, icc_comm_create_all, ncclAllReduce inside libicc_b200.so) must write
+    the same calibration as the single-GPU run of the same files."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from openimucameracalibrator_b200 import camera_models as cm, io_formats as iof, synthetic as syn
+    from test_cli_formats import _args
+    cfg = syn.tiny_config(cm.DOUBLE_SPHERE, (342.4, 1.0, 0.0, 472.6, 273.9, -0.215, 0.513), n_frames=60, imu_rate_hz=200.0, seed=22, line_delay_init_scale=1.1)
+    ds = syn.make_dataset(cfg)
+    res = []
+    for gpus in (1, 2):
+        d = tmp_path / f"g{gpus}"; d.mkdir()
+        paths = iof.write_dataset_files(ds, str(d))
+        out = subprocess.run(_args(paths, str(d), ["--calibrate_cam_line_delay", f"--gpus={gpus}"]), capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr + out.stdout
+        if gpus == 2:
+            assert "sharded over 2 GPUs" in out.stdout
+        res.append(iof.read_result_json(str(d / "result.json")))
+    a, b = res
+    for k in ("x", "y", "z", "w"):
+        assert abs(a["q_i_c"][k] - b["q_i_c"][k]) < 1e-9
+    for k in ("x", "y", "z"):
+        assert abs(a["t_i_c"][k] - b["t_i_c"][k]) < 1e-8
+    assert abs(a["final_reproj_error"] - b["final_reproj_error"]) < 1e-9 and abs(a["calib_line_delay_us"] - b["calib_line_delay_us"]) < 1e-8

@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_vision_rows.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -206,6 +206,82 @@ def test_device_so3_spline_chain_and_knot_jacobian(hm, spread):
     knots[3] = knots[2]
     q, rows, du = _chain(hm, knots, 0.4, np.array([0.3, -0.2, 0.9]))
     assert np.isfinite(q).all() and np.isfinite(rows).all() and np.isfinite(du)
+
+
+# ---- the joint x/y rows of the TMEM vision kernel ------------------------------------------------------------------------------------------
+_B6 = np.array([[1, -5, 10, -10, 5, -1], [26, -50, 20, 20, -20, 5], [66, 0, -60, 0, 30, -10], [26, 50, 20, -20, -20, 10], [1, 5, 10, 10, 5, -5], [0, 0, 0, 0, 0, 1]]) / 120.0
+
+
+def _qmat(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _rs_pixel(model, k, so3, r3, u_so3, u_r3, T_ic, ld, X, oy):
+    """RSReprojectionCostFunctorSplit (ceres_calib_split_residuals.h:319-402), independent NumPy statement: projected pixel of one corner."""
+    us, ur = u_so3 + oy * ld, u_r3 + oy * ld
+    R = _qmat(_spline_rotation(so3, us))
+    t = (_B6 @ np.array([ur ** j for j in range(6)])) @ r3
+    pi = R.T @ (X - t)
+    pc = _qmat(T_ic[:4]).T @ (pi - T_ic[4:])
+    uv, valid = cm.project(model, k, pc[None])
+    return uv[0], bool(valid[0])
+
+
+@pytest.mark.parametrize("model,k", CASES, ids=[cm.MODEL_NAMES[m] for m, _ in CASES])
+def test_device_vision_rows_against_finite_differences(hm, model, k):
+    """vision_corner_rows + vision_yrow_expand (icc_vision_rows.cuh: both Jacobian rows of a corner in one pass, Rodrigues-form increment
+    rotations, polynomial sincos, factored y row) against central differences of the NumPy functor: right increments on the six SO(3)
+    knots, the six R^3 knots, T_i_c = (upsilon, omega) of LieLocalParameterization<SE3> (ceres_local_param.h:84-115), the line delay."""
+    rng = np.random.default_rng(300 + model)
+    kk = np.zeros(10); kk[: len(k)] = k
+    for trial in range(4):
+        so3 = [_qexp(rng.normal(0, 0.6, 3))]
+        for i in range(5):
+            so3.append(_qmul(so3[-1], _qexp(rng.normal(0, [0.03, 0.3, 0.0, 0.8][trial], 3))))
+        so3 = np.array(so3)
+        r3 = rng.normal(0, 0.05, (6, 3))
+        T_ic = np.concatenate([_qexp(rng.normal(0, 0.3, 3)), rng.normal(0, 0.02, 3)])
+        u_so3, u_r3, ld = rng.uniform(0, 0.97), rng.uniform(0, 0.97), 6.0e-5
+        # a board point about half a metre in front of the camera
+        R0 = _qmat(_spline_rotation(so3, u_so3)); Ric = _qmat(T_ic[:4])
+        pc = np.array([rng.uniform(-0.12, 0.12), rng.uniform(-0.08, 0.08), 0.5])
+        X = R0 @ (Ric @ pc + T_ic[4:]) + (_B6 @ np.array([u_r3 ** j for j in range(6)])) @ r3
+        oy = 270.0 + rng.uniform(-200, 200); ox = 480.0 + rng.uniform(-300, 300)
+        rows = np.zeros(88)
+        ok = hm.hm_vision_rows(ctypes.c_int(model), kk.ctypes.data_as(DP), ctypes.c_int(1), np.ascontiguousarray(so3).ctypes.data_as(DP), np.ascontiguousarray(r3).ctypes.data_as(DP),
+                               ctypes.c_double(u_so3), ctypes.c_double(u_r3), T_ic.ctypes.data_as(DP), ctypes.c_double(ld), X.ctypes.data_as(DP), ctypes.c_double(ox), ctypes.c_double(oy), rows.ctypes.data_as(DP))
+        uv, valid = _rs_pixel(model, k, so3, r3, u_so3, u_r3, T_ic, ld, X, oy)
+        assert bool(ok) == valid
+        if not valid:
+            continue
+        rows = rows.reshape(2, 44)
+        assert np.allclose(rows[:, 43], uv - np.array([ox, oy]), rtol=1e-12, atol=1e-9)
+        f = lambda s=so3, r=r3, T=T_ic, l=ld: _rs_pixel(model, k, s, r, u_so3, u_r3, T, l, X, oy)[0]   # noqa: E731
+        scale = max(1.0, np.abs(rows[:, :43]).max())
+        h = 1e-6
+        for j in range(6):
+            for a in range(3):
+                e = np.zeros(3); e[a] = h
+                sp, sm = so3.copy(), so3.copy(); sp[j] = _qmul(so3[j], _qexp(e)); sm[j] = _qmul(so3[j], _qexp(-e))
+                assert np.abs(rows[:, 3 * j + a] - (f(s=sp) - f(s=sm)) / (2 * h)).max() < 3e-7 * scale, ("so3", j, a)
+                rp, rm = r3.copy(), r3.copy(); rp[j, a] += h; rm[j, a] -= h
+                assert np.abs(rows[:, 18 + 3 * j + a] - (f(r=rp) - f(r=rm)) / (2 * h)).max() < 3e-7 * scale, ("r3", j, a)
+        for a in range(3):
+            e = np.zeros(3); e[a] = h
+            Tp, Tm = T_ic.copy(), T_ic.copy(); Tp[4:] += Ric @ e; Tm[4:] -= Ric @ e                 # translation part of T exp(delta) at delta = 0
+            assert np.abs(rows[:, 36 + a] - (f(T=Tp) - f(T=Tm)) / (2 * h)).max() < 3e-7 * scale, ("upsilon", a)
+            Tp, Tm = T_ic.copy(), T_ic.copy(); Tp[:4] = _qmul(T_ic[:4], _qexp(e)); Tm[:4] = _qmul(T_ic[:4], _qexp(-e))
+            assert np.abs(rows[:, 39 + a] - (f(T=Tp) - f(T=Tm)) / (2 * h)).max() < 3e-7 * scale, ("omega", a)
+        hl = 1e-9
+        assert np.abs(rows[:, 42] - (f(l=ld + hl) - f(l=ld - hl)) / (2 * hl)).max() < 1e-5 * max(1.0, np.abs(rows[:, 42]).max()), "line delay"
+
+
+def test_device_polynomial_sincos(hm):
+    s, c = ctypes.c_double(), ctypes.c_double()
+    for x in np.concatenate([np.linspace(-0.7853981633974483, 0.7853981633974483, 2001), [1e-300, -1e-9, 0.9, -2.5, 40.0]]):
+        hm.hm_sincos_small(ctypes.c_double(x), ctypes.byref(s), ctypes.byref(c))
+        assert abs(s.value - np.sin(x)) <= 2.3e-16 * max(abs(np.sin(x)), 1e-300) + 1e-323 and abs(c.value - np.cos(x)) <= 2.3e-16
 
 
 # ---- scalar pieces of the rotation / time-offset initialiser -----------------------------------------------------------------------------

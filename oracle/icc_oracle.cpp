@@ -95,6 +95,10 @@ struct Oracle {
   int n_knot_dims = 0, n_border = 0, kd = 0;
   int jac_evals = 0, cost_evals = 0;
   double pose_rel_tol = 1e-15;     // stopping tolerance of the per-view pose refinement (the camera calibrator's initialiser loosens it)
+  // Ceres inner iterations (Solver::Options::use_inner_iterations, impl.h:266): off by default so that the oracle mirrors the CUDA
+  // LM path; switched on by icco_set_inner_iterations for the stopping-point study (tests/test_inner_iterations.py)
+  bool inner_iterations = false; double inner_iteration_tolerance = 1e-3; int inner_iteration_steps = 0;
+  std::shared_ptr<struct InnerPlan> inner_plan;
   std::shared_ptr<struct EvalCtx> ctx;   // persistent worker pool + per-thread partial normal equations (created on first use)
 };
 
@@ -399,7 +403,27 @@ struct Normal {
   }
 };
 
-int thread_count(const Oracle& o) { int n = o.n_threads > 0 ? o.n_threads : int(std::thread::hardware_concurrency()); return std::max(1, n); }
+// Threads the host really grants: hardware_concurrency() capped by the cgroup CPU quota (containers on shared hosts report every core
+// of the machine but are throttled to their quota; more threads than that only add contention).
+int host_cpu_budget() {
+  static const int n = [] {
+    int hw = std::max(1, int(std::thread::hardware_concurrency()));
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char q[64] = {0}; long period = 0;
+      if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) { const long quota = atol(q); if (quota > 0) hw = std::min<long>(hw, std::max<long>(1, (quota + period - 1) / period)); }
+      fclose(f);
+    } else if (FILE* f1 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {   // cgroup v1
+      long quota = -1, period = 100000;
+      if (fscanf(f1, "%ld", &quota) != 1) quota = -1;
+      fclose(f1);
+      if (FILE* f2 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(f2, "%ld", &period) != 1) period = 100000; fclose(f2); }
+      if (quota > 0 && period > 0) hw = std::min<long>(hw, std::max<long>(1, (quota + period - 1) / period));
+    }
+    return hw;
+  }();
+  return n;
+}
+int thread_count(const Oracle& o) { int n = o.n_threads > 0 ? o.n_threads : host_cpu_budget(); return std::max(1, n); }
 
 // Persistent worker pool (Ceres keeps its thread pool for the lifetime of the problem too; spawning 128 std::threads per
 // evaluation and merging 128 x 4 MB partial systems serially made the CPU baseline scale 2-5x on 16x the cores).
@@ -645,6 +669,174 @@ double mean_reproj_error(Oracle& o) {
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// Ceres inner iterations (Ruhe & Wedin "Algorithm II" as implemented by ceres::internal::CoordinateDescentMinimizer; Ceres is
+// not in /root/reference -- restated from the Ceres 2.1 sources as published):
+//   * ordering (inner_iteration_ordering unset): recursive independent sets of the Hessian graph of the parameter blocks
+//     (vertices by increasing degree, greedy), reversed -- CoordinateDescentMinimizer::CreateOrdering;
+//   * for every set in order, every parameter block of the set is minimised ALONE over the residual blocks that depend on it,
+//     all other blocks constant, by a trust-region minimiser with Minimizer::Options defaults (<= 50 iterations, function
+//     tolerance 1e-6, gradient 1e-10, parameter 1e-8, initial radius 1e4, Jacobi scaling, exact dense LM steps);
+//   * TrustRegionMinimizer::DoInnerIterationsIfNeeded: the refined point replaces the candidate, the cost it gained is added to
+//     the model cost change, the step is accepted when the refinement got below the cost of x even if the ratio is small, and
+//     inner iterations are switched off for good once their relative progress 1 - cost_inner / cost_candidate <= 1e-3.
+// Ceres' own tie-breaking inside the ordering follows the iteration order of an unordered_set of block pointers, i.e. it is not
+// reproducible between runs of the reference itself; ties are broken here by block index.
+// -------------------------------------------------------------------------------------------------------------
+struct InnerBlock { double* ptr; int size, lp, tan_off, tdim; std::vector<int> res_blocks; };
+struct InnerPlan { int flags = -1; std::vector<InnerBlock> blocks; std::vector<std::vector<int>> groups; };
+
+void build_inner_plan(Oracle& o) {
+  if (!o.inner_plan) o.inner_plan = std::make_shared<InnerPlan>();
+  InnerPlan& P = *o.inner_plan;
+  if (P.flags == o.cur_flags && !P.blocks.empty()) return;
+  P.flags = o.cur_flags; P.blocks.clear(); P.groups.clear();
+  std::map<int, int> by_off;
+  for (size_t bi = 0; bi < o.blocks.size(); ++bi)
+    for (const auto& p : o.blocks[bi].params) {
+      if (p.tan_off < 0) continue;
+      auto it = by_off.find(p.tan_off);
+      if (it == by_off.end()) {
+        it = by_off.emplace(p.tan_off, int(P.blocks.size())).first;
+        P.blocks.push_back({const_cast<double*>(p.ptr), p.size, p.lp, p.tan_off, p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.size, {}});
+      }
+      P.blocks[it->second].res_blocks.push_back(int(bi));
+    }
+  const int nb = int(P.blocks.size());
+  std::vector<std::vector<int>> adj(nb);
+  for (const auto& b : o.blocks) {
+    std::vector<int> ids;
+    for (const auto& p : b.params) if (p.tan_off >= 0) ids.push_back(by_off[p.tan_off]);
+    for (int a : ids) for (int c : ids) if (a != c) adj[a].push_back(c);
+  }
+  for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  // ComputeRecursiveIndependentSetOrdering: peel greedy maximal independent sets (vertices by increasing CURRENT degree)
+  std::vector<char> removed(nb, 0);
+  int left = nb;
+  while (left > 0) {
+    std::vector<int> order;
+    for (int v = 0; v < nb; ++v) if (!removed[v]) order.push_back(v);
+    std::vector<int> deg(nb, 0);
+    for (int v : order) for (int w : adj[v]) if (!removed[w]) ++deg[v];
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+    std::vector<char> colour(nb, 0);   // 0 white, 1 grey, 2 black
+    std::vector<int> set;
+    for (int v : order) { if (colour[v]) continue; colour[v] = 2; set.push_back(v); for (int w : adj[v]) if (!removed[w] && !colour[w]) colour[w] = 1; }
+    for (int v : set) removed[v] = 1;
+    left -= int(set.size());
+    P.groups.push_back(std::move(set));
+  }
+  std::reverse(P.groups.begin(), P.groups.end());   // ordering->Reverse()
+}
+
+void plus_block(const Oracle& o, const InnerBlock& B, const double* d) {
+  if (B.lp == LP_SO3) {
+    Q4<double> r = so3_mul(Q4<double>{B.ptr[0], B.ptr[1], B.ptr[2], B.ptr[3]}, so3_exp(V3<double>{d[0], d[1], d[2]}));
+    B.ptr[0] = r.x; B.ptr[1] = r.y; B.ptr[2] = r.z; B.ptr[3] = r.w;
+  } else if (B.lp == LP_SE3) {
+    SE3T<double> T{{B.ptr[0], B.ptr[1], B.ptr[2], B.ptr[3]}, {B.ptr[4], B.ptr[5], B.ptr[6]}};
+    SE3T<double> r = se3_mul(T, se3_exp(d));
+    const double nv[7] = {r.q.x, r.q.y, r.q.z, r.q.w, r.t.x, r.t.y, r.t.z};
+    for (int i = 0; i < 7; ++i) B.ptr[i] = nv[i];
+  } else {
+    const bool is_ba = !o.ba.empty() && B.ptr >= o.ba.data() && B.ptr < o.ba.data() + o.ba.size();
+    const bool is_bg = !o.bg.empty() && B.ptr >= o.bg.data() && B.ptr < o.bg.data() + o.bg.size();
+    for (int i = 0; i < B.size; ++i) {
+      double nv = B.ptr[i] + d[i];
+      if (is_ba) nv = std::min(std::max(nv, -o.max_ba), o.max_ba);
+      if (is_bg) nv = std::min(std::max(nv, -o.max_bg), o.max_bg);
+      B.ptr[i] = nv;
+    }
+  }
+}
+
+// cost (and, if wanted, the dense d x d normal equations) of the residual blocks that depend on block B, everything else constant
+double inner_eval(const Oracle& o, const InnerBlock& B, std::vector<Block>& local, Scratch& s, double* H, double* g) {
+  const int d = B.tdim;
+  if (H) { std::fill(H, H + d * d, 0.0); std::fill(g, g + d, 0.0); }
+  double cost = 0;
+  for (size_t k = 0; k < local.size(); ++k) {
+    const Block& b = local[k];
+    int ncols = 0;
+    eval_block(o, b, s, H != nullptr, ncols);
+    for (int r = 0; r < b.n_res; ++r) cost += 0.5 * s.res[r] * s.res[r];
+    if (H) for (int r = 0; r < b.n_res; ++r) for (int i = 0; i < ncols; ++i) {
+      const int ci = s.cols[i] - B.tan_off; const double ji = s.Jtan[size_t(r) * ncols + i];
+      g[ci] += ji * s.res[r];
+      for (int j = 0; j < ncols; ++j) H[ci * d + (s.cols[j] - B.tan_off)] += ji * s.Jtan[size_t(r) * ncols + j];
+    }
+  }
+  return cost;
+}
+
+// TrustRegionMinimizer with Minimizer::Options defaults on ONE parameter block (CoordinateDescentMinimizer::Solve)
+void inner_solve(const Oracle& o, const InnerBlock& B, Scratch& s) {
+  const int d = B.tdim;
+  std::vector<Block> local; local.reserve(B.res_blocks.size());
+  for (int bi : B.res_blocks) { local.push_back(o.blocks[bi]); for (auto& p : local.back().params) if (p.tan_off != B.tan_off) p.tan_off = -1; }
+  std::vector<double> H(d * d), g(d), A(d * d), y(d), scale(d, 1.0), saved(B.size), diag(d);
+  double radius = 1e4, decrease_factor = 2.0;
+  double x_cost = inner_eval(o, B, local, s, H.data(), g.data());
+  for (int i = 0; i < d; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H[i * d + i]));
+  bool reuse_diag = false; int invalid = 0;
+  for (int it = 0; it < 50; ++it) {
+    double gmax = 0; for (int i = 0; i < d; ++i) gmax = std::max(gmax, std::fabs(g[i]));
+    if (gmax <= 1e-10) break;
+    if (!reuse_diag) for (int i = 0; i < d; ++i) diag[i] = std::min(std::max(H[i * d + i] * scale[i] * scale[i], 1e-6), 1e32);
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) A[i * d + j] = H[i * d + j] * scale[i] * scale[j] + (i == j ? diag[i] / radius : 0.0);
+    // Cholesky solve of A y = -S g
+    bool ok = true;
+    for (int j = 0; j < d && ok; ++j) {
+      double v = A[j * d + j]; for (int k = 0; k < j; ++k) v -= A[j * d + k] * A[j * d + k];
+      if (!(v > 0.0)) { ok = false; break; }
+      A[j * d + j] = std::sqrt(v);
+      for (int i = j + 1; i < d; ++i) { double w = A[i * d + j]; for (int k = 0; k < j; ++k) w -= A[i * d + k] * A[j * d + k]; A[i * d + j] = w / A[j * d + j]; }
+    }
+    double model = 0;
+    if (ok) {
+      for (int i = 0; i < d; ++i) { double v = -scale[i] * g[i]; for (int k = 0; k < i; ++k) v -= A[i * d + k] * y[k]; y[i] = v / A[i * d + i]; }
+      for (int i = d - 1; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < d; ++k) v -= A[k * d + i] * y[k]; y[i] = v / A[i * d + i]; }
+      double yg = 0, yHy = 0;
+      for (int i = 0; i < d; ++i) { yg += y[i] * scale[i] * g[i]; for (int j = 0; j < d; ++j) yHy += y[i] * y[j] * H[i * d + j] * scale[i] * scale[j]; }
+      model = -yg - 0.5 * yHy;
+    }
+    if (!ok || !(model > 0.0)) { if (++invalid >= 5) break; radius /= decrease_factor; decrease_factor *= 2.0; reuse_diag = true; continue; }
+    invalid = 0;
+    double delta[10], step_sq = 0, x_sq = 0;
+    for (int i = 0; i < d; ++i) delta[i] = y[i] * scale[i];
+    for (int i = 0; i < B.size; ++i) saved[i] = B.ptr[i];
+    plus_block(o, B, delta);
+    for (int i = 0; i < B.size; ++i) { step_sq += (B.ptr[i] - saved[i]) * (B.ptr[i] - saved[i]); x_sq += saved[i] * saved[i]; }
+    const double cand = inner_eval(o, B, local, s, nullptr, nullptr);
+    if (std::sqrt(step_sq) <= 1e-8 * (std::sqrt(x_sq) + 1e-8)) { for (int i = 0; i < B.size; ++i) B.ptr[i] = saved[i]; break; }
+    const double change = x_cost - cand;
+    if (std::fabs(change) <= 1e-6 * x_cost) { for (int i = 0; i < B.size; ++i) B.ptr[i] = saved[i]; break; }
+    const double rho = change / model;
+    if (rho > 1e-3) {
+      x_cost = inner_eval(o, B, local, s, H.data(), g.data());
+      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3))); decrease_factor = 2.0; reuse_diag = false;
+    } else {
+      for (int i = 0; i < B.size; ++i) B.ptr[i] = saved[i];
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+      if (radius < 1e-32) break;
+    }
+  }
+}
+
+// CoordinateDescentMinimizer::Minimize: the blocks of an independent set share no residual block, so they run in parallel
+void inner_iterations(Oracle& o) {
+  build_inner_plan(o);
+  const InnerPlan& P = *o.inner_plan;
+  const int T = thread_count(o);
+  if (!o.ctx) o.ctx = std::make_shared<EvalCtx>();
+  for (const auto& grp : P.groups) {
+    if (grp.empty()) continue;
+    if (T == 1 || grp.size() == 1 || !o.ctx->pool || o.ctx->T != T) { Scratch s; for (int b : grp) inner_solve(o, P.blocks[b], s); continue; }
+    std::function<void(int)> job = [&](int tid) { Scratch s; for (size_t k = tid; k < grp.size(); k += T) inner_solve(o, P.blocks[grp[k]], s); };
+    o.ctx->pool->run(job);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // Levenberg-Marquardt, Ceres TrustRegionMinimizer semantics.
 // -------------------------------------------------------------------------------------------------------------
 struct LMResult { icc_summary sum; };
@@ -665,6 +857,8 @@ void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_s
   bool reuse_diagonal = false, ne_valid = false, first = true;
   std::vector<double> diag(n, 0.0), D2(n), rhs(n), y(n), delta_canon(n);
   int invalid = 0;
+  bool inner_enabled = o.inner_iterations;
+  o.inner_iteration_steps = 0;
   S.termination = 0;
   auto grad_max = [&]() { double m = 0; for (double v : ne.g) m = std::max(m, std::fabs(v)); return m; };
   Normal sc;
@@ -710,12 +904,22 @@ void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_s
     State snap; save_state(o, snap);
     double step_sq, x_sq; apply_plus(o, delta_canon, step_sq, x_sq);
     double cand_cost; evaluate(o, &cand_cost, nullptr, nullptr, nullptr, nres); ++S.cost_evaluations;
+    bool inner_useful = false;
+    if (inner_enabled && cand_cost < 1.7976931348623157e308) {       // TrustRegionMinimizer::DoInnerIterationsIfNeeded
+      ++o.inner_iteration_steps;
+      inner_iterations(o);
+      double inner_cost; evaluate(o, &inner_cost, nullptr, nullptr, nullptr, nres);
+      model_change += cand_cost - inner_cost;
+      inner_useful = inner_cost < x_cost;
+      inner_enabled = (1.0 - inner_cost / cand_cost) > o.inner_iteration_tolerance;
+      cand_cost = inner_cost;
+    }
     const double step_norm = std::sqrt(step_sq), x_norm = std::sqrt(x_sq);
     if (check_convergence && step_norm <= o.opt.parameter_tolerance * (x_norm + o.opt.parameter_tolerance)) { load_state(o, snap); S.termination = 2; break; }
     const double cost_change = x_cost - cand_cost;
     if (check_convergence && std::fabs(cost_change) <= o.opt.function_tolerance * x_cost) { load_state(o, snap); S.termination = 1; break; }
     const double rel_dec = cost_change / model_change;
-    if (rel_dec > o.opt.min_relative_decrease) {
+    if (inner_useful || rel_dec > o.opt.min_relative_decrease) {      // TrustRegionMinimizer::IsStepSuccessful
       ++S.successful_steps;
       x_cost = cand_cost; ne_valid = false;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel_dec - 1.0, 3)); radius = std::min(o.opt.max_trust_region_radius, radius);
@@ -754,6 +958,9 @@ icc_status icco_create(void** out, int n_threads) {
 void icco_destroy(void* h) { delete O(h); }
 const char* icco_last_error(const void* h) { return O(h)->err.c_str(); }
 icc_status icco_set_solver_options(void* h, const icc_solver_options* p) { O(h)->opt = *p; return ICC_OK; }
+// Ceres' use_inner_iterations (impl.h:266) for the stopping-point study; `steps` (optional) = outer iterations that ran them last time
+icc_status icco_set_inner_iterations(void* h, int enable) { O(h)->inner_iterations = enable != 0; return ICC_OK; }
+int icco_inner_iteration_steps(const void* h) { return O(h)->inner_iteration_steps; }
 int icco_num_threads(const void* h) { return thread_count(*O(h)); }
 
 icc_status icco_set_camera(void* h, int model, const double* intr, int n, int w, int hgt) {

@@ -122,5 +122,5 @@ def test_config3_whole_sequence_both_stages_against_oracle(oracle_factory, gpu_f
     s2g, s2o = g.optimize(10, F_STAGE2), o.optimize(10, F_STAGE2)
     assert s2g.iterations == s2o.iterations and s2g.num_tangent == 1
     assert abs(g.get_line_delay() - o.get_line_delay()) <= 1e-7 * abs(o.get_line_delay())
-    assert abs(g.get_line_delay() - ds["truth"]["line_delay"]) <= 0.02 * ds["truth"]["line_delay"]     # init was 10 % off
+    # (with the reference's function_tolerance = 1e-4 the one-parameter stage stops where the oracle stops, not at the truth)
     assert rel(g.get_T_i_c(), o.get_T_i_c()) < 1e-8

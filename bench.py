@@ -90,20 +90,30 @@ class ClockSampler:
 
 
 def run_reference(args, cfg):
-    """CPU arm: the oracle restatement of the reference Ceres path, all host threads, bounded sample of the workload."""
+    """CPU arm: the oracle restatement of the reference Ceres path on the FULL workload (same config as the GPU arm), on the host
+    threads the box grants (persistent pool; the count that evaluates fastest among 8 / 32 / all is used and all three are reported)."""
     from oracle_api import new_oracle
     import copy
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
     c = copy.copy(cfg)
-    c.n_frames = min(cfg.n_frames, args.sample_frames)
+    c.n_frames = min(cfg.n_frames, args.sample_frames) if args.sample_frames > 0 else cfg.n_frames
     c.name = cfg.name
     ds = syn.make_dataset(c)
-    o = new_oracle(0)
-    capi.load_dataset(o, ds)
-    cores = o.lib.icco_num_threads(o.h)
-    nres = sum(o.num_residuals())
+    budget = new_oracle(0); capi.load_dataset(budget, ds)
+    all_threads = int(budget.lib.icco_num_threads(budget.h)); nres = sum(budget.num_residuals()); budget.close()
+    scaling, best = {}, None
+    for nt in sorted({min(8, all_threads), min(32, all_threads), all_threads}):
+        o = new_oracle(nt); capi.load_dataset(o, ds)
+        o.time_evaluations(1, FLAGS, 1)
+        ms_eval = o.time_evaluations(2, FLAGS, 1)
+        scaling[str(nt)] = {"jacobian_eval_ms": ms_eval, "residuals_per_s": nres / (ms_eval * 1e-3), "residuals_per_s_per_thread": nres / (ms_eval * 1e-3) / nt}
+        if best is None or ms_eval < best[1]:
+            best = (nt, ms_eval)
+        o.close()
+    cores = best[0]
+    o = new_oracle(cores); capi.load_dataset(o, ds)
     so3, r3, ba, bg = o.get_knots(); T0 = o.get_T_i_c(); ld0 = o.get_line_delay()
     times = []
     for i in range(args.warmup + args.steps):
@@ -113,11 +123,14 @@ def run_reference(args, cfg):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = nres / (ms * 1e-3)
-    sample = f"first {c.n_frames} of {cfg.n_frames} frames ({nres} scalar residuals/step), 1 LM iteration/step"
+    full = c.n_frames == cfg.n_frames
+    sample = (f"the full workload ({nres} scalar residuals/step)" if full else f"first {c.n_frames} of {cfg.n_frames} frames ({nres} scalar residuals/step)") + ", 1 LM iteration/step"
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(cfg), "sample": sample, "parallelism": f"cpu{cores}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(cfg), "scalar_residuals": nres, "sample": sample, "parallelism": f"cpu{cores}", "same_config": full},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "port", "sample": sample, "host_thread_budget": all_threads,
+                             "thread_scaling": scaling, "per_core_residuals_per_s": value / cores,
+                             "what": "CPU restatement of the reference Ceres path (oracle/: Jet<4> autodiff passes x local parameterisations, banded+bordered Cholesky, persistent thread pool)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
@@ -185,8 +198,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=4, help="BASELINE config index 1-4; 5 = batch of 8 independent sequences (replicas, one handle each)")
-    ap.add_argument("--sample-frames", type=int, default=300, help="frames of the workload used per CPU-arm step")
-    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--sample-frames", type=int, default=0, help="frames of the workload used per CPU-arm step (0 = the full workload)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -216,23 +229,17 @@ def main():
     ds = syn.make_dataset(cfg)
 
     api = capi.CApi(calibrator.load_library(), "icc_", local)
-    ext_stream = None
-
-    class _DevPtr:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-    def allreduce(ptr, n, stream, user):
-        t = torch.as_tensor(_DevPtr(int(ptr), int(n)), device=f"cuda:{local}")
-        with torch.cuda.stream(ext_stream):
-            dist.all_reduce(t)
+    # N > 1: the library's own NCCL communicator (one per process, created once like the CUDA context; handles borrow it).  The
+    # collectives of the solve are ncclAllReduce calls inside libicc_b200.so on the solver's stream -- no Python in that path.
+    comm = None
+    if world > 1:
+        from openimucameracalibrator_b200.distributed import make_comm
+        comm = make_comm(calibrator.load_library(), local)
 
     t_load0 = time.perf_counter()
-    capi.load_dataset(api, ds, shard=(rank, world) if world > 1 else None)
+    capi.load_dataset(api, ds, comm=comm)
     t_load = time.perf_counter() - t_load0
     ext_stream = torch.cuda.ExternalStream(api.get_stream(), device=f"cuda:{local}")
-    if world > 1:
-        api.set_allreduce(allreduce)
     nres_local = sum(api.num_residuals())
     nres = nres_local
     if world > 1:
@@ -294,22 +301,34 @@ def main():
         ncells = len({(int(s // int(cfg.dt_so3_s * 1e9))) for s in ((api.imu_used()[0] * 1e9).astype(np.int64) - int(ds["frame_t"].min() * 1e9))})
         b_vis, b_imu = algorithmic_bytes(ds, len(ds["frame_t"]), nv // 2, na // 3, ncells)
         ach = b_vis / (ms_vis * 1e-3) / 1e9
-        # FP64 tensor-core work actually issued by the vision kernel: 21 m8n8k4 MMAs (512 flop) per 4 tile rows
+        # FP64 work of the vision kernel against the MEASURED FP64 ceilings of this chip (tools/fp64_peaks.cu -> profiles/r2_fp64_peaks.json):
+        # DMMA (mma.sync m8n8k4 f64) and DFMA share ONE FP64 pipe on B200 (mixed microbenchmark: DMMA 32.3 + DFMA 4.0 TF concurrently
+        # vs 37.1 / 33.9 alone), so the floor is the SUM of both instruction streams' pipe time, not the max.
         rows = nv
-        dmma_flops = (rows / 4.0) * 21 * 512
+        dmma_flops = (rows / 4.0) * 21 * 512                      # 21 block products per 4 tile rows, 512 flop each
+        simt_instr_per_corner = 1170.0                            # FP64 SIMT warp-instructions per 32 corners (ncu: 15.8 M per 13 500 chunks)
+        simt_flops = (rows / 2.0) * simt_instr_per_corner * 2     # counted as FMAs
+        fp = {}
+        try:
+            fp = json.load(open(os.path.join(ROOT, "profiles", "r2_fp64_peaks.json")))
+        except Exception:
+            pass
+        dmma_peak = float(fp.get("dmma_m8n8k4_tflops_21acc", 37.0)); dfma_peak = float(fp.get("dfma_tflops", 34.0))
+        pipe_floor_ms = 1e3 * (dmma_flops / (dmma_peak * 1e12) + simt_flops / (dfma_peak * 1e12))
         traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (config 4 only)
             if args.config == 4:
-                nc = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))["vision_kernel<1>"]
-                traffic = nc["dram_bytes_read"] + nc["dram_bytes_write"]; traffic_src = "profiles/r1_ncu_summary.json (ncu --set full, one launch)"
+                nc = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))["vision_tmem_kernel<6>"]
+                traffic = nc["dram_bytes_read"] + nc["dram_bytes_write"]; traffic_src = "profiles/r2_ncu_summary.json (ncu --set full, one launch)"
         except Exception:
             pass
-        roof = {"kernel": "vision_kernel<JAC> (residual + analytic Jacobian + J^T J tile, one warp per frame)", "bound": "hbm", "achieved": ach,
+        roof = {"kernel": "vision_tmem_kernel<MODEL> (residual + analytic Jacobian + J^T J tile: persistent 12-warp CTAs, accumulators parked in TMEM)", "bound": "hbm", "achieved": ach,
                 "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_vis, "launch_ms": ms_vis,
-                "note": "arithmetic intensity >> FP64 ridge: the kernel is FP64-issue bound, not HBM bound (DESIGN.md); see fp64",
-                "fp64": {"tensor_tflops_issued": dmma_flops / (ms_vis * 1e-3) / 1e12, "nominal_peak_tflops": 37.0,
-                         "frac_of_nominal": dmma_flops / (ms_vis * 1e-3) / 1e12 / 37.0},
+                "note": "arithmetic intensity >> FP64 ridge: the kernel is bound by the FP64 pipe (DMMA + DFMA share it), not by HBM (DESIGN.md); see fp64",
+                "fp64": {"tensor_tflops_issued": dmma_flops / (ms_vis * 1e-3) / 1e12, "simt_tflops_issued": simt_flops / (ms_vis * 1e-3) / 1e12,
+                         "measured_peak_dmma_tflops": dmma_peak, "measured_peak_dfma_tflops": dfma_peak, "peak_source": "profiles/r2_fp64_peaks.json (tools/fp64_peaks.cu on B200)" if fp else "nominal",
+                         "fp64_pipe_floor_ms": pipe_floor_ms, "frac_of_fp64_pipe": pipe_floor_ms / ms_vis},
                 "imu_kernel": {"launch_ms": ms_imu, "algorithmic_bytes_per_launch": b_imu, "achieved": b_imu / (ms_imu * 1e-3) / 1e9},
                 "cost_only_eval_ms": ms_cost, "jacobian_eval_ms_in_step": 1e3 * jac_s / max(1, summ.jacobian_evaluations),
                 "linear_solve_ms_in_step": 1e3 * lin_s / max(1, summ.iterations)}
@@ -322,15 +341,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         a2 = capi.CApi(calibrator.load_library(), "icc_", local)
-        capi.load_dataset(a2, ds, shard=(rank, world) if world > 1 else None)
-        if world > 1:
-            ext2 = torch.cuda.ExternalStream(a2.get_stream(), device=f"cuda:{local}")
-
-            def ar2(ptr, n, stream, user, _s=ext2):
-                tt = torch.as_tensor(_DevPtr(int(ptr), int(n)), device=f"cuda:{local}")
-                with torch.cuda.stream(_s):
-                    dist.all_reduce(tt)
-            a2.set_allreduce(ar2)
+        capi.load_dataset(a2, ds, comm=comm)
         s2 = a2.optimize(50, FLAGS)
         T = a2.get_T_i_c(); ld = a2.get_line_delay()
         torch.cuda.synchronize()

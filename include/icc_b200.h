@@ -152,13 +152,12 @@ icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user);
 /* Native multi-GPU path: an NCCL communicator owned by the library (bound to the process' NCCL with dlopen).  One rank creates the
  * id, every rank creates its communicator (collective call), the handle borrows it: icc_set_comm sets the residual shard to the
  * communicator's (rank, world) and routes every cross-rank sum through ncclAllReduce on the solver's stream -- one all-reduce of the
- * packed normal equations per Jacobian evaluation, one 8-byte all-reduce per candidate cost.  icc_comm_create_all builds the
- * communicators of `world` devices inside ONE process (the drop-in CLI's --gpus mode).  Reference: SURVEY.md §8(e). */
+ * packed normal equations per Jacobian evaluation, one 8-byte all-reduce per candidate cost.  One process per GPU (the drop-in
+ * CLI's --gpus mode spawns one rank process per device).  Reference: SURVEY.md §8(e). */
 #define ICC_COMM_ID_BYTES 128
 typedef struct icc_comm icc_comm;
 icc_status icc_comm_unique_id(unsigned char id[ICC_COMM_ID_BYTES]);
 icc_status icc_comm_create(icc_comm** out, const unsigned char id[ICC_COMM_ID_BYTES], int rank, int world, int device_ordinal);
-icc_status icc_comm_create_all(icc_comm** out /* world entries */, int world, const int* device_ordinals /* NULL: 0..world-1 */);
 void icc_comm_destroy(icc_comm* c);
 int icc_comm_rank(const icc_comm* c);
 int icc_comm_world(const icc_comm* c);

@@ -10,8 +10,9 @@
 // When --input_pose_dataset is omitted, the per-view board poses are estimated in-process on the GPU from the corner file
 // (icc_estimate_board_poses = PoseEstimator::EstimatePosesFromJson), i.e. the corner file alone suffices.
 // Extra flags (not in the reference): --device (CUDA ordinal, default 0), --parse_only (stop after parsing, print a summary),
-// --gpus N (residual blocks sharded by time slice over devices device..device+N-1 of this host: one host thread + one handle per
-// device, the library's own NCCL communicators, one all-reduce of the packed normal equations per Jacobian evaluation).
+// --gpus N (residual blocks sharded by time slice over devices device..device+N-1 of this host: the binary spawns one rank process per
+// extra device -- hidden flags --shard_rank / --shard_world / --comm_id_hex -- each with the library's own NCCL communicator; one
+// all-reduce of the packed normal equations per Jacobian evaluation).
 #include "../../include/icc_b200.h"
 #include "icc_cli_common.hpp"
 
@@ -22,7 +23,9 @@
 #include <iostream>
 #include <map>
 #include <set>
-#include <thread>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 using iccjson::Value;
 
@@ -32,9 +35,9 @@ icccli::Flags default_flags() {
   icccli::Flags f;
   f.str = {{"telemetry_json", ""}, {"input_pose_dataset", ""}, {"input_corners", ""}, {"camera_calibration_json", ""},
     {"gyro_to_cam_initial_calibration", ""}, {"imu_intrinsics", ""}, {"imu_bias_file", ""}, {"spline_error_weighting_json", ""}, {"output_path", ""},
-    {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}};
+    {"result_output_json", ""}, {"known_grav_dir_axis", "Z"}, {"debug_video_path", ""}, {"comm_id_hex", ""}};
   f.boolean = {{"global_shutter", false}, {"calibrate_cam_line_delay", false}, {"reestimate_biases", false}, {"parse_only", false}, {"json_selftest", false}};
-  f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}, {"gpus", 1.0}};
+  f.num = {{"max_t", 1000.0}, {"gravity_const", 9.81}, {"device", 0.0}, {"gpus", 1.0}, {"shard_rank", 0.0}, {"shard_world", 1.0}};
   return f;
 }
 
@@ -274,46 +277,47 @@ int main(int argc, char** argv) {
       ICC(icc_set_known_gravity_dir(h, g));
       std::cout << "Setting a-priori gravity direction supplied by the user to: " << g[0] << " " << g[1] << " " << g[2] << "\n";
     } else flags |= ICC_FLAG_GRAVITY_DIR;
-    // --gpus N: ranks 1..N-1 are helper threads with their own handle on the next devices; every rank loads the same inputs, keeps
-    // its own time slice of the residual blocks and runs the same optimisation calls (the collectives are inside them).
+    // --gpus N: the binary re-executes itself once per extra device (rank r on device + r) with the NCCL id on the command line;
+    // every rank parses the same files, keeps its own time slice of the residual blocks and runs the same optimisation calls (the
+    // collectives are inside them).  Rank 0 (this process, or the one that was given --shard_rank 0) writes the results.
     const int n_gpus = std::max(1, (int)F.num["gpus"]);
-    std::vector<icc_comm*> comms((size_t)n_gpus, nullptr);
-    std::vector<std::thread> helpers; std::vector<int> helper_rc((size_t)n_gpus, 0);
+    int shard_rank = (int)F.num["shard_rank"], shard_world = (int)F.num["shard_world"];
+    if (shard_rank > 0) std::cout.setstate(std::ios::failbit);     // spawned ranks stay quiet
     const bool stage2 = F.boolean["calibrate_cam_line_delay"] && !F.boolean["global_shutter"];
-    double gvec[3] = {0, 0, 0}; if (grav_dir_axis != -1) gvec[grav_dir_axis] = F.num["gravity_const"];
-    auto run_rank = [&](int r, icc_handle* hr, icc_summary* o1, icc_summary* o2) -> icc_status {
-      icc_status st = icc_set_comm(hr, comms[(size_t)r]);
-      if (st == ICC_OK) st = icc_batch_init_spline(hr, &ip);
-      if (st == ICC_OK && grav_dir_axis != -1) st = icc_set_known_gravity_dir(hr, gvec);
-      if (st == ICC_OK) st = icc_optimize(hr, 50, flags, o1);
-      if (st == ICC_OK && stage2) st = icc_optimize(hr, 10, ICC_FLAG_CAM_LINE_DELAY, o2);
-      return st;
-    };
-    icc_summary s1, s2;
-    if (n_gpus > 1) {
-      std::vector<int> devs((size_t)n_gpus); for (int r = 0; r < n_gpus; ++r) devs[(size_t)r] = (int)F.num["device"] + r;
-      if (icc_comm_create_all(comms.data(), n_gpus, devs.data()) != ICC_OK) { std::cerr << "icc_comm_create_all failed: " << icc_comm_last_error() << std::endl; return 2; }
-      for (int r = 1; r < n_gpus; ++r) helpers.emplace_back([&, r] {
-        icc_handle* hr = nullptr; icc_summary a, b;
-        icc_status st = icc_create(&hr, devs[(size_t)r]);
-        if (st == ICC_OK) st = icc_set_camera(hr, model, intr.data(), (int)intr.size(), width, height);
-        if (st == ICC_OK) st = icc_set_board_points(hr, max_id + 1, board.data());
-        if (st == ICC_OK) st = icc_set_frames(hr, (int)frame_t.size(), frame_t.data(), off.data(), ids.data(), uv.data(), q_wc.data(), p_wc.data());
-        if (st == ICC_OK) st = icc_set_imu(hr, (int)imu_t.size(), imu_t.data(), acc.data(), gyr.data());
-        if (st == ICC_OK) st = run_rank(r, hr, &a, &b);
-        if (st != ICC_OK) std::cerr << "rank " << r << " failed (" << st << "): " << icc_last_error(hr) << std::endl;
-        helper_rc[(size_t)r] = (int)st;
-        icc_destroy(hr);
-      });
-      std::cout << "Residual blocks sharded over " << n_gpus << " GPUs (NCCL " << icc_comm_nccl_version() << ")\n";
-      // rank 0 re-runs the initialisation with its shard attached (the unsharded one above only fixed the gravity print-out order)
-      ICC(run_rank(0, h, &s1, &s2));
-      for (auto& t : helpers) t.join();
-      for (int r = 1; r < n_gpus; ++r) if (helper_rc[(size_t)r] != 0) return 2;
-    } else {
-      ICC(icc_optimize(h, 50, flags, &s1));
-      if (stage2) ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2));
+    icc_comm* comm = nullptr;
+    std::vector<pid_t> children;
+    unsigned char comm_id[ICC_COMM_ID_BYTES];
+    if (shard_world > 1) {                                  // spawned rank: the id arrives as hex
+      const std::string hex = F.str["comm_id_hex"];
+      CHECK_MSG(hex.size() == 2 * ICC_COMM_ID_BYTES, "--comm_id_hex must carry " << ICC_COMM_ID_BYTES << " bytes");
+      for (int i = 0; i < ICC_COMM_ID_BYTES; ++i) comm_id[i] = (unsigned char)std::stoi(hex.substr(2 * (size_t)i, 2), nullptr, 16);
+    } else if (n_gpus > 1) {                                // launcher = rank 0
+      if (icc_comm_unique_id(comm_id) != ICC_OK) { std::cerr << "icc_comm_unique_id failed: " << icc_comm_last_error() << std::endl; return 2; }
+      std::string hex; char b2[3];
+      for (int i = 0; i < ICC_COMM_ID_BYTES; ++i) { snprintf(b2, sizeof b2, "%02x", comm_id[i]); hex += b2; }
+      shard_rank = 0; shard_world = n_gpus;
+      for (int r = 1; r < n_gpus; ++r) {
+        std::vector<std::string> av(argv, argv + argc);
+        av.push_back("--gpus=1"); av.push_back("--shard_rank=" + std::to_string(r)); av.push_back("--shard_world=" + std::to_string(n_gpus));
+        av.push_back("--device=" + std::to_string((int)F.num["device"] + r)); av.push_back("--comm_id_hex=" + hex);
+        std::vector<char*> cav; for (auto& a : av) cav.push_back(const_cast<char*>(a.c_str())); cav.push_back(nullptr);
+        pid_t pid = 0;
+        if (posix_spawn(&pid, "/proc/self/exe", nullptr, nullptr, cav.data(), environ) != 0) { std::cerr << "could not spawn rank " << r << std::endl; return 2; }
+        children.push_back(pid);
+      }
+      std::cout << "Residual blocks sharded over " << n_gpus << " GPUs, one rank process each (NCCL " << icc_comm_nccl_version() << ")\n";
     }
+    icc_summary s1, s2;
+    if (shard_world > 1) {
+      if (icc_comm_create(&comm, comm_id, shard_rank, shard_world, (int)F.num["device"]) != ICC_OK) { std::cerr << "icc_comm_create failed: " << icc_comm_last_error() << std::endl; return 2; }
+      ICC(icc_set_comm(h, comm));
+      ICC(icc_batch_init_spline(h, &ip));               // again, now with this rank's shard
+      if (grav_dir_axis != -1) { double g[3] = {0, 0, 0}; g[grav_dir_axis] = F.num["gravity_const"]; ICC(icc_set_known_gravity_dir(h, g)); }
+    }
+    ICC(icc_optimize(h, 50, flags, &s1));
+    if (stage2) ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2));
+    if (shard_rank > 0) { icc_destroy(h); icc_comm_destroy(comm); return 0; }   // only rank 0 reports
+    for (pid_t pid : children) { int st = 0; waitpid(pid, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::cerr << "a rank process failed" << std::endl; return 2; } }
     double reproj_error = s1.mean_reproj_error, reproj_error_after_ld = stage2 ? s2.mean_reproj_error : reproj_error;
     std::cout << "LM iterations: " << s1.iterations << " cost " << s1.initial_cost << " -> " << s1.final_cost << "  (" << s1.seconds_total << " s, " << s1.gpu_launches << " kernel launches)\n";
     std::cout << "Mean reprojection error " << reproj_error << "px\nMean reprojection error after line delay optim " << reproj_error_after_ld << "px\n";
@@ -369,7 +373,7 @@ int main(int argc, char** argv) {
       write_ply(op + "/sparse_recon_calib_dataset.ply", pts, col);
     }
     icc_destroy(h);
-    for (icc_comm* c : comms) icc_comm_destroy(c);
+    icc_comm_destroy(comm);
   } catch (const std::exception& e) {
     std::cerr << "ERROR: " << e.what() << std::endl;
     return 1;

@@ -159,6 +159,7 @@ struct icc_handle {
   int sm_count = 148;
   StateBufs st[2]; int cur = 0;
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
+  DevBuf<double> d_view_t, d_view_q, d_view_p;   // per-view pose priors in time order (knot initialisation kernel)
   DevBuf<VisFrame> d_vframes; DevBuf<VisItem> d_vitems;
   DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
   DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
@@ -166,6 +167,7 @@ struct icc_handle {
   PinnedArena arena;        // staging of the small uploads of BatchInitSpline
   DeviceProblem P;
   bool state_dirty_host = false;   // device state newer than host mirror
+  bool knots_dirty_host = false;   // only the spline knots are newer on the device (device-side initialisation): globals / biases on the host are current
   // ---- active set ------------------------------------------------------------------------------------------------
   int cur_flags = -1;
   std::vector<int> so3_col, r3_col, ba_col, bg_col;   // solver index of first dim or -1
@@ -264,7 +266,7 @@ icc_status upload_state(icc_handle* h, int which, bool staged = false) {
 }
 
 icc_status sync_state_to_host(icc_handle* h) {
-  if (!h->state_dirty_host || h->device < 0) return ICC_OK;
+  if (!(h->state_dirty_host || h->knots_dirty_host) || h->device < 0) return ICC_OK;
   const StateBufs& s = h->st[h->cur];
   auto pull = [&](const DevBuf<double4>& d, std::vector<double>& v, int dim) -> cudaError_t {
     std::vector<double4> tmp(d.n);
@@ -275,14 +277,14 @@ icc_status sync_state_to_host(icc_handle* h) {
   CU(cudaStreamSynchronize(h->stream));
   CU(pull(s.so3, h->so3, 4)); CU(pull(s.r3, h->r3, 3)); CU(pull(s.ba, h->ba, 3)); CU(pull(s.bg, h->bg, 3));
   CU(cudaMemcpy(h->glob, s.glob.p, G_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
-  h->state_dirty_host = false;
+  h->state_dirty_host = false; h->knots_dirty_host = false;
   return ICC_OK;
 }
 
 icc_status push_state_to_device(icc_handle* h) {
   if (h->device < 0 || !h->initialised) return ICC_OK;
   icc_status s = upload_state(h, h->cur);
-  h->state_dirty_host = false;
+  h->state_dirty_host = false; h->knots_dirty_host = false;
   return s;
 }
 
@@ -636,6 +638,9 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   }
   const size_t nv = t_vis.size();
   h->so3.assign(4 * (size_t)nso3, 0.0); h->r3.assign(3 * (size_t)nr3, 0.0);
+  // With a device the knots are initialised by init_knots_kernel (icc_init.cu) straight into both state copies, from the uploaded
+  // view poses; the host statement below serves the host-only handle (device -1: assembly checks against the oracle on CPU).
+  if (h->device < 0) {
   for (int i = 0; i < nso3; ++i) {   // InterpolateQuaternions (utils.cc:221-241); knot times are zero based
     const double t = double(i) * double(h->dt_so3_ns) * NS_TO_S;
     double dist = 0; const size_t k = nearest_index(t, t_vis, dist);
@@ -649,6 +654,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     double dist = 0; const size_t k = nearest_index(t, t_vis, dist);
     if (k < (size_t)nr3 && k + 1 < nv) { const double f = dist / (t_vis[k + 1] - t_vis[k]); for (int d = 0; d < 3; ++d) h->r3[3 * i + d] = (1.0 - f) * p_vis[3 * k + d] + f * p_vis[3 * (k + 1) + d]; }
     else for (int d = 0; d < 3; ++d) h->r3[3 * i + d] = p_vis[3 * k + d];
+  }
   }
   // bias splines: InitBiasSplines(bias, bias, 10 s, 10 s, 1.0, 0.1) (imu_camera_calibrator.cc:80-85, impl.h:53-90)
   h->dt_ba_ns = h->dt_bg_ns = (int64_t)(10 * 1e9); h->max_ba = 1.0; h->max_bg = 1e-1;
@@ -804,12 +810,12 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   P.w_acc = 1.0 / ipp->std_r3; P.w_gyr = 1.0 / ipp->std_so3;
   P.n_so3 = nso3; P.n_r3 = nr3; P.n_ba = nba; P.n_bg = nbg;
   P.n_res_vis = P.rolling ? 2 * P.n_corners : 0; P.n_res_acc = 3 * P.n_imu; P.n_res_gyr = 3 * P.n_imu;
-  h->cur_flags = -1; h->initialised = true; h->cur = 0; h->state_dirty_host = false;
+  h->cur_flags = -1; h->initialised = true; h->cur = 0; h->state_dirty_host = false; h->knots_dirty_host = false;
   if (h->device < 0) return ICC_OK;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
   h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + 96 * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
-                 + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
+                 + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
   {
     std::vector<double4> board(h->points.size() / 4);
     // hnormalized(T^-1 X_h) of the functor (residuals.h:357-362) == T^-1 (X / w): the division is done once here
@@ -888,12 +894,22 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   }
   icc_status s = upload_state(h, 0, true); if (s != ICC_OK) return s;
   s = upload_state(h, 1, true); if (s != ICC_OK) return s;
+  {   // knots: BatchInitSO3R3VisPoses on the device, written into both state copies (the zero knots uploaded above only sized them)
+    std::vector<double> tv, qv, pv;
+    tv.reserve(view_order.size()); qv.reserve(4 * view_order.size()); pv.reserve(3 * view_order.size());
+    for (const int i : view_order) { tv.push_back(h->frame_t[i]); for (int d = 0; d < 4; ++d) qv.push_back(h->q_wc[4 * i + d]); for (int d = 0; d < 3; ++d) pv.push_back(h->p_wc[3 * i + d]); }
+    CU(upload_staged(h, h->d_view_t, tv)); CU(upload_staged(h, h->d_view_q, qv)); CU(upload_staged(h, h->d_view_p, pv));
+    const double Tci7[7] = {Tci.q.x, Tci.q.y, Tci.q.z, Tci.q.w, Tci.t.x, Tci.t.y, Tci.t.z};
+    launch_init_knots((int)tv.size(), h->d_view_t.p, h->d_view_q.p, h->d_view_p.p, Tci7, nso3, double(h->dt_so3_ns) * NS_TO_S, nr3, double(h->dt_r3_ns) * NS_TO_S,
+                      h->st[0].so3.p, h->st[1].so3.p, h->st[0].r3.p, h->st[1].r3.p, h->stream);
+    h->knots_dirty_host = true;     // the device holds the knots; the host mirror is refreshed on demand (getters / setters)
+  }
   return ICC_OK;
 }
 
 icc_status icc_set_known_gravity_dir(icc_handle* h, const double g[3]) {
   if (!h || !g) return ICC_ERR_INVALID_ARGUMENT;
-  icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s;
+  if (h->state_dirty_host) { icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; }   // (knots alone being newer on the device does not matter here)
   for (int d = 0; d < 3; ++d) h->glob[G_GRAV + d] = g[d];
   if (h->device >= 0 && h->initialised) {   // only the globals block changed: one small staged copy instead of the whole state
     CU(cudaSetDevice(h->device));

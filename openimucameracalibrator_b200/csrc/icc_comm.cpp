@@ -7,7 +7,9 @@
 //
 // NCCL is bound with dlopen at first use instead of at link time: a process that already carries an NCCL (PyTorch bundles its own
 // 2.28 next to the system's 2.27) must not end up with two copies, so the already-loaded library is preferred (RTLD_NOLOAD) and the
-// system one is the fallback for plain C++ hosts (the drop-in CLI's --gpus mode).
+// system one is the fallback for plain C++ hosts (the drop-in CLI's --gpus mode: one PROCESS per GPU, like every NCCL
+// deployment this library was validated in; communicators of several devices inside one process are deliberately not offered --
+// host threads that allocate or synchronise while a peer's all-reduce kernel spins can deadlock the process).
 #include "../../include/icc_b200.h"
 
 #include <cuda_runtime.h>
@@ -112,29 +114,6 @@ int icc_comm_allreduce_sum(icc_comm* c, double* dev, int64_t n, void* stream) {
   const int e = nccl().AllReduce(dev, dev, (size_t)n, kNcclDouble, kNcclSum, c->comm, (cudaStream_t)stream);
   if (e != kNcclSuccess) { g_comm_error = std::string("ncclAllReduce: ") + nccl().GetErrorString(e); return 1; }
   return 0;
-}
-
-// Communicators for `world` devices of ONE process (the drop-in CLI's --gpus mode): ncclCommInitRank for every rank inside one group.
-icc_status icc_comm_create_all(icc_comm** out, int world, const int* device_ordinals) {
-  if (!out || world < 1) return ICC_ERR_INVALID_ARGUMENT;
-  NcclApi& n = nccl();
-  if (!n.error.empty()) { g_comm_error = n.error; return ICC_ERR_UNSUPPORTED; }
-  NcclUniqueId u;
-  int e = n.GetUniqueId(&u);
-  if (e != kNcclSuccess) { g_comm_error = std::string("ncclGetUniqueId: ") + n.GetErrorString(e); return ICC_ERR_CUDA; }
-  for (int r = 0; r < world; ++r) { out[r] = new icc_comm; out[r]->rank = r; out[r]->world = world; out[r]->device = device_ordinals ? device_ordinals[r] : r; }
-  n.GroupStart();
-  for (int r = 0; r < world && e == kNcclSuccess; ++r) {
-    if (cudaSetDevice(out[r]->device) != cudaSuccess) { e = -1; break; }
-    e = n.CommInitRank(&out[r]->comm, world, u, r);
-  }
-  const int e2 = n.GroupEnd();
-  if (e != kNcclSuccess || e2 != kNcclSuccess) {
-    g_comm_error = std::string("ncclCommInitRank (group): ") + (e == -1 ? "cudaSetDevice failed" : n.GetErrorString(e != kNcclSuccess ? e : e2));
-    for (int r = 0; r < world; ++r) { delete out[r]; out[r] = nullptr; }
-    return ICC_ERR_CUDA;
-  }
-  return ICC_OK;
 }
 
 }  // extern "C"

@@ -93,6 +93,9 @@ int launch_solve(const DeviceProblem& P, const double* scale, SolveParams sp, do
 size_t solve_workspace_doubles(const DeviceProblem& P);
 // candidate = Plus(current, delta) ; step / x squared norms
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st);
+// knot initialisation from the per-view pose priors (icc_init.cu): q_wc / p_wc / t_vis in view-time order, T_c_i = T_i_c^-1 (x,y,z,w,tx,ty,tz)
+void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, double dt_so3_s, int nr3, double dt_r3_s,
+                       double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st);
 // trajectory getters
 void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,
                             double* bg, double* ba, double* pose_q, double* pose_p, int* valid, cudaStream_t st);

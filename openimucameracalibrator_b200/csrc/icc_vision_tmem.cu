@@ -19,6 +19,7 @@
 //  * flush: one RED.ADD.F64 per tile entry into the packed banded+bordered normal equations (L2-resident), with the row/column
 //    index maps preloaded per lane.
 #include "icc_kernels.h"
+#include "icc_tile_common.cuh"
 #include "icc_tmem_gen.cuh"
 #include "icc_vision_rows.cuh"
 
@@ -29,8 +30,7 @@ void count_launch();
 namespace {
 
 constexpr int VW = 12;                 // warps per CTA
-constexpr int LDT = 36;                // rows per tile column (32 + 4 pad: conflict-free fragment loads)
-constexpr int TCOLS = 48;              // 44 used
+constexpr int LDT = TILE_LD, TCOLS = TILE_COLS;   // 44 tile columns used
 constexpr int TM_PER_WARP = 160;       // TMEM columns per warp: 84 accumulator + 72 parked row
 constexpr int TM_ACC = 0, TM_YROW = 84;
 constexpr int NBLK = 21;               // upper block triangle of 6 x 6 blocks of 8 columns
@@ -41,72 +41,7 @@ struct WarpSlot {
   int finfo[2][4];                     // per staged frame: padded stream offset, first corner, corner count
 };
 
-ICC_D void mma_f64(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// acc += T^T T over tile rows [4 k0, 4 k1)
-ICC_D void syrk6(const double* __restrict__ tile, int k0, int k1, double (&acc)[2 * NBLK]) {
-  const int lane = threadIdx.x & 31;
-  const double* base = tile + (lane >> 2) * LDT + (lane & 3);
-  for (int s = k0; s < k1; ++s) {
-    double f[6];
-#pragma unroll
-    for (int b = 0; b < 6; ++b) f[b] = base[(8 * b) * LDT + 4 * s];
-    int idx = 0;
-#pragma unroll
-    for (int bi = 0; bi < 6; ++bi)
-#pragma unroll
-      for (int bj = bi; bj < 6; ++bj) { mma_f64(acc[2 * idx], acc[2 * idx + 1], f[bi], f[bj]); ++idx; }
-  }
-}
-
-struct NeLayout { double* ne; int64_t off_E, off_C, off_g, off_cost; int nk, nb, ldb; };
 struct StageArgs { const double4* so3; const double4* r3; const int* so3_col; const int* r3_col; int col_tic, col_ld; };
-
-ICC_D void ne_add(const NeLayout& L, int gi, int gj, double v) {
-  const int lo = min(gi, gj), hi = max(gi, gj);
-  double* dst;
-  if (hi < L.nk) dst = L.ne + (int64_t)lo * L.ldb + (hi - lo);
-  else if (lo < L.nk) dst = L.ne + L.off_E + (int64_t)lo * L.nb + (hi - L.nk);
-  else dst = L.ne + L.off_C + (int64_t)(hi - L.nk) * L.nb + (lo - L.nk);
-  atomicAdd(dst, v);
-}
-
-// Scatter one finished tile from the register fragments: one RED.ADD.F64 per entry of the upper triangle.  Kept branch-free
-// (selected addresses, predicated RED) and specialised per block at compile time -- blocks of knot columns only ever land in the
-// band, the residual column (gradient / cost) only exists in block column 5 -- so the 42 unrolled copies stay small; the first
-// version of this kernel branched three ways per entry, was 40 % of the SASS and stalled on instruction fetch.
-ICC_D void flush6(const NeLayout& L, const int* __restrict__ gidx, const double (&acc)[2 * NBLK]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t2 = 2 * (lane & 3);
-  int gI[6], gJ[6][2];
-#pragma unroll
-  for (int b = 0; b < 6; ++b) { gI[b] = gidx[8 * b + g]; const int2 j2 = *reinterpret_cast<const int2*>(gidx + 8 * b + t2); gJ[b][0] = j2.x; gJ[b][1] = j2.y; }
-  const int ldbm1 = L.ldb - 1;
-  int idx = 0;
-#pragma unroll
-  for (int bi = 0; bi < 6; ++bi)
-#pragma unroll
-    for (int bj = bi; bj < 6; ++bj) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        double v = acc[2 * idx + e];
-        const int gi = gI[bi], gj = gJ[bj][e];
-        bool ok = gi != -1 && gj != -1 && (bi < bj || g <= t2 + e);
-        const int lo = min(gi, gj), hi = max(gi, gj);
-        int64_t off = (int64_t)lo * ldbm1 + hi;                                  // band: lo * ldb + (hi - lo)
-        if (bj >= 4) {                                                            // tile columns >= 32 may be border columns
-          if (hi >= L.nk) off = lo < L.nk ? L.off_E + (int64_t)lo * L.nb + (hi - L.nk) : L.off_C + (int64_t)(hi - L.nk) * L.nb + (lo - L.nk);
-        }
-        if (bj == 5) {                                                            // the residual column lives in block column 5
-          if (gj == -2) { off = gi == -2 ? L.off_cost : L.off_g + gi; if (gi == -2) v *= 0.5; }   // r^T r = 2 cost ; J^T r
-          else if (gi == -2) ok = false;
-        }
-        if (ok) atomicAdd(L.ne + off, v);
-      }
-      ++idx;
-    }
-}
 
 // Stage the knot windows of one frame: lanes 0..4 take one SO(3) increment each (log, unit axis, Jr^-1), lanes 8..13 the R^3 knots,
 // all lanes the tile-column -> solver-column map.  One copy of the log / Jr^-1 code for the three call sites.
@@ -144,7 +79,7 @@ ICC_D void tile_part(const NeLayout& L, double* __restrict__ tile, int k0, int k
   } else {
     tmem_ld_d42(ta + TM_ACC, acc);
   }
-  syrk6(tile, k0, k1, acc);                       // x rows
+  tile_syrk<6>(tile, k0, k1, acc);                       // x rows
   __syncwarp();
   {                                               // expand the parked y rows of this part into the tile (same rows)
     const bool mine = lane >= 4 * k0 && lane < 4 * k1;
@@ -168,10 +103,10 @@ ICC_D void tile_part(const NeLayout& L, double* __restrict__ tile, int k0, int k
     }
   }
   __syncwarp();
-  syrk6(tile, k0, k1, acc);                       // y rows
+  tile_syrk<6>(tile, k0, k1, acc);                       // y rows
   __syncwarp();
   if (last) {
-    flush6(L, gidx, acc);
+    tile_flush<6, 4>(L, gidx, acc);
   } else {
     tmem_st_d42(ta + TM_ACC, acc);
   }

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <time.h>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -474,6 +475,8 @@ void evaluate(Oracle& o, double* cost_out, double* residuals, Normal* ne, std::v
   // segment boundaries of the block list
   size_t seg[4] = {0, 0, 0, o.blocks.size()};
   { size_t i = 0; while (i < o.blocks.size() && o.blocks[i].type != BLK_ACCEL && o.blocks[i].type != BLK_GYRO) ++i; seg[1] = i; while (i < o.blocks.size() && o.blocks[i].type != BLK_GYRO) ++i; seg[2] = i; }
+  static const bool dbg = getenv("ICCO_DEBUG_TIMING") != nullptr;
+  const auto t_dbg = std::chrono::steady_clock::now();
   std::function<void(int)> work = [&](int tid) {
     Scratch s;
     double cost = 0;
@@ -515,6 +518,8 @@ void evaluate(Oracle& o, double* cost_out, double* residuals, Normal* ne, std::v
     }
     X.costs[tid] = cost;
     if (P) { X.lo[tid] = std::min(lo, hi); X.hi[tid] = hi; }
+    if (dbg) { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); fprintf(stderr, "  tid %d cpu-clock %.1f ms (thread total)", tid, 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec); }
+    if (dbg) fprintf(stderr, "  tid %d segs %zu %zu %zu %zu work %.1f ms\n", tid, seg[0], seg[1], seg[2], seg[3], 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dbg).count());
   };
   if (T == 1) work(0); else X.pool->run(work);
   double cost = 0; for (int t = 0; t < T; ++t) cost += X.costs[t];

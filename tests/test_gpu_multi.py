@@ -54,48 +54,9 @@ def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, gpu_factory, native):
     assert abs(rp[0] - s.mean_reproj_error) < 1e-8 and abs(rp[1] - s.final_cost) <= 1e-9 * s.final_cost
 
 
-def test_single_process_two_device_communicators(gpu_factory):
-    """icc_comm_create_all: the drop-in CLI's --gpus mode -- one process, one host thread and one handle per device, the library's
-    communicators built in one NCCL group.  Both ranks must end on the single-GPU result."""
-    import ctypes as C
-    import threading
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    sys.path.insert(0, ROOT)
-    from helpers import F_STAGE1, rel
-    from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
-    lib = calibrator.load_library()
-    comms = (C.c_void_p * 2)()
-    f = lib.icc_comm_create_all; f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    assert f(comms, 2, None) == 0
-    ds = syn.make_dataset(syn.CONFIGS[2])
-    out = [None, None]
-
-    class _C:      # Comm-shaped wrapper for CApi.set_comm
-        def __init__(self, c): self.c = C.c_void_p(c)
-
-    def run(r):
-        g = capi.CApi(lib, "icc_", r)
-        capi.load_dataset(g, ds, comm=_C(comms[r]))
-        s = g.optimize(50, F_STAGE1)
-        out[r] = (s.iterations, s.final_cost, g.get_T_i_c())
-        g.close()
-    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
-    [t.start() for t in th]; [t.join() for t in th]
-    g = gpu_factory(); capi.load_dataset(g, ds)
-    s = g.optimize(50, F_STAGE1)
-    for r in range(2):
-        assert out[r] is not None and out[r][0] == s.iterations
-        assert abs(out[r][1] - s.final_cost) <= 1e-9 * s.final_cost and rel(out[r][2], g.get_T_i_c()) < 1e-8
-    d = lib.icc_comm_destroy; d.restype = None; d.argtypes = [C.c_void_p]
-    for r in range(2):
-        d(comms[r])
-
-
 def test_cli_gpus_flag_matches_single_gpu(tmp_path):
-    """The drop-in binary's sharded mode (--gpus 2: helper threads, icc_comm_create_all, ncclAllReduce inside libicc_b200.so) must write
-    the same calibration as the single-GPU run of the same files."""
+    """The drop-in binary's sharded mode (--gpus 2: one rank process per device spawned by the binary itself, the NCCL id handed over on
+    the command line, ncclAllReduce inside libicc_b200.so) must write the same calibration as the single-GPU run of the same files."""
     import subprocess
     import torch
     if torch.cuda.device_count() < 2:
@@ -109,7 +70,7 @@ def test_cli_gpus_flag_matches_single_gpu(tmp_path):
     for gpus in (1, 2):
         d = tmp_path / f"g{gpus}"; d.mkdir()
         paths = iof.write_dataset_files(ds, str(d))
-        out = subprocess.run(_args(paths, str(d), ["--calibrate_cam_line_delay", f"--gpus={gpus}"]), capture_output=True, text=True)
+        out = subprocess.run(_args(paths, str(d), ["--calibrate_cam_line_delay", f"--gpus={gpus}"]), capture_output=True, text=True, timeout=240)
         assert out.returncode == 0, out.stderr + out.stdout
         if gpus == 2:
             assert "sharded over 2 GPUs" in out.stdout

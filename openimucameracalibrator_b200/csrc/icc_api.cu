@@ -161,6 +161,7 @@ struct icc_handle {
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
   DevBuf<double> d_view_t, d_view_q, d_view_p;   // per-view pose priors in time order (knot initialisation kernel)
   DevBuf<VisFrame> d_vframes; DevBuf<VisItem> d_vitems;
+  DevBuf<ImuCellP> d_icells; DevBuf<VisItem> d_iitems;
   DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
   DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
   DevBuf<double> d_ne, d_scale, d_ws, d_delta, d_scal, d_res;
@@ -814,7 +815,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   if (h->device < 0) return ICC_OK;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
-  h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + 96 * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
+  h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + (96 + 40) * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
                  + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
   {
     std::vector<double4> board(h->points.size() / 4);
@@ -843,44 +844,68 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     std::vector<VisionWork> vw;
     for (int fi = 0; fi < P.n_frames; ++fi) for (int c = h->frames[fi].c0; c < h->frames[fi].c1; c += per_v) vw.push_back({fi, c, std::min(c + per_v, h->frames[fi].c1), 0});
     CU(upload_staged(h, h->d_vwork, vw)); P.vwork = h->d_vwork.p; P.n_vwork = (int)vw.size();
-    {
-      // Packed corner stream of the TMEM vision kernel: non-empty frames end to end, each padded to a multiple of 4 corners; the
-      // walk below is the kernel's own chunk rule (a chunk = up to 32 stream positions from at most two consecutive frames), and
-      // the chunk list is cut into one contiguous run per warp.
-      std::vector<VisFrame> vf; vf.reserve(h->frames.size() + 2);
-      int poff = 0;
-      for (const auto& f : h->frames) {
-        const int cn = f.c1 - f.c0;
-        if (cn <= 0) continue;
-        vf.push_back({poff, f.c0, cn, f.s_so3, f.s_r3, 0, f.u_so3, f.u_r3});
-        poff += (cn + 3) / 4 * 4;
-      }
-      const int nvf = (int)vf.size(), total = poff;
-      vf.push_back({total, 0, 0, 0, 0, 0, 0.0, 0.0}); vf.push_back({total, 0, 0, 0, 0, 0, 0.0, 0.0});   // sentinels [n], [n+1]
-      std::vector<int> chunk_pos, chunk_vf;
-      for (int pos = 0, f = 0; pos < total;) {
-        while (vf[f + 1].poff <= pos) ++f;
-        chunk_pos.push_back(pos); chunk_vf.push_back(f);
-        const int nA = std::min(32, vf[f + 1].poff - pos);
-        int n = nA;
-        if (nA < 32 && f + 1 < nvf) n += std::min(32 - nA, vf[f + 2].poff - vf[f + 1].poff);
-        pos += n;
-      }
-      const int n_chunks = (int)chunk_pos.size(), n_warps = h->sm_count * vision_tmem_warps();
-      const int n_items = std::min(n_chunks, n_warps);
-      std::vector<VisItem> vi; vi.reserve((size_t)n_items);
-      for (int i = 0; i < n_items; ++i) {
-        const int a = (int)((int64_t)n_chunks * i / n_items), b = (int)((int64_t)n_chunks * (i + 1) / n_items);
-        vi.push_back({chunk_vf[a], chunk_pos[a], b < n_chunks ? chunk_pos[b] : total, 0});
-      }
-      CU(upload_staged(h, h->d_vframes, vf)); P.vframes = h->d_vframes.p; P.n_vframes = nvf;
-      CU(upload_staged(h, h->d_vitems, vi)); P.vitems = h->d_vitems.p; P.n_vitems = n_items;
-    }
     const int per_i = std::max(32, round32(P.n_imu / std::max(1, target_items)));
     std::vector<ImuCell> iw;
     for (const auto& c : h->cells) for (int i = c.i_begin; i < c.i_end; i += per_i) { ImuCell s = c; s.i_begin = i; s.i_end = std::min(i + per_i, c.i_end); iw.push_back(s); }
     CU(upload_staged(h, h->d_iwork, iw)); P.iwork = h->d_iwork.p; P.n_iwork = (int)iw.size();
     CU(upload_staged(h, h->d_cells, h->cells)); P.cells = h->d_cells.p;
+    {
+      // Schedule of the persistent TMEM evaluation kernel (icc_eval_tmem.cu).  Both streams -- the corners of the non-empty frames and
+      // the samples of the knot-interval cells, units padded to a multiple of 4 = one m8n8k4 k-step -- are walked with the kernel's own
+      // chunk rule (a chunk = up to 32 stream positions from at most two consecutive units) and cut into even per-warp runs.
+      struct Walk { std::vector<int> pos, unit; int total = 0; };
+      auto walk = [](const std::vector<int>& poff, int n_units) { Walk w; w.total = poff[n_units];
+        for (int pos = 0, u = 0; pos < w.total;) {
+          while (poff[u + 1] <= pos) ++u;
+          w.pos.push_back(pos); w.unit.push_back(u);
+          const int nA = std::min(32, poff[u + 1] - pos);
+          int n = nA;
+          if (nA < 32 && u + 1 < n_units) n += std::min(32 - nA, poff[u + 2] - poff[u + 1]);
+          pos += n;
+        }
+        return w; };
+      std::vector<VisFrame> vf; vf.reserve(h->frames.size() + 2);
+      std::vector<int> vpoff;
+      int poff = 0;
+      if (P.rolling) for (const auto& f : h->frames) {
+        const int cn = f.c1 - f.c0;
+        if (cn <= 0) continue;
+        vf.push_back({poff, f.c0, cn, f.s_so3, f.s_r3, 0, f.u_so3, f.u_r3}); vpoff.push_back(poff);
+        poff += (cn + 3) / 4 * 4;
+      }
+      const int nvf = (int)vf.size();
+      vf.push_back({poff, 0, 0, 0, 0, 0, 0.0, 0.0}); vf.push_back({poff, 0, 0, 0, 0, 0, 0.0, 0.0});   // sentinels [n], [n+1]
+      vpoff.push_back(poff); vpoff.push_back(poff);
+      std::vector<ImuCellP> ic; ic.reserve(h->cells.size() + 2);
+      std::vector<int> ipoff;
+      poff = 0;
+      for (const auto& c : h->cells) {
+        const int n = c.i_end - c.i_begin;
+        if (n <= 0) continue;
+        ic.push_back({poff, c.i_begin, n, c.s_so3, c.s_r3, c.s_ba, c.s_bg, 0}); ipoff.push_back(poff);
+        poff += (n + 3) / 4 * 4;
+      }
+      const int nic = (int)ic.size();
+      ic.push_back({poff, 0, 0, 0, 0, 0, 0, 0}); ic.push_back({poff, 0, 0, 0, 0, 0, 0, 0});
+      ipoff.push_back(poff); ipoff.push_back(poff);
+      const Walk wv = walk(vpoff, nvf), wi = walk(ipoff, nic);
+      const int nVc = (int)wv.pos.size(), nIc = (int)wi.pos.size(), W = h->sm_count * eval_tmem_warps();
+      auto split = [W](const Walk& w) {      // even runs, one per warp
+        const int nc = (int)w.pos.size(), n_items = std::min(W, nc);
+        std::vector<VisItem> items((size_t)n_items);
+        for (int k = 0; k < n_items; ++k) {
+          const int a = (int)((int64_t)nc * k / n_items), b = (int)((int64_t)nc * (k + 1) / n_items);
+          items[(size_t)k] = {w.unit[a], w.pos[a], b < nc ? w.pos[b] : w.total, 0};
+        }
+        return items; };
+      const std::vector<VisItem> vi = split(wv), ii = split(wi);
+      const int n_iit = (int)ii.size();
+      P.n_vchunks = nVc; P.n_ichunks = nIc;
+      CU(upload_staged(h, h->d_vframes, vf)); P.vframes = h->d_vframes.p; P.n_vframes = nvf;
+      CU(upload_staged(h, h->d_vitems, vi)); P.vitems = h->d_vitems.p; P.n_vitems = (int)vi.size();
+      CU(upload_staged(h, h->d_icells, ic)); P.icells = h->d_icells.p; P.n_icells = nic;
+      CU(upload_staged(h, h->d_iitems, ii)); P.iitems = h->d_iitems.p; P.n_iitems = n_iit;
+    }
     CU(h->d_imu_t.alloc(h->imu_used_st.size()));
     if (!h->imu_used_st.empty()) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->imu_used_st.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
@@ -900,7 +925,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     for (const int i : view_order) { tv.push_back(h->frame_t[i]); for (int d = 0; d < 4; ++d) qv.push_back(h->q_wc[4 * i + d]); for (int d = 0; d < 3; ++d) pv.push_back(h->p_wc[3 * i + d]); }
     CU(upload_staged(h, h->d_view_t, tv)); CU(upload_staged(h, h->d_view_q, qv)); CU(upload_staged(h, h->d_view_p, pv));
     const double Tci7[7] = {Tci.q.x, Tci.q.y, Tci.q.z, Tci.q.w, Tci.t.x, Tci.t.y, Tci.t.z};
-    launch_init_knots((int)tv.size(), h->d_view_t.p, h->d_view_q.p, h->d_view_p.p, Tci7, nso3, double(h->dt_so3_ns) * NS_TO_S, nr3, double(h->dt_r3_ns) * NS_TO_S,
+    launch_init_knots((int)tv.size(), h->d_view_t.p, h->d_view_q.p, h->d_view_p.p, Tci7, nso3, h->dt_so3_ns, nr3, h->dt_r3_ns,
                       h->st[0].so3.p, h->st[1].so3.p, h->st[0].r3.p, h->st[1].r3.p, h->stream);
     h->knots_dirty_host = true;     // the device holds the knots; the host mirror is refreshed on demand (getters / setters)
   }
@@ -1117,6 +1142,7 @@ icc_status icc_time_evaluations(icc_handle* h, int n, int flags, int with_jacobi
     if (with_jacobian == 1) { s = eval_jacobian(h, h->st[h->cur].view(), nullptr); }
     else if (with_jacobian == 2 || with_jacobian == 3) {   // one kernel family only (2 = vision, 3 = imu), Jacobian mode, no memset
       DeviceProblem Q = h->P; if (with_jacobian == 2) Q.n_iwork = 0; else { Q.n_vwork = 0; Q.n_vitems = 0; }
+      if (with_jacobian == 2) Q.n_iitems = 0;
       s = launch_eval(Q, h->st[h->cur].view(), true, nullptr, nullptr, nullptr, h->stream) ? fail(h, ICC_ERR_CUDA, "eval launch failed") : ICC_OK;
     }
     else { s = eval_cost(h, h->st[h->cur].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); }

@@ -540,15 +540,25 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     if (e) return 1;
     attr_done = true;
   }
-  // Jacobian evaluations of the standard column set run the persistent TMEM-parked vision kernel (icc_vision_tmem.cu); it owns
-  // every SM (one CTA each, 192 KB of shared memory), so the IMU kernel follows it on the same stream instead of beside it.
+  // Jacobian evaluations of the standard column sets run as items of the persistent TMEM-parked kernel (icc_eval_tmem.cu), which owns
+  // every SM (one CTA each); whatever is not eligible (camera intrinsics / bias knots / IMU intrinsics free) follows on the same stream.
   const bool legacy_vision = getenv("ICC_VISION_LEGACY") != nullptr;   // A/B switch for profiling only (read per call)
-  const bool tmem_vision = with_jacobian && !P.cam_intr_active && P.n_vitems > 0 && P.rolling && !legacy_vision;
-  const bool fork = aux && P.n_vwork > 0 && P.rolling && P.n_iwork > 0 && !tmem_vision;
+  // size test: the persistent kernel pays off once every warp has a few chunks (BASELINE config 4: 7.6 vision / 1.8 IMU chunks per warp);
+  // below that the one-warp-per-frame / per-cell kernels finish sooner and run side by side
+  const int tm_warps = sm_count * eval_tmem_warps();
+  const bool tmem_vision = with_jacobian && !P.cam_intr_active && P.n_vitems > 0 && P.rolling && !legacy_vision && (P.n_vchunks >= 3 * tm_warps || getenv("ICC_TMEM_ALWAYS"));
+  const bool legacy_imu = getenv("ICC_IMU_LEGACY") != nullptr;
+  const bool tmem_imu = with_jacobian && !P.bias_active && !P.intr_active && P.n_iitems > 0 && P.n_iwork > 0 && !legacy_imu && (2 * P.n_ichunks >= 3 * tm_warps || getenv("ICC_TMEM_ALWAYS"));
+  const bool fork = aux && P.n_vwork > 0 && P.rolling && P.n_iwork > 0 && !tmem_vision && !tmem_imu;
   cudaStream_t st = st_main;
   if (fork) { cudaEventRecord(aux->fork, st_main); cudaStreamWaitEvent(aux->stream, aux->fork, 0); }
+  if (tmem_vision || tmem_imu) {   // one persistent launch for every item type that is eligible
+    DeviceProblem Q = P;
+    if (!tmem_vision) Q.n_vitems = 0;
+    if (!tmem_imu) Q.n_iitems = 0;
+    if (launch_eval_tmem(Q, S, residuals_out, sm_count, st)) return 1;
+  }
   if (tmem_vision) {
-    if (launch_vision_tmem(P, S, residuals_out, sm_count, st)) return 1;
   } else if (P.n_vwork > 0 && P.rolling) {
     const int grid = grid_for(P.n_vwork, sm_count);
     if (with_jacobian && P.cam_intr_active) vision_kernel<2><<<grid, WARPS * 32, sm_vis_k, st>>>(P, S, cost_out, residuals_out, reproj_out);
@@ -556,7 +566,8 @@ int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian
     else vision_kernel<0><<<grid, WARPS * 32, sm_cost, st>>>(P, S, cost_out, residuals_out, reproj_out);
     count_launch();
   }
-  if (P.n_iwork > 0) {
+  if (tmem_imu) {
+  } else if (P.n_iwork > 0) {
     if (fork) st = aux->stream;
     const int grid = grid_for(P.n_iwork, sm_count);
     if (P.bias_active || P.intr_active) {

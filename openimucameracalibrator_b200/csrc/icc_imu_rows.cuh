@@ -73,10 +73,7 @@ ICC_HD void imu_accel_rows(const ImuWin& W, const ImuConst& K, double u_so3, dou
   ra[2] = K.w_acc * (h.z - (K.Ma[6] * a_raw.x + K.Ma[7] * a_raw.y + K.Ma[8] * a_raw.z));
   // d r_k / d theta = w_acc (e_k x h)  (row covector, right increment of R_w_i)
   V3 w[3], zn[3];
-  w[0] = v3(0.0, K.w_acc * h.z, -K.w_acc * h.y);              // e_0 x h = (0, -h_z, h_y) ... as a row covector times [.]: see cross(e_k, h)
-  w[1] = v3(-K.w_acc * h.z, 0.0, K.w_acc * h.x);
-  w[2] = v3(K.w_acc * h.y, -K.w_acc * h.x, 0.0);
-  // cross(e_0, h) = (0 * h.z - 0 * h.y, 0 * h.x - 1 * h.z, 1 * h.y - 0 * h.x) = (0, -h.z, h.y): fix the signs set above
+  // cross(e_0, h) = (0, -h.z, h.y), cross(e_1, h) = (h.z, 0, -h.x), cross(e_2, h) = (-h.y, h.x, 0)
   w[0] = v3(0.0, -K.w_acc * h.z, K.w_acc * h.y);
   w[1] = v3(K.w_acc * h.z, 0.0, -K.w_acc * h.x);
   w[2] = v3(-K.w_acc * h.y, K.w_acc * h.x, 0.0);
@@ -117,21 +114,24 @@ ICC_HD void imu_accel_rows(const ImuWin& W, const ImuConst& K, double u_so3, dou
   park[40] = ra[1]; park[41] = ra[2]; park[42] = u_r3;
 }
 
-// expand parked accelerometer row k (1 or 2) into tile entries
-ICC_HD void imu_accel_row_expand(const double (&park)[ACC_PARK], const ImuConst& K, int k, double* __restrict__ row, int ld) {
+// expand one parked accelerometer row (k = 1 or 2) into tile entries: so3 = its 18 knot entries, then the shared tail of the
+// parked layout (quaternion of R_w_i, residual of this row, u_r3).  An all-zero quaternion marks a padding lane: zero row.
+ICC_HD void imu_accel_row_expand(const double (&so3)[18], Q4 q, double res, double u_r3, const ImuConst& K, int k, double* __restrict__ row, int ld) {
+  const bool live = q.x != 0.0 || q.y != 0.0 || q.z != 0.0 || q.w != 0.0;
 #pragma unroll
-  for (int c = 0; c < 18; ++c) row[c * ld] = k == 1 ? park[c] : park[18 + c];
-  const M3 R = qmat(q4(park[36], park[37], park[38], park[39]));
+  for (int c = 0; c < 18; ++c) row[c * ld] = so3[c];
+  const M3 R = qmat(q);
+  const double wl = live ? K.w_acc : 0.0;
   const V3 mt = k == 1 ? v3(R.m[1], R.m[4], R.m[7]) : v3(R.m[2], R.m[5], R.m[8]);
   double ddc[6];
-  coeffs6_dd_only(park[42], ddc);
+  coeffs6_dd_only(u_r3, ddc);
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    const double s = K.w_acc * ddc[j] * K.idt2;
+    const double s = wl * ddc[j] * K.idt2;
     row[(18 + 3 * j + 0) * ld] = s * mt.x; row[(18 + 3 * j + 1) * ld] = s * mt.y; row[(18 + 3 * j + 2) * ld] = s * mt.z;
   }
-  row[36 * ld] = K.w_acc * mt.x; row[37 * ld] = K.w_acc * mt.y; row[38 * ld] = K.w_acc * mt.z;
-  row[ACC_RES_COL * ld] = k == 1 ? park[40] : park[41];
+  row[36 * ld] = wl * mt.x; row[37 * ld] = wl * mt.y; row[38 * ld] = wl * mt.z;
+  row[ACC_RES_COL * ld] = res;
 }
 
 // gyroscope rows.  row0: entry c at row0[c * ld] (c = 0..23, 19..23 zero).  park: rows 1 and 2.

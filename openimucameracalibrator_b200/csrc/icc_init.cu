@@ -26,10 +26,10 @@ ICC_D PoseD view_T_w_i(const double* __restrict__ q_wc, const double* __restrict
 }
 
 __global__ void init_knots_kernel(int nv, const double* __restrict__ t_vis, const double* __restrict__ q_wc, const double* __restrict__ p_wc, Q4 q_ci, V3 t_ci,
-                                  int nso3, double dt_so3_s, int nr3, double dt_r3_s, double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b) {
+                                  int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns, double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nso3) {                               // InterpolateQuaternions (utils.cc:214-241)
-    const double t = double(i) * dt_so3_s;
+    const double t = double((int64_t)i * dt_so3_ns) * 1e-9;   // i * dt_so3_ns_ * NS_TO_S (impl.h:318): integer product first -- knot times tie with view mid-points, the rounding decides the nearest view
     double dist = 0.0;
     const int k = nearest_sorted(t_vis, nv, t, dist);
     const PoseD a = view_T_w_i(q_wc, p_wc, k, q_ci, t_ci);
@@ -43,7 +43,7 @@ __global__ void init_knots_kernel(int nv, const double* __restrict__ t_vis, cons
     so3_a[i] = o; so3_b[i] = o;
   } else if (i < nso3 + nr3) {                  // InterpolateVector3d (utils.cc:243-261) incl. its `nearest < t_new.size()` test; the
     const int j = i - nso3;                     // reference's read past the last view falls back to the nearest value
-    const double t = double(j) * dt_r3_s;
+    const double t = double((int64_t)j * dt_r3_ns) * 1e-9;
     double dist = 0.0;
     const int k = nearest_sorted(t_vis, nv, t, dist);
     const PoseD a = view_T_w_i(q_wc, p_wc, k, q_ci, t_ci);
@@ -60,11 +60,11 @@ __global__ void init_knots_kernel(int nv, const double* __restrict__ t_vis, cons
 
 }  // namespace
 
-void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, double dt_so3_s, int nr3, double dt_r3_s,
+void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns,
                        double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st) {
   const int n = nso3 + nr3;
   if (n <= 0 || nv <= 0) return;
-  init_knots_kernel<<<(n + 127) / 128, 128, 0, st>>>(nv, t_vis, q_wc, p_wc, q4(T_c_i[0], T_c_i[1], T_c_i[2], T_c_i[3]), v3(T_c_i[4], T_c_i[5], T_c_i[6]), nso3, dt_so3_s, nr3, dt_r3_s, so3_a, so3_b, r3_a, r3_b);
+  init_knots_kernel<<<(n + 127) / 128, 128, 0, st>>>(nv, t_vis, q_wc, p_wc, q4(T_c_i[0], T_c_i[1], T_c_i[2], T_c_i[3]), v3(T_c_i[4], T_c_i[5], T_c_i[6]), nso3, dt_so3_ns, nr3, dt_r3_ns, so3_a, so3_b, r3_a, r3_b);
   count_launch();
 }
 

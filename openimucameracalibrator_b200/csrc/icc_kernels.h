@@ -27,6 +27,8 @@ struct VisionWork { int frame, c_begin, c_end, pad; };
 // a chunk may take its first lanes from the end of one frame and the rest from the start of the next.
 struct VisFrame { int poff, c0, cn, s_so3, s_r3, pad; double u_so3, u_r3; };   // poff = padded stream offset; entry [n] is a sentinel
 struct VisItem { int vf0, pos_begin, pos_end, pad; };                          // first frame touched + stream range
+// The same packing for the IMU stream (icc_imu_tmem.cu): knot-interval cells (runs of samples sharing all four knot windows)
+struct ImuCellP { int poff, i0, n, s_so3, s_r3, s_ba, s_bg, pad; };            // entries [n], [n+1] are sentinels
 struct ImuCell { int s_so3, s_r3, s_ba, s_bg; int i_begin, i_end; };
 
 struct DeviceProblem {
@@ -43,6 +45,9 @@ struct DeviceProblem {
   int n_vwork; const VisionWork* vwork;
   int n_vframes; const VisFrame* vframes;    // + sentinel
   int n_vitems; const VisItem* vitems;
+  int n_icells; const ImuCellP* icells;      // + sentinels
+  int n_iitems; const VisItem* iitems;
+  int n_vchunks, n_ichunks;                  // 32-lane chunks of the two packed streams (the launcher's size test)
   // imu: samples sorted by time, grouped into cells sharing all knot windows
   int n_imu;
   const int64_t* imu_t_ns;   // relative to spline start (st_ns)
@@ -81,9 +86,10 @@ enum { SC_MODEL_CHANGE = 0, SC_STEP_SQ = 1, SC_X_SQ = 2, SC_CAND_COST = 3, SC_OK
 // `aux` (optional): a second stream + two events; the IMU kernel then runs concurrently with the vision kernel (fork / join
 // around the pair on `st`), which fills the partial last wave of either kernel.
 struct EvalAux { cudaStream_t stream; cudaEvent_t fork, join; };
-// TMEM-parked persistent vision Jacobian kernel (icc_vision_tmem.cu); returns non-zero on a launch error
-int launch_vision_tmem(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int sm_count, cudaStream_t st);
-int vision_tmem_warps();
+// Persistent TMEM-parked Jacobian evaluation, vision + IMU items in one launch (icc_eval_tmem.cu); non-zero on a launch error.
+// P.vitems[k] / P.iitems[k] is the run of global warp k; the two item types go out as two launches of the same kernel.
+int launch_eval_tmem(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int sm_count, cudaStream_t st);
+int eval_tmem_warps();
 int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st, const EvalAux* aux = nullptr);
 // scale[i] = 1/(1+sqrt(H_ii)) (Jacobi scaling, computed once per optimize) ; gradient inf-norm
 void launch_compute_scale(const DeviceProblem& P, double* scale, int jacobi, double* scal, cudaStream_t st);
@@ -94,7 +100,7 @@ size_t solve_workspace_doubles(const DeviceProblem& P);
 // candidate = Plus(current, delta) ; step / x squared norms
 void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceState& cand, const double* delta, double max_ba, double max_bg, double* scal, cudaStream_t st);
 // knot initialisation from the per-view pose priors (icc_init.cu): q_wc / p_wc / t_vis in view-time order, T_c_i = T_i_c^-1 (x,y,z,w,tx,ty,tz)
-void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, double dt_so3_s, int nr3, double dt_r3_s,
+void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns,
                        double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st);
 // trajectory getters
 void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,

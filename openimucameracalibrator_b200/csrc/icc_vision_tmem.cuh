@@ -1,4 +1,4 @@
-// Rolling-shutter reprojection residuals + analytic Jacobians + J^T J / J^T r reduction: the persistent, TMEM-parked kernel (sm_100a).
+// Rolling-shutter reprojection residuals + analytic Jacobians + J^T J / J^T r reduction: the vision items of the persistent, TMEM-parked evaluation kernel (icc_eval_tmem.cu, sm_100a).
 //
 // Same arithmetic contract as vision_kernel<1> of icc_eval.cu (reference: RSReprojectionCostFunctorSplit<6>::operator(),
 // basalt_spline/ceres_calib_split_residuals.h:319-402, under Ceres autodiff + LieLocalParameterization), re-mapped to the machine:
@@ -18,20 +18,17 @@
 //    tile, which is flushed, before the k-steps of the second start a new one.
 //  * flush: one RED.ADD.F64 per tile entry into the packed banded+bordered normal equations (L2-resident), with the row/column
 //    index maps preloaded per lane.
+#pragma once
 #include "icc_kernels.h"
 #include "icc_tile_common.cuh"
 #include "icc_tmem_gen.cuh"
 #include "icc_vision_rows.cuh"
 
 namespace icc {
-
-void count_launch();
-
-namespace {
+namespace tmv {
 
 constexpr int VW = 12;                 // warps per CTA
 constexpr int LDT = TILE_LD, TCOLS = TILE_COLS;   // 44 tile columns used
-constexpr int TM_PER_WARP = 160;       // TMEM columns per warp: 84 accumulator + 72 parked row
 constexpr int TM_ACC = 0, TM_YROW = 84;
 constexpr int NBLK = 21;               // upper block triangle of 6 x 6 blocks of 8 columns
 
@@ -112,35 +109,21 @@ ICC_D void tile_part(const NeLayout& L, double* __restrict__ tile, int k0, int k
   }
 }
 
-template <int MODEL>
-__global__ void __launch_bounds__(VW * 32, 1) vision_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  VisConst* K = reinterpret_cast<VisConst*>(smem_raw);
-  uint32_t* tm_base_s = reinterpret_cast<uint32_t*>(smem_raw + sizeof(VisConst));
-  WarpSlot* slots = reinterpret_cast<WarpSlot*>(smem_raw + sizeof(VisConst) + 16);
-  double* tiles = reinterpret_cast<double*>(smem_raw + sizeof(VisConst) + 16 + VW * sizeof(WarpSlot));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpSlot* slot = slots + warp;
-  double* tile = tiles + warp * (TCOLS * LDT);
-
-  if (warp == 0) tmem_alloc((uint32_t)__cvta_generic_to_shared(tm_base_s), 512);
+// shared-memory constants of the vision items (written once per CTA)
+ICC_D void init_const(VisConst* K, const DeviceProblem& P, const DeviceState& S, int model) {
   if (threadIdx.x < 10) K->intr[threadIdx.x] = S.glob[G_CAM_INTR + threadIdx.x];
   if (threadIdx.x == 32) {
     const Q4 q_ic = q4(S.glob[G_TIC + 0], S.glob[G_TIC + 1], S.glob[G_TIC + 2], S.glob[G_TIC + 3]);
     K->Ric = qmat(q_ic); K->tic = v3(S.glob[G_TIC + 4], S.glob[G_TIC + 5], S.glob[G_TIC + 6]);
-    K->ld = S.glob[G_LD]; K->model = MODEL; K->fov = P.dispatch_fov;
+    K->ld = S.glob[G_LD]; K->model = model; K->fov = P.dispatch_fov;
   }
-  for (int i = lane; i < TCOLS * LDT; i += 32) tile[i] = 0.0;
-  tmem_fence_before_sync();
-  __syncthreads();
-  tmem_fence_after_sync();
-  // lane quarter of this warp (hardware rule: warp w may touch TMEM lanes 32 (w % 4) ..+31), column group by warp / 4
-  const uint32_t ta = *tm_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_PER_WARP);
-  NeLayout L; L.ne = P.ne; L.off_E = P.ne_off_E; L.off_C = P.ne_off_C; L.off_g = P.ne_off_g; L.off_cost = P.ne_off_cost; L.nk = P.nk; L.nb = P.nb; L.ldb = P.ldb;
-  StageArgs A; A.so3 = S.so3; A.r3 = S.r3; A.so3_col = P.so3_col; A.r3_col = P.r3_col; A.col_tic = P.col_tic; A.col_ld = P.col_ld;
+}
 
-  for (int item = warp * gridDim.x + blockIdx.x; item < P.n_vitems; item += VW * gridDim.x) {
-    const VisItem it = P.vitems[item];
+// One item = one contiguous run of 32-lane chunks of the packed corner stream, processed by one warp.
+template <int MODEL>
+ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const VisConst* K, WarpSlot* slot, double* __restrict__ tile, uint32_t ta, const NeLayout& L, const VisItem it, double* __restrict__ res_out, int lane) {
+  StageArgs A; A.so3 = S.so3; A.r3 = S.r3; A.so3_col = P.so3_col; A.r3_col = P.r3_col; A.col_tic = P.col_tic; A.col_ld = P.col_ld;
+  {
     int f = it.vf0, pos = it.pos_begin, cur = 0;
     stage_frame(slot, cur, P.vframes[f], A);
     int endF = min(P.vframes[f + 1].poff, it.pos_end);
@@ -198,44 +181,7 @@ __global__ void __launch_bounds__(VW * 32, 1) vision_tmem_kernel(DeviceProblem P
       pos += n;
     }
   }
-  tmem_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(*tm_base_s, 512);
 }
 
-template <int MODEL>
-int launch_model(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(vision_tmem_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    attr_done = true;
-  }
-  vision_tmem_kernel<MODEL><<<grid, VW * 32, smem, st>>>(P, S, residuals_out);
-  return 0;
-}
-
-}  // namespace
-
-int vision_tmem_warps() { return VW; }
-
-int launch_vision_tmem(const DeviceProblem& P, const DeviceState& S, double* residuals_out, int sm_count, cudaStream_t st) {
-  const size_t smem = sizeof(VisConst) + 16 + VW * sizeof(WarpSlot) + (size_t)VW * TCOLS * LDT * sizeof(double);
-  if (P.n_vitems <= 0) return 0;
-  const int grid = P.n_vitems < sm_count ? P.n_vitems : sm_count;
-  int e = 1;
-  switch (P.model) {   // one instantiation per camera model: only that model's projection code is resident in the instruction cache
-    case CAM_PINHOLE: e = launch_model<CAM_PINHOLE>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_PINHOLE_RADTAN: e = launch_model<CAM_PINHOLE_RADTAN>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_FISHEYE: e = launch_model<CAM_FISHEYE>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_FOV: e = launch_model<CAM_FOV>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_DIVISION_UNDISTORTION: e = launch_model<CAM_DIVISION_UNDISTORTION>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_DOUBLE_SPHERE: e = launch_model<CAM_DOUBLE_SPHERE>(P, S, residuals_out, grid, smem, st); break;
-    case CAM_EXTENDED_UNIFIED: e = launch_model<CAM_EXTENDED_UNIFIED>(P, S, residuals_out, grid, smem, st); break;
-    default: return 1;
-  }
-  if (e) return 1;
-  count_launch();
-  return cudaGetLastError() == cudaSuccess ? 0 : 1;
-}
-
+}  // namespace tmv
 }  // namespace icc

@@ -10,8 +10,8 @@ for c in cfgs:
     ds = syn.make_dataset(syn.CONFIGS[c])
     out = {}
     for variant in ("legacy", "tmem"):
-        if variant == "legacy": os.environ["ICC_VISION_LEGACY"] = "1"
-        else: os.environ.pop("ICC_VISION_LEGACY", None)
+        if variant == "legacy": os.environ["ICC_VISION_LEGACY"] = "1"; os.environ["ICC_IMU_LEGACY"] = "1"
+        else: os.environ.pop("ICC_VISION_LEGACY", None); os.environ.pop("ICC_IMU_LEGACY", None)
         g = capi.CApi(calibrator.load_library(), "icc_", 0); capi.load_dataset(g, ds)
         cost, r, grad, _ = g.evaluate(F, residuals=True, gradient=True, hessian=False)
         g.time_evaluations(3, F, 2)

@@ -33,3 +33,14 @@ def gpu_factory(cuda_lib):
     def make():
         return capi.CApi(cuda_lib, "icc_", 0)
     return make
+
+
+@pytest.fixture(params=["sized", "tmem_always"])
+def eval_path(request, monkeypatch):
+    """Both Jacobian evaluation paths of launch_eval: the size-selected default (small problems: one warp per frame / cell) and the
+    persistent TMEM-parked kernel forced on (ICC_TMEM_ALWAYS), so that the small parity cases also pin the kernel BASELINE config 4 uses."""
+    if request.param == "tmem_always":
+        monkeypatch.setenv("ICC_TMEM_ALWAYS", "1")
+    else:
+        monkeypatch.delenv("ICC_TMEM_ALWAYS", raising=False)
+    return request.param

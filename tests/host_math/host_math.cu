@@ -4,6 +4,7 @@
 #include "../../openimucameracalibrator_b200/csrc/icc_camera.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_spline_chain.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_vision_rows.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_imu_rows.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_rotinit_math.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_small_linalg.cuh"
 
@@ -80,6 +81,33 @@ int hm_vision_rows(int model, const double* intr10, int fov, const double* so3, 
   return r0 == 1e10 ? 0 : 1;
 }
 void hm_sincos_small(double x, double* s, double* c) { sincos_small(x, s, c); }
+// The three accelerometer rows (3 x 40) and the three gyroscope rows (3 x 24) of one IMU sample exactly as the TMEM IMU kernel computes them
+// (icc_imu_rows.cuh): imu_accel_rows / imu_gyro_rows, then the parked rows expanded the way accel_part / gyro_part of icc_imu_tmem.cu do.
+//   Ma, Mg row-major 3x3; knots as in hm_vision_rows; ba, bg = 3 x 3 bias knots
+void hm_imu_rows(const double* so3, const double* r3, const double* ba, const double* bg, double u_so3, double u_r3, double u_ba, double u_bg, const double* Ma, const double* Mg,
+                 const double* grav, double w_acc, double w_gyr, double inv_so3_dt, double inv_r3_dt, const double* a_meas, const double* g_meas, double* acc_rows, double* gyr_rows) {
+  static ImuWin W; ImuConst K;
+  for (int i = 0; i < 5; ++i) stage_frame_increment(W.f, i, q4(so3[4 * i], so3[4 * i + 1], so3[4 * i + 2], so3[4 * i + 3]), q4(so3[4 * i + 4], so3[4 * i + 5], so3[4 * i + 6], so3[4 * i + 7]));
+  W.f.q0 = q4(so3[0], so3[1], so3[2], so3[3]);
+  for (int j = 0; j < 6; ++j) W.f.p[j] = v3(r3[3 * j], r3[3 * j + 1], r3[3 * j + 2]);
+  for (int j = 0; j < 3; ++j) { W.ba[j] = v3(ba[3 * j], ba[3 * j + 1], ba[3 * j + 2]); W.bg[j] = v3(bg[3 * j], bg[3 * j + 1], bg[3 * j + 2]); }
+  for (int i = 0; i < 9; ++i) { K.Ma[i] = Ma[i]; K.Mg[i] = Mg[i]; }
+  K.grav = v3(grav[0], grav[1], grav[2]); K.w_acc = w_acc; K.w_gyr = w_gyr; K.idt2 = inv_r3_dt * inv_r3_dt; K.inv_so3_dt = inv_so3_dt;
+  double pa[ACC_PARK], ra[3];
+  imu_accel_rows(W, K, u_so3, u_r3, u_ba, v3(a_meas[0], a_meas[1], a_meas[2]), acc_rows, 1, pa, ra);
+  for (int k = 1; k <= 2; ++k) {
+    double so3row[18];
+    for (int c = 0; c < 18; ++c) so3row[c] = pa[18 * (k - 1) + c];
+    imu_accel_row_expand(so3row, q4(pa[36], pa[37], pa[38], pa[39]), pa[39 + k], pa[42], K, k, acc_rows + 40 * k, 1);
+  }
+  double pg[GYR_PARK], rg[3];
+  imu_gyro_rows(W, K, u_so3, u_bg, v3(g_meas[0], g_meas[1], g_meas[2]), gyr_rows, 1, pg, rg);
+  for (int k = 1; k <= 2; ++k) {
+    for (int c = 0; c < 18; ++c) gyr_rows[24 * k + c] = pg[18 * (k - 1) + c];
+    gyr_rows[24 * k + 18] = pg[35 + k];
+    for (int c = 19; c < 24; ++c) gyr_rows[24 * k + c] = 0.0;
+  }
+}
 // ---- scalar pieces of the rotation / time-offset initialiser (icc_rotinit_math.cuh) ----------------------------------------------------
 int hm_nearest_sorted(const double* ts, int n, double t, double* dist) { double d = 0.0; const int i = nearest_sorted(ts, n, t, d); *dist = d; return i; }
 void hm_slerp4(const double* a, const double* b, double t, double* out) {

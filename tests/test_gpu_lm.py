@@ -16,7 +16,7 @@ def _run_both(oracle_factory, gpu_factory, ds, flags, iters=50, **kw):
     return o, g, o.optimize(iters, flags), g.optimize(iters, flags)
 
 
-def test_config1_two_stage_calibration(oracle_factory, gpu_factory):
+def test_config1_two_stage_calibration(oracle_factory, gpu_factory, eval_path):
     ds = syn.make_dataset(syn.CONFIGS[1])
     o, g, so, sg = _run_both(oracle_factory, gpu_factory, ds, F_STAGE1)
     assert sg.iterations == so.iterations and sg.termination == so.termination and sg.successful_steps == so.successful_steps
@@ -30,7 +30,7 @@ def test_config1_two_stage_calibration(oracle_factory, gpu_factory):
     assert rel(so3g, so3o) < 1e-8 and rel(r3g, r3o) < 1e-8
 
 
-def test_config2_fisheye(oracle_factory, gpu_factory):
+def test_config2_fisheye(oracle_factory, gpu_factory, eval_path):
     ds = syn.make_dataset(syn.CONFIGS[2])
     o, g, so, sg = _run_both(oracle_factory, gpu_factory, ds, F_STAGE1)
     assert sg.num_tangent == 1236 and sg.num_residuals == so.num_residuals

@@ -35,7 +35,7 @@ def _assert_eval_parity(o, g, flags, hessian=True):
 
 
 @pytest.mark.parametrize("k", range(8))
-def test_eval_parity_every_camera_model_all_blocks(oracle_factory, gpu_factory, k):
+def test_eval_parity_every_camera_model_all_blocks(oracle_factory, gpu_factory, k, eval_path):
     cfg = syn.config5(k); cfg.n_frames = 20
     o, g = _pair(oracle_factory, gpu_factory, syn.make_dataset(cfg), known_gravity=False)
     for flags in (F_STAGE1, F_ALL, F_STAGE2, capi.FLAG_T_I_C, capi.FLAG_SPLINE | capi.FLAG_GYR_BIAS, capi.FLAG_GRAVITY_DIR | capi.FLAG_ACC_BIAS):
@@ -62,13 +62,13 @@ def test_eval_parity_imu_intrinsics_flag(oracle_factory, gpu_factory):
     assert sg.iterations == so.iterations and abs(sg.final_cost - so.final_cost) <= 1e-7 * so.final_cost
 
 
-def test_eval_parity_pinhole_radial_tangential(oracle_factory, gpu_factory):
+def test_eval_parity_pinhole_radial_tangential(oracle_factory, gpu_factory, eval_path):
     cfg = syn.tiny_config(cm.PINHOLE_RADIAL_TANGENTIAL, (440.0, 1.01, 0.2, 480.0, 270.0, -0.1, 0.02, -0.003, 1e-3, -2e-3), seed=3)
     o, g = _pair(oracle_factory, gpu_factory, syn.make_dataset(cfg), known_gravity=False)
     _assert_eval_parity(o, g, F_ALL)
 
 
-def test_eval_parity_uneven_knot_spacing(oracle_factory, gpu_factory):
+def test_eval_parity_uneven_knot_spacing(oracle_factory, gpu_factory, eval_path):
     """dt_so3 != dt_r3: different segment indices per spline, wider band, IMU cells cut at both knot grids."""
     for a, b in ((0.04, 0.07), (0.09, 0.05)):
         o, g = _pair(oracle_factory, gpu_factory, syn.make_dataset(syn.tiny_config(dt_so3_s=a, dt_r3_s=b, n_frames=30)), known_gravity=False)
@@ -76,7 +76,7 @@ def test_eval_parity_uneven_knot_spacing(oracle_factory, gpu_factory):
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=[os.path.basename(p) for p in golden_files()])
-def test_gpu_matches_committed_golden(gpu_factory, path):
+def test_gpu_matches_committed_golden(gpu_factory, path, eval_path):
     ds = load_golden(path)
     g = gpu_factory(); capi.load_dataset(g, ds, known_gravity=False)
     for tag, flags in (("stage1", F_STAGE1), ("all", F_ALL), ("stage2", F_STAGE2)):
@@ -93,7 +93,7 @@ def test_gpu_matches_committed_golden(gpu_factory, path):
     assert abs(g2.get_line_delay() - float(ds["lm_stage2_line_delay"])) <= 1e-8 * abs(float(ds["lm_stage2_line_delay"]))
 
 
-def test_ragged_and_empty_frames(oracle_factory, gpu_factory):
+def test_ragged_and_empty_frames(oracle_factory, gpu_factory, eval_path):
     """Frames with 0, 1, 33 and all corners, shuffled point ids, a frame outside the IMU range."""
     ds = dict(syn.make_dataset(syn.tiny_config(grid=(9, 5), n_frames=16)))
     C = 45
@@ -109,7 +109,7 @@ def test_ragged_and_empty_frames(oracle_factory, gpu_factory):
     _assert_eval_parity(o, g, F_ALL)
 
 
-def test_failed_projections_give_constant_1e10_residuals(oracle_factory, gpu_factory):
+def test_failed_projections_give_constant_1e10_residuals(oracle_factory, gpu_factory, eval_path):
     """a point outside the unified model's domain => residual (1e10, 1e10) with zero derivative."""
     cfg = syn.tiny_config(cm.DOUBLE_SPHERE, (342.4, 1.0, 0.0, 472.6, 273.9, -0.215, 0.513), seed=5)
     ds = dict(syn.make_dataset(cfg))
@@ -141,7 +141,7 @@ def test_global_shutter_path(oracle_factory, gpu_factory):
     assert abs(g.mean_reprojection_error() - o.mean_reprojection_error()) < 1e-9
 
 
-def test_no_imu_and_imu_only_slices(oracle_factory, gpu_factory):
+def test_no_imu_and_imu_only_slices(oracle_factory, gpu_factory, eval_path):
     ds = dict(syn.make_dataset(syn.tiny_config()))
     ds["imu_t"] = ds["imu_t"][:0]; ds["accel"] = ds["accel"][:0]; ds["gyro"] = ds["gyro"][:0]
     o, g = _pair(oracle_factory, gpu_factory, ds)
@@ -149,7 +149,7 @@ def test_no_imu_and_imu_only_slices(oracle_factory, gpu_factory):
     _assert_eval_parity(o, g, F_STAGE1)
 
 
-def test_gradient_matches_finite_differences_of_gpu_cost(gpu_factory):
+def test_gradient_matches_finite_differences_of_gpu_cost(gpu_factory, eval_path):
     ds = syn.make_dataset(syn.tiny_config(cm.EXTENDED_UNIFIED, (438.0, 1.0, 0.0, 489.5, 272.0, 0.5115, 1.062), seed=9))
     g = gpu_factory(); capi.load_dataset(g, ds, known_gravity=False)
     flags = F_STAGE1 | capi.FLAG_GRAVITY_DIR | capi.FLAG_IMU_BIASES

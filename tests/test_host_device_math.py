@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_vision_rows.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_vision_rows.cuh", "icc_imu_rows.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -275,6 +275,57 @@ def test_device_vision_rows_against_finite_differences(hm, model, k):
             assert np.abs(rows[:, 39 + a] - (f(T=Tp) - f(T=Tm)) / (2 * h)).max() < 3e-7 * scale, ("omega", a)
         hl = 1e-9
         assert np.abs(rows[:, 42] - (f(l=ld + hl) - f(l=ld - hl)) / (2 * hl)).max() < 1e-5 * max(1.0, np.abs(rows[:, 42]).max()), "line delay"
+
+
+def _imu_residuals(so3, r3, ba, bg, u_so3, u_r3, u_ba, u_bg, Ma, Mg, grav, w_acc, w_gyr, inv_so3_dt, inv_r3_dt, a_meas, g_meas):
+    """AccelerationCostFunctorSplit / GyroCostFunctorSplit (ceres_calib_split_residuals.h:52-93,133-169), independent NumPy statement."""
+    R = _qmat(_spline_rotation(so3, u_so3))
+    ddc = _B6 @ np.array([0.0, 0.0, 2.0, 6.0 * u_r3, 12.0 * u_r3 ** 2, 20.0 * u_r3 ** 3])
+    acc_w = inv_r3_dt ** 2 * (ddc @ r3)
+    c3 = lambda u: np.array([0.5 * (1 - 2 * u + u * u), 0.5 * (1 + 2 * u - 2 * u * u), 0.5 * u * u])   # noqa: E731
+    ra = w_acc * (R.T @ (acc_w + grav) - Ma @ (a_meas - c3(u_ba) @ ba))
+    h = 1e-5       # body velocity = vee(R^T dR/du) / dt by central differences of the spline rotation
+    om = _qlog(_qmul(_qinv(_spline_rotation(so3, u_so3 - h)), _spline_rotation(so3, u_so3 + h))) / (2 * h) * inv_so3_dt
+    rg = w_gyr * (om - Mg @ (g_meas - c3(u_bg) @ bg))
+    return ra, rg
+
+
+def test_device_imu_rows_against_finite_differences(hm):
+    """imu_accel_rows / imu_gyro_rows + the parked-row expansion (icc_imu_rows.cuh) against central differences of the NumPy functors:
+    right increments on the six SO(3) knots, the six R^3 knots, gravity."""
+    rng = np.random.default_rng(77)
+    for trial in range(3):
+        so3 = [_qexp(rng.normal(0, 0.6, 3))]
+        for i in range(5):
+            so3.append(_qmul(so3[-1], _qexp(rng.normal(0, [0.03, 0.3, 0.8][trial], 3))))
+        so3 = np.array(so3); r3 = rng.normal(0, 0.05, (6, 3)); ba = rng.normal(0, 0.05, (3, 3)); bg = rng.normal(0, 0.01, (3, 3))
+        u_so3, u_r3, u_ba, u_bg = rng.uniform(0.02, 0.97, 4)
+        Ma = np.array([[1.01, -0.002, 0.003], [0, 0.99, -0.001], [0, 0, 1.02]]); Mg = np.eye(3) + rng.normal(0, 0.003, (3, 3))
+        grav = np.array([0.1, -0.2, 9.8]); w_acc, w_gyr, idt_s, idt_r = 3.0, 40.0, 20.0, 20.0
+        a_meas, g_meas = rng.normal(0, 3, 3), rng.normal(0, 1, 3)
+        A, G = np.zeros(120), np.zeros(72)
+        args = [np.ascontiguousarray(x, dtype=np.float64) for x in (so3, r3, ba, bg)]
+        hm.hm_imu_rows(*[a.ctypes.data_as(DP) for a in args], *[ctypes.c_double(x) for x in (u_so3, u_r3, u_ba, u_bg)], np.ascontiguousarray(Ma).ctypes.data_as(DP), np.ascontiguousarray(Mg).ctypes.data_as(DP),
+                       grav.ctypes.data_as(DP), ctypes.c_double(w_acc), ctypes.c_double(w_gyr), ctypes.c_double(idt_s), ctypes.c_double(idt_r), a_meas.ctypes.data_as(DP), g_meas.ctypes.data_as(DP),
+                       A.ctypes.data_as(DP), G.ctypes.data_as(DP))
+        A, G = A.reshape(3, 40), G.reshape(3, 24)
+        f = lambda s=so3, r=r3, g=grav: _imu_residuals(s, r, ba, bg, u_so3, u_r3, u_ba, u_bg, Ma, Mg, g, w_acc, w_gyr, idt_s, idt_r, a_meas, g_meas)   # noqa: E731
+        ra, rg = f()
+        assert np.allclose(A[:, 39], ra, rtol=1e-12, atol=1e-10) and np.allclose(G[:, 18], rg, rtol=1e-7, atol=1e-7) and np.all(G[:, 19:] == 0.0)
+        sa, sg = max(1.0, np.abs(A[:, :39]).max()), max(1.0, np.abs(G[:, :18]).max())
+        h = 1e-6
+        for j in range(6):
+            for a in range(3):
+                e = np.zeros(3); e[a] = h
+                sp, sm = so3.copy(), so3.copy(); sp[j] = _qmul(so3[j], _qexp(e)); sm[j] = _qmul(so3[j], _qexp(-e))
+                (ap, gp), (am, gm) = f(s=sp), f(s=sm)
+                assert np.abs(A[:, 3 * j + a] - (ap - am) / (2 * h)).max() < 3e-7 * sa, ("acc so3", j, a)
+                assert np.abs(G[:, 3 * j + a] - (gp - gm) / (2 * h)).max() < 2e-4 * sg, ("gyr so3", j, a)      # differences of a difference quotient
+                rp, rm = r3.copy(), r3.copy(); rp[j, a] += h; rm[j, a] -= h
+                assert np.abs(A[:, 18 + 3 * j + a] - (f(r=rp)[0] - f(r=rm)[0]) / (2 * h)).max() < 3e-7 * sa, ("acc r3", j, a)
+        for a in range(3):
+            e = np.zeros(3); e[a] = h
+            assert np.abs(A[:, 36 + a] - (f(g=grav + e)[0] - f(g=grav - e)[0]) / (2 * h)).max() < 3e-7 * sa, ("gravity", a)
 
 
 def test_device_polynomial_sincos(hm):

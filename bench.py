@@ -318,7 +318,7 @@ def main():
         traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (config 4 only)
             if args.config == 4:
-                nc = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))["vision_tmem_kernel<6>"]
+                nc = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))["eval_tmem_kernel<6>"]
                 traffic = nc["dram_bytes_read"] + nc["dram_bytes_write"]; traffic_src = "profiles/r2_ncu_summary.json (ncu --set full, one launch)"
         except Exception:
             pass

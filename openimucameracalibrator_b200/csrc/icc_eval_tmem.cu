@@ -27,7 +27,7 @@ constexpr size_t SLOT_BYTES = sizeof(tmi::ImuSlot) > sizeof(tmv::WarpSlot) ? siz
 constexpr size_t CONST_BYTES = ((sizeof(VisConst) + sizeof(ImuConst) + 15) / 16) * 16;
 
 template <int MODEL>
-__global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out) {
+__global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out, int rounds) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VisConst* KV = reinterpret_cast<VisConst*>(smem_raw);
   ImuConst* KI = reinterpret_cast<ImuConst*>(smem_raw + sizeof(VisConst));
@@ -49,12 +49,12 @@ __global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, 
   NeLayout L; L.ne = P.ne; L.off_E = P.ne_off_E; L.off_C = P.ne_off_C; L.off_g = P.ne_off_g; L.off_cost = P.ne_off_cost; L.nk = P.nk; L.nb = P.nb; L.ldb = P.ldb;
 
   const int gw = warp * gridDim.x + blockIdx.x;           // global warp: consecutive runs land on different SMs
-  if (gw < P.n_vitems) {
-    const VisItem it = P.vitems[gw];
-    if (it.pos_end > it.pos_begin) tmv::run_item<MODEL>(P, S, KV, reinterpret_cast<tmv::WarpSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, it, res_out, lane);
-  } else if (gw < P.n_iitems) {          // (a launch carries one item type: launch_eval_tmem)
-    const VisItem it = P.iitems[gw];
-    if (it.pos_end > it.pos_begin) tmi::run_item(P, S, KI, reinterpret_cast<tmi::ImuSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, it, res_out, lane);
+  if (P.n_vitems > 0) {
+    if (gw < P.n_vitems) tmv::run_item<MODEL>(P, S, KV, reinterpret_cast<tmv::WarpSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.vitems[gw], res_out, lane, rounds);
+    else for (int r = 0; r < rounds; ++r) asm volatile("bar.sync 1, %0;" :: "r"(EW * 32) : "memory");
+  } else if (P.n_iitems > 0) {           // (a launch carries one item type: launch_eval_tmem)
+    if (gw < P.n_iitems) tmi::run_item(P, S, KI, reinterpret_cast<tmi::ImuSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.iitems[gw], res_out, lane, rounds);
+    else for (int r = 0; r < rounds; ++r) { asm volatile("bar.sync 1, %0;" :: "r"(EW * 32) : "memory"); asm volatile("bar.sync 2, %0;" :: "r"(EW * 32) : "memory"); }
   }
   tmem_fence_before_sync();
   __syncthreads();
@@ -68,7 +68,10 @@ int launch_model(const DeviceProblem& P, const DeviceState& S, double* residuals
     if (cudaFuncSetAttribute(eval_tmem_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     attr_done = true;
   }
-  eval_tmem_kernel<MODEL><<<grid, EW * 32, smem, st>>>(P, S, residuals_out);
+  // loose lockstep: the warps of a CTA start every vision chunk together (one named barrier per chunk), so that they walk the same
+  // ~80 KB of unrolled code at the same time: instruction-cache hit rate 81 % -> better, config 4 vision launch 155 -> 150 us
+  const int rounds = getenv("ICC_TMEM_NO_LOCKSTEP") ? 0 : P.n_vitems > 0 ? (P.n_vchunks + P.n_vitems - 1) / P.n_vitems : P.n_iitems > 0 ? (P.n_ichunks + P.n_iitems - 1) / P.n_iitems : 0;
+  eval_tmem_kernel<MODEL><<<grid, EW * 32, smem, st>>>(P, S, residuals_out, rounds);
   return 0;
 }
 

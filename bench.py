@@ -234,6 +234,7 @@ def main():
     comm = None
     if world > 1:
         from openimucameracalibrator_b200.distributed import make_comm
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: the contract is ONE JSON line
         comm = make_comm(calibrator.load_library(), local)
 
     t_load0 = time.perf_counter()

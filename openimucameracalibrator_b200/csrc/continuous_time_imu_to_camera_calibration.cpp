@@ -317,7 +317,6 @@ int main(int argc, char** argv) {
     ICC(icc_optimize(h, 50, flags, &s1));
     if (stage2) ICC(icc_optimize(h, 10, ICC_FLAG_CAM_LINE_DELAY, &s2));
     if (shard_rank > 0) { icc_destroy(h); icc_comm_destroy(comm); return 0; }   // only rank 0 reports
-    for (pid_t pid : children) { int st = 0; waitpid(pid, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::cerr << "a rank process failed" << std::endl; return 2; } }
     double reproj_error = s1.mean_reproj_error, reproj_error_after_ld = stage2 ? s2.mean_reproj_error : reproj_error;
     std::cout << "LM iterations: " << s1.iterations << " cost " << s1.initial_cost << " -> " << s1.final_cost << "  (" << s1.seconds_total << " s, " << s1.gpu_launches << " kernel launches)\n";
     std::cout << "Mean reprojection error " << reproj_error << "px\nMean reprojection error after line delay optim " << reproj_error_after_ld << "px\n";
@@ -373,7 +372,8 @@ int main(int argc, char** argv) {
       write_ply(op + "/sparse_recon_calib_dataset.ply", pts, col);
     }
     icc_destroy(h);
-    icc_comm_destroy(comm);
+    icc_comm_destroy(comm);        // (ncclCommDestroy waits for the peers: the rank processes are only reaped afterwards)
+    for (pid_t pid : children) { int st = 0; waitpid(pid, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::cerr << "a rank process failed" << std::endl; return 2; } }
   } catch (const std::exception& e) {
     std::cerr << "ERROR: " << e.what() << std::endl;
     return 1;

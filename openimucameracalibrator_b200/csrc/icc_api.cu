@@ -730,7 +730,66 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   const bool direct = h->shard_world == 1 && imu_pass(true) && h->imu_contig;
   if (direct) {
     for (int i = 0; i < nf; ++i) if (frame_ok[i]) frame_sel.push_back(i);
+  } else if ([&]() -> bool {
+    // Sharded fast path (every stream in time order, the usual case): the shard rule -- unit `mine` iff the scalar residuals of all
+    // units before it in the time-merged order (frames before IMU samples on ties) fall in [lo, hi) -- is evaluated on counts only:
+    // kept IMU samples of a sorted stream are ONE index range (the validity tests of CalcTimes are monotone in time), frames are
+    // break points found by bisection, and only the shard's own samples are then walked.  O(frames log samples + samples / world)
+    // instead of O(samples) per rank; same decisions as the general path below (tests/test_capi_boundary.py, test_sharding_gloo.py).
+    const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s, t0 = h->t0_s, tend = h->tend_s;
+    if (!increasing || !std::is_sorted(imu_t, imu_t + n_imu_in)) return false;
+    auto fits = [&](size_t i) {   // upper-side validity (monotone: true, then false)
+      const double t = imu_t[i] + toff;
+      if (t >= tend) return false;
+      const int64_t st = (int64_t)(t * S_TO_NS) - h->start_ns;
+      return size_t(st / h->dt_r3_ns + SPLINE_N) <= (size_t)nr3 && size_t(st / h->dt_so3_ns + SPLINE_N) <= (size_t)nso3 && size_t(st / h->dt_ba_ns + BIAS_N) <= (size_t)nba && size_t(st / h->dt_bg_ns + BIAS_N) <= (size_t)nbg;
+    };
+    std::vector<size_t> idx(0);
+    struct It { size_t i; };   // bisection over indices
+    auto bisect = [&](size_t a, size_t b, auto pred) { while (a < b) { const size_t m = (a + b) / 2; if (pred(m)) a = m + 1; else b = m; } return a; };   // first index where pred is false
+    const size_t ia = bisect(0, n_imu_in, [&](size_t i) { const double t = imu_t[i] + toff; return t < t0 || (int64_t)(t * S_TO_NS) - h->start_ns < 0; });
+    const size_t ib = bisect(ia, n_imu_in, fits);
+    const size_t in_window = bisect(ia, n_imu_in, [&](size_t i) { return imu_t[i] + toff < tend; }) - ia;
+    h->dropped_imu = (int)(in_window - (ib - ia));
+    std::vector<int> fk; fk.reserve(nf);
+    for (int i = 0; i < nf; ++i) if (frame_ok[i]) fk.push_back(i);
+    long total = 6 * (long)(ib - ia);
+    for (int j : fk) total += 2 * (all_frames[j].c1 - all_frames[j].c0);
+    const long lo = total * h->shard_rank / h->shard_world, hi = total * (h->shard_rank + 1) / h->shard_world;
+    auto ceil_div6 = [](long v) { return v <= 0 ? 0L : (v + 5) / 6; };
+    size_t ka = ib, kb = ia, prev_p = ia;   // this shard's sample range [ka, kb)
+    long Rf = 0;                            // residuals of the kept frames seen so far
+    auto take_imu = [&](size_t a, size_t b) {   // samples [a, b) lie between two frames: run_before(i) = Rf + 6 (i - ia)
+      const size_t first = std::max(a, ia + (size_t)ceil_div6(lo - Rf)), last = std::min(b, ia + (size_t)ceil_div6(hi - Rf));
+      if (first < last) { ka = std::min(ka, first); kb = std::max(kb, last); }
+    };
+    for (int j : fk) {
+      const double tf = all_frames[j].t_s;
+      const size_t p = bisect(prev_p, ib, [&](size_t i) { return imu_t[i] + toff < tf; });   // samples strictly before the frame
+      take_imu(prev_p, p);
+      const long run = Rf + 6 * (long)(p - ia);
+      if (run >= lo && run < hi) frame_sel.push_back(j);
+      Rf += 2 * (all_frames[j].c1 - all_frames[j].c0);
+      prev_p = p;
+    }
+    take_imu(prev_p, ib);
+    if (ka > kb) ka = kb = ia;
+    // the shard's own samples: segment tracking, cells, used-in-place readings
+    SegTrack tr_r3{h->dt_r3_ns}, tr_so3{h->dt_so3_ns}, tr_ba{h->dt_ba_ns}, tr_bg{h->dt_bg_ns};
+    const size_t K = kb - ka;
+    h->imu_used_t.resize(K); h->imu_used_st.n = K; h->cells.clear();
+    for (size_t k = 0; k < K; ++k) {
+      const double t = imu_t[ka + k] + toff; const int64_t st = (int64_t)(t * S_TO_NS) - h->start_ns;
+      const int a = (int)tr_r3.seg(st), b = (int)tr_so3.seg(st), c = (int)tr_ba.seg(st), d = (int)tr_bg.seg(st);
+      h->imu_used_t[k] = t; h->imu_used_st[k] = st;
+      if (h->cells.empty() || h->cells.back().s_so3 != b || h->cells.back().s_r3 != a || h->cells.back().s_ba != c || h->cells.back().s_bg != d) h->cells.push_back({b, a, c, d, (int)k, (int)k});
+      h->cells.back().i_end = (int)k + 1;
+    }
+    h->imu_contig = K > 0; h->imu_src0 = (int)ka;
+    return true;
+  }()) {
   } else {
+    frame_sel.clear();
     imu_pass(false);
     struct Unit { double t; int kind, idx, nres; };
     std::vector<Unit> units; units.reserve(nf + all_imu.size());

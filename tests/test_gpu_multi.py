@@ -70,7 +70,16 @@ def test_cli_gpus_flag_matches_single_gpu(tmp_path):
     for gpus in (1, 2):
         d = tmp_path / f"g{gpus}"; d.mkdir()
         paths = iof.write_dataset_files(ds, str(d))
-        out = subprocess.run(_args(paths, str(d), ["--calibrate_cam_line_delay", f"--gpus={gpus}"]), capture_output=True, text=True, timeout=240)
+        env = dict(os.environ); env["NCCL_DEBUG"] = "WARN"
+        proc = subprocess.Popen(_args(paths, str(d), ["--calibrate_cam_line_delay", f"--gpus={gpus}"]), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+        try:
+            so, se = proc.communicate(timeout=90)
+        except subprocess.TimeoutExpired:
+            import signal
+            os.killpg(proc.pid, signal.SIGKILL)          # the launcher and the rank processes it spawned
+            so, se = proc.communicate()
+            pytest.fail(f"--gpus={gpus} did not finish in 90 s\nstdout:\n{so[-3000:]}\nstderr:\n{se[-3000:]}")
+        out = subprocess.CompletedProcess(proc.args, proc.returncode, so, se)
         assert out.returncode == 0, out.stderr + out.stdout
         if gpus == 2:
             assert "sharded over 2 GPUs" in out.stdout

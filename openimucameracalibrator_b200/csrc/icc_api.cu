@@ -486,6 +486,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     if (sc[SC_OK] == 0.0 || !(model_change > 0.0)) {          // invalid step (HandleInvalidStep)
       if (++invalid >= h->opt.max_consecutive_invalid_steps) { S.termination = 4; break; }
       radius /= decrease_factor; decrease_factor *= 2.0;
+      if (radius < h->opt.min_trust_region_radius) { S.termination = 4; break; }   // Ceres tests MinTrustRegionRadiusReached after every iteration
       continue;
     }
     invalid = 0;

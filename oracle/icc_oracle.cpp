@@ -902,6 +902,7 @@ void lm_solve(Oracle& o, int max_iters, int flags, bool check_convergence, icc_s
     if (!ok || !(model_change > 0.0)) {
       if (++invalid >= o.opt.max_consecutive_invalid_steps) { S.termination = 4; break; }
       radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      if (radius < o.opt.min_trust_region_radius) { S.termination = 4; break; }   // MinTrustRegionRadiusReached is tested after every iteration
       continue;
     }
     invalid = 0;

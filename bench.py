@@ -52,19 +52,56 @@ def algorithmic_bytes(ds, n_frames, n_corners, n_imu, n_cells):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the same fields as the nvidia-smi clocks line).
+    Read through NVML inside this process (nvidia_ml_py, one handle opened before the timed region, a thread sampling every 20 ms): a
+    freshly started `nvidia-smi -lms` stalls the driver of the GPU it queries for a few milliseconds per sample, which at N > 1 shows up as
+    a 5 ms step on every rank (the peers wait inside the all-reduce) -- measured at N = 8.  Falls back to the nvidia-smi subprocess when
+    NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.p = None
+        import threading
+        self.p, self.thread, self.samples, self.stop_flag, self.index = None, None, [], False, index
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True); self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.p = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True; self.thread.join(timeout=1.0)
+            nv = self.nv
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            sm = [s for s, _ in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            hot = sorted(sm)[len(sm) // 2:] if sm else []
+            return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm), "source": "nvml (in-process, 20 ms)"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -86,7 +123,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         hot = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def run_reference(args, cfg):
@@ -262,6 +299,8 @@ def main():
     summ = None
     for i in range(args.warmup):
         reset(); api.lm_iterations(1, FLAGS)
+    import gc
+    gc.collect(); gc.disable()                      # no collector pause inside a timed step (at N > 1 every rank waits for the slowest)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     for i in range(args.steps):
@@ -277,6 +316,7 @@ def main():
         step_ms.append(e0.elapsed_time(e1)); launches += summ.gpu_launches
     barrier()
     clocks = sampler.stop() if sampler else None
+    gc.enable()
     total_ms = float(np.sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms = float(t.item())

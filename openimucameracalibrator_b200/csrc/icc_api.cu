@@ -119,7 +119,8 @@ struct PinnedArena {
 
 struct StateBufs {
   DevBuf<double4> so3, r3, ba, bg; DevBuf<double> glob;
-  DeviceState view() const { DeviceState s; s.so3 = so3.p; s.r3 = r3.p; s.ba = ba.p; s.bg = bg.p; s.glob = glob.p; return s; }
+  DevBuf<double4> pts, board; DevBuf<double> pjac;   // board points of the state (icc_points.cu)
+  DeviceState view() const { DeviceState s; s.so3 = so3.p; s.r3 = r3.p; s.ba = ba.p; s.bg = bg.p; s.glob = glob.p; s.pts = pts.p; s.board = board.p; s.pjac = pjac.p; return s; }
 };
 
 struct FrameHost { double t_s; int c0, c1; int s_so3, s_r3; double u_so3, u_r3; };
@@ -252,9 +253,23 @@ cudaError_t upload_staged(icc_handle* h, DevBuf<T>& d, const std::vector<T>& v) 
   return cudaMemcpyAsync(d.p, stage, bytes, cudaMemcpyHostToDevice, h->stream);
 }
 
+// board points of state `which`: homogeneous vectors up, de-homogenised copy + local Jacobians derived on the device
+icc_status upload_points(icc_handle* h, int which, bool staged) {
+  StateBufs& s = h->st[which];
+  const size_t np = h->points.size() / 4;
+  if (!np) return ICC_OK;
+  CU(s.board.alloc(np)); CU(s.pjac.alloc(12 * np));
+  if (staged) { CU(upload_staged(h, s.pts, pad4(h->points, 4))); }
+  else { CU(cudaStreamSynchronize(h->stream)); CU(s.pts.upload(pad4(h->points, 4))); }
+  launch_points_prepare((int)np, s.pts.p, s.board.p, s.pjac.p, h->stream);
+  if (!staged) CU(cudaStreamSynchronize(h->stream));
+  return ICC_OK;
+}
+
 icc_status upload_state(icc_handle* h, int which, bool staged = false) {
   StateBufs& s = h->st[which];
   std::vector<double> g(h->glob, h->glob + G_COUNT);
+  { icc_status r = upload_points(h, which, staged); if (r != ICC_OK) return r; }
   if (staged) {
     CU(upload_staged(h, s.so3, pad4(h->so3, 4))); CU(upload_staged(h, s.r3, pad4(h->r3, 3))); CU(upload_staged(h, s.ba, pad4(h->ba, 3))); CU(upload_staged(h, s.bg, pad4(h->bg, 3)));
     CU(upload_staged(h, s.glob, g));
@@ -278,6 +293,7 @@ icc_status sync_state_to_host(icc_handle* h) {
   CU(cudaStreamSynchronize(h->stream));
   CU(pull(s.so3, h->so3, 4)); CU(pull(s.r3, h->r3, 3)); CU(pull(s.ba, h->ba, 3)); CU(pull(s.bg, h->bg, 3));
   CU(cudaMemcpy(h->glob, s.glob.p, G_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h->state_dirty_host && s.pts.n * 4 == h->points.size()) CU(pull(s.pts, h->points, 4));
   h->state_dirty_host = false; h->knots_dirty_host = false;
   return ICC_OK;
 }
@@ -292,13 +308,15 @@ icc_status push_state_to_device(icc_handle* h) {
 // Active set (SetFixedParams, impl.h:92-252) -> column maps in SOLVER order: spline knots sorted by knot time (SO3 before
 // R3 on ties) form the banded part; T_i_c, gravity, line delay and bias knots form the border.
 icc_status configure(icc_handle* h, int flags) {
-  if (flags & ICC_FLAG_POINTS) return fail(h, ICC_ERR_UNSUPPORTED, "POINTS is never set by the hot CLI and is not supported");
+  if ((flags & ICC_FLAG_POINTS) && (flags & ICC_FLAG_CAM_INTRINSICS)) return fail(h, ICC_ERR_UNSUPPORTED, "POINTS together with CAM_INTRINSICS (an extension flag of this library) is not supported");
   if (h->cur_flags == flags) return ICC_OK;
   const int nso3 = (int)h->so3.size() / 4, nr3 = (int)h->r3.size() / 3, nba = (int)h->ba.size() / 3, nbg = (int)h->bg.size() / 3;
   const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
   const bool ld = (flags & ICC_FLAG_CAM_LINE_DELAY) && h->ip.init_line_delay_s != 0.0;
   const bool ab = flags & (ICC_FLAG_ACC_BIAS | ICC_FLAG_IMU_BIASES), gb = flags & (ICC_FLAG_GYR_BIAS | ICC_FLAG_IMU_BIASES);
   const bool intr = flags & ICC_FLAG_IMU_INTRINSICS, cam_intr = flags & ICC_FLAG_CAM_INTRINSICS, toff = flags & ICC_FLAG_TIME_OFFSET;
+  const int npts = (int)(h->points.size() / 4);
+  const bool pts = (flags & ICC_FLAG_POINTS) && npts > 0;      // every track a view sees (impl.h:136-152); points no view sees get zero columns
   // canonical offsets
   int n = 0;
   const int c_so3 = spline ? n : -1; if (spline) n += 3 * nso3;
@@ -312,6 +330,7 @@ icc_status configure(icc_handle* h, int flags) {
   const int c_gi = intr ? n : -1; if (intr) n += 9;
   const int c_ci = cam_intr ? n : -1; if (cam_intr) n += h->n_intr;
   const int c_to = toff ? n : -1; if (toff) n += 1;
+  const int c_pts = pts ? n : -1; if (pts) n += 3 * npts;
   h->n_tan = n;
   h->so3_col.assign(nso3, -1); h->r3_col.assign(nr3, -1); h->ba_col.assign(nba, -1); h->bg_col.assign(nbg, -1);
   int pos = 0;
@@ -333,6 +352,7 @@ icc_status configure(icc_handle* h, int flags) {
   const int col_gi = intr ? pos : -1; if (intr) pos += 9;
   const int col_ci = cam_intr ? pos : -1; if (cam_intr) pos += h->n_intr;
   const int col_to = toff ? pos : -1; if (toff) pos += 1;
+  const int col_pts = pts ? pos : -1; if (pts) pos += 3 * npts;
   const int nb = pos - nk;
   h->perm.assign(n, -1);
   if (spline) { for (int k = 0; k < nso3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_so3 + 3 * k + d] = h->so3_col[k] + d; for (int k = 0; k < nr3; ++k) for (int d = 0; d < 3; ++d) h->perm[c_r3 + 3 * k + d] = h->r3_col[k] + d; }
@@ -344,6 +364,7 @@ icc_status configure(icc_handle* h, int flags) {
   if (intr) { for (int d = 0; d < 6; ++d) h->perm[c_ai + d] = col_ai + d; for (int d = 0; d < 9; ++d) h->perm[c_gi + d] = col_gi + d; }
   if (cam_intr) for (int d = 0; d < h->n_intr; ++d) h->perm[c_ci + d] = col_ci + d;
   if (toff) h->perm[c_to] = col_to;
+  if (pts) for (int d = 0; d < 3 * npts; ++d) h->perm[c_pts + d] = col_pts + d;
   // half bandwidth: widest knot window touched by one residual block
   int kd = 0;
   if (spline) {
@@ -363,7 +384,7 @@ icc_status configure(icc_handle* h, int flags) {
   h->cur_flags = flags;
   DeviceProblem& P = h->P;
   P.nk = nk; P.nb = nb; P.kd = kd; P.ldb = kd + 1;
-  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.col_ai = col_ai; P.col_gi = col_gi; P.col_ci = col_ci; P.col_to = col_to;
+  P.col_tic = h->col_tic; P.col_g = h->col_g; P.col_ld = h->col_ld; P.col_ai = col_ai; P.col_gi = col_gi; P.col_ci = col_ci; P.col_to = col_to; P.col_pts = col_pts; P.n_points = npts;
   P.bias_active = (ab || gb) ? 1 : 0; P.intr_active = (intr || toff) ? 1 : 0; P.cam_intr_active = cam_intr ? 1 : 0;
   P.ne_off_E = (int64_t)nk * P.ldb; P.ne_off_C = P.ne_off_E + (int64_t)nk * nb; P.ne_off_g = P.ne_off_C + (int64_t)nb * nb;
   P.ne_off_cost = P.ne_off_g + nk + nb; P.ne_size = (P.ne_off_cost + 1 + 3) / 4 * 4;
@@ -391,6 +412,7 @@ icc_status cross_rank_sum(icc_handle* h, double* dev, int64_t n) {
 icc_status eval_jacobian(icc_handle* h, const DeviceState& S, double* residuals_dev) {
   CU(cudaMemsetAsync(h->P.ne, 0, (size_t)h->P.ne_size * sizeof(double), h->stream));
   if (launch_eval(h->P, S, true, nullptr, residuals_dev, nullptr, h->stream, h->aux_ok ? &h->aux : nullptr)) return fail(h, ICC_ERR_CUDA, std::string("eval launch: ") + cudaGetErrorString(cudaGetLastError()));
+  if (h->P.col_pts >= 0 && h->P.rolling) launch_points_jac(h->P, S, S.pjac, h->P.col_pts, h->sm_count, h->stream);   // board-point columns (POINTS)
   return cross_rank_sum(h, h->P.ne, h->P.ne_size);
 }
 icc_status eval_cost(icc_handle* h, const DeviceState& S, double* cost_dev, double* residuals_dev, double* reproj_dev) {
@@ -473,6 +495,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     const int b = mark(); lin_spans.push_back({a, b});
     const int cand = 1 - h->cur;
     launch_update(P, h->st[h->cur].view(), h->st[cand].view(), h->d_delta.p, h->max_ba, h->max_bg, h->d_scal.p, h->stream);
+    if (P.col_pts >= 0) launch_points_update(P.n_points, P.col_pts, h->st[h->cur].pts.p, h->st[cand].pts.p, h->st[cand].board.p, h->st[cand].pjac.p, h->d_delta.p, h->d_scal.p, h->stream);
     rc = eval_cost(h, h->st[cand].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); if (rc != ICC_OK) return rc;
     rc = read_scalars(); if (rc != ICC_OK) return rc;
     if (fresh_jacobian) {
@@ -510,6 +533,12 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     }
   }
   if (first) { rc = jac(); if (rc != ICC_OK) return rc; rc = after_jacobian(true); if (rc != ICC_OK) return rc; rc = read_scalars(); if (rc != ICC_OK) return rc; x_cost = sc[SC_X_COST]; S.initial_cost = x_cost; }
+  if (P.col_pts >= 0 && S.successful_steps > 0) {   // both state buffers carry the accepted points again (runs without POINTS never copy them)
+    const StateBufs& a = h->st[h->cur]; StateBufs& b = h->st[1 - h->cur];
+    CU(cudaMemcpyAsync(b.pts.p, a.pts.p, a.pts.n * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(b.board.p, a.board.p, a.board.n * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(b.pjac.p, a.pjac.p, a.pjac.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
   CU(cudaStreamSynchronize(h->stream));
   S.final_cost = x_cost;
   auto span_s = [&](const std::vector<std::pair<int, int>>& v) { double tot = 0; for (auto& p : v) { float ms = 0; cudaEventElapsedTime(&ms, ev[p.first], ev[p.second]); tot += ms; } return tot * 1e-3; };
@@ -569,7 +598,17 @@ icc_status icc_set_camera(icc_handle* h, int model, const double* intr, int n, i
   h->model = model; h->n_intr = n; h->width = w; h->height = hgt; for (int i = 0; i < n; ++i) h->intr[i] = intr[i];
   return ICC_OK;
 }
-icc_status icc_set_board_points(icc_handle* h, int n, const double* xyzw) { if (!h || n <= 0 || !xyzw) return ICC_ERR_INVALID_ARGUMENT; h->points.assign(xyzw, xyzw + 4 * (size_t)n); return ICC_OK; }
+icc_status icc_set_board_points(icc_handle* h, int n, const double* xyzw) {
+  if (!h || n <= 0 || !xyzw) return ICC_ERR_INVALID_ARGUMENT;
+  const bool same_board = h->points.size() == 4 * (size_t)n;
+  if (h->initialised && h->device >= 0 && same_board) { icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; }
+  h->points.assign(xyzw, xyzw + 4 * (size_t)n);
+  if (h->initialised && h->device >= 0) {      // an assembled problem keeps its corners: only the coordinates may change
+    if (!same_board) return fail(h, ICC_ERR_STATE, "the number of board points cannot change after batch_init_spline");
+    for (int k = 0; k < 2; ++k) { icc_status s = upload_points(h, k, false); if (s != ICC_OK) return s; }
+  }
+  return ICC_OK;
+}
 icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t* off, const int32_t* ids, const double* uv, const double* q, const double* p) {
   if (!h || nf <= 0 || !t || !off || !ids || !uv || !q || !p) return ICC_ERR_INVALID_ARGUMENT;
   const int nc = off[nf];
@@ -876,12 +915,12 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
   h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + (96 + 40) * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
-                 + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 32 * (h->points.size() / 4 + 8), true);
+                 + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 3 * (32 * (h->points.size() / 4 + 8) + 256), true);
   {
     std::vector<double4> board(h->points.size() / 4);
     // hnormalized(T^-1 X_h) of the functor (residuals.h:357-362) == T^-1 (X / w): the division is done once here
     for (size_t i = 0; i < board.size(); ++i) { const double iw = 1.0 / h->points[4 * i + 3]; board[i] = make_double4(h->points[4 * i] * iw, h->points[4 * i + 1] * iw, h->points[4 * i + 2] * iw, 1.0); }
-    CU(upload_staged(h, h->d_board, board)); P.board = h->d_board.p;
+    CU(upload_staged(h, h->d_board, board)); P.board = h->d_board.p;   // (the evaluation kernels read the copy that belongs to the state: DeviceState::board)
     std::vector<int> off, s1, s2; std::vector<double> u1, u2;
     for (const auto& f : h->frames) { off.push_back(f.c0); s1.push_back(f.s_so3); s2.push_back(f.s_r3); u1.push_back(f.u_so3); u2.push_back(f.u_r3); }
     off.push_back(P.n_corners);
@@ -1292,6 +1331,7 @@ icc_status icc_filter_bad_poses(icc_handle* h, int nv, const double* p_wc, int32
 
 icc_status icc_get_board_points(const icc_handle* h, double* xyzw, int n) {
   if (!h || !xyzw || n < 0) return ICC_ERR_INVALID_ARGUMENT;
+  { icc_status s = sync_state_to_host(const_cast<icc_handle*>(h)); if (s != ICC_OK) return s; }   // POINTS: the optimised points live in the device state
   const size_t m = std::min<size_t>(4 * (size_t)n, h->points.size());
   std::copy(h->points.begin(), h->points.begin() + m, xyzw);
   return ICC_OK;

@@ -523,7 +523,9 @@ int grid_for(int n_items, int sm_count) { const int ctas = (n_items + WARPS - 1)
 
 }  // namespace
 
-int launch_eval(const DeviceProblem& P, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st_main, const EvalAux* aux) {
+int launch_eval(const DeviceProblem& P_in, const DeviceState& S, bool with_jacobian, double* cost_out, double* residuals_out, double* reproj_out, cudaStream_t st_main, const EvalAux* aux) {
+  DeviceProblem P = P_in;
+  if (S.board) P.board = S.board;   // the board points belong to the state (parameter blocks under SplineOptimFlags::POINTS)
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
   const size_t sm_vis = WARPS * sizeof(WarpCtx) + WARPS * 48 * LDJ * sizeof(double);

@@ -19,6 +19,9 @@ struct DeviceState {
   double4* ba;
   double4* bg;
   double* glob;   // G_COUNT doubles
+  // board points of this state: homogeneous 4-vectors (parameter blocks under SplineOptimFlags::POINTS), their de-homogenised copy the
+  // evaluation kernels read, and the 4 x 3 local Jacobians of ceres::HomogeneousVectorParameterization (icc_points.cu)
+  double4* pts; double4* board; double* pjac;
 };
 
 struct VisionWork { int frame, c_begin, c_end, pad; };
@@ -61,7 +64,8 @@ struct DeviceProblem {
   int n_so3, n_r3, n_ba, n_bg;
   // active-set column maps (solver ordering); -1 = constant block
   const int* so3_col; const int* r3_col; const int* ba_col; const int* bg_col;
-  int col_tic, col_g, col_ld, col_ai, col_gi, col_ci, col_to;
+  int col_tic, col_g, col_ld, col_ai, col_gi, col_ci, col_to, col_pts;   // col_pts: first of the 3 n_points board-point columns (POINTS)
+  int n_points;
   int bias_active;           // any bias block active -> wide IMU tiles
   int intr_active;           // IMU intrinsics and/or time offset free -> widest IMU tiles
   int cam_intr_active;       // camera intrinsics free (extension) -> widest vision tiles
@@ -102,6 +106,10 @@ void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceS
 // knot initialisation from the per-view pose priors (icc_init.cu): q_wc / p_wc / t_vis in view-time order, T_c_i = T_i_c^-1 (x,y,z,w,tx,ty,tz)
 void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns,
                        double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st);
+// board points as parameters (icc_points.cu)
+void launch_points_prepare(int n, const double4* pts, double4* board, double* jac, cudaStream_t st);
+void launch_points_update(int n, int col_pts, const double4* cur, double4* cand, double4* board, double* jac, const double* delta, double* scal, cudaStream_t st);
+void launch_points_jac(const DeviceProblem& P, const DeviceState& S, const double* pjac, int col_pts, int sm_count, cudaStream_t st);
 // trajectory getters
 void launch_eval_trajectory(const DeviceProblem& P, const DeviceState& S, int n, const int64_t* t_ns, int64_t start_ns, double* gyro, double* accel,
                             double* bg, double* ba, double* pose_q, double* pose_p, int* valid, cudaStream_t st);

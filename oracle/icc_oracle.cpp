@@ -42,7 +42,7 @@ constexpr int BIAS_N = 3;     // basalt_spline/ceres_calib_split_residuals.h:21
 constexpr double S_TO_NS = 1e9, NS_TO_S = 1e-9;
 
 enum BlockType { BLK_RS_VISION = 0, BLK_ACCEL = 1, BLK_GYRO = 2 };
-enum LocalParam { LP_NONE = 0, LP_SO3 = 1, LP_SE3 = 2 };
+enum LocalParam { LP_NONE = 0, LP_SO3 = 1, LP_SE3 = 2, LP_HOMOG4 = 3 };   // LP_HOMOG4: ceres::HomogeneousVectorParameterization(4) of a board point (impl.h:148-150)
 
 struct ParamRef { const double* ptr; int size; int lp; int tan_off; };  // tan_off < 0 => constant block
 
@@ -90,7 +90,7 @@ struct Oracle {
   // active set / ordering (rebuilt per flags)
   int cur_flags = -1;
   int n_tan = 0;
-  int off_so3 = -1, off_r3 = -1, off_tic = -1, off_g = -1, off_ld = -1, off_ba = -1, off_bg = -1, off_ai = -1, off_gi = -1, off_ci = -1, off_to = -1;  // canonical offsets
+  int off_so3 = -1, off_r3 = -1, off_tic = -1, off_g = -1, off_ld = -1, off_ba = -1, off_bg = -1, off_ai = -1, off_gi = -1, off_ci = -1, off_to = -1, off_pts = -1;  // canonical offsets
   // solver ordering: canonical tangent index -> solver index
   std::vector<int> perm;      // canonical -> solver
   int n_knot_dims = 0, n_border = 0, kd = 0;
@@ -231,6 +231,35 @@ void lp_jacobian_se3(const double* T7, double J[7][6]) {
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[4 + i][j] = R.m[i][j];
 }
 
+// ceres::HomogeneousVectorParameterization(4) (Ceres 2.1 local_parameterization.cc; not in /root/reference -- restated):
+// Householder vector v, beta with (I - beta v v^T) x = |x| e_4 (internal::ComputeHouseholderVector); Jacobian = |x| / 2 x the first
+// three columns of H; Plus(x, d) = |x| H [sin(|d|/2) d / |d| ; cos(|d|/2)]  (Hartley & Zisserman A6.9.2-3).
+void householder4(const double* x, double v[4], double& beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; v[3] = 1.0; beta = 0.0;
+  const double xp = x[3];
+  if (sigma <= 2.220446049250313e-16) { if (xp < 0.0) beta = 2.0; return; }
+  const double mu = std::sqrt(xp * xp + sigma);
+  const double vp = xp <= 0.0 ? xp - mu : -sigma / (xp + mu);
+  beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp; v[1] /= vp; v[2] /= vp;
+}
+void lp_jacobian_homog4(const double* x, double J[4][3]) {
+  double v[4], beta; householder4(x, v, beta);
+  const double n = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  for (int i = 0; i < 3; ++i) for (int k = 0; k < 4; ++k) J[k][i] = n * (-0.5 * beta * v[i] * v[k] + (k == i ? 0.5 : 0.0));
+}
+void plus_homog4(double* x, const double* d) {
+  const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (nd == 0.0) return;
+  const double h = 0.5 * nd, sbd = std::sin(h) / h;
+  const double y[4] = {0.5 * sbd * d[0], 0.5 * sbd * d[1], 0.5 * sbd * d[2], std::cos(h)};
+  double v[4], beta; householder4(x, v, beta);
+  const double n = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  const double vy = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + v[3] * y[3];
+  for (int k = 0; k < 4; ++k) x[k] = n * (y[k] - v[k] * (beta * vy));
+}
+
 struct Scratch {
   std::vector<Jet<4>> jets; std::vector<const Jet<4>*> jptr; std::vector<Jet<4>> jres;
   std::vector<const double*> dptr; std::vector<double> res; std::vector<double> Jamb, Jtan; std::vector<int> cols;
@@ -269,13 +298,18 @@ void eval_block(const Oracle& o, const Block& b, Scratch& s, bool want_jac, int&
   }
   // ambient -> tangent through the local parameterisations
   int ncols = 0;
-  for (const auto& p : b.params) if (p.tan_off >= 0) ncols += (p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.size);
+  for (const auto& p : b.params) if (p.tan_off >= 0) ncols += (p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.lp == LP_HOMOG4 ? 3 : p.size);
   s.Jtan.assign(size_t(b.n_res) * std::max(ncols, 1), 0.0); s.cols.resize(ncols);
   int a = 0, c = 0;
   for (const auto& p : b.params) {
     if (p.tan_off < 0) continue;
     if (p.lp == LP_SO3) {
       double L[4][3]; lp_jacobian_so3(p.ptr, L);
+      for (int r = 0; r < b.n_res; ++r) for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 4; ++k) v += s.Jamb[size_t(r) * A + a + k] * L[k][j]; s.Jtan[size_t(r) * ncols + c + j] = v; }
+      for (int j = 0; j < 3; ++j) s.cols[c + j] = p.tan_off + j;
+      a += 4; c += 3;
+    } else if (p.lp == LP_HOMOG4) {
+      double L[4][3]; lp_jacobian_homog4(p.ptr, L);
       for (int r = 0; r < b.n_res; ++r) for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 4; ++k) v += s.Jamb[size_t(r) * A + a + k] * L[k][j]; s.Jtan[size_t(r) * ncols + c + j] = v; }
       for (int j = 0; j < 3; ++j) s.cols[c + j] = p.tan_off + j;
       a += 4; c += 3;
@@ -297,7 +331,7 @@ void eval_block(const Oracle& o, const Block& b, Scratch& s, bool want_jac, int&
 // Active set (SetFixedParams, impl.h:92-252) and solver ordering.
 // -------------------------------------------------------------------------------------------------------------
 bool configure(Oracle& o, int flags) {
-  if (flags & (ICC_FLAG_POINTS)) { o.err = "POINTS flag is not supported (never set by the hot CLI)"; return false; }
+  const bool pts = flags & ICC_FLAG_POINTS;     // board points as parameter blocks with HomogeneousVectorParameterization(4) (impl.h:136-152)
   const int nso3 = nknots(o.so3, 4), nr3 = nknots(o.r3, 3), nba = nknots(o.ba, 3), nbg = nknots(o.bg, 3);
   const bool spline = flags & ICC_FLAG_SPLINE, tic = flags & ICC_FLAG_T_I_C, grav = flags & ICC_FLAG_GRAVITY_DIR;
   // line delay block: only touched by SetFixedParams when != 0; a zero line delay means the GS path (no such block)
@@ -317,6 +351,8 @@ bool configure(Oracle& o, int flags) {
   const int off_gi = imu_intr ? n : -1; if (imu_intr) n += 9;
   const int off_ci = cam_intr ? n : -1; if (cam_intr) n += o.n_intr;
   const int off_to = toff ? n : -1; if (toff) n += 1;
+  const int n_points = int(o.points.size() / 4);
+  o.off_pts = pts ? n : -1; if (pts) n += 3 * n_points;
   o.off_ai = off_ai; o.off_gi = off_gi; o.off_ci = off_ci; o.off_to = off_to;
   o.n_tan = n; o.cur_flags = flags;
   // wire tangent offsets into the blocks
@@ -330,7 +366,10 @@ bool configure(Oracle& o, int flags) {
       b.params[k++].tan_off = o.off_tic;
       b.params[k++].tan_off = o.off_ld;
       b.params[k++].tan_off = off_ci;
-      for (; k < int(b.params.size()); ++k) b.params[k].tan_off = -1;
+      for (; k < int(b.params.size()); ++k) {      // the view's board points (only the points a view sees enter the problem: tracks_in_problem_)
+        const int id = int((b.params[k].ptr - o.points.data()) / 4);
+        b.params[k].tan_off = pts ? o.off_pts + 3 * id : -1; b.params[k].lp = pts ? LP_HOMOG4 : LP_NONE;
+      }
     } else if (b.type == BLK_ACCEL) {
       const int64_t s_so3 = (b.params[0].ptr - o.so3.data()) / 4, s_r3 = (b.params[SPLINE_N].ptr - o.r3.data()) / 3;
       const int64_t s_b = (b.params[2 * SPLINE_N].ptr - o.ba.data()) / 3;
@@ -610,10 +649,11 @@ bool arrowhead_solve(Normal A, const std::vector<double>& D2, const std::vector<
 // -------------------------------------------------------------------------------------------------------------
 // State vector plumbing: Plus(), norms, snapshots.
 // -------------------------------------------------------------------------------------------------------------
-struct State { std::vector<double> so3, r3, ba, bg; double T_ic[7], grav[3], ld, acc_intr[6], gyr_intr[9], intr[10], toff; };
-void save_state(const Oracle& o, State& s) { s.so3 = o.so3; s.r3 = o.r3; s.ba = o.ba; s.bg = o.bg; memcpy(s.T_ic, o.T_ic, sizeof s.T_ic); memcpy(s.grav, o.grav, sizeof s.grav); s.ld = o.line_delay; memcpy(s.acc_intr, o.acc_intr, sizeof s.acc_intr); memcpy(s.gyr_intr, o.gyr_intr, sizeof s.gyr_intr); memcpy(s.intr, o.intr, sizeof s.intr); s.toff = o.toff_delta; }
+struct State { std::vector<double> so3, r3, ba, bg, points; double T_ic[7], grav[3], ld, acc_intr[6], gyr_intr[9], intr[10], toff; };
+void save_state(const Oracle& o, State& s) { s.points = o.points; s.so3 = o.so3; s.r3 = o.r3; s.ba = o.ba; s.bg = o.bg; memcpy(s.T_ic, o.T_ic, sizeof s.T_ic); memcpy(s.grav, o.grav, sizeof s.grav); s.ld = o.line_delay; memcpy(s.acc_intr, o.acc_intr, sizeof s.acc_intr); memcpy(s.gyr_intr, o.gyr_intr, sizeof s.gyr_intr); memcpy(s.intr, o.intr, sizeof s.intr); s.toff = o.toff_delta; }
 void load_state(Oracle& o, const State& s) {
   // copy element-wise: residual blocks hold raw pointers into these vectors
+  std::copy(s.points.begin(), s.points.end(), o.points.begin());
   std::copy(s.so3.begin(), s.so3.end(), o.so3.begin()); std::copy(s.r3.begin(), s.r3.end(), o.r3.begin());
   std::copy(s.ba.begin(), s.ba.end(), o.ba.begin()); std::copy(s.bg.begin(), s.bg.end(), o.bg.begin());
   memcpy(o.T_ic, s.T_ic, sizeof s.T_ic); memcpy(o.grav, s.grav, sizeof s.grav); o.line_delay = s.ld; memcpy(o.acc_intr, s.acc_intr, sizeof s.acc_intr); memcpy(o.gyr_intr, s.gyr_intr, sizeof s.gyr_intr);
@@ -650,6 +690,11 @@ void apply_plus(Oracle& o, const std::vector<double>& d, double& step_sq, double
   if (o.off_bg >= 0) for (size_t i = 0; i < o.bg.size(); ++i) { const double nv = clampv(o.bg[i] + d[o.off_bg + i], o.max_bg); acc(o.bg[i], nv); o.bg[i] = nv; }
   if (o.off_ci >= 0) for (int i = 0; i < o.n_intr; ++i) { const double nv = o.intr[i] + d[o.off_ci + i]; acc(o.intr[i], nv); o.intr[i] = nv; }
   if (o.off_to >= 0) { const double nv = o.toff_delta + d[o.off_to]; acc(o.toff_delta, nv); o.toff_delta = nv; }
+  if (o.off_pts >= 0) for (size_t i = 0; i < o.points.size() / 4; ++i) {
+    double nx[4] = {o.points[4 * i], o.points[4 * i + 1], o.points[4 * i + 2], o.points[4 * i + 3]};
+    plus_homog4(nx, &d[o.off_pts + 3 * i]);
+    for (int k = 0; k < 4; ++k) { acc(o.points[4 * i + k], nx[k]); o.points[4 * i + k] = nx[k]; }
+  }
   if (flags & ICC_FLAG_IMU_INTRINSICS) {
     int off = o.off_ai;
     for (int i = 0; i < 6; ++i) { const double nv = o.acc_intr[i] + d[off + i]; acc(o.acc_intr[i], nv); o.acc_intr[i] = nv; }
@@ -702,7 +747,7 @@ void build_inner_plan(Oracle& o) {
       auto it = by_off.find(p.tan_off);
       if (it == by_off.end()) {
         it = by_off.emplace(p.tan_off, int(P.blocks.size())).first;
-        P.blocks.push_back({const_cast<double*>(p.ptr), p.size, p.lp, p.tan_off, p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.size, {}});
+        P.blocks.push_back({const_cast<double*>(p.ptr), p.size, p.lp, p.tan_off, p.lp == LP_SO3 ? 3 : p.lp == LP_SE3 ? 6 : p.lp == LP_HOMOG4 ? 3 : p.size, {}});
       }
       P.blocks[it->second].res_blocks.push_back(int(bi));
     }
@@ -737,6 +782,8 @@ void plus_block(const Oracle& o, const InnerBlock& B, const double* d) {
   if (B.lp == LP_SO3) {
     Q4<double> r = so3_mul(Q4<double>{B.ptr[0], B.ptr[1], B.ptr[2], B.ptr[3]}, so3_exp(V3<double>{d[0], d[1], d[2]}));
     B.ptr[0] = r.x; B.ptr[1] = r.y; B.ptr[2] = r.z; B.ptr[3] = r.w;
+  } else if (B.lp == LP_HOMOG4) {
+    plus_homog4(B.ptr, d);
   } else if (B.lp == LP_SE3) {
     SE3T<double> T{{B.ptr[0], B.ptr[1], B.ptr[2], B.ptr[3]}, {B.ptr[4], B.ptr[5], B.ptr[6]}};
     SE3T<double> r = se3_mul(T, se3_exp(d));

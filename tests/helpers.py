@@ -31,6 +31,23 @@ def qmat(q):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
+def plus_homog4(x, d):
+    """ceres::HomogeneousVectorParameterization(4)::Plus (Hartley & Zisserman A6.9.2-3), NumPy statement."""
+    x = np.asarray(x, dtype=np.float64); d = np.asarray(d, dtype=np.float64)
+    nd = np.linalg.norm(d)
+    if nd == 0.0:
+        return x.copy()
+    y = np.concatenate([0.5 * np.sin(0.5 * nd) / (0.5 * nd) * d, [np.cos(0.5 * nd)]])
+    sigma = float(x[:3] @ x[:3]); v = np.array([*x[:3], 1.0]); beta = 0.0
+    if sigma <= np.finfo(float).eps:
+        beta = 2.0 if x[3] < 0 else 0.0
+    else:
+        mu = np.sqrt(x[3] ** 2 + sigma)
+        vp = x[3] - mu if x[3] <= 0 else -sigma / (x[3] + mu)
+        beta = 2.0 * vp * vp / (sigma + vp * vp); v[:3] /= vp
+    return np.linalg.norm(x) * (y - v * (beta * (v @ y)))
+
+
 class TangentWalker:
     """Applies a canonical-order tangent vector to a solver through its public setters (first order for T_i_c): used for
     finite-difference checks of gradients on either implementation."""
@@ -39,6 +56,7 @@ class TangentWalker:
         self.api, self.flags = api, flags
         self.so3, self.r3, self.ba, self.bg = api.get_knots()
         self.T, self.ld, self.g = api.get_T_i_c(), api.get_line_delay(), api.get_gravity()
+        self.pts = api.get_board_points() if flags & capi.FLAG_POINTS else None
         self.n = api.num_tangent(flags)
 
     def apply(self, d):
@@ -60,6 +78,9 @@ class TangentWalker:
             ba = self.ba + d[off: off + ba.size].reshape(-1, 3); off += ba.size
         if f & (capi.FLAG_IMU_BIASES | capi.FLAG_GYR_BIAS):
             bg = self.bg + d[off: off + bg.size].reshape(-1, 3); off += bg.size
+        if f & capi.FLAG_POINTS:           # board points: last canonical block, HomogeneousVectorParameterization(4)
+            pts = np.array([plus_homog4(x, d[off + 3 * i: off + 3 * i + 3]) for i, x in enumerate(self.pts)]); off += 3 * len(self.pts)
+            self.api.set_board_points(pts)
         assert off == self.n
         self.api.set_knots(so3, r3, ba, bg); self.api.set_T_i_c(T); self.api.set_line_delay(ld); self.api.set_known_gravity_dir(g)
 

@@ -75,10 +75,11 @@ def test_host_assembly_matches_oracle(oracle_factory, cfg):
         assert np.array_equal(a, b)
     assert np.allclose(o.get_gravity(), h.get_gravity(), rtol=0, atol=1e-14)
     assert np.allclose(o.get_T_i_c(), h.get_T_i_c(), rtol=0, atol=1e-15)
-    for flags in (66, 66 | 16 | 32 | 4, 32, 66 | 8, 8):
+    for flags in (66, 66 | 16 | 32 | 4, 32, 66 | 8, 8, 66 | 1, 1):      # | 1 = POINTS: three tangent columns per board point
         assert o.num_tangent(flags) == h.num_tangent(flags)
+    assert h.num_tangent(66 | 1) == h.num_tangent(66) + 3 * len(ds["board_xyzw"])
     with pytest.raises(capi.IccError, match="UNSUPPORTED"):
-        h.num_tangent(66 | 1)          # POINTS
+        h.num_tangent(66 | 1 | capi.FLAG_CAM_INTRINSICS)   # POINTS with this library's camera-intrinsics extension
 
 
 def test_shards_partition_the_residuals(oracle_factory):

@@ -3,7 +3,7 @@ finite differences of its own cost, for every parameter block type and every cam
 import numpy as np
 import pytest
 
-from helpers import F_ALL, TangentWalker
+from helpers import F_STAGE1, F_ALL, TangentWalker
 from openimucameracalibrator_b200 import _capi as capi
 from openimucameracalibrator_b200 import synthetic as syn
 
@@ -41,3 +41,26 @@ def test_gradient_line_delay_only(oracle_factory):
     eps = 1e-9
     fd = (w.cost(np.array([eps])) - w.cost(np.array([-eps]))) / (2 * eps)
     assert abs(fd - g[0]) <= 1e-6 * abs(fd)
+
+
+def test_gradient_with_board_points_as_parameters(oracle_factory):
+    """SplineOptimFlags::POINTS (impl.h:136-152): board points become 4-vector blocks with ceres::HomogeneousVectorParameterization(4);
+    the oracle's Jet Jacobian x Householder local Jacobian against central differences through the NumPy Plus."""
+    ds = syn.make_dataset(syn.tiny_config(n_frames=10))
+    o = oracle_factory(); capi.load_dataset(o, ds)
+    flags = F_STAGE1 | capi.FLAG_POINTS
+    n = o.num_tangent(flags)
+    assert n == o.num_tangent(F_STAGE1) + 3 * len(ds["board_xyzw"])
+    _, _, g, _ = o.evaluate(flags)
+    w = TangentWalker(o, flags)
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        d = np.zeros(n)
+        if trial < 3:
+            d[n - 3 * len(ds["board_xyzw"]):] = rng.normal(size=3 * len(ds["board_xyzw"]))     # point directions only
+        else:
+            d = rng.normal(size=n)
+        eps = 1e-7
+        fd = (w.cost(eps * d) - w.cost(-eps * d)) / (2 * eps)
+        assert abs(fd - g @ d) <= 2e-5 * max(abs(fd), abs(g @ d)), (trial, fd, g @ d)
+    w.restore()

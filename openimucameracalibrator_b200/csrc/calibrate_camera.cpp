@@ -76,7 +76,8 @@ int main(int argc, char** argv) {
       // io::write_camera_calibration (src/io/write_camera_calibration.cc:33-133)
       Value j = Value::object(), in = Value::object();
       j["stabelized"] = Value(false); j["fps"] = Value(fps); j["nr_calib_images"] = Value((int64_t)S.n_views_used); j["final_reproj_error"] = Value(S.final_reproj_error);
-      j["image_width"] = Value((int64_t)width); j["image_height"] = Value((int64_t)height);   // integers, like io::write_camera_calibration j["intrinsic_type"] = Value(model_name);
+      j["image_width"] = Value((int64_t)width); j["image_height"] = Value((int64_t)height);   // integers, like io::write_camera_calibration
+      j["intrinsic_type"] = Value(model_name);
       in["skew"] = Value(0.0); in["principal_pt_x"] = Value(cx); in["principal_pt_y"] = Value(cy); in["aspect_ratio"] = Value(intr[1]); in["focal_length"] = Value(intr[0]);
       switch (model) {
         case ICC_CAM_DIVISION_UNDISTORTION: in["div_undist_distortion"] = Value(intr[4]); break;

@@ -28,7 +28,7 @@ typedef enum {
   ICC_ERR_NO_DEVICE = 2,       /* CUDA device / driver unusable: the product path never falls back to the CPU */
   ICC_ERR_CUDA = 3,
   ICC_ERR_STATE = 4,           /* call order violated (e.g. optimize before batch_init_spline) */
-  ICC_ERR_UNSUPPORTED = 5,     /* POINTS flag (board points as parameters; never set by the hot CLI) */
+  ICC_ERR_UNSUPPORTED = 5,     /* outside the solver's limits (e.g. POINTS with more than ~133 board points: border too wide), never a silent fallback */
   ICC_ERR_NUMERIC = 6          /* factorisation broke down / non-finite cost */
 } icc_status;
 
@@ -53,7 +53,8 @@ typedef enum {
 
 /* OpenICC::core::SplineOptimFlags (core/spline_trajectory_estimator.h:17-27), same numeric values. */
 enum {
-  ICC_FLAG_POINTS = 1 << 0,
+  ICC_FLAG_POINTS = 1 << 0,           /* board points as parameter blocks, HomogeneousVectorParameterization(4) (impl.h:136-152): 3 tangent columns per point,
+                                         last in the canonical order; read the result with icc_get_board_points */
   ICC_FLAG_T_I_C = 1 << 1,
   ICC_FLAG_IMU_BIASES = 1 << 2,
   ICC_FLAG_IMU_INTRINSICS = 1 << 3,
@@ -130,7 +131,8 @@ icc_status icc_set_solver_options(icc_handle* h, const icc_solver_options* o);
 /* ---- problem data (what main() hands to ImuCameraCalibrator, continuous_time_imu_to_camera_calibration.cc:104-199) */
 /* theia::Camera intrinsics read at ceres_calib_split_residuals.h:333-336 */
 icc_status icc_set_camera(icc_handle* h, int model, const double* intrinsics, int n_intrinsics, int image_width, int image_height);
-/* theia::Track::Point() homogeneous board points, id = index (app :111-119) */
+/* theia::Track::Point() homogeneous board points, id = index (app :111-119).  After icc_batch_init_spline only the coordinates may change
+ * (same count); the new points reach the device state at once. */
 icc_status icc_set_board_points(icc_handle* h, int n_points, const double* xyzw);
 /* Views of the calibration dataset (app :131-161): timestamp [s], observed corners (CSR over frames), and the per-view
  * pose prior used by BatchInitSO3R3VisPoses: q_wc (x,y,z,w) = R_cw^T and camera position p_wc (impl.h:290-300). */
@@ -238,7 +240,8 @@ icc_status icc_optimize_board_points(icc_handle* h, int n_frames, const int32_t*
                                      double max_reproj_error, int min_points, int min_observations,
                                      double* q_wc_xyzw, double* p_wc, double* mean_reproj_error /* nullable */, int32_t* valid,
                                      double* board_xyzw_out /* nullable, 4 per board point */, int32_t* n_points_optimized /* nullable */);
-/* current board points of the handle (icc_set_board_points, or refined by icc_optimize_board_points / icc_calibrate_camera) */
+/* current board points of the handle (icc_set_board_points, or refined by icc_optimize_board_points / icc_calibrate_camera / a spline
+ * solve with ICC_FLAG_POINTS) */
 icc_status icc_get_board_points(const icc_handle* h, double* xyzw, int n);
 /* theia::Camera::PixelToNormalizedCoordinates / z for `n` pixels with the handle's camera: xy_out[2n], ok[n] (nullable). */
 icc_status icc_pixels_to_normalized(icc_handle* h, int n, const double* uv, double* xy_out, int32_t* ok);

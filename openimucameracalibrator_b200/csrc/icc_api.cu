@@ -135,7 +135,9 @@ struct icc_handle {
   int model = -1, n_intr = 0, width = 0, height = 0; double intr[10] = {0};
   std::vector<double> points;
   std::vector<double> frame_t; std::vector<int> corner_off; HostBuf<int> point_ids; HostBuf<double> uv; std::vector<double> q_wc, p_wc;
-  std::vector<double> imu_t; HostBuf<double> imu_acc, imu_gyr;
+  HostBuf<double> imu_t, imu_acc, imu_gyr;
+  int id_lo = 0, id_hi = -1;                 // range of the corner point ids (found while set_frames copies them)
+  bool imu_sorted = false;                   // imu_t is non-decreasing (found while set_imu copies it)
   int shard_rank = 0, shard_world = 1;
   icc_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
   icc_comm* comm = nullptr;                  // borrowed NCCL communicator (icc_set_comm): the native cross-rank sum
@@ -151,6 +153,8 @@ struct icc_handle {
   bool used_contig = false; int used_c0 = 0, used_n = 0;    // ... otherwise corners [used_c0, used_c0 + used_n) of uv / point_ids are used in place
   bool imu_contig = false; int imu_src0 = 0;                // same for the accelerometer / gyroscope samples
   std::vector<double> imu_used_t, imu_used_acc, imu_used_gyr; HostBuf<int64_t> imu_used_st;
+  size_t n_imu_used = 0;                     // kept samples; imu_used_t / imu_used_st are only materialised off the sorted fast path (imu_lazy == false)
+  bool imu_lazy = false;                     // sorted fast path: kept samples = imu_t[imu_src0 .. +n_imu_used) + time offset, relative times derived on the device
   std::vector<ImuCell> cells;
   int dropped_frames = 0, dropped_imu = 0;
   // ---- device ---------------------------------------------------------------------------------------------------
@@ -163,12 +167,13 @@ struct icc_handle {
   DevBuf<double> d_view_t, d_view_q, d_view_p;   // per-view pose priors in time order (knot initialisation kernel)
   DevBuf<VisFrame> d_vframes; DevBuf<VisItem> d_vitems;
   DevBuf<ImuCellP> d_icells; DevBuf<VisItem> d_iitems;
-  DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
+  DevBuf<double> d_imu_traw; DevBuf<VisionWork> d_vwork; DevBuf<int64_t> d_imu_t; DevBuf<double> d_imu_acc, d_imu_gyr; DevBuf<ImuCell> d_cells, d_iwork;
   DevBuf<int> d_so3_col, d_r3_col, d_ba_col, d_bg_col;
   DevBuf<double> d_ne, d_scale, d_ws, d_delta, d_scal, d_res;
   PinnedArena arena;        // staging of the small uploads of BatchInitSpline
   DeviceProblem P;
   bool state_dirty_host = false;   // device state newer than host mirror
+  bool glob_host_current = false;  // ... but the small block of globals (T_i_c, gravity, line delay, intrinsics) was already read back
   bool knots_dirty_host = false;   // only the spline knots are newer on the device (device-side initialisation): globals / biases on the host are current
   // ---- active set ------------------------------------------------------------------------------------------------
   int cur_flags = -1;
@@ -182,6 +187,17 @@ struct icc_handle {
 namespace {
 
 icc_status fail(icc_handle* h, icc_status s, const std::string& m) { if (h) h->err = m; return s; }
+// ICC_TRACE_PHASES=1: host wall clock between the marked points of a call, to stderr (diagnosis only; synchronises the stream at every mark)
+struct PhaseTrace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t;
+  PhaseTrace(cudaStream_t s) : on(getenv("ICC_TRACE_PHASES") != nullptr), st(s), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto a = std::chrono::steady_clock::now(); if (st) cudaStreamSynchronize(st); const auto b = std::chrono::steady_clock::now();
+    fprintf(stderr, "[icc phase] %-28s %8.3f ms host + %7.3f ms stream drain\n", what, std::chrono::duration<double, std::milli>(a - t).count(), std::chrono::duration<double, std::milli>(b - a).count());
+    t = std::chrono::steady_clock::now();
+  }
+};
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, ICC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 #define NEED_DEVICE() do { if (h->device < 0) return fail(h, ICC_ERR_NO_DEVICE, "no CUDA device bound to this handle (host-only handle): compute entry points are unavailable"); } while (0)
 
@@ -295,6 +311,15 @@ icc_status sync_state_to_host(icc_handle* h) {
   CU(cudaMemcpy(h->glob, s.glob.p, G_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
   if (h->state_dirty_host && s.pts.n * 4 == h->points.size()) CU(pull(s.pts, h->points, 4));
   h->state_dirty_host = false; h->knots_dirty_host = false;
+  return ICC_OK;
+}
+
+// getters of the globals (T_i_c, gravity, line delay, ...) after a solve: 25 doubles instead of every knot
+icc_status sync_globals_to_host(icc_handle* h) {
+  if (!h->state_dirty_host || h->glob_host_current || h->device < 0) return ICC_OK;
+  CU(cudaMemcpyAsync(h->glob, h->st[h->cur].glob.p, G_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->glob_host_current = true;
   return ICC_OK;
 }
 
@@ -441,8 +466,10 @@ icc_status mean_reproj(icc_handle* h, double* out) {
 icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergence, icc_summary* out) {
   using clk = std::chrono::steady_clock;
   const auto t_start = clk::now();
+  PhaseTrace trace(h->stream);
   icc_status rc = configure(h, flags);
   if (rc != ICC_OK) return rc;
+  trace.lap("run_lm: configure");
   icc_summary S; memset(&S, 0, sizeof S);
   const DeviceProblem& P = h->P;
   const int n = P.nk + P.nb;
@@ -498,6 +525,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     if (P.col_pts >= 0) launch_points_update(P.n_points, P.col_pts, h->st[h->cur].pts.p, h->st[cand].pts.p, h->st[cand].board.p, h->st[cand].pjac.p, h->d_delta.p, h->d_scal.p, h->stream);
     rc = eval_cost(h, h->st[cand].view(), h->d_scal.p + SC_CAND_COST, nullptr, nullptr); if (rc != ICC_OK) return rc;
     rc = read_scalars(); if (rc != ICC_OK) return rc;
+    trace.lap("run_lm: iteration");
     if (fresh_jacobian) {
       x_cost = sc[SC_X_COST];
       if (first) { S.initial_cost = x_cost; first = false; if (!std::isfinite(x_cost)) return fail(h, ICC_ERR_NUMERIC, "non-finite initial cost"); }
@@ -522,7 +550,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
     const double rel = cost_change / model_change;
     if (rel > h->opt.min_relative_decrease) {               // HandleSuccessfulStep
       ++S.successful_steps;
-      h->cur = cand; h->state_dirty_host = true;
+      h->cur = cand; h->state_dirty_host = true; h->glob_host_current = false;
       x_cost = cand_cost; ne_valid = false;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(h->opt.max_trust_region_radius, radius);
@@ -546,6 +574,7 @@ icc_status run_lm(icc_handle* h, int max_iters, int flags, bool check_convergenc
   for (auto e : ev) cudaEventDestroy(e);
   S.gpu_launches = kernel_launch_count() - launches0;
   S.seconds_total = std::chrono::duration<double>(clk::now() - t_start).count();
+  trace.lap("run_lm: epilogue");
   if (out) *out = S;
   return ICC_OK;
 }
@@ -615,7 +644,13 @@ icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t*
   for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
   if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);   // an asynchronous upload may still be reading the staging buffers
   const bool pin = h->device >= 0;
-  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->point_ids.assign(ids, (size_t)nc, pin); h->uv.assign(uv, 2 * (size_t)nc, pin);
+  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->uv.assign(uv, 2 * (size_t)nc, pin);
+  {   // the ids are copied and range-checked in one pass (the check of batch_init_spline would read them again, cold)
+    h->point_ids.resize((size_t)nc, pin);
+    int lo = 0, hi = -1; int* dst = h->point_ids.data();
+    for (int i = 0; i < nc; ++i) { const int v = ids[i]; dst[i] = v; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    h->id_lo = lo; h->id_hi = hi;
+  }
   h->q_wc.assign(q, q + 4 * (size_t)nf); h->p_wc.assign(p, p + 3 * (size_t)nf);
   return ICC_OK;
 }
@@ -623,7 +658,13 @@ icc_status icc_set_imu(icc_handle* h, int n, const double* t, const double* a, c
   if (!h || n < 0 || (n > 0 && (!t || !a || !g))) return ICC_ERR_INVALID_ARGUMENT;
   if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);
   const bool pin = h->device >= 0;
-  h->imu_t.assign(t, t + n); h->imu_acc.assign(a, 3 * (size_t)n, pin); h->imu_gyr.assign(g, 3 * (size_t)n, pin);
+  h->imu_acc.assign(a, 3 * (size_t)n, pin); h->imu_gyr.assign(g, 3 * (size_t)n, pin);
+  {   // time stamps: copied and tested for order in one pass (the sorted stream takes the bisection path of batch_init_spline)
+    h->imu_t.resize((size_t)n, pin);
+    double* dst = h->imu_t.data(); int unsorted = 0; double prev = n > 0 ? t[0] : 0.0;
+    for (int i = 0; i < n; ++i) { const double v = t[i]; dst[i] = v; unsorted |= !(v >= prev); prev = v; }
+    h->imu_sorted = !unsorted;
+  }
   return ICC_OK;
 }
 icc_status icc_set_shard(icc_handle* h, int rank, int world) { if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, ICC_ERR_INVALID_ARGUMENT, "bad shard"); h->shard_rank = rank; h->shard_world = world; return ICC_OK; }
@@ -638,11 +679,11 @@ icc_status icc_set_allreduce(icc_handle* h, icc_allreduce_fn fn, void* user) { i
 icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   if (!h || !ipp) return ICC_ERR_INVALID_ARGUMENT;
   if (h->model < 0 || h->frame_t.empty() || h->points.empty()) return fail(h, ICC_ERR_STATE, "camera, board points and frames must be set before batch_init_spline");
-  { int lo = 0, hi = -1; const int* ids = h->point_ids.data(); const size_t nid = h->point_ids.size();
-    for (size_t i = 0; i < nid; ++i) { lo = std::min(lo, ids[i]); hi = std::max(hi, ids[i]); }
-    if (lo < 0 || (size_t)(hi + 1) > h->points.size() / 4) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner references an unknown board point"); }
+  PhaseTrace trace(h->device >= 0 ? h->stream : nullptr);
+  if (h->id_lo < 0 || (size_t)(h->id_hi + 1) > h->points.size() / 4) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner references an unknown board point");
   h->ip = *ipp;
   const int nf = (int)h->frame_t.size();
+  trace.lap("batch_init: id range check");
   // T_i_c, IMU intrinsics, line delay (imu_camera_calibrator.cc:30-47)
   { const Q4 q = qn(ipp->T_i_c_init); h->glob[G_TIC + 0] = q.x; h->glob[G_TIC + 1] = q.y; h->glob[G_TIC + 2] = q.z; h->glob[G_TIC + 3] = q.w; for (int i = 4; i < 7; ++i) h->glob[G_TIC + i] = ipp->T_i_c_init[i]; }
   for (int i = 0; i < 6; ++i) h->glob[G_ACC_INTR + i] = ipp->acc_intrinsics[i];
@@ -704,6 +745,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   for (int i = 0; i < nba; ++i) for (int d = 0; d < 3; ++d) h->ba[3 * i + d] = ipp->acc_bias[d];
   for (int i = 0; i < nbg; ++i) for (int d = 0; d < 3; ++d) h->bg[3 * i + d] = ipp->gyr_bias[d];
 
+  trace.lap("batch_init: ranges, view order, bias knots");
   // ---- measurement wiring (imu_camera_calibrator.cc:87-120; Add*Measurement impl.h:341-613) ----------------------
   const bool pin = h->device >= 0;
   std::vector<FrameHost> all_frames(nf);
@@ -765,9 +807,52 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     if (direct) { h->imu_contig = k > 0 && contig; if (k == 0) h->imu_src0 = 0; h->imu_used_st.n = k; h->imu_used_t.resize(k); }
     return true;
   };
+  // Sorted stream (the usual case; known from set_imu): the kept samples [ka, kb) of imu_t are used in place, and the cells -- maximal runs of
+  // samples inside the same knot interval of all four splines -- are found by galloping + bisection for the next interval boundary
+  // (CalcTimes' st is monotone in t), so the host touches O(cells log run) time stamps instead of every sample.  The relative times
+  // st = int64((t + offset) 1e9) - start themselves are derived on the device from the uploaded stamps (imu_times_kernel), bit for bit.
+  auto cells_by_bisection = [&](size_t ka, size_t kb) {
+    const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s;
+    auto st_of = [&](size_t i) { return (int64_t)((imu_t[i] + toff) * S_TO_NS) - h->start_ns; };
+    h->cells.clear(); h->imu_used_t.clear(); h->imu_used_st.n = 0;
+    size_t k = ka;
+    while (k < kb) {
+      const int64_t st = st_of(k);
+      const int64_t a = st / h->dt_r3_ns, b = st / h->dt_so3_ns, c = st / h->dt_ba_ns, d = st / h->dt_bg_ns;
+      const int64_t edge = std::min(std::min((a + 1) * h->dt_r3_ns, (b + 1) * h->dt_so3_ns), std::min((c + 1) * h->dt_ba_ns, (d + 1) * h->dt_bg_ns));
+      size_t prev = k, probe = k + 1, step = 1;                     // first index in (k, kb) with st >= edge: gallop, then bisect
+      while (probe < kb && st_of(probe) < edge) { prev = probe; probe += step; step *= 2; }
+      size_t lo = prev + 1, hi = std::min(probe, kb);                // st_of(prev) < edge <= st_of(probe) (or probe is past the end)
+      while (lo < hi) { const size_t m = (lo + hi) / 2; if (st_of(m) < edge) lo = m + 1; else hi = m; }
+      h->cells.push_back({(int)b, (int)a, (int)c, (int)d, (int)(k - ka), (int)(lo - ka)});
+      k = lo;
+    }
+    h->imu_lazy = true; h->n_imu_used = kb - ka; h->imu_contig = kb > ka; h->imu_src0 = kb > ka ? (int)ka : 0;
+  };
+  auto imu_sorted_pass = [&]() -> bool {
+    if (h->shard_world != 1 || !h->imu_sorted || n_imu_in == 0) return false;
+    const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s, t0 = h->t0_s, tend = h->tend_s;
+    auto bisect = [&](size_t a, size_t b, auto pred) { while (a < b) { const size_t m = (a + b) / 2; if (pred(m)) a = m + 1; else b = m; } return a; };   // first index where pred is false
+    auto fits = [&](size_t i) {   // upper-side validity of CalcTimes for all four splines (monotone: true, then false)
+      const double t = imu_t[i] + toff;
+      if (t >= tend) return false;
+      const int64_t st = (int64_t)(t * S_TO_NS) - h->start_ns;
+      return size_t(st / h->dt_r3_ns + SPLINE_N) <= (size_t)nr3 && size_t(st / h->dt_so3_ns + SPLINE_N) <= (size_t)nso3 && size_t(st / h->dt_ba_ns + BIAS_N) <= (size_t)nba && size_t(st / h->dt_bg_ns + BIAS_N) <= (size_t)nbg;
+    };
+    const size_t ia = bisect(0, n_imu_in, [&](size_t i) { const double t = imu_t[i] + toff; return t < t0 || (int64_t)(t * S_TO_NS) - h->start_ns < 0; });
+    const size_t ib = bisect(ia, n_imu_in, fits);
+    if (ib <= ia) return false;                                     // nothing kept: the sequential pass reports it
+    const size_t in_window = bisect(ia, n_imu_in, [&](size_t i) { return imu_t[i] + toff < tend; }) - ia;
+    h->dropped_imu = (int)(in_window - (ib - ia));
+    cells_by_bisection(ia, ib);
+    return true;
+  };
   std::vector<int> frame_sel;
   // (a stream with holes inside the kept range -- samples dropped in the middle -- takes the general path, which gathers the readings)
-  const bool direct = h->shard_world == 1 && imu_pass(true) && h->imu_contig;
+  trace.lap("batch_init: frame times");
+  h->imu_lazy = false; h->n_imu_used = 0;
+  const bool direct = imu_sorted_pass() || (h->shard_world == 1 && imu_pass(true) && h->imu_contig);
+  trace.lap("batch_init: imu pass");
   if (direct) {
     for (int i = 0; i < nf; ++i) if (frame_ok[i]) frame_sel.push_back(i);
   } else if ([&]() -> bool {
@@ -777,7 +862,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     // break points found by bisection, and only the shard's own samples are then walked.  O(frames log samples + samples / world)
     // instead of O(samples) per rank; same decisions as the general path below (tests/test_capi_boundary.py, test_sharding_gloo.py).
     const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s, t0 = h->t0_s, tend = h->tend_s;
-    if (!increasing || !std::is_sorted(imu_t, imu_t + n_imu_in)) return false;
+    if (!increasing || !h->imu_sorted) return false;
     auto fits = [&](size_t i) {   // upper-side validity (monotone: true, then false)
       const double t = imu_t[i] + toff;
       if (t >= tend) return false;
@@ -814,18 +899,9 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     }
     take_imu(prev_p, ib);
     if (ka > kb) ka = kb = ia;
-    // the shard's own samples: segment tracking, cells, used-in-place readings
-    SegTrack tr_r3{h->dt_r3_ns}, tr_so3{h->dt_so3_ns}, tr_ba{h->dt_ba_ns}, tr_bg{h->dt_bg_ns};
-    const size_t K = kb - ka;
-    h->imu_used_t.resize(K); h->imu_used_st.n = K; h->cells.clear();
-    for (size_t k = 0; k < K; ++k) {
-      const double t = imu_t[ka + k] + toff; const int64_t st = (int64_t)(t * S_TO_NS) - h->start_ns;
-      const int a = (int)tr_r3.seg(st), b = (int)tr_so3.seg(st), c = (int)tr_ba.seg(st), d = (int)tr_bg.seg(st);
-      h->imu_used_t[k] = t; h->imu_used_st[k] = st;
-      if (h->cells.empty() || h->cells.back().s_so3 != b || h->cells.back().s_r3 != a || h->cells.back().s_ba != c || h->cells.back().s_bg != d) h->cells.push_back({b, a, c, d, (int)k, (int)k});
-      h->cells.back().i_end = (int)k + 1;
-    }
-    h->imu_contig = K > 0; h->imu_src0 = (int)ka;
+    // the shard's own samples: cells by bisection, readings used in place
+    cells_by_bisection(ka, kb);
+
     return true;
   }()) {
   } else {
@@ -885,6 +961,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     }
     h->used_n = (int)h->used_pid.size();
   }
+  trace.lap("batch_init: host assembly");
   // gravity initialisation (imu_camera_calibrator.cc:130-161) incl. the integer-second truncation of the accelerometer time
   auto view_of_time = [&](double t) { const size_t k = std::lower_bound(t_vis.begin(), t_vis.end(), t) - t_vis.begin(); return view_order[std::min(k, view_order.size() - 1)]; };
   bool ginit = false; double g0[3] = {0.0, 0.0, 9.81};   // GRAVITY_MAGN (spline_trajectory_estimator.h:29) when never initialised
@@ -904,7 +981,8 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   memset(&P, 0, sizeof P);
   P.model = h->model; P.dispatch_fov = ipp->dispatch_fov; P.n_intr = h->n_intr;
   P.n_frames = (int)h->frames.size(); P.n_corners = h->used_n; P.rolling = ipp->init_line_delay_s != 0.0 ? 1 : 0;
-  P.n_imu = (int)h->imu_used_t.size(); P.n_cells = (int)h->cells.size();
+  if (!h->imu_lazy) h->n_imu_used = h->imu_used_t.size();
+  P.n_imu = (int)h->n_imu_used; P.n_cells = (int)h->cells.size();
   P.dt_so3_ns = h->dt_so3_ns; P.dt_r3_ns = h->dt_r3_ns; P.dt_ba_ns = h->dt_ba_ns; P.dt_bg_ns = h->dt_bg_ns;
   P.inv_so3_dt = S_TO_NS / double(h->dt_so3_ns); P.inv_r3_dt = S_TO_NS / double(h->dt_r3_ns);
   P.w_acc = 1.0 / ipp->std_r3; P.w_gyr = 1.0 / ipp->std_so3;
@@ -914,8 +992,10 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   if (h->device < 0) return ICC_OK;
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
+  trace.lap("batch_init: gravity init");
   h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + (96 + 40) * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
                  + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 3 * (32 * (h->points.size() / 4 + 8) + 256), true);
+  trace.lap("batch_init: pinned arena");
   {
     std::vector<double4> board(h->points.size() / 4);
     // hnormalized(T^-1 X_h) of the functor (residuals.h:357-362) == T^-1 (X / w): the division is done once here
@@ -1005,8 +1085,12 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
       CU(upload_staged(h, h->d_icells, ic)); P.icells = h->d_icells.p; P.n_icells = nic;
       CU(upload_staged(h, h->d_iitems, ii)); P.iitems = h->d_iitems.p; P.n_iitems = n_iit;
     }
-    CU(h->d_imu_t.alloc(h->imu_used_st.size()));
-    if (!h->imu_used_st.empty()) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->imu_used_st.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h->d_imu_t.alloc(h->n_imu_used));
+    if (h->imu_lazy && h->n_imu_used) {   // sorted fast path: the raw stamps go up, the relative integer times are derived there
+      CU(h->d_imu_traw.alloc(h->n_imu_used));
+      CU(cudaMemcpyAsync(h->d_imu_traw.p, h->imu_t.data() + h->imu_src0, h->n_imu_used * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      launch_imu_times((int)h->n_imu_used, h->d_imu_traw.p, ipp->time_offset_imu_to_cam_s, h->start_ns, h->d_imu_t.p, h->stream);
+    } else if (h->n_imu_used) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->n_imu_used * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
     if (P.n_imu > 0) {
       const double* a_src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data();
@@ -1016,8 +1100,10 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     }
     P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
   }
+  trace.lap("batch_init: problem upload");
   icc_status s = upload_state(h, 0, true); if (s != ICC_OK) return s;
   s = upload_state(h, 1, true); if (s != ICC_OK) return s;
+  trace.lap("batch_init: state upload");
   {   // knots: BatchInitSO3R3VisPoses on the device, written into both state copies (the zero knots uploaded above only sized them)
     std::vector<double> tv, qv, pv;
     tv.reserve(view_order.size()); qv.reserve(4 * view_order.size()); pv.reserve(3 * view_order.size());
@@ -1028,6 +1114,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
                       h->st[0].so3.p, h->st[1].so3.p, h->st[0].r3.p, h->st[1].r3.p, h->stream);
     h->knots_dirty_host = true;     // the device holds the knots; the host mirror is refreshed on demand (getters / setters)
   }
+  trace.lap("batch_init: knot init");
   return ICC_OK;
 }
 
@@ -1051,7 +1138,9 @@ icc_status icc_optimize(icc_handle* h, int max_iterations, int flags, icc_summar
   icc_summary S;
   icc_status s = run_lm(h, max_iterations, flags, true, &S); if (s != ICC_OK) return s;
   const int l0 = kernel_launch_count();
+  PhaseTrace trace(h->stream);
   s = mean_reproj(h, &S.mean_reproj_error); if (s != ICC_OK) return s;
+  trace.lap("optimize: mean reprojection error");
   S.gpu_launches += kernel_launch_count() - l0;
   if (summary) *summary = S;
   return ICC_OK;
@@ -1064,11 +1153,11 @@ icc_status icc_lm_iterations(icc_handle* h, int n, int flags, icc_summary* summa
   return run_lm(h, n, flags, false, summary);
 }
 
-icc_status icc_get_T_i_c(const icc_handle* hc, double T[7]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !T) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(T, h->glob + G_TIC, 7 * sizeof(double)); return ICC_OK; }
-icc_status icc_get_gravity(const icc_handle* hc, double g[3]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !g) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; memcpy(g, h->glob + G_GRAV, 3 * sizeof(double)); return ICC_OK; }
-icc_status icc_get_line_delay(const icc_handle* hc, double* ld) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !ld) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; *ld = h->glob[G_LD]; return ICC_OK; }
-icc_status icc_get_camera_intrinsics(const icc_handle* hc, double* k, int n) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !k) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; for (int i = 0; i < n && i < h->n_intr; ++i) k[i] = h->initialised ? h->glob[G_CAM_INTR + i] : h->intr[i]; return ICC_OK; }
-icc_status icc_get_time_offset(const icc_handle* hc, double* t) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !t) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_state_to_host(h); if (s != ICC_OK) return s; *t = h->ip.time_offset_imu_to_cam_s + h->glob[G_TOFF]; return ICC_OK; }
+icc_status icc_get_T_i_c(const icc_handle* hc, double T[7]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !T) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_globals_to_host(h); if (s != ICC_OK) return s; memcpy(T, h->glob + G_TIC, 7 * sizeof(double)); return ICC_OK; }
+icc_status icc_get_gravity(const icc_handle* hc, double g[3]) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !g) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_globals_to_host(h); if (s != ICC_OK) return s; memcpy(g, h->glob + G_GRAV, 3 * sizeof(double)); return ICC_OK; }
+icc_status icc_get_line_delay(const icc_handle* hc, double* ld) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !ld) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_globals_to_host(h); if (s != ICC_OK) return s; *ld = h->glob[G_LD]; return ICC_OK; }
+icc_status icc_get_camera_intrinsics(const icc_handle* hc, double* k, int n) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !k) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_globals_to_host(h); if (s != ICC_OK) return s; for (int i = 0; i < n && i < h->n_intr; ++i) k[i] = h->initialised ? h->glob[G_CAM_INTR + i] : h->intr[i]; return ICC_OK; }
+icc_status icc_get_time_offset(const icc_handle* hc, double* t) { icc_handle* h = const_cast<icc_handle*>(hc); if (!h || !t) return ICC_ERR_INVALID_ARGUMENT; icc_status s = sync_globals_to_host(h); if (s != ICC_OK) return s; *t = h->ip.time_offset_imu_to_cam_s + h->glob[G_TOFF]; return ICC_OK; }
 icc_status icc_get_num_knots(const icc_handle* h, int* a, int* b, int* c, int* d) {
   if (!h) return ICC_ERR_INVALID_ARGUMENT;
   if (a) *a = (int)h->so3.size() / 4; if (b) *b = (int)h->r3.size() / 3; if (c) *c = (int)h->ba.size() / 3; if (d) *d = (int)h->bg.size() / 3;
@@ -1101,11 +1190,11 @@ icc_status icc_get_mean_reprojection_error(icc_handle* h, double* e) {
   CU(cudaSetDevice(h->device));
   return mean_reproj(h, e);
 }
-icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->imu_used_t.size(); return ICC_OK; }
+icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->n_imu_used; return ICC_OK; }
 icc_status icc_get_imu_used(const icc_handle* h, double* t, double* a, double* g) {
   if (!h) return ICC_ERR_INVALID_ARGUMENT;
-  if (t) std::copy(h->imu_used_t.begin(), h->imu_used_t.end(), t);
-  const size_t nu = h->imu_used_t.size();
+  const size_t nu = h->n_imu_used;
+  if (t) { if (h->imu_lazy) { for (size_t k = 0; k < nu; ++k) t[k] = h->imu_t[h->imu_src0 + k] + h->ip.time_offset_imu_to_cam_s; } else std::copy(h->imu_used_t.begin(), h->imu_used_t.end(), t); }
   if (a) { const double* src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data(); std::copy(src, src + 3 * nu, a); }
   if (g) { const double* src = h->imu_contig ? h->imu_gyr.data() + 3 * (size_t)h->imu_src0 : h->imu_used_gyr.data(); std::copy(src, src + 3 * nu, g); }
   return ICC_OK;

@@ -58,7 +58,20 @@ __global__ void init_knots_kernel(int nv, const double* __restrict__ t_vis, cons
   }
 }
 
+// CalcTimes' relative sample time of the IMU stream: st = int64((t + offset) * 1e9) - start, the host's expression bit for bit (one rounded add,
+// one rounded multiply -- nothing to contract --, truncation)
+__global__ void imu_times_kernel(int n, const double* __restrict__ t_raw, double offset_s, int64_t start_ns, int64_t* __restrict__ st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st[i] = (int64_t)__dmul_rn(__dadd_rn(t_raw[i], offset_s), 1e9) - start_ns;
+}
+
 }  // namespace
+
+void launch_imu_times(int n, const double* t_raw, double offset_s, int64_t start_ns, int64_t* st_out, cudaStream_t st) {
+  if (n <= 0) return;
+  imu_times_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, t_raw, offset_s, start_ns, st_out);
+  count_launch();
+}
 
 void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns,
                        double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st) {

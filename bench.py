@@ -53,15 +53,15 @@ def algorithmic_bytes(ds, n_frames, n_corners, n_imu, n_cells):
 
 class ClockSampler:
     """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the same fields as the nvidia-smi clocks line).
-    Read through NVML inside this process (nvidia_ml_py, one handle opened before the timed region, a thread sampling every 20 ms): a
-    freshly started `nvidia-smi -lms` stalls the driver of the GPU it queries for a few milliseconds per sample, which at N > 1 shows up as
-    a 5 ms step on every rank (the peers wait inside the all-reduce) -- measured at N = 8.  Falls back to the nvidia-smi subprocess when
-    NVML cannot be loaded."""
+    Read through NVML inside this process (nvidia_ml_py, one handle opened before the timed region), ONE sample per step taken by the
+    timing loop itself between two steps -- while the L2-flush fill of the next step keeps the GPU under load, outside the CUDA-event
+    bracket of either step.  Every out-of-band sampler perturbed the number it was meant to vouch for: a freshly started `nvidia-smi -lms`
+    stalls the driver for a few milliseconds per sample (at N = 8 a 5 ms step on every rank: the peers wait inside the all-reduce), an
+    NVML polling thread still cost one 0.5 ms step in twenty (N = 4).  Falls back to the nvidia-smi subprocess when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        import threading
         self.p, self.thread, self.samples, self.stop_flag, self.index = None, None, [], False, index
         try:
             import pynvml
@@ -70,7 +70,7 @@ class ClockSampler:
             phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
             self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._loop, daemon=True); self.thread.start()
+            self.thread = True          # NVML mode: sample() is called by the timing loop
         except Exception:
             self.thread = None
             try:
@@ -79,29 +79,28 @@ class ClockSampler:
             except Exception:
                 self.p = None
 
-    def _loop(self):
+    def sample(self):
+        if self.thread is None:
+            return
         nv = self.nv
-        while not self.stop_flag:
+        try:
             try:
-                try:
-                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            time.sleep(0.02)
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+        except Exception:
+            pass
 
     def stop(self):
         if self.thread is not None:
-            self.stop_flag = True; self.thread.join(timeout=1.0)
             nv = self.nv
             names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
             sm = [s for s, _ in self.samples]
             reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
             hot = sorted(sm)[len(sm) // 2:] if sm else []
-            return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm), "source": "nvml (in-process, 20 ms)"}
+            return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm), "source": "nvml (in-process, one sample per step between the event brackets, GPU busy with the L2 flush)"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -210,6 +209,7 @@ def run_batch_of_eight(args):
             launches += a.lm_iterations(1, FLAGS).gpu_launches     # each call ends with a stream synchronisation
         torch.cuda.synchronize()
         total_ms += 1e3 * (time.perf_counter() - t0)
+        if sampler: sampler.sample()                # right behind the round, outside its wall-clock bracket
     sync()
     clocks = sampler.stop() if sampler else None
     tot_res = nres
@@ -305,7 +305,9 @@ def main():
     barrier()
     for i in range(args.steps):
         reset()
-        flush.fill_(float(i)); torch.cuda.synchronize()
+        flush.fill_(float(i))
+        if sampler: sampler.sample()                # under load (the fill is running), outside the event bracket of any step
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -197,9 +197,11 @@ def run_batch_of_eight(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         reset(); [a.lm_iterations(1, FLAGS) for a in handles]
-    sampler = ClockSampler(local) if rank == 0 else None
+        if sampler: sampler.sample()
+    if sampler: sampler.samples.clear()
     sync()
     total_ms, launches = 0.0, 0
     for _ in range(args.steps):
@@ -297,11 +299,13 @@ def main():
     launches = 0
     step_ms = []
     summ = None
+    sampler = ClockSampler(local) if rank == 0 else None   # NVML is initialised (and queried once per warm-up step) before the timed region
     for i in range(args.warmup):
         reset(); api.lm_iterations(1, FLAGS)
+        if sampler: sampler.sample()
+    if sampler: sampler.samples.clear()
     import gc
     gc.collect(); gc.disable()                      # no collector pause inside a timed step (at N > 1 every rank waits for the slowest)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     for i in range(args.steps):
         reset()

@@ -384,11 +384,16 @@ def main():
     e2e = None
     h2d = sum(int(np.asarray(ds[k]).nbytes) for k in ("uv", "point_ids", "corner_offsets", "frame_t", "q_wc", "p_wc", "imu_t", "accel", "gyro", "board_xyzw"))
     e2e_vals, e2e_wall, e2e_iters = [], [], []
+    # the job's inputs live in page-locked host memory (the contract's "from pinned host memory"): the library then sends the large arrays
+    # straight to the device by DMA inside icc_set_frames / icc_set_imu and waits for it there (no staging copy, nothing borrowed after return)
+    ds_host, _pins = dict(ds), []
+    for k in ("uv", "point_ids", "accel", "gyro", "imu_t"):
+        tpin = torch.from_numpy(np.ascontiguousarray(ds[k])).pin_memory(); _pins.append(tpin); ds_host[k] = tpin.numpy()
     for i in range(max(1, args.e2e_steps)):
         barrier()
         t0 = time.perf_counter()
         a2 = capi.CApi(calibrator.load_library(), "icc_", local)
-        capi.load_dataset(a2, ds, comm=comm)
+        capi.load_dataset(a2, ds_host, comm=comm)
         s2 = a2.optimize(50, FLAGS)
         T = a2.get_T_i_c(); ld = a2.get_line_delay()
         torch.cuda.synchronize()
@@ -400,7 +405,7 @@ def main():
     e2e = {"value": float(np.median(e2e_vals)), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 8 + 8 * 8 * int(np.median(e2e_iters)),
            "wall_clock_to_convergence_s": float(np.median(e2e_wall)), "lm_iterations": int(np.median(e2e_iters)),
            "final_T_i_c": [float(x) for x in T], "final_reproj_error_px": float(s2.mean_reproj_error),
-           "what": "set_* + BatchInitSpline (host assembly + H2D) + Optimize(50) to Ceres-style convergence + getters, host buffers in, results out"}
+           "what": "set_* (H2D of the corner / IMU arrays from page-locked host buffers) + BatchInitSpline (host assembly + H2D of the tables) + Optimize(50) to Ceres-style convergence + getters, host buffers in, results out"}
 
     # ---- CPU baseline (rank 0, N == 1) ---------------------------------------------------------------------------------
     cpu = None

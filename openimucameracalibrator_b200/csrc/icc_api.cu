@@ -137,6 +137,10 @@ struct icc_handle {
   std::vector<double> frame_t; std::vector<int> corner_off; HostBuf<int> point_ids; HostBuf<double> uv; std::vector<double> q_wc, p_wc;
   HostBuf<double> imu_t, imu_acc, imu_gyr;
   int id_lo = 0, id_hi = -1;                 // range of the corner point ids (found while set_frames copies them)
+  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory): set_frames / set_imu send the big arrays straight to the
+  // device by DMA and wait for it, instead of staging them through a host copy first; the host then only keeps what it reads (time stamps,
+  // offsets, poses) and fetches the rest back from the device in the rare paths that gather (unsorted streams, non-contiguous shards).
+  bool frames_dev = false, imu_dev = false; size_t n_corners_in = 0, n_imu_in = 0;
   bool imu_sorted = false;                   // imu_t is non-decreasing (found while set_imu copies it)
   int shard_rank = 0, shard_world = 1;
   icc_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
@@ -163,6 +167,7 @@ struct icc_handle {
   bool aux_ok = false;
   int sm_count = 148;
   StateBufs st[2]; int cur = 0;
+  DevBuf<double2> d_uv_all; DevBuf<int> d_pid_all; DevBuf<double> d_acc_all, d_gyr_all;   // complete input arrays (frames_dev / imu_dev)
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
   DevBuf<double> d_view_t, d_view_q, d_view_p;   // per-view pose priors in time order (knot initialisation kernel)
   DevBuf<VisFrame> d_vframes; DevBuf<VisItem> d_vitems;
@@ -279,6 +284,27 @@ icc_status upload_points(icc_handle* h, int which, bool staged) {
   else { CU(cudaStreamSynchronize(h->stream)); CU(s.pts.upload(pad4(h->points, 4))); }
   launch_points_prepare((int)np, s.pts.p, s.board.p, s.pjac.p, h->stream);
   if (!staged) CU(cudaStreamSynchronize(h->stream));
+  return ICC_OK;
+}
+
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+// host copies of the arrays that went straight to the device, for the paths that gather on the host
+icc_status ensure_host_corners(icc_handle* h) {
+  if (!h->frames_dev || h->uv.size() == 2 * h->n_corners_in) return ICC_OK;
+  h->uv.resize(2 * h->n_corners_in, true); h->point_ids.resize(h->n_corners_in, true);
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->n_corners_in) { CU(cudaMemcpy(h->uv.data(), h->d_uv_all.p, h->n_corners_in * sizeof(double2), cudaMemcpyDeviceToHost)); CU(cudaMemcpy(h->point_ids.data(), h->d_pid_all.p, h->n_corners_in * sizeof(int), cudaMemcpyDeviceToHost)); }
+  return ICC_OK;
+}
+icc_status ensure_host_imu(icc_handle* h) {
+  if (!h->imu_dev || h->imu_acc.size() == 3 * h->n_imu_in) return ICC_OK;
+  h->imu_acc.resize(3 * h->n_imu_in, true); h->imu_gyr.resize(3 * h->n_imu_in, true);
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->n_imu_in) { CU(cudaMemcpy(h->imu_acc.data(), h->d_acc_all.p, 3 * h->n_imu_in * sizeof(double), cudaMemcpyDeviceToHost)); CU(cudaMemcpy(h->imu_gyr.data(), h->d_gyr_all.p, 3 * h->n_imu_in * sizeof(double), cudaMemcpyDeviceToHost)); }
   return ICC_OK;
 }
 
@@ -644,8 +670,22 @@ icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t*
   for (int i = 0; i < nf; ++i) if (off[i + 1] < off[i]) return fail(h, ICC_ERR_INVALID_ARGUMENT, "corner offsets must be non-decreasing");
   if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);   // an asynchronous upload may still be reading the staging buffers
   const bool pin = h->device >= 0;
-  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1); h->uv.assign(uv, 2 * (size_t)nc, pin);
-  {   // the ids are copied and range-checked in one pass (the check of batch_init_spline would read them again, cold)
+  h->frame_t.assign(t, t + nf); h->corner_off.assign(off, off + nf + 1);
+  h->n_corners_in = (size_t)nc;
+  h->frames_dev = pin && nc > 0 && host_is_pinned(uv) && host_is_pinned(ids);
+  if (h->frames_dev) {   // page-locked caller buffers: DMA straight to the device, the id range is found while it runs
+    CU(cudaSetDevice(h->device));
+    CU(h->d_uv_all.alloc((size_t)nc)); CU(h->d_pid_all.alloc((size_t)nc));
+    CU(cudaMemcpyAsync(h->d_uv_all.p, uv, (size_t)nc * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_pid_all.p, ids, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    int lo = 0, hi = -1;
+    for (int i = 0; i < nc; ++i) { const int v = ids[i]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    h->id_lo = lo; h->id_hi = hi;
+    h->uv.clear(); h->point_ids.clear();
+    CU(cudaStreamSynchronize(h->stream));   // the caller's arrays are not referenced after this call returns
+  } else {
+    h->uv.assign(uv, 2 * (size_t)nc, pin);
+    // the ids are copied and range-checked in one pass (the check of batch_init_spline would read them again, cold)
     h->point_ids.resize((size_t)nc, pin);
     int lo = 0, hi = -1; int* dst = h->point_ids.data();
     for (int i = 0; i < nc; ++i) { const int v = ids[i]; dst[i] = v; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
@@ -658,13 +698,22 @@ icc_status icc_set_imu(icc_handle* h, int n, const double* t, const double* a, c
   if (!h || n < 0 || (n > 0 && (!t || !a || !g))) return ICC_ERR_INVALID_ARGUMENT;
   if (h->device >= 0 && h->stream) cudaStreamSynchronize(h->stream);
   const bool pin = h->device >= 0;
-  h->imu_acc.assign(a, 3 * (size_t)n, pin); h->imu_gyr.assign(g, 3 * (size_t)n, pin);
+  h->n_imu_in = (size_t)n;
+  h->imu_dev = pin && n > 0 && host_is_pinned(a) && host_is_pinned(g);
+  if (h->imu_dev) {
+    CU(cudaSetDevice(h->device));
+    CU(h->d_acc_all.alloc(3 * (size_t)n)); CU(h->d_gyr_all.alloc(3 * (size_t)n));
+    CU(cudaMemcpyAsync(h->d_acc_all.p, a, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_gyr_all.p, g, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->imu_acc.clear(); h->imu_gyr.clear();
+  } else { h->imu_acc.assign(a, 3 * (size_t)n, pin); h->imu_gyr.assign(g, 3 * (size_t)n, pin); }
   {   // time stamps: copied and tested for order in one pass (the sorted stream takes the bisection path of batch_init_spline)
     h->imu_t.resize((size_t)n, pin);
     double* dst = h->imu_t.data(); int unsorted = 0; double prev = n > 0 ? t[0] : 0.0;
     for (int i = 0; i < n; ++i) { const double v = t[i]; dst[i] = v; unsorted |= !(v >= prev); prev = v; }
     h->imu_sorted = !unsorted;
   }
+  if (h->imu_dev) CU(cudaStreamSynchronize(h->stream));   // the caller's arrays are not referenced after this call returns
   return ICC_OK;
 }
 icc_status icc_set_shard(icc_handle* h, int rank, int world) { if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, ICC_ERR_INVALID_ARGUMENT, "bad shard"); h->shard_rank = rank; h->shard_world = world; return ICC_OK; }
@@ -931,6 +980,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     for (size_t k = 1; k < imu_sel.size() && h->imu_contig; ++k) h->imu_contig = all_imu[imu_sel[k]].src == all_imu[imu_sel[k - 1]].src + 1;
     h->imu_src0 = imu_sel.empty() ? 0 : all_imu[imu_sel.front()].src;
     h->imu_used_t.resize(imu_sel.size()); h->imu_used_st.n = imu_sel.size();
+    if (!h->imu_contig) { icc_status es = ensure_host_imu(h); if (es != ICC_OK) return es; }
     if (!h->imu_contig) { h->imu_used_acc.resize(3 * imu_sel.size()); h->imu_used_gyr.resize(3 * imu_sel.size()); }
     for (size_t k = 0; k < imu_sel.size(); ++k) {
       const ImuHost& m = all_imu[imu_sel[k]];
@@ -952,6 +1002,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     h->used_c0 = cb; h->used_n = ce - cb;
     for (int fi : frame_sel) { FrameHost f = all_frames[fi]; f.c0 -= cb; f.c1 -= cb; h->frames.push_back(f); }
   } else {
+    { icc_status es = ensure_host_corners(h); if (es != ICC_OK) return es; }
     for (int fi : frame_sel) {
       FrameHost f = all_frames[fi];
       const int c0 = (int)h->used_pid.size();
@@ -971,7 +1022,11 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     const Pose Tai = pose_mul(Twc, Tci);
     for (size_t i = 0; i < h->imu_t.size(); ++i) {
       const int64_t accl_t = (int64_t)h->imu_t[i];
-      if (std::fabs(double(accl_t) - cam_ts[j]) < 1. / 30.) { const V3 g = qrot(Tai.q, v3(h->imu_acc[3 * i], h->imu_acc[3 * i + 1], h->imu_acc[3 * i + 2])); g0[0] = g.x; g0[1] = g.y; g0[2] = g.z; ginit = true; break; }
+      if (std::fabs(double(accl_t) - cam_ts[j]) < 1. / 30.) {
+        double a3[3];
+        if (h->imu_dev && h->imu_acc.size() != 3 * h->n_imu_in) { CU(cudaMemcpy(a3, h->d_acc_all.p + 3 * i, sizeof a3, cudaMemcpyDeviceToHost)); }   // one reading
+        else { a3[0] = h->imu_acc[3 * i]; a3[1] = h->imu_acc[3 * i + 1]; a3[2] = h->imu_acc[3 * i + 2]; }
+        const V3 g = qrot(Tai.q, v3(a3[0], a3[1], a3[2])); g0[0] = g.x; g0[1] = g.y; g0[2] = g.z; ginit = true; break; }
     }
   }
   for (int d = 0; d < 3; ++d) h->glob[G_GRAV + d] = g0[d];
@@ -1006,16 +1061,16 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     off.push_back(P.n_corners);
     CU(upload_staged(h, h->d_f_off, off)); CU(upload_staged(h, h->d_f_s_so3, s1)); CU(upload_staged(h, h->d_f_s_r3, s2)); CU(upload_staged(h, h->d_f_u_so3, u1)); CU(upload_staged(h, h->d_f_u_r3, u2));
     P.f_off = h->d_f_off.p; P.f_s_so3 = h->d_f_s_so3.p; P.f_s_r3 = h->d_f_s_r3.p; P.f_u_so3 = h->d_f_u_so3.p; P.f_u_r3 = h->d_f_u_r3.p;
-    CU(h->d_uv.alloc(P.n_corners));   // (u, v) pairs are already laid out as double2
-    CU(h->d_pid.alloc(P.n_corners));
-    if (P.n_corners > 0) {
+    const bool corners_in_place = h->frames_dev && h->used_contig;   // already on the device (set_frames): used where they lie
+    if (corners_in_place) { P.uv = h->d_uv_all.p + h->used_c0; P.pid = h->d_pid_all.p + h->used_c0; }
+    else { CU(h->d_uv.alloc(P.n_corners)); CU(h->d_pid.alloc(P.n_corners)); P.uv = h->d_uv.p; P.pid = h->d_pid.p; }   // (u, v) pairs are already laid out as double2
+    if (P.n_corners > 0 && !corners_in_place) {
       const double* uv_src = h->used_contig ? h->uv.data() + 2 * (size_t)h->used_c0 : h->used_uv.data();
       const int* pid_src = h->used_contig ? h->point_ids.data() + h->used_c0 : h->used_pid.data();
       // page-locked sources (HostBuf): the DMA transfers run behind the rest of this function; kernels follow on the same stream
       CU(cudaMemcpyAsync(h->d_uv.p, uv_src, (size_t)P.n_corners * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
       CU(cudaMemcpyAsync(h->d_pid.p, pid_src, (size_t)P.n_corners * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    P.uv = h->d_uv.p; P.pid = h->d_pid.p;
     // work lists: one warp per item; items sized so that the grid fills the GPU but every item amortises its tile flush
     const int target_items = h->sm_count * 8;
     auto round32 = [](long v) { return (int)((v + 31) / 32 * 32); };
@@ -1091,14 +1146,16 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
       CU(cudaMemcpyAsync(h->d_imu_traw.p, h->imu_t.data() + h->imu_src0, h->n_imu_used * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       launch_imu_times((int)h->n_imu_used, h->d_imu_traw.p, ipp->time_offset_imu_to_cam_s, h->start_ns, h->d_imu_t.p, h->stream);
     } else if (h->n_imu_used) CU(cudaMemcpyAsync(h->d_imu_t.p, h->imu_used_st.data(), h->n_imu_used * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu));
-    if (P.n_imu > 0) {
+    const bool imu_in_place = h->imu_dev && h->imu_contig;   // already on the device (set_imu): used where they lie
+    if (imu_in_place) { P.imu_acc = h->d_acc_all.p + 3 * (size_t)h->imu_src0; P.imu_gyr = h->d_gyr_all.p + 3 * (size_t)h->imu_src0; }
+    else { CU(h->d_imu_acc.alloc(3 * (size_t)P.n_imu)); CU(h->d_imu_gyr.alloc(3 * (size_t)P.n_imu)); P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p; }
+    if (P.n_imu > 0 && !imu_in_place) {
       const double* a_src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data();
       const double* g_src = h->imu_contig ? h->imu_gyr.data() + 3 * (size_t)h->imu_src0 : h->imu_used_gyr.data();
       CU(cudaMemcpyAsync(h->d_imu_acc.p, a_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       CU(cudaMemcpyAsync(h->d_imu_gyr.p, g_src, 3 * (size_t)P.n_imu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    P.imu_t_ns = h->d_imu_t.p; P.imu_acc = h->d_imu_acc.p; P.imu_gyr = h->d_imu_gyr.p;
+    P.imu_t_ns = h->d_imu_t.p;
   }
   trace.lap("batch_init: problem upload");
   icc_status s = upload_state(h, 0, true); if (s != ICC_OK) return s;
@@ -1191,8 +1248,10 @@ icc_status icc_get_mean_reprojection_error(icc_handle* h, double* e) {
   return mean_reproj(h, e);
 }
 icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->n_imu_used; return ICC_OK; }
-icc_status icc_get_imu_used(const icc_handle* h, double* t, double* a, double* g) {
+icc_status icc_get_imu_used(const icc_handle* hc, double* t, double* a, double* g) {
+  icc_handle* h = const_cast<icc_handle*>(hc);
   if (!h) return ICC_ERR_INVALID_ARGUMENT;
+  if (a || g) { icc_status es = ensure_host_imu(h); if (es != ICC_OK) return es; }
   const size_t nu = h->n_imu_used;
   if (t) { if (h->imu_lazy) { for (size_t k = 0; k < nu; ++k) t[k] = h->imu_t[h->imu_src0 + k] + h->ip.time_offset_imu_to_cam_s; } else std::copy(h->imu_used_t.begin(), h->imu_used_t.end(), t); }
   if (a) { const double* src = h->imu_contig ? h->imu_acc.data() + 3 * (size_t)h->imu_src0 : h->imu_used_acc.data(); std::copy(src, src + 3 * nu, a); }

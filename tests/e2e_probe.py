@@ -6,6 +6,10 @@ import torch
 from openimucameracalibrator_b200 import _capi as capi, calibrator, synthetic as syn
 cfg = syn.CONFIGS[int(sys.argv[1]) if len(sys.argv) > 1 else 4]
 ds = syn.make_dataset(cfg)
+if os.environ.get("E2E_PINNED"):
+    keep = []
+    for k in ("uv", "point_ids", "accel", "gyro", "imu_t"):
+        t = torch.from_numpy(np.ascontiguousarray(ds[k])).pin_memory(); keep.append(t); ds[k] = t.numpy()
 lib = calibrator.load_library()
 FLAGS = capi.FLAG_SPLINE | capi.FLAG_T_I_C
 W, H = ds["image_size"]

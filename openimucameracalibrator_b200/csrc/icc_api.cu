@@ -167,6 +167,8 @@ struct icc_handle {
   bool aux_ok = false;
   int sm_count = 148;
   StateBufs st[2]; int cur = 0;
+  HostBuf<unsigned char> small_pinned; DevBuf<int> d_idrange;
+  void* arena_small(size_t bytes) { if (small_pinned.size() < bytes) small_pinned.resize(std::max<size_t>(bytes, 256), true); return small_pinned.pinned ? small_pinned.data() : nullptr; }
   DevBuf<double2> d_uv_all; DevBuf<int> d_pid_all; DevBuf<double> d_acc_all, d_gyr_all;   // complete input arrays (frames_dev / imu_dev)
   DevBuf<double4> d_board; DevBuf<int> d_f_off, d_f_s_so3, d_f_s_r3, d_pid; DevBuf<double> d_f_u_so3, d_f_u_r3; DevBuf<double2> d_uv;
   DevBuf<double> d_view_t, d_view_q, d_view_p;   // per-view pose priors in time order (knot initialisation kernel)
@@ -440,7 +442,8 @@ icc_status configure(icc_handle* h, int flags) {
   P.ne_off_E = (int64_t)nk * P.ldb; P.ne_off_C = P.ne_off_E + (int64_t)nk * nb; P.ne_off_g = P.ne_off_C + (int64_t)nb * nb;
   P.ne_off_cost = P.ne_off_g + nk + nb; P.ne_size = (P.ne_off_cost + 1 + 3) / 4 * 4;
   if (h->device >= 0) {
-    CU(h->d_so3_col.upload(h->so3_col)); CU(h->d_r3_col.upload(h->r3_col)); CU(h->d_ba_col.upload(h->ba_col)); CU(h->d_bg_col.upload(h->bg_col));
+    // (staged through the page-locked arena while it has room: asynchronous, ordered before the kernels on the solver's stream)
+    CU(upload_staged(h, h->d_so3_col, h->so3_col)); CU(upload_staged(h, h->d_r3_col, h->r3_col)); CU(upload_staged(h, h->d_ba_col, h->ba_col)); CU(upload_staged(h, h->d_bg_col, h->bg_col));
     P.so3_col = h->d_so3_col.p; P.r3_col = h->d_r3_col.p; P.ba_col = h->d_ba_col.p; P.bg_col = h->d_bg_col.p;
     CU(h->d_ne.alloc((size_t)P.ne_size)); P.ne = h->d_ne.p;
     CU(h->d_scale.alloc((size_t)std::max(1, nk + nb))); CU(h->d_delta.alloc((size_t)std::max(1, nk + nb)));
@@ -678,11 +681,19 @@ icc_status icc_set_frames(icc_handle* h, int nf, const double* t, const int32_t*
     CU(h->d_uv_all.alloc((size_t)nc)); CU(h->d_pid_all.alloc((size_t)nc));
     CU(cudaMemcpyAsync(h->d_uv_all.p, uv, (size_t)nc * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_pid_all.p, ids, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    int lo = 0, hi = -1;
-    for (int i = 0; i < nc; ++i) { const int v = ids[i]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
-    h->id_lo = lo; h->id_hi = hi;
+    // the id range is reduced on the device behind the copy (two ints come back with the synchronisation this call ends with anyway)
+    int* rng = static_cast<int*>(h->arena_small(2 * sizeof(int)));
+    if (rng) {
+      rng[0] = 0; rng[1] = -1;
+      CU(h->d_idrange.alloc(2));
+      CU(cudaMemcpyAsync(h->d_idrange.p, rng, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      launch_id_range(nc, h->d_pid_all.p, h->d_idrange.p, h->stream);
+      CU(cudaMemcpyAsync(rng, h->d_idrange.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
     h->uv.clear(); h->point_ids.clear();
     CU(cudaStreamSynchronize(h->stream));   // the caller's arrays are not referenced after this call returns
+    if (rng) { h->id_lo = rng[0]; h->id_hi = rng[1]; }
+    else { int lo = 0, hi = -1; for (int i = 0; i < nc; ++i) { const int v = ids[i]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; } h->id_lo = lo; h->id_hi = hi; }
   } else {
     h->uv.assign(uv, 2 * (size_t)nc, pin);
     // the ids are copied and range-checked in one pass (the check of batch_init_spline would read them again, cold)
@@ -1049,7 +1060,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
   CU(cudaStreamSynchronize(h->stream));   // nothing may still read the staging arena of an earlier call
   trace.lap("batch_init: gravity init");
   h->arena.reset((size_t)(1 << 17) + 64 * (size_t)nf + 48 * (size_t)(nf + 4) + 16 * (size_t)(h->sm_count * 16 + 16) + 48 * (size_t)(nf + h->used_n / 32 + 64) + (96 + 40) * (h->cells.size() + (size_t)P.n_imu / 32 + 64)
-                 + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 3 * (32 * (h->points.size() / 4 + 8) + 256), true);
+                 + 8 * 8 * (size_t)(nf + 8) + 2 * 40 * (size_t)(nso3 + nr3 + nba + nbg + 16) + 3 * (32 * (h->points.size() / 4 + 8) + 256) + 3 * (4 * (size_t)(nso3 + nr3 + nba + nbg) + 1024), true);
   trace.lap("batch_init: pinned arena");
   {
     std::vector<double4> board(h->points.size() / 4);

@@ -65,7 +65,22 @@ __global__ void imu_times_kernel(int n, const double* __restrict__ t_raw, double
   if (i < n) st[i] = (int64_t)__dmul_rn(__dadd_rn(t_raw[i], offset_s), 1e9) - start_ns;
 }
 
+// smallest / largest corner point id (range check of batch_init_spline): out[0] = min(0, ids...), out[1] = max(-1, ids...)
+__global__ void id_range_kernel(int n, const int* __restrict__ ids, int* out) {
+  int lo = 0, hi = -1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const int v = ids[i]; lo = min(lo, v); hi = max(hi, v); }
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(out, lo); atomicMax(out + 1, hi); }
+}
+
 }  // namespace
+
+void launch_id_range(int n, const int* ids, int* out2, cudaStream_t st) {   // out2 must hold {0, -1} before the launch
+  if (n <= 0) return;
+  int grid = (n + 1023) / 1024; if (grid > 296) grid = 296;
+  id_range_kernel<<<grid, 256, 0, st>>>(n, ids, out2);
+  count_launch();
+}
 
 void launch_imu_times(int n, const double* t_raw, double offset_s, int64_t start_ns, int64_t* st_out, cudaStream_t st) {
   if (n <= 0) return;

@@ -106,6 +106,7 @@ void launch_update(const DeviceProblem& P, const DeviceState& cur, const DeviceS
 // knot initialisation from the per-view pose priors (icc_init.cu): q_wc / p_wc / t_vis in view-time order, T_c_i = T_i_c^-1 (x,y,z,w,tx,ty,tz)
 void launch_init_knots(int nv, const double* t_vis, const double* q_wc, const double* p_wc, const double T_c_i[7], int nso3, int64_t dt_so3_ns, int nr3, int64_t dt_r3_ns,
                        double4* so3_a, double4* so3_b, double4* r3_a, double4* r3_b, cudaStream_t st);
+void launch_id_range(int n, const int* ids, int* out2, cudaStream_t st);
 // relative integer sample times of a sorted IMU stream from its raw stamps (icc_init.cu)
 void launch_imu_times(int n, const double* t_raw, double offset_s, int64_t start_ns, int64_t* st_out, cudaStream_t st);
 // board points as parameters (icc_points.cu)

@@ -46,8 +46,9 @@ def test_pinned_inputs_match_staged_inputs(gpu_factory, name, ds, shard):
     assert np.array_equal(a.get_gravity(), b.get_gravity())
     ca, ra, ga, _ = a.evaluate(F_STAGE1)
     cb, rb, gb, _ = b.evaluate(F_STAGE1)
-    assert ca == cb and np.array_equal(ra, rb)
-    assert np.allclose(ga, gb, rtol=1e-12, atol=1e-9 * np.abs(ga).max())       # (atomics: summation order differs between runs)
+    assert np.array_equal(ra, rb)
+    assert abs(ca - cb) <= 1e-13 * ca                                          # (atomics: summation order differs between runs)
+    assert np.allclose(ga, gb, rtol=1e-12, atol=1e-9 * np.abs(ga).max())
     if shard is None:
         sa, sb = a.optimize(10, F_STAGE1), b.optimize(10, F_STAGE1)
         assert sa.iterations == sb.iterations and abs(sa.final_cost - sb.final_cost) <= 1e-9 * sa.final_cost
@@ -69,4 +70,4 @@ def test_pinned_buffers_are_not_referenced_after_set(gpu_factory):
                         acc_bias=dp["acc_bias"], gyr_bias=dp["gyr_bias"], dispatch_fov=False)
     b.set_known_gravity_dir(dp["gravity"])
     ca = a.evaluate(F_STAGE1, residuals=False, gradient=False)[0]; cb = b.evaluate(F_STAGE1, residuals=False, gradient=False)[0]
-    assert ca == cb
+    assert abs(ca - cb) <= 1e-13 * ca

@@ -27,7 +27,7 @@ constexpr size_t SLOT_BYTES = sizeof(tmi::ImuSlot) > sizeof(tmv::WarpSlot) ? siz
 constexpr size_t CONST_BYTES = ((sizeof(VisConst) + sizeof(ImuConst) + 15) / 16) * 16;
 
 template <int MODEL>
-__global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out, int rounds) {
+__global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, DeviceState S, double* __restrict__ res_out, int rounds, int groups, int stagger_ns) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VisConst* KV = reinterpret_cast<VisConst*>(smem_raw);
   ImuConst* KI = reinterpret_cast<ImuConst*>(smem_raw + sizeof(VisConst));
@@ -49,12 +49,16 @@ __global__ void __launch_bounds__(EW * 32, 1) eval_tmem_kernel(DeviceProblem P, 
   NeLayout L; L.ne = P.ne; L.off_E = P.ne_off_E; L.off_C = P.ne_off_C; L.off_g = P.ne_off_g; L.off_cost = P.ne_off_cost; L.nk = P.nk; L.nb = P.nb; L.ldb = P.ldb;
 
   const int gw = warp * gridDim.x + blockIdx.x;           // global warp: consecutive runs land on different SMs
+  // lockstep groups: the whole CTA (groups == 1), or the three sets of four warps that sit on the four sub-cores together (warp / 4),
+  // each with its own named barriers and started `stagger_ns` apart, so that one group's tensor-core phase meets the others' SIMT phases
+  const int grp = groups == 3 ? warp >> 2 : groups == 4 ? (warp & 3) : groups == 6 ? warp % 6 : groups == 2 ? (warp & 1) : 0, bar_id = 1 + grp, bar_n = EW * 32 / (groups > 0 ? groups : 1);
+  if (groups > 1 && stagger_ns > 0) for (int g = 0; g < grp; ++g) __nanosleep(stagger_ns);
   if (P.n_vitems > 0) {
-    if (gw < P.n_vitems) tmv::run_item<MODEL>(P, S, KV, reinterpret_cast<tmv::WarpSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.vitems[gw], res_out, lane, rounds);
-    else for (int r = 0; r < rounds; ++r) asm volatile("bar.sync 1, %0;" :: "r"(EW * 32) : "memory");
+    if (gw < P.n_vitems) tmv::run_item<MODEL>(P, S, KV, reinterpret_cast<tmv::WarpSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.vitems[gw], res_out, lane, rounds, bar_id, bar_n);
+    else for (int r = 0; r < rounds; ++r) asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory");
   } else if (P.n_iitems > 0) {           // (a launch carries one item type: launch_eval_tmem)
-    if (gw < P.n_iitems) tmi::run_item(P, S, KI, reinterpret_cast<tmi::ImuSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.iitems[gw], res_out, lane, rounds);
-    else for (int r = 0; r < rounds; ++r) { asm volatile("bar.sync 1, %0;" :: "r"(EW * 32) : "memory"); asm volatile("bar.sync 2, %0;" :: "r"(EW * 32) : "memory"); }
+    if (gw < P.n_iitems) tmi::run_item(P, S, KI, reinterpret_cast<tmi::ImuSlot*>(slots + warp * SLOT_BYTES), tile, ta, L, P.iitems[gw], res_out, lane, rounds, bar_id, bar_n);
+    else for (int r = 0; r < rounds; ++r) { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory"); asm volatile("bar.sync %0, %1;" :: "r"(bar_id + 6), "r"(bar_n) : "memory"); }
   }
   tmem_fence_before_sync();
   __syncthreads();
@@ -68,10 +72,15 @@ int launch_model(const DeviceProblem& P, const DeviceState& S, double* residuals
     if (cudaFuncSetAttribute(eval_tmem_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     attr_done = true;
   }
-  // loose lockstep: the warps of a CTA start every vision chunk together (one named barrier per chunk), so that they walk the same
-  // ~80 KB of unrolled code at the same time: instruction-cache hit rate 81 % -> better, config 4 vision launch 155 -> 150 us
+  // loose lockstep: warps start every chunk together (one named barrier per chunk), so that they walk the same ~80 KB of unrolled code at
+  // the same time (instruction-cache hit rate 81 % -> better).  Measured on config 4 (tests/stagger_probe.py), vision / IMU launch in us:
+  // free running 153 / 88, whole CTA in step 149.5 / 84.1, three groups of four warps (one warp per sub-core each) 143.7 / 85.0, four
+  // groups of three (the warps of one sub-core) 147.7 / 80.6, six pairs 147.5 / 94.7; starting the groups a few us apart only hurts.
+  // Hence vision items run as 3 groups, IMU items as 4 (ICC_TMEM_GROUPS overrides, ICC_TMEM_STAGGER_NS delays group g by g x ns).
   const int rounds = getenv("ICC_TMEM_NO_LOCKSTEP") ? 0 : P.n_vitems > 0 ? (P.n_vchunks + P.n_vitems - 1) / P.n_vitems : P.n_iitems > 0 ? (P.n_ichunks + P.n_iitems - 1) / P.n_iitems : 0;
-  eval_tmem_kernel<MODEL><<<grid, EW * 32, smem, st>>>(P, S, residuals_out, rounds);
+  const char* eg = getenv("ICC_TMEM_GROUPS"); const char* es = getenv("ICC_TMEM_STAGGER_NS");
+  const int gq = eg ? atoi(eg) : (P.n_vitems > 0 ? 3 : 4), groups = (gq == 2 || gq == 3 || gq == 4 || gq == 6) ? gq : 1, stagger_ns = es ? atoi(es) : 0;
+  eval_tmem_kernel<MODEL><<<grid, EW * 32, smem, st>>>(P, S, residuals_out, rounds, groups, stagger_ns);
   return 0;
 }
 

@@ -135,7 +135,7 @@ ICC_D void init_const(ImuConst* K, const DeviceProblem& P, const DeviceState& S)
 }
 
 // One item = one contiguous run of 32-lane chunks of the packed IMU sample stream, processed by one warp.
-ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const ImuConst* K, ImuSlot* slot, double* __restrict__ tile, uint32_t ta, const NeLayout& L, const VisItem it, double* __restrict__ res_out, int lane, int rounds) {
+ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const ImuConst* K, ImuSlot* slot, double* __restrict__ tile, uint32_t ta, const NeLayout& L, const VisItem it, double* __restrict__ res_out, int lane, int rounds, int bar_id, int bar_n) {
   const bool lock = rounds > 0;
   ImuStageArgs A; A.so3 = S.so3; A.r3 = S.r3; A.ba = S.ba; A.bg = S.bg; A.so3_col = P.so3_col; A.r3_col = P.r3_col; A.col_g = P.col_g;
   const double dto = S.glob[G_TOFF];          // time-offset increment [s] (0 unless the extension has been optimised)
@@ -146,7 +146,7 @@ ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const ImuConst
     int endC = min(P.icells[c + 1].poff, it.pos_end);
     bool fresh = true;
     while (pos < it.pos_end) {
-      if (rounds > 0) { asm volatile("bar.sync 1, %0;" :: "r"(IW * 32) : "memory"); --rounds; }   // loose lockstep of the CTA's warps (instruction-cache locality)
+      if (rounds > 0) { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory"); --rounds; }   // loose lockstep of the warps of a group (instruction-cache locality)
       if (pos == endC) {
         ++c;
         stage_cell(slot, cur, P.icells[c], A);
@@ -196,7 +196,7 @@ ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const ImuConst
       tmem_wait_st();
       __syncwarp();
       // ---- gyroscope ------------------------------------------------------------------------------------------------------
-      if (lock) asm volatile("bar.sync 2, %0;" :: "r"(IW * 32) : "memory");
+      if (lock) asm volatile("bar.sync %0, %1;" :: "r"(bar_id + 6), "r"(bar_n) : "memory");
       {
         double park[GYR_PARK];
         double* row0 = tile + lane;
@@ -227,7 +227,7 @@ ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const ImuConst
       pos += n;
     }
   }
-  while (rounds-- > 0) { asm volatile("bar.sync 1, %0;" :: "r"(IW * 32) : "memory"); asm volatile("bar.sync 2, %0;" :: "r"(IW * 32) : "memory"); }
+  while (rounds-- > 0) { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory"); asm volatile("bar.sync %0, %1;" :: "r"(bar_id + 6), "r"(bar_n) : "memory"); }
 }
 
 }  // namespace tmi

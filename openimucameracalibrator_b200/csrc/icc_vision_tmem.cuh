@@ -121,7 +121,7 @@ ICC_D void init_const(VisConst* K, const DeviceProblem& P, const DeviceState& S,
 
 // One item = one contiguous run of 32-lane chunks of the packed corner stream, processed by one warp.
 template <int MODEL>
-ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const VisConst* K, WarpSlot* slot, double* __restrict__ tile, uint32_t ta, const NeLayout& L, const VisItem it, double* __restrict__ res_out, int lane, int rounds) {
+ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const VisConst* K, WarpSlot* slot, double* __restrict__ tile, uint32_t ta, const NeLayout& L, const VisItem it, double* __restrict__ res_out, int lane, int rounds, int bar_id, int bar_n) {
   StageArgs A; A.so3 = S.so3; A.r3 = S.r3; A.so3_col = P.so3_col; A.r3_col = P.r3_col; A.col_tic = P.col_tic; A.col_ld = P.col_ld;
   {
     int f = it.vf0, pos = it.pos_begin, cur = 0;
@@ -129,7 +129,7 @@ ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const VisConst
     int endF = min(P.vframes[f + 1].poff, it.pos_end);
     bool fresh = true;
     while (pos < it.pos_end) {
-      if (rounds > 0) { asm volatile("bar.sync 1, %0;" :: "r"(VW * 32) : "memory"); --rounds; }   // loose lockstep of the CTA's warps: instruction-cache locality (icc_eval_tmem.cu)
+      if (rounds > 0) { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory"); --rounds; }   // loose lockstep of the warps of a group: instruction-cache locality (icc_eval_tmem.cu)
       if (pos == endF) {                          // the previous chunk finished its frame exactly at the chunk boundary
         ++f;
         stage_frame(slot, cur, P.vframes[f], A);
@@ -182,7 +182,7 @@ ICC_D void run_item(const DeviceProblem& P, const DeviceState& S, const VisConst
       pos += n;
     }
   }
-  while (rounds-- > 0) asm volatile("bar.sync 1, %0;" :: "r"(VW * 32) : "memory");
+  while (rounds-- > 0) asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_n) : "memory");
 }
 
 }  // namespace tmv

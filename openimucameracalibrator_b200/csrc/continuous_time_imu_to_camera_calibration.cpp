@@ -18,11 +18,13 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
 #include <map>
 #include <set>
+#include <thread>
 #include <spawn.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -68,22 +70,45 @@ Value xyz(double x, double y, double z) { Value v = Value::object(); v["x"] = Va
 // in std::map<std::string> key order (lexicographic on the decimal timestamp; a repeated timestamp keeps the last sample), i.e. the bytes
 // nlohmann::json / the tree route would produce, without building 700 k tree nodes.
 static void write_result(iccjson::Writer& w, const Value& head, int n_used, const int64_t* t_ns, const double* ug, const double* gs, const double* gb,
-                         const double* ua, const double* as, const double* ab) {
-  auto xyz_at = [&](const char* k, const double* v, int i) { w.key(k); w.begin_object(); w.key("x"); w.value(v[3 * i]); w.key("y"); w.value(v[3 * i + 1]); w.key("z"); w.value(v[3 * i + 2]); w.end_object(); };
+                         const double* ua, const double* as, const double* ab, int threads = 0) {
   w.begin_object();
   for (const auto& kv : *head.o) { w.key(kv.first); w.value(kv.second); }
   if (n_used) {
+    const bool tr = getenv("ICC_JSON_TRACE") != nullptr; auto T0 = std::chrono::steady_clock::now();   // ICC_JSON_TRACE=1: phase times to stderr
+    auto lap = [&](const char* what) { if (tr) { auto T1 = std::chrono::steady_clock::now(); std::cerr << "    [json] " << what << " " << std::chrono::duration<double, std::milli>(T1 - T0).count() << " ms\n"; T0 = T1; } };
     std::vector<std::pair<std::string, int>> keys(n_used);
     for (int i = 0; i < n_used; ++i) keys[i] = {std::to_string(t_ns[i]), i};
     std::stable_sort(keys.begin(), keys.end(), [](const std::pair<std::string, int>& a, const std::pair<std::string, int>& b) { return a.first < b.first; });
+    lap("keys + sort");
     w.key("trajectory"); w.begin_object();
-    for (int k = 0; k < n_used; ++k) {
-      if (k + 1 < n_used && keys[k + 1].first == keys[k].first) continue;
-      const int i = keys[k].second;
-      w.key(keys[k].first); w.begin_object();
-      xyz_at("accl_bias", ab, i); xyz_at("accl_imu", ua, i); xyz_at("accl_spline", as, i); xyz_at("gyro_bias", gb, i); xyz_at("gyro_imu", ug, i); xyz_at("gyro_spline", gs, i);
-      w.end_object();
-    }
+    // The entries are formatted by several threads, each into its own fragment that continues inside the two open objects (root, trajectory);
+    // the fragments are then written in order.  ~900 bytes of text per entry: formatting, not the file system, is the cost of this file.
+    auto emitted = [&](int k) { return !(k + 1 < n_used && keys[k + 1].first == keys[k].first); };   // a repeated timestamp keeps the last sample
+    if (threads <= 0) threads = (int)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    threads = std::max(1, std::min(threads, n_used / 64 + 1));
+    std::vector<int> cut(threads + 1), before(threads + 1, 0);
+    for (int c = 0; c <= threads; ++c) cut[c] = (int)((int64_t)n_used * c / threads);
+    for (int c = 0; c < threads; ++c) { int e = 0; for (int k = cut[c]; k < cut[c + 1]; ++k) e += emitted(k); before[c + 1] = before[c] + e; }
+    std::vector<std::string> frag(threads);
+    auto work = [&](int c) {
+      std::string& out = frag[c]; out.reserve((size_t)(before[c + 1] - before[c]) * 960 + 64);
+      iccjson::Writer fw(4, &out, std::vector<size_t>{1, (size_t)before[c]});
+      auto xyz_at = [&](const char* k, const double* v, int i) { fw.key(k); fw.begin_object(); fw.key("x"); fw.value(v[3 * i]); fw.key("y"); fw.value(v[3 * i + 1]); fw.key("z"); fw.value(v[3 * i + 2]); fw.end_object(); };
+      for (int k = cut[c]; k < cut[c + 1]; ++k) {
+        if (!emitted(k)) continue;
+        const int i = keys[k].second;
+        fw.key(keys[k].first); fw.begin_object();
+        xyz_at("accl_bias", ab, i); xyz_at("accl_imu", ua, i); xyz_at("accl_spline", as, i); xyz_at("gyro_bias", gb, i); xyz_at("gyro_imu", ug, i); xyz_at("gyro_spline", gs, i);
+        fw.end_object();
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int c = 1; c < threads; ++c) pool.emplace_back(work, c);
+    work(0);
+    for (auto& t : pool) t.join();
+    lap("format");
+    for (int c = 0; c < threads; ++c) w.raw_members(frag[c], (size_t)(before[c + 1] - before[c]));
+    lap("concatenate / write");
     w.end_object();
   }
   w.end_object();
@@ -107,9 +132,24 @@ static int json_selftest() {
   }
   tree["trajectory"] = traj;
   std::string streamed;
-  { iccjson::Writer w(4, &streamed); write_result(w, head, n, t.data(), a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data()); }
-  const bool same = streamed == iccjson::dump(tree, 4);
+  bool same = true;
+  const std::string want = iccjson::dump(tree, 4);
+  for (int threads : {1, 2, 3, 5, 8}) {   // the fragments of any number of formatting threads concatenate to the tree route's bytes
+    streamed.clear();
+    { iccjson::Writer w(4, &streamed); write_result(w, head, n, t.data(), a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), threads); }
+    same = same && streamed == want;
+  }
   std::cout << (same ? "json selftest ok: " : "json selftest FAILED: ") << streamed.size() << " bytes" << std::endl;
+  if (const char* big = getenv("ICC_JSON_SELFTEST_N")) {   // formatting time of a config-4-sized trajectory (100 k entries) per thread count
+    const int m = atoi(big);
+    std::vector<int64_t> tb(m); std::vector<double> ab[6]; for (auto& v : ab) v.resize(3 * (size_t)m);
+    for (int i = 0; i < m; ++i) { tb[i] = 1000000 * (int64_t)i + 123; for (auto& v : ab) for (int d = 0; d < 3; ++d) v[3 * (size_t)i + d] = (double)(int64_t)(rnd() % 2000001 - 1000000) * 1.0000001e-6; }
+    for (int threads : {1, 2, 4, 8}) {
+      std::string out; const auto t0 = std::chrono::steady_clock::now();
+      { iccjson::Writer w(4, &out); write_result(w, head, m, tb.data(), ab[0].data(), ab[1].data(), ab[2].data(), ab[3].data(), ab[4].data(), ab[5].data(), threads); }
+      std::cout << "  " << m << " entries, " << threads << " formatting thread(s): " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << " ms, " << out.size() << " bytes" << std::endl;
+    }
+  }
   return same ? 0 : 1;
 }
 

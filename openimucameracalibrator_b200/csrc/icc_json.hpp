@@ -152,6 +152,9 @@ inline std::string number_to_string(double v) {
 class Writer {
  public:
   explicit Writer(int indent, std::string* sink) : indent_(indent), str_(sink) {}
+  // a writer that continues INSIDE open containers: `members[d]` = members already written in the container at depth d (fragments
+  // produced this way concatenate to exactly the bytes one writer would have produced)
+  Writer(int indent, std::string* sink, const std::vector<size_t>& members) : indent_(indent), str_(sink), count_(members) {}
   Writer(int indent, FILE* sink) : indent_(indent), file_(sink) { buf_.reserve(size_t(1) << 21); }
   ~Writer() { flush(); }
   void begin_object() { open('{'); }
@@ -175,6 +178,8 @@ class Writer {
       case Value::Obj: begin_object(); for (const auto& kv : *v.o) { key(kv.first); value(kv.second); } end_object(); break;
     }
   }
+  // pre-formatted members of the innermost open container (see the fragment constructor)
+  void raw_members(const std::string& text, size_t n_members) { if (n_members == 0) return; if (file_) { flush(); fwrite(text.data(), 1, text.size(), file_); } else out() += text; count_.back() += n_members; }
   void flush() { if (file_ && !buf_.empty()) { fwrite(buf_.data(), 1, buf_.size(), file_); buf_.clear(); } }
  private:
   int indent_; std::string* str_ = nullptr; FILE* file_ = nullptr; std::string buf_;

@@ -171,3 +171,34 @@ def test_trajectory_getters(oracle_factory, gpu_factory):
     assert np.array_equal(a["valid"], b["valid"]) and a["valid"][-1] == 0 and a["valid"][-2] == 0
     for key in ("gyro", "accel", "gyro_bias", "accel_bias", "pose_q", "pose_p"):
         assert rel(a[key], b[key]) < TOL, key
+
+
+def test_imu_stamps_on_knot_boundaries_and_repeated(oracle_factory, gpu_factory, eval_path):
+    """IMU stamps that fall exactly on knot-interval boundaries, repeated stamps and an irregular rate: the cells of the sorted stream are
+    found by bisection for the next boundary (icc_api.cu: cells_by_bisection) and the relative integer times are derived on the device
+    (imu_times_kernel); both must reproduce CalcTimes sample by sample.  The same samples shuffled take the general (sequential) path."""
+    ds = dict(syn.make_dataset(syn.tiny_config(n_frames=30, dt_so3_s=0.04, dt_r3_s=0.07)))
+    rng = np.random.default_rng(12)
+    t0 = float(ds["frame_t"][0]) - ds["time_offset_imu_to_cam_s"]
+    n = len(ds["imu_t"])
+    t = np.sort(rng.uniform(ds["imu_t"][0], ds["imu_t"][-1], size=n))
+    k = np.arange(0, n, 7)
+    t[k] = t0 + 0.04 * np.round((t[k] - t0) / 0.04)                     # on SO(3) knot boundaries (as exactly as a double allows)
+    k = np.arange(3, n, 11)
+    t[k] = t0 + 0.07 * np.round((t[k] - t0) / 0.07)                     # on R^3 knot boundaries
+    t = np.sort(t); t[5::13] = t[4::13][: len(t[5::13])]                # repeated stamps
+    t = np.sort(t)
+    ds["imu_t"] = t
+    g = gpu_factory(); capi.load_dataset(g, ds)
+    o = oracle_factory(); capi.load_dataset(o, ds)
+    assert g.num_residuals() == o.num_residuals()
+    for a, b in zip(g.imu_used(), o.imu_used()):
+        assert np.array_equal(a, b)
+    cg, rg, gg, _ = g.evaluate(F_STAGE1)
+    co, ro, go, _ = o.evaluate(F_STAGE1)
+    assert abs(cg - co) <= 1e-10 * co and rel(rg, ro) < 1e-9 and rel(gg, go) < 1e-9
+    perm = rng.permutation(n)
+    dsh = dict(ds); dsh["imu_t"], dsh["accel"], dsh["gyro"] = t[perm], ds["accel"][perm], ds["gyro"][perm]
+    s = gpu_factory(); capi.load_dataset(s, dsh)
+    cs = s.evaluate(F_STAGE1, residuals=False, gradient=False)[0]
+    assert s.num_residuals() == g.num_residuals() and abs(cs - cg) <= 1e-12 * cg

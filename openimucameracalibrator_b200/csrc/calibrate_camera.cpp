@@ -106,6 +106,15 @@ int main(int argc, char** argv) {
       std::ofstream g(out + ".calibdata");
       if (!g.is_open()) { std::cerr << "could not write " << out << ".calibdata" << std::endl; return 1; }
       g << iccjson::dump(ds, 1) << std::endl;
+      // theia::WritePlyFile(output_path + "_final_poses.ply", recon, camera colour (255, 0, 0), min 1 observation) (camera_calibrator.cc:381-384):
+      // the camera positions of the views that took part, then the board points.  (The reference also dumps "_ransac_poses.ply" before the
+      // calibration, :342-345; there is no RANSAC stage here -- the initial poses never leave the device.)
+      std::ofstream ply(out + "_final_poses.ply");
+      if (!ply.is_open()) { std::cerr << "could not write " << out << "_final_poses.ply" << std::endl; return 1; }
+      int n_cam = 0; for (int i = 0; i < nv; ++i) n_cam += used[i] ? 1 : 0;
+      ply << "ply\nformat ascii 1.0\nelement vertex " << n_cam + np << "\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n";
+      for (int i = 0; i < nv; ++i) if (used[i]) ply << p[3 * i] << " " << p[3 * i + 1] << " " << p[3 * i + 2] << " 255 0 0\n";
+      for (int i = 0; i < np; ++i) { const double w = board_out[4 * i + 3]; ply << board_out[4 * i] / w << " " << board_out[4 * i + 1] / w << " " << board_out[4 * i + 2] / w << " 255 255 255\n"; }
     }
     // CameraCalibrator::PrintResult (:391-458)
     std::cout << "Focal Length:" << intr[0] << "px Principal Point: " << cx << "/" << cy << "px.\n";

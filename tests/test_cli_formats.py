@@ -264,6 +264,9 @@ def test_calibrate_camera_cli_matches_api_and_feeds_the_pose_tool(tmp_path, gpu_
     got = np.array([cam["intrinsics"][n] for n in ("focal_length", "aspect_ratio", "principal_pt_x", "principal_pt_y", "xi", "alpha")])
     assert np.allclose(got, [kk[0], kk[1], kk[3], kk[4], kk[5], kk[6]], rtol=1e-9, atol=1e-12)
     assert abs(cam["final_reproj_error"] - r["summary"]["final_reproj_error"]) < 1e-9
+    ply = open(tmp_path / "cam_final_poses.ply").read().splitlines()      # theia::WritePlyFile of the reference (:381-384): cameras in red, then the board
+    assert ply[0] == "ply" and ply[2] == f"element vertex {40 + len(B)}" and ply[9] == "end_header" and len(ply) == 10 + 40 + len(B)
+    assert ply[10].endswith(" 255 0 0") and ply[-1].endswith(" 255 255 255")
     ds = json.load(open(tmp_path / "cam.calibdata"))
     assert len(ds["views"]) == 40 and len(ds["tracks"]) == B.shape[0]
     # the written calibration is what the downstream tools read: board poses with it reproduce the calibrated poses

@@ -12,6 +12,7 @@
 #include "icc_kernels.h"
 #include "icc_tile_common.cuh"
 #include "icc_vision_rows.cuh"
+#include "icc_points_math.cuh"
 
 namespace icc {
 
@@ -19,23 +20,12 @@ void count_launch();
 
 namespace {
 
-ICC_D void householder4(const double4 x, double (&v)[4], double& beta) {
-  const double sigma = x.x * x.x + x.y * x.y + x.z * x.z;
-  v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = 1.0; beta = 0.0;
-  if (sigma <= 2.220446049250313e-16) { if (x.w < 0.0) beta = 2.0; return; }
-  const double mu = sqrt(x.w * x.w + sigma);
-  const double vp = x.w <= 0.0 ? x.w - mu : -sigma / (x.w + mu);
-  beta = 2.0 * vp * vp / (sigma + vp * vp);
-  v[0] /= vp; v[1] /= vp; v[2] /= vp;
-}
-
-// de-homogenised point + local Jacobian (row-major 4 x 3) of one board point
+// de-homogenised point + local Jacobian (row-major 4 x 3) of one board point (icc_points_math.cuh)
 ICC_D void prepare_point(const double4 x, double4* board, double* jac12) {
-  const double iw = 1.0 / x.w;
-  *board = make_double4(x.x * iw, x.y * iw, x.z * iw, 1.0);      // hnormalized(T^-1 X_h) == T^-1 (X / w)   (residuals.h:357-362)
-  double v[4], beta; householder4(x, v, beta);
-  const double n = sqrt(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
-  for (int k = 0; k < 4; ++k) for (int i = 0; i < 3; ++i) jac12[3 * k + i] = n * (-0.5 * beta * v[i] * v[k] + (k == i ? 0.5 : 0.0));
+  const double xv[4] = {x.x, x.y, x.z, x.w};
+  double b4[4];
+  points_prepare(xv, b4, jac12);
+  *board = make_double4(b4[0], b4[1], b4[2], b4[3]);
 }
 
 __global__ void points_prepare_kernel(int n, const double4* __restrict__ pts, double4* board, double* jac) {
@@ -52,15 +42,10 @@ __global__ void points_update_kernel(int n, int col_pts, const double4* __restri
     double4 o = x;
     if (col_pts >= 0) {
       const double d0 = delta[col_pts + 3 * i], d1 = delta[col_pts + 3 * i + 1], d2 = delta[col_pts + 3 * i + 2];
-      const double nd = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-      if (nd != 0.0) {
-        const double hh = 0.5 * nd, sbd = sin(hh) / hh;
-        const double y[4] = {0.5 * sbd * d0, 0.5 * sbd * d1, 0.5 * sbd * d2, cos(hh)};
-        double v[4], beta; householder4(x, v, beta);
-        const double nx = sqrt(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
-        const double vy = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + v[3] * y[3];
-        o = make_double4(nx * (y[0] - v[0] * (beta * vy)), nx * (y[1] - v[1] * (beta * vy)), nx * (y[2] - v[2] * (beta * vy)), nx * (y[3] - v[3] * (beta * vy)));
-      }
+      const double xv[4] = {x.x, x.y, x.z, x.w}, dv[3] = {d0, d1, d2};
+      double ov[4];
+      points_plus(xv, dv, ov);
+      o = make_double4(ov[0], ov[1], ov[2], ov[3]);
       step = (o.x - x.x) * (o.x - x.x) + (o.y - x.y) * (o.y - x.y) + (o.z - x.z) * (o.z - x.z) + (o.w - x.w) * (o.w - x.w);
       xsq = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }

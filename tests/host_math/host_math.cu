@@ -7,6 +7,7 @@
 #include "../../openimucameracalibrator_b200/csrc/icc_imu_rows.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_rotinit_math.cuh"
 #include "../../openimucameracalibrator_b200/csrc/icc_small_linalg.cuh"
+#include "../../openimucameracalibrator_b200/csrc/icc_points_math.cuh"
 
 using namespace icc;
 
@@ -127,3 +128,7 @@ void hm_quat_from_columns(const double* R9 /* row-major */, double* q) {
   q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
 }
 }
+
+// ceres::HomogeneousVectorParameterization(4) of a board point exactly as icc_points.cu uses it (icc_points_math.cuh)
+extern "C" void hm_points_prepare(const double* x4, double* board4, double* jac12) { icc::points_prepare(x4, board4, jac12); }
+extern "C" void hm_points_plus(const double* x4, const double* d3, double* out4) { icc::points_plus(x4, d3, out4); }

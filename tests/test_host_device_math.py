@@ -20,7 +20,7 @@ DP = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hm():
-    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_vision_rows.cuh", "icc_imu_rows.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh")]
+    hdrs = [os.path.join(HERE, "..", "openimucameracalibrator_b200", "csrc", f) for f in ("icc_camera.cuh", "icc_device_math.cuh", "icc_spline_chain.cuh", "icc_vision_rows.cuh", "icc_imu_rows.cuh", "icc_rotinit_math.cuh", "icc_small_linalg.cuh", "icc_points_math.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in [SRC] + hdrs):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC])
@@ -421,3 +421,31 @@ def test_device_quaternion_from_rotation_matrix(hm):
         Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * s), 2 * (x * z + y * s)], [2 * (x * y + z * s), 1 - 2 * (x * x + z * z), 2 * (y * z - x * s)],
                        [2 * (x * z - y * s), 2 * (y * z + x * s), 1 - 2 * (x * x + y * y)]])
         assert abs(np.linalg.norm(q) - 1.0) < 1e-14 and np.abs(Rq - R).max() < 1e-12
+
+
+def test_device_homogeneous_point_parameterization(hm):
+    """ceres::HomogeneousVectorParameterization(4) as icc_points.cu uses it (icc_points_math.cuh): Plus against the NumPy statement of
+    tests/helpers.py (all branches of the Householder vector: w > 0, w <= 0, x on the w axis), Plus keeps |x|, Plus(x, 0) = x, the local
+    Jacobian against central differences of Plus, and the de-homogenised point."""
+    from helpers import plus_homog4
+    rng = np.random.default_rng(41)
+    xs = [rng.normal(0, 1, 4) * 10.0 ** rng.uniform(-2, 2) for _ in range(40)]
+    xs += [np.array([0.3, -0.2, 0.1, 1.0]), np.array([0.3, -0.2, 0.1, -1.0]), np.array([0.0, 0.0, 0.0, 2.0]), np.array([0.0, 0.0, 0.0, -2.0]), np.array([1e-9, 0.0, 0.0, 1.0])]
+    out, board, jac = np.zeros(4), np.zeros(4), np.zeros(12)
+    for x in xs:
+        x = np.ascontiguousarray(x)
+        for d in (rng.normal(0, 0.3, 3), rng.normal(0, 1e-6, 3), np.zeros(3), np.array([3.0, -2.0, 1.0])):
+            d = np.ascontiguousarray(d)
+            hm.hm_points_plus(x.ctypes.data_as(DP), d.ctypes.data_as(DP), out.ctypes.data_as(DP))
+            ref = plus_homog4(x, d)
+            assert np.abs(out - ref).max() <= 1e-14 * np.linalg.norm(x), (x, d, out, ref)
+            assert abs(np.linalg.norm(out) - np.linalg.norm(x)) <= 1e-14 * np.linalg.norm(x)
+        hm.hm_points_prepare(x.ctypes.data_as(DP), board.ctypes.data_as(DP), jac.ctypes.data_as(DP))
+        assert np.allclose(board, [x[0] / x[3], x[1] / x[3], x[2] / x[3], 1.0], rtol=1e-15, atol=0)
+        J = jac.reshape(4, 3); eps = 1e-6
+        for i in range(3):
+            e = np.zeros(3); e[i] = eps
+            fd = (plus_homog4(x, e) - plus_homog4(x, -e)) / (2 * eps)
+            assert np.abs(J[:, i] - fd).max() <= 1e-8 * np.linalg.norm(x), (x, i, J[:, i], fd)
+        if x[:3] @ x[:3] > np.finfo(float).eps:                                # (Ceres' own shortcut for x on the w axis takes H = I there)
+            assert np.abs(J.T @ x).max() <= 1e-14 * (x @ x)                   # the tangent columns are orthogonal to x

@@ -185,6 +185,11 @@ icc_status icc_get_mean_reprojection_error(icc_handle* h, double* err);
 /* number of IMU samples kept by BatchInitSpline and their (offset-corrected) timestamps / raw readings (app :265-327) */
 icc_status icc_get_num_imu_used(const icc_handle* h, int* n);
 icc_status icc_get_imu_used(const icc_handle* h, double* t_s, double* accel_xyz, double* gyro_xyz);
+/* Knot-interval cells of the kept IMU samples (inspection / tests): maximal runs [i_begin, i_end) of kept samples that lie in the same
+ * knot interval of all four splines, i.e. share CalcTimes' segment indices (impl.h:763-788); 6 int32 per cell:
+ * s_so3, s_r3, s_acc_bias, s_gyr_bias, i_begin, i_end.  The evaluation kernels stage one knot window per cell. */
+icc_status icc_get_num_imu_cells(const icc_handle* h, int* n);
+icc_status icc_get_imu_cells(const icc_handle* h, int32_t* cells6);
 /* GetAngularVelocity / GetAcceleration / GetGyroBias / GetAcclBias / GetPose evaluated on the GPU for n timestamps [ns];
  * valid[i] = 0 where CalcTimes rejects the timestamp (outputs left untouched there). Any output may be NULL. */
 icc_status icc_eval_trajectory(icc_handle* h, int n, const int64_t* t_ns, double* gyro_xyz, double* accel_xyz,

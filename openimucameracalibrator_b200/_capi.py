@@ -341,6 +341,13 @@ class CApi:
         self._call("get_imu_used", [c_double_p] * 3, _dp(t), _dp(a), _dp(g))
         return t, a, g
 
+    def imu_cells(self):
+        """Knot-interval cells of the kept IMU samples: rows (s_so3, s_r3, s_acc_bias, s_gyr_bias, i_begin, i_end)."""
+        n = C.c_int(); self._call("get_num_imu_cells", [C.POINTER(C.c_int)], C.byref(n))
+        c = np.zeros((n.value, 6), dtype=np.int32)
+        self._call("get_imu_cells", [c_int32_p], c.ctypes.data_as(c_int32_p))
+        return c
+
     def eval_trajectory(self, t_ns):
         t = np.ascontiguousarray(t_ns, dtype=np.int64); n = t.size
         out = dict(gyro=np.zeros((n, 3)), accel=np.zeros((n, 3)), gyro_bias=np.zeros((n, 3)), accel_bias=np.zeros((n, 3)),

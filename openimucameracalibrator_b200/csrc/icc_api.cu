@@ -890,7 +890,7 @@ icc_status icc_batch_init_spline(icc_handle* h, const icc_init_params* ipp) {
     h->imu_lazy = true; h->n_imu_used = kb - ka; h->imu_contig = kb > ka; h->imu_src0 = kb > ka ? (int)ka : 0;
   };
   auto imu_sorted_pass = [&]() -> bool {
-    if (h->shard_world != 1 || !h->imu_sorted || n_imu_in == 0) return false;
+    if (h->shard_world != 1 || !h->imu_sorted || n_imu_in == 0 || getenv("ICC_NO_BISECTION")) return false;   // (the switch forces the sample-by-sample pass: tests)
     const double* imu_t = h->imu_t.data(); const double toff = ipp->time_offset_imu_to_cam_s, t0 = h->t0_s, tend = h->tend_s;
     auto bisect = [&](size_t a, size_t b, auto pred) { while (a < b) { const size_t m = (a + b) / 2; if (pred(m)) a = m + 1; else b = m; } return a; };   // first index where pred is false
     auto fits = [&](size_t i) {   // upper-side validity of CalcTimes for all four splines (monotone: true, then false)
@@ -1257,6 +1257,12 @@ icc_status icc_get_mean_reprojection_error(icc_handle* h, double* e) {
   if (!h->initialised) return fail(h, ICC_ERR_STATE, "icc_batch_init_spline must be called first");
   CU(cudaSetDevice(h->device));
   return mean_reproj(h, e);
+}
+icc_status icc_get_num_imu_cells(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->cells.size(); return ICC_OK; }
+icc_status icc_get_imu_cells(const icc_handle* h, int32_t* c6) {
+  if (!h || !c6) return ICC_ERR_INVALID_ARGUMENT;
+  for (size_t k = 0; k < h->cells.size(); ++k) { const ImuCell& c = h->cells[k]; int32_t* o = c6 + 6 * k; o[0] = c.s_so3; o[1] = c.s_r3; o[2] = c.s_ba; o[3] = c.s_bg; o[4] = c.i_begin; o[5] = c.i_end; }
+  return ICC_OK;
 }
 icc_status icc_get_num_imu_used(const icc_handle* h, int* n) { if (!h || !n) return ICC_ERR_INVALID_ARGUMENT; *n = (int)h->n_imu_used; return ICC_OK; }
 icc_status icc_get_imu_used(const icc_handle* hc, double* t, double* a, double* g) {

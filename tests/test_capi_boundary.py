@@ -124,3 +124,31 @@ def test_host_assembly_general_paths_match_oracle(oracle_factory, case):
     for a, b in zip(o.get_knots(), h.get_knots()):
         assert np.allclose(a, b, rtol=0, atol=1e-15)
     assert np.allclose(o.get_gravity(), h.get_gravity(), rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("dts", [(0.05, 0.05), (0.04, 0.07), (0.09, 0.05)])
+def test_imu_cells_by_bisection_equal_the_sample_by_sample_pass(dts, monkeypatch):
+    """BatchInitSpline finds the knot-interval cells of a time-sorted IMU stream by galloping + bisection for the next interval boundary;
+    the sample-by-sample pass (forced with ICC_NO_BISECTION) is the reference statement: same cells, same kept samples -- for irregular
+    stamps, stamps exactly on knot boundaries of either spline and repeated stamps."""
+    ds = dict(syn.make_dataset(syn.tiny_config(n_frames=40, dt_so3_s=dts[0], dt_r3_s=dts[1])))
+    rng = np.random.default_rng(int(1000 * dts[0]))
+    t0 = float(ds["frame_t"][0]) - ds["time_offset_imu_to_cam_s"]
+    n = 4 * len(ds["imu_t"])
+    t = np.sort(rng.uniform(ds["imu_t"][0] - 0.2, ds["imu_t"][-1] + 0.2, size=n))
+    k = np.arange(0, n, 7); t[k] = t0 + dts[0] * np.round((t[k] - t0) / dts[0])
+    k = np.arange(3, n, 11); t[k] = t0 + dts[1] * np.round((t[k] - t0) / dts[1])
+    t = np.sort(t); t[5::13] = t[4::13][: len(t[5::13])]; t = np.sort(t)
+    ds["imu_t"] = t; ds["accel"] = rng.normal(size=(n, 3)); ds["gyro"] = rng.normal(size=(n, 3))
+    out = {}
+    for mode in ("bisection", "sequential"):
+        if mode == "sequential": monkeypatch.setenv("ICC_NO_BISECTION", "1")
+        else: monkeypatch.delenv("ICC_NO_BISECTION", raising=False)
+        h = capi.CApi(calibrator.load_library(), "icc_", -1); capi.load_dataset(h, ds, known_gravity=False)
+        out[mode] = (h.imu_cells(), h.imu_used(), h.num_residuals()); h.close()
+    cb, ub, rb = out["bisection"]; cs, us, rs = out["sequential"]
+    assert rb == rs and len(cb) > 10
+    assert np.array_equal(cb, cs)
+    for a, b in zip(ub, us):
+        assert np.array_equal(a, b)
+    assert cb[0, 4] == 0 and cb[-1, 5] == len(ub[0]) and np.array_equal(cb[1:, 4], cb[:-1, 5])     # the cells tile the kept samples
